@@ -1,0 +1,229 @@
+"""Deterministic synthetic rendered-marker frames.
+
+numpy only (no cv2), so the same frames can be produced on the GPU box.  Frame
+`f` of a batch uses `seed = base_seed + f`.  The reference has no test images
+(SURVEY section 4); these frames are the benchmark and parity inputs for the
+`detectMarkers` / `estimatePoseSingleMarkers` path of reference
+src/aruco_slam.cpp:313-314.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .dictionaries import Dictionary, getPredefinedDictionary
+
+_CELL = 24  # source pixels per marker cell
+
+
+@dataclass
+class Frame:
+    image: np.ndarray                 # (H, W) uint8 gray
+    ids: np.ndarray                   # (n,) int32 ground-truth marker ids
+    corners: np.ndarray               # (n, 4, 2) float64 ground-truth corners (TL,TR,BR,BL)
+    meta: dict = field(default_factory=dict)
+
+
+def _homography(src: np.ndarray, dst: np.ndarray) -> np.ndarray:
+    """3x3 H with dst ~ H src, from 4 point pairs."""
+    A = np.zeros((8, 8))
+    b = np.zeros(8)
+    for i in range(4):
+        x, y = src[i]
+        u, v = dst[i]
+        A[2 * i] = [x, y, 1, 0, 0, 0, -u * x, -u * y]
+        A[2 * i + 1] = [0, 0, 0, x, y, 1, -v * x, -v * y]
+        b[2 * i], b[2 * i + 1] = u, v
+    h = np.linalg.solve(A, b)
+    return np.append(h, 1.0).reshape(3, 3)
+
+
+def _gauss_blur(img: np.ndarray, sigma: float) -> np.ndarray:
+    r = int(np.ceil(3 * sigma))
+    x = np.arange(-r, r + 1, dtype=np.float64)
+    k = np.exp(-0.5 * (x / sigma) ** 2)
+    k /= k.sum()
+    out = img.astype(np.float64)
+    for axis in (0, 1):
+        pad = [(0, 0), (0, 0)]
+        pad[axis] = (r, r)
+        p = np.pad(out, pad, mode="reflect")
+        acc = np.zeros_like(out)
+        for i in range(2 * r + 1):
+            sl = [slice(None), slice(None)]
+            sl[axis] = slice(i, i + out.shape[axis])
+            acc += k[i] * p[tuple(sl)]
+        out = acc
+    return out
+
+
+def background(W: int, H: int) -> np.ndarray:
+    x = np.arange(W, dtype=np.float64)[None, :]
+    y = np.arange(H, dtype=np.float64)[:, None]
+    return 110.0 + 30.0 * np.sin(x / 97.0) * np.cos(y / 71.0)
+
+
+def paste_marker(img: np.ndarray, dic: Dictionary, marker_id: int, quad: np.ndarray,
+                 quiet: float = 0.2) -> None:
+    """Warp marker `marker_id` (plus a white quiet zone of `quiet`*side) so that
+    its four outer corners land on `quad` (TL,TR,BR,BL; pixel-centre coords)."""
+    H, W = img.shape
+    m = dic.marker_image(marker_id, _CELL)
+    M = m.shape[0]
+    q = int(round(quiet * M))
+    src = np.full((M + 2 * q, M + 2 * q), 255, np.uint8)
+    src[q:q + M, q:q + M] = m
+    S = src.shape[0]
+    # continuous coords: source pixel i covers [i-0.5, i+0.5]
+    c0, c1 = q - 0.5, q + M - 0.5
+    src_c = np.array([[c0, c0], [c1, c0], [c1, c1], [c0, c1]])
+    Hm = _homography(src_c, quad)            # src -> dst
+    Hi = np.linalg.inv(Hm)
+    ext = np.array([[-0.5, -0.5], [S - 0.5, -0.5], [S - 0.5, S - 0.5], [-0.5, S - 0.5]])
+    e = np.c_[ext, np.ones(4)] @ Hm.T
+    e = e[:, :2] / e[:, 2:3]
+    x0 = max(int(np.floor(e[:, 0].min())), 0)
+    x1 = min(int(np.ceil(e[:, 0].max())) + 1, W)
+    y0 = max(int(np.floor(e[:, 1].min())), 0)
+    y1 = min(int(np.ceil(e[:, 1].max())) + 1, H)
+    if x1 <= x0 or y1 <= y0:
+        return
+    xs, ys = np.meshgrid(np.arange(x0, x1, dtype=np.float64), np.arange(y0, y1, dtype=np.float64))
+    w = Hi[2, 0] * xs + Hi[2, 1] * ys + Hi[2, 2]
+    u = (Hi[0, 0] * xs + Hi[0, 1] * ys + Hi[0, 2]) / w
+    v = (Hi[1, 0] * xs + Hi[1, 1] * ys + Hi[1, 2]) / w
+    inside = (u >= -0.5) & (u <= S - 0.5) & (v >= -0.5) & (v <= S - 0.5)
+    uc = np.clip(u, 0, S - 1)
+    vc = np.clip(v, 0, S - 1)
+    u0 = np.floor(uc).astype(np.int64)
+    v0 = np.floor(vc).astype(np.int64)
+    u1 = np.minimum(u0 + 1, S - 1)
+    v1 = np.minimum(v0 + 1, S - 1)
+    fu = uc - u0
+    fv = vc - v0
+    sf = src.astype(np.float64)
+    val = (sf[v0, u0] * (1 - fu) * (1 - fv) + sf[v0, u1] * fu * (1 - fv)
+           + sf[v1, u0] * (1 - fu) * fv + sf[v1, u1] * fu * fv)
+    roi = img[y0:y1, x0:x1]
+    roi[inside] = val[inside]
+
+
+def render_frame(W: int, H: int, n_markers: int, dict_id: int, seed: int,
+                 noise_sigma: float = 0.0, blur_sigma: float = 0.0,
+                 side_range=(60.0, 160.0), jitter: float = 0.12) -> Frame:
+    dic = getPredefinedDictionary(dict_id)
+    rng = np.random.default_rng(seed)
+    img = background(W, H)
+    ids = rng.choice(dic.n_markers, size=min(n_markers, dic.n_markers), replace=False)
+    placed = []          # (cx, cy, side)
+    out_ids, out_corners = [], []
+    for mid in ids:
+        s = rng.uniform(*side_range)
+        rad = 0.9 * s
+        ok = False
+        for _ in range(1000):
+            cx = rng.uniform(rad, W - rad) if W > 2 * rad else W / 2
+            cy = rng.uniform(rad, H - rad) if H > 2 * rad else H / 2
+            if all((cx - px) ** 2 + (cy - py) ** 2 > (0.8 * (s + ps)) ** 2 for px, py, ps in placed):
+                ok = True
+                break
+        if not ok:
+            continue
+        th = rng.uniform(0, 2 * np.pi)
+        base = np.array([[-0.5, -0.5], [0.5, -0.5], [0.5, 0.5], [-0.5, 0.5]]) * s
+        R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        quad = base @ R.T + np.array([cx, cy]) + rng.uniform(-jitter, jitter, (4, 2)) * s
+        paste_marker(img, dic, int(mid), quad)
+        placed.append((cx, cy, s))
+        out_ids.append(int(mid))
+        out_corners.append(quad)
+    if blur_sigma > 0:
+        img = _gauss_blur(img, blur_sigma)
+    if noise_sigma > 0:
+        img = img + rng.normal(0.0, noise_sigma, img.shape)
+    u8 = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return Frame(u8, np.array(out_ids, np.int32), np.array(out_corners, np.float64).reshape(-1, 4, 2),
+                 dict(W=W, H=H, dict_id=dict_id, seed=seed, noise_sigma=noise_sigma, blur_sigma=blur_sigma))
+
+
+# BASELINE.json configs: name -> kwargs
+CONFIGS = {
+    "C1": dict(W=640, H=480, n_markers=4, dict_id=0, side_range=(50.0, 90.0)),
+    "C2": dict(W=1920, H=1080, n_markers=30, dict_id=10, side_range=(60.0, 160.0)),
+    "C3": dict(W=3840, H=2160, n_markers=100, dict_id=10, side_range=(80.0, 220.0),
+               noise_sigma=4.0, blur_sigma=1.0),
+}
+
+
+def render_config(name: str, seed: int) -> Frame:
+    return render_frame(seed=seed, **CONFIGS[name])
+
+
+def render_batch(name: str, batch: int, base_seed: int = 0) -> np.ndarray:
+    """(batch, H, W) uint8 frames with seeds base_seed .. base_seed+batch-1."""
+    return np.stack([render_config(name, base_seed + f).image for f in range(batch)])
+
+
+def gray_to_bgr(gray: np.ndarray, seed: int = 0) -> np.ndarray:
+    """A colour frame whose channels differ (exercises the BGR->gray ingest,
+    reference src/aruco_slam_node.cpp:93 delivers bgr8)."""
+    rng = np.random.default_rng(seed)
+    d = rng.integers(-6, 7, size=gray.shape + (3,))
+    return np.clip(gray[..., None].astype(np.int64) + d, 0, 255).astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------
+# 3-D scenes (config C4 style): markers on planes, pinhole + Brown distortion
+# ----------------------------------------------------------------------------
+
+def rodrigues(r: np.ndarray) -> np.ndarray:
+    th = float(np.linalg.norm(r))
+    if th < 1e-12:
+        return np.eye(3)
+    k = r / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+
+
+def project(obj: np.ndarray, rvec, tvec, K: np.ndarray, D: np.ndarray) -> np.ndarray:
+    """Pinhole + (k1,k2,p1,p2,k3) projection of (n,3) points."""
+    P = obj @ rodrigues(np.asarray(rvec, float)).T + np.asarray(tvec, float)
+    x = P[:, 0] / P[:, 2]
+    y = P[:, 1] / P[:, 2]
+    k1, k2, p1, p2, k3 = (list(D) + [0] * 5)[:5]
+    r2 = x * x + y * y
+    rad = 1 + k1 * r2 + k2 * r2 ** 2 + k3 * r2 ** 3
+    xd = x * rad + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
+    yd = y * rad + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
+    return np.stack([K[0, 0] * xd + K[0, 2], K[1, 1] * yd + K[1, 2]], axis=1)
+
+
+def marker_object_points(L: float) -> np.ndarray:
+    """estimatePoseSingleMarkers object points (reference aruco_slam.h:189)."""
+    h = L / 2.0
+    return np.array([[-h, h, 0], [h, h, 0], [h, -h, 0], [-h, -h, 0]], float)
+
+
+def render_scene(W: int, H: int, dict_id: int, K: np.ndarray, D: np.ndarray, marker_length: float,
+                 poses, seed: int = 0, noise_sigma: float = 0.0, blur_sigma: float = 0.0) -> Frame:
+    """Render markers given as [(id, rvec, tvec)] camera-frame poses; the corner
+    positions are the projected object points, the interior is warped by the
+    homography through them (exact for D=0, first-order otherwise)."""
+    dic = getPredefinedDictionary(dict_id)
+    rng = np.random.default_rng(seed)
+    img = background(W, H)
+    obj = marker_object_points(marker_length)
+    ids, cs = [], []
+    for mid, rvec, tvec in poses:
+        quad = project(obj, rvec, tvec, K, D)
+        paste_marker(img, dic, int(mid), quad)
+        ids.append(int(mid))
+        cs.append(quad)
+    if blur_sigma > 0:
+        img = _gauss_blur(img, blur_sigma)
+    if noise_sigma > 0:
+        img = img + rng.normal(0.0, noise_sigma, img.shape)
+    u8 = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return Frame(u8, np.array(ids, np.int32), np.array(cs, float).reshape(-1, 4, 2),
+                 dict(W=W, H=H, dict_id=dict_id, seed=seed))
