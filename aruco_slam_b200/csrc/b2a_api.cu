@@ -1,0 +1,842 @@
+// b2a_api.cu -- the C ABI of include/b2aruco.h: handles, device memory, stream, launch order.
+// Everything that computes is a kernel in detect_kernels.cuh / ekf_kernels.cuh or the pose
+// kernel below; this file only orchestrates.  No CPU fallback: without a CUDA device the
+// create calls fail.
+#include "../../include/b2aruco.h"
+#include "detect_kernels.cuh"
+#include "ekf_kernels.cuh"
+#include "pose_core.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace b2a;
+
+static thread_local std::string g_err;
+static int set_err(int code, const std::string &msg) { g_err = msg; return code; }
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return set_err(B2A_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));      \
+    } while (0)
+
+extern "C" const char *b2a_last_error(void) { return g_err.c_str(); }
+extern "C" const char *b2a_version(void) { return "b2aruco 0.1 (sm_100a)"; }
+
+extern "C" void b2a_default_detector_params(b2a_detector_params *p)
+{
+    p->adaptiveThreshWinSizeMin = 3; p->adaptiveThreshWinSizeMax = 23; p->adaptiveThreshWinSizeStep = 10;
+    p->adaptiveThreshConstant = 7.0;
+    p->minMarkerPerimeterRate = 0.03; p->maxMarkerPerimeterRate = 4.0;
+    p->polygonalApproxAccuracyRate = 0.03; p->minCornerDistanceRate = 0.05;
+    p->minDistanceToBorder = 3; p->minMarkerDistanceRate = 0.125; p->minGroupDistance = 0.21f;
+    p->markerBorderBits = 1; p->perspectiveRemovePixelPerCell = 4; p->perspectiveRemoveIgnoredMarginPerCell = 0.13;
+    p->maxErroneousBitsInBorderRate = 0.35; p->minOtsuStdDev = 5.0; p->errorCorrectionRate = 0.6;
+    p->cornerRefinementMethod = 0; p->cornerRefinementWinSize = 5; p->relativeCornerRefinmentWinSize = 0.3;
+    p->cornerRefinementMaxIterations = 30; p->cornerRefinementMinAccuracy = 0.1; p->detectInvertedMarker = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// predefined dictionaries (tables generated from data/dict_tables.inc)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Family { const char *name; int markerSize, nMarkers, nBytes; const char *hex; };
+struct Predef { int id; const char *name; const char *family; int nMarkers, maxCorr; };
+#define B2A_DICT_FAMILY(name, ms, n, nb, hex) {#name, ms, n, nb, hex},
+#define B2A_DICT_PREDEFINED(id, name, fam, n, mc)
+static const Family k_families[] = {
+#include "../data/dict_tables.inc"
+};
+#undef B2A_DICT_FAMILY
+#undef B2A_DICT_PREDEFINED
+#define B2A_DICT_FAMILY(name, ms, n, nb, hex)
+#define B2A_DICT_PREDEFINED(id, name, fam, n, mc) {id, #name, #fam, n, mc},
+static const Predef k_predef[] = {
+#include "../data/dict_tables.inc"
+};
+#undef B2A_DICT_FAMILY
+#undef B2A_DICT_PREDEFINED
+
+static int hexval(char c) { return c <= '9' ? c - '0' : c - 'a' + 10; }
+
+// rotation r = bit matrix rotated counter-clockwise r times (np.rot90(bits, r))
+static std::vector<uint8_t> build_table(const Family &f, int n)
+{
+    const int ms = f.markerSize, nb = f.nBytes, nbits = ms * ms;
+    std::vector<uint8_t> t((size_t)n * 4 * nb, 0);
+    std::vector<uint8_t> bits(nbits), rot(nbits);
+    auto shift_of = [&](int i) { const int byte = i / 8; return (byte == nb - 1 && (nbits % 8)) ? (nbits % 8) - 1 - (i % 8) : 7 - (i % 8); };
+    for (int m = 0; m < n; ++m) {
+        for (int i = 0; i < nbits; ++i) {
+            const int byte = i / 8;
+            const int v = hexval(f.hex[((size_t)m * nb + byte) * 2]) * 16 + hexval(f.hex[((size_t)m * nb + byte) * 2 + 1]);
+            bits[i] = (v >> shift_of(i)) & 1;
+        }
+        for (int r = 0; r < 4; ++r) {
+            uint8_t *o = &t[((size_t)m * 4 + r) * nb];
+            for (int i = 0; i < nbits; ++i) o[i / 8] |= (uint8_t)(bits[i] << shift_of(i));
+            // rot90 ccw: out[y][x] = in[x][ms-1-y]
+            for (int y = 0; y < ms; ++y) for (int x = 0; x < ms; ++x) rot[y * ms + x] = bits[x * ms + (ms - 1 - y)];
+            bits = rot;
+        }
+    }
+    return t;
+}
+static std::map<int, std::vector<uint8_t>> &table_cache() { static std::map<int, std::vector<uint8_t>> c; return c; }
+}  // namespace
+
+extern "C" int b2a_get_predefined_dictionary(int dict_id, b2a_dictionary *out)
+{
+    if (!out) return set_err(B2A_ERR_INVALID, "null output");
+    for (const Predef &p : k_predef) {
+        if (p.id != dict_id) continue;
+        for (const Family &f : k_families) {
+            if (std::strcmp(f.name, p.family)) continue;
+            auto &cache = table_cache();
+            auto it = cache.find(dict_id);
+            if (it == cache.end()) it = cache.emplace(dict_id, build_table(f, p.nMarkers)).first;
+            out->markerSize = f.markerSize; out->maxCorrectionBits = p.maxCorr; out->nMarkers = p.nMarkers;
+            out->nBytes = f.nBytes; out->table = it->second.data();
+            return B2A_OK;
+        }
+    }
+    return set_err(B2A_ERR_INVALID, "unknown predefined dictionary id");
+}
+
+// ------------------------------------------------------------------------------------------------
+// pose / observation kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pose(const float *__restrict__ corners, const int32_t *__restrict__ n_acc, int B, int max_markers,
+                       Camera cam, float marker_length, double *__restrict__ rvecs, double *__restrict__ tvecs)
+{
+    const int total = B * max_markers;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int f = t / max_markers, m = t - f * max_markers;
+        if (n_acc && m >= n_acc[f]) continue;
+        solve_marker_pose(cam, marker_length, corners + (size_t)t * 8, rvecs + (size_t)t * 3, tvecs + (size_t)t * 3);
+    }
+}
+
+__global__ void k_observations(const float *__restrict__ corners, const int32_t *__restrict__ ids, const double *__restrict__ rvecs,
+                               const double *__restrict__ tvecs, int n, Camera cam, ObsParams op, Observation *__restrict__ out,
+                               int *__restrict__ keep)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        keep[i] = make_observation(cam, op, corners + (size_t)i * 8, ids[i], rvecs + (size_t)i * 3, tvecs + (size_t)i * 3, out[i]) ? 1 : 0;
+}
+
+static Camera to_camera(const b2a_camera *c)
+{
+    Camera cam;
+    cam.fx = c->K[0]; cam.fy = c->K[4]; cam.cx = c->K[2]; cam.cy = c->K[5];
+    double D[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < c->nD && i < 5; ++i) D[i] = c->D[i];
+    cam.k1 = D[0]; cam.k2 = D[1]; cam.p1 = D[2]; cam.p2 = D[3]; cam.k3 = D[4];
+    return cam;
+}
+
+// ------------------------------------------------------------------------------------------------
+// detector handle
+// ------------------------------------------------------------------------------------------------
+enum { ST_H2D, ST_GRAY, ST_THRESH, ST_STARTS, ST_WALK, ST_SORT, ST_WRITE, ST_APPROX, ST_GROUP, ST_IDENT, ST_FINAL, ST_POSE, ST_D2H, ST_COUNT };
+static const char *k_stage_names[ST_COUNT] = {"h2d", "bgr2gray", "threshold", "starts", "walk_count", "sort_scan", "walk_write",
+                                              "approx", "group", "identify", "finalize", "pose", "d2h"};
+
+struct b2a_detector {
+    b2a_detector_config cfg;
+    b2a_detector_params prm;
+    b2a_dictionary dict;
+    std::vector<uint8_t> dict_bytes;
+    int device = 0, num_sms = 148;
+    cudaStream_t stream = nullptr;
+    int nScales = 0, radius[MAX_SCALES];
+    int max_cand = 0, max_markers = 0, surv_cap = 0;
+    size_t gray_pitch = 0;
+    // device memory
+    uint8_t *d_in = nullptr, *d_gray = nullptr;
+    uint32_t *d_masks = nullptr; size_t masks_words = 0;
+    uint2 *d_starts = nullptr; unsigned starts_cap = 0;
+    int *d_counters = nullptr;               // [0] n_starts (unsigned), then per-(f,s) arrays
+    int *d_surv_count = nullptr, *d_contour_count = nullptr, *d_iso_count = nullptr, *d_status = nullptr;
+    uint4 *d_surv = nullptr, *d_sorted = nullptr;
+    int *d_pts_off = nullptr; uint32_t *d_pts = nullptr; int pts_cap = 0;
+    uint8_t *d_quad_ok = nullptr; int32_t *d_quad_xy = nullptr, *d_quad_len = nullptr;
+    unsigned long long *d_dict = nullptr;
+    FrameScratch fs0{};                       // frame-0 pointers
+    FrameOutputs fo0{};
+    float *d_corners2 = nullptr;              // subpix output
+    double *d_rvecs = nullptr, *d_tvecs = nullptr;
+    // pinned host mirrors of the outputs
+    int32_t *h_nacc = nullptr, *h_nrej = nullptr, *h_ids = nullptr, *h_status = nullptr;
+    float *h_corners = nullptr, *h_rejected = nullptr;
+    double *h_rvecs = nullptr, *h_tvecs = nullptr;
+    // geometry of the last call (mask padding must be re-zeroed when it changes)
+    int lastW = -1, lastH = -1, lastB = -1;
+    // timing
+    cudaEvent_t ev[ST_COUNT + 1];
+    bool ev_used[ST_COUNT + 1];
+    float stage_ms[ST_COUNT];
+    int launches = 0;
+    std::vector<void *> allocs, pinned;
+};
+
+template <class T>
+static int dev_alloc(b2a_detector *d, T **p, size_t count)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return set_err(B2A_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    d->allocs.push_back(q);
+    *p = (T *)q;
+    return B2A_OK;
+}
+template <class T>
+static int pin_alloc(b2a_detector *d, T **p, size_t count)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMallocHost(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return set_err(B2A_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    d->pinned.push_back(q);
+    *p = (T *)q;
+    return B2A_OK;
+}
+#define TRY(x) do { int rc__ = (x); if (rc__ != B2A_OK) return rc__; } while (0)
+
+extern "C" void b2a_detector_destroy(b2a_detector *d)
+{
+    if (!d) return;
+    cudaSetDevice(d->device);
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    for (void *p : d->allocs) cudaFree(p);
+    for (void *p : d->pinned) cudaFreeHost(p);
+    for (int i = 0; i <= ST_COUNT; ++i) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+static int create_impl(b2a_detector *d)
+{
+    const b2a_detector_config &c = d->cfg;
+    const b2a_detector_params &p = d->prm;
+    CU(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, c.device));
+    d->num_sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    for (int i = 0; i <= ST_COUNT; ++i) CU(cudaEventCreate(&d->ev[i]));
+    const int B = c.max_batch, W = c.max_width, H = c.max_height, nS = d->nScales;
+    const size_t P = (size_t)W * H;
+    d->gray_pitch = ((size_t)W + 15) & ~(size_t)15;
+    TRY(dev_alloc(d, &d->d_in, (size_t)B * P * 3));
+    TRY(dev_alloc(d, &d->d_gray, (size_t)B * d->gray_pitch * H));
+    const int WW = (W + 31) / 32, PWW = WW + 2;
+    d->masks_words = (size_t)B * nS * PWW * (H + 2);
+    TRY(dev_alloc(d, &d->d_masks, d->masks_words));
+    d->starts_cap = (unsigned)std::min<size_t>(std::max<size_t>((size_t)B * nS * (P / 8), 1u << 20), 0x7FFFFFFFu);
+    TRY(dev_alloc(d, &d->d_starts, d->starts_cap));
+    const size_t FS = (size_t)B * nS;
+    TRY(dev_alloc(d, &d->d_counters, 4 + 3 * FS + B));
+    d->d_surv_count = d->d_counters + 4; d->d_contour_count = d->d_surv_count + FS; d->d_iso_count = d->d_contour_count + FS;
+    d->d_status = d->d_iso_count + FS;
+    TRY(dev_alloc(d, &d->d_surv, FS * d->surv_cap));
+    TRY(dev_alloc(d, &d->d_sorted, FS * d->surv_cap));
+    TRY(dev_alloc(d, &d->d_pts_off, FS * d->surv_cap));
+    d->pts_cap = (int)std::max<size_t>(P / 4, 1 << 16);
+    TRY(dev_alloc(d, &d->d_pts, FS * (size_t)d->pts_cap));
+    TRY(dev_alloc(d, &d->d_quad_ok, FS * d->surv_cap));
+    TRY(dev_alloc(d, &d->d_quad_xy, FS * d->surv_cap * 8));
+    TRY(dev_alloc(d, &d->d_quad_len, FS * d->surv_cap));
+    // dictionary: one u64 per (marker, rotation), byte k in bits 8k..8k+7
+    {
+        std::vector<unsigned long long> packed((size_t)d->dict.nMarkers * 4, 0);
+        for (int m = 0; m < d->dict.nMarkers; ++m) for (int r = 0; r < 4; ++r) {
+            unsigned long long v = 0;
+            for (int k = 0; k < d->dict.nBytes; ++k) v |= (unsigned long long)d->dict_bytes[((size_t)m * 4 + r) * d->dict.nBytes + k] << (8 * k);
+            packed[(size_t)m * 4 + r] = v;
+        }
+        TRY(dev_alloc(d, &d->d_dict, packed.size()));
+        CU(cudaMemcpy(d->d_dict, packed.data(), packed.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
+    const size_t MC = d->max_cand, BM = (size_t)B * MC;
+    FrameScratch &fs = d->fs0;
+    TRY(dev_alloc(d, &fs.cq, BM * 8)); TRY(dev_alloc(d, &fs.clen, BM)); TRY(dev_alloc(d, &fs.tq, BM * 8)); TRY(dev_alloc(d, &fs.tper, BM));
+    TRY(dev_alloc(d, &fs.gid, BM)); TRY(dev_alloc(d, &fs.sel, BM)); TRY(dev_alloc(d, &fs.gstart, (size_t)B * (MC + 1))); TRY(dev_alloc(d, &fs.gfill, BM));
+    TRY(dev_alloc(d, &fs.members, BM)); TRY(dev_alloc(d, &fs.closeIdx, BM)); TRY(dev_alloc(d, &fs.closeCnt, BM));
+    TRY(dev_alloc(d, &fs.S, BM)); TRY(dev_alloc(d, &fs.parent, BM)); TRY(dev_alloc(d, &fs.depth, BM)); TRY(dev_alloc(d, &fs.selGroup, BM));
+    TRY(dev_alloc(d, &fs.closeM, BM * ((MC + 31) / 32)));
+    TRY(dev_alloc(d, &fs.wq, BM * 8)); TRY(dev_alloc(d, &fs.wres, BM)); TRY(dev_alloc(d, &fs.closeStart, BM)); TRY(dev_alloc(d, &fs.closeNum, BM));
+    TRY(dev_alloc(d, &fs.counters, (size_t)B * 8));
+    const size_t BK = (size_t)B * d->max_markers;
+    FrameOutputs &fo = d->fo0;
+    TRY(dev_alloc(d, &fo.n_accepted, B)); TRY(dev_alloc(d, &fo.n_rejected, B)); TRY(dev_alloc(d, &fo.status, B));
+    TRY(dev_alloc(d, &fo.corners, BK * 8)); TRY(dev_alloc(d, &fo.ids, BK)); TRY(dev_alloc(d, &fo.rejected, BK * 8));
+    TRY(dev_alloc(d, &d->d_corners2, BK * 8));
+    TRY(dev_alloc(d, &d->d_rvecs, BK * 3)); TRY(dev_alloc(d, &d->d_tvecs, BK * 3));
+    TRY(pin_alloc(d, &d->h_nacc, B)); TRY(pin_alloc(d, &d->h_nrej, B)); TRY(pin_alloc(d, &d->h_status, B));
+    TRY(pin_alloc(d, &d->h_corners, BK * 8)); TRY(pin_alloc(d, &d->h_ids, BK)); TRY(pin_alloc(d, &d->h_rejected, BK * 8));
+    TRY(pin_alloc(d, &d->h_rvecs, BK * 3)); TRY(pin_alloc(d, &d->h_tvecs, BK * 3));
+    CU(cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CU(cudaStreamSynchronize(d->stream));
+    return B2A_OK;
+}
+
+extern "C" int b2a_detector_create(const b2a_detector_config *cfg, const b2a_dictionary *dict, const b2a_detector_params *params, b2a_detector **out)
+{
+    if (!cfg || !dict || !out || !dict->table) return set_err(B2A_ERR_INVALID, "null argument");
+    if (cfg->max_width <= 0 || cfg->max_height <= 0 || cfg->max_batch <= 0) return set_err(B2A_ERR_INVALID, "bad geometry");
+    if (cfg->max_width > 32767 || cfg->max_height > 32767) return set_err(B2A_ERR_UNSUPPORTED, "frame larger than 32767");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return set_err(B2A_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return set_err(B2A_ERR_INVALID, "bad device ordinal");
+    b2a_detector_params prm;
+    if (params) prm = *params; else b2a_default_detector_params(&prm);
+    if (prm.detectInvertedMarker) return set_err(B2A_ERR_UNSUPPORTED, "detectInvertedMarker");
+    if (prm.markerBorderBits < 1) return set_err(B2A_ERR_INVALID, "markerBorderBits < 1");
+    if (prm.adaptiveThreshWinSizeMin < 3 || prm.adaptiveThreshWinSizeMax < prm.adaptiveThreshWinSizeMin || prm.adaptiveThreshWinSizeStep <= 0)
+        return set_err(B2A_ERR_INVALID, "adaptiveThreshWinSize*");
+    if (dict->markerSize < 1 || dict->markerSize * dict->markerSize > 64 || dict->nBytes != (dict->markerSize * dict->markerSize + 7) / 8)
+        return set_err(B2A_ERR_UNSUPPORTED, "marker size (up to 8x8)");
+    b2a_detector *d = new b2a_detector();
+    std::memset(d->ev, 0, sizeof(d->ev));
+    d->cfg = *cfg; d->prm = prm; d->device = cfg->device;
+    d->dict = *dict;
+    d->dict_bytes.assign(dict->table, dict->table + (size_t)dict->nMarkers * 4 * dict->nBytes);
+    d->dict.table = d->dict_bytes.data();
+    d->nScales = (prm.adaptiveThreshWinSizeMax - prm.adaptiveThreshWinSizeMin) / prm.adaptiveThreshWinSizeStep + 1;
+    if (d->nScales > MAX_SCALES) { delete d; return set_err(B2A_ERR_UNSUPPORTED, "more than 8 threshold scales"); }
+    for (int i = 0; i < d->nScales; ++i) {
+        int k = prm.adaptiveThreshWinSizeMin + i * prm.adaptiveThreshWinSizeStep;
+        if (k % 2 == 0) k++;                                   // OpenCV bumps even window sizes to the next odd
+        d->radius[i] = k / 2;
+        if (d->radius[i] > R_MAX) { delete d; return set_err(B2A_ERR_UNSUPPORTED, "threshold window larger than 31"); }
+    }
+    const int S = (dict->markerSize + 2 * prm.markerBorderBits) * prm.perspectiveRemovePixelPerCell;
+    if (S > ID_MAX_S || dict->markerSize + 2 * prm.markerBorderBits > 9) { delete d; return set_err(B2A_ERR_UNSUPPORTED, "warped marker image larger than 72 px"); }
+    d->max_markers = cfg->max_markers > 0 ? cfg->max_markers : 256;
+    d->max_cand = cfg->max_candidates > 0 ? cfg->max_candidates : 2048;
+    d->max_cand = (d->max_cand + 31) & ~31;
+    d->surv_cap = SORT_CAP;
+    int rc = create_impl(d);
+    if (rc != B2A_OK) { std::string keep = g_err; b2a_detector_destroy(d); g_err = keep; return rc; }
+    *out = d;
+    return B2A_OK;
+}
+
+extern "C" int b2a_detector_num_scales(const b2a_detector *d) { return d ? d->nScales : 0; }
+extern "C" void *b2a_detector_stream(const b2a_detector *d) { return d ? (void *)d->stream : nullptr; }
+extern "C" int b2a_last_launch_count(const b2a_detector *d) { return d ? d->launches : 0; }
+extern "C" int b2a_last_stage_times(const b2a_detector *d, const char **names, float *ms, int cap)
+{
+    if (!d) return 0;
+    int n = 0;
+    for (int i = 0; i < ST_COUNT && n < cap; ++i) { if (names) names[n] = k_stage_names[i]; if (ms) ms[n] = d->stage_ms[i]; ++n; }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the pipeline
+// ------------------------------------------------------------------------------------------------
+struct RunCtx {
+    DetGeom g;
+    const uint8_t *gray; size_t pitch, frame_stride;
+};
+
+static int check_frames(b2a_detector *d, const b2a_frames *f)
+{
+    if (!d || !f || !f->data) return set_err(B2A_ERR_INVALID, "null argument");
+    if (f->batch <= 0 || f->batch > d->cfg.max_batch) return set_err(B2A_ERR_INVALID, "batch outside [1, max_batch]");
+    if (f->width <= 0 || f->height <= 0 || f->width > d->cfg.max_width || f->height > d->cfg.max_height || (size_t)f->width * f->height > (size_t)d->cfg.max_width * d->cfg.max_height)
+        return set_err(B2A_ERR_INVALID, "frame size outside the handle's maximum");
+    if (f->channels != 1 && f->channels != 3) return set_err(B2A_ERR_INVALID, "channels must be 1 or 3");
+    if (f->row_stride && f->row_stride < (size_t)f->width * f->channels) return set_err(B2A_ERR_INVALID, "row_stride too small");
+    return B2A_OK;
+}
+
+static void stage_mark(b2a_detector *d, int st) { cudaEventRecord(d->ev[st], d->stream); d->ev_used[st] = true; }
+
+static int launch_err(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_err(B2A_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return B2A_OK;
+}
+
+// ingest + A1 + A2 + A3: everything up to the quads of every (frame, scale)
+static int run_front(b2a_detector *d, const b2a_frames *f, RunCtx &rc, int walk_max_len /* 0 = maxPerimeter */)
+{
+    TRY(check_frames(d, f));
+    CU(cudaSetDevice(d->device));
+    const int B = f->batch, W = f->width, H = f->height;
+    const size_t in_pitch = f->row_stride ? f->row_stride : (size_t)W * f->channels;
+    const size_t in_frame = f->frame_stride ? f->frame_stride : in_pitch * H;
+    std::memset(d->ev_used, 0, sizeof(d->ev_used));
+    d->launches = 0;
+    cudaStream_t st = d->stream;
+    stage_mark(d, ST_H2D);
+    const uint8_t *src = f->data;
+    size_t src_pitch = in_pitch, src_frame = in_frame;
+    if (!f->on_device) {
+        // one 2-D copy: rows of all frames (frame_stride must be a multiple of row_stride for that), else per frame
+        const size_t rowbytes = (size_t)W * f->channels;
+        if (in_frame == in_pitch * H) CU(cudaMemcpy2DAsync(d->d_in, rowbytes, f->data, in_pitch, rowbytes, (size_t)H * B, cudaMemcpyHostToDevice, st));
+        else for (int b = 0; b < B; ++b) CU(cudaMemcpy2DAsync(d->d_in + (size_t)b * rowbytes * H, rowbytes, f->data + (size_t)b * in_frame, in_pitch, rowbytes, H, cudaMemcpyHostToDevice, st));
+        src = d->d_in; src_pitch = rowbytes; src_frame = rowbytes * H;
+    }
+    stage_mark(d, ST_GRAY);
+    if (f->channels == 3) {
+        k_bgr2gray<<<d->num_sms * 8, 256, 0, st>>>(src, src_pitch, src_frame, d->d_gray, d->gray_pitch, d->gray_pitch * H, W, H, B);
+        d->launches++;
+        rc.gray = d->d_gray; rc.pitch = d->gray_pitch; rc.frame_stride = d->gray_pitch * H;
+    } else { rc.gray = src; rc.pitch = src_pitch; rc.frame_stride = src_frame; }
+    DetGeom &g = rc.g;
+    g.W = W; g.H = H; g.B = B; g.nScales = d->nScales;
+    for (int i = 0; i < MAX_SCALES; ++i) g.radius[i] = i < d->nScales ? d->radius[i] : 0;
+    g.Cfloor = (int)std::floor(d->prm.adaptiveThreshConstant);
+    g.WW = (W + 31) / 32; g.PWW = g.WW + 2; g.mask_plane = (long long)g.PWW * (H + 2);
+    g.KS = W + 1;
+    g.maxWH = std::max(W, H);
+    g.minPerim = (int)(unsigned)(d->prm.minMarkerPerimeterRate * g.maxWH);
+    g.maxPerim = (int)(unsigned)(d->prm.maxMarkerPerimeterRate * g.maxWH);
+    g.approxRate = d->prm.polygonalApproxAccuracyRate; g.minCornerDistRate = d->prm.minCornerDistanceRate;
+    g.surv_cap = d->surv_cap; g.pts_cap = d->pts_cap; g.starts_cap = d->starts_cap;
+    const size_t FS = (size_t)B * g.nScales;
+    if (W != d->lastW || H != d->lastH || B > d->lastB) {       // padding words / rows must be zero
+        CU(cudaMemsetAsync(d->d_masks, 0, d->masks_words * sizeof(uint32_t), st));
+        d->lastW = W; d->lastH = H; d->lastB = std::max(B, d->lastB);
+    }
+    const size_t FSmax = (size_t)d->cfg.max_batch * d->nScales;
+    CU(cudaMemsetAsync(d->d_counters, 0, (4 + 3 * FSmax + d->cfg.max_batch) * sizeof(int), st));
+    stage_mark(d, ST_THRESH);
+    {
+        dim3 grid((W + TH_TW - 1) / TH_TW, (H + TH_TH - 1) / TH_TH, B);
+        k_threshold<<<grid, TH_THREADS, 0, st>>>(rc.gray, rc.pitch, rc.frame_stride, d->d_masks, g);
+        d->launches++;
+    }
+    stage_mark(d, ST_STARTS);
+    k_starts<<<d->num_sms * 8, 256, 0, st>>>(d->d_masks, d->d_starts, (unsigned *)d->d_counters, d->d_iso_count, g);
+    d->launches++;
+    stage_mark(d, ST_WALK);
+    k_walk_count<<<d->num_sms * 16, 128, 0, st>>>(d->d_masks, d->d_starts, (const unsigned *)d->d_counters, d->d_surv, d->d_surv_count,
+                                                  d->d_contour_count, walk_max_len > 0 ? walk_max_len : g.maxPerim, g);
+    d->launches++;
+    stage_mark(d, ST_SORT);
+    k_sort_scan<<<(unsigned)FS, 1024, 0, st>>>(d->d_surv, d->d_surv_count, d->d_sorted, d->d_pts_off, d->d_status, g);
+    d->launches++;
+    stage_mark(d, ST_WRITE);
+    k_walk_write<<<dim3(8, (unsigned)FS), 128, 0, st>>>(d->d_masks, d->d_sorted, d->d_surv_count, d->d_pts_off, d->d_pts, g);
+    d->launches++;
+    stage_mark(d, ST_APPROX);
+    k_approx<<<dim3(8, (unsigned)FS), 256, 0, st>>>(d->d_sorted, d->d_surv_count, d->d_pts_off, d->d_pts, d->d_quad_ok, d->d_quad_xy, d->d_quad_len, g);
+    d->launches++;
+    return launch_err("front-end kernels");
+}
+
+static FrameParams frame_params(const b2a_detector *d, const DetGeom &g)
+{
+    FrameParams fp;
+    fp.W = g.W; fp.H = g.H; fp.nScales = g.nScales; fp.surv_cap = g.surv_cap; fp.max_cand = d->max_cand; fp.max_markers = d->max_markers;
+    fp.markerSize = d->dict.markerSize; fp.borderBits = d->prm.markerBorderBits; fp.minDistanceToBorder = d->prm.minDistanceToBorder;
+    fp.minMarkerDistanceRate = (float)d->prm.minMarkerDistanceRate; fp.minGroupDistance = d->prm.minGroupDistance;
+    return fp;
+}
+
+static int run_back(b2a_detector *d, const RunCtx &rc, const b2a_camera *cam, bool stop_after_group)
+{
+    const DetGeom &g = rc.g;
+    cudaStream_t st = d->stream;
+    FrameArrays fa;
+    fa.fs0 = d->fs0; fa.fo0 = d->fo0; fa.surv_count = d->d_surv_count; fa.quad_ok = d->d_quad_ok; fa.quad_xy = d->d_quad_xy; fa.quad_len = d->d_quad_len;
+    fa.fo0.status = d->d_status;
+    const FrameParams fp = frame_params(d, g);
+    stage_mark(d, ST_GROUP);
+    const int smem_words = 24 * 1024;                       // 96 KB closeness matrix in shared memory
+    k_group<<<g.B, 256, smem_words * sizeof(uint32_t), st>>>(fa, fp, smem_words);
+    d->launches++;
+    if (stop_after_group) return launch_err("k_group");
+    stage_mark(d, ST_IDENT);
+    IdentParams ip;
+    ip.markerSize = d->dict.markerSize; ip.borderBits = d->prm.markerBorderBits; ip.cellSize = d->prm.perspectiveRemovePixelPerCell;
+    ip.cellMargin = (int)(d->prm.perspectiveRemoveIgnoredMarginPerCell * ip.cellSize);
+    ip.nMarkers = d->dict.nMarkers; ip.maxCorr = (int)((double)d->dict.maxCorrectionBits * d->prm.errorCorrectionRate);
+    ip.maxBorderErr = (int)(d->dict.markerSize * d->dict.markerSize * d->prm.maxErroneousBitsInBorderRate);
+    ip.minOtsuStdDev = d->prm.minOtsuStdDev; ip.W = g.W; ip.H = g.H; ip.pitch = rc.pitch; ip.frame_stride = rc.frame_stride; ip.max_cand = d->max_cand;
+    k_identify<<<dim3(128, g.B), ID_THREADS, 0, st>>>(rc.gray, d->d_dict, fa, ip);
+    d->launches++;
+    stage_mark(d, ST_FINAL);
+    k_finalize<<<g.B, 32, 0, st>>>(fa, fp);
+    d->launches++;
+    float *corners = d->fo0.corners;
+    if (d->prm.cornerRefinementMethod == 1) {
+        SubpixParams sp;
+        sp.W = g.W; sp.H = g.H; sp.pitch = rc.pitch; sp.frame_stride = rc.frame_stride; sp.max_markers = d->max_markers;
+        sp.markerSize = d->dict.markerSize; sp.borderBits = d->prm.markerBorderBits; sp.maxWin = d->prm.cornerRefinementWinSize;
+        sp.maxIter = d->prm.cornerRefinementMaxIterations; sp.relWin = d->prm.relativeCornerRefinmentWinSize; sp.eps = d->prm.cornerRefinementMinAccuracy;
+        k_subpix<<<d->num_sms * 2, 128, 0, st>>>(rc.gray, d->fo0.n_accepted, d->fo0.corners, d->d_corners2, g.B, sp);
+        d->launches++;
+        corners = d->d_corners2;
+    }
+    stage_mark(d, ST_POSE);
+    if (cam) {
+        k_pose<<<d->num_sms, 64, 0, st>>>(corners, d->fo0.n_accepted, g.B, d->max_markers, to_camera(cam), cam->marker_length, d->d_rvecs, d->d_tvecs);
+        d->launches++;
+    }
+    stage_mark(d, ST_D2H);
+    const size_t BK = (size_t)g.B * d->max_markers;
+    CU(cudaMemcpyAsync(d->h_nacc, d->fo0.n_accepted, g.B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d->h_nrej, d->fo0.n_rejected, g.B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d->h_status, d->d_status, g.B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d->h_corners, corners, BK * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d->h_ids, d->fo0.ids, BK * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d->h_rejected, d->fo0.rejected, BK * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (cam) {
+        CU(cudaMemcpyAsync(d->h_rvecs, d->d_rvecs, BK * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(d->h_tvecs, d->d_tvecs, BK * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    cudaEventRecord(d->ev[ST_COUNT], st);
+    TRY(launch_err("back-end kernels"));
+    CU(cudaStreamSynchronize(st));
+    // stage times
+    int prev = -1;
+    for (int i = 0; i < ST_COUNT; ++i) d->stage_ms[i] = 0.f;
+    for (int i = 0; i <= ST_COUNT; ++i) {
+        if (i < ST_COUNT && !d->ev_used[i]) continue;
+        if (prev >= 0) cudaEventElapsedTime(&d->stage_ms[prev], d->ev[prev], d->ev[i]);
+        prev = i;
+    }
+    return B2A_OK;
+}
+
+static int fill_out(b2a_detector *d, int B, bool pose, b2a_detections *out)
+{
+    out->batch = B; out->max_markers = d->max_markers;
+    out->n_accepted = d->h_nacc; out->n_rejected = d->h_nrej; out->corners = d->h_corners; out->ids = d->h_ids;
+    out->rejected = d->h_rejected; out->rvecs = pose ? d->h_rvecs : nullptr; out->tvecs = pose ? d->h_tvecs : nullptr;
+    out->status = d->h_status;
+    for (int b = 0; b < B; ++b) if (d->h_status[b] != 0) return set_err(B2A_ERR_CAPACITY, "an internal list overflowed (see b2a_detections.status)");
+    return B2A_OK;
+}
+
+extern "C" int b2a_detect(b2a_detector *d, const b2a_frames *frames, b2a_detections *out)
+{
+    if (!out) return set_err(B2A_ERR_INVALID, "null output");
+    RunCtx rc;
+    TRY(run_front(d, frames, rc, 0));
+    TRY(run_back(d, rc, nullptr, false));
+    return fill_out(d, frames->batch, false, out);
+}
+
+extern "C" int b2a_detect_pose(b2a_detector *d, const b2a_frames *frames, const b2a_camera *cam, b2a_detections *out)
+{
+    if (!out || !cam) return set_err(B2A_ERR_INVALID, "null argument");
+    if (!(cam->marker_length > 0)) return set_err(B2A_ERR_INVALID, "markerLength <= 0");
+    RunCtx rc;
+    TRY(run_front(d, frames, rc, 0));
+    TRY(run_back(d, rc, cam, false));
+    return fill_out(d, frames->batch, true, out);
+}
+
+extern "C" int b2a_estimate_pose_single_markers(b2a_detector *d, const float *corners, int n, const b2a_camera *cam, double *rvecs, double *tvecs)
+{
+    if (!d || !cam || (n > 0 && (!corners || !rvecs || !tvecs))) return set_err(B2A_ERR_INVALID, "null argument");
+    if (!(cam->marker_length > 0)) return set_err(B2A_ERR_INVALID, "markerLength <= 0");
+    if (n <= 0) return B2A_OK;
+    CU(cudaSetDevice(d->device));
+    float *dc = nullptr; double *dr = nullptr, *dt = nullptr;
+    CU(cudaMalloc(&dc, (size_t)n * 8 * sizeof(float)));
+    CU(cudaMalloc(&dr, (size_t)n * 3 * sizeof(double)));
+    CU(cudaMalloc(&dt, (size_t)n * 3 * sizeof(double)));
+    cudaStream_t st = d->stream;
+    cudaMemcpyAsync(dc, corners, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice, st);
+    k_pose<<<std::min(d->num_sms * 2, (n + 63) / 64), 64, 0, st>>>(dc, nullptr, 1, n, to_camera(cam), cam->marker_length, dr, dt);
+    cudaMemcpyAsync(rvecs, dr, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(tvecs, dt, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(dc); cudaFree(dr); cudaFree(dt);
+    if (e != cudaSuccess) return set_err(B2A_ERR_CUDA, cudaGetErrorString(e));
+    return launch_err("k_pose");
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage taps
+// ------------------------------------------------------------------------------------------------
+extern "C" int b2a_debug_threshold(b2a_detector *d, const b2a_frames *f, uint8_t *gray, uint8_t *masks)
+{
+    RunCtx rc;
+    TRY(run_front(d, f, rc, 0));
+    const DetGeom &g = rc.g;
+    cudaStream_t st = d->stream;
+    if (gray) CU(cudaMemcpy2DAsync(gray, g.W, rc.gray, rc.pitch, g.W, (size_t)g.H * g.B, cudaMemcpyDeviceToHost, st));
+    if (gray && rc.frame_stride != rc.pitch * g.H)
+        for (int b = 0; b < g.B; ++b) CU(cudaMemcpy2DAsync(gray + (size_t)b * g.W * g.H, g.W, rc.gray + (size_t)b * rc.frame_stride, rc.pitch, g.W, g.H, cudaMemcpyDeviceToHost, st));
+    if (masks) {
+        uint8_t *tmp = nullptr;
+        const size_t n = (size_t)g.B * g.nScales * g.H * g.W;
+        CU(cudaMalloc(&tmp, n));
+        k_unpack_masks<<<d->num_sms * 8, 256, 0, st>>>(d->d_masks, tmp, g);
+        cudaMemcpyAsync(masks, tmp, n, cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        cudaFree(tmp);
+        if (e != cudaSuccess) return set_err(B2A_ERR_CUDA, cudaGetErrorString(e));
+    }
+    CU(cudaStreamSynchronize(st));
+    return launch_err("debug_threshold");
+}
+
+extern "C" int b2a_debug_contours(b2a_detector *d, const b2a_frames *f, int32_t *counts, int32_t *n_kept, int32_t *kept_len, int cap, int16_t *pts, int pts_cap)
+{
+    RunCtx rc;
+    TRY(run_front(d, f, rc, 2 * f->width * f->height + 16));       // exact total count: never give up on long borders
+    const DetGeom &g = rc.g;
+    CU(cudaStreamSynchronize(d->stream));
+    const size_t FS = (size_t)g.B * g.nScales;
+    std::vector<int> cc(FS), iso(FS), sc(FS), off((size_t)FS * g.surv_cap);
+    std::vector<uint4> sorted((size_t)FS * g.surv_cap);
+    CU(cudaMemcpy(cc.data(), d->d_contour_count, FS * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(iso.data(), d->d_iso_count, FS * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(sc.data(), d->d_surv_count, FS * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(off.data(), d->d_pts_off, off.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(sorted.data(), d->d_sorted, sorted.size() * sizeof(uint4), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> p((size_t)g.pts_cap);
+    for (size_t fs = 0; fs < FS; ++fs) {
+        if (counts) counts[fs] = cc[fs] + iso[fs];
+        if (n_kept) n_kept[fs] = sc[fs];
+        if (pts) CU(cudaMemcpy(p.data(), d->d_pts + fs * g.pts_cap, (size_t)g.pts_cap * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        int w = 0;
+        for (int i = 0; i < sc[fs]; ++i) {
+            const uint4 e = sorted[fs * g.surv_cap + i];
+            if (kept_len && i < cap) kept_len[fs * cap + i] = (int)e.y;
+            const int o = off[fs * g.surv_cap + i];
+            if (pts && o >= 0)
+                for (int k = 0; k < (int)e.y && w < pts_cap; ++k, ++w) {
+                    pts[(fs * pts_cap + w) * 2] = (int16_t)(p[o + k] & 0xFFFF);
+                    pts[(fs * pts_cap + w) * 2 + 1] = (int16_t)(p[o + k] >> 16);
+                }
+        }
+    }
+    return B2A_OK;
+}
+
+extern "C" int b2a_debug_candidates(b2a_detector *d, const b2a_frames *f, int32_t *n_cand, float *quads, int cap)
+{
+    RunCtx rc;
+    TRY(run_front(d, f, rc, 0));
+    TRY(run_back(d, rc, nullptr, true));
+    CU(cudaStreamSynchronize(d->stream));
+    const int B = rc.g.B;
+    std::vector<int> cnt((size_t)B * 8);
+    CU(cudaMemcpy(cnt.data(), d->fs0.counters, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < B; ++b) {
+        const int n = cnt[(size_t)b * 8 + FC_NCAND];
+        if (n_cand) n_cand[b] = n;
+        if (quads && n > 0) CU(cudaMemcpy(quads + (size_t)b * cap * 8, d->fs0.cq + (size_t)b * d->max_cand * 8, (size_t)std::min(n, cap) * 8 * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return B2A_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SLAM handle: observation mapping + EKF with Sigma resident on the device
+// ------------------------------------------------------------------------------------------------
+struct b2a_slam {
+    b2a_slam_params p;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int N = 3, LD = 0, cap_lm = 0;
+    double *d_mu = nullptr, *d_mus = nullptr, *d_sigma = nullptr, *d_K = nullptr, *d_GS = nullptr, *d_scratch = nullptr;
+    std::vector<int32_t> ids;                       // landmark k -> aruco id (aruco_id_map, aruco_slam.h:164)
+    std::vector<int32_t> last_ids; std::vector<double> last_obs;   // last_observed_marker_ (NaN = unset)
+    bool is_init = false;
+};
+
+extern "C" void b2a_default_slam_params(b2a_slam_params *p)
+{
+    p->Q_k = 0.01; p->R_x = 100.0; p->R_y = 100.0; p->R_theta = 10.0;       // parameters.yaml:5-8
+    p->kl = 0.05; p->kr = 0.05; p->b = 0.09;                                 // parameters.yaml:11-13
+    p->r2c_tx = 0.0; p->r2c_ty = 0.0;
+    p->useful_distance_threshold = 3.f;                                      // aruco_slam.h:58 (the yaml key is never read)
+    p->max_landmarks = 512;
+}
+
+extern "C" void b2a_slam_destroy(b2a_slam *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_mu); cudaFree(s->d_mus); cudaFree(s->d_sigma); cudaFree(s->d_K); cudaFree(s->d_GS); cudaFree(s->d_scratch);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+extern "C" int b2a_slam_create(int device, const b2a_slam_params *p, b2a_slam **out)
+{
+    if (!out) return set_err(B2A_ERR_INVALID, "null output");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return set_err(B2A_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return set_err(B2A_ERR_INVALID, "bad device ordinal");
+    b2a_slam *s = new b2a_slam();
+    if (p) s->p = *p; else b2a_default_slam_params(&s->p);
+    s->device = device;
+    s->cap_lm = s->p.max_landmarks > 0 ? s->p.max_landmarks : 512;
+    s->LD = ((3 + 3 * s->cap_lm) + 15) & ~15;
+    auto fail = [&](const char *m) { std::string e = m; b2a_slam_destroy(s); return set_err(B2A_ERR_CUDA, e); };
+    if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice");
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+    const size_t LD = s->LD;
+    if (cudaMalloc(&s->d_mu, LD * 8) || cudaMalloc(&s->d_mus, LD * 8) || cudaMalloc(&s->d_sigma, LD * LD * 8) ||
+        cudaMalloc(&s->d_K, LD * 3 * 8) || cudaMalloc(&s->d_GS, LD * 3 * 8) || cudaMalloc(&s->d_scratch, LD * 6 * 8))
+        return fail("cudaMalloc (EKF state)");
+    cudaMemsetAsync(s->d_mu, 0, LD * 8, s->stream);
+    cudaMemsetAsync(s->d_sigma, 0, LD * LD * 8, s->stream);
+    if (cudaStreamSynchronize(s->stream) != cudaSuccess) return fail("memset");
+    *out = s;
+    return B2A_OK;
+}
+
+extern "C" int b2a_slam_dim(const b2a_slam *s) { return s ? s->N : 0; }
+
+extern "C" int b2a_slam_get_state(b2a_slam *s, double *mu, double *sigma, int32_t *ids)
+{
+    if (!s) return set_err(B2A_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    if (mu) CU(cudaMemcpy(mu, s->d_mu, (size_t)s->N * 8, cudaMemcpyDeviceToHost));
+    if (sigma) CU(cudaMemcpy2D(sigma, (size_t)s->N * 8, s->d_sigma, (size_t)s->LD * 8, (size_t)s->N * 8, s->N, cudaMemcpyDeviceToHost));
+    if (ids) std::memcpy(ids, s->ids.data(), s->ids.size() * sizeof(int32_t));
+    return B2A_OK;
+}
+
+extern "C" int b2a_slam_set_state(b2a_slam *s, int N, const double *mu, const double *sigma, const int32_t *ids)
+{
+    if (!s || !mu || !sigma) return set_err(B2A_ERR_INVALID, "null argument");
+    if (N < 3 || (N - 3) % 3 || (N - 3) / 3 > s->cap_lm) return set_err(B2A_ERR_INVALID, "state dimension");
+    if (N > 3 && !ids) return set_err(B2A_ERR_INVALID, "ids required");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaMemset(s->d_sigma, 0, (size_t)s->LD * s->LD * 8));
+    CU(cudaMemcpy(s->d_mu, mu, (size_t)N * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy2D(s->d_sigma, (size_t)s->LD * 8, sigma, (size_t)N * 8, (size_t)N * 8, N, cudaMemcpyHostToDevice));
+    s->N = N;
+    s->ids.assign(ids, ids + (N - 3) / 3);
+    s->last_ids.clear(); s->last_obs.clear();
+    s->is_init = true;
+    return B2A_OK;
+}
+
+extern "C" int b2a_slam_add_encoder(b2a_slam *s, double wl, double wr, double dt)
+{
+    if (!s) return set_err(B2A_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(s->device));
+    s->is_init = true;
+    k_ekf_predict<<<1, 256, 0, s->stream>>>(s->d_sigma, s->d_mu, s->N, s->LD, wl, wr, dt, s->p.kl, s->p.kr, s->p.b, s->p.Q_k, s->d_scratch);
+    return launch_err("k_ekf_predict");
+}
+
+extern "C" int b2a_slam_make_observations(b2a_slam *s, const float *corners, const int32_t *ids, const double *rvecs, const double *tvecs,
+                                          int n, const b2a_camera *cam, b2a_observation *out, int *n_out)
+{
+    if (!s || !cam || !n_out || (n > 0 && (!corners || !ids || !rvecs || !tvecs || !out))) return set_err(B2A_ERR_INVALID, "null argument");
+    *n_out = 0;
+    if (n <= 0) return B2A_OK;
+    CU(cudaSetDevice(s->device));
+    float *dc; int32_t *di; double *dr, *dtv; Observation *dobs; int *dkeep;
+    CU(cudaMalloc(&dc, (size_t)n * 32)); CU(cudaMalloc(&di, (size_t)n * 4)); CU(cudaMalloc(&dr, (size_t)n * 24)); CU(cudaMalloc(&dtv, (size_t)n * 24));
+    CU(cudaMalloc(&dobs, (size_t)n * sizeof(Observation))); CU(cudaMalloc(&dkeep, (size_t)n * 4));
+    cudaStream_t st = s->stream;
+    cudaMemcpyAsync(dc, corners, (size_t)n * 32, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(di, ids, (size_t)n * 4, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dr, rvecs, (size_t)n * 24, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(dtv, tvecs, (size_t)n * 24, cudaMemcpyHostToDevice, st);
+    ObsParams op;
+    op.R_x = s->p.R_x; op.R_y = s->p.R_y; op.R_theta = s->p.R_theta; op.marker_length = (double)cam->marker_length;
+    op.r2c_tx = s->p.r2c_tx; op.r2c_ty = s->p.r2c_ty; op.useful_distance_threshold = s->p.useful_distance_threshold;
+    k_observations<<<(n + 63) / 64, 64, 0, st>>>(dc, di, dr, dtv, n, to_camera(cam), op, dobs, dkeep);
+    std::vector<Observation> ho(n); std::vector<int> hk(n);
+    cudaMemcpyAsync(ho.data(), dobs, (size_t)n * sizeof(Observation), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(hk.data(), dkeep, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(dc); cudaFree(di); cudaFree(dr); cudaFree(dtv); cudaFree(dobs); cudaFree(dkeep);
+    if (e != cudaSuccess) return set_err(B2A_ERR_CUDA, cudaGetErrorString(e));
+    int k = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!hk[i]) continue;
+        b2a_observation &o = out[k++];
+        o.aruco_id = ho[i].aruco_id; o.aruco_index = -1; o.x = ho[i].x; o.y = ho[i].y; o.theta = ho[i].theta;
+        std::memcpy(o.cov, ho[i].cov, sizeof(o.cov));
+    }
+    *n_out = k;
+    return launch_err("k_observations");
+}
+
+extern "C" int b2a_slam_update(b2a_slam *s, const b2a_observation *obs, int n)
+{
+    if (!s || (n > 0 && !obs)) return set_err(B2A_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(s->device));
+    if (n <= 0) { s->last_ids.clear(); s->last_obs.clear(); return B2A_OK; }
+    // checkLandmark (:423-435) + priority-queue order (aruco_slam.h:85-88): ascending index, new (-1) first;
+    // ties keep detection order (the reference's heap order among equals is implementation-defined)
+    struct Item { int index, seq; };
+    std::vector<Item> q(n);
+    for (int i = 0; i < n; ++i) {
+        int idx = -1;
+        for (size_t k = 0; k < s->ids.size(); ++k) if (s->ids[k] == obs[i].aruco_id) { idx = (int)k; break; }
+        q[i] = {idx, i};
+    }
+    std::stable_sort(q.begin(), q.end(), [](const Item &a, const Item &b) { return a.index < b.index; });
+    int n_new = 0;
+    for (const Item &it : q) n_new += it.index < 0;
+    if ((int)s->ids.size() + n_new > s->cap_lm) return set_err(B2A_ERR_CAPACITY, "landmark capacity exceeded");
+    cudaStream_t st = s->stream;
+    CU(cudaMemcpyAsync(s->d_mus, s->d_mu, (size_t)s->N * 8, cudaMemcpyDeviceToDevice, st));      // mu snapshot (:88)
+    std::vector<int32_t> new_last_ids(n);
+    std::vector<double> new_last_obs((size_t)n * 3, NAN);
+    for (int qi = 0; qi < n; ++qi) {
+        const b2a_observation &o = obs[q[qi].seq];
+        EkfObs eo;
+        eo.index = q[qi].index;
+        eo.z[0] = o.x; eo.z[1] = o.y; eo.z[2] = o.theta;
+        std::memcpy(eo.Rk, o.cov, sizeof(eo.Rk));
+        if (eo.index >= 0) {
+            bool stationary = false;                                  // :192-198
+            for (size_t l = 0; l < s->last_ids.size(); ++l)
+                if (s->last_ids[l] == o.aruco_id) {
+                    const double d0 = s->last_obs[3 * l] - o.x, d1 = s->last_obs[3 * l + 1] - o.y, d2 = s->last_obs[3 * l + 2] - o.theta;
+                    if (std::sqrt(d0 * d0 + d1 * d1 + d2 * d2) < 0.01) stationary = true;
+                    break;
+                }
+            if (!stationary) {
+                new_last_obs[3 * qi] = o.x; new_last_obs[3 * qi + 1] = o.y; new_last_obs[3 * qi + 2] = o.theta;
+                const int N = s->N;
+                k_ekf_gain<<<(N + 255) / 256, 256, 0, st>>>(s->d_sigma, s->d_mus, N, s->LD, eo, s->d_K, s->d_GS);
+                dim3 grid((N + 2 * EK_TX - 1) / (2 * EK_TX), (N + EK_ROWS - 1) / EK_ROWS);
+                k_ekf_rank3<<<grid, dim3(EK_TX, EK_TY), 0, st>>>(s->d_sigma, s->d_mu, s->d_mus, N, s->LD, eo, s->d_K, s->d_GS);
+            }
+        } else {
+            k_ekf_augment<<<1, 256, 0, st>>>(s->d_sigma, s->d_mu, s->d_mus, s->N, s->LD, eo);
+            s->N += 3;
+            s->ids.push_back(o.aruco_id);                              // :256
+        }
+        new_last_ids[qi] = o.aruco_id;
+    }
+    s->last_ids.swap(new_last_ids); s->last_obs.swap(new_last_obs);    // :263
+    return launch_err("EKF kernels");
+}
+
+extern "C" int b2a_slam_add_image(b2a_slam *s, b2a_detector *d, const b2a_frames *frame, const b2a_camera *cam)
+{
+    if (!s || !d || !frame || !cam) return set_err(B2A_ERR_INVALID, "null argument");
+    if (frame->batch != 1) return set_err(B2A_ERR_INVALID, "add_image takes one frame");
+    if (!s->is_init) return B2A_OK;                                    // :84-85 (needs one encoder message first)
+    b2a_detections det;
+    TRY(b2a_detect_pose(d, frame, cam, &det));
+    const int n = det.n_accepted[0];
+    std::vector<b2a_observation> obs(std::max(n, 1));
+    int k = 0;
+    TRY(b2a_slam_make_observations(s, det.corners, det.ids, det.rvecs, det.tvecs, n, cam, obs.data(), &k));
+    return b2a_slam_update(s, obs.data(), k);
+}

@@ -1,0 +1,635 @@
+// core.h -- per-thread / per-warp building blocks of the detect path, written so that the
+// same source compiles for the device (inside the kernels of detect_kernels.cuh) and for the
+// host (tests/hostemu: a single-lane emulation used by the CPU-only tests to check the
+// kernel logic against the oracle; it is test infrastructure, never a product path).
+//
+// What each block replaces inside cv::aruco::detectMarkers (reference src/aruco_slam.cpp:313;
+// algorithm per SURVEY.md Appendix A, OpenCV 4.13.0):
+//   border states / walks      -> findContours(RETR_LIST, CHAIN_APPROX_NONE)   (A3a, marking-free form)
+//   approx_closed              -> approxPolyDP(closed)                          (A3b)
+//   quad tests                 -> isContourConvex + corner-distance gate        (A3)
+//   perimeter / avg distance   -> filterTooCloseCandidates arithmetic           (A5)
+//   point_in_quad              -> pointPolygonTest(measureDist=false)           (A5 hierarchy)
+//   perspective / otsu / bits  -> _extractBits / Dictionary::identify           (A7)
+#pragma once
+#include <stdint.h>
+#include <float.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define B2A_HD __host__ __device__ __forceinline__
+#else
+#define B2A_HD inline
+#endif
+
+namespace b2a {
+
+// ---------------------------------------------------------------------------------------------
+// bit helpers
+// ---------------------------------------------------------------------------------------------
+B2A_HD int ffs32(unsigned v)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v);
+#else
+    return __builtin_ffs((int)v);
+#endif
+}
+B2A_HD int clz32(unsigned v)
+{
+#if defined(__CUDA_ARCH__)
+    return __clz((int)v);
+#else
+    return v ? __builtin_clz(v) : 32;
+#endif
+}
+B2A_HD int popc64(unsigned long long v)
+{
+#if defined(__CUDA_ARCH__)
+    return __popcll(v);
+#else
+    return __builtin_popcountll(v);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// Border states.  A mask pixel's "code" byte has bit d set iff its neighbour in direction d is
+// set (d = 0..7: E, NE, N, NW, W, SW, S, SE; y grows downward); code == 0 means the pixel is
+// not set (an isolated set pixel has no border longer than one point and is stored as 0 too).
+// A border state is (pixel, s_in) with s_in the direction towards the previous border pixel.
+// Suzuki-Abe border following is the permutation succ() on these states; every border is one
+// cycle, its first point is the state with the smallest "start key" on the cycle.
+// ---------------------------------------------------------------------------------------------
+B2A_HD int dir_dx(int d) { return (int)((0x901Au >> (2 * d)) & 3u) - 1; }
+B2A_HD int dir_dy(int d) { return (int)((0xA901u >> (2 * d)) & 3u) - 1; }
+B2A_HD unsigned ror8(unsigned v, int r)
+{
+    r &= 7;
+    return ((v >> r) | (v << (8 - r))) & 0xFFu;
+}
+// direction of the next border pixel: first set neighbour scanning s_in+1, s_in+2, ... (ccw)
+B2A_HD int succ_dir(unsigned code, int s_in)
+{
+    unsigned r = ror8(code, s_in + 1);
+    return (s_in + ffs32(r)) & 7;            // s_in + 1 + (ffs - 1)
+}
+// first set neighbour scanning from-1, from-2, ..., from-7 (cw); -1 if none
+B2A_HD int first_cw(unsigned code, int from)
+{
+    unsigned r = ror8(code, from) & 0xFEu;
+    if (!r) return -1;
+    return (from + (31 - clz32(r))) & 7;
+}
+// s_in of the state that precedes (c, s_in): p = c + d[s_in], t = s_in ^ 4 is the direction p -> c
+B2A_HD int pred_dir(unsigned code_p, int t)
+{
+    int s = first_cw(code_p, t);
+    return s < 0 ? t : s;
+}
+// Start key of a state if it is start-eligible, else 0xFFFFFFFF.  Keys are strictly monotone in
+// the raster position at which the sequential scan would detect the border (outer borders at
+// the pixel itself, hole borders at the 0-pixel to its right), outer before hole.
+B2A_HD uint32_t start_key(int x, int y, int s, unsigned code, int W)
+{
+    if (!(code & 16u) && first_cw(code, 4) == s) return (uint32_t)((y * (W + 1) + x) * 2);
+    if (!(code & 1u) && first_cw(code, 0) == s) return (uint32_t)((y * (W + 1) + x + 1) * 2 + 1);
+    return 0xFFFFFFFFu;
+}
+// local necessary conditions for a pixel to carry the first state of a border
+B2A_HD bool outer_start_candidate(unsigned code) { return code != 0 && (code & 0x1Eu) == 0; }   // W,NW,N,NE clear
+B2A_HD bool hole_start_candidate(unsigned code) { return (code & 3u) == 2u; }                   // E clear, NE set
+
+// Word-parallel start-candidate test for the 32 pixels of mask word m.  ml / mr are the words to
+// its left / right, u* the row above, d* the row below (bit i of a word = pixel 32*w + i).
+//   outer start: pixel set, W / NW / N / NE clear, at least one other neighbour
+//   hole  start: pixel set, E clear, NE set
+//   iso        : set pixel without any neighbour (a one-point border, counted only)
+B2A_HD void start_candidate_words(uint32_t m, uint32_t ml, uint32_t mr, uint32_t u, uint32_t ul, uint32_t ur,
+                                  uint32_t d, uint32_t dl, uint32_t dr, uint32_t &outer, uint32_t &hole, uint32_t &iso)
+{
+    const uint32_t mW = (m << 1) | (ml >> 31), mE = (m >> 1) | (mr << 31);
+    const uint32_t uW = (u << 1) | (ul >> 31), uE = (u >> 1) | (ur << 31);
+    const uint32_t dW = (d << 1) | (dl >> 31), dE = (d >> 1) | (dr << 31);
+    outer = m & ~mW & ~uW & ~u & ~uE & (mE | dW | d | dE);
+    hole = m & ~mE & uE;
+    iso = m & ~(mW | mE | uW | u | uE | dW | d | dE);
+}
+// initial state and key of a start candidate of the given type (0 outer, 1 hole); false if the
+// state is also outer-eligible with a smaller key (then it cannot be a hole border's first state)
+B2A_HD bool start_state(unsigned code, int x, int y, int type, int KS, int &s0, uint32_t &key0)
+{
+    s0 = first_cw(code, type ? 0 : 4);
+    key0 = (uint32_t)((y * KS + x + type) * 2 + type);
+    if (type == 1 && start_key(x, y, s0, code, KS - 1) < key0) return false;
+    return true;
+}
+
+// Packed mask access: `plane` points at row -1; pixel (x,y) is bit (x & 31) of word
+// (y + 1) * PWW + (x >> 5) + 1.  One zero word left and >= 1 right of every row and zero rows
+// above and below, so 3x3 neighbourhoods never need bounds checks.
+B2A_HD uint32_t ld_ro(const uint32_t *p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+struct MaskView {
+    const uint32_t *plane;
+    int PWW;
+    B2A_HD unsigned win3(int x, int y) const      // bits x-1, x, x+1 of row y
+    {
+        const uint32_t *row = plane + (size_t)(y + 1) * PWW + (x >> 5) + 1;
+        const int o = x & 31;
+        const uint32_t w = ld_ro(row);
+        if (o == 0) return ((w << 1) | (ld_ro(row - 1) >> 31)) & 7u;
+        if (o == 31) return ((w >> 30) | (ld_ro(row + 1) << 2)) & 7u;
+        return (w >> (o - 1)) & 7u;
+    }
+    // neighbour code of pixel (x,y): bit d = neighbour in direction d
+    B2A_HD unsigned operator()(int x, int y) const
+    {
+        const unsigned u = win3(x, y - 1), m = win3(x, y), d = win3(x, y + 1);
+        return ((m >> 2) & 1u) | (((u >> 2) & 1u) << 1) | (((u >> 1) & 1u) << 2) | ((u & 1u) << 3) |
+               ((m & 1u) << 4) | ((d & 1u) << 5) | (((d >> 1) & 1u) << 6) | (((d >> 2) & 1u) << 7);
+    }
+};
+
+// Walk the border through state (x0,y0,s0) in both directions at once.  Returns the border
+// length if (x0,y0,s0) is the border's first state; 0 if another start-eligible state with a
+// smaller key lies on the border (then that one reports it); -1 once more than max_len steps
+// were taken without closing (the border is discarded by the perimeter gate anyway).
+// code_at(x, y) returns the neighbour code of a set pixel; W1 = key stride - 1.
+template <class CodeAt>
+B2A_HD int walk_count(const CodeAt &code_at, int W1, int x0, int y0, int s0, uint32_t key0, int max_len)
+{
+    int xf = x0, yf = y0, sf = s0, xb = x0, yb = y0, sb = s0;
+    unsigned cf = code_at(x0, y0);
+    int n = 0;
+    for (;;) {
+        const int so = succ_dir(cf, sf);
+        xf += dir_dx(so); yf += dir_dy(so); sf = so ^ 4;
+        ++n;
+        if (xf == xb && yf == yb && sf == sb) return n;
+        const int xp = xb + dir_dx(sb), yp = yb + dir_dy(sb);
+        cf = code_at(xf, yf);                       // two independent loads in flight
+        const unsigned cp = code_at(xp, yp);
+        if (start_key(xf, yf, sf, cf, W1) < key0) return 0;
+        if (n > max_len) return -1;
+        sb = pred_dir(cp, sb ^ 4);
+        xb = xp; yb = yp;
+        ++n;
+        if (xf == xb && yf == yb && sf == sb) return n;
+        if (start_key(xb, yb, sb, cp, W1) < key0) return 0;
+        if (n > max_len) return -1;
+    }
+}
+// Emit the n border points (x | y << 16) starting at state (x0,y0,s0), filling from both ends.
+template <class CodeAt>
+B2A_HD void walk_write(const CodeAt &code_at, int x0, int y0, int s0, int n, uint32_t *__restrict__ out)
+{
+    int xf = x0, yf = y0, sf = s0, xb = x0, yb = y0, sb = s0;
+    out[0] = (uint32_t)x0 | ((uint32_t)y0 << 16);
+    int lo = 1, hi = n - 1;
+    unsigned cf = code_at(x0, y0);
+    while (lo <= hi) {
+        const int so = succ_dir(cf, sf);
+        xf += dir_dx(so); yf += dir_dy(so); sf = so ^ 4;
+        out[lo++] = (uint32_t)xf | ((uint32_t)yf << 16);
+        if (lo > hi) break;
+        const int xp = xb + dir_dx(sb), yp = yb + dir_dy(sb);
+        cf = code_at(xf, yf);
+        const unsigned cp = code_at(xp, yp);
+        sb = pred_dir(cp, sb ^ 4);
+        xb = xp; yb = yp;
+        out[hi--] = (uint32_t)xb | ((uint32_t)yb << 16);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// approxPolyDP(closed = true) on integer points, cooperative over a group of lanes.
+// LG supplies lane(), nlanes() and argmax_first(d, pos): the maximum d over the lanes and,
+// among equal maxima, the smallest pos (= OpenCV's strict '>' first-maximum rule).
+// Only results with <= 8 vertices before the clean-up pass can end as quadrilaterals, so the
+// recursion stops (returns -1) as soon as more than 8 vertices or 16 pending slices exist.
+// ---------------------------------------------------------------------------------------------
+struct SingleLane {
+    B2A_HD int lane() const { return 0; }
+    B2A_HD int nlanes() const { return 1; }
+    B2A_HD void argmax_first(long long &, int &) const {}
+};
+
+B2A_HD int px_of(uint32_t p) { return (int)(p & 0xFFFFu); }
+B2A_HD int py_of(uint32_t p) { return (int)(p >> 16); }
+
+template <class LG>
+B2A_HD int approx_closed(const LG &lg, const uint32_t *__restrict__ P, int count, double eps, int *ox, int *oy)
+{
+    const double eps2 = eps * eps;
+    const int lane = lg.lane(), nl = lg.nlanes();
+    int right = 0, pos = 0, startp = 0;
+    long long maxd = 0;
+    for (int it = 0; it < 3; ++it) {
+        pos = (pos + right) % count;
+        startp = pos;
+        const int sx = px_of(P[pos]), sy = py_of(P[pos]);
+        pos = (pos + 1) % count;
+        long long bd = 0; int bj = 0x7FFFFFFF;
+        for (int j = 1 + lane; j < count; j += nl) {
+            int idx = pos + j - 1; if (idx >= count) idx -= count;
+            const uint32_t q = P[idx];
+            long long dx = px_of(q) - sx, dy = py_of(q) - sy, d = dx * dx + dy * dy;
+            if (d > bd) { bd = d; bj = j; }
+        }
+        lg.argmax_first(bd, bj);
+        maxd = bd;
+        if (bd > 0) right = bj;
+        pos = (pos + count - 1) % count;
+    }
+    int m = 0;
+    if ((double)maxd <= eps2) { ox[0] = px_of(P[startp]); oy[0] = py_of(P[startp]); return 1; }
+    int st_s[16], st_e[16], top = 0;
+    {
+        int a = pos % count, b = (right + a) % count;
+        st_s[0] = b; st_e[0] = a; st_s[1] = a; st_e[1] = b; top = 2;
+    }
+    while (top > 0) {
+        --top;
+        const int s = st_s[top], e = st_e[top];
+        const int ex = px_of(P[e]), ey = py_of(P[e]);
+        const int sx = px_of(P[s]), sy = py_of(P[s]);
+        int inner = e - s - 1; if (inner < 0) inner += count;     // points strictly between s and e (count-1 when s == e)
+        bool le = true;
+        int split = 0;
+        if (inner > 0) {
+            const long long dx = ex - sx, dy = ey - sy, L2 = dx * dx + dy * dy;
+            long long bd = 0; int bt = 0x7FFFFFFF;
+            for (int t = lane; t < inner; t += nl) {
+                int idx = s + 1 + t; if (idx >= count) idx -= count;
+                const uint32_t q = P[idx];
+                const long long px = px_of(q) - sx, py = py_of(q) - sy;
+                const long long dot = px * dx + py * dy;
+                long long d;
+                if (dot < 0) d = (px * px + py * py) * L2;
+                else if (dot > L2) { long long qx = px - dx, qy = py - dy; d = (qx * qx + qy * qy) * L2; }
+                else { long long cr = py * dx - px * dy; d = cr * cr; }
+                if (d > bd) { bd = d; bt = t; }
+            }
+            lg.argmax_first(bd, bt);
+            if (bd > 0) { split = s + 1 + bt; if (split >= count) split -= count; }
+            le = (double)bd <= eps2 * (double)L2;
+        }
+        if (le) {
+            if (m >= 8) return -1;
+            ox[m] = sx; oy[m] = sy; ++m;
+        } else {
+            if (top + 2 > 16) return -1;
+            st_s[top] = split; st_e[top] = e; ++top;
+            st_s[top] = s; st_e[top] = split; ++top;
+        }
+    }
+    // clean-up pass (sequential, <= 8 points; every lane computes the same thing)
+    int new_count = m;
+    {
+        int r = 0, w = 0;
+        double stx = ox[m - 1], sty = oy[m - 1];
+        double ptx = ox[0], pty = oy[0];
+        r = 1 % m;
+        for (int i = 0; i < m && new_count > 2; ++i) {
+            const double ex = ox[r], ey = oy[r];
+            r = (r + 1) % m;
+            const double dx = ex - stx, dy = ey - sty;
+            const double dist = fabs((ptx - stx) * dy - (pty - sty) * dx);
+            const double sip = (ptx - stx) * (ex - ptx) + (pty - sty) * (ey - pty);
+            if (dist * dist <= 0.5 * eps2 * (dx * dx + dy * dy) && dx != 0 && dy != 0 && sip >= 0) {
+                --new_count;
+                ox[w] = (int)ex; oy[w] = (int)ey; w = (w + 1) % m;
+                stx = ex; sty = ey;
+                ptx = ox[r]; pty = oy[r];
+                r = (r + 1) % m;
+                ++i;
+                continue;
+            }
+            ox[w] = (int)ptx; oy[w] = (int)pty; w = (w + 1) % m;
+            stx = ptx; sty = pty;
+            ptx = ex; pty = ey;
+        }
+    }
+    return new_count;
+}
+
+// isContourConvex on 4 integer points (any collinear consecutive edge pair -> false)
+B2A_HD bool quad_is_convex(const int *qx, const int *qy)
+{
+    long long px = qx[2], py = qy[2], cx = qx[3], cy = qy[3];
+    long long dx0 = cx - px, dy0 = cy - py;
+    int o = 0;
+    for (int i = 0; i < 4; ++i) {
+        px = cx; py = cy; cx = qx[i]; cy = qy[i];
+        long long dx = cx - px, dy = cy - py;
+        long long a = dx * dy0, b = dy * dx0;
+        o |= (b > a) ? 1 : ((b < a) ? 2 : 3);
+        if (o == 3) return false;
+        dx0 = dx; dy0 = dy;
+    }
+    return true;
+}
+
+// A3 gate after approxPolyDP: 4 vertices, convex, shortest side >= n * minCornerDistanceRate
+B2A_HD bool quad_passes(const int *qx, const int *qy, int n_approx, int contour_len, int maxWH, double minCornerDistanceRate)
+{
+    if (n_approx != 4 || !quad_is_convex(qx, qy)) return false;
+    double minDistSq = (double)maxWH * (double)maxWH;
+    for (int j = 0; j < 4; ++j) {
+        double dx = qx[j] - qx[(j + 1) & 3], dy = qy[j] - qy[(j + 1) & 3];
+        double d = dx * dx + dy * dy;
+        if (d < minDistSq) minDistSq = d;
+    }
+    double mcd = (double)contour_len * minCornerDistanceRate;
+    return !(minDistSq < mcd * mcd);
+}
+
+// A4: make the corner order clockwise (swap corners 1 and 3 when the cross product is negative)
+B2A_HD void quad_make_clockwise(float *c)
+{
+    double dx1 = c[2] - c[0], dy1 = c[3] - c[1], dx2 = c[4] - c[0], dy2 = c[5] - c[1];
+    if (dx1 * dy2 - dy1 * dx2 < 0.0) {
+        float tx = c[2], ty = c[3];
+        c[2] = c[6]; c[3] = c[7]; c[6] = tx; c[7] = ty;
+    }
+}
+
+// ---- float32 arithmetic of filterTooCloseCandidates (A5); operation order matters ----
+B2A_HD float f_mul(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+B2A_HD float f_add(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+B2A_HD float f_sqrt(float a)
+{
+#if defined(__CUDA_ARCH__)
+    return __fsqrt_rn(a);
+#else
+    return sqrtf(a);
+#endif
+}
+B2A_HD float f_div(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+B2A_HD float norm2f(float dx, float dy) { return f_add(f_mul(dx, dx), f_mul(dy, dy)); }
+
+B2A_HD float quad_perimeter(const float *c)
+{
+    float p = 0.f;
+    for (int i = 0; i < 4; ++i) {
+        int j = (i + 1) & 3;
+        p = f_add(p, f_sqrt(norm2f(c[2 * i] - c[2 * j], c[2 * i + 1] - c[2 * j + 1])));
+    }
+    return p;
+}
+B2A_HD float quad_avg_distance(const float *a, const float *b)
+{
+    float minsq = FLT_MAX;
+    for (int fc = 0; fc < 4; ++fc) {
+        float dsq = 0.f;
+        for (int c = 0; c < 4; ++c) {
+            int mc = (c + fc) & 3;
+            dsq = f_add(dsq, norm2f(a[2 * mc] - b[2 * c], a[2 * mc + 1] - b[2 * c + 1]));
+        }
+        dsq = f_div(dsq, 4.f);
+        if (dsq < minsq) minsq = dsq;
+    }
+    return f_sqrt(minsq);
+}
+B2A_HD float quad_module_size(const float *c, int markerSize, int borderBits)
+{
+    float a = quad_perimeter(c);
+    int nm = markerSize + borderBits * 2;
+    return f_div(a, 4.f * (float)nm);
+}
+B2A_HD bool quad_near_border(const float *c, int W, int H, int mdb)
+{
+    for (int j = 0; j < 4; ++j) {
+        float x = c[2 * j], y = c[2 * j + 1];
+        if (x < (float)mdb || y < (float)mdb || x > (float)(W - 1 - mdb) || y > (float)(H - 1 - mdb)) return true;
+    }
+    return false;
+}
+// pointPolygonTest(measureDist = false) >= 0 for a float quad
+B2A_HD int point_in_quad(const float *poly, float ptx, float pty)
+{
+    int counter = 0;
+    float vx = poly[6], vy = poly[7];
+    for (int i = 0; i < 4; ++i) {
+        float v0x = vx, v0y = vy;
+        vx = poly[2 * i]; vy = poly[2 * i + 1];
+        if ((v0y <= pty && vy <= pty) || (v0y > pty && vy > pty) || (v0x < ptx && vx < ptx)) {
+            if (pty == vy && (ptx == vx || (pty == v0y && ((v0x <= ptx && ptx <= vx) || (vx <= ptx && ptx <= v0x)))))
+                return 0;
+            continue;
+        }
+        // coordinates are integers below 2^13: the products are exact in double
+        double dist = (double)(pty - v0y) * (double)(vx - v0x) - (double)(ptx - v0x) * (double)(vy - v0y);
+        if (dist == 0) return 0;
+        if (vy < v0y) dist = -dist;
+        counter += dist > 0;
+    }
+    return (counter % 2 == 0) ? -1 : 1;
+}
+B2A_HD bool quad_inside_quad(const float *inner, const float *outer)
+{
+    return point_in_quad(outer, inner[0], inner[1]) >= 0 && point_in_quad(outer, inner[2], inner[3]) >= 0 &&
+           point_in_quad(outer, inner[4], inner[5]) >= 0 && point_in_quad(outer, inner[6], inner[7]) >= 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A7 arithmetic: getPerspectiveTransform (8x8 LU, partial pivoting, double, no FMA contraction),
+// closed-form 3x3 inverse, nearest-neighbour source coordinates, Otsu scan.
+// ---------------------------------------------------------------------------------------------
+B2A_HD double d_mul(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+B2A_HD double d_add(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+B2A_HD double d_sub(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+B2A_HD double d_div(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+
+// src quad -> [0,S-1]^2 ; writes the INVERSE map M (dst -> src) used by the warp
+B2A_HD void perspective_inverse(const float *src, int S, double *M)
+{
+    double A[8][8], b[8];
+    const float fs = (float)S - 1.f;
+    const float dstx[4] = {0.f, fs, fs, 0.f}, dsty[4] = {0.f, 0.f, fs, fs};
+    for (int i = 0; i < 8; ++i) for (int j = 0; j < 8; ++j) A[i][j] = 0.0;
+    for (int i = 0; i < 4; ++i) {
+        double sx = src[2 * i], sy = src[2 * i + 1], dx = dstx[i], dy = dsty[i];
+        A[i][0] = A[i + 4][3] = sx;
+        A[i][1] = A[i + 4][4] = sy;
+        A[i][2] = A[i + 4][5] = 1.0;
+        A[i][6] = d_mul(-sx, dx); A[i][7] = d_mul(-sy, dx);
+        A[i + 4][6] = d_mul(-sx, dy); A[i + 4][7] = d_mul(-sy, dy);
+        b[i] = dx; b[i + 4] = dy;
+    }
+    for (int i = 0; i < 8; ++i) {
+        int k = i;
+        for (int j = i + 1; j < 8; ++j) if (fabs(A[j][i]) > fabs(A[k][i])) k = j;
+        if (k != i) {
+            for (int j = i; j < 8; ++j) { double t = A[i][j]; A[i][j] = A[k][j]; A[k][j] = t; }
+            double t = b[i]; b[i] = b[k]; b[k] = t;
+        }
+        double d = d_div(-1.0, A[i][i]);
+        for (int j = i + 1; j < 8; ++j) {
+            double alpha = d_mul(A[j][i], d);
+            for (int kk = i + 1; kk < 8; ++kk) A[j][kk] = d_add(A[j][kk], d_mul(alpha, A[i][kk]));
+            b[j] = d_add(b[j], d_mul(alpha, b[i]));
+        }
+    }
+    for (int i = 7; i >= 0; --i) {
+        double s = b[i];
+        for (int k = i + 1; k < 8; ++k) s = d_sub(s, d_mul(A[i][k], b[k]));
+        b[i] = d_div(s, A[i][i]);
+    }
+    const double a0 = b[0], a1 = b[1], a2 = b[2], a3 = b[3], a4 = b[4], a5 = b[5], a6 = b[6], a7 = b[7], a8 = 1.0;
+    double det = d_add(d_sub(d_mul(a0, d_sub(d_mul(a4, a8), d_mul(a5, a7))), d_mul(a1, d_sub(d_mul(a3, a8), d_mul(a5, a6)))),
+                       d_mul(a2, d_sub(d_mul(a3, a7), d_mul(a4, a6))));
+    det = d_div(1.0, det);
+    M[0] = d_mul(d_sub(d_mul(a4, a8), d_mul(a5, a7)), det);
+    M[1] = d_mul(d_sub(d_mul(a2, a7), d_mul(a1, a8)), det);
+    M[2] = d_mul(d_sub(d_mul(a1, a5), d_mul(a2, a4)), det);
+    M[3] = d_mul(d_sub(d_mul(a5, a6), d_mul(a3, a8)), det);
+    M[4] = d_mul(d_sub(d_mul(a0, a8), d_mul(a2, a6)), det);
+    M[5] = d_mul(d_sub(d_mul(a2, a3), d_mul(a0, a5)), det);
+    M[6] = d_mul(d_sub(d_mul(a3, a7), d_mul(a4, a6)), det);
+    M[7] = d_mul(d_sub(d_mul(a1, a6), d_mul(a0, a7)), det);
+    M[8] = d_mul(d_sub(d_mul(a0, a4), d_mul(a1, a3)), det);
+}
+// source pixel of destination (x,y) under INTER_NEAREST (round half to even); returns 0 outside
+B2A_HD unsigned warp_sample(const uint8_t *__restrict__ gray, int W, int H, size_t pitch, const double *M, int x, int y)
+{
+    const double X0 = d_add(d_mul(M[1], (double)y), M[2]);
+    const double Y0 = d_add(d_mul(M[4], (double)y), M[5]);
+    const double W0 = d_add(d_mul(M[7], (double)y), M[8]);
+    double w = d_add(W0, d_mul(M[6], (double)x));
+    w = (w != 0.0) ? d_div(1.0, w) : 0.0;
+    double fx = d_mul(d_add(X0, d_mul(M[0], (double)x)), w);
+    double fy = d_mul(d_add(Y0, d_mul(M[3], (double)x)), w);
+    fx = fx < -2147483648.0 ? -2147483648.0 : (fx > 2147483647.0 ? 2147483647.0 : fx);
+    fy = fy < -2147483648.0 ? -2147483648.0 : (fy > 2147483647.0 ? 2147483647.0 : fy);
+    const long long X = (long long)rint(fx), Y = (long long)rint(fy);
+    return (X >= 0 && X < W && Y >= 0 && Y < H) ? gray[(size_t)Y * pitch + (size_t)X] : 0u;
+}
+// OpenCV's Otsu between-class-variance scan over a 256-bin histogram of n samples
+B2A_HD int otsu_threshold(const int *h, int n)
+{
+    double mu = 0, scale = d_div(1.0, (double)n);
+    for (int i = 0; i < 256; ++i) mu = d_add(mu, d_mul((double)i, (double)h[i]));
+    mu = d_mul(mu, scale);
+    double mu1 = 0, q1 = 0, max_sigma = 0;
+    int max_val = 0;
+    for (int i = 0; i < 256; ++i) {
+        double p_i = d_mul((double)h[i], scale);
+        mu1 = d_mul(mu1, q1);
+        q1 = d_add(q1, p_i);
+        double q2 = d_sub(1.0, q1);
+        double mn = q1 < q2 ? q1 : q2, mx = q1 > q2 ? q1 : q2;
+        if (mn < (double)FLT_EPSILON || mx > 1.0 - (double)FLT_EPSILON) continue;
+        mu1 = d_div(d_add(mu1, d_mul((double)i, p_i)), q1);
+        double mu2 = d_div(d_sub(mu, d_mul(q1, mu1)), q2);
+        double dm = d_sub(mu1, mu2);
+        double sigma = d_mul(d_mul(d_mul(q1, q2), dm), dm);
+        if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+    }
+    return max_val;
+}
+
+// ---- A7 glue shared by k_identify and the host emulation ----
+// mode: 0 / 1 = every bit is 0 / 1 (flat patch), 2 = Otsu threshold thr
+B2A_HD void ident_decide(long long sum, long long sq, int S, int m0, double minOtsuStdDev, const int *hist, int &mode, int &thr)
+{
+    const int cnt = (S - 2 * m0) * (S - 2 * m0);
+    const double scale = d_div(1.0, (double)cnt);
+    const double mean = d_mul((double)sum, scale);
+    double var = d_sub(d_mul((double)sq, scale), d_mul(mean, mean));
+    if (var < 0) var = 0;
+    const double sd = sqrt(var);
+    thr = 0;
+    if (sd < minOtsuStdDev) mode = (mean > 127.0) ? 1 : 0;
+    else { mode = 2; thr = otsu_threshold(hist, S * S); }
+}
+B2A_HD int ident_cell_bit(const uint8_t *patch, int S, int cellSize, int cellMargin, int cy, int cx, int thr)
+{
+    const int cw = cellSize - 2 * cellMargin;
+    int nz = 0;
+    for (int yy = 0; yy < cw; ++yy)
+        for (int xx = 0; xx < cw; ++xx)
+            nz += patch[(cy * cellSize + cellMargin + yy) * S + cx * cellSize + cellMargin + xx] > thr;
+    return nz > (cw * cw) / 2;
+}
+// border check + code word (byte k of the cv2 byte list in bits 8k..8k+7); false = border wrong
+B2A_HD bool ident_border_code(const uint8_t *bits, int markerSize, int bb, int maxBorderErr, unsigned long long &code)
+{
+    const int nb = markerSize + 2 * bb;
+    int err = 0;
+    for (int y = 0; y < nb; ++y) for (int k = 0; k < bb; ++k) { err += bits[y * nb + k] != 0; err += bits[y * nb + nb - 1 - k] != 0; }
+    for (int x = bb; x < nb - bb; ++x) for (int k = 0; k < bb; ++k) { err += bits[k * nb + x] != 0; err += bits[(nb - 1 - k) * nb + x] != 0; }
+    code = 0;
+    const int ms = markerSize, nbits = ms * ms, nby = (nbits + 7) / 8;
+    for (int i = 0; i < nbits; ++i) {
+        const int y = i / ms, x = i - y * ms, byte = i >> 3;
+        const int shift = (byte == nby - 1 && (nbits & 7)) ? ((nbits & 7) - 1 - (i & 7)) : (7 - (i & 7));
+        code |= (unsigned long long)bits[(y + bb) * nb + x + bb] << (8 * byte + shift);
+    }
+    return err <= maxBorderErr;
+}
+// smallest Hamming distance of marker m over its 4 rotations (first minimum wins)
+B2A_HD int ident_marker_distance(const unsigned long long *dict4, unsigned long long code, int markerSize, int &rot)
+{
+    int best = markerSize * markerSize + 1;
+    rot = -1;
+    for (int r = 0; r < 4; ++r) { const int hd = popc64(dict4[r] ^ code); if (hd < best) { best = hd; rot = r; } }
+    return best;
+}
+
+}  // namespace b2a

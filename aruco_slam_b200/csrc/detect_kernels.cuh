@@ -1,0 +1,617 @@
+// detect_kernels.cuh -- hand-written sm_100a kernels of the detect path (one batch of frames
+// per launch).  Replaces the inside of cv::aruco::detectMarkers (reference
+// src/aruco_slam.cpp:313); stage letters follow SURVEY.md Appendix A.
+//
+//   k_bgr2gray        A1   bgr8 -> gray (15-bit fixed point)
+//   k_threshold       A2   gray -> nScales bit-packed adaptive-threshold masks, one pass, shared-memory
+//                          staged row-prefix tile, ballot-packed output
+//   k_starts          A3a  word-parallel search for border start candidates on the packed masks
+//   k_walk_count      A3a  bidirectional border walks: canonical start test + border length
+//   k_sort_scan       A3a  per (frame,scale): order kept borders like cv2.findContours, offsets
+//   k_walk_write      A3a  emit border points
+//   k_approx          A3b  warp-cooperative approxPolyDP + quad gates
+//   k_group           A4-5 per frame: grouping / selection / hierarchy (frame_logic.h)
+//   k_identify        A7   per candidate: homography, NN warp, Otsu, bits, dictionary match
+//   k_finalize        A6   per frame: depth-ordered acceptance, output
+//   k_subpix          A8   optional cornerSubPix
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "core.h"
+#include "frame_logic.h"
+
+namespace b2a {
+
+constexpr int MAX_SCALES = 8;
+constexpr int R_MAX = 15;           // largest supported threshold window radius (window 31)
+constexpr int SORT_CAP = 4096;      // largest survivors-per-(frame,scale) the sort kernel handles
+
+struct DetGeom {
+    int W, H, B, nScales;
+    int radius[MAX_SCALES];
+    int Cfloor;                     // floor(adaptiveThreshConstant)
+    int WW, PWW;                    // mask words per row, padded pitch (WW + 2)
+    long long mask_plane;           // words per (frame,scale) mask plane = PWW * (H + 2)
+    int KS;                         // key stride (W + 1)
+    int minPerim, maxPerim, maxWH;
+    double approxRate, minCornerDistRate;
+    int surv_cap, pts_cap;
+    unsigned starts_cap;
+};
+
+// ---------------------------------------------------------------------------------------------
+// A1
+// ---------------------------------------------------------------------------------------------
+__global__ void k_bgr2gray(const uint8_t *__restrict__ bgr, size_t in_pitch, size_t in_frame,
+                           uint8_t *__restrict__ gray, size_t out_pitch, size_t out_frame, int W, int H, int B)
+{
+    const long long total = (long long)B * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        const long long t = i / W;
+        const int y = (int)(t % H), b = (int)(t / H);
+        const uint8_t *p = bgr + (size_t)b * in_frame + (size_t)y * in_pitch + (size_t)x * 3;
+        const int v = (3735 * (int)p[0] + 19235 * (int)p[1] + 9798 * (int)p[2] + 16384) >> 15;
+        gray[(size_t)b * out_frame + (size_t)y * out_pitch + x] = (uint8_t)v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A2: adaptive threshold, all scales in one pass.
+//   tile = TW x TH output pixels; shared memory holds the replicate-clamped input tile (halo
+//   R_MAX + 1) and its per-row exclusive prefix sums E (u16).  Thread (column c, half h) slides
+//   the three vertical window sums down its half of the rows; a box sum is
+//   sum_rows (E[row][x + r + 1] - E[row][x - r]).  mask bit:  g - mean <= -C  with
+//   mean = (2 S + k^2) div (2 k^2)   <=>   2 S >= (2 (g + C) - 1) k^2      (exact integers).
+//   The 32 lanes of a warp hold 32 neighbouring columns: one ballot = one packed mask word.
+// ---------------------------------------------------------------------------------------------
+constexpr int TH_TW = 128, TH_TH = 64, TH_HALO = 16;
+constexpr int TH_COLS = TH_TW + 2 * TH_HALO;          // 160
+constexpr int TH_ROWS = TH_TH + 2 * R_MAX;            // 94
+constexpr int TH_EPITCH = TH_COLS + 2;                // 162 (161 used)
+constexpr int TH_THREADS = 256;
+
+__global__ void __launch_bounds__(TH_THREADS)
+k_threshold(const uint8_t *__restrict__ gray, size_t pitch, size_t frame_stride, uint32_t *__restrict__ masks, DetGeom g)
+{
+    __shared__ __align__(16) uint8_t s_in[TH_ROWS][TH_COLS];
+    __shared__ uint16_t s_E[TH_ROWS + 1][TH_EPITCH];   // +1: the last slide reads one row past the tile (unused)
+
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * TH_TW, y0 = blockIdx.y * TH_TH;
+    const uint8_t *src = gray + (size_t)b * frame_stride;
+    const int tid = threadIdx.x;
+
+    // ---- load the clamped tile ----
+    const bool fast = (x0 - TH_HALO >= 0) && (x0 + TH_TW + TH_HALO <= g.W) && ((pitch & 15) == 0) &&
+                      ((((size_t)src) & 15) == 0);
+    if (fast) {
+        for (int t = tid; t < TH_ROWS * (TH_COLS / 16); t += TH_THREADS) {
+            const int r = t / (TH_COLS / 16), c16 = t - r * (TH_COLS / 16);
+            int gy = y0 - R_MAX + r; gy = gy < 0 ? 0 : (gy >= g.H ? g.H - 1 : gy);
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)gy * pitch + (x0 - TH_HALO)) + c16);
+            *reinterpret_cast<uint4 *>(&s_in[r][c16 * 16]) = v;
+        }
+    } else {
+        for (int t = tid; t < TH_ROWS * TH_COLS; t += TH_THREADS) {
+            const int r = t / TH_COLS, c = t - r * TH_COLS;
+            int gy = y0 - R_MAX + r; gy = gy < 0 ? 0 : (gy >= g.H ? g.H - 1 : gy);
+            int gx = x0 - TH_HALO + c; gx = gx < 0 ? 0 : (gx >= g.W ? g.W - 1 : gx);
+            s_in[r][c] = __ldg(src + (size_t)gy * pitch + gx);
+        }
+    }
+    __syncthreads();
+
+    // ---- per-row exclusive prefix sums (one warp per row, 5 bytes per lane) ----
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int r = warp; r < TH_ROWS; r += TH_THREADS / 32) {
+        unsigned v[5], s = 0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { v[i] = s_in[r][lane * 5 + i]; s += v[i]; }
+        unsigned incl = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
+        unsigned run = incl - s;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { s_E[r][lane * 5 + i] = (uint16_t)run; run += v[i]; }
+        if (lane == 31) s_E[r][TH_COLS] = (uint16_t)run;
+    }
+    __syncthreads();
+
+    // ---- vertical sliding sums, compare, ballot ----
+    const int c = tid & (TH_TW - 1), half = tid >> 7;             // 128 columns x 2 halves
+    const int xo = TH_HALO + c;                                   // tile column of the output pixel
+    const int j0 = half * (TH_TH / 2);                            // first output row of this thread
+    const int gx = x0 + c;
+    const bool col_ok = gx < g.W;
+    unsigned V[MAX_SCALES];
+    int rhs_mul[MAX_SCALES];
+#pragma unroll
+    for (int s = 0; s < MAX_SCALES; ++s) {
+        if (s < g.nScales) {
+            const int r = g.radius[s];
+            unsigned acc = 0;
+            for (int dy = -r; dy <= r; ++dy) acc += (unsigned)s_E[R_MAX + j0 + dy][xo + r + 1] - (unsigned)s_E[R_MAX + j0 + dy][xo - r];
+            V[s] = acc;
+            rhs_mul[s] = (2 * r + 1) * (2 * r + 1);
+        }
+    }
+    const int wi = (x0 >> 5) + (c >> 5) + 1;                      // padded word index of this warp's 32 columns
+    for (int j = j0; j < j0 + TH_TH / 2; ++j) {
+        const int gy = y0 + j;
+        const int gv = s_in[R_MAX + j][xo];
+        const bool ok = col_ok && gy < g.H;
+#pragma unroll
+        for (int s = 0; s < MAX_SCALES; ++s) {
+            if (s < g.nScales) {
+                const int r = g.radius[s];
+                const long long rhs = (long long)(2 * (gv + g.Cfloor) - 1) * rhs_mul[s];
+                const bool bit = ok && ((long long)(2u * V[s]) >= rhs);
+                const unsigned word = __ballot_sync(0xFFFFFFFFu, bit);
+                if (lane == 0 && gy < g.H && wi <= g.WW)
+                    masks[((size_t)b * g.nScales + s) * g.mask_plane + (size_t)(gy + 1) * g.PWW + wi] = word;
+                // slide to row j + 1
+                V[s] += ((unsigned)s_E[R_MAX + j + 1 + r][xo + r + 1] - (unsigned)s_E[R_MAX + j + 1 + r][xo - r])
+                      - ((unsigned)s_E[R_MAX + j - r][xo + r + 1] - (unsigned)s_E[R_MAX + j - r][xo - r]);
+            }
+        }
+    }
+}
+
+// expand packed masks to 0/255 bytes (debug / parity tap)
+__global__ void k_unpack_masks(const uint32_t *__restrict__ masks, uint8_t *__restrict__ out, DetGeom g)
+{
+    const long long total = (long long)g.B * g.nScales * g.H * g.W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % g.W);
+        long long t = i / g.W;
+        const int y = (int)(t % g.H);
+        t /= g.H;                                             // frame * nScales + scale
+        const uint32_t w = masks[(size_t)t * g.mask_plane + (size_t)(y + 1) * g.PWW + (x >> 5) + 1];
+        out[i] = ((w >> (x & 31)) & 1u) ? 255 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A3a step 1: start candidates, 32 pixels per thread with word-level logic.
+//   outer start: pixel set, W / NW / N / NE clear, at least one other neighbour
+//   hole  start: pixel set, E clear, NE set
+// entries: .x = (frame*nScales+scale) << 1 | type, .y = x | y << 16
+// ---------------------------------------------------------------------------------------------
+__global__ void k_starts(const uint32_t *__restrict__ masks, uint2 *__restrict__ starts, unsigned *__restrict__ n_starts,
+                         int *__restrict__ iso_count, DetGeom g)
+{
+    const long long words_per_plane = (long long)g.H * g.WW;
+    const long long total = (long long)g.B * g.nScales * words_per_plane;
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // all lanes of a warp run the same number of iterations (warp-aggregated append below)
+    const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (long long i0 = first - lane; i0 < total; i0 += stride) {
+        const long long i = i0 + lane;
+        unsigned outer = 0, hole = 0;
+        int fs = 0, y = 0, wx = 0;
+        if (i < total) {
+            fs = (int)(i / words_per_plane);
+            const long long rem = i - (long long)fs * words_per_plane;
+            y = (int)(rem / g.WW); wx = (int)(rem - (long long)y * g.WW);
+            const uint32_t *row = masks + (size_t)fs * g.mask_plane + (size_t)(y + 1) * g.PWW + wx + 1;
+            const uint32_t m = __ldg(row);
+            if (m) {
+                const uint32_t ml = __ldg(row - 1), mr = __ldg(row + 1);
+                const uint32_t u = __ldg(row - g.PWW), ul = __ldg(row - g.PWW - 1), ur = __ldg(row - g.PWW + 1);
+                const uint32_t d = __ldg(row + g.PWW), dl = __ldg(row + g.PWW - 1), dr = __ldg(row + g.PWW + 1);
+                uint32_t iso;
+                start_candidate_words(m, ml, mr, u, ul, ur, d, dl, dr, outer, hole, iso);
+                if (iso) atomicAdd(&iso_count[fs], __popc(iso));
+            }
+        }
+        const int cnt = __popc(outer) + __popc(hole);
+        int incl = cnt;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) { const int o = __shfl_up_sync(0xFFFFFFFFu, incl, dd); if (lane >= dd) incl += o; }
+        const int tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (tot == 0) continue;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(n_starts, (unsigned)tot);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        unsigned pos = base + (unsigned)(incl - cnt);
+        while (outer) {
+            const int bpos = __ffs(outer) - 1; outer &= outer - 1;
+            if (pos < g.starts_cap) starts[pos] = make_uint2((unsigned)fs << 1, (unsigned)(wx * 32 + bpos) | ((unsigned)y << 16));
+            ++pos;
+        }
+        while (hole) {
+            const int bpos = __ffs(hole) - 1; hole &= hole - 1;
+            if (pos < g.starts_cap) starts[pos] = make_uint2(((unsigned)fs << 1) | 1u, (unsigned)(wx * 32 + bpos) | ((unsigned)y << 16));
+            ++pos;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A3a step 2: one thread per start candidate walks its border both ways.
+//   surv[(fs)*surv_cap + slot] = (key, length, x | y<<16, 0)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_walk_count(const uint32_t *__restrict__ masks, const uint2 *__restrict__ starts,
+                             const unsigned *__restrict__ n_starts, uint4 *__restrict__ surv, int *__restrict__ surv_count,
+                             int *__restrict__ contour_count, int max_len, DetGeom g)
+{
+    unsigned n = *n_starts;
+    if (n > g.starts_cap) n = g.starts_cap;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint2 e = starts[i];
+        const int fs = (int)(e.x >> 1), type = (int)(e.x & 1u);
+        const int x = (int)(e.y & 0xFFFFu), y = (int)(e.y >> 16);
+        MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
+        const unsigned c0 = rd(x, y);
+        int s0; uint32_t key0;
+        if (!start_state(c0, x, y, type, g.KS, s0, key0)) continue;
+        const int len = walk_count(rd, g.KS - 1, x, y, s0, key0, max_len);
+        if (len > 0) {
+            atomicAdd(&contour_count[fs], 1);
+            if (len >= g.minPerim && len <= g.maxPerim) {
+                const int slot = atomicAdd(&surv_count[fs], 1);
+                if (slot < g.surv_cap) surv[(size_t)fs * g.surv_cap + slot] = make_uint4(key0, (unsigned)len, e.y, (unsigned)s0);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A3a step 3: per (frame,scale) sort the kept borders by start key, descending (= the order of
+// cv2.findContours' list) and assign point offsets.  One CTA per (frame,scale).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_sort_scan(const uint4 *__restrict__ surv, int *__restrict__ surv_count, uint4 *__restrict__ sorted,
+            int *__restrict__ pts_off, int *__restrict__ status, DetGeom g)
+{
+    __shared__ uint32_t s_key[SORT_CAP];
+    __shared__ uint16_t s_idx[SORT_CAP];
+    __shared__ int s_scan[SORT_CAP];
+    const int fs = blockIdx.x;
+    int n = surv_count[fs];
+    if (n > g.surv_cap) { n = g.surv_cap; if (threadIdx.x == 0) status[fs / g.nScales] = 3; }
+    int N = 32; while (N < n) N <<= 1;
+    const uint4 *in = surv + (size_t)fs * g.surv_cap;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        s_key[i] = (i < n) ? ~in[i].x : 0xFFFFFFFFu;      // ascending sort of ~key == descending key; pads last
+        s_idx[i] = (uint16_t)i;
+    }
+    __syncthreads();
+    for (int k = 2; k <= N; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < N; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool up = (i & k) == 0;
+                    const uint32_t a = s_key[i], b = s_key[ixj];
+                    if ((a > b) == up) { s_key[i] = b; s_key[ixj] = a; const uint16_t t = s_idx[i]; s_idx[i] = s_idx[ixj]; s_idx[ixj] = t; }
+                }
+            }
+            __syncthreads();
+        }
+    uint4 *out = sorted + (size_t)fs * g.surv_cap;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        int len = 0;
+        if (i < n) { const uint4 e = in[s_idx[i]]; out[i] = e; len = (int)e.y; }
+        s_scan[i] = len;
+    }
+    __syncthreads();
+    for (int d = 1; d < N; d <<= 1) {                 // inclusive Hillis-Steele scan
+        int v[SORT_CAP / 1024];
+        int k = 0;
+        for (int i = threadIdx.x; i < N; i += blockDim.x, ++k) v[k] = (i >= d) ? s_scan[i - d] : 0;
+        __syncthreads();
+        k = 0;
+        for (int i = threadIdx.x; i < N; i += blockDim.x, ++k) s_scan[i] += v[k];
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int len = (int)out[i].y;
+        const int off = s_scan[i] - len;
+        const bool fits = off + len <= g.pts_cap;
+        pts_off[(size_t)fs * g.surv_cap + i] = fits ? off : -1;
+        if (!fits) status[fs / g.nScales] = 3;
+    }
+    if (threadIdx.x == 0) surv_count[fs] = n;
+}
+
+// A3a step 4: emit the border points of the kept borders
+__global__ void k_walk_write(const uint32_t *__restrict__ masks, const uint4 *__restrict__ sorted, const int *__restrict__ surv_count,
+                             const int *__restrict__ pts_off, uint32_t *__restrict__ pts, DetGeom g)
+{
+    const int fs = blockIdx.y;
+    const int n = surv_count[fs];
+    MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int off = pts_off[(size_t)fs * g.surv_cap + i];
+        if (off < 0) continue;
+        const uint4 e = sorted[(size_t)fs * g.surv_cap + i];
+        walk_write(rd, (int)(e.z & 0xFFFFu), (int)(e.z >> 16), (int)e.w, (int)e.y, pts + (size_t)fs * g.pts_cap + off);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A3b: one warp per kept border
+// ---------------------------------------------------------------------------------------------
+struct WarpLanes {
+    __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+    __device__ __forceinline__ int nlanes() const { return 32; }
+    __device__ __forceinline__ void argmax_first(long long &d, int &pos) const
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const long long od = __shfl_xor_sync(0xFFFFFFFFu, d, o);
+            const int op = __shfl_xor_sync(0xFFFFFFFFu, pos, o);
+            if (od > d || (od == d && op < pos)) { d = od; pos = op; }
+        }
+    }
+};
+
+__global__ void k_approx(const uint4 *__restrict__ sorted, const int *__restrict__ surv_count, const int *__restrict__ pts_off,
+                         const uint32_t *__restrict__ pts, uint8_t *__restrict__ quad_ok, int32_t *__restrict__ quad_xy,
+                         int32_t *__restrict__ quad_len, DetGeom g)
+{
+    const int fs = blockIdx.y;
+    const int n = surv_count[fs];
+    const int warps_per_block = blockDim.x >> 5;
+    WarpLanes lg;
+    for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_block) {
+        const size_t slot = (size_t)fs * g.surv_cap + i;
+        const int off = pts_off[slot];
+        const int len = (int)sorted[slot].y;
+        bool ok = false;
+        int ox[8], oy[8];
+        if (off >= 0) {
+            const int m = approx_closed(lg, pts + (size_t)fs * g.pts_cap + off, len, (double)len * g.approxRate, ox, oy);
+            ok = (m == 4) && quad_passes(ox, oy, m, len, g.maxWH, g.minCornerDistRate);
+        }
+        if (lg.lane() == 0) {
+            quad_ok[slot] = ok ? 1 : 0;
+            quad_len[slot] = len;
+            if (ok) for (int k = 0; k < 4; ++k) { quad_xy[slot * 8 + 2 * k] = ox[k]; quad_xy[slot * 8 + 2 * k + 1] = oy[k]; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-frame stages
+// ---------------------------------------------------------------------------------------------
+struct BlockCtx {
+    int *s_warp;   // [33] shared scratch
+    __device__ __forceinline__ int tid() const { return threadIdx.x; }
+    __device__ __forceinline__ int nthreads() const { return blockDim.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ int exclusive_scan(int flag, int &total) const
+    {
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, flag != 0);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, tot = 0;
+        for (int w = 0; w < nw; ++w) { const int v = s_warp[w]; tot += v; if (w < warp) before += v; }
+        __syncthreads();
+        total = tot;
+        return before + __popc(m & ((1u << lane) - 1u));
+    }
+};
+
+struct FrameArrays {             // device base pointers; frame f uses offset f * (per-frame size)
+    FrameScratch fs0;            // pointers of frame 0
+    FrameOutputs fo0;
+    const int32_t *surv_count;   // [B*nScales]
+    const uint8_t *quad_ok;      // [B*nScales*surv_cap]
+    const int32_t *quad_xy;
+    const int32_t *quad_len;
+};
+
+__device__ __forceinline__ FrameScratch frame_scratch(const FrameScratch &b, int f, int mc)
+{
+    FrameScratch s = b;
+    const size_t o = (size_t)f * mc;
+    s.cq += o * 8; s.clen += o; s.tq += o * 8; s.tper += o; s.gid += o; s.sel += o;
+    s.gstart += (size_t)f * (mc + 1); s.gfill += o; s.members += o; s.closeIdx += o; s.closeCnt += o;
+    s.S += o; s.parent += o; s.depth += o; s.selGroup += o;
+    s.closeM += o * (size_t)((mc + 31) / 32);
+    s.wq += o * 8; s.wres += o; s.closeStart += o; s.closeNum += o;
+    s.counters += (size_t)f * 8;
+    return s;
+}
+
+__global__ void __launch_bounds__(256)
+k_group(FrameArrays fa, FrameParams fp, int smem_words)
+{
+    extern __shared__ uint32_t s_M[];
+    __shared__ int s_warp[33];
+    const int f = blockIdx.x;
+    BlockCtx ctx{s_warp};
+    const FrameScratch fs = frame_scratch(fa.fs0, f, fp.max_cand);
+    ScaleQuads sq;
+    sq.count = fa.surv_count + (size_t)f * fp.nScales;
+    sq.quad_ok = fa.quad_ok + (size_t)f * fp.nScales * fp.surv_cap;
+    sq.quad_xy = fa.quad_xy + (size_t)f * fp.nScales * fp.surv_cap * 8;
+    sq.len = fa.quad_len + (size_t)f * fp.nScales * fp.surv_cap;
+    frame_group(ctx, fp, sq, fs, s_M, smem_words);
+}
+
+__global__ void k_finalize(FrameArrays fa, FrameParams fp)
+{
+    __shared__ int s_warp[33];
+    const int f = blockIdx.x;
+    BlockCtx ctx{s_warp};
+    const FrameScratch fs = frame_scratch(fa.fs0, f, fp.max_cand);
+    FrameOutputs fo = fa.fo0;
+    fo.n_accepted += f; fo.n_rejected += f; fo.status += f;
+    fo.corners += (size_t)f * fp.max_markers * 8; fo.ids += (size_t)f * fp.max_markers; fo.rejected += (size_t)f * fp.max_markers * 8;
+    frame_finalize(ctx, fp, fs, fo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// A7: one CTA per identification work item
+// ---------------------------------------------------------------------------------------------
+struct IdentParams {
+    int markerSize, borderBits, cellSize, cellMargin;
+    int nMarkers, maxCorr, maxBorderErr;
+    double minOtsuStdDev;
+    int W, H;
+    size_t pitch, frame_stride;
+    int max_cand;
+};
+
+constexpr int ID_THREADS = 128;
+constexpr int ID_MAX_S = 9 * 8;     // (7 + 2) cells * up to 8 px
+
+__global__ void __launch_bounds__(ID_THREADS)
+k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restrict__ dict, FrameArrays fa, IdentParams ip)
+{
+    __shared__ double s_M[9];
+    __shared__ uint8_t s_patch[ID_MAX_S * ID_MAX_S];
+    __shared__ int s_hist[256];
+    __shared__ int s_sum, s_sq, s_thr, s_mode, s_best;
+    __shared__ unsigned long long s_code;
+    __shared__ uint8_t s_bits[81];
+
+    const int f = blockIdx.y;
+    const int *counters = fa.fs0.counters + (size_t)f * 8;
+    const int nw = counters[FC_NWORK];
+    const int nb = ip.markerSize + 2 * ip.borderBits;
+    const int S = nb * ip.cellSize;
+    const int tid = threadIdx.x;
+    const uint8_t *img = gray + (size_t)f * ip.frame_stride;
+    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+        const float *corners = fa.fs0.wq + ((size_t)f * ip.max_cand + w) * 8;
+        if (tid == 0) { perspective_inverse(corners, S, s_M); s_sum = 0; s_sq = 0; s_best = 0x7FFFFFFF; }
+        for (int i = tid; i < 256; i += ID_THREADS) s_hist[i] = 0;
+        __syncthreads();
+        double M[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) M[i] = s_M[i];
+        const int m0 = ip.cellSize / 2;
+        int ls = 0, lq = 0;
+        for (int p = tid; p < S * S; p += ID_THREADS) {
+            const int y = p / S, x = p - y * S;
+            const unsigned v = warp_sample(img, ip.W, ip.H, ip.pitch, M, x, y);
+            s_patch[p] = (uint8_t)v;
+            atomicAdd(&s_hist[v], 1);
+            if (x >= m0 && x < S - m0 && y >= m0 && y < S - m0) { ls += (int)v; lq += (int)(v * v); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { ls += __shfl_xor_sync(0xFFFFFFFFu, ls, o); lq += __shfl_xor_sync(0xFFFFFFFFu, lq, o); }
+        if ((tid & 31) == 0) { atomicAdd(&s_sum, ls); atomicAdd(&s_sq, lq); }
+        __syncthreads();
+        if (tid == 0) { int mode, thr; ident_decide(s_sum, s_sq, S, m0, ip.minOtsuStdDev, s_hist, mode, thr); s_mode = mode; s_thr = thr; }
+        __syncthreads();
+        for (int cidx = tid; cidx < nb * nb; cidx += ID_THREADS) {
+            const int cy = cidx / nb, cx = cidx - cy * nb;
+            s_bits[cidx] = (uint8_t)((s_mode < 2) ? s_mode : ident_cell_bit(s_patch, S, ip.cellSize, ip.cellMargin, cy, cx, s_thr));
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long code;
+            const bool ok = ident_border_code(s_bits, ip.markerSize, ip.borderBits, ip.maxBorderErr, code);
+            s_code = code;
+            s_mode = ok ? 0 : -1;
+        }
+        __syncthreads();
+        if (s_mode == 0) {
+            const unsigned long long code = s_code;
+            for (int m = tid; m < ip.nMarkers; m += ID_THREADS) {
+                int rot;
+                if (ident_marker_distance(dict + (size_t)m * 4, code, ip.markerSize, rot) <= ip.maxCorr) { atomicMin(&s_best, m); break; }   // later m of this thread are larger
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int res = 0;
+            if (s_mode == 0 && s_best != 0x7FFFFFFF) {
+                const int m = s_best;
+                int rot;
+                ident_marker_distance(dict + (size_t)m * 4, s_code, ip.markerSize, rot);
+                res = (int)(0x80000000u | ((unsigned)m << 8) | (unsigned)rot);
+            }
+            fa.fs0.wres[(size_t)f * ip.max_cand + w] = res;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A8: cornerSubPix on the accepted corners (one thread per corner)
+// ---------------------------------------------------------------------------------------------
+struct SubpixParams {
+    int W, H; size_t pitch, frame_stride;
+    int max_markers, markerSize, borderBits, maxWin, maxIter;
+    double relWin, eps;
+};
+
+__device__ __forceinline__ float subpix_sample(const uint8_t *img, int W, int H, size_t pitch, int ipx, int ipy, float a11, float a12, float a21, float a22, int x, int y)
+{
+    int x0 = ipx + x, x1 = x0 + 1, y0 = ipy + y, y1 = y0 + 1;
+    x0 = x0 < 0 ? 0 : (x0 >= W ? W - 1 : x0); x1 = x1 < 0 ? 0 : (x1 >= W ? W - 1 : x1);
+    y0 = y0 < 0 ? 0 : (y0 >= H ? H - 1 : y0); y1 = y1 < 0 ? 0 : (y1 >= H ? H - 1 : y1);
+    return f_add(f_add(f_add(f_mul((float)img[y0 * pitch + x0], a11), f_mul((float)img[y0 * pitch + x1], a12)),
+                       f_mul((float)img[y1 * pitch + x0], a21)), f_mul((float)img[y1 * pitch + x1], a22));
+}
+
+__global__ void k_subpix(const uint8_t *__restrict__ gray, const int32_t *__restrict__ n_acc, const float *__restrict__ corners,
+                         float *__restrict__ corners_out, int B, SubpixParams sp)
+{
+    const int total = B * sp.max_markers * 4;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int f = t / (sp.max_markers * 4), r = t - f * sp.max_markers * 4, mk = r >> 2;
+        if (mk >= n_acc[f]) continue;
+        const float *c = corners + ((size_t)f * sp.max_markers + mk) * 8;
+        const float per = quad_perimeter(c);
+        const int nm = sp.markerSize + 2 * sp.borderBits;
+        int win = (int)lroundf((float)sp.relWin * f_div(per, 4.f * (float)nm));
+        win = win < 1 ? 1 : (win > sp.maxWin ? sp.maxWin : win);
+        const uint8_t *img = gray + (size_t)f * sp.frame_stride;
+        const float *pin = corners + ((size_t)f * sp.max_markers + mk) * 8 + (r & 3) * 2;
+        float *pt = corners_out + ((size_t)f * sp.max_markers + mk) * 8 + (r & 3) * 2;
+        const float cTx = pin[0], cTy = pin[1];
+        float cIx = cTx, cIy = cTy;
+        const int ww = 2 * win + 1;
+        const double eps2 = sp.eps * sp.eps;
+        int iter = 0; double err = 0;
+        do {
+            const float fx = cIx - (float)(ww + 1) * 0.5f, fy = cIy - (float)(ww + 1) * 0.5f;   // centre - (ww+2-1)/2
+            const int ipx = (int)floorf(fx), ipy = (int)floorf(fy);
+            const float a = fx - (float)ipx, b = fy - (float)ipy;
+            const float a11 = f_mul(1.f - a, 1.f - b), a12 = f_mul(a, 1.f - b), a21 = f_mul(1.f - a, b), a22 = f_mul(a, b);
+            double A = 0, Bm = 0, C = 0, bb1 = 0, bb2 = 0;
+            for (int i = 0; i < ww; ++i) {
+                const float yy = (float)(i - win) / (float)win;
+                const float my = (float)exp(-(double)(yy * yy));
+                const double py = i - win;
+                for (int j = 0; j < ww; ++j) {
+                    const float xx = (float)(j - win) / (float)win;
+                    const float mx = (float)exp(-(double)(xx * xx));
+                    const double m = (double)f_mul(my, mx);
+                    // subimage index (j+1, i+1) in the (ww+2)^2 patch
+                    const double tgx = (double)subpix_sample(img, sp.W, sp.H, sp.pitch, ipx, ipy, a11, a12, a21, a22, j + 2, i + 1)
+                                     - (double)subpix_sample(img, sp.W, sp.H, sp.pitch, ipx, ipy, a11, a12, a21, a22, j, i + 1);
+                    const double tgy = (double)subpix_sample(img, sp.W, sp.H, sp.pitch, ipx, ipy, a11, a12, a21, a22, j + 1, i + 2)
+                                     - (double)subpix_sample(img, sp.W, sp.H, sp.pitch, ipx, ipy, a11, a12, a21, a22, j + 1, i);
+                    const double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
+                    const double px = j - win;
+                    A += gxx; Bm += gxy; C += gyy;
+                    bb1 += gxx * px + gxy * py;
+                    bb2 += gxy * px + gyy * py;
+                }
+            }
+            const double det = A * C - Bm * Bm;
+            if (fabs(det) <= DBL_EPSILON * DBL_EPSILON) break;
+            const double scale = 1.0 / det;
+            const float nx = (float)((double)cIx + (C * scale * bb1 - Bm * scale * bb2));
+            const float ny = (float)((double)cIy + (-Bm * scale * bb1 + A * scale * bb2));
+            err = (double)((nx - cIx) * (nx - cIx) + (ny - cIy) * (ny - cIy));
+            cIx = nx; cIy = ny;
+            if (cIx < 0 || cIx >= (float)sp.W || cIy < 0 || cIy >= (float)sp.H) break;
+        } while (++iter < sp.maxIter && err > eps2);
+        if (fabsf(cIx - cTx) > (float)win || fabsf(cIy - cTy) > (float)win) { cIx = cTx; cIy = cTy; }
+        pt[0] = cIx; pt[1] = cIy;
+    }
+}
+
+}  // namespace b2a

@@ -1,0 +1,298 @@
+// frame_logic.h -- per-frame (one CTA per frame) stages of the detect path:
+//   frame_group    : candidate gathering, A4 reorder, A5 filterTooCloseCandidates + hierarchy,
+//                    identification work list                       
+//   frame_finalize : A6 depth-ordered acceptance, corner rotation, accepted / rejected output
+// Replaces the corresponding parts of cv::aruco::detectMarkers (reference
+// src/aruco_slam.cpp:313).  Written against a small "Ctx" (tid / nthreads / sync / scan) so
+// that the identical source runs as a CUDA block on the device and as one sequential lane in
+// tests/hostemu (CPU-only logic check against the oracle; test infrastructure only).
+#pragma once
+#include "core.h"
+
+namespace b2a {
+
+struct FrameParams {
+    int W, H;
+    int nScales;
+    int surv_cap;            // capacity of the per-(frame,scale) survivor arrays
+    int max_cand;            // capacity of candidates per frame
+    int max_markers;         // capacity of accepted / rejected per frame
+    int markerSize, borderBits;
+    int minDistanceToBorder;
+    float minMarkerDistanceRate;   // (float)params.minMarkerDistanceRate
+    float minGroupDistance;
+};
+
+// per-(frame,scale) outputs of the contour / polygon stages, in cv2.findContours list order
+struct ScaleQuads {
+    const int32_t *count;        // [nScales]      survivors of this frame
+    const uint8_t *quad_ok;      // [nScales][surv_cap]
+    const int32_t *quad_xy;      // [nScales][surv_cap][8]  x0,y0,...,x3,y3
+    const int32_t *len;          // [nScales][surv_cap]      contour length
+};
+
+// per-frame scratch in global memory (all indexed within the frame)
+struct FrameScratch {
+    float   *cq;        // [max_cand][8] candidate quads in candidate order (after A4)
+    int32_t *clen;      // [max_cand]
+    float   *tq;        // [max_cand][8] quads in T order (sorted by perimeter, descending, stable)
+    float   *tper;      // [max_cand]
+    int32_t *gid;       // [max_cand]
+    int32_t *sel;       // [max_cand]
+    int32_t *gstart;    // [max_cand + 1]
+    int32_t *gfill;     // [max_cand]
+    int32_t *members;   // [max_cand]
+    int32_t *closeIdx;  // [max_cand]  per group segment: T indices of "close" candidates
+    int32_t *closeCnt;  // [max_cand]  per group
+    int32_t *S;         // [max_cand]  selected -> T index
+    int32_t *parent;    // [max_cand]
+    int32_t *depth;     // [max_cand]
+    int32_t *selGroup;  // [max_cand]  selected -> group id or -1
+    uint32_t *closeM;   // [max_cand][max_cand/32] closeness bit matrix (row i: bits j > i), global fallback
+    // identification work list: item w < n_sel is selected candidate w; then the close candidates
+    float   *wq;        // [max_cand][8]
+    int32_t *wres;      // [max_cand]  result: bit 31 valid, bits 8..: id, bits 0..1: rot   (written by identify)
+    int32_t *closeStart;// [max_cand]  selected -> first work item of its close list
+    int32_t *closeNum;  // [max_cand]
+    int32_t *counters;  // [8]: 0 n_cand, 1 n_sel, 2 n_work, 3 status
+};
+
+enum { FC_NCAND = 0, FC_NSEL = 1, FC_NWORK = 2, FC_STATUS = 3 };
+
+// --------------------------------------------------------------------------------------------
+template <class Ctx>
+B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, const FrameScratch &fs,
+                        uint32_t *smemM, int smemM_words)
+{
+    const int tid = ctx.tid(), nt = ctx.nthreads();
+    // ---- 1. gather candidates in reference order (scale by scale, contour list order) + A4 ----
+    int n = 0;
+    for (int s = 0; s < fp.nScales; ++s) {
+        const int cnt = sq.count[s] < fp.surv_cap ? sq.count[s] : fp.surv_cap;
+        for (int base = 0; base < cnt; base += nt) {
+            const int i = base + tid;
+            const int flag = (i < cnt) ? (int)sq.quad_ok[s * fp.surv_cap + i] : 0;
+            int total;
+            const int pos = ctx.exclusive_scan(flag, total);
+            if (flag && n + pos < fp.max_cand) {
+                float *c = fs.cq + (size_t)(n + pos) * 8;
+                const int32_t *q = sq.quad_xy + ((size_t)s * fp.surv_cap + i) * 8;
+                for (int k = 0; k < 8; ++k) c[k] = (float)q[k];
+                quad_make_clockwise(c);
+                fs.clen[n + pos] = sq.len[s * fp.surv_cap + i];
+            }
+            n += total;
+        }
+    }
+    if (n > fp.max_cand) { if (tid == 0) fs.counters[FC_STATUS] = 3; n = fp.max_cand; }
+    ctx.sync();
+    // ---- 2. stable sort by perimeter, descending: rank = #greater + #equal-before ----
+    for (int i = tid; i < n; i += nt) fs.tper[i] = quad_perimeter(fs.cq + (size_t)i * 8);   // tper used as temp (candidate order)
+    ctx.sync();
+    for (int i = tid; i < n; i += nt) {
+        const float p = fs.tper[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) { const float q = fs.tper[j]; rank += (q > p) || (q == p && j < i); }
+        fs.members[i] = rank;       // temp: candidate i -> T position
+    }
+    ctx.sync();
+    for (int i = tid; i < n; i += nt) {
+        const int r = fs.members[i];
+        for (int k = 0; k < 8; ++k) fs.tq[(size_t)r * 8 + k] = fs.cq[(size_t)i * 8 + k];
+        fs.gfill[r] = i;            // temp: T position -> candidate index
+    }
+    ctx.sync();
+    for (int i = tid; i < n; i += nt) { fs.gid[i] = -1; fs.sel[i] = 1; }
+    ctx.sync();
+    for (int i = tid; i < n; i += nt) fs.tper[i] = quad_perimeter(fs.tq + (size_t)i * 8);
+    ctx.sync();
+    // ---- 3. closeness bit matrix: bit j of row i (j > i) iff avgDist(T[i],T[j]) < perimeter_j * rate ----
+    const int wpr = (n + 31) >> 5;
+    uint32_t *M = ((long long)n * wpr <= (long long)smemM_words) ? smemM : fs.closeM;
+    for (int t = tid; t < n * wpr; t += nt) {
+        const int i = t / wpr, w = t - i * wpr;
+        uint32_t bits = 0;
+        if (w * 32 + 31 > i) {
+            const float *a = fs.tq + (size_t)i * 8;
+            const float acx = (a[0] + a[2]) + (a[4] + a[6]), acy = (a[1] + a[3]) + (a[5] + a[7]);   // 4 * centroid
+            for (int b = 0; b < 32; ++b) {
+                const int j = w * 32 + b;
+                if (j <= i || j >= n) continue;
+                const float *q = fs.tq + (size_t)j * 8;
+                const float thr = f_mul(fs.tper[j], fp.minMarkerDistanceRate);
+                // |centroid_a - centroid_b| <= avgDist: cheap exact-safe rejection (integer coordinates)
+                const float dcx = (acx - ((q[0] + q[2]) + (q[4] + q[6]))) * 0.25f, dcy = (acy - ((q[1] + q[3]) + (q[5] + q[7]))) * 0.25f;
+                if (dcx * dcx + dcy * dcy > thr * thr * 1.01f + 1.0f) continue;
+                if (quad_avg_distance(a, q) < thr) bits |= 1u << b;
+            }
+        }
+        M[t] = bits;
+    }
+    ctx.sync();
+    // ---- 4. sequential group assignment in (i, j) order (A5), one lane ----
+    if (tid == 0) {
+        int ng = 0;
+        for (int i = 0; i < n; ++i) {
+            for (int w = i >> 5; w < wpr; ++w) {
+                uint32_t bits = M[i * wpr + w];
+                while (bits) {
+                    const int b = ffs32(bits) - 1;
+                    bits &= bits - 1;
+                    const int j = w * 32 + b;
+                    fs.sel[i] = 0; fs.sel[j] = 0;
+                    const int gi = fs.gid[i], gj = fs.gid[j];
+                    if (gi < 0 && gj < 0) { fs.gid[i] = fs.gid[j] = ng; ++ng; }
+                    else if (gi > -1 && gj == -1) fs.gid[j] = gi;
+                    else if (gj > -1 && gi == -1) fs.gid[i] = gj;
+                }
+            }
+        }
+        // group segments: members grouped by gid, ascending T index inside a group
+        for (int g = 0; g <= ng; ++g) fs.gstart[g] = 0;
+        for (int i = 0; i < n; ++i) if (fs.gid[i] >= 0) fs.gstart[fs.gid[i] + 1]++;
+        for (int g = 0; g < ng; ++g) fs.gstart[g + 1] += fs.gstart[g];
+        for (int g = 0; g < ng; ++g) { fs.closeCnt[g] = 0; fs.gfill[g] = fs.gstart[g]; }
+        for (int i = 0; i < n; ++i) if (fs.gid[i] >= 0) fs.members[fs.gfill[fs.gid[i]]++] = i;
+        fs.counters[4] = ng;
+    }
+    ctx.sync();
+    const int ng = fs.counters[4];
+    // ---- 5. per group: representative + close contours ----
+    for (int g = tid; g < ng; g += nt) {
+        const int b = fs.gstart[g], e = fs.gstart[g + 1];
+        int cur = fs.members[b];
+        fs.sel[cur] = 1;
+        int nc = 0;
+        for (int k = b + 1; k < e; ++k) {
+            const int id = fs.members[k];
+            const float dist = quad_avg_distance(fs.tq + (size_t)id * 8, fs.tq + (size_t)cur * 8);
+            const float ms = quad_module_size(fs.tq + (size_t)id * 8, fp.markerSize, fp.borderBits);
+            if (dist > f_mul(fp.minGroupDistance, ms)) { cur = id; fs.closeIdx[b + nc] = id; ++nc; }
+        }
+        fs.closeCnt[g] = nc;
+    }
+    ctx.sync();
+    // ---- 6. selected candidates (minus the ones near the image border), in T order ----
+    int nS = 0;
+    for (int base = 0; base < n; base += nt) {
+        const int i = base + tid;
+        const int flag = (i < n) && fs.sel[i] && !quad_near_border(fs.tq + (size_t)i * 8, fp.W, fp.H, fp.minDistanceToBorder);
+        int total;
+        const int pos = ctx.exclusive_scan(flag, total);
+        if (flag) { fs.S[nS + pos] = i; fs.selGroup[nS + pos] = fs.gid[i]; }
+        nS += total;
+    }
+    ctx.sync();
+    // ---- 7. containment hierarchy ----
+    for (int i = tid; i < nS; i += nt) {
+        int par = -1;
+        const float *a = fs.tq + (size_t)fs.S[i] * 8;
+        for (int j = i - 1; j >= 0; --j)
+            if (quad_inside_quad(a, fs.tq + (size_t)fs.S[j] * 8)) { par = j; break; }
+        fs.parent[i] = par;
+        fs.depth[i] = 0;
+    }
+    ctx.sync();
+    if (tid == 0) {
+        for (int i = nS - 1; i >= 0; --i) {
+            const int par = fs.parent[i];
+            if (par >= 0 && fs.depth[par] < fs.depth[i] + 1) fs.depth[par] = fs.depth[i] + 1;
+        }
+        // ---- 8. identification work list ----
+        int nw = nS;
+        for (int v = 0; v < nS; ++v) {
+            const int g = fs.selGroup[v];
+            int cnt = 0;
+            // only a group's representative (its first member) owns the close list
+            if (g >= 0 && fs.members[fs.gstart[g]] == fs.S[v]) cnt = fs.closeCnt[g];
+            fs.closeStart[v] = nw;
+            if (nw + cnt > fp.max_cand) { cnt = fp.max_cand - nw; fs.counters[FC_STATUS] = 3; }
+            fs.closeNum[v] = cnt;
+            nw += cnt;
+        }
+        fs.counters[FC_NCAND] = n;
+        fs.counters[FC_NSEL] = nS;
+        fs.counters[FC_NWORK] = nw;
+    }
+    ctx.sync();
+    const int nw = fs.counters[FC_NWORK];
+    for (int v = tid; v < nS; v += nt) {
+        for (int k = 0; k < 8; ++k) fs.wq[(size_t)v * 8 + k] = fs.tq[(size_t)fs.S[v] * 8 + k];
+        const int g = fs.selGroup[v];
+        for (int c = 0; c < fs.closeNum[v]; ++c) {
+            const int id = fs.closeIdx[fs.gstart[g] + c];
+            for (int k = 0; k < 8; ++k) fs.wq[(size_t)(fs.closeStart[v] + c) * 8 + k] = fs.tq[(size_t)id * 8 + k];
+        }
+    }
+    for (int w = tid; w < nw; w += nt) fs.wres[w] = 0;
+    ctx.sync();
+}
+
+// --------------------------------------------------------------------------------------------
+struct FrameOutputs {
+    int32_t *n_accepted;   // [1]
+    int32_t *n_rejected;   // [1]
+    float   *corners;      // [max_markers][8]
+    int32_t *ids;          // [max_markers]
+    float   *rejected;     // [max_markers][8]
+    int32_t *status;       // [1]
+};
+
+// A6 + output (single lane: the per-frame lists are a few dozen entries)
+template <class Ctx>
+B2A_HD void frame_finalize(Ctx &ctx, const FrameParams &fp, const FrameScratch &fs, const FrameOutputs &fo)
+{
+    if (ctx.tid() != 0) return;
+    const int nS = fs.counters[FC_NSEL];
+    // valid / was flags live in gid / sel (free after grouping); chosen work item in gfill
+    int32_t *valid = fs.gid, *was = fs.sel, *chosen = fs.gfill;
+    int maxDepth = 0;
+    for (int v = 0; v < nS; ++v) { valid[v] = 0; was[v] = 0; chosen[v] = v; if (fs.depth[v] > maxDepth) maxDepth = fs.depth[v]; }
+    int counter = 0;
+    for (int depth = 0; counter < nS && depth <= maxDepth; ++depth) {
+        for (int v = 0; v < nS; ++v) {
+            if (fs.depth[v] != depth) continue;
+            was[v] = 1;
+            if (fs.wres[v] < 0) valid[v] = 1;
+            else
+                for (int c = 0; c < fs.closeNum[v]; ++c)
+                    if (fs.wres[fs.closeStart[v] + c] < 0) { valid[v] = 1; chosen[v] = fs.closeStart[v] + c; break; }
+        }
+        for (int v = 0; v < nS; ++v) {
+            if (fs.depth[v] != depth) continue;
+            if (valid[v]) {
+                int par = fs.parent[v];
+                while (par != -1) { if (!was[par]) { was[par] = 1; ++counter; } par = fs.parent[par]; }
+            }
+            ++counter;
+        }
+    }
+    int na = 0, nr = 0, status = fs.counters[FC_STATUS];
+    for (int v = 0; v < nS; ++v) {
+        if (valid[v]) {
+            const int w = chosen[v];
+            const uint32_t res = (uint32_t)fs.wres[w];
+            const int rot = (int)(res & 3u), id = (int)((res >> 8) & 0x7FFFFFu);
+            if (na < fp.max_markers) {
+                const float *c = fs.wq + (size_t)w * 8;
+                float *o = fo.corners + (size_t)na * 8;
+                for (int j = 0; j < 4; ++j) {       // std::rotate(begin, begin + 4 - rot, end)
+                    const int src = (j + 4 - rot) & 3;
+                    o[2 * j] = c[2 * src]; o[2 * j + 1] = c[2 * src + 1];
+                }
+                fo.ids[na] = id;
+                ++na;
+            } else status = 3;
+        } else {
+            if (nr < fp.max_markers) {
+                const float *c = fs.wq + (size_t)v * 8;
+                float *o = fo.rejected + (size_t)nr * 8;
+                for (int k = 0; k < 8; ++k) o[k] = c[k];
+                ++nr;
+            } else status = 3;
+        }
+    }
+    *fo.n_accepted = na; *fo.n_rejected = nr; *fo.status = status;
+}
+
+}  // namespace b2a

@@ -1,0 +1,312 @@
+// pose_core.h -- per-marker pose and observation arithmetic (FP64), host/device.
+// Replaces cv::aruco::estimatePoseSingleMarkers (per-marker cv::solvePnP, SOLVEPNP_ITERATIVE;
+// reference src/aruco_slam.cpp:314), cv::Rodrigues / cv::projectPoints (:354, :441) and the
+// reference's own observation mapping and CalculateCovariance (:325-374, :412-421, :437-471).
+//
+// solvePnP ITERATIVE minimises the distorted reprojection error of the 4 corners starting from
+// a homography decomposition (SURVEY.md App. A "Pose").  Here: same initialisation, then a
+// Levenberg-Marquardt iteration on SE(3) with a local rotation perturbation R <- R exp([w]x)
+// and analytic Jacobians, run to convergence; the minimiser does not depend on the
+// parametrisation, so the result agrees with cv2.solvePnP to ~1e-7 (tolerance 1e-4 rad / m).
+#pragma once
+#include "core.h"
+
+namespace b2a {
+
+struct Camera {
+    double fx, fy, cx, cy;
+    double k1, k2, p1, p2, k3;
+};
+
+B2A_HD void rodrigues_to_R(const double *r, double *R)
+{
+    const double th = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    if (th < DBL_EPSILON) { for (int i = 0; i < 9; ++i) R[i] = 0; R[0] = R[4] = R[8] = 1; return; }
+    const double c = cos(th), s = sin(th), c1 = 1 - c, it = 1 / th;
+    const double x = r[0] * it, y = r[1] * it, z = r[2] * it;
+    R[0] = c + c1 * x * x;     R[1] = c1 * x * y - s * z; R[2] = c1 * x * z + s * y;
+    R[3] = c1 * x * y + s * z; R[4] = c + c1 * y * y;     R[5] = c1 * y * z - s * x;
+    R[6] = c1 * x * z - s * y; R[7] = c1 * y * z + s * x; R[8] = c + c1 * z * z;
+}
+
+B2A_HD void R_to_rodrigues(const double *R, double *r)
+{
+    double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
+    const double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+    double c = (R[0] + R[4] + R[8] - 1) * 0.5;
+    c = c > 1 ? 1 : (c < -1 ? -1 : c);
+    double th = acos(c);
+    if (s < 1e-5) {
+        if (c > 0) { r[0] = r[1] = r[2] = 0; return; }
+        double t;
+        t = (R[0] + 1) * 0.5; rx = sqrt(t > 0 ? t : 0);
+        t = (R[4] + 1) * 0.5; ry = sqrt(t > 0 ? t : 0) * (R[1] < 0 ? -1. : 1.);
+        t = (R[8] + 1) * 0.5; rz = sqrt(t > 0 ? t : 0) * (R[2] < 0 ? -1. : 1.);
+        if (fabs(rx) < fabs(ry) && fabs(rx) < fabs(rz) && (R[5] > 0) != (ry * rz > 0)) rz = -rz;
+        th /= sqrt(rx * rx + ry * ry + rz * rz);
+        r[0] = th * rx; r[1] = th * ry; r[2] = th * rz;
+        return;
+    }
+    const double vth = th / (2 * s);
+    r[0] = rx * vth; r[1] = ry * vth; r[2] = rz * vth;
+}
+
+// normalised camera point -> pixel, optionally with d(pixel)/d(x,y)
+B2A_HD void distort_project(const Camera &cam, double x, double y, double &u, double &v, double *J /* 2x2 or null */)
+{
+    const double r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+    const double a1 = 2 * x * y, a2 = r2 + 2 * x * x, a3 = r2 + 2 * y * y;
+    const double cd = 1 + cam.k1 * r2 + cam.k2 * r4 + cam.k3 * r6;
+    const double xd = x * cd + cam.p1 * a1 + cam.p2 * a2;
+    const double yd = y * cd + cam.p1 * a3 + cam.p2 * a1;
+    u = xd * cam.fx + cam.cx;
+    v = yd * cam.fy + cam.cy;
+    if (J) {
+        const double dcd = cam.k1 + 2 * cam.k2 * r2 + 3 * cam.k3 * r4;          // d cd / d r2
+        const double dxd_dx = cd + x * dcd * 2 * x + cam.p1 * 2 * y + cam.p2 * (2 * x + 4 * x);
+        const double dxd_dy = x * dcd * 2 * y + cam.p1 * 2 * x + cam.p2 * 2 * y;
+        const double dyd_dx = y * dcd * 2 * x + cam.p1 * 2 * x + cam.p2 * 2 * y;
+        const double dyd_dy = cd + y * dcd * 2 * y + cam.p1 * (2 * y + 4 * y) + cam.p2 * 2 * x;
+        J[0] = cam.fx * dxd_dx; J[1] = cam.fx * dxd_dy; J[2] = cam.fy * dyd_dx; J[3] = cam.fy * dyd_dy;
+    }
+}
+
+// cv::projectPoints for one object point
+B2A_HD void project_point(const Camera &cam, const double *R, const double *t, const double *X, double &u, double &v)
+{
+    double x = R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + t[0];
+    double y = R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + t[1];
+    double z = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + t[2];
+    z = z != 0 ? 1. / z : 1;
+    distort_project(cam, x * z, y * z, u, v, nullptr);
+}
+
+// cv::undistortPoints default: 5 fixed-point iterations
+B2A_HD void undistort_point(const Camera &cam, double u, double v, double &xo, double &yo)
+{
+    double x = (u - cam.cx) / cam.fx, y = (v - cam.cy) / cam.fy;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; ++j) {
+        const double r2 = x * x + y * y;
+        const double icd = 1. / (1 + ((cam.k3 * r2 + cam.k2) * r2 + cam.k1) * r2);
+        if (icd < 0) { x = x0; y = y0; break; }
+        const double dx = 2 * cam.p1 * x * y + cam.p2 * (r2 + 2 * x * x);
+        const double dy = cam.p1 * (r2 + 2 * y * y) + 2 * cam.p2 * x * y;
+        x = (x0 - dx) * icd;
+        y = (y0 - dy) * icd;
+    }
+    xo = x; yo = y;
+}
+
+template <int N>
+B2A_HD bool solve_linear(double *A, double *b)
+{
+    for (int i = 0; i < N; ++i) {
+        int k = i;
+        for (int j = i + 1; j < N; ++j) if (fabs(A[j * N + i]) > fabs(A[k * N + i])) k = j;
+        if (fabs(A[k * N + i]) < 1e-300) return false;
+        if (k != i) {
+            for (int j = 0; j < N; ++j) { const double t = A[i * N + j]; A[i * N + j] = A[k * N + j]; A[k * N + j] = t; }
+            const double t = b[i]; b[i] = b[k]; b[k] = t;
+        }
+        for (int j = i + 1; j < N; ++j) {
+            const double a = A[j * N + i] / A[i * N + i];
+            for (int c = i; c < N; ++c) A[j * N + c] -= a * A[i * N + c];
+            b[j] -= a * b[i];
+        }
+    }
+    for (int i = N - 1; i >= 0; --i) {
+        double s = b[i];
+        for (int k = i + 1; k < N; ++k) s -= A[i * N + k] * b[k];
+        b[i] = s / A[i * N + i];
+    }
+    return true;
+}
+
+B2A_HD void nearest_rotation(double *R)
+{
+    for (int it = 0; it < 60; ++it) {
+        double a[9];
+        for (int i = 0; i < 9; ++i) a[i] = R[i];
+        const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+        const double id = 1 / det;
+        double iT[9];
+        iT[0] = (a[4] * a[8] - a[5] * a[7]) * id; iT[1] = (a[5] * a[6] - a[3] * a[8]) * id; iT[2] = (a[3] * a[7] - a[4] * a[6]) * id;
+        iT[3] = (a[2] * a[7] - a[1] * a[8]) * id; iT[4] = (a[0] * a[8] - a[2] * a[6]) * id; iT[5] = (a[1] * a[6] - a[0] * a[7]) * id;
+        iT[6] = (a[1] * a[5] - a[2] * a[4]) * id; iT[7] = (a[2] * a[3] - a[0] * a[5]) * id; iT[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+        double diff = 0;
+        for (int i = 0; i < 9; ++i) { const double v = 0.5 * (a[i] + iT[i]); diff += fabs(v - a[i]); R[i] = v; }
+        if (diff < 1e-15) break;
+    }
+}
+
+// residuals (8) of pose (R,t); optionally the 8x6 Jacobian w.r.t. (w, dt) of R exp([w]x), t + dt
+B2A_HD double pose_residuals(const Camera &cam, const double *obj, const double *ip, const double *R, const double *t, double *res, double *J)
+{
+    double e = 0;
+    for (int i = 0; i < 4; ++i) {
+        const double *X = obj + 3 * i;
+        const double RX[3] = {R[0] * X[0] + R[1] * X[1] + R[2] * X[2], R[3] * X[0] + R[4] * X[1] + R[5] * X[2], R[6] * X[0] + R[7] * X[1] + R[8] * X[2]};
+        const double Px = RX[0] + t[0], Py = RX[1] + t[1], Pz = RX[2] + t[2];
+        const double iz = Pz != 0 ? 1. / Pz : 1;
+        const double x = Px * iz, y = Py * iz;
+        double u, v, Jd[4];
+        distort_project(cam, x, y, u, v, J ? Jd : nullptr);
+        res[2 * i] = u - ip[2 * i]; res[2 * i + 1] = v - ip[2 * i + 1];
+        e += res[2 * i] * res[2 * i] + res[2 * i + 1] * res[2 * i + 1];
+        if (J) {
+            // d(x,y)/dP
+            const double dxdP[3] = {iz, 0, -x * iz}, dydP[3] = {0, iz, -y * iz};
+            // dP/dw = -R [X]x  (columns), dP/dt = I
+            // R [X]x : column k = R * (e_k x X)... use d(R exp(w) X)/dw = R * (-[X]x) = -R [X]x
+            double M[9];   // -R [X]x
+            // [X]x = [[0,-X2,X1],[X2,0,-X0],[-X1,X0,0]]
+            for (int r = 0; r < 3; ++r) {
+                const double a = R[3 * r], b = R[3 * r + 1], c = R[3 * r + 2];
+                M[3 * r + 0] = -(b * X[2] - c * X[1]);
+                M[3 * r + 1] = -(-a * X[2] + c * X[0]);
+                M[3 * r + 2] = -(a * X[1] - b * X[0]);
+            }
+            for (int k = 0; k < 6; ++k) {
+                double dP[3];
+                if (k < 3) { dP[0] = M[k]; dP[1] = M[3 + k]; dP[2] = M[6 + k]; }
+                else { dP[0] = (k == 3); dP[1] = (k == 4); dP[2] = (k == 5); }
+                const double dx = dxdP[0] * dP[0] + dxdP[2] * dP[2];
+                const double dy = dydP[1] * dP[1] + dydP[2] * dP[2];
+                J[(2 * i) * 6 + k] = Jd[0] * dx + Jd[1] * dy;
+                J[(2 * i + 1) * 6 + k] = Jd[2] * dx + Jd[3] * dy;
+            }
+        }
+    }
+    return e;
+}
+
+// one marker: corners (4x2, image pixels) -> rvec, tvec
+B2A_HD void solve_marker_pose(const Camera &cam, float marker_length, const float *corners, double *rvec, double *tvec)
+{
+    const float hf = marker_length / 2.f;                         // Vec3f(-L/2.f, L/2.f, 0) ...
+    const double h = (double)hf;
+    const double obj[12] = {-h, h, 0, h, h, 0, h, -h, 0, -h, -h, 0};
+    double ip[8];
+    for (int i = 0; i < 8; ++i) ip[i] = (double)corners[i];
+    // ---- initialisation: homography obj.xy -> undistorted normalised points ----
+    double A[64], b[8];
+    for (int i = 0; i < 64; ++i) A[i] = 0;
+    for (int i = 0; i < 4; ++i) {
+        double u, v;
+        undistort_point(cam, ip[2 * i], ip[2 * i + 1], u, v);
+        const double X = obj[3 * i], Y = obj[3 * i + 1];
+        double *r0 = A + (2 * i) * 8, *r1 = A + (2 * i + 1) * 8;
+        r0[0] = X; r0[1] = Y; r0[2] = 1; r0[6] = -u * X; r0[7] = -u * Y; b[2 * i] = u;
+        r1[3] = X; r1[4] = Y; r1[5] = 1; r1[6] = -v * X; r1[7] = -v * Y; b[2 * i + 1] = v;
+    }
+    solve_linear<8>(A, b);
+    const double hm[9] = {b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], 1.0};
+    const double n1 = sqrt(hm[0] * hm[0] + hm[3] * hm[3] + hm[6] * hm[6]);
+    const double n2 = sqrt(hm[1] * hm[1] + hm[4] * hm[4] + hm[7] * hm[7]);
+    const double a1[3] = {hm[0] / n1, hm[3] / n1, hm[6] / n1}, a2[3] = {hm[1] / n2, hm[4] / n2, hm[7] / n2};
+    const double a3[3] = {a1[1] * a2[2] - a1[2] * a2[1], a1[2] * a2[0] - a1[0] * a2[2], a1[0] * a2[1] - a1[1] * a2[0]};
+    double R[9], t[3];
+    for (int i = 0; i < 3; ++i) { R[3 * i] = a1[i]; R[3 * i + 1] = a2[i]; R[3 * i + 2] = a3[i]; }
+    nearest_rotation(R);
+    const double sc = 2. / (n1 + n2);
+    t[0] = hm[2] * sc; t[1] = hm[5] * sc; t[2] = hm[8] * sc;
+    // ---- Levenberg-Marquardt ----
+    double res[8], J[48];
+    double e = pose_residuals(cam, obj, ip, R, t, res, J);
+    double lambda = 1e-3;
+    for (int it = 0; it < 100; ++it) {
+        double JtJ[36], Jtr[6];
+        for (int a = 0; a < 6; ++a) {
+            double s = 0;
+            for (int i = 0; i < 8; ++i) s += J[i * 6 + a] * res[i];
+            Jtr[a] = s;
+            for (int c = a; c < 6; ++c) {
+                double q = 0;
+                for (int i = 0; i < 8; ++i) q += J[i * 6 + a] * J[i * 6 + c];
+                JtJ[a * 6 + c] = q; JtJ[c * 6 + a] = q;
+            }
+        }
+        bool improved = false;
+        double step2 = 0;
+        for (int tries = 0; tries < 30 && !improved; ++tries) {
+            double M[36], d[6];
+            for (int i = 0; i < 36; ++i) M[i] = JtJ[i];
+            for (int a = 0; a < 6; ++a) { M[a * 6 + a] *= 1 + lambda; d[a] = -Jtr[a]; }
+            if (!solve_linear<6>(M, d)) { lambda *= 10; continue; }
+            // R2 = R exp([w]x), t2 = t + dt
+            double E[9], R2[9], t2[3], r2[8];
+            rodrigues_to_R(d, E);
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
+                R2[3 * r + c] = R[3 * r] * E[c] + R[3 * r + 1] * E[3 + c] + R[3 * r + 2] * E[6 + c];
+            t2[0] = t[0] + d[3]; t2[1] = t[1] + d[4]; t2[2] = t[2] + d[5];
+            const double e2 = pose_residuals(cam, obj, ip, R2, t2, r2, nullptr);
+            if (e2 < e) {
+                for (int i = 0; i < 9; ++i) R[i] = R2[i];
+                t[0] = t2[0]; t[1] = t2[1]; t[2] = t2[2];
+                e = e2;
+                step2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3] + d[4] * d[4] + d[5] * d[5];
+                lambda = lambda > 1e-16 ? lambda * 0.1 : lambda;
+                improved = true;
+            } else lambda *= 10;
+        }
+        if (!improved) break;
+        if (step2 < 1e-26) break;
+        e = pose_residuals(cam, obj, ip, R, t, res, J);
+    }
+    nearest_rotation(R);          // remove accumulated drift before taking the log
+    R_to_rodrigues(R, rvec);
+    tvec[0] = t[0]; tvec[1] = t[1]; tvec[2] = t[2];
+}
+
+// ---- observation mapping (reference src/aruco_slam.cpp:325-374, 437-471) ----
+struct ObsParams {
+    double R_x, R_y, R_theta, marker_length, r2c_tx, r2c_ty;
+    float useful_distance_threshold;
+};
+struct Observation {
+    int32_t aruco_id, aruco_index;
+    double x, y, theta;
+    double cov[9];
+};
+B2A_HD void norm_angle(double &a)
+{   // aruco_slam.cpp:412-421, single wrap
+    const double PI = 3.14159265358979323846, TWO_PI = 2.0 * PI;
+    if (a >= PI) a -= TWO_PI;
+    if (a < -PI) a += TWO_PI;
+}
+// returns false when the marker is gated out (range :327-333 or covariance norm :367-368)
+B2A_HD bool make_observation(const Camera &cam, const ObsParams &op, const float *corners, int id,
+                             const double *rvec, const double *tvec, Observation &o)
+{
+    const double tn = sqrt(tvec[0] * tvec[0] + tvec[1] * tvec[1] + tvec[2] * tvec[2]);
+    const float dist = (float)tn;
+    if (dist > op.useful_distance_threshold) return false;
+    double R[9];
+    rodrigues_to_R(rvec, R);
+    const double x = tvec[2] + op.r2c_tx, y = -tvec[0] + op.r2c_ty;
+    double theta = atan2(-R[2], R[8]);
+    norm_angle(theta);
+    const float hf = (float)op.marker_length / 2.f;               // objectPoints_ (Point3f), aruco_slam.h:189
+    const double h = (double)hf;
+    const double obj[12] = {-h, h, 0, h, h, 0, h, -h, 0, -h, -h, 0};
+    double total = 0;
+    for (int j = 0; j < 4; ++j) {
+        double u, v;
+        project_point(cam, R, tvec, obj + 3 * j, u, v);
+        const double dx = (double)corners[2 * j] - (double)(float)u, dy = (double)corners[2 * j + 1] - (double)(float)v;
+        const double err = sqrt(dx * dx + dy * dy);
+        total += err * err;
+    }
+    const double rms = total / 4.0;                                // "rmserror" is a mean of squares (:465)
+    const double gx = (double)corners[0] - (double)corners[4], gy = (double)corners[1] - (double)corners[5];
+    const double oe = (rms / sqrt(gx * gx + gy * gy)) * (tn / op.marker_length);
+    for (int i = 0; i < 9; ++i) o.cov[i] = 0;
+    o.cov[0] = oe * op.R_x + 1e-2; o.cov[4] = oe * op.R_y + 1e-2; o.cov[8] = oe * op.R_theta + 1e-3;
+    const double fro = sqrt(o.cov[0] * o.cov[0] + o.cov[4] * o.cov[4] + o.cov[8] * o.cov[8]);
+    if (fro > 1) return false;
+    o.aruco_id = id; o.aruco_index = -1; o.x = x; o.y = y; o.theta = theta;
+    return true;
+}
+
+}  // namespace b2a

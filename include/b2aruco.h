@@ -1,0 +1,194 @@
+/* b2aruco.h -- C ABI of the B200-native ArUco detect + pose (+ EKF landmark update) path.
+ *
+ * Drop-in boundary for the calls the reference makes at
+ *   /root/reference/src/aruco_slam.cpp:11-12  cv::aruco::getPredefinedDictionary
+ *   /root/reference/src/aruco_slam.cpp:313    cv::aruco::detectMarkers(img, dictionary_, corners, IDs)
+ *   /root/reference/src/aruco_slam.cpp:314    cv::aruco::estimatePoseSingleMarkers(corners, marker_length_, K, D, rvs, tvs)
+ *   /root/reference/src/aruco_slam.cpp:325-374,437-471  observation mapping + CalculateCovariance
+ *   /root/reference/src/aruco_slam.cpp:21-74   ArucoSlam::addEncoder (EKF prediction)
+ *   /root/reference/src/aruco_slam.cpp:88-263  ArucoSlam::addImage   (EKF correction / augmentation)
+ * The reference has no plugin/FFI layer of its own; these entry points are what a
+ * C++ shim (include/b2aruco.hpp), a ctypes binding (aruco_slam_b200/_lib.py) or a ROS
+ * node would bind instead of the cv::aruco / Eigen calls.  Plain pointers and sizes
+ * only; every function returns a b2a_status (0 = OK) unless stated otherwise; no
+ * exceptions cross the boundary.  All compute runs in hand-written CUDA kernels
+ * (sm_100a); there is no CPU fallback: without a usable CUDA device the create calls
+ * fail with B2A_ERR_CUDA.
+ */
+#ifndef B2ARUCO_H
+#define B2ARUCO_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    B2A_OK = 0,
+    B2A_ERR_INVALID = 1,     /* bad argument (cv::Exception from CV_Assert in the reference path) */
+    B2A_ERR_CUDA = 2,        /* CUDA runtime error, see b2a_last_error() */
+    B2A_ERR_CAPACITY = 3,    /* an internal list overflowed its configured capacity; results incomplete */
+    B2A_ERR_UNSUPPORTED = 4  /* parameter combination outside what the kernels implement */
+} b2a_status;
+
+const char *b2a_last_error(void);
+const char *b2a_version(void);
+
+/* ---- cv::aruco::DetectorParameters (fields the detect path reads; cv2 4.13.0 defaults) ---- */
+typedef struct {
+    int    adaptiveThreshWinSizeMin;              /* 3 */
+    int    adaptiveThreshWinSizeMax;              /* 23 */
+    int    adaptiveThreshWinSizeStep;             /* 10 */
+    double adaptiveThreshConstant;                /* 7 */
+    double minMarkerPerimeterRate;                /* 0.03 */
+    double maxMarkerPerimeterRate;                /* 4.0 */
+    double polygonalApproxAccuracyRate;           /* 0.03 */
+    double minCornerDistanceRate;                 /* 0.05 */
+    int    minDistanceToBorder;                   /* 3 */
+    double minMarkerDistanceRate;                 /* 0.125 */
+    float  minGroupDistance;                      /* 0.21 */
+    int    markerBorderBits;                      /* 1 */
+    int    perspectiveRemovePixelPerCell;         /* 4 */
+    double perspectiveRemoveIgnoredMarginPerCell; /* 0.13 */
+    double maxErroneousBitsInBorderRate;          /* 0.35 */
+    double minOtsuStdDev;                         /* 5.0 */
+    double errorCorrectionRate;                   /* 0.6 */
+    int    cornerRefinementMethod;                /* 0 = CORNER_REFINE_NONE, 1 = CORNER_REFINE_SUBPIX */
+    int    cornerRefinementWinSize;               /* 5 */
+    double relativeCornerRefinmentWinSize;        /* 0.3 */
+    int    cornerRefinementMaxIterations;         /* 30 */
+    double cornerRefinementMinAccuracy;           /* 0.1 */
+    int    detectInvertedMarker;                  /* 0 (1 is B2A_ERR_UNSUPPORTED) */
+} b2a_detector_params;
+
+void b2a_default_detector_params(b2a_detector_params *p);
+
+/* ---- dictionaries: cv::aruco::getPredefinedDictionary (aruco_slam.cpp:11-12) ---- */
+typedef struct {
+    int markerSize, maxCorrectionBits, nMarkers, nBytes;
+    const uint8_t *table;             /* [nMarkers][4 rotations][nBytes], cv2 bytesList memory order */
+} b2a_dictionary;
+
+/* dict_id = cv::aruco::PREDEFINED_DICTIONARY_NAME value (16 = DICT_ARUCO_ORIGINAL, parameters.yaml:16).
+ * The returned table is owned by the library and lives for the process. */
+int b2a_get_predefined_dictionary(int dict_id, b2a_dictionary *out);
+
+/* ---- detector handle: one per GPU; single caller at a time (like one ArucoSlam instance) ---- */
+typedef struct b2a_detector b2a_detector;
+
+typedef struct {
+    int device;                 /* CUDA device ordinal */
+    int max_width, max_height;  /* largest frame */
+    int max_batch;              /* largest number of frames per call */
+    int max_markers;            /* capacity of accepted (and of rejected) quads per frame; 0 = 256 */
+    int max_candidates;         /* capacity of quad candidates per frame before grouping; 0 = 2048 */
+} b2a_detector_config;
+
+int  b2a_detector_create(const b2a_detector_config *cfg, const b2a_dictionary *dict,
+                         const b2a_detector_params *params, b2a_detector **out);
+void b2a_detector_destroy(b2a_detector *d);
+
+/* Where the frames of a batch live. */
+typedef struct {
+    const uint8_t *data;        /* first frame */
+    int    on_device;           /* 0: host memory (copied H2D inside the call), 1: device memory */
+    int    batch, width, height, channels;   /* channels 1 (gray) or 3 (bgr8, aruco_slam_node.cpp:93) */
+    size_t row_stride;          /* bytes between rows   (0 = width*channels) */
+    size_t frame_stride;        /* bytes between frames (0 = row_stride*height) */
+} b2a_frames;
+
+/* Results of one call; pointers are library-owned pinned host memory, valid until the next
+ * call on the same handle.  Arrays are [batch][max_markers]..., frame f's entries start at
+ * f*max_markers.  Order inside a frame is the reference's (cv2 4.13.0) output order. */
+typedef struct {
+    int batch, max_markers;
+    const int32_t *n_accepted;  /* [batch] */
+    const int32_t *n_rejected;  /* [batch] */
+    const float   *corners;     /* [batch][max_markers][4][2]  clockwise from the marker's top-left */
+    const int32_t *ids;         /* [batch][max_markers] */
+    const float   *rejected;    /* [batch][max_markers][4][2] */
+    const double  *rvecs;       /* [batch][max_markers][3]  (only after b2a_detect_pose) */
+    const double  *tvecs;       /* [batch][max_markers][3] */
+    const int32_t *status;      /* [batch] per-frame b2a_status (capacity overflow) */
+} b2a_detections;
+
+/* detectMarkers over a batch of frames (aruco_slam.cpp:313). */
+int b2a_detect(b2a_detector *d, const b2a_frames *frames, b2a_detections *out);
+
+/* Camera model of the pose step: K row-major 3x3, D = (k1,k2,p1,p2[,k3]), nD in {0,4,5}. */
+typedef struct {
+    double K[9];
+    double D[5];
+    int    nD;
+    float  marker_length;       /* markerLength of estimatePoseSingleMarkers (parameters.yaml:17) */
+} b2a_camera;
+
+/* detectMarkers + estimatePoseSingleMarkers without leaving the device (aruco_slam.cpp:313-314). */
+int b2a_detect_pose(b2a_detector *d, const b2a_frames *frames, const b2a_camera *cam, b2a_detections *out);
+
+/* estimatePoseSingleMarkers on caller-provided corners (host arrays): corners [n][4][2] f32,
+ * rvecs/tvecs [n][3] f64.  (aruco_slam.cpp:314) */
+int b2a_estimate_pose_single_markers(b2a_detector *d, const float *corners, int n, const b2a_camera *cam,
+                                     double *rvecs, double *tvecs);
+
+/* Stage taps for parity tests (host output buffers):
+ *   gray  [batch][H][W] u8 (after A1),  masks [batch][nScales][H][W] u8 (0/255, A2). */
+int b2a_debug_threshold(b2a_detector *d, const b2a_frames *frames, uint8_t *gray, uint8_t *masks);
+/* Contours that pass the perimeter gate, in cv2.findContours list order per (frame,scale):
+ *   counts [batch][nScales] (all borders found, incl. short ones), n_kept [batch][nScales],
+ *   kept_len / kept_start_xy filled up to cap entries per (frame,scale), points of kept contours
+ *   concatenated per (frame,scale) into pts (x,y int16 pairs), pts_cap points per (frame,scale). */
+int b2a_debug_contours(b2a_detector *d, const b2a_frames *frames, int32_t *counts, int32_t *n_kept,
+                       int32_t *kept_len, int cap, int16_t *pts, int pts_cap);
+/* Quad candidates before grouping (A3/A4), in reference order: n_cand [batch], quads [batch][cap][4][2]. */
+int b2a_debug_candidates(b2a_detector *d, const b2a_frames *frames, int32_t *n_cand, float *quads, int cap);
+int b2a_detector_num_scales(const b2a_detector *d);
+
+/* timing taps: milliseconds of the last b2a_detect / b2a_detect_pose call, per stage, measured with
+ * CUDA events on the handle's stream.  names[i] are static strings; returns number of stages. */
+int b2a_last_stage_times(const b2a_detector *d, const char **names, float *ms, int cap);
+/* number of kernel launches issued by the last detect call (for bench.py's gpu_launches) */
+int b2a_last_launch_count(const b2a_detector *d);
+/* the CUDA stream (cudaStream_t) the handle launches on */
+void *b2a_detector_stream(const b2a_detector *d);
+
+/* ---- observation mapping + EKF (ArucoSlam, reference include/aruco_slam/aruco_slam.h:101-193) ---- */
+typedef struct {
+    double Q_k, R_x, R_y, R_theta;   /* parameters.yaml:5-8 */
+    double kl, kr, b;                /* parameters.yaml:11-13 */
+    double r2c_tx, r2c_ty;           /* transformStamped_r2c_.transform.translation.{x,y} */
+    float  useful_distance_threshold;/* aruco_slam.h:58 (default 3) */
+    int    max_landmarks;            /* capacity of the map (state dim 3+3n); 0 = 512 */
+} b2a_slam_params;
+
+void b2a_default_slam_params(b2a_slam_params *p);
+
+typedef struct {
+    int32_t aruco_id, aruco_index;
+    double  x, y, theta;
+    double  cov[9];
+} b2a_observation;
+
+typedef struct b2a_slam b2a_slam;
+int  b2a_slam_create(int device, const b2a_slam_params *p, b2a_slam **out);
+void b2a_slam_destroy(b2a_slam *s);
+int  b2a_slam_dim(const b2a_slam *s);                     /* 3 + 3*landmarks */
+/* mu [N], sigma [N][N] row-major, ids [n landmarks] (host). NULL pointers are skipped. */
+int  b2a_slam_get_state(b2a_slam *s, double *mu, double *sigma, int32_t *ids);
+int  b2a_slam_set_state(b2a_slam *s, int N, const double *mu, const double *sigma, const int32_t *ids);
+/* addEncoder(wl, wr) with an explicit dt (aruco_slam.cpp:21-74 reads ros::Time::now()). */
+int  b2a_slam_add_encoder(b2a_slam *s, double wl, double wr, double dt);
+/* getObservations' post-processing (aruco_slam.cpp:325-374) on host arrays; returns the kept
+ * observations in detection order through out (capacity n), *n_out = count. */
+int  b2a_slam_make_observations(b2a_slam *s, const float *corners, const int32_t *ids, const double *rvecs,
+                                const double *tvecs, int n, const b2a_camera *cam,
+                                b2a_observation *out, int *n_out);
+/* The EKF loop of addImage (aruco_slam.cpp:88-263) for one frame's observations. */
+int  b2a_slam_update(b2a_slam *s, const b2a_observation *obs, int n);
+/* addImage(img): detect + pose + observations + EKF update for one frame (aruco_slam.cpp:76-263). */
+int  b2a_slam_add_image(b2a_slam *s, b2a_detector *d, const b2a_frames *frame, const b2a_camera *cam);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,201 @@
+// hostemu.cpp -- TEST INFRASTRUCTURE ONLY.  Single-lane host emulation of the product's kernel
+// logic (aruco_slam_b200/csrc/core.h, frame_logic.h, pose_core.h compiled for the host) so that
+// the CPU-only test tier (`pytest -m "not gpu"`) can check that logic against the oracle without
+// a GPU.  It is not built into, shipped with or reachable from the product library; the CUDA
+// kernels proper (thread mapping, shared memory, ballots) are checked by the `-m gpu` tests.
+#include "../../aruco_slam_b200/csrc/core.h"
+#include "../../aruco_slam_b200/csrc/frame_logic.h"
+#include "../../aruco_slam_b200/csrc/pose_core.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+using namespace b2a;
+
+struct HostCtx {
+    int tid() const { return 0; }
+    int nthreads() const { return 1; }
+    void sync() const {}
+    int exclusive_scan(int flag, int &total) const { total = flag ? 1 : 0; return 0; }
+};
+
+struct EmuParams {
+    int nScales; int radius[8]; int Cfloor;
+    double minPerimRate, maxPerimRate, approxRate, minCornerDistRate;
+    int minDistanceToBorder; float minMarkerDistanceRate, minGroupDistance;
+    int markerSize, borderBits, cellSize, cellMargin, nMarkers, maxCorr, maxBorderErr;
+    double minOtsuStdDev;
+    int max_cand, max_markers, surv_cap;
+};
+
+// packed masks exactly as the device lays them out (the bits themselves come from a plain loop:
+// k_threshold's tiling / ballots are device-only and are checked on the GPU)
+static void emu_threshold(const uint8_t *g, int W, int H, int r, int C, uint32_t *plane, int PWW)
+{
+    const int k = 2 * r + 1, kk = k * k;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            long long S = 0;
+            for (int dy = -r; dy <= r; ++dy) {
+                int yy = std::min(std::max(y + dy, 0), H - 1);
+                for (int dx = -r; dx <= r; ++dx) { int xx = std::min(std::max(x + dx, 0), W - 1); S += g[(size_t)yy * W + xx]; }
+            }
+            if (2 * S >= (long long)(2 * ((int)g[(size_t)y * W + x] + C) - 1) * kk)
+                plane[(size_t)(y + 1) * PWW + (x >> 5) + 1] |= 1u << (x & 31);
+        }
+}
+
+extern "C" {
+
+// masks_in: optional [nScales][H][W] u8 masks to use instead of thresholding (0 = compute)
+// outputs: n_acc/n_rej, corners[max_markers*8], ids, rejected; debug: n_contours[nScales] (incl. one-point borders),
+// n_cand, cand[max_cand*8]; kept contour lengths / points of scale dbg_scale
+int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const unsigned long long *dict, const EmuParams *ep,
+               int *n_acc, int *n_rej, float *corners, int32_t *ids, float *rejected,
+               int *n_contours, int *n_cand, float *cand,
+               int dbg_scale, int *dbg_nkept, int *dbg_len, int dbg_cap, int16_t *dbg_pts, int dbg_pts_cap)
+{
+    const int nS = ep->nScales, WW = (W + 31) / 32, PWW = WW + 2, KS = W + 1;
+    const size_t plane_words = (size_t)PWW * (H + 2);
+    const int maxWH = std::max(W, H);
+    const int minPerim = (int)(unsigned)(ep->minPerimRate * maxWH), maxPerim = (int)(unsigned)(ep->maxPerimRate * maxWH);
+    std::vector<uint32_t> masks(plane_words * nS, 0);
+    for (int s = 0; s < nS; ++s) {
+        uint32_t *pl = masks.data() + plane_words * s;
+        if (masks_in) {
+            for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x)
+                if (masks_in[((size_t)s * H + y) * W + x]) pl[(size_t)(y + 1) * PWW + (x >> 5) + 1] |= 1u << (x & 31);
+        } else emu_threshold(gray, W, H, ep->radius[s], ep->Cfloor, pl, PWW);
+    }
+    const int surv_cap = ep->surv_cap;
+    std::vector<int32_t> s_count(nS, 0), q_len((size_t)nS * surv_cap), q_xy((size_t)nS * surv_cap * 8);
+    std::vector<uint8_t> q_ok((size_t)nS * surv_cap, 0);
+    int status = 0;
+    for (int s = 0; s < nS; ++s) {
+        const uint32_t *pl = masks.data() + plane_words * s;
+        MaskView mv{pl, PWW};
+        struct Surv { uint32_t key; int len, x, y, s0; };
+        std::vector<Surv> surv;
+        int ncont = 0;
+        for (int y = 0; y < H; ++y)
+            for (int wx = 0; wx < WW; ++wx) {
+                const uint32_t *row = pl + (size_t)(y + 1) * PWW + wx + 1;
+                const uint32_t m = row[0];
+                if (!m) continue;
+                uint32_t outer, hole, iso;
+                start_candidate_words(m, row[-1], row[1], row[-PWW], row[-PWW - 1], row[-PWW + 1], row[PWW], row[PWW - 1], row[PWW + 1], outer, hole, iso);
+                ncont += __builtin_popcount(iso);
+                for (int type = 0; type < 2; ++type) {
+                    uint32_t bits = type ? hole : outer;
+                    while (bits) {
+                        const int b = __builtin_ffs(bits) - 1; bits &= bits - 1;
+                        const int x = wx * 32 + b;
+                        const unsigned c0 = mv(x, y);
+                        int s0; uint32_t key0;
+                        if (!start_state(c0, x, y, type, KS, s0, key0)) continue;
+                        const int len = walk_count(mv, KS - 1, x, y, s0, key0, 2 * W * H + 16);
+                        if (len > 0) {
+                            ++ncont;
+                            if (len >= minPerim && len <= maxPerim) surv.push_back({key0, len, x, y, s0});
+                        }
+                    }
+                }
+            }
+        if (n_contours) n_contours[s] = ncont;
+        std::sort(surv.begin(), surv.end(), [](const Surv &a, const Surv &b) { return a.key > b.key; });
+        if ((int)surv.size() > surv_cap) { surv.resize(surv_cap); status = 3; }
+        s_count[s] = (int)surv.size();
+        int w = 0;
+        if (s == dbg_scale && dbg_nkept) *dbg_nkept = (int)surv.size();
+        for (size_t i = 0; i < surv.size(); ++i) {
+            const Surv &e = surv[i];
+            std::vector<uint32_t> pts(e.len);
+            walk_write(mv, e.x, e.y, e.s0, e.len, pts.data());
+            if (s == dbg_scale) {
+                if (dbg_len && (int)i < dbg_cap) dbg_len[i] = e.len;
+                if (dbg_pts) for (int k = 0; k < e.len && w < dbg_pts_cap; ++k, ++w) { dbg_pts[2 * w] = (int16_t)px_of(pts[k]); dbg_pts[2 * w + 1] = (int16_t)py_of(pts[k]); }
+            }
+            int ox[8], oy[8];
+            SingleLane lg;
+            const int m = approx_closed(lg, pts.data(), e.len, (double)e.len * ep->approxRate, ox, oy);
+            const bool ok = (m == 4) && quad_passes(ox, oy, m, e.len, maxWH, ep->minCornerDistRate);
+            const size_t slot = (size_t)s * surv_cap + i;
+            q_ok[slot] = ok; q_len[slot] = e.len;
+            if (ok) for (int k = 0; k < 4; ++k) { q_xy[slot * 8 + 2 * k] = ox[k]; q_xy[slot * 8 + 2 * k + 1] = oy[k]; }
+        }
+    }
+    // per-frame logic
+    const int MC = ep->max_cand;
+    std::vector<float> cq((size_t)MC * 8), tq((size_t)MC * 8), tper(MC), wq((size_t)MC * 8);
+    std::vector<int32_t> clen(MC), gid(MC), sel(MC), gstart(MC + 1), gfill(MC), members(MC), closeIdx(MC), closeCnt(MC), S(MC), parent(MC), depth(MC),
+        selGroup(MC), wres(MC), closeStart(MC), closeNum(MC), counters(8, 0);
+    std::vector<uint32_t> closeM((size_t)MC * ((MC + 31) / 32));
+    FrameScratch fs{cq.data(), clen.data(), tq.data(), tper.data(), gid.data(), sel.data(), gstart.data(), gfill.data(), members.data(),
+                    closeIdx.data(), closeCnt.data(), S.data(), parent.data(), depth.data(), selGroup.data(), closeM.data(),
+                    wq.data(), wres.data(), closeStart.data(), closeNum.data(), counters.data()};
+    FrameParams fp;
+    fp.W = W; fp.H = H; fp.nScales = nS; fp.surv_cap = surv_cap; fp.max_cand = MC; fp.max_markers = ep->max_markers;
+    fp.markerSize = ep->markerSize; fp.borderBits = ep->borderBits; fp.minDistanceToBorder = ep->minDistanceToBorder;
+    fp.minMarkerDistanceRate = ep->minMarkerDistanceRate; fp.minGroupDistance = ep->minGroupDistance;
+    ScaleQuads sq{s_count.data(), q_ok.data(), q_xy.data(), q_len.data()};
+    HostCtx ctx;
+    counters[FC_STATUS] = status;
+    frame_group(ctx, fp, sq, fs, nullptr, 0);
+    if (n_cand) *n_cand = counters[FC_NCAND];
+    if (cand) std::memcpy(cand, cq.data(), (size_t)counters[FC_NCAND] * 8 * sizeof(float));
+    // identification of every work item (k_identify's body, one lane)
+    const int nb = ep->markerSize + 2 * ep->borderBits, Sz = nb * ep->cellSize, m0 = ep->cellSize / 2;
+    for (int w = 0; w < counters[FC_NWORK]; ++w) {
+        double M[9];
+        perspective_inverse(wq.data() + (size_t)w * 8, Sz, M);
+        std::vector<uint8_t> patch((size_t)Sz * Sz);
+        int hist[256] = {0};
+        long long sum = 0, sqs = 0;
+        for (int p = 0; p < Sz * Sz; ++p) {
+            const int y = p / Sz, x = p - y * Sz;
+            const unsigned v = warp_sample(gray, W, H, (size_t)W, M, x, y);
+            patch[p] = (uint8_t)v; hist[v]++;
+            if (x >= m0 && x < Sz - m0 && y >= m0 && y < Sz - m0) { sum += v; sqs += v * v; }
+        }
+        int mode, thr;
+        ident_decide(sum, sqs, Sz, m0, ep->minOtsuStdDev, hist, mode, thr);
+        std::vector<uint8_t> bits((size_t)nb * nb);
+        for (int c = 0; c < nb * nb; ++c) bits[c] = (uint8_t)((mode < 2) ? mode : ident_cell_bit(patch.data(), Sz, ep->cellSize, ep->cellMargin, c / nb, c % nb, thr));
+        unsigned long long code;
+        int res = 0;
+        if (ident_border_code(bits.data(), ep->markerSize, ep->borderBits, ep->maxBorderErr, code))
+            for (int m = 0; m < ep->nMarkers; ++m) {
+                int rot;
+                if (ident_marker_distance(dict + (size_t)m * 4, code, ep->markerSize, rot) <= ep->maxCorr) { res = (int)(0x80000000u | ((unsigned)m << 8) | (unsigned)rot); break; }
+            }
+        wres[w] = res;
+    }
+    int st = 0;
+    FrameOutputs fo{n_acc, n_rej, corners, ids, rejected, &st};
+    frame_finalize(ctx, fp, fs, fo);
+    return st;
+}
+
+void emu_pose(const float *corners, int n, const double *K9, const double *D5, float marker_length, double *rvecs, double *tvecs)
+{
+    Camera cam{K9[0], K9[4], K9[2], K9[5], D5[0], D5[1], D5[2], D5[3], D5[4]};
+    for (int i = 0; i < n; ++i) solve_marker_pose(cam, marker_length, corners + 8 * i, rvecs + 3 * i, tvecs + 3 * i);
+}
+
+// returns kept flag; obs = (x, y, theta, cov[9])
+int emu_observation(const float *corners, int id, const double *rvec, const double *tvec, const double *K9, const double *D5,
+                    double R_x, double R_y, double R_theta, double marker_length, double tx, double ty, float thr, double *obs12)
+{
+    Camera cam{K9[0], K9[4], K9[2], K9[5], D5[0], D5[1], D5[2], D5[3], D5[4]};
+    ObsParams op{R_x, R_y, R_theta, marker_length, tx, ty, thr};
+    Observation o;
+    if (!make_observation(cam, op, corners, id, rvec, tvec, o)) return 0;
+    obs12[0] = o.x; obs12[1] = o.y; obs12[2] = o.theta;
+    for (int i = 0; i < 9; ++i) obs12[3 + i] = o.cov[i];
+    return 1;
+}
+
+}  // extern "C"

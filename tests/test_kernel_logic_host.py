@@ -1,0 +1,91 @@
+"""CPU-only check of the product's kernel *logic* (aruco_slam_b200/csrc/core.h, frame_logic.h,
+pose_core.h) compiled for the host as a single lane (tests/hostemu) against the oracle and the
+cv2 golden vectors.  The CUDA kernels themselves are exercised by the `-m gpu` tests; this
+tier catches algorithmic slips without a GPU."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import golden, golden_names
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "hostemu"))
+import emu  # noqa: E402
+from aruco_slam_b200 import dictionaries as D, synth  # noqa: E402
+
+
+@pytest.mark.parametrize("name", golden_names("detect_") + golden_names("stages_"))
+def test_detect_logic_matches_golden(name):
+    g = golden(name)
+    dic = D.getPredefinedDictionary(int(g["dict_id"]))
+    r = emu.detect(g["frame"], dic)
+    assert r["status"] == 0
+    assert np.array_equal(r["ids"], g["ids"])
+    assert np.array_equal(r["corners"], g["corners"])
+    assert np.array_equal(r["rejected"], g["rejected"])
+    if "n_contours" in g.files and min(g["frame"].shape) >= 67:
+        assert np.array_equal(r["n_contours"], g["n_contours"])
+
+
+@pytest.mark.parametrize("name", golden_names("stages_"))
+def test_contour_points_match_golden(name):
+    g = golden(name)
+    H, W = g["frame"].shape
+    dic = D.getPredefinedDictionary(int(g["dict_id"]))
+    mn, mx = int(0.03 * max(W, H)), int(4.0 * max(W, H))
+    for si in range(3):
+        r = emu.detect(g["frame"], dic, dbg_scale=si)
+        offs, pts = g["cont_offs%d" % si], g["cont_pts%d" % si]
+        lens = np.diff(offs)
+        keep = [i for i, n in enumerate(lens) if mn <= n <= mx]
+        assert r["n_contours"][si] == len(lens)
+        assert np.array_equal(r["kept_len"], lens[keep])
+        want = np.concatenate([pts[offs[i]:offs[i + 1]] for i in keep]) if keep else np.zeros((0, 2), np.int16)
+        assert np.array_equal(r["kept_pts"], want)
+
+
+@pytest.mark.parametrize("p", [0.2, 0.5, 0.8])
+def test_contours_random_masks_vs_oracle(oracle, p):
+    rng = np.random.default_rng(int(p * 10))
+    m = ((rng.random((97, 131)) < p) * 255).astype(np.uint8)
+    dic = D.getPredefinedDictionary(0)
+    r = emu.detect(m, dic, masks=np.stack([m, m, m]), dbg_scale=0)
+    cs = oracle.find_contours(m)
+    mn, mx = int(0.03 * 131), 4 * 131
+    kept = [c for c in cs if mn <= len(c) <= mx]
+    assert r["n_contours"][0] == len(cs)
+    assert np.array_equal(r["kept_len"], [len(c) for c in kept])
+    assert np.array_equal(r["kept_pts"], np.concatenate(kept).astype(np.int16))
+
+
+def test_pose_logic_matches_golden():
+    g = golden("pose")
+    K, Dd = g["K"], g["D"]
+    wr = wt = 0.0
+    for row in g["rows"]:
+        L, use_d = float(row[0]), int(row[1])
+        r, t = emu.pose(row[2:10].astype(np.float32), K, Dd if use_d else np.zeros(5), L)
+        wr = max(wr, np.abs(r[0] - row[10:13]).max())
+        wt = max(wt, np.abs(t[0] - row[13:16]).max())
+    assert wr < 1e-4 and wt < 1e-4          # north_star tolerance
+    assert wr < 1e-5 and wt < 1e-5, (wr, wt)
+
+
+def test_observation_logic_matches_oracle(oracle):
+    g = golden("pose")
+    K, Dd = g["K"], g["D"]
+    sp = oracle.slam_params(useful_distance_threshold=3.0)
+    kept = 0
+    for i, row in enumerate(g["rows"][::7]):
+        corners = row[2:10].astype(np.float32)
+        dist = Dd if int(row[1]) else np.zeros(5)
+        sp.marker_length = float(row[0])
+        obs = oracle.make_observations(corners.reshape(1, 4, 2), [i], row[10:13].reshape(1, 3), row[13:16].reshape(1, 3), K, dist, sp)
+        ok, o = emu.observation(corners, i, row[10:13], row[13:16], K, dist, sp)
+        assert ok == (len(obs) == 1)
+        if ok:
+            kept += 1
+            assert abs(o[0] - obs[0].x) < 1e-12 and abs(o[1] - obs[0].y) < 1e-12 and abs(o[2] - obs[0].theta) < 1e-12
+            assert np.abs(o[3:] - np.array(obs[0].cov[:])).max() < 1e-12
+    assert kept > 5
