@@ -1,0 +1,133 @@
+"""ctypes loader of the product library `csrc/libb2aruco.so` (C ABI: include/b2aruco.h).
+
+There is no CPU fallback: if the library is missing, or no CUDA device can be
+opened, the calls raise -- loudly -- instead of computing anything on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "csrc", "libb2aruco.so")
+
+
+class B2AError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b2aruco error {code}: {msg}")
+        self.code = code
+
+
+class DetectorParams(C.Structure):
+    """cv::aruco::DetectorParameters (cv2 4.13.0 defaults via b2a_default_detector_params)."""
+    _fields_ = [
+        ("adaptiveThreshWinSizeMin", C.c_int), ("adaptiveThreshWinSizeMax", C.c_int),
+        ("adaptiveThreshWinSizeStep", C.c_int), ("adaptiveThreshConstant", C.c_double),
+        ("minMarkerPerimeterRate", C.c_double), ("maxMarkerPerimeterRate", C.c_double),
+        ("polygonalApproxAccuracyRate", C.c_double), ("minCornerDistanceRate", C.c_double),
+        ("minDistanceToBorder", C.c_int), ("minMarkerDistanceRate", C.c_double),
+        ("minGroupDistance", C.c_float), ("markerBorderBits", C.c_int),
+        ("perspectiveRemovePixelPerCell", C.c_int), ("perspectiveRemoveIgnoredMarginPerCell", C.c_double),
+        ("maxErroneousBitsInBorderRate", C.c_double), ("minOtsuStdDev", C.c_double),
+        ("errorCorrectionRate", C.c_double), ("cornerRefinementMethod", C.c_int),
+        ("cornerRefinementWinSize", C.c_int), ("relativeCornerRefinmentWinSize", C.c_double),
+        ("cornerRefinementMaxIterations", C.c_int), ("cornerRefinementMinAccuracy", C.c_double),
+        ("detectInvertedMarker", C.c_int),
+    ]
+
+
+class CDictionary(C.Structure):
+    _fields_ = [("markerSize", C.c_int), ("maxCorrectionBits", C.c_int), ("nMarkers", C.c_int),
+                ("nBytes", C.c_int), ("table", C.c_void_p)]
+
+
+class DetectorConfig(C.Structure):
+    _fields_ = [("device", C.c_int), ("max_width", C.c_int), ("max_height", C.c_int), ("max_batch", C.c_int),
+                ("max_markers", C.c_int), ("max_candidates", C.c_int)]
+
+
+class Frames(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("on_device", C.c_int), ("batch", C.c_int), ("width", C.c_int),
+                ("height", C.c_int), ("channels", C.c_int), ("row_stride", C.c_size_t), ("frame_stride", C.c_size_t)]
+
+
+class Detections(C.Structure):
+    _fields_ = [("batch", C.c_int), ("max_markers", C.c_int),
+                ("n_accepted", C.POINTER(C.c_int32)), ("n_rejected", C.POINTER(C.c_int32)),
+                ("corners", C.POINTER(C.c_float)), ("ids", C.POINTER(C.c_int32)), ("rejected", C.POINTER(C.c_float)),
+                ("rvecs", C.POINTER(C.c_double)), ("tvecs", C.POINTER(C.c_double)), ("status", C.POINTER(C.c_int32))]
+
+
+class Camera(C.Structure):
+    _fields_ = [("K", C.c_double * 9), ("D", C.c_double * 5), ("nD", C.c_int), ("marker_length", C.c_float)]
+
+
+class SlamParams(C.Structure):
+    _fields_ = [("Q_k", C.c_double), ("R_x", C.c_double), ("R_y", C.c_double), ("R_theta", C.c_double),
+                ("kl", C.c_double), ("kr", C.c_double), ("b", C.c_double), ("r2c_tx", C.c_double), ("r2c_ty", C.c_double),
+                ("useful_distance_threshold", C.c_float), ("max_landmarks", C.c_int)]
+
+
+class Observation(C.Structure):
+    _fields_ = [("aruco_id", C.c_int32), ("aruco_index", C.c_int32), ("x", C.c_double), ("y", C.c_double),
+                ("theta", C.c_double), ("cov", C.c_double * 9)]
+
+
+# every symbol include/b2aruco.h declares
+SYMBOLS = [
+    "b2a_last_error", "b2a_version", "b2a_default_detector_params", "b2a_get_predefined_dictionary",
+    "b2a_detector_create", "b2a_detector_destroy", "b2a_detect", "b2a_detect_pose",
+    "b2a_estimate_pose_single_markers", "b2a_debug_threshold", "b2a_debug_contours", "b2a_debug_candidates",
+    "b2a_detector_num_scales", "b2a_last_stage_times", "b2a_last_launch_count", "b2a_detector_stream",
+    "b2a_default_slam_params", "b2a_slam_create", "b2a_slam_destroy", "b2a_slam_dim", "b2a_slam_get_state",
+    "b2a_slam_set_state", "b2a_slam_add_encoder", "b2a_slam_make_observations", "b2a_slam_update", "b2a_slam_add_image",
+]
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile csrc/libb2aruco.so in-tree with nvcc for sm_100a (no GPU needed to compile)."""
+    args = ["make", "-C", os.path.join(_HERE, "csrc"), "-s", "libb2aruco.so"]
+    if force:
+        args.insert(1, "-B")
+    subprocess.check_call(args)
+    return SO_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise B2AError(-1, f"{SO_PATH} is not built (run __graft_entry__.build() or make -C aruco_slam_b200/csrc); "
+                               "there is no CPU fallback")
+        L = C.CDLL(SO_PATH)
+        L.b2a_last_error.restype = C.c_char_p
+        L.b2a_version.restype = C.c_char_p
+        L.b2a_detector_stream.restype = C.c_void_p
+        for name in ("b2a_detector_destroy", "b2a_detector_num_scales", "b2a_last_launch_count", "b2a_detector_stream",
+                     "b2a_slam_destroy", "b2a_slam_dim"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.b2a_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2a_detect_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2a_estimate_pose_single_markers.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2a_debug_threshold.argtypes = [C.c_void_p] * 4
+        L.b2a_debug_contours.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.b2a_debug_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.b2a_last_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.b2a_slam_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.b2a_slam_get_state.argtypes = [C.c_void_p] * 4
+        L.b2a_slam_set_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2a_slam_add_encoder.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.b2a_slam_make_observations.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2a_slam_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.b2a_slam_add_image.argtypes = [C.c_void_p] * 4
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise B2AError(rc, lib().b2a_last_error().decode())

@@ -1,0 +1,259 @@
+"""Host-side mirror of the call surface the reference uses (src/aruco_slam.cpp:11-12, 313-314):
+
+    dictionary = getPredefinedDictionary(id)
+    corners, ids, rejected = detectMarkers(image, dictionary, parameters)
+    rvecs, tvecs = estimatePoseSingleMarkers(corners, markerLength, cameraMatrix, distCoeffs)
+
+with the same argument meaning and result shapes as the `cv2.aruco` Python binding
+(corners: tuple of (1,4,2) float32; ids: (N,1) int32 or None; rvecs/tvecs: (N,1,3) float64),
+plus batched entry points (`ArucoDetector.detect_batch` / `detect_pose_batch`) that the
+benchmark uses.  All compute happens in the CUDA library behind include/b2aruco.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import B2AError, DetectorParams
+from .dictionaries import Dictionary, getPredefinedDictionary  # noqa: F401  (re-export)
+
+CORNER_REFINE_NONE, CORNER_REFINE_SUBPIX = 0, 1
+
+
+def DetectorParameters(**overrides) -> DetectorParams:
+    """cv::aruco::DetectorParameters with the library's defaults."""
+    p = DetectorParams()
+    _lib.lib().b2a_default_detector_params(C.byref(p))
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def _cdict(dic: Dictionary):
+    t = np.ascontiguousarray(dic.table, np.uint8)
+    cd = _lib.CDictionary(dic.marker_size, dic.max_correction_bits, dic.n_markers, dic.n_bytes, t.ctypes.data)
+    return cd, t
+
+
+def library_dictionary(dict_id: int) -> Dictionary:
+    """The table compiled into the library (b2a_get_predefined_dictionary)."""
+    cd = _lib.CDictionary()
+    _lib.check(_lib.lib().b2a_get_predefined_dictionary(int(dict_id), C.byref(cd)))
+    n = cd.nMarkers * 4 * cd.nBytes
+    buf = (C.c_uint8 * n).from_address(cd.table)
+    table = np.frombuffer(buf, np.uint8).reshape(cd.nMarkers, 4, cd.nBytes).copy()
+    return Dictionary(dict_id, "lib", cd.markerSize, cd.maxCorrectionBits, table)
+
+
+def _camera(K, D, marker_length) -> _lib.Camera:
+    cam = _lib.Camera()
+    K = np.asarray(K, np.float64).reshape(9)
+    for i in range(9):
+        cam.K[i] = K[i]
+    D = np.zeros(0) if D is None else np.asarray(D, np.float64).reshape(-1)
+    if len(D) not in (0, 4, 5):
+        raise B2AError(1, "distCoeffs must have 0, 4 or 5 entries")
+    for i in range(len(D)):
+        cam.D[i] = D[i]
+    cam.nD = len(D)
+    cam.marker_length = float(marker_length)
+    return cam
+
+
+@dataclass
+class BatchDetections:
+    """Per-frame lists in the reference's output order."""
+    corners: list      # [frame] -> (n,4,2) float32
+    ids: list          # [frame] -> (n,) int32
+    rejected: list     # [frame] -> (m,4,2) float32
+    rvecs: list | None = None   # [frame] -> (n,3) float64
+    tvecs: list | None = None
+
+
+class ArucoDetector:
+    """One detector handle (one GPU, one stream).  `max_shape` = (H, W) of the largest frame."""
+
+    def __init__(self, dictionary: Dictionary, parameters: DetectorParams | None = None, *, max_shape=(1080, 1920),
+                 max_batch: int = 1, device: int = 0, max_markers: int = 256, max_candidates: int = 2048):
+        self.dictionary = dictionary
+        self.parameters = parameters or DetectorParameters()
+        cfg = _lib.DetectorConfig(int(device), int(max_shape[1]), int(max_shape[0]), int(max_batch), int(max_markers), int(max_candidates))
+        cd, self._keep = _cdict(dictionary)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().b2a_detector_create(C.byref(cfg), C.byref(cd), C.byref(self.parameters), C.byref(h)))
+        self._h = h
+        self.max_markers = max_markers
+        self.max_batch = max_batch
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().b2a_detector_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- frames descriptor -------------------------------------------------------------------
+    @staticmethod
+    def _frames_host(images: np.ndarray):
+        a = np.asarray(images)
+        if a.dtype != np.uint8:
+            raise B2AError(1, "image must be uint8 (CV_8UC1 or CV_8UC3)")
+        if a.ndim == 2:
+            a = a[None]
+        elif a.ndim == 3 and a.shape[2] == 3 and a.shape[0] != 3:
+            a = a[None]                 # one (H,W,3) colour frame
+        if a.ndim == 3:
+            ch = 1
+        elif a.ndim == 4 and a.shape[3] in (1, 3):
+            ch = a.shape[3]
+        else:
+            raise B2AError(1, "expected (H,W), (H,W,3), (B,H,W) or (B,H,W,3) uint8")
+        a = np.ascontiguousarray(a)
+        B, H, W = a.shape[:3]
+        if a.size == 0:
+            raise B2AError(1, "empty image")
+        return _lib.Frames(a.ctypes.data, 0, B, W, H, ch, 0, 0), a
+
+    @staticmethod
+    def frames_device(ptr: int, batch: int, height: int, width: int, channels: int = 1, row_stride: int = 0, frame_stride: int = 0):
+        """Frames already resident in device memory (e.g. a torch uint8 CUDA tensor's data_ptr())."""
+        return _lib.Frames(int(ptr), 1, batch, width, height, channels, row_stride, frame_stride)
+
+    # ---- batched API -------------------------------------------------------------------------
+    def _collect(self, det, pose) -> BatchDetections:
+        B, K = det.batch, det.max_markers
+        na = np.ctypeslib.as_array(det.n_accepted, (B,))
+        nr = np.ctypeslib.as_array(det.n_rejected, (B,))
+        c = np.ctypeslib.as_array(det.corners, (B, K, 4, 2))
+        i = np.ctypeslib.as_array(det.ids, (B, K))
+        r = np.ctypeslib.as_array(det.rejected, (B, K, 4, 2))
+        out = BatchDetections([c[b, :na[b]].copy() for b in range(B)], [i[b, :na[b]].copy() for b in range(B)],
+                              [r[b, :nr[b]].copy() for b in range(B)])
+        if pose:
+            rv = np.ctypeslib.as_array(det.rvecs, (B, K, 3))
+            tv = np.ctypeslib.as_array(det.tvecs, (B, K, 3))
+            out.rvecs = [rv[b, :na[b]].copy() for b in range(B)]
+            out.tvecs = [tv[b, :na[b]].copy() for b in range(B)]
+        return out
+
+    def detect_raw(self, frames, camera=None):
+        """Run the pipeline; returns the C struct (pinned host buffers valid until the next call)."""
+        det = _lib.Detections()
+        if camera is None:
+            _lib.check(_lib.lib().b2a_detect(self._h, C.byref(frames), C.byref(det)))
+        else:
+            _lib.check(_lib.lib().b2a_detect_pose(self._h, C.byref(frames), C.byref(camera), C.byref(det)))
+        return det
+
+    def detect_batch(self, images) -> BatchDetections:
+        fr, keep = self._frames_host(images) if not isinstance(images, _lib.Frames) else (images, None)
+        return self._collect(self.detect_raw(fr), False)
+
+    def detect_pose_batch(self, images, marker_length, K, D) -> BatchDetections:
+        fr, keep = self._frames_host(images) if not isinstance(images, _lib.Frames) else (images, None)
+        return self._collect(self.detect_raw(fr, _camera(K, D, marker_length)), True)
+
+    # ---- cv2-shaped single-image API -----------------------------------------------------------
+    def detectMarkers(self, image):
+        a = np.asarray(image)
+        if a.ndim not in (2, 3):
+            raise B2AError(1, "detectMarkers takes one image")
+        r = self.detect_batch(a if a.ndim == 2 or a.shape[2] == 3 else a[..., 0])
+        corners = tuple(c.reshape(1, 4, 2) for c in r.corners[0])
+        ids = r.ids[0].reshape(-1, 1) if len(r.ids[0]) else None
+        rejected = tuple(c.reshape(1, 4, 2) for c in r.rejected[0])
+        return corners, ids, rejected
+
+    def estimatePoseSingleMarkers(self, corners, markerLength, cameraMatrix, distCoeffs):
+        c = np.ascontiguousarray(np.asarray(corners, np.float32).reshape(-1, 8))
+        n = len(c)
+        if not markerLength > 0:
+            raise B2AError(1, "markerLength must be > 0")
+        rv = np.zeros((n, 3))
+        tv = np.zeros((n, 3))
+        cam = _camera(cameraMatrix, distCoeffs, markerLength)
+        _lib.check(_lib.lib().b2a_estimate_pose_single_markers(self._h, c.ctypes.data, n, C.byref(cam), rv.ctypes.data, tv.ctypes.data))
+        return rv.reshape(n, 1, 3), tv.reshape(n, 1, 3)
+
+    # ---- stage taps (parity tests) ---------------------------------------------------------------
+    @property
+    def num_scales(self) -> int:
+        return _lib.lib().b2a_detector_num_scales(self._h)
+
+    def debug_threshold(self, images):
+        fr, keep = self._frames_host(images)
+        gray = np.zeros((fr.batch, fr.height, fr.width), np.uint8)
+        masks = np.zeros((fr.batch, self.num_scales, fr.height, fr.width), np.uint8)
+        _lib.check(_lib.lib().b2a_debug_threshold(self._h, C.byref(fr), gray.ctypes.data, masks.ctypes.data))
+        return gray, masks
+
+    def debug_contours(self, images, cap=4096, pts_cap=None):
+        fr, keep = self._frames_host(images)
+        nS = self.num_scales
+        pts_cap = pts_cap or (fr.width * fr.height) // 4
+        counts = np.zeros((fr.batch, nS), np.int32)
+        kept = np.zeros((fr.batch, nS), np.int32)
+        lens = np.zeros((fr.batch, nS, cap), np.int32)
+        pts = np.zeros((fr.batch, nS, pts_cap, 2), np.int16)
+        _lib.check(_lib.lib().b2a_debug_contours(self._h, C.byref(fr), counts.ctypes.data, kept.ctypes.data, lens.ctypes.data, cap,
+                                                 pts.ctypes.data, pts_cap))
+        return counts, kept, lens, pts
+
+    def debug_candidates(self, images, cap=2048):
+        fr, keep = self._frames_host(images)
+        n = np.zeros(fr.batch, np.int32)
+        q = np.zeros((fr.batch, cap, 4, 2), np.float32)
+        _lib.check(_lib.lib().b2a_debug_candidates(self._h, C.byref(fr), n.ctypes.data, q.ctypes.data, cap))
+        return [q[b, :n[b]].copy() for b in range(fr.batch)]
+
+    def last_stage_times(self) -> dict:
+        names = (C.c_char_p * 32)()
+        ms = (C.c_float * 32)()
+        k = _lib.lib().b2a_last_stage_times(self._h, names, ms, 32)
+        return {names[i].decode(): float(ms[i]) for i in range(k)}
+
+    def last_launch_count(self) -> int:
+        return _lib.lib().b2a_last_launch_count(self._h)
+
+    @property
+    def stream(self) -> int:
+        return int(_lib.lib().b2a_detector_stream(self._h) or 0)
+
+
+# ---- free functions shaped like the legacy cv::aruco API the reference calls -------------------------
+_detectors: dict = {}
+
+
+def _cached_detector(dictionary, parameters, shape, device=0):
+    key = (dictionary.dict_id, dictionary.table.tobytes()[:64], bytes(parameters), shape, device)
+    d = _detectors.get(key)
+    if d is None:
+        if len(_detectors) > 8:
+            _detectors.pop(next(iter(_detectors))).close()
+        d = _detectors[key] = ArucoDetector(dictionary, parameters, max_shape=shape, max_batch=1, device=device)
+    return d
+
+
+def detectMarkers(image, dictionary: Dictionary, parameters: DetectorParams | None = None):
+    """cv::aruco::detectMarkers(image, dictionary, corners, ids, parameters, rejectedImgPoints)."""
+    a = np.asarray(image)
+    if a.size == 0:
+        raise B2AError(1, "empty image")
+    p = parameters or DetectorParameters()
+    return _cached_detector(dictionary, p, a.shape[:2]).detectMarkers(a)
+
+
+def estimatePoseSingleMarkers(corners, markerLength, cameraMatrix, distCoeffs, dictionary: Dictionary | None = None):
+    """cv::aruco::estimatePoseSingleMarkers -> (rvecs (N,1,3), tvecs (N,1,3))."""
+    dic = dictionary or getPredefinedDictionary(0)
+    return _cached_detector(dic, DetectorParameters(), (64, 64)).estimatePoseSingleMarkers(corners, markerLength, cameraMatrix, distCoeffs)

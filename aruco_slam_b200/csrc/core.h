@@ -1,7 +1,7 @@
 // core.h -- per-thread / per-warp building blocks of the detect path, written so that the
 // same source compiles for the device (inside the kernels of detect_kernels.cuh) and for the
 // host (tests/hostemu: a single-lane emulation used by the CPU-only tests to check the
-// kernel logic against the oracle; it is test infrastructure, never a product path).
+// kernel logic against the CPU restatement; it is test infrastructure, never a product path).
 //
 // What each block replaces inside cv::aruco::detectMarkers (reference src/aruco_slam.cpp:313;
 // algorithm per SURVEY.md Appendix A, OpenCV 4.13.0):

@@ -5,7 +5,7 @@
 // Replaces the corresponding parts of cv::aruco::detectMarkers (reference
 // src/aruco_slam.cpp:313).  Written against a small "Ctx" (tid / nthreads / sync / scan) so
 // that the identical source runs as a CUDA block on the device and as one sequential lane in
-// tests/hostemu (CPU-only logic check against the oracle; test infrastructure only).
+// tests/hostemu (CPU-only logic check against the CPU restatement; test infrastructure only).
 #pragma once
 #include "core.h"
 

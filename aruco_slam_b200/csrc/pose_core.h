@@ -211,6 +211,8 @@ B2A_HD void solve_marker_pose(const Camera &cam, float marker_length, const floa
     nearest_rotation(R);
     const double sc = 2. / (n1 + n2);
     t[0] = hm[2] * sc; t[1] = hm[5] * sc; t[2] = hm[8] * sc;
+    double r0[3];
+    R_to_rodrigues(R, r0);        // solvePnP iterates on the rotation vector from here (see the end)
     // ---- Levenberg-Marquardt ----
     double res[8], J[48];
     double e = pose_residuals(cam, obj, ip, R, t, res, J);
@@ -256,6 +258,18 @@ B2A_HD void solve_marker_pose(const Camera &cam, float marker_length, const floa
     }
     nearest_rotation(R);          // remove accumulated drift before taking the log
     R_to_rodrigues(R, rvec);
+    // cv2.solvePnP refines the rotation *vector* continuously from its initial value, so near a
+    // half turn it can return |rvec| > pi.  Report the same branch: of the two equivalent
+    // vectors r and r (1 - 2 pi / |r|) take the one closer to the initial rotation vector.
+    {
+        const double nr = sqrt(rvec[0] * rvec[0] + rvec[1] * rvec[1] + rvec[2] * rvec[2]);
+        if (nr > 1e-9) {
+            const double f = 1.0 - 2.0 * 3.14159265358979323846 / nr;
+            double d1 = 0, d2 = 0;
+            for (int i = 0; i < 3; ++i) { const double a = rvec[i] - r0[i], b = rvec[i] * f - r0[i]; d1 += a * a; d2 += b * b; }
+            if (d2 < d1) { rvec[0] *= f; rvec[1] *= f; rvec[2] *= f; }
+        }
+    }
     tvec[0] = t[0]; tvec[1] = t[1]; tvec[2] = t[2];
 }
 

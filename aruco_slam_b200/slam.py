@@ -1,0 +1,110 @@
+"""Host-side mirror of the reference's `ArucoSlam` class (include/aruco_slam/aruco_slam.h:101-193):
+addEncoder / addImage / setCameraParameters and state accessors, with the detection, pose,
+observation mapping and EKF arithmetic running on the GPU behind include/b2aruco.h.
+No ROS types: poses and covariances are plain arrays; `dt` is explicit (the reference reads
+ros::Time::now(), src/aruco_slam.cpp:26,31-32)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .aruco import ArucoDetector, DetectorParameters, _camera
+from .dictionaries import getPredefinedDictionary
+
+
+def slam_params(**kw) -> _lib.SlamParams:
+    """defaults: reference parameters.yaml:5-13 and aruco_slam.h:58"""
+    p = _lib.SlamParams()
+    _lib.lib().b2a_default_slam_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+class ArucoSlam:
+    def __init__(self, markers_dictionary: int = 16, marker_length: float = 0.27, *, image_shape=(480, 640), device: int = 0,
+                 detector_parameters=None, **slam_kw):
+        self.marker_length = float(marker_length)
+        self.params = slam_params(**slam_kw)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().b2a_slam_create(int(device), C.byref(self.params), C.byref(h)))
+        self._h = h
+        self.detector = ArucoDetector(getPredefinedDictionary(markers_dictionary), detector_parameters or DetectorParameters(),
+                                      max_shape=image_shape, max_batch=1, device=device)
+        self._cam = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().b2a_slam_destroy(self._h)
+            self._h = None
+        if getattr(self, "detector", None):
+            self.detector.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setCameraParameters(self, camera_matrix, dist_coeffs):
+        """aruco_slam.h:129-133"""
+        self._cam = _camera(camera_matrix, dist_coeffs, self.marker_length)
+
+    def addEncoder(self, wl: float, wr: float, dt: float):
+        """src/aruco_slam.cpp:21-74; the first call only latches time in the reference (:24-29):
+        pass dt=None for that call."""
+        if dt is None:
+            # latch: marks the filter initialised without moving it
+            _lib.check(_lib.lib().b2a_slam_add_encoder(self._h, 0.0, 0.0, 0.0))
+            return
+        _lib.check(_lib.lib().b2a_slam_add_encoder(self._h, float(wl), float(wr), float(dt)))
+
+    def addImage(self, image):
+        """src/aruco_slam.cpp:76-263"""
+        if self._cam is None:
+            raise _lib.B2AError(1, "setCameraParameters first")
+        fr, keep = ArucoDetector._frames_host(image)
+        _lib.check(_lib.lib().b2a_slam_add_image(self._h, self.detector._h, C.byref(fr), C.byref(self._cam)))
+
+    def make_observations(self, corners, ids, rvecs, tvecs):
+        c = np.ascontiguousarray(corners, np.float32).reshape(-1, 8)
+        n = len(c)
+        ids = np.ascontiguousarray(ids, np.int32).reshape(-1)
+        out = (_lib.Observation * max(n, 1))()
+        k = C.c_int(0)
+        _lib.check(_lib.lib().b2a_slam_make_observations(
+            self._h, c.ctypes.data, ids.ctypes.data, np.ascontiguousarray(rvecs, np.float64).ctypes.data,
+            np.ascontiguousarray(tvecs, np.float64).ctypes.data, n, C.byref(self._cam), out, C.byref(k)))
+        return [out[i] for i in range(k.value)]
+
+    def update(self, observations):
+        n = len(observations)
+        arr = (_lib.Observation * max(n, 1))(*observations)
+        _lib.check(_lib.lib().b2a_slam_update(self._h, arr, n))
+
+    @property
+    def dim(self) -> int:
+        return _lib.lib().b2a_slam_dim(self._h)
+
+    def get_state(self):
+        N = self.dim
+        mu = np.zeros(N)
+        sg = np.zeros((N, N))
+        ids = np.zeros(max((N - 3) // 3, 1), np.int32)
+        _lib.check(_lib.lib().b2a_slam_get_state(self._h, mu.ctypes.data, sg.ctypes.data, ids.ctypes.data))
+        return mu, sg, ids[:(N - 3) // 3]
+
+    def set_state(self, mu, sigma, ids):
+        mu = np.ascontiguousarray(mu, np.float64)
+        sigma = np.ascontiguousarray(sigma, np.float64)
+        ids = np.ascontiguousarray(ids, np.int32)
+        _lib.check(_lib.lib().b2a_slam_set_state(self._h, len(mu), mu.ctypes.data, sigma.ctypes.data, ids.ctypes.data if len(ids) else None))
+
+    def robot_pose(self):
+        """toRosPose() without ROS (src/aruco_slam.cpp:378-410): (x, y, theta) and the 3x3 covariance block."""
+        mu, sg, _ = self.get_state()
+        return mu[:3].copy(), sg[:3, :3].copy()

@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of detect+pose on synthetic 1080p DICT_6X6_250 frames (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2] [--batch 32]
+
+One "step" = one pass of the hot path (detectMarkers + estimatePoseSingleMarkers, reference
+src/aruco_slam.cpp:313-314) over one batch of frames per GPU.  Frames are independent, so N GPUs run
+N independent shards (weak scaling, no collective on the data path); torch.distributed is used only
+for the barrier and the max-over-ranks of the timed region.
+
+  value  : whole-job frames/s with the frames already resident in HBM (CUDA events on the library's
+           stream around K steps, detections copied back to pinned host memory inside the region).
+  e2e    : the same through the public API with HOST (pinned) frames: H2D of the frames and D2H of
+           the detections inside the timed region.
+  roofline    : the adaptive-threshold kernel (the streaming stage), algorithmic bytes / its CUDA-event time.
+  cpu_baseline: the reference's CPU path (cv2 4.13 wheel = the library the reference calls) or, if cv2 is
+           not importable, the C port in oracle/, on a bounded sample of the same frames.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from aruco_slam_b200 import synth, dictionaries as D  # noqa: E402
+
+K_CAM = np.array([[1400.0, 0, 960], [0, 1400.0, 540], [0, 0, 1]])
+D_CAM = np.array([0.05, -0.1, 0.001, -0.002, 0.02])
+MARKER_LENGTH = 0.27                    # reference parameters.yaml:17
+WORKLOADS = {
+    "C1": ("640x480 gray, 4 DICT_4X4_50 markers", D.DICT_4X4_50),
+    "C2": ("1920x1080 gray, 30 DICT_6X6_250 markers", D.DICT_6X6_250),
+    "C3": ("3840x2160 gray, 100 DICT_6X6_250 markers, noise sigma 4, blur sigma 1", D.DICT_6X6_250),
+}
+
+
+def measured_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:6]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def result(self):
+        self.stop_flag = True
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU reference arm
+# ----------------------------------------------------------------------------------------------
+def _cpu_worker_init(use_cv2, dict_id):
+    global _W
+    _W = {}
+    if use_cv2:
+        import cv2
+        cv2.setNumThreads(1)
+        _W["det"] = cv2.aruco.ArucoDetector(cv2.aruco.getPredefinedDictionary(dict_id), cv2.aruco.DetectorParameters())
+        h = np.float32(MARKER_LENGTH) / np.float32(2)
+        _W["obj"] = np.array([[-h, h, 0], [h, h, 0], [h, -h, 0], [-h, -h, 0]], np.float32)
+        _W["cv2"] = cv2
+    else:
+        from oracle import oracle as O
+        _W["O"] = O
+        _W["dic"] = D.getPredefinedDictionary(dict_id)
+
+
+def _cpu_worker(frame):
+    if "cv2" in _W:
+        cv2 = _W["cv2"]
+        corners, ids, _ = _W["det"].detectMarkers(frame)
+        n = 0
+        for c in corners:                       # estimatePoseSingleMarkers == per-marker solvePnP (ITERATIVE)
+            cv2.solvePnP(_W["obj"], c.reshape(-1, 1, 2), K_CAM, D_CAM)
+            n += 1
+        return n
+    O = _W["O"]
+    c, ids, _ = O.detect(frame, _W["dic"])
+    O.estimate_pose_single_markers(c, MARKER_LENGTH, K_CAM, D_CAM)
+    return len(ids)
+
+
+def cpu_reference_fps(frames, dict_id, seconds_target=12.0, max_passes=50, pool=None):
+    """frames/s of the CPU path, frame-parallel over all host cores (the CPU's best case)."""
+    import multiprocessing as mp
+    try:
+        import cv2  # noqa: F401
+        use_cv2 = True
+    except Exception:
+        use_cv2 = False
+    cores = os.cpu_count() or 1
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(cores, initializer=_cpu_worker_init, initargs=(use_cv2, dict_id))
+    lst = [f for f in frames]
+    pool.map(_cpu_worker, lst[:min(len(lst), cores)])            # warm-up
+    t0 = time.perf_counter()
+    done = 0
+    passes = 0
+    while passes < max_passes:
+        pool.map(_cpu_worker, lst, chunksize=max(1, len(lst) // (cores * 2) or 1))
+        done += len(lst)
+        passes += 1
+        if time.perf_counter() - t0 > seconds_target:
+            break
+    dt = time.perf_counter() - t0
+    if own:
+        pool.close()
+    kind = "reference" if use_cv2 else "port"
+    what = ("cv2 4.13 ArucoDetector.detectMarkers + per-marker solvePnP(ITERATIVE)" if use_cv2 else "oracle/ C port (detect + pose)")
+    return done / dt, cores, kind, "%s, %d passes over %d frames, %d worker processes x 1 thread" % (what, passes, len(lst), cores)
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    desc, dict_id = WORKLOADS[args.workload]
+    cfg = synth.CONFIGS[args.workload]
+    W, H, B = cfg["W"], cfg["H"], args.batch
+    config = {"workload": "%s: %s, batch %d per GPU, detect+pose" % (args.workload, desc, B), "batch_per_gpu": B,
+              "l2": "L2 flushed (256 MiB write) between timed steps", "parallelism": "frame shards, %d GPU(s), no collective" % world}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        frames = synth.render_batch(args.workload, B, base_seed=0)
+        import multiprocessing as mp
+        try:
+            import cv2  # noqa: F401
+            use_cv2 = True
+        except Exception:
+            use_cv2 = False
+        cores = os.cpu_count() or 1
+        pool = mp.get_context("fork").Pool(cores, initializer=_cpu_worker_init, initargs=(use_cv2, dict_id))
+        lst = [f for f in frames]
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_cpu_worker, lst)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_worker, lst)
+        dt = time.perf_counter() - t0
+        pool.close()
+        fps = args.steps * B / dt
+        kind = "reference" if use_cv2 else "port"
+        sample = ("cv2 4.13 detectMarkers + per-marker solvePnP" if use_cv2 else "oracle/ C port") + \
+                 ", %d steps x %d frames, %d worker processes x 1 thread" % (args.steps, B, cores)
+        print(json.dumps({"impl": "reference", "metric": "frames/sec detect+pose", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
+                          "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from aruco_slam_b200 import aruco
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    frames = synth.render_batch(args.workload, B, base_seed=1000 * rank)          # this rank's shard
+    dic = D.getPredefinedDictionary(dict_id)
+    det = aruco.ArucoDetector(dic, max_shape=(H, W), max_batch=B, device=local_rank)
+    cam = aruco._camera(K_CAM, D_CAM, MARKER_LENGTH)
+    d_frames = torch.from_numpy(frames).cuda()
+    h_frames = torch.from_numpy(frames).pin_memory()
+    fr_dev = aruco.ArucoDetector.frames_device(d_frames.data_ptr(), B, H, W)
+    fr_host, _keep = aruco.ArucoDetector._frames_host(h_frames.numpy())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    lib_stream = torch.cuda.ExternalStream(det.stream, device=local_rank)
+
+    # parity spot check against the CPU port (checker only; not in the timed region)
+    parity = "unchecked"
+    if rank == 0:
+        from oracle import oracle as O
+        r = det._collect(det.detect_raw(fr_dev, cam), True)
+        ok = True
+        for b in (0, B - 1):
+            oc, oi, orj = O.detect(frames[b], dic)
+            orv, otv = O.estimate_pose_single_markers(oc, MARKER_LENGTH, K_CAM, D_CAM)
+            ok &= np.array_equal(r.ids[b], oi) and np.array_equal(r.corners[b], oc) and np.array_equal(r.rejected[b], orj)
+            ok &= bool(len(oi) == 0 or (np.abs(r.rvecs[b] - orv).max() < 1e-4 and np.abs(r.tvecs[b] - otv).max() < 1e-4))
+        parity = "ok" if ok else "MISMATCH"
+        n_markers = int(sum(len(x) for x in r.ids))
+    else:
+        n_markers = 0
+
+    def run(frames_desc, steps, warmup):
+        stage_acc, launches = {}, 0
+        for _ in range(warmup):
+            det.detect_raw(frames_desc, cam)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total_ms = 0.0
+        for _ in range(steps):
+            flush.fill_(1)                                     # evict L2 between timed steps
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(lib_stream)
+            det.detect_raw(frames_desc, cam)                   # launches on lib_stream, returns after the D2H completed
+            e1.record(lib_stream)
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+            launches += det.last_launch_count()
+            for k, v in det.last_stage_times().items():
+                stage_acc[k] = stage_acc.get(k, 0.0) + v
+        torch.cuda.synchronize()
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), {k: v / steps for k, v in stage_acc.items()}, launches
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, stages, launches = run(fr_dev, args.steps, args.warmup)
+    ms_e2e, stages_e2e, _ = run(fr_host, args.steps, args.warmup)
+    clocks = sampler.result() if rank == 0 else None
+
+    if rank == 0:
+        total_frames = world * B * args.steps
+        value = total_frames / (ms_dev * 1e-3)
+        e2e = total_frames / (ms_e2e * 1e-3)
+        P = W * H
+        nS = det.num_scales
+        peak, which = measured_peak_gbs()
+        thr_bytes = B * (P + nS * (P // 8))                    # read gray + write nS bit-packed masks
+        thr_ms = stages.get("threshold", 0.0)
+        achieved = thr_bytes / (thr_ms * 1e-3) / 1e9 if thr_ms > 0 else 0.0
+        K = det.max_markers
+        d2h = B * (3 * 4 + K * (32 + 4 + 32 + 24 + 24))
+        out = {
+            "metric": "frames/sec detect+pose (1080p, DICT_6X6_250)" if args.workload == "C2" else "frames/sec detect+pose (%s)" % args.workload,
+            "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 (detect) / f64 (pose)", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * P, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "k_threshold", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": which,
+                         "algorithmic_bytes_per_launch": thr_bytes,
+                         "note": "bytes = B*(P + nScales*P/8): gray read once, bit-packed masks written; SURVEY's 4P/frame assumes byte masks",
+                         "pipeline_frac_7P": (value / world) * 7 * P / (peak * 1e9)},
+            "stages_ms_per_step": {k: round(v, 4) for k, v in stages.items()},
+            "stages_ms_per_step_e2e": {k: round(v, 4) for k, v in stages_e2e.items()},
+            "parity": parity, "markers_per_step": n_markers,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            fps, cores, kind, sample = cpu_reference_fps(frames, dict_id)
+            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
+        print(json.dumps(out))
+    det.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

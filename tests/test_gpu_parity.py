@@ -1,0 +1,229 @@
+"""-m gpu: the CUDA path (through the C ABI, include/b2aruco.h) against the CPU oracle and the
+cv2 golden vectors.  Bars (BASELINE.json north_star): ids and threshold masks bit-exact;
+corners <= 0.05 px; rvec <= 1e-4 rad, tvec <= 1e-4 m; accepted / rejected lists in the
+reference's order.  Without sub-pixel refinement corners are integer valued, so they are
+compared for equality."""
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import golden, golden_names
+from aruco_slam_b200 import dictionaries as D, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def aruco():
+    from aruco_slam_b200 import aruco as A
+    return A
+
+
+def _detector(A, dic, shape, batch=1, **prm):
+    return A.ArucoDetector(dic, A.DetectorParameters(**prm), max_shape=shape, max_batch=batch)
+
+
+@pytest.mark.parametrize("name", golden_names("stages_"))
+def test_stage_taps_vs_golden(aruco, oracle, name):
+    g = golden(name)
+    gray = g["frame"]
+    H, W = gray.shape
+    dic = D.getPredefinedDictionary(int(g["dict_id"]))
+    det = _detector(aruco, dic, gray.shape)
+    # A1 + A2 through the colour path
+    bgr = synth.gray_to_bgr(gray, 7)
+    gg, masks = det.debug_threshold(bgr)
+    assert zlib.crc32(gg[0].tobytes()) == int(g["bgr_gray_crc"])
+    # A2 on the gray frame: masks bit-exact
+    gg, masks = det.debug_threshold(gray)
+    assert np.array_equal(gg[0], gray)
+    for si in range(3):
+        assert np.array_equal(np.packbits(masks[0, si] > 0), g["mask%d" % si]), si
+    # A3a: contour count, kept contours (order, lengths, points)
+    counts, kept, lens, pts = det.debug_contours(gray, pts_cap=W * H)
+    mn, mx = int(0.03 * max(W, H)), int(4.0 * max(W, H))
+    for si in range(3):
+        offs, gp = g["cont_offs%d" % si], g["cont_pts%d" % si]
+        L = np.diff(offs)
+        keep = [i for i, n in enumerate(L) if mn <= n <= mx]
+        assert counts[0, si] == len(L)
+        assert kept[0, si] == len(keep)
+        assert np.array_equal(lens[0, si, :len(keep)], L[keep])
+        want = np.concatenate([gp[offs[i]:offs[i + 1]] for i in keep]) if keep else np.zeros((0, 2), np.int16)
+        assert np.array_equal(pts[0, si, :len(want)], want)
+    # A3/A4 candidates vs oracle
+    _, _, _, dbg = oracle.detect(gray, dic, debug=True)
+    cand = det.debug_candidates(gray)[0]
+    assert np.array_equal(cand, dbg["cand"])
+    # final
+    c, ids, rej = det.detectMarkers(gray)
+    assert np.array_equal(np.array(c, np.float32).reshape(-1, 4, 2), g["corners"])
+    assert np.array_equal(ids.ravel() if ids is not None else np.zeros(0, np.int32), g["ids"])
+    assert np.array_equal(np.array(rej, np.float32).reshape(-1, 4, 2), g["rejected"])
+    c, ids, rej = det.detectMarkers(bgr)
+    assert np.array_equal(np.array(c, np.float32).reshape(-1, 4, 2), g["bgr_corners"])
+    assert np.array_equal(ids.ravel(), g["bgr_ids"])
+    assert np.array_equal(np.array(rej, np.float32).reshape(-1, 4, 2), g["bgr_rejected"])
+    det.close()
+
+
+@pytest.mark.parametrize("name", golden_names("detect_"))
+def test_detect_vs_golden(aruco, name):
+    g = golden(name)
+    gray = g["frame"]
+    dic = D.getPredefinedDictionary(int(g["dict_id"]))
+    det = _detector(aruco, dic, gray.shape)
+    r = det.detect_batch(gray)
+    assert np.array_equal(r.ids[0], g["ids"])                 # bit exact, same order
+    assert np.array_equal(r.corners[0], g["corners"])
+    assert np.array_equal(r.rejected[0], g["rejected"])
+    _, masks = det.debug_threshold(gray)
+    for si in range(3):
+        assert zlib.crc32(masks[0, si].tobytes()) == int(g["mask_crc"][si])
+    det.close()
+    det = _detector(aruco, dic, gray.shape, cornerRefinementMethod=1)
+    r = det.detect_batch(gray)
+    assert np.array_equal(r.ids[0], g["subpix_ids"])
+    if len(r.ids[0]):
+        assert np.abs(r.corners[0] - g["subpix_corners"]).max() < 0.05     # north_star: 0.05 px
+        assert np.abs(r.corners[0] - g["subpix_corners"]).max() < 1e-2
+    det.close()
+
+
+def test_legacy_free_functions(aruco):
+    g = golden("detect_vga_4x4_s2")
+    dic = D.getPredefinedDictionary(int(g["dict_id"]))
+    corners, ids, rejected = aruco.detectMarkers(g["frame"], dic)
+    assert isinstance(corners, tuple) and corners[0].shape == (1, 4, 2) and corners[0].dtype == np.float32
+    assert ids.shape == (len(corners), 1) and ids.dtype == np.int32
+    assert np.array_equal(ids.ravel(), g["ids"])
+    blank = golden("detect_blank")
+    corners, ids, rejected = aruco.detectMarkers(blank["frame"], dic)
+    assert corners == () and ids is None                      # cv2: zero detections -> ids None
+    with pytest.raises(aruco.B2AError):
+        aruco.detectMarkers(np.zeros((0, 0), np.uint8), dic)    # cv::Exception in the reference
+    with pytest.raises(aruco.B2AError):
+        aruco.estimatePoseSingleMarkers(np.zeros((1, 4, 2), np.float32), 0.0, np.eye(3), np.zeros(5))
+
+
+def test_library_dictionaries_match_package(aruco):
+    for did in (D.DICT_4X4_50, D.DICT_5X5_100, D.DICT_6X6_250, D.DICT_7X7_1000, D.DICT_ARUCO_ORIGINAL, D.DICT_APRILTAG_36H11):
+        a, b = aruco.library_dictionary(did), D.getPredefinedDictionary(did)
+        assert a.marker_size == b.marker_size and a.max_correction_bits == b.max_correction_bits
+        assert np.array_equal(a.table, b.table)
+
+
+def test_known_answer_generated_markers(aruco):
+    """generateImageMarker(id) -> detect -> id (SURVEY 8c known-answer identity), all four rotations."""
+    dic = D.getPredefinedDictionary(D.DICT_6X6_250)
+    det = _detector(aruco, dic, (400, 400))
+    for mid in (0, 17, 123, 249):
+        for rot in range(4):
+            img = np.full((400, 400), 255, np.uint8)
+            m = np.rot90(dic.marker_image(mid, 30), rot)
+            img[80:80 + m.shape[0], 80:80 + m.shape[1]] = m
+            r = det.detect_batch(img)
+            assert r.ids[0].tolist() == [mid], (mid, rot, r.ids[0])
+    det.close()
+
+
+def test_batch_vs_oracle_1080p(aruco, oracle):
+    """config C2 frames in one batch: every frame identical to the oracle (ids, corners, rejected, order)."""
+    B = 4
+    frames = synth.render_batch("C2", B, base_seed=100)
+    dic = D.getPredefinedDictionary(D.DICT_6X6_250)
+    det = _detector(aruco, dic, frames.shape[1:], batch=B)
+    K = np.array([[1400.0, 0, 960], [0, 1400.0, 540], [0, 0, 1]])
+    Dist = np.array([0.05, -0.1, 0.001, -0.002, 0.02])
+    r = det.detect_pose_batch(frames, 0.27, K, Dist)
+    for b in range(B):
+        oc, oi, orj = oracle.detect(frames[b], dic)
+        assert np.array_equal(r.ids[b], oi) and np.array_equal(r.corners[b], oc) and np.array_equal(r.rejected[b], orj)
+        orv, otv = oracle.estimate_pose_single_markers(oc, 0.27, K, Dist)
+        assert np.abs(r.rvecs[b] - orv).max() < 1e-4 and np.abs(r.tvecs[b] - otv).max() < 1e-4
+    # idempotence: a second call on the same handle returns the same result
+    r2 = det.detect_pose_batch(frames, 0.27, K, Dist)
+    for b in range(B):
+        assert np.array_equal(r.ids[b], r2.ids[b]) and np.array_equal(r.corners[b], r2.corners[b])
+        assert np.array_equal(r.rvecs[b], r2.rvecs[b])
+    # a sub-batch and a smaller frame on the same handle
+    r3 = det.detect_batch(frames[1:2])
+    assert np.array_equal(r3.ids[0], r.ids[1])
+    small = synth.render_config("C1", 3).image
+    det2 = _detector(aruco, D.getPredefinedDictionary(0), frames.shape[1:], batch=B)
+    oc, oi, orj = oracle.detect(small, D.getPredefinedDictionary(0))
+    r4 = det2.detect_batch(small)
+    assert np.array_equal(r4.ids[0], oi) and np.array_equal(r4.corners[0], oc) and np.array_equal(r4.rejected[0], orj)
+    det.close(); det2.close()
+
+
+def test_noisy_4k_frame_vs_oracle(aruco, oracle):
+    """config C3 (4K, noise + blur), one frame."""
+    fr = synth.render_config("C3", 0).image
+    dic = D.getPredefinedDictionary(D.DICT_6X6_250)
+    det = _detector(aruco, dic, fr.shape)
+    r = det.detect_batch(fr)
+    oc, oi, orj = oracle.detect(fr, dic)
+    assert np.array_equal(r.ids[0], oi) and np.array_equal(r.corners[0], oc) and np.array_equal(r.rejected[0], orj)
+    det.close()
+
+
+def test_pose_vs_golden(aruco):
+    g = golden("pose")
+    K, Dd = g["K"], g["D"]
+    det = _detector(aruco, D.getPredefinedDictionary(0), (64, 64))
+    rows = g["rows"]
+    for use_d in (0, 1):
+        for L in (0.27, 0.1):
+            sel = rows[(rows[:, 1] == use_d) & (np.abs(rows[:, 0] - L) < 1e-9)]
+            rv, tv = det.estimatePoseSingleMarkers(sel[:, 2:10].astype(np.float32).reshape(-1, 4, 2), L, K, Dd if use_d else np.zeros(5))
+            assert rv.shape == (len(sel), 1, 3)
+            assert np.abs(rv.reshape(-1, 3) - sel[:, 10:13]).max() < 1e-4      # rad
+            assert np.abs(tv.reshape(-1, 3) - sel[:, 13:16]).max() < 1e-4      # m
+    det.close()
+
+
+def test_threshold_edge_shapes(aruco, oracle):
+    """ragged sizes: widths not multiples of 16/32/128, tiny frames, non-default window list."""
+    rng = np.random.default_rng(3)
+    dic = D.getPredefinedDictionary(0)
+    for (H, W) in ((31, 33), (64, 129), (95, 257), (130, 64), (7, 300)):
+        img = rng.integers(0, 256, (H, W)).astype(np.uint8)
+        det = _detector(aruco, dic, (H, W))
+        _, masks = det.debug_threshold(img)
+        for si, k in enumerate((3, 13, 23)):
+            assert np.array_equal(masks[0, si], oracle.adaptive_threshold(img, k, 7.0)), (H, W, k)
+        det.close()
+    img = rng.integers(0, 256, (120, 200)).astype(np.uint8)
+    det = _detector(aruco, dic, img.shape, adaptiveThreshWinSizeMin=5, adaptiveThreshWinSizeMax=29, adaptiveThreshWinSizeStep=8, adaptiveThreshConstant=3.0)
+    assert det.num_scales == 4
+    _, masks = det.debug_threshold(img)
+    for si, k in enumerate((5, 13, 21, 29)):
+        assert np.array_equal(masks[0, si], oracle.adaptive_threshold(img, k, 3.0)), k
+    det.close()
+
+
+def test_contours_random_masks(aruco, oracle):
+    """Bernoulli masks through the contour stages (threshold of a two-level image reproduces the mask)."""
+    rng = np.random.default_rng(9)
+    dic = D.getPredefinedDictionary(0)
+    for p in (0.3, 0.5, 0.7):
+        H, W = 97, 131
+        # a frame whose k=3 mask is the Bernoulli pattern is hard to construct; instead compare
+        # against the oracle's contours of the mask the GPU itself produced (bit-exact masks are
+        # checked above)
+        img = rng.integers(0, 256, (H, W)).astype(np.uint8)
+        det = _detector(aruco, dic, (H, W))
+        _, masks = det.debug_threshold(img)
+        counts, kept, lens, pts = det.debug_contours(img, pts_cap=2 * W * H)
+        mn, mx = int(0.03 * max(W, H)), int(4.0 * max(W, H))
+        for si in range(3):
+            cs = oracle.find_contours(masks[0, si])
+            keep = [c for c in cs if mn <= len(c) <= mx]
+            assert counts[0, si] == len(cs)
+            assert kept[0, si] == len(keep)
+            assert np.array_equal(lens[0, si, :len(keep)], [len(c) for c in keep])
+            want = np.concatenate(keep).astype(np.int16) if keep else np.zeros((0, 2), np.int16)
+            assert np.array_equal(pts[0, si, :len(want)], want)
+        det.close()
