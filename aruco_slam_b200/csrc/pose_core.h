@@ -4,10 +4,10 @@
 // reference's own observation mapping and CalculateCovariance (:325-374, :412-421, :437-471).
 //
 // solvePnP ITERATIVE minimises the distorted reprojection error of the 4 corners starting from
-// a homography decomposition (SURVEY.md App. A "Pose").  Here: same initialisation, then a
-// Levenberg-Marquardt iteration on SE(3) with a local rotation perturbation R <- R exp([w]x)
-// and analytic Jacobians, run to convergence; the minimiser does not depend on the
-// parametrisation, so the result agrees with cv2.solvePnP to ~1e-7 (tolerance 1e-4 rad / m).
+// a homography decomposition (SURVEY.md App. A "Pose") with OpenCV's Levenberg-Marquardt
+// schedule on (rvec, tvec).  Small markers seen nearly head-on have two close local minima
+// (planar pose ambiguity), so the iteration schedule -- not just the cost -- is followed:
+// same initialisation, same parametrisation, same damping rule, analytic Jacobians.
 #pragma once
 #include "core.h"
 
@@ -140,14 +140,51 @@ B2A_HD void nearest_rotation(double *R)
     }
 }
 
-// residuals (8) of pose (R,t); optionally the 8x6 Jacobian w.r.t. (w, dt) of R exp([w]x), t + dt
-B2A_HD double pose_residuals(const Camera &cam, const double *obj, const double *ip, const double *R, const double *t, double *res, double *J)
+// cv::Rodrigues with its 3x9 Jacobian: dR[i*9 + k] = d R_flat[k] / d r[i]
+B2A_HD void rodrigues_with_jacobian(const double *rv, double *R, double *dR)
 {
+    const double th = sqrt(rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2]);
+    if (th < DBL_EPSILON) {
+        for (int i = 0; i < 9; ++i) R[i] = 0;
+        R[0] = R[4] = R[8] = 1;
+        for (int i = 0; i < 27; ++i) dR[i] = 0;
+        dR[5] = dR[15] = dR[19] = -1;
+        dR[7] = dR[11] = dR[21] = 1;
+        return;
+    }
+    const double c = cos(th), s = sin(th), c1 = 1. - c, it = 1. / th;
+    const double rx = rv[0] * it, ry = rv[1] * it, rz = rv[2] * it;
+    const double rrt[9] = {rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz};
+    const double r_x[9] = {0, -rz, ry, rz, 0, -rx, -ry, rx, 0};
+    const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int k = 0; k < 9; ++k) R[k] = c * I[k] + c1 * rrt[k] + s * r_x[k];
+    const double drrt[27] = {rx + rx, ry, rz, ry, 0, 0, rz, 0, 0,
+                             0, rx, 0, rx, ry + ry, rz, 0, rz, 0,
+                             0, 0, rx, 0, 0, ry, rx, ry, rz + rz};
+    const double d_r_x[27] = {0, 0, 0, 0, 0, -1, 0, 1, 0,
+                              0, 0, 1, 0, 0, 0, -1, 0, 0,
+                              0, -1, 0, 1, 0, 0, 0, 0, 0};
+    const double rr[3] = {rx, ry, rz};
+    for (int i = 0; i < 3; ++i) {
+        const double ri = rr[i];
+        const double a0 = -s * ri, a1 = (s - 2 * c1 * it) * ri, a2 = c1 * it, a3 = (c - s * it) * ri, a4 = s * it;
+        for (int k = 0; k < 9; ++k)
+            dR[i * 9 + k] = a0 * I[k] + a1 * rrt[k] + a2 * drrt[i * 9 + k] + a3 * r_x[k] + a4 * d_r_x[i * 9 + k];
+    }
+}
+
+// reprojection residuals (8) at (rvec, tvec) = p[0..5]; optionally the 8x6 Jacobian d res / d p
+// (cv::projectPoints' dpdr | dpdt).  Returns the L2 norm of the residual vector.
+B2A_HD double pose_residuals(const Camera &cam, const double *obj, const double *ip, const double *p, double *res, double *J)
+{
+    double R[9], dR[27];
+    if (J) rodrigues_with_jacobian(p, R, dR); else rodrigues_to_R(p, R);
     double e = 0;
     for (int i = 0; i < 4; ++i) {
         const double *X = obj + 3 * i;
-        const double RX[3] = {R[0] * X[0] + R[1] * X[1] + R[2] * X[2], R[3] * X[0] + R[4] * X[1] + R[5] * X[2], R[6] * X[0] + R[7] * X[1] + R[8] * X[2]};
-        const double Px = RX[0] + t[0], Py = RX[1] + t[1], Pz = RX[2] + t[2];
+        const double Px = R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + p[3];
+        const double Py = R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + p[4];
+        const double Pz = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + p[5];
         const double iz = Pz != 0 ? 1. / Pz : 1;
         const double x = Px * iz, y = Py * iz;
         double u, v, Jd[4];
@@ -155,33 +192,40 @@ B2A_HD double pose_residuals(const Camera &cam, const double *obj, const double 
         res[2 * i] = u - ip[2 * i]; res[2 * i + 1] = v - ip[2 * i + 1];
         e += res[2 * i] * res[2 * i] + res[2 * i + 1] * res[2 * i + 1];
         if (J) {
-            // d(x,y)/dP
-            const double dxdP[3] = {iz, 0, -x * iz}, dydP[3] = {0, iz, -y * iz};
-            // dP/dw = -R [X]x  (columns), dP/dt = I
-            // R [X]x : column k = R * (e_k x X)... use d(R exp(w) X)/dw = R * (-[X]x) = -R [X]x
-            double M[9];   // -R [X]x
-            // [X]x = [[0,-X2,X1],[X2,0,-X0],[-X1,X0,0]]
-            for (int r = 0; r < 3; ++r) {
-                const double a = R[3 * r], b = R[3 * r + 1], c = R[3 * r + 2];
-                M[3 * r + 0] = -(b * X[2] - c * X[1]);
-                M[3 * r + 1] = -(-a * X[2] + c * X[0]);
-                M[3 * r + 2] = -(a * X[1] - b * X[0]);
-            }
             for (int k = 0; k < 6; ++k) {
                 double dP[3];
-                if (k < 3) { dP[0] = M[k]; dP[1] = M[3 + k]; dP[2] = M[6 + k]; }
-                else { dP[0] = (k == 3); dP[1] = (k == 4); dP[2] = (k == 5); }
-                const double dx = dxdP[0] * dP[0] + dxdP[2] * dP[2];
-                const double dy = dydP[1] * dP[1] + dydP[2] * dP[2];
+                if (k < 3) {
+                    const double *d = dR + k * 9;
+                    dP[0] = d[0] * X[0] + d[1] * X[1] + d[2] * X[2];
+                    dP[1] = d[3] * X[0] + d[4] * X[1] + d[5] * X[2];
+                    dP[2] = d[6] * X[0] + d[7] * X[1] + d[8] * X[2];
+                } else { dP[0] = (k == 3); dP[1] = (k == 4); dP[2] = (k == 5); }
+                const double dx = iz * (dP[0] - x * dP[2]);
+                const double dy = iz * (dP[1] - y * dP[2]);
                 J[(2 * i) * 6 + k] = Jd[0] * dx + Jd[1] * dy;
                 J[(2 * i + 1) * 6 + k] = Jd[2] * dx + Jd[3] * dy;
             }
         }
     }
-    return e;
+    return sqrt(e);
 }
 
-// one marker: corners (4x2, image pixels) -> rvec, tvec
+// one LM trial step of OpenCV's CvLevMarq::step(): p = prev - (JtJ with diagonal * (1 + 10^lg))^-1 JtErr
+B2A_HD void lm_step(const double *JtJ, const double *JtErr, int lambdaLg10, const double *prev, double *p)
+{
+    double M[36], d[6];
+    const double lambda = exp(lambdaLg10 * 2.302585092994046);
+    for (int i = 0; i < 36; ++i) M[i] = JtJ[i];
+    for (int a = 0; a < 6; ++a) { M[a * 6 + a] *= 1. + lambda; d[a] = JtErr[a]; }
+    if (!solve_linear<6>(M, d)) for (int a = 0; a < 6; ++a) d[a] = 0;
+    for (int a = 0; a < 6; ++a) p[a] = prev[a] - d[a];
+}
+
+// one marker: corners (4x2, image pixels) -> rvec, tvec.  Follows cv::solvePnP(SOLVEPNP_ITERATIVE)
+// for 4 coplanar points: homography initialisation, then OpenCV's Levenberg-Marquardt schedule
+// (CvLevMarq: lambda = 10^-3 start, x10 on a worse step (up to 10^16), /10 after every accepted
+// iteration, at most 20 iterations, stop when the relative parameter change < FLT_EPSILON) on the
+// rotation *vector* and translation, so that the same local minimum and rvec branch are reached.
 B2A_HD void solve_marker_pose(const Camera &cam, float marker_length, const float *corners, double *rvec, double *tvec)
 {
     const float hf = marker_length / 2.f;                         // Vec3f(-L/2.f, L/2.f, 0) ...
@@ -206,71 +250,47 @@ B2A_HD void solve_marker_pose(const Camera &cam, float marker_length, const floa
     const double n2 = sqrt(hm[1] * hm[1] + hm[4] * hm[4] + hm[7] * hm[7]);
     const double a1[3] = {hm[0] / n1, hm[3] / n1, hm[6] / n1}, a2[3] = {hm[1] / n2, hm[4] / n2, hm[7] / n2};
     const double a3[3] = {a1[1] * a2[2] - a1[2] * a2[1], a1[2] * a2[0] - a1[0] * a2[2], a1[0] * a2[1] - a1[1] * a2[0]};
-    double R[9], t[3];
+    double R[9];
     for (int i = 0; i < 3; ++i) { R[3 * i] = a1[i]; R[3 * i + 1] = a2[i]; R[3 * i + 2] = a3[i]; }
     nearest_rotation(R);
+    double p[6], prev[6];
+    R_to_rodrigues(R, p);
     const double sc = 2. / (n1 + n2);
-    t[0] = hm[2] * sc; t[1] = hm[5] * sc; t[2] = hm[8] * sc;
-    double r0[3];
-    R_to_rodrigues(R, r0);        // solvePnP iterates on the rotation vector from here (see the end)
-    // ---- Levenberg-Marquardt ----
-    double res[8], J[48];
-    double e = pose_residuals(cam, obj, ip, R, t, res, J);
-    double lambda = 1e-3;
-    for (int it = 0; it < 100; ++it) {
-        double JtJ[36], Jtr[6];
+    p[3] = hm[2] * sc; p[4] = hm[5] * sc; p[5] = hm[8] * sc;
+    // ---- Levenberg-Marquardt, CvLevMarq schedule ----
+    double res[8], J[48], JtJ[36], JtErr[6];
+    int lambdaLg10 = -3, iters = 0;
+    double prevErr = 0;
+    const int max_iter = 20;
+    for (;;) {
+        const double errAtP = pose_residuals(cam, obj, ip, p, res, J);
         for (int a = 0; a < 6; ++a) {
             double s = 0;
             for (int i = 0; i < 8; ++i) s += J[i * 6 + a] * res[i];
-            Jtr[a] = s;
+            JtErr[a] = s;
             for (int c = a; c < 6; ++c) {
                 double q = 0;
                 for (int i = 0; i < 8; ++i) q += J[i * 6 + a] * J[i * 6 + c];
                 JtJ[a * 6 + c] = q; JtJ[c * 6 + a] = q;
             }
         }
-        bool improved = false;
-        double step2 = 0;
-        for (int tries = 0; tries < 30 && !improved; ++tries) {
-            double M[36], d[6];
-            for (int i = 0; i < 36; ++i) M[i] = JtJ[i];
-            for (int a = 0; a < 6; ++a) { M[a * 6 + a] *= 1 + lambda; d[a] = -Jtr[a]; }
-            if (!solve_linear<6>(M, d)) { lambda *= 10; continue; }
-            // R2 = R exp([w]x), t2 = t + dt
-            double E[9], R2[9], t2[3], r2[8];
-            rodrigues_to_R(d, E);
-            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c)
-                R2[3 * r + c] = R[3 * r] * E[c] + R[3 * r + 1] * E[3 + c] + R[3 * r + 2] * E[6 + c];
-            t2[0] = t[0] + d[3]; t2[1] = t[1] + d[4]; t2[2] = t[2] + d[5];
-            const double e2 = pose_residuals(cam, obj, ip, R2, t2, r2, nullptr);
-            if (e2 < e) {
-                for (int i = 0; i < 9; ++i) R[i] = R2[i];
-                t[0] = t2[0]; t[1] = t2[1]; t[2] = t2[2];
-                e = e2;
-                step2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3] + d[4] * d[4] + d[5] * d[5];
-                lambda = lambda > 1e-16 ? lambda * 0.1 : lambda;
-                improved = true;
-            } else lambda *= 10;
+        for (int a = 0; a < 6; ++a) prev[a] = p[a];
+        lm_step(JtJ, JtErr, lambdaLg10, prev, p);
+        if (iters == 0) prevErr = errAtP;
+        double r2[8];
+        double err = pose_residuals(cam, obj, ip, p, r2, nullptr);
+        while (err > prevErr && ++lambdaLg10 <= 16) {
+            lm_step(JtJ, JtErr, lambdaLg10, prev, p);
+            err = pose_residuals(cam, obj, ip, p, r2, nullptr);
         }
-        if (!improved) break;
-        if (step2 < 1e-26) break;
-        e = pose_residuals(cam, obj, ip, R, t, res, J);
+        lambdaLg10 = lambdaLg10 - 1 > -16 ? lambdaLg10 - 1 : -16;
+        double dn = 0, pn = 0;
+        for (int a = 0; a < 6; ++a) { dn += (p[a] - prev[a]) * (p[a] - prev[a]); pn += prev[a] * prev[a]; }
+        if (++iters >= max_iter || sqrt(dn) < (double)FLT_EPSILON * sqrt(pn)) break;
+        prevErr = err;
     }
-    nearest_rotation(R);          // remove accumulated drift before taking the log
-    R_to_rodrigues(R, rvec);
-    // cv2.solvePnP refines the rotation *vector* continuously from its initial value, so near a
-    // half turn it can return |rvec| > pi.  Report the same branch: of the two equivalent
-    // vectors r and r (1 - 2 pi / |r|) take the one closer to the initial rotation vector.
-    {
-        const double nr = sqrt(rvec[0] * rvec[0] + rvec[1] * rvec[1] + rvec[2] * rvec[2]);
-        if (nr > 1e-9) {
-            const double f = 1.0 - 2.0 * 3.14159265358979323846 / nr;
-            double d1 = 0, d2 = 0;
-            for (int i = 0; i < 3; ++i) { const double a = rvec[i] - r0[i], b = rvec[i] * f - r0[i]; d1 += a * a; d2 += b * b; }
-            if (d2 < d1) { rvec[0] *= f; rvec[1] *= f; rvec[2] *= f; }
-        }
-    }
-    tvec[0] = t[0]; tvec[1] = t[1]; tvec[2] = t[2];
+    rvec[0] = p[0]; rvec[1] = p[1]; rvec[2] = p[2];
+    tvec[0] = p[3]; tvec[1] = p[4]; tvec[2] = p[5];
 }
 
 // ---- observation mapping (reference src/aruco_slam.cpp:325-374, 437-471) ----

@@ -186,6 +186,12 @@ def rodrigues(r: np.ndarray) -> np.ndarray:
     return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
 
 
+def rvec_distance(r1, r2) -> float:
+    """Largest element difference of the rotation matrices of two rotation vectors (radians to first
+    order).  solvePnP can return |rvec| > pi near a half turn; r and r (1 - 2 pi/|r|) are the same rotation."""
+    return float(np.abs(rodrigues(np.asarray(r1, float).ravel()) - rodrigues(np.asarray(r2, float).ravel())).max())
+
+
 def project(obj: np.ndarray, rvec, tvec, K: np.ndarray, D: np.ndarray) -> np.ndarray:
     """Pinhole + (k1,k2,p1,p2,k3) projection of (n,3) points."""
     P = obj @ rodrigues(np.asarray(rvec, float)).T + np.asarray(tvec, float)

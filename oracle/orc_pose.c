@@ -130,18 +130,86 @@ static void nearest_rotation(double *R)
     }
 }
 
-static double reproj_residuals(const double *obj, const double *ip, const double *p6, const double *K, const double *D, double *res)
+/* cv::Rodrigues(rvec -> R) with the 3x9 Jacobian (row i = d R_flat / d r_i), OpenCV's formula */
+static void rodrigues_jac(const double *r, double *R, double *J)
 {
-    double proj[8];
-    orc_project_points(obj, 4, p6, p6 + 3, K, D, proj);
-    double e = 0;
-    for (int i = 0; i < 8; i++) { res[i] = proj[i] - ip[i]; e += res[i] * res[i]; }
-    return e;
+    double th = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    if (th < DBL_EPSILON) {
+        memset(R, 0, 9 * sizeof(double)); R[0] = R[4] = R[8] = 1;
+        memset(J, 0, 27 * sizeof(double));
+        J[5] = J[15] = J[19] = -1; J[7] = J[11] = J[21] = 1;
+        return;
+    }
+    double c = cos(th), s = sin(th), c1 = 1. - c, itheta = 1. / th;
+    double x = r[0] * itheta, y = r[1] * itheta, z = r[2] * itheta;
+    double rrt[9] = {x * x, x * y, x * z, x * y, y * y, y * z, x * z, y * z, z * z};
+    double rx[9] = {0, -z, y, z, 0, -x, -y, x, 0};
+    double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int k = 0; k < 9; k++) R[k] = c * I[k] + c1 * rrt[k] + s * rx[k];
+    double drrt[27] = {x + x, y, z, y, 0, 0, z, 0, 0, 0, x, 0, x, y + y, z, 0, z, 0, 0, 0, x, 0, 0, y, x, y, z + z};
+    double drx[27] = {0, 0, 0, 0, 0, -1, 0, 1, 0, 0, 0, 1, 0, 0, 0, -1, 0, 0, 0, -1, 0, 1, 0, 0, 0, 0, 0};
+    double rr[3] = {x, y, z};
+    for (int i = 0; i < 3; i++) {
+        double ri = rr[i], a0 = -s * ri, a1 = (s - 2 * c1 * itheta) * ri, a2 = c1 * itheta, a3 = (c - s * itheta) * ri, a4 = s * itheta;
+        for (int k = 0; k < 9; k++) J[i * 9 + k] = a0 * I[k] + a1 * rrt[k] + a2 * drrt[i * 9 + k] + a3 * rx[k] + a4 * drx[i * 9 + k];
+    }
+}
+
+/* projectPoints residuals (proj - measured) and, if J != NULL, dpdr | dpdt (8 x 6), as cv::projectPoints */
+static double reproj_err(const double *obj, const double *ip, const double *p6, const double *K, const double *D, double *err, double *J)
+{
+    double R[9], dRdr[27];
+    rodrigues_jac(p6, R, dRdr);
+    double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    double k1 = D[0], k2 = D[1], p1 = D[2], p2 = D[3], k3 = D[4];
+    double e2 = 0;
+    for (int i = 0; i < 4; i++) {
+        double X = obj[3 * i], Y = obj[3 * i + 1], Z = obj[3 * i + 2];
+        double x = R[0] * X + R[1] * Y + R[2] * Z + p6[3];
+        double y = R[3] * X + R[4] * Y + R[5] * Z + p6[4];
+        double z = R[6] * X + R[7] * Y + R[8] * Z + p6[5];
+        z = z ? 1. / z : 1;
+        x *= z; y *= z;
+        double r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+        double a1 = 2 * x * y, a2 = r2 + 2 * x * x, a3 = r2 + 2 * y * y;
+        double cdist = 1 + k1 * r2 + k2 * r4 + k3 * r6;
+        double xd = x * cdist + p1 * a1 + p2 * a2, yd = y * cdist + p1 * a3 + p2 * a1;
+        err[2 * i] = xd * fx + cx - ip[2 * i];
+        err[2 * i + 1] = yd * fy + cy - ip[2 * i + 1];
+        e2 += err[2 * i] * err[2 * i] + err[2 * i + 1] * err[2 * i + 1];
+        if (!J) continue;
+        for (int k = 0; k < 6; k++) {
+            double dx0, dy0, dz0;
+            if (k < 3) {
+                const double *d = dRdr + 9 * k;
+                dx0 = X * d[0] + Y * d[1] + Z * d[2];
+                dy0 = X * d[3] + Y * d[4] + Z * d[5];
+                dz0 = X * d[6] + Y * d[7] + Z * d[8];
+            } else { dx0 = (k == 3); dy0 = (k == 4); dz0 = (k == 5); }
+            double dxd = z * (dx0 - x * dz0), dyd = z * (dy0 - y * dz0);
+            double dr2 = 2 * x * dxd + 2 * y * dyd;
+            double dcd = k1 * dr2 + 2 * k2 * r2 * dr2 + 3 * k3 * r4 * dr2;
+            double da1 = 2 * (x * dyd + y * dxd);
+            J[(2 * i) * 6 + k] = fx * (dxd * cdist + x * dcd + p1 * da1 + p2 * (dr2 + 4 * x * dxd));
+            J[(2 * i + 1) * 6 + k] = fy * (dyd * cdist + y * dcd + p1 * (dr2 + 4 * y * dyd) + p2 * da1);
+        }
+    }
+    return sqrt(e2);
+}
+
+static void levmarq_step(const double *JtJ, const double *JtErr, int lambdaLg10, const double *prev, double *param)
+{   /* CvLevMarq::step(): diag(JtJ) *= 1 + lambda; param = prevParam - JtJN^-1 JtErr */
+    double M[36], d[6], lambda = exp(lambdaLg10 * log(10.));
+    memcpy(M, JtJ, sizeof(M)); memcpy(d, JtErr, sizeof(d));
+    for (int a = 0; a < 6; a++) M[a * 6 + a] *= 1. + lambda;
+    if (!solve_n(M, d, 6)) memset(d, 0, sizeof(d));
+    for (int a = 0; a < 6; a++) param[a] = prev[a] - d[a];
 }
 
 static void solve_pnp_planar4(const double *obj, const double *ip, const double *K, const double *D, double *rvec, double *tvec)
 {
-    /* init: homography obj.xy -> undistorted normalised points (SURVEY App. A pose recipe) */
+    /* init: homography obj.xy -> undistorted normalised points (SURVEY App. A pose recipe; OpenCV's
+     * planar branch of findExtrinsicCameraParams2) */
     double un[8];
     orc_undistort_points(ip, 4, K, D, un);
     double A[64], b[8];
@@ -161,55 +229,38 @@ static void solve_pnp_planar4(const double *obj, const double *ip, const double 
     double a3[3] = {a1[1] * a2[2] - a1[2] * a2[1], a1[2] * a2[0] - a1[0] * a2[2], a1[0] * a2[1] - a1[1] * a2[0]};
     for (int i = 0; i < 3; i++) { R[3 * i] = a1[i]; R[3 * i + 1] = a2[i]; R[3 * i + 2] = a3[i]; }
     nearest_rotation(R);
-    double p[6];
-    rot_to_rvec(R, p);
+    double param[6], prev[6];
+    rot_to_rvec(R, param);
     double sc = 2. / (n1 + n2);
-    p[3] = h[2] * sc; p[4] = h[5] * sc; p[5] = h[8] * sc;
+    param[3] = h[2] * sc; param[4] = h[5] * sc; param[5] = h[8] * sc;
 
-    /* Levenberg-Marquardt on the distorted reprojection error, run to convergence */
-    double res[8], e = reproj_residuals(obj, ip, p, K, D, res);
-    double lambda = 1e-3;
-    for (int it = 0; it < 200; it++) {
-        double J[8 * 6];
-        for (int k = 0; k < 6; k++) {
-            double hstep = 1e-6 * (fabs(p[k]) > 1 ? fabs(p[k]) : 1.0);
-            double pp[6], pm[6], rp[8], rm[8];
-            memcpy(pp, p, sizeof(pp)); memcpy(pm, p, sizeof(pm));
-            pp[k] += hstep; pm[k] -= hstep;
-            reproj_residuals(obj, ip, pp, K, D, rp);
-            reproj_residuals(obj, ip, pm, K, D, rm);
-            for (int i = 0; i < 8; i++) J[i * 6 + k] = (rp[i] - rm[i]) / (2 * hstep);
-        }
-        double JtJ[36], Jtr[6];
+    /* OpenCV's CvLevMarq driven as in findExtrinsicCameraParams2: criteria (20 iterations, FLT_EPSILON) */
+    int lambdaLg10 = -3, iters = 0;
+    double prevErrNorm = 0, err[8], J[48], JtJ[36], JtErr[6];
+    for (;;) {
+        double en = reproj_err(obj, ip, param, K, D, err, J);          /* state CALC_J */
         for (int a = 0; a < 6; a++) {
             double s = 0;
-            for (int i = 0; i < 8; i++) s += J[i * 6 + a] * res[i];
-            Jtr[a] = s;
+            for (int i = 0; i < 8; i++) s += J[i * 6 + a] * err[i];
+            JtErr[a] = s;
             for (int c = 0; c < 6; c++) { double t = 0; for (int i = 0; i < 8; i++) t += J[i * 6 + a] * J[i * 6 + c]; JtJ[a * 6 + c] = t; }
         }
-        int improved = 0;
-        double step_norm = 0, pn = 0;
-        for (int tries = 0; tries < 40 && !improved; tries++) {
-            double M[36], d[6];
-            memcpy(M, JtJ, sizeof(M));
-            for (int a = 0; a < 6; a++) { M[a * 6 + a] *= 1 + lambda; d[a] = -Jtr[a]; }
-            if (!solve_n(M, d, 6)) { lambda *= 10; continue; }
-            double pn2[6], r2[8];
-            for (int a = 0; a < 6; a++) pn2[a] = p[a] + d[a];
-            double e2 = reproj_residuals(obj, ip, pn2, K, D, r2);
-            if (e2 < e) {
-                step_norm = 0; pn = 0;
-                for (int a = 0; a < 6; a++) { step_norm += d[a] * d[a]; pn += pn2[a] * pn2[a]; }
-                memcpy(p, pn2, sizeof(pn2)); memcpy(res, r2, sizeof(r2)); e = e2;
-                lambda = lambda > 1e-16 ? lambda * 0.1 : lambda;
-                improved = 1;
-            } else lambda *= 10;
+        memcpy(prev, param, sizeof(prev));
+        levmarq_step(JtJ, JtErr, lambdaLg10, prev, param);
+        if (iters == 0) prevErrNorm = en;
+        double errNorm = reproj_err(obj, ip, param, K, D, err, NULL);   /* state CHECK_ERR */
+        while (errNorm > prevErrNorm && ++lambdaLg10 <= 16) {
+            levmarq_step(JtJ, JtErr, lambdaLg10, prev, param);
+            errNorm = reproj_err(obj, ip, param, K, D, err, NULL);
         }
-        if (!improved) break;
-        if (sqrt(step_norm) < 1e-13 * (sqrt(pn) + 1e-13)) break;
+        lambdaLg10 = lambdaLg10 - 1 > -16 ? lambdaLg10 - 1 : -16;
+        double dn = 0, pn = 0;
+        for (int a = 0; a < 6; a++) { dn += (param[a] - prev[a]) * (param[a] - prev[a]); pn += prev[a] * prev[a]; }
+        if (++iters >= 20 || sqrt(dn) / sqrt(pn) < FLT_EPSILON) break;
+        prevErrNorm = errNorm;
     }
-    memcpy(rvec, p, 3 * sizeof(double));
-    memcpy(tvec, p + 3, 3 * sizeof(double));
+    memcpy(rvec, param, 3 * sizeof(double));
+    memcpy(tvec, param + 3, 3 * sizeof(double));
 }
 
 int orc_estimate_pose_single_markers(const float *corners, int n, double L, const double *K,

@@ -89,3 +89,12 @@ def test_observation_logic_matches_oracle(oracle):
             assert abs(o[0] - obs[0].x) < 1e-12 and abs(o[1] - obs[0].y) < 1e-12 and abs(o[2] - obs[0].theta) < 1e-12
             assert np.abs(o[3:] - np.array(obs[0].cov[:])).max() < 1e-12
     assert kept > 5
+
+
+def test_pose_logic_detected_markers():
+    g = golden("pose_detected")
+    rows = g["rows"]
+    r, t = emu.pose(rows[:, 2:10].astype(np.float32), g["K"], g["D"], 0.27)
+    assert np.abs(t - rows[:, 13:16]).max() < 1e-4                                                   # m
+    assert max(synth.rvec_distance(a, b) for a, b in zip(r, rows[:, 10:13])) < 1e-4                  # rad (rotation)
+    assert np.abs(r - rows[:, 10:13]).max() < 5e-4                                                   # same rvec branch

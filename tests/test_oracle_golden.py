@@ -113,3 +113,15 @@ def test_pose(oracle):
         assert np.abs(oracle.rodrigues(rvec).ravel() - R).max() < 1e-12
     assert worst_r < 1e-4 and worst_t < 1e-4, (worst_r, worst_t)
     assert worst_r < 1e-5 and worst_t < 1e-5
+
+
+def test_pose_detected_markers(oracle):
+    """Detected (integer, small) quads: planar pose ambiguity; the LM schedule must pick cv2's minimum."""
+    g = golden("pose_detected")
+    K, Dd = g["K"], g["D"]
+    rows = g["rows"]
+    r, t = oracle.estimate_pose_single_markers(rows[:, 2:10].astype(np.float32).reshape(-1, 4, 2), 0.27, K, Dd)
+    assert np.abs(t - rows[:, 13:16]).max() < 1e-4
+    assert max(synth.rvec_distance(a, b) for a, b in zip(r, rows[:, 10:13])) < 1e-4
+    assert np.abs(r - rows[:, 10:13]).max() < 5e-4            # same rotation-vector branch, too
+    assert np.median(np.abs(r - rows[:, 10:13]).max(1)) < 1e-7

@@ -144,6 +144,24 @@ def pose_fixture():
          columns=np.array("L use_dist corners[8] rvec[3] tvec[3] proj[8] R[9]"))
 
 
+def pose_detected_fixture():
+    """poses of really detected (integer-valued, small, nearly fronto-parallel) markers: this is where
+    the planar pose ambiguity bites and the Levenberg-Marquardt *schedule* decides the result."""
+    K = np.array([[1400., 0, 960], [0, 1400., 540], [0, 0, 1]])
+    Dist = np.array([0.05, -0.1, 0.001, -0.002, 0.02])
+    L = 0.27
+    h = np.float32(L) / np.float32(2)
+    obj = np.array([[-h, h, 0], [h, h, 0], [h, -h, 0], [-h, -h, 0]], np.float32)
+    rows = []
+    for seed in list(range(100, 104)) + list(range(0, 12)):
+        fr = synth.render_config("C2", seed).image
+        c, ids, _ = cv_detect(fr, D.DICT_6X6_250)
+        for cc in c:
+            ok, r1, t1 = cv2.solvePnP(obj, cc.reshape(-1, 1, 2), K, Dist)
+            rows.append(np.concatenate([[L, 1], cc.ravel(), r1.ravel(), t1.ravel()]))
+    save("pose_detected", rows=np.array(rows), K=K, D=Dist, columns=np.array("L use_dist corners[8] rvec[3] tvec[3]"))
+
+
 def prims_fixture():
     rng = np.random.default_rng(5)
     fr = synth.render_config("C1", 11)
@@ -188,6 +206,7 @@ def main():
     detect_fixture("detect_odd_5x5", synth.render_frame(seed=1, **cfg).image, D.DICT_5X5_100)
     detect_fixture("detect_blank", np.full((120, 160), 128, np.uint8), D.DICT_4X4_50)
     pose_fixture()
+    pose_detected_fixture()
     prims_fixture()
     with open(os.path.join(OUT, "README.md"), "w") as f:
         f.write("# Golden vectors\n\nWritten by `tools/make_golden.py` in the authoring container from\n"
