@@ -222,6 +222,10 @@ class ArucoDetector:
         k = _lib.lib().b2a_last_stage_times(self._h, names, ms, 32)
         return {names[i].decode(): float(ms[i]) for i in range(k)}
 
+    def set_streams(self, n: int):
+        """number of concurrent sub-batches (CUDA streams) a call is cut into; 1 = serial stages"""
+        _lib.check(_lib.lib().b2a_detector_set_streams(self._h, int(n)))
+
     def last_launch_count(self) -> int:
         return _lib.lib().b2a_last_launch_count(self._h)
 

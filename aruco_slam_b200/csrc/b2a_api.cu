@@ -155,7 +155,11 @@ struct b2a_detector {
     b2a_dictionary dict;
     std::vector<uint8_t> dict_bytes;
     int device = 0, num_sms = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;            // == streams[0]
+    static constexpr int MAX_SUB = 8;
+    cudaStream_t streams[MAX_SUB] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
+    int n_sub_max = MAX_SUB, n_streams = 4;
     int nScales = 0, radius[MAX_SCALES];
     int max_cand = 0, max_markers = 0, surv_cap = 0;
     size_t gray_pitch = 0;
@@ -217,7 +221,8 @@ extern "C" void b2a_detector_destroy(b2a_detector *d)
     for (void *p : d->allocs) cudaFree(p);
     for (void *p : d->pinned) cudaFreeHost(p);
     for (int i = 0; i <= ST_COUNT; ++i) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
-    if (d->stream) cudaStreamDestroy(d->stream);
+    for (int i = 0; i < b2a_detector::MAX_SUB; ++i) { if (d->streams[i]) cudaStreamDestroy(d->streams[i]); if (d->ev_join[i]) cudaEventDestroy(d->ev_join[i]); }
+    if (d->ev_fork) cudaEventDestroy(d->ev_fork);
     delete d;
 }
 
@@ -229,7 +234,13 @@ static int create_impl(b2a_detector *d)
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, c.device));
     d->num_sms = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < b2a_detector::MAX_SUB; ++i) {
+        CU(cudaStreamCreateWithFlags(&d->streams[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&d->ev_join[i], cudaEventDisableTiming));
+    }
+    d->stream = d->streams[0];
+    CU(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+    if (const char *e = std::getenv("B2A_STREAMS")) d->n_streams = std::max(1, std::min(std::atoi(e), b2a_detector::MAX_SUB));
     for (int i = 0; i <= ST_COUNT; ++i) CU(cudaEventCreate(&d->ev[i]));
     const int B = c.max_batch, W = c.max_width, H = c.max_height, nS = d->nScales;
     const size_t P = (size_t)W * H;
@@ -242,8 +253,8 @@ static int create_impl(b2a_detector *d)
     d->starts_cap = (unsigned)std::min<size_t>(std::max<size_t>((size_t)B * nS * (P / 8), 1u << 20), 0x7FFFFFFFu);
     TRY(dev_alloc(d, &d->d_starts, d->starts_cap));
     const size_t FS = (size_t)B * nS;
-    TRY(dev_alloc(d, &d->d_counters, 4 + 3 * FS + B));
-    d->d_surv_count = d->d_counters + 4; d->d_contour_count = d->d_surv_count + FS; d->d_iso_count = d->d_contour_count + FS;
+    TRY(dev_alloc(d, &d->d_counters, d->n_sub_max + 3 * FS + B));
+    d->d_surv_count = d->d_counters + d->n_sub_max; d->d_contour_count = d->d_surv_count + FS; d->d_iso_count = d->d_contour_count + FS;
     d->d_status = d->d_iso_count + FS;
     TRY(dev_alloc(d, &d->d_surv, FS * d->surv_cap));
     TRY(dev_alloc(d, &d->d_sorted, FS * d->surv_cap));
@@ -282,7 +293,8 @@ static int create_impl(b2a_detector *d)
     TRY(pin_alloc(d, &d->h_nacc, B)); TRY(pin_alloc(d, &d->h_nrej, B)); TRY(pin_alloc(d, &d->h_status, B));
     TRY(pin_alloc(d, &d->h_corners, BK * 8)); TRY(pin_alloc(d, &d->h_ids, BK)); TRY(pin_alloc(d, &d->h_rejected, BK * 8));
     TRY(pin_alloc(d, &d->h_rvecs, BK * 3)); TRY(pin_alloc(d, &d->h_tvecs, BK * 3));
-    CU(cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CU(cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (int)sizeof(int32_t) * d->max_cand));
     CU(cudaStreamSynchronize(d->stream));
     return B2A_OK;
 }
@@ -322,6 +334,7 @@ extern "C" int b2a_detector_create(const b2a_detector_config *cfg, const b2a_dic
     d->max_markers = cfg->max_markers > 0 ? cfg->max_markers : 256;
     d->max_cand = cfg->max_candidates > 0 ? cfg->max_candidates : 2048;
     d->max_cand = (d->max_cand + 31) & ~31;
+    if (d->max_cand > 4096) { delete d; return set_err(B2A_ERR_UNSUPPORTED, "max_candidates > 4096"); }
     d->surv_cap = SORT_CAP;
     int rc = create_impl(d);
     if (rc != B2A_OK) { std::string keep = g_err; b2a_detector_destroy(d); g_err = keep; return rc; }
@@ -341,11 +354,19 @@ extern "C" int b2a_last_stage_times(const b2a_detector *d, const char **names, f
 }
 
 // ------------------------------------------------------------------------------------------------
-// the pipeline
+// the pipeline.  A call's batch is cut into sub-batches that run on separate CUDA streams: the
+// contour walks, the per-frame grouping, the identification and the pose chains are latency-bound
+// (few long dependent chains), so sub-batches overlap their tails with each other's bulk work.
+// Frames are independent; every per-frame / per-(frame,scale) array is simply addressed from the
+// sub-batch's first frame, and each sub-batch owns a slice of the start-candidate list.
 // ------------------------------------------------------------------------------------------------
-struct RunCtx {
-    DetGeom g;
-    const uint8_t *gray; size_t pitch, frame_stride;
+struct Sub {
+    int sb;                  // sub-batch index
+    int b0, nb;              // first frame, number of frames
+    cudaStream_t st;
+    bool timed;              // stage events are recorded for sub-batch 0 only
+    DetGeom g;               // geometry with B = nb
+    const uint8_t *gray; size_t pitch, frame_stride;      // gray frames of this sub-batch
 };
 
 static int check_frames(b2a_detector *d, const b2a_frames *f)
@@ -359,7 +380,12 @@ static int check_frames(b2a_detector *d, const b2a_frames *f)
     return B2A_OK;
 }
 
-static void stage_mark(b2a_detector *d, int st) { cudaEventRecord(d->ev[st], d->stream); d->ev_used[st] = true; }
+static void stage_mark(b2a_detector *d, const Sub &s, int st)
+{
+    if (!s.timed) return;
+    cudaEventRecord(d->ev[st], s.st);
+    d->ev_used[st] = true;
+}
 
 static int launch_err(const char *what)
 {
@@ -368,34 +394,9 @@ static int launch_err(const char *what)
     return B2A_OK;
 }
 
-// ingest + A1 + A2 + A3: everything up to the quads of every (frame, scale)
-static int run_front(b2a_detector *d, const b2a_frames *f, RunCtx &rc, int walk_max_len /* 0 = maxPerimeter */)
+static DetGeom make_geom(const b2a_detector *d, int W, int H, int B)
 {
-    TRY(check_frames(d, f));
-    CU(cudaSetDevice(d->device));
-    const int B = f->batch, W = f->width, H = f->height;
-    const size_t in_pitch = f->row_stride ? f->row_stride : (size_t)W * f->channels;
-    const size_t in_frame = f->frame_stride ? f->frame_stride : in_pitch * H;
-    std::memset(d->ev_used, 0, sizeof(d->ev_used));
-    d->launches = 0;
-    cudaStream_t st = d->stream;
-    stage_mark(d, ST_H2D);
-    const uint8_t *src = f->data;
-    size_t src_pitch = in_pitch, src_frame = in_frame;
-    if (!f->on_device) {
-        // one 2-D copy: rows of all frames (frame_stride must be a multiple of row_stride for that), else per frame
-        const size_t rowbytes = (size_t)W * f->channels;
-        if (in_frame == in_pitch * H) CU(cudaMemcpy2DAsync(d->d_in, rowbytes, f->data, in_pitch, rowbytes, (size_t)H * B, cudaMemcpyHostToDevice, st));
-        else for (int b = 0; b < B; ++b) CU(cudaMemcpy2DAsync(d->d_in + (size_t)b * rowbytes * H, rowbytes, f->data + (size_t)b * in_frame, in_pitch, rowbytes, H, cudaMemcpyHostToDevice, st));
-        src = d->d_in; src_pitch = rowbytes; src_frame = rowbytes * H;
-    }
-    stage_mark(d, ST_GRAY);
-    if (f->channels == 3) {
-        k_bgr2gray<<<d->num_sms * 8, 256, 0, st>>>(src, src_pitch, src_frame, d->d_gray, d->gray_pitch, d->gray_pitch * H, W, H, B);
-        d->launches++;
-        rc.gray = d->d_gray; rc.pitch = d->gray_pitch; rc.frame_stride = d->gray_pitch * H;
-    } else { rc.gray = src; rc.pitch = src_pitch; rc.frame_stride = src_frame; }
-    DetGeom &g = rc.g;
+    DetGeom g;
     g.W = W; g.H = H; g.B = B; g.nScales = d->nScales;
     for (int i = 0; i < MAX_SCALES; ++i) g.radius[i] = i < d->nScales ? d->radius[i] : 0;
     g.Cfloor = (int)std::floor(d->prm.adaptiveThreshConstant);
@@ -406,34 +407,80 @@ static int run_front(b2a_detector *d, const b2a_frames *f, RunCtx &rc, int walk_
     g.maxPerim = (int)(unsigned)(d->prm.maxMarkerPerimeterRate * g.maxWH);
     g.approxRate = d->prm.polygonalApproxAccuracyRate; g.minCornerDistRate = d->prm.minCornerDistanceRate;
     g.surv_cap = d->surv_cap; g.pts_cap = d->pts_cap; g.starts_cap = d->starts_cap;
-    const size_t FS = (size_t)B * g.nScales;
-    if (W != d->lastW || H != d->lastH || B > d->lastB) {       // padding words / rows must be zero
-        CU(cudaMemsetAsync(d->d_masks, 0, d->masks_words * sizeof(uint32_t), st));
-        d->lastW = W; d->lastH = H; d->lastB = std::max(B, d->lastB);
+    return g;
+}
+
+static FrameScratch offset_scratch(const FrameScratch &b, size_t f, size_t mc)
+{
+    FrameScratch s = b;
+    const size_t o = f * mc;
+    s.cq += o * 8; s.clen += o; s.tq += o * 8; s.tper += o; s.gid += o; s.sel += o;
+    s.gstart += f * (mc + 1); s.gfill += o; s.members += o; s.closeIdx += o; s.closeCnt += o;
+    s.S += o; s.parent += o; s.depth += o; s.selGroup += o;
+    s.closeM += o * ((mc + 31) / 32);
+    s.wq += o * 8; s.wres += o; s.closeStart += o; s.closeNum += o;
+    s.counters += f * 8;
+    return s;
+}
+
+// ingest + A1 + A2 + A3 for one sub-batch: everything up to the quads of every (frame, scale)
+static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_len /* 0 = maxPerimeter */)
+{
+    const int W = f->width, H = f->height, nb = s.nb, b0 = s.b0;
+    const size_t in_pitch = f->row_stride ? f->row_stride : (size_t)W * f->channels;
+    const size_t in_frame = f->frame_stride ? f->frame_stride : in_pitch * H;
+    cudaStream_t st = s.st;
+    stage_mark(d, s, ST_H2D);
+    const uint8_t *src = f->data + (size_t)b0 * in_frame;
+    size_t src_pitch = in_pitch, src_frame = in_frame;
+    if (!f->on_device) {
+        const size_t rowbytes = (size_t)W * f->channels;
+        uint8_t *dst = d->d_in + (size_t)b0 * rowbytes * H;
+        if (in_frame == in_pitch * H) CU(cudaMemcpy2DAsync(dst, rowbytes, src, in_pitch, rowbytes, (size_t)H * nb, cudaMemcpyHostToDevice, st));
+        else for (int b = 0; b < nb; ++b) CU(cudaMemcpy2DAsync(dst + (size_t)b * rowbytes * H, rowbytes, src + (size_t)b * in_frame, in_pitch, rowbytes, H, cudaMemcpyHostToDevice, st));
+        src = dst; src_pitch = rowbytes; src_frame = rowbytes * H;
     }
-    const size_t FSmax = (size_t)d->cfg.max_batch * d->nScales;
-    CU(cudaMemsetAsync(d->d_counters, 0, (4 + 3 * FSmax + d->cfg.max_batch) * sizeof(int), st));
-    stage_mark(d, ST_THRESH);
+    stage_mark(d, s, ST_GRAY);
+    if (f->channels == 3) {
+        uint8_t *gdst = d->d_gray + (size_t)b0 * d->gray_pitch * H;
+        k_bgr2gray<<<d->num_sms * 4, 256, 0, st>>>(src, src_pitch, src_frame, gdst, d->gray_pitch, d->gray_pitch * H, W, H, nb);
+        d->launches++;
+        s.gray = gdst; s.pitch = d->gray_pitch; s.frame_stride = d->gray_pitch * H;
+    } else { s.gray = src; s.pitch = src_pitch; s.frame_stride = src_frame; }
+    s.g = make_geom(d, W, H, nb);
+    DetGeom &g = s.g;
+    // this sub-batch's slice of the start list, and its arrays addressed from frame b0
+    const unsigned slice = d->starts_cap / (unsigned)d->n_sub_max;
+    g.starts_cap = slice;
+    uint2 *starts = d->d_starts + (size_t)s.sb * slice;
+    unsigned *n_starts = (unsigned *)d->d_counters + s.sb;
+    const size_t fs0 = (size_t)b0 * g.nScales, FS = (size_t)nb * g.nScales;
+    uint32_t *masks = d->d_masks + fs0 * g.mask_plane;
+    stage_mark(d, s, ST_THRESH);
     {
-        dim3 grid((W + TH_TW - 1) / TH_TW, (H + TH_TH - 1) / TH_TH, B);
-        k_threshold<<<grid, TH_THREADS, 0, st>>>(rc.gray, rc.pitch, rc.frame_stride, d->d_masks, g);
+        dim3 grid((W + TH_TW - 1) / TH_TW, (H + TH_TH - 1) / TH_TH, nb);
+        k_threshold<<<grid, TH_THREADS, 0, st>>>(s.gray, s.pitch, s.frame_stride, masks, g);
         d->launches++;
     }
-    stage_mark(d, ST_STARTS);
-    k_starts<<<d->num_sms * 8, 256, 0, st>>>(d->d_masks, d->d_starts, (unsigned *)d->d_counters, d->d_iso_count, g);
+    stage_mark(d, s, ST_STARTS);
+    k_starts<<<d->num_sms * 4, 256, 0, st>>>(masks, starts, n_starts, d->d_iso_count + fs0, g);
     d->launches++;
-    stage_mark(d, ST_WALK);
-    k_walk_count<<<d->num_sms * 16, 128, 0, st>>>(d->d_masks, d->d_starts, (const unsigned *)d->d_counters, d->d_surv, d->d_surv_count,
-                                                  d->d_contour_count, walk_max_len > 0 ? walk_max_len : g.maxPerim, g);
+    stage_mark(d, s, ST_WALK);
+    k_walk_count<<<d->num_sms * 8, 128, 0, st>>>(masks, starts, n_starts, d->d_surv + fs0 * g.surv_cap, d->d_surv_count + fs0,
+                                                 d->d_contour_count + fs0, walk_max_len > 0 ? walk_max_len : g.maxPerim, g);
     d->launches++;
-    stage_mark(d, ST_SORT);
-    k_sort_scan<<<(unsigned)FS, 1024, 0, st>>>(d->d_surv, d->d_surv_count, d->d_sorted, d->d_pts_off, d->d_status, g);
+    stage_mark(d, s, ST_SORT);
+    k_sort_scan<<<(unsigned)FS, 1024, 0, st>>>(d->d_surv + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_sorted + fs0 * g.surv_cap,
+                                               d->d_pts_off + fs0 * g.surv_cap, d->d_status + b0, g);
     d->launches++;
-    stage_mark(d, ST_WRITE);
-    k_walk_write<<<dim3(8, (unsigned)FS), 128, 0, st>>>(d->d_masks, d->d_sorted, d->d_surv_count, d->d_pts_off, d->d_pts, g);
+    stage_mark(d, s, ST_WRITE);
+    k_walk_write<<<dim3(8, (unsigned)FS), 128, 0, st>>>(masks, d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,
+                                                        d->d_pts + fs0 * (size_t)g.pts_cap, g);
     d->launches++;
-    stage_mark(d, ST_APPROX);
-    k_approx<<<dim3(8, (unsigned)FS), 256, 0, st>>>(d->d_sorted, d->d_surv_count, d->d_pts_off, d->d_pts, d->d_quad_ok, d->d_quad_xy, d->d_quad_len, g);
+    stage_mark(d, s, ST_APPROX);
+    k_approx<<<dim3(8, (unsigned)FS), 256, 0, st>>>(d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,
+                                                    d->d_pts + fs0 * (size_t)g.pts_cap, d->d_quad_ok + fs0 * g.surv_cap, d->d_quad_xy + fs0 * g.surv_cap * 8,
+                                                    d->d_quad_len + fs0 * g.surv_cap, g);
     d->launches++;
     return launch_err("front-end kernels");
 }
@@ -447,69 +494,111 @@ static FrameParams frame_params(const b2a_detector *d, const DetGeom &g)
     return fp;
 }
 
-static int run_back(b2a_detector *d, const RunCtx &rc, const b2a_camera *cam, bool stop_after_group)
+static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_after_group)
 {
-    const DetGeom &g = rc.g;
-    cudaStream_t st = d->stream;
+    const DetGeom &g = s.g;
+    cudaStream_t st = s.st;
+    const int b0 = s.b0, nb = s.nb;
+    const size_t fs0 = (size_t)b0 * g.nScales, K = d->max_markers;
     FrameArrays fa;
-    fa.fs0 = d->fs0; fa.fo0 = d->fo0; fa.surv_count = d->d_surv_count; fa.quad_ok = d->d_quad_ok; fa.quad_xy = d->d_quad_xy; fa.quad_len = d->d_quad_len;
-    fa.fo0.status = d->d_status;
+    fa.fs0 = offset_scratch(d->fs0, b0, d->max_cand);
+    fa.fo0 = d->fo0;
+    fa.fo0.n_accepted += b0; fa.fo0.n_rejected += b0; fa.fo0.corners += (size_t)b0 * K * 8; fa.fo0.ids += (size_t)b0 * K; fa.fo0.rejected += (size_t)b0 * K * 8;
+    fa.fo0.status = d->d_status + b0;
+    fa.surv_count = d->d_surv_count + fs0; fa.quad_ok = d->d_quad_ok + fs0 * g.surv_cap; fa.quad_xy = d->d_quad_xy + fs0 * g.surv_cap * 8;
+    fa.quad_len = d->d_quad_len + fs0 * g.surv_cap;
     const FrameParams fp = frame_params(d, g);
-    stage_mark(d, ST_GROUP);
-    const int smem_words = 24 * 1024;                       // 96 KB closeness matrix in shared memory
-    k_group<<<g.B, 256, smem_words * sizeof(uint32_t), st>>>(fa, fp, smem_words);
+    stage_mark(d, s, ST_GROUP);
+    const int smem_words = 50 * 1024;                       // 200 KB: per-candidate arrays + closeness matrix
+    k_group<<<nb, 256, smem_words * sizeof(uint32_t), st>>>(fa, fp, smem_words);
     d->launches++;
     if (stop_after_group) return launch_err("k_group");
-    stage_mark(d, ST_IDENT);
+    stage_mark(d, s, ST_IDENT);
     IdentParams ip;
     ip.markerSize = d->dict.markerSize; ip.borderBits = d->prm.markerBorderBits; ip.cellSize = d->prm.perspectiveRemovePixelPerCell;
     ip.cellMargin = (int)(d->prm.perspectiveRemoveIgnoredMarginPerCell * ip.cellSize);
     ip.nMarkers = d->dict.nMarkers; ip.maxCorr = (int)((double)d->dict.maxCorrectionBits * d->prm.errorCorrectionRate);
     ip.maxBorderErr = (int)(d->dict.markerSize * d->dict.markerSize * d->prm.maxErroneousBitsInBorderRate);
-    ip.minOtsuStdDev = d->prm.minOtsuStdDev; ip.W = g.W; ip.H = g.H; ip.pitch = rc.pitch; ip.frame_stride = rc.frame_stride; ip.max_cand = d->max_cand;
-    k_identify<<<dim3(128, g.B), ID_THREADS, 0, st>>>(rc.gray, d->d_dict, fa, ip);
+    ip.minOtsuStdDev = d->prm.minOtsuStdDev; ip.W = g.W; ip.H = g.H; ip.pitch = s.pitch; ip.frame_stride = s.frame_stride; ip.max_cand = d->max_cand;
+    k_identify<<<dim3(128, nb), ID_THREADS, 0, st>>>(s.gray, d->d_dict, fa, ip);
     d->launches++;
-    stage_mark(d, ST_FINAL);
-    k_finalize<<<g.B, 32, 0, st>>>(fa, fp);
+    stage_mark(d, s, ST_FINAL);
+    k_finalize<<<nb, 128, 8 * sizeof(int32_t) * d->max_cand, st>>>(fa, fp);
     d->launches++;
-    float *corners = d->fo0.corners;
+    float *corners = fa.fo0.corners;
     if (d->prm.cornerRefinementMethod == 1) {
         SubpixParams sp;
-        sp.W = g.W; sp.H = g.H; sp.pitch = rc.pitch; sp.frame_stride = rc.frame_stride; sp.max_markers = d->max_markers;
+        sp.W = g.W; sp.H = g.H; sp.pitch = s.pitch; sp.frame_stride = s.frame_stride; sp.max_markers = d->max_markers;
         sp.markerSize = d->dict.markerSize; sp.borderBits = d->prm.markerBorderBits; sp.maxWin = d->prm.cornerRefinementWinSize;
         sp.maxIter = d->prm.cornerRefinementMaxIterations; sp.relWin = d->prm.relativeCornerRefinmentWinSize; sp.eps = d->prm.cornerRefinementMinAccuracy;
-        k_subpix<<<d->num_sms * 2, 128, 0, st>>>(rc.gray, d->fo0.n_accepted, d->fo0.corners, d->d_corners2, g.B, sp);
+        float *c2 = d->d_corners2 + (size_t)b0 * K * 8;
+        k_subpix<<<d->num_sms * 2, 128, 0, st>>>(s.gray, fa.fo0.n_accepted, fa.fo0.corners, c2, nb, sp);
         d->launches++;
-        corners = d->d_corners2;
+        corners = c2;
     }
-    stage_mark(d, ST_POSE);
+    stage_mark(d, s, ST_POSE);
     if (cam) {
-        k_pose<<<d->num_sms, 64, 0, st>>>(corners, d->fo0.n_accepted, g.B, d->max_markers, to_camera(cam), cam->marker_length, d->d_rvecs, d->d_tvecs);
+        k_pose<<<(nb * (int)K + 31) / 32, 32, 0, st>>>(corners, fa.fo0.n_accepted, nb, d->max_markers, to_camera(cam), cam->marker_length,
+                                                        d->d_rvecs + (size_t)b0 * K * 3, d->d_tvecs + (size_t)b0 * K * 3);
         d->launches++;
     }
-    stage_mark(d, ST_D2H);
-    const size_t BK = (size_t)g.B * d->max_markers;
-    CU(cudaMemcpyAsync(d->h_nacc, d->fo0.n_accepted, g.B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(d->h_nrej, d->fo0.n_rejected, g.B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(d->h_status, d->d_status, g.B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(d->h_corners, corners, BK * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(d->h_ids, d->fo0.ids, BK * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(d->h_rejected, d->fo0.rejected, BK * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    stage_mark(d, s, ST_D2H);
+    const size_t BK = (size_t)nb * K, o = (size_t)b0 * K;
+    CU(cudaMemcpyAsync(d->h_nacc + b0, fa.fo0.n_accepted, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d->h_nrej + b0, fa.fo0.n_rejected, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d->h_status + b0, d->d_status + b0, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d->h_corners + o * 8, corners, BK * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d->h_ids + o, fa.fo0.ids, BK * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d->h_rejected + o * 8, fa.fo0.rejected, BK * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (cam) {
-        CU(cudaMemcpyAsync(d->h_rvecs, d->d_rvecs, BK * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(d->h_tvecs, d->d_tvecs, BK * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(d->h_rvecs + o * 3, d->d_rvecs + o * 3, BK * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(d->h_tvecs + o * 3, d->d_tvecs + o * 3, BK * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
-    cudaEventRecord(d->ev[ST_COUNT], st);
-    TRY(launch_err("back-end kernels"));
-    CU(cudaStreamSynchronize(st));
-    // stage times
-    int prev = -1;
-    for (int i = 0; i < ST_COUNT; ++i) d->stage_ms[i] = 0.f;
-    for (int i = 0; i <= ST_COUNT; ++i) {
-        if (i < ST_COUNT && !d->ev_used[i]) continue;
-        if (prev >= 0) cudaEventElapsedTime(&d->stage_ms[prev], d->ev[prev], d->ev[i]);
-        prev = i;
+    if (s.timed) cudaEventRecord(d->ev[ST_COUNT], st);
+    return launch_err("back-end kernels");
+}
+
+// mode: 0 full pipeline, 1 stop after the front end (taps), 2 stop after grouping (candidate tap)
+static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *cam, int mode, int walk_max_len, std::vector<Sub> *subs_out)
+{
+    TRY(check_frames(d, f));
+    CU(cudaSetDevice(d->device));
+    const int B = f->batch, W = f->width, H = f->height;
+    std::memset(d->ev_used, 0, sizeof(d->ev_used));
+    d->launches = 0;
+    cudaStream_t s0 = d->stream;
+    if (W != d->lastW || H != d->lastH || B > d->lastB) {       // padding words / rows of the masks must be zero
+        CU(cudaMemsetAsync(d->d_masks, 0, d->masks_words * sizeof(uint32_t), s0));
+        d->lastW = W; d->lastH = H; d->lastB = std::max(B, d->lastB);
     }
+    const size_t FSmax = (size_t)d->cfg.max_batch * d->nScales;
+    CU(cudaMemsetAsync(d->d_counters, 0, (d->n_sub_max + 3 * FSmax + d->cfg.max_batch) * sizeof(int), s0));
+    // sub-batches
+    const int nsub = std::max(1, std::min(std::min(d->n_streams, d->n_sub_max), B));
+    std::vector<Sub> subs(nsub);
+    for (int i = 0; i < nsub; ++i) {
+        Sub &s = subs[i];
+        s.sb = i; s.b0 = (int)((long long)B * i / nsub); s.nb = (int)((long long)B * (i + 1) / nsub) - s.b0;
+        s.st = d->streams[i]; s.timed = (i == 0);
+    }
+    CU(cudaEventRecord(d->ev_fork, s0));
+    for (int i = 1; i < nsub; ++i) CU(cudaStreamWaitEvent(subs[i].st, d->ev_fork, 0));
+    for (int i = 0; i < nsub; ++i) {
+        TRY(run_front(d, f, subs[i], walk_max_len));
+        if (mode != 1) TRY(run_back(d, subs[i], cam, mode == 2));
+    }
+    for (int i = 1; i < nsub; ++i) { CU(cudaEventRecord(d->ev_join[i], subs[i].st)); CU(cudaStreamWaitEvent(s0, d->ev_join[i], 0)); }
+    CU(cudaStreamSynchronize(s0));
+    if (mode == 0) {
+        int prev = -1;
+        for (int i = 0; i < ST_COUNT; ++i) d->stage_ms[i] = 0.f;
+        for (int i = 0; i <= ST_COUNT; ++i) {
+            if (i < ST_COUNT && !d->ev_used[i]) continue;
+            if (prev >= 0) cudaEventElapsedTime(&d->stage_ms[prev], d->ev[prev], d->ev[i]);
+            prev = i;
+        }
+    }
+    if (subs_out) *subs_out = subs;
     return B2A_OK;
 }
 
@@ -526,9 +615,7 @@ static int fill_out(b2a_detector *d, int B, bool pose, b2a_detections *out)
 extern "C" int b2a_detect(b2a_detector *d, const b2a_frames *frames, b2a_detections *out)
 {
     if (!out) return set_err(B2A_ERR_INVALID, "null output");
-    RunCtx rc;
-    TRY(run_front(d, frames, rc, 0));
-    TRY(run_back(d, rc, nullptr, false));
+    TRY(run_pipeline(d, frames, nullptr, 0, 0, nullptr));
     return fill_out(d, frames->batch, false, out);
 }
 
@@ -536,10 +623,15 @@ extern "C" int b2a_detect_pose(b2a_detector *d, const b2a_frames *frames, const 
 {
     if (!out || !cam) return set_err(B2A_ERR_INVALID, "null argument");
     if (!(cam->marker_length > 0)) return set_err(B2A_ERR_INVALID, "markerLength <= 0");
-    RunCtx rc;
-    TRY(run_front(d, frames, rc, 0));
-    TRY(run_back(d, rc, cam, false));
+    TRY(run_pipeline(d, frames, cam, 0, 0, nullptr));
     return fill_out(d, frames->batch, true, out);
+}
+
+extern "C" int b2a_detector_set_streams(b2a_detector *d, int n)
+{
+    if (!d || n < 1) return set_err(B2A_ERR_INVALID, "streams must be >= 1");
+    d->n_streams = std::min(n, d->n_sub_max);
+    return B2A_OK;
 }
 
 extern "C" int b2a_estimate_pose_single_markers(b2a_detector *d, const float *corners, int n, const b2a_camera *cam, double *rvecs, double *tvecs)
@@ -554,7 +646,7 @@ extern "C" int b2a_estimate_pose_single_markers(b2a_detector *d, const float *co
     CU(cudaMalloc(&dt, (size_t)n * 3 * sizeof(double)));
     cudaStream_t st = d->stream;
     cudaMemcpyAsync(dc, corners, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice, st);
-    k_pose<<<std::min(d->num_sms * 2, (n + 63) / 64), 64, 0, st>>>(dc, nullptr, 1, n, to_camera(cam), cam->marker_length, dr, dt);
+    k_pose<<<(n + 31) / 32, 32, 0, st>>>(dc, nullptr, 1, n, to_camera(cam), cam->marker_length, dr, dt);
     cudaMemcpyAsync(rvecs, dr, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(tvecs, dt, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
@@ -568,13 +660,14 @@ extern "C" int b2a_estimate_pose_single_markers(b2a_detector *d, const float *co
 // ------------------------------------------------------------------------------------------------
 extern "C" int b2a_debug_threshold(b2a_detector *d, const b2a_frames *f, uint8_t *gray, uint8_t *masks)
 {
-    RunCtx rc;
-    TRY(run_front(d, f, rc, 0));
-    const DetGeom &g = rc.g;
+    std::vector<Sub> subs;
+    TRY(run_pipeline(d, f, nullptr, 1, 0, &subs));
+    const DetGeom g = make_geom(d, f->width, f->height, f->batch);
     cudaStream_t st = d->stream;
-    if (gray) CU(cudaMemcpy2DAsync(gray, g.W, rc.gray, rc.pitch, g.W, (size_t)g.H * g.B, cudaMemcpyDeviceToHost, st));
-    if (gray && rc.frame_stride != rc.pitch * g.H)
-        for (int b = 0; b < g.B; ++b) CU(cudaMemcpy2DAsync(gray + (size_t)b * g.W * g.H, g.W, rc.gray + (size_t)b * rc.frame_stride, rc.pitch, g.W, g.H, cudaMemcpyDeviceToHost, st));
+    if (gray)
+        for (const Sub &s : subs)
+            for (int b = 0; b < s.nb; ++b)
+                CU(cudaMemcpy2DAsync(gray + (size_t)(s.b0 + b) * g.W * g.H, g.W, s.gray + (size_t)b * s.frame_stride, s.pitch, g.W, g.H, cudaMemcpyDeviceToHost, st));
     if (masks) {
         uint8_t *tmp = nullptr;
         const size_t n = (size_t)g.B * g.nScales * g.H * g.W;
@@ -591,10 +684,9 @@ extern "C" int b2a_debug_threshold(b2a_detector *d, const b2a_frames *f, uint8_t
 
 extern "C" int b2a_debug_contours(b2a_detector *d, const b2a_frames *f, int32_t *counts, int32_t *n_kept, int32_t *kept_len, int cap, int16_t *pts, int pts_cap)
 {
-    RunCtx rc;
-    TRY(run_front(d, f, rc, 2 * f->width * f->height + 16));       // exact total count: never give up on long borders
-    const DetGeom &g = rc.g;
-    CU(cudaStreamSynchronize(d->stream));
+    if (!f) return set_err(B2A_ERR_INVALID, "null argument");
+    TRY(run_pipeline(d, f, nullptr, 1, 2 * f->width * f->height + 16, nullptr));     // exact total count: never give up on long borders
+    const DetGeom g = make_geom(d, f->width, f->height, f->batch);
     const size_t FS = (size_t)g.B * g.nScales;
     std::vector<int> cc(FS), iso(FS), sc(FS), off((size_t)FS * g.surv_cap);
     std::vector<uint4> sorted((size_t)FS * g.surv_cap);
@@ -625,11 +717,8 @@ extern "C" int b2a_debug_contours(b2a_detector *d, const b2a_frames *f, int32_t 
 
 extern "C" int b2a_debug_candidates(b2a_detector *d, const b2a_frames *f, int32_t *n_cand, float *quads, int cap)
 {
-    RunCtx rc;
-    TRY(run_front(d, f, rc, 0));
-    TRY(run_back(d, rc, nullptr, true));
-    CU(cudaStreamSynchronize(d->stream));
-    const int B = rc.g.B;
+    TRY(run_pipeline(d, f, nullptr, 2, 0, nullptr));
+    const int B = f->batch;
     std::vector<int> cnt((size_t)B * 8);
     CU(cudaMemcpy(cnt.data(), d->fs0.counters, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost));
     for (int b = 0; b < B; ++b) {

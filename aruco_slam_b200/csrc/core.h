@@ -140,12 +140,16 @@ struct MaskView {
     int PWW;
     B2A_HD unsigned win3(int x, int y) const      // bits x-1, x, x+1 of row y
     {
-        const uint32_t *row = plane + (size_t)(y + 1) * PWW + (x >> 5) + 1;
-        const int o = x & 31;
-        const uint32_t w = ld_ro(row);
-        if (o == 0) return ((w << 1) | (ld_ro(row - 1) >> 31)) & 7u;
-        if (o == 31) return ((w >> 30) | (ld_ro(row + 1) << 2)) & 7u;
-        return (w >> (o - 1)) & 7u;
+        // two unconditional loads + funnel shift: no data-dependent branch between the loads, so
+        // the six loads of a 3x3 neighbourhood are all in flight together
+        const int bit = x + 31;                                   // padded bit position of pixel x-1
+        const uint32_t *row = plane + (size_t)(y + 1) * PWW + (bit >> 5);
+        const uint32_t lo = ld_ro(row), hi = ld_ro(row + 1);
+#if defined(__CUDA_ARCH__)
+        return __funnelshift_r(lo, hi, bit & 31) & 7u;
+#else
+        return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (bit & 31)) & 7u;
+#endif
     }
     // neighbour code of pixel (x,y): bit d = neighbour in direction d
     B2A_HD unsigned operator()(int x, int y) const

@@ -419,31 +419,53 @@ __device__ __forceinline__ FrameScratch frame_scratch(const FrameScratch &b, int
     return s;
 }
 
+// dynamic shared memory of k_group: 8 per-candidate arrays (gid, sel, gstart, gfill, members,
+// closeIdx, closeCnt, tper) that the sequential grouping section hammers, then the closeness
+// bit matrix in whatever is left (global fallback when it does not fit)
 __global__ void __launch_bounds__(256)
 k_group(FrameArrays fa, FrameParams fp, int smem_words)
 {
-    extern __shared__ uint32_t s_M[];
+    extern __shared__ uint32_t s_dyn[];
     __shared__ int s_warp[33];
     const int f = blockIdx.x;
     BlockCtx ctx{s_warp};
-    const FrameScratch fs = frame_scratch(fa.fs0, f, fp.max_cand);
+    FrameScratch fs = frame_scratch(fa.fs0, f, fp.max_cand);
+    const int mc1 = fp.max_cand + 1;
+    int32_t *base = reinterpret_cast<int32_t *>(s_dyn);
+    fs.gid = base; fs.sel = base + mc1; fs.gstart = base + 2 * mc1; fs.gfill = base + 3 * mc1;
+    fs.members = base + 4 * mc1; fs.closeIdx = base + 5 * mc1; fs.closeCnt = base + 6 * mc1;
+    fs.tper = reinterpret_cast<float *>(base + 7 * mc1);
     ScaleQuads sq;
     sq.count = fa.surv_count + (size_t)f * fp.nScales;
     sq.quad_ok = fa.quad_ok + (size_t)f * fp.nScales * fp.surv_cap;
     sq.quad_xy = fa.quad_xy + (size_t)f * fp.nScales * fp.surv_cap * 8;
     sq.len = fa.quad_len + (size_t)f * fp.nScales * fp.surv_cap;
-    frame_group(ctx, fp, sq, fs, s_M, smem_words);
+    frame_group(ctx, fp, sq, fs, s_dyn + 8 * mc1, smem_words - 8 * mc1);
 }
 
-__global__ void k_finalize(FrameArrays fa, FrameParams fp)
+// dynamic shared memory of k_finalize: copies of depth, parent, closeStart, closeNum (n_sel entries),
+// wres (n_work entries) and the valid / was / chosen scratch, so the single-lane A6 loop runs on-chip
+__global__ void __launch_bounds__(128)
+k_finalize(FrameArrays fa, FrameParams fp)
 {
+    extern __shared__ uint32_t s_dyn[];
     __shared__ int s_warp[33];
     const int f = blockIdx.x;
     BlockCtx ctx{s_warp};
-    const FrameScratch fs = frame_scratch(fa.fs0, f, fp.max_cand);
+    FrameScratch fs = frame_scratch(fa.fs0, f, fp.max_cand);
     FrameOutputs fo = fa.fo0;
     fo.n_accepted += f; fo.n_rejected += f; fo.status += f;
     fo.corners += (size_t)f * fp.max_markers * 8; fo.ids += (size_t)f * fp.max_markers; fo.rejected += (size_t)f * fp.max_markers * 8;
+    const int mc = fp.max_cand;
+    int32_t *base = reinterpret_cast<int32_t *>(s_dyn);
+    const int nS = fs.counters[FC_NSEL], nW = fs.counters[FC_NWORK];
+    for (int i = threadIdx.x; i < nS; i += blockDim.x) {
+        base[i] = fs.depth[i]; base[mc + i] = fs.parent[i]; base[2 * mc + i] = fs.closeStart[i]; base[3 * mc + i] = fs.closeNum[i];
+    }
+    for (int i = threadIdx.x; i < nW; i += blockDim.x) base[4 * mc + i] = fs.wres[i];
+    __syncthreads();
+    fs.depth = base; fs.parent = base + mc; fs.closeStart = base + 2 * mc; fs.closeNum = base + 3 * mc; fs.wres = base + 4 * mc;
+    fs.gid = base + 5 * mc; fs.sel = base + 6 * mc; fs.gfill = base + 7 * mc;
     frame_finalize(ctx, fp, fs, fo);
 }
 

@@ -65,6 +65,8 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
                         uint32_t *smemM, int smemM_words)
 {
     const int tid = ctx.tid(), nt = ctx.nthreads();
+    if (tid == 0) fs.counters[FC_STATUS] = 0;
+    ctx.sync();
     // ---- 1. gather candidates in reference order (scale by scale, contour list order) + A4 ----
     int n = 0;
     for (int s = 0; s < fp.nScales; ++s) {
@@ -268,6 +270,7 @@ B2A_HD void frame_finalize(Ctx &ctx, const FrameParams &fp, const FrameScratch &
         }
     }
     int na = 0, nr = 0, status = fs.counters[FC_STATUS];
+    if (*fo.status != 0) status = *fo.status;               // overflow flagged by an earlier stage
     for (int v = 0; v < nS; ++v) {
         if (valid[v]) {
             const int w = chosen[v];

@@ -142,7 +142,6 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
     fp.minMarkerDistanceRate = ep->minMarkerDistanceRate; fp.minGroupDistance = ep->minGroupDistance;
     ScaleQuads sq{s_count.data(), q_ok.data(), q_xy.data(), q_len.data()};
     HostCtx ctx;
-    counters[FC_STATUS] = status;
     frame_group(ctx, fp, sq, fs, nullptr, 0);
     if (n_cand) *n_cand = counters[FC_NCAND];
     if (cand) std::memcpy(cand, cq.data(), (size_t)counters[FC_NCAND] * 8 * sizeof(float));
@@ -173,7 +172,7 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
             }
         wres[w] = res;
     }
-    int st = 0;
+    int st = status;
     FrameOutputs fo{n_acc, n_rej, corners, ids, rejected, &st};
     frame_finalize(ctx, fp, fs, fo);
     return st;
