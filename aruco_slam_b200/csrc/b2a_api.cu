@@ -173,6 +173,7 @@ struct b2a_detector {
     int *d_pts_off = nullptr; uint32_t *d_pts = nullptr; int pts_cap = 0;
     uint8_t *d_quad_ok = nullptr; int32_t *d_quad_xy = nullptr, *d_quad_len = nullptr;
     unsigned long long *d_dict = nullptr;
+    WalkTables *d_tables = nullptr;
     FrameScratch fs0{};                       // frame-0 pointers
     FrameOutputs fo0{};
     float *d_corners2 = nullptr;              // subpix output
@@ -274,6 +275,12 @@ static int create_impl(b2a_detector *d)
         }
         TRY(dev_alloc(d, &d->d_dict, packed.size()));
         CU(cudaMemcpy(d->d_dict, packed.data(), packed.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
+    {
+        static WalkTables wt;
+        for (int i = 0; i < 4096; ++i) build_walk_table_entry(wt, i);
+        TRY(dev_alloc(d, &d->d_tables, 1));
+        CU(cudaMemcpy(d->d_tables, &wt, sizeof(wt), cudaMemcpyHostToDevice));
     }
     const size_t MC = d->max_cand, BM = (size_t)B * MC;
     FrameScratch &fs = d->fs0;
@@ -466,8 +473,8 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     k_starts<<<d->num_sms * 4, 256, 0, st>>>(masks, starts, n_starts, d->d_iso_count + fs0, g);
     d->launches++;
     stage_mark(d, s, ST_WALK);
-    k_walk_count<<<d->num_sms * 8, 128, 0, st>>>(masks, starts, n_starts, d->d_surv + fs0 * g.surv_cap, d->d_surv_count + fs0,
-                                                 d->d_contour_count + fs0, walk_max_len > 0 ? walk_max_len : g.maxPerim, g);
+    k_walk_count<<<d->num_sms * 4, 256, 0, st>>>(masks, starts, n_starts, d->d_surv + fs0 * g.surv_cap, d->d_surv_count + fs0,
+                                                 d->d_contour_count + fs0, walk_max_len > 0 ? walk_max_len : g.maxPerim, d->d_tables, g);
     d->launches++;
     stage_mark(d, s, ST_SORT);
     k_sort_scan<<<(unsigned)FS, 1024, 0, st>>>(d->d_surv + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_sorted + fs0 * g.surv_cap,
@@ -475,7 +482,7 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     d->launches++;
     stage_mark(d, s, ST_WRITE);
     k_walk_write<<<dim3(8, (unsigned)FS), 128, 0, st>>>(masks, d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,
-                                                        d->d_pts + fs0 * (size_t)g.pts_cap, g);
+                                                        d->d_pts + fs0 * (size_t)g.pts_cap, d->d_tables, g);
     d->launches++;
     stage_mark(d, s, ST_APPROX);
     k_approx<<<dim3(8, (unsigned)FS), 256, 0, st>>>(d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,

@@ -151,61 +151,91 @@ struct MaskView {
         return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (bit & 31)) & 7u;
 #endif
     }
+    // 3x3 window of pixel (x,y) as 9 bits: rows y-1, y, y+1 at bits 0-2, 3-5, 6-8 (bit j = column x-1+j)
+    B2A_HD unsigned win9(int x, int y) const { return win3(x, y - 1) | (win3(x, y) << 3) | (win3(x, y + 1) << 6); }
     // neighbour code of pixel (x,y): bit d = neighbour in direction d
-    B2A_HD unsigned operator()(int x, int y) const
+    B2A_HD unsigned operator()(int x, int y) const { return code_of_win9(win9(x, y)); }
+    B2A_HD static unsigned code_of_win9(unsigned w)
     {
-        const unsigned u = win3(x, y - 1), m = win3(x, y), d = win3(x, y + 1);
+        const unsigned u = w & 7u, m = (w >> 3) & 7u, d = (w >> 6) & 7u;
         return ((m >> 2) & 1u) | (((u >> 2) & 1u) << 1) | (((u >> 1) & 1u) << 2) | ((u & 1u) << 3) |
                ((m & 1u) << 4) | ((d & 1u) << 5) | (((d >> 1) & 1u) << 6) | (((d >> 2) & 1u) << 7);
     }
 };
 
+// Border walking is driven by two 4 KB tables indexed by (3x3 window, direction) so that one step is
+// "six mask loads, one table load":
+//   succ[w9 | s_in << 9] = s_out | elig     the state's successor direction and its start eligibility
+//   pred[w9 | t    << 9] = s_p   | elig     w9 = window of the previous pixel p, t = direction p -> c;
+//                                           s_p = p's own incoming direction, elig = eligibility of (p, s_p)
+// elig: WT_OUTER = outer-type start-eligible (key (y,x,0)), WT_HOLE = hole-type only (key (y,x+1,1)).
+enum { WT_OUTER = 8, WT_HOLE = 16, WT_ELIG = 24 };
+struct WalkTables { uint8_t succ[4096]; uint8_t pred[4096]; };
+
+B2A_HD unsigned state_eligibility(unsigned code, int s)
+{
+    if (!(code & 16u) && first_cw(code, 4) == s) return WT_OUTER;
+    if (!(code & 1u) && first_cw(code, 0) == s) return WT_HOLE;
+    return 0;
+}
+B2A_HD void build_walk_table_entry(WalkTables &t, int idx)
+{
+    const unsigned w9 = (unsigned)idx & 511u, code = MaskView::code_of_win9(w9);
+    const int s = idx >> 9;
+    t.succ[idx] = (uint8_t)((unsigned)succ_dir(code, s) | state_eligibility(code, s));
+    const int sp = pred_dir(code, s);                       // here s plays the role of t (direction p -> c)
+    t.pred[idx] = (uint8_t)((unsigned)sp | state_eligibility(code, sp));
+}
+B2A_HD uint32_t key_of(int x, int y, unsigned elig, int KS)
+{
+    return (elig & WT_OUTER) ? (uint32_t)((y * KS + x) * 2) : (uint32_t)((y * KS + x + 1) * 2 + 1);
+}
+
 // Walk the border through state (x0,y0,s0) in both directions at once.  Returns the border
 // length if (x0,y0,s0) is the border's first state; 0 if another start-eligible state with a
 // smaller key lies on the border (then that one reports it); -1 once more than max_len steps
 // were taken without closing (the border is discarded by the perimeter gate anyway).
-// code_at(x, y) returns the neighbour code of a set pixel; W1 = key stride - 1.
-template <class CodeAt>
-B2A_HD int walk_count(const CodeAt &code_at, int W1, int x0, int y0, int s0, uint32_t key0, int max_len)
+template <class Win>
+B2A_HD int walk_count(const Win &win, const uint8_t *__restrict__ succ, const uint8_t *__restrict__ pred, int KS,
+                      int x0, int y0, int s0, uint32_t key0, int max_len)
 {
     int xf = x0, yf = y0, sf = s0, xb = x0, yb = y0, sb = s0;
-    unsigned cf = code_at(x0, y0);
+    int so = succ[win.win9(x0, y0) | ((unsigned)s0 << 9)] & 7;
     int n = 0;
     for (;;) {
-        const int so = succ_dir(cf, sf);
         xf += dir_dx(so); yf += dir_dy(so); sf = so ^ 4;
         ++n;
         if (xf == xb && yf == yb && sf == sb) return n;
         const int xp = xb + dir_dx(sb), yp = yb + dir_dy(sb);
-        cf = code_at(xf, yf);                       // two independent loads in flight
-        const unsigned cp = code_at(xp, yp);
-        if (start_key(xf, yf, sf, cf, W1) < key0) return 0;
+        const unsigned wf = win.win9(xf, yf), wp = win.win9(xp, yp);       // twelve independent loads in flight
+        const unsigned ef = succ[wf | ((unsigned)sf << 9)], ep = pred[wp | ((unsigned)(sb ^ 4) << 9)];
+        if ((ef & WT_ELIG) && key_of(xf, yf, ef, KS) < key0) return 0;
         if (n > max_len) return -1;
-        sb = pred_dir(cp, sb ^ 4);
-        xb = xp; yb = yp;
+        sb = (int)(ep & 7u); xb = xp; yb = yp;
         ++n;
         if (xf == xb && yf == yb && sf == sb) return n;
-        if (start_key(xb, yb, sb, cp, W1) < key0) return 0;
+        if ((ep & WT_ELIG) && key_of(xb, yb, ep, KS) < key0) return 0;
         if (n > max_len) return -1;
+        so = (int)(ef & 7u);
     }
 }
 // Emit the n border points (x | y << 16) starting at state (x0,y0,s0), filling from both ends.
-template <class CodeAt>
-B2A_HD void walk_write(const CodeAt &code_at, int x0, int y0, int s0, int n, uint32_t *__restrict__ out)
+template <class Win>
+B2A_HD void walk_write(const Win &win, const uint8_t *__restrict__ succ, const uint8_t *__restrict__ pred,
+                       int x0, int y0, int s0, int n, uint32_t *__restrict__ out)
 {
     int xf = x0, yf = y0, sf = s0, xb = x0, yb = y0, sb = s0;
     out[0] = (uint32_t)x0 | ((uint32_t)y0 << 16);
     int lo = 1, hi = n - 1;
-    unsigned cf = code_at(x0, y0);
+    int so = succ[win.win9(x0, y0) | ((unsigned)s0 << 9)] & 7;
     while (lo <= hi) {
-        const int so = succ_dir(cf, sf);
         xf += dir_dx(so); yf += dir_dy(so); sf = so ^ 4;
         out[lo++] = (uint32_t)xf | ((uint32_t)yf << 16);
         if (lo > hi) break;
         const int xp = xb + dir_dx(sb), yp = yb + dir_dy(sb);
-        cf = code_at(xf, yf);
-        const unsigned cp = code_at(xp, yp);
-        sb = pred_dir(cp, sb ^ 4);
+        const unsigned wf = win.win9(xf, yf), wp = win.win9(xp, yp);
+        so = succ[wf | ((unsigned)sf << 9)] & 7;
+        sb = pred[wp | ((unsigned)(sb ^ 4) << 9)] & 7;
         xb = xp; yb = yp;
         out[hi--] = (uint32_t)xb | ((uint32_t)yb << 16);
     }

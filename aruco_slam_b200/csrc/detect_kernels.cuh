@@ -233,12 +233,27 @@ __global__ void k_starts(const uint32_t *__restrict__ masks, uint2 *__restrict__
 // A3a step 2: one thread per start candidate walks its border both ways.
 //   surv[(fs)*surv_cap + slot] = (key, length, x | y<<16, 0)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_walk_count(const uint32_t *__restrict__ masks, const uint2 *__restrict__ starts,
-                             const unsigned *__restrict__ n_starts, uint4 *__restrict__ surv, int *__restrict__ surv_count,
-                             int *__restrict__ contour_count, int max_len, DetGeom g)
+__device__ __forceinline__ void load_walk_tables(const WalkTables *__restrict__ g, uint8_t *s_succ, uint8_t *s_pred)
 {
+    const uint4 *src = reinterpret_cast<const uint4 *>(g);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        reinterpret_cast<uint4 *>(s_succ)[i] = __ldg(src + i);
+        reinterpret_cast<uint4 *>(s_pred)[i] = __ldg(src + 256 + i);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+k_walk_count(const uint32_t *__restrict__ masks, const uint2 *__restrict__ starts, const unsigned *__restrict__ n_starts,
+             uint4 *__restrict__ surv, int *__restrict__ surv_count, int *__restrict__ contour_count, int max_len,
+             const WalkTables *__restrict__ tables, DetGeom g)
+{
+    __shared__ __align__(16) uint8_t s_succ[4096];
+    __shared__ __align__(16) uint8_t s_pred[4096];
     unsigned n = *n_starts;
     if (n > g.starts_cap) n = g.starts_cap;
+    if (blockIdx.x * blockDim.x >= n) return;
+    load_walk_tables(tables, s_succ, s_pred);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint2 e = starts[i];
         const int fs = (int)(e.x >> 1), type = (int)(e.x & 1u);
@@ -247,7 +262,7 @@ __global__ void k_walk_count(const uint32_t *__restrict__ masks, const uint2 *__
         const unsigned c0 = rd(x, y);
         int s0; uint32_t key0;
         if (!start_state(c0, x, y, type, g.KS, s0, key0)) continue;
-        const int len = walk_count(rd, g.KS - 1, x, y, s0, key0, max_len);
+        const int len = walk_count(rd, s_succ, s_pred, g.KS, x, y, s0, key0, max_len);
         if (len > 0) {
             atomicAdd(&contour_count[fs], 1);
             if (len >= g.minPerim && len <= g.maxPerim) {
@@ -318,17 +333,22 @@ k_sort_scan(const uint4 *__restrict__ surv, int *__restrict__ surv_count, uint4 
 }
 
 // A3a step 4: emit the border points of the kept borders
-__global__ void k_walk_write(const uint32_t *__restrict__ masks, const uint4 *__restrict__ sorted, const int *__restrict__ surv_count,
-                             const int *__restrict__ pts_off, uint32_t *__restrict__ pts, DetGeom g)
+__global__ void __launch_bounds__(128)
+k_walk_write(const uint32_t *__restrict__ masks, const uint4 *__restrict__ sorted, const int *__restrict__ surv_count,
+             const int *__restrict__ pts_off, uint32_t *__restrict__ pts, const WalkTables *__restrict__ tables, DetGeom g)
 {
+    __shared__ __align__(16) uint8_t s_succ[4096];
+    __shared__ __align__(16) uint8_t s_pred[4096];
     const int fs = blockIdx.y;
     const int n = surv_count[fs];
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    load_walk_tables(tables, s_succ, s_pred);
     MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int off = pts_off[(size_t)fs * g.surv_cap + i];
         if (off < 0) continue;
         const uint4 e = sorted[(size_t)fs * g.surv_cap + i];
-        walk_write(rd, (int)(e.z & 0xFFFFu), (int)(e.z >> 16), (int)e.w, (int)e.y, pts + (size_t)fs * g.pts_cap + off);
+        walk_write(rd, s_succ, s_pred, (int)(e.z & 0xFFFFu), (int)(e.z >> 16), (int)e.w, (int)e.y, pts + (size_t)fs * g.pts_cap + off);
     }
 }
 

@@ -70,6 +70,8 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
                 if (masks_in[((size_t)s * H + y) * W + x]) pl[(size_t)(y + 1) * PWW + (x >> 5) + 1] |= 1u << (x & 31);
         } else emu_threshold(gray, W, H, ep->radius[s], ep->Cfloor, pl, PWW);
     }
+    static WalkTables wt;
+    for (int i = 0; i < 4096; ++i) build_walk_table_entry(wt, i);
     const int surv_cap = ep->surv_cap;
     std::vector<int32_t> s_count(nS, 0), q_len((size_t)nS * surv_cap), q_xy((size_t)nS * surv_cap * 8);
     std::vector<uint8_t> q_ok((size_t)nS * surv_cap, 0);
@@ -96,7 +98,7 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
                         const unsigned c0 = mv(x, y);
                         int s0; uint32_t key0;
                         if (!start_state(c0, x, y, type, KS, s0, key0)) continue;
-                        const int len = walk_count(mv, KS - 1, x, y, s0, key0, 2 * W * H + 16);
+                        const int len = walk_count(mv, wt.succ, wt.pred, KS, x, y, s0, key0, 2 * W * H + 16);
                         if (len > 0) {
                             ++ncont;
                             if (len >= minPerim && len <= maxPerim) surv.push_back({key0, len, x, y, s0});
@@ -113,7 +115,7 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
         for (size_t i = 0; i < surv.size(); ++i) {
             const Surv &e = surv[i];
             std::vector<uint32_t> pts(e.len);
-            walk_write(mv, e.x, e.y, e.s0, e.len, pts.data());
+            walk_write(mv, wt.succ, wt.pred, e.x, e.y, e.s0, e.len, pts.data());
             if (s == dbg_scale) {
                 if (dbg_len && (int)i < dbg_cap) dbg_len[i] = e.len;
                 if (dbg_pts) for (int k = 0; k < e.len && w < dbg_pts_cap; ++k, ++w) { dbg_pts[2 * w] = (int16_t)px_of(pts[k]); dbg_pts[2 * w + 1] = (int16_t)py_of(pts[k]); }
