@@ -145,8 +145,8 @@ static Camera to_camera(const b2a_camera *c)
 // ------------------------------------------------------------------------------------------------
 // detector handle
 // ------------------------------------------------------------------------------------------------
-enum { ST_H2D, ST_GRAY, ST_THRESH, ST_STARTS, ST_WALK, ST_SORT, ST_WRITE, ST_APPROX, ST_GROUP, ST_IDENT, ST_FINAL, ST_POSE, ST_D2H, ST_COUNT };
-static const char *k_stage_names[ST_COUNT] = {"h2d", "bgr2gray", "threshold", "starts", "walk_count", "sort_scan", "walk_write",
+enum { ST_H2D, ST_GRAY, ST_THRESH, ST_ANCHORS, ST_SEGMENTS, ST_CYCLES, ST_SORT, ST_ASSIGN, ST_EMIT, ST_APPROX, ST_GROUP, ST_IDENT, ST_FINAL, ST_POSE, ST_D2H, ST_COUNT };
+static const char *k_stage_names[ST_COUNT] = {"h2d", "bgr2gray", "threshold", "anchors", "segments", "cycles", "sort_scan", "assign", "emit",
                                               "approx", "group", "identify", "finalize", "pose", "d2h"};
 
 struct b2a_detector {
@@ -166,8 +166,10 @@ struct b2a_detector {
     // device memory
     uint8_t *d_in = nullptr, *d_gray = nullptr;
     uint32_t *d_masks = nullptr; size_t masks_words = 0;
-    uint2 *d_starts = nullptr; unsigned starts_cap = 0;
-    int *d_counters = nullptr;               // [0] n_starts (unsigned), then per-(f,s) arrays
+    // border graph (core.h): anchors of all (frame,scale) masks of a sub-batch share one slice of these arrays
+    uint2 *d_ast = nullptr; Seg *d_seg = nullptr; uint32_t *d_minoff = nullptr; int4 *d_emit = nullptr; uint32_t *d_amap = nullptr;
+    unsigned anchors_cap = 0; int anchor_R = 8;
+    int *d_counters = nullptr;               // [sub-batch] n_anchors (unsigned), then per-(f,s) arrays
     int *d_surv_count = nullptr, *d_contour_count = nullptr, *d_iso_count = nullptr, *d_status = nullptr;
     uint4 *d_surv = nullptr, *d_sorted = nullptr;
     int *d_pts_off = nullptr; uint32_t *d_pts = nullptr; int pts_cap = 0;
@@ -251,8 +253,11 @@ static int create_impl(b2a_detector *d)
     const int WW = (W + 31) / 32, PWW = WW + 2;
     d->masks_words = (size_t)B * nS * PWW * (H + 2);
     TRY(dev_alloc(d, &d->d_masks, d->masks_words));
-    d->starts_cap = (unsigned)std::min<size_t>(std::max<size_t>((size_t)B * nS * (P / 8), 1u << 20), 0x7FFFFFFFu);
-    TRY(dev_alloc(d, &d->d_starts, d->starts_cap));
+    d->anchors_cap = (unsigned)std::min<size_t>(std::max<size_t>((size_t)B * nS * (P / 4), 1u << 20), 0x7FFFFFF0u);
+    TRY(dev_alloc(d, &d->d_ast, d->anchors_cap)); TRY(dev_alloc(d, &d->d_seg, d->anchors_cap));
+    TRY(dev_alloc(d, &d->d_minoff, d->anchors_cap)); TRY(dev_alloc(d, &d->d_emit, d->anchors_cap));
+    TRY(dev_alloc(d, &d->d_amap, (size_t)B * nS * P));
+    if (const char *e = std::getenv("B2A_ANCHOR_R")) { const int r = std::atoi(e); if (r >= 1 && r <= 32 && !(r & (r - 1))) d->anchor_R = r; }
     const size_t FS = (size_t)B * nS;
     TRY(dev_alloc(d, &d->d_counters, d->n_sub_max + 3 * FS + B));
     d->d_surv_count = d->d_counters + d->n_sub_max; d->d_contour_count = d->d_surv_count + FS; d->d_iso_count = d->d_contour_count + FS;
@@ -394,6 +399,17 @@ static void stage_mark(b2a_detector *d, const Sub &s, int st)
     d->ev_used[st] = true;
 }
 
+// B2A_SYNC_DEBUG=1: synchronize after every front-end kernel so that a device fault names its kernel
+static bool sync_debug() { static const bool on = std::getenv("B2A_SYNC_DEBUG") != nullptr; return on; }
+#define DBG_SYNC(st)                                                                                           \
+    do {                                                                                                       \
+        if (sync_debug()) {                                                                                    \
+            cudaError_t e__ = cudaStreamSynchronize(st);                                                       \
+            if (e__ != cudaSuccess) return set_err(B2A_ERR_CUDA, std::string("after launch ") + std::to_string(d->launches) + \
+                                                   " of the front end (line " + std::to_string(__LINE__) + "): " + cudaGetErrorString(e__)); \
+        }                                                                                                      \
+    } while (0)
+
 static int launch_err(const char *what)
 {
     cudaError_t e = cudaGetLastError();
@@ -413,7 +429,7 @@ static DetGeom make_geom(const b2a_detector *d, int W, int H, int B)
     g.minPerim = (int)(unsigned)(d->prm.minMarkerPerimeterRate * g.maxWH);
     g.maxPerim = (int)(unsigned)(d->prm.maxMarkerPerimeterRate * g.maxWH);
     g.approxRate = d->prm.polygonalApproxAccuracyRate; g.minCornerDistRate = d->prm.minCornerDistanceRate;
-    g.surv_cap = d->surv_cap; g.pts_cap = d->pts_cap; g.starts_cap = d->starts_cap;
+    g.surv_cap = d->surv_cap; g.pts_cap = d->pts_cap;
     return g;
 }
 
@@ -456,12 +472,15 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     } else { s.gray = src; s.pitch = src_pitch; s.frame_stride = src_frame; }
     s.g = make_geom(d, W, H, nb);
     DetGeom &g = s.g;
-    // this sub-batch's slice of the start list, and its arrays addressed from frame b0
-    const unsigned slice = d->starts_cap / (unsigned)d->n_sub_max;
-    g.starts_cap = slice;
-    uint2 *starts = d->d_starts + (size_t)s.sb * slice;
-    unsigned *n_starts = (unsigned *)d->d_counters + s.sb;
+    // this sub-batch's slice of the anchor arrays, and its per-(frame,scale) arrays addressed from frame b0
     const size_t fs0 = (size_t)b0 * g.nScales, FS = (size_t)nb * g.nScales;
+    const unsigned slice = d->anchors_cap / (unsigned)d->n_sub_max;
+    BorderGraph bg;
+    bg.ast = d->d_ast + (size_t)s.sb * slice; bg.seg = d->d_seg + (size_t)s.sb * slice; bg.minoff = d->d_minoff + (size_t)s.sb * slice;
+    bg.emit = d->d_emit + (size_t)s.sb * slice; bg.amap = d->d_amap + fs0 * (size_t)W * H;
+    bg.n_anchors = (unsigned *)d->d_counters + s.sb; bg.cap = slice;
+    const int Rm = d->anchor_R - 1, max_len = walk_max_len > 0 ? walk_max_len : g.maxPerim;
+    const unsigned walk_grid = (unsigned)d->num_sms * 8;
     uint32_t *masks = d->d_masks + fs0 * g.mask_plane;
     stage_mark(d, s, ST_THRESH);
     {
@@ -469,26 +488,30 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
         k_threshold<<<grid, TH_THREADS, 0, st>>>(s.gray, s.pitch, s.frame_stride, masks, g);
         d->launches++;
     }
-    stage_mark(d, s, ST_STARTS);
-    k_starts<<<d->num_sms * 4, 256, 0, st>>>(masks, starts, n_starts, d->d_iso_count + fs0, g);
-    d->launches++;
-    stage_mark(d, s, ST_WALK);
-    k_walk_count<<<d->num_sms * 4, 256, 0, st>>>(masks, starts, n_starts, d->d_surv + fs0 * g.surv_cap, d->d_surv_count + fs0,
-                                                 d->d_contour_count + fs0, walk_max_len > 0 ? walk_max_len : g.maxPerim, d->d_tables, g);
-    d->launches++;
+    stage_mark(d, s, ST_ANCHORS);
+    k_anchors<<<d->num_sms * 4, 256, 0, st>>>(masks, bg, d->d_iso_count + fs0, d->d_tables, Rm, g);
+    d->launches++; DBG_SYNC(st);
+    stage_mark(d, s, ST_SEGMENTS);
+    k_segments<<<walk_grid, 256, 0, st>>>(masks, bg, max_len, d->d_tables, Rm, g);
+    d->launches++; DBG_SYNC(st);
+    stage_mark(d, s, ST_CYCLES);
+    k_cycles<<<walk_grid, 256, 0, st>>>(bg, d->d_surv + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_contour_count + fs0, max_len, g);
+    d->launches++; DBG_SYNC(st);
     stage_mark(d, s, ST_SORT);
     k_sort_scan<<<(unsigned)FS, 1024, 0, st>>>(d->d_surv + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_sorted + fs0 * g.surv_cap,
-                                               d->d_pts_off + fs0 * g.surv_cap, d->d_status + b0, g);
-    d->launches++;
-    stage_mark(d, s, ST_WRITE);
-    k_walk_write<<<dim3(8, (unsigned)FS), 128, 0, st>>>(masks, d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,
-                                                        d->d_pts + fs0 * (size_t)g.pts_cap, d->d_tables, g);
-    d->launches++;
+                                               d->d_pts_off + fs0 * g.surv_cap, d->d_status + b0, bg.n_anchors, bg.cap, g);
+    d->launches++; DBG_SYNC(st);
+    stage_mark(d, s, ST_ASSIGN);
+    k_assign<<<dim3(8, (unsigned)FS), 128, 0, st>>>(bg, d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap, g);
+    d->launches++; DBG_SYNC(st);
+    stage_mark(d, s, ST_EMIT);
+    k_emit<<<walk_grid, 256, 0, st>>>(masks, bg, d->d_pts + fs0 * (size_t)g.pts_cap, d->d_tables, g);
+    d->launches++; DBG_SYNC(st);
     stage_mark(d, s, ST_APPROX);
     k_approx<<<dim3(8, (unsigned)FS), 256, 0, st>>>(d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,
                                                     d->d_pts + fs0 * (size_t)g.pts_cap, d->d_quad_ok + fs0 * g.surv_cap, d->d_quad_xy + fs0 * g.surv_cap * 8,
                                                     d->d_quad_len + fs0 * g.surv_cap, g);
-    d->launches++;
+    d->launches++; DBG_SYNC(st);
     return launch_err("front-end kernels");
 }
 

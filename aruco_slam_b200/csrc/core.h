@@ -59,6 +59,9 @@ B2A_HD int popc64(unsigned long long v)
 // A border state is (pixel, s_in) with s_in the direction towards the previous border pixel.
 // Suzuki-Abe border following is the permutation succ() on these states; every border is one
 // cycle, its first point is the state with the smallest "start key" on the cycle.
+// Start keys are strictly monotone in the raster position at which the sequential scan would
+// detect the border (outer borders at the pixel itself, hole borders at the 0-pixel to its
+// right), outer before hole (key_of below).
 // ---------------------------------------------------------------------------------------------
 B2A_HD int dir_dx(int d) { return (int)((0x901Au >> (2 * d)) & 3u) - 1; }
 B2A_HD int dir_dy(int d) { return (int)((0xA901u >> (2 * d)) & 3u) - 1; }
@@ -80,49 +83,9 @@ B2A_HD int first_cw(unsigned code, int from)
     if (!r) return -1;
     return (from + (31 - clz32(r))) & 7;
 }
-// s_in of the state that precedes (c, s_in): p = c + d[s_in], t = s_in ^ 4 is the direction p -> c
-B2A_HD int pred_dir(unsigned code_p, int t)
-{
-    int s = first_cw(code_p, t);
-    return s < 0 ? t : s;
-}
-// Start key of a state if it is start-eligible, else 0xFFFFFFFF.  Keys are strictly monotone in
-// the raster position at which the sequential scan would detect the border (outer borders at
-// the pixel itself, hole borders at the 0-pixel to its right), outer before hole.
-B2A_HD uint32_t start_key(int x, int y, int s, unsigned code, int W)
-{
-    if (!(code & 16u) && first_cw(code, 4) == s) return (uint32_t)((y * (W + 1) + x) * 2);
-    if (!(code & 1u) && first_cw(code, 0) == s) return (uint32_t)((y * (W + 1) + x + 1) * 2 + 1);
-    return 0xFFFFFFFFu;
-}
 // local necessary conditions for a pixel to carry the first state of a border
 B2A_HD bool outer_start_candidate(unsigned code) { return code != 0 && (code & 0x1Eu) == 0; }   // W,NW,N,NE clear
 B2A_HD bool hole_start_candidate(unsigned code) { return (code & 3u) == 2u; }                   // E clear, NE set
-
-// Word-parallel start-candidate test for the 32 pixels of mask word m.  ml / mr are the words to
-// its left / right, u* the row above, d* the row below (bit i of a word = pixel 32*w + i).
-//   outer start: pixel set, W / NW / N / NE clear, at least one other neighbour
-//   hole  start: pixel set, E clear, NE set
-//   iso        : set pixel without any neighbour (a one-point border, counted only)
-B2A_HD void start_candidate_words(uint32_t m, uint32_t ml, uint32_t mr, uint32_t u, uint32_t ul, uint32_t ur,
-                                  uint32_t d, uint32_t dl, uint32_t dr, uint32_t &outer, uint32_t &hole, uint32_t &iso)
-{
-    const uint32_t mW = (m << 1) | (ml >> 31), mE = (m >> 1) | (mr << 31);
-    const uint32_t uW = (u << 1) | (ul >> 31), uE = (u >> 1) | (ur << 31);
-    const uint32_t dW = (d << 1) | (dl >> 31), dE = (d >> 1) | (dr << 31);
-    outer = m & ~mW & ~uW & ~u & ~uE & (mE | dW | d | dE);
-    hole = m & ~mE & uE;
-    iso = m & ~(mW | mE | uW | u | uE | dW | d | dE);
-}
-// initial state and key of a start candidate of the given type (0 outer, 1 hole); false if the
-// state is also outer-eligible with a smaller key (then it cannot be a hole border's first state)
-B2A_HD bool start_state(unsigned code, int x, int y, int type, int KS, int &s0, uint32_t &key0)
-{
-    s0 = first_cw(code, type ? 0 : 4);
-    key0 = (uint32_t)((y * KS + x + type) * 2 + type);
-    if (type == 1 && start_key(x, y, s0, code, KS - 1) < key0) return false;
-    return true;
-}
 
 // Packed mask access: `plane` points at row -1; pixel (x,y) is bit (x & 31) of word
 // (y + 1) * PWW + (x >> 5) + 1.  One zero word left and >= 1 right of every row and zero rows
@@ -163,14 +126,29 @@ struct MaskView {
     }
 };
 
-// Border walking is driven by two 4 KB tables indexed by (3x3 window, direction) so that one step is
-// "six mask loads, one table load":
-//   succ[w9 | s_in << 9] = s_out | elig     the state's successor direction and its start eligibility
-//   pred[w9 | t    << 9] = s_p   | elig     w9 = window of the previous pixel p, t = direction p -> c;
-//                                           s_p = p's own incoming direction, elig = eligibility of (p, s_p)
-// elig: WT_OUTER = outer-type start-eligible (key (y,x,0)), WT_HOLE = hole-type only (key (y,x+1,1)).
-enum { WT_OUTER = 8, WT_HOLE = 16, WT_ELIG = 24 };
-struct WalkTables { uint8_t succ[4096]; uint8_t pred[4096]; };
+// ---------------------------------------------------------------------------------------------
+// Border graph.  The states that lie on borders are locally enumerable (checked against
+// cv2.findContours on every golden mask and on random masks: the state set below has exactly
+// one element per traced border point and its succ-cycles are exactly the borders longer than
+// one point):
+//     a set pixel c with code != 0 carries one state per maximal run of clear neighbours around
+//     its 8-ring that contains a 4-neighbour D in {E, N, W, S};  s_in = first_cw(code, D).
+// The run's clockwise-most 4-neighbour is the state's "canonical" D: D clear and (D-1 set or D-2 set).
+// A sparse, locally decidable subset of the states are ANCHORS:
+//     - the state hugs a clear W or E neighbour and y % R == 0, or a clear N or S neighbour and x % R == 0
+//     - or it satisfies the local necessary conditions of a border's first state (so every border
+//       carries at least one anchor whatever R is)
+// The stage then runs as   anchors -> segments (walk anchor to next anchor, all in parallel)
+//                                   -> cycles (hop over the anchors of a border: leader, length)
+//                                   -> order / offsets -> assign (position of each segment) -> emit points.
+// Tables, indexed by the 3x3 window w9 (and the incoming direction):
+//   succ[w9 | s_in << 9] : bits 0-2 successor direction, WT_OUTER / WT_HOLE start eligibility,
+//                          ST_ROW / ST_COL / ST_UNC anchor classes, ST_VALID
+//   pix[w9]              : byte k (canonical D = 2k): 0x80 present | ST_ROW/COL/UNC >> 2 | s_in
+// ---------------------------------------------------------------------------------------------
+enum { WT_OUTER = 8, WT_HOLE = 16, WT_ELIG = 24, ST_ROW = 32, ST_COL = 64, ST_UNC = 128, ST_VALID = 256 };
+enum : uint32_t { A_NONE = 0xFFFFFFFFu, SEG_OVERFLOW = 0x7FFFFFFFu };
+struct WalkTables { uint16_t succ[4096]; uint32_t pix[512]; };
 
 B2A_HD unsigned state_eligibility(unsigned code, int s)
 {
@@ -178,66 +156,161 @@ B2A_HD unsigned state_eligibility(unsigned code, int s)
     if (!(code & 1u) && first_cw(code, 0) == s) return WT_HOLE;
     return 0;
 }
+// flags of state (code, s); 0 if (code, s) is not a border state
+B2A_HD unsigned state_flags(unsigned code, int s)
+{
+    if (!code) return 0;
+    unsigned types = 0;
+    for (int D = 0; D < 8; D += 2)
+        if (!((code >> D) & 1u) && first_cw(code, D) == s) types |= 1u << (D >> 1);
+    if (!types) return 0;
+    unsigned f = ST_VALID | state_eligibility(code, s);
+    if (types & 5u) f |= ST_ROW;                 // E or W
+    if (types & 10u) f |= ST_COL;                // N or S
+    if (((f & WT_OUTER) && outer_start_candidate(code)) || ((f & WT_HOLE) && hole_start_candidate(code))) f |= ST_UNC;
+    return f;
+}
 B2A_HD void build_walk_table_entry(WalkTables &t, int idx)
 {
-    const unsigned w9 = (unsigned)idx & 511u, code = MaskView::code_of_win9(w9);
+    const unsigned w9 = (unsigned)idx & 511u;
+    const unsigned code = ((w9 >> 4) & 1u) ? MaskView::code_of_win9(w9) : 0u;
     const int s = idx >> 9;
-    t.succ[idx] = (uint8_t)((unsigned)succ_dir(code, s) | state_eligibility(code, s));
-    const int sp = pred_dir(code, s);                       // here s plays the role of t (direction p -> c)
-    t.pred[idx] = (uint8_t)((unsigned)sp | state_eligibility(code, sp));
+    const unsigned f = state_flags(code, s);
+    t.succ[idx] = (uint16_t)(f ? ((unsigned)succ_dir(code, s) | f) : 0u);
+    if (s == 0) {
+        uint32_t p = 0;
+        for (int k = 0; k < 4; ++k) {
+            const int D = 2 * k, d1 = (D + 7) & 7, d2 = (D + 6) & 7;
+            if (!code || ((code >> D) & 1u)) continue;
+            int sk;
+            if ((code >> d1) & 1u) sk = d1; else if ((code >> d2) & 1u) sk = d2; else continue;
+            const unsigned fk = state_flags(code, sk);
+            p |= (0x80u | ((fk & (ST_ROW | ST_COL | ST_UNC)) >> 2) | (unsigned)sk) << (8 * k);
+        }
+        t.pix[w9] = p;
+    }
 }
 B2A_HD uint32_t key_of(int x, int y, unsigned elig, int KS)
 {
     return (elig & WT_OUTER) ? (uint32_t)((y * KS + x) * 2) : (uint32_t)((y * KS + x + 1) * 2 + 1);
 }
-
-// Walk the border through state (x0,y0,s0) in both directions at once.  Returns the border
-// length if (x0,y0,s0) is the border's first state; 0 if another start-eligible state with a
-// smaller key lies on the border (then that one reports it); -1 once more than max_len steps
-// were taken without closing (the border is discarded by the perimeter gate anyway).
-template <class Win>
-B2A_HD int walk_count(const Win &win, const uint8_t *__restrict__ succ, const uint8_t *__restrict__ pred, int KS,
-                      int x0, int y0, int s0, uint32_t key0, int max_len)
+// Rm = R - 1 (R a power of two <= 32); flags carry ST_ROW / ST_COL / ST_UNC
+B2A_HD bool is_anchor(unsigned flags, int x, int y, int Rm)
 {
-    int xf = x0, yf = y0, sf = s0, xb = x0, yb = y0, sb = s0;
-    int so = succ[win.win9(x0, y0) | ((unsigned)s0 << 9)] & 7;
-    int n = 0;
+    return (flags & ST_UNC) || ((flags & ST_ROW) && !(y & Rm)) || ((flags & ST_COL) && !(x & Rm));
+}
+// rank of state (pixel, s) among the anchors of its pixel (ordered by canonical D); pixword = pix[w9]
+B2A_HD int anchor_rank(uint32_t pixword, int s, int x, int y, int Rm)
+{
+    int r = 0;
+    for (int k = 0; k < 4; ++k) {
+        const unsigned b = (pixword >> (8 * k)) & 0xFFu;
+        if (!(b & 0x80u)) continue;
+        if ((int)(b & 7u) == s) return r;
+        r += is_anchor((b << 2) & (ST_ROW | ST_COL | ST_UNC), x, y, Rm) ? 1 : 0;
+    }
+    return r;
+}
+// bits b-1, b, b+1 of the row whose words left / at / right of the pixel's word are ml, m, mr
+B2A_HD unsigned win3_words(uint32_t ml, uint32_t m, uint32_t mr, int b)
+{
+    const unsigned long long t = ((unsigned long long)m << 1) | (ml >> 31) | ((unsigned long long)(mr & 1u) << 33);
+    return (unsigned)(t >> b) & 7u;
+}
+// Pixels of mask word m (row y; ml / mr = the words left / right of it, u* the row above, d* the row below; bit i = pixel 32*w + i) that can carry an anchor:
+// border pixels (a clear 4-neighbour, at least one neighbour) on the R-grid or with the start conditions.
+B2A_HD uint32_t anchor_pixel_candidates(uint32_t m, uint32_t ml, uint32_t mr, uint32_t u, uint32_t ul, uint32_t ur,
+                                        uint32_t d, uint32_t dl, uint32_t dr, int y, int Rm, uint32_t &iso)
+{
+    const uint32_t mW = (m << 1) | (ml >> 31), mE = (m >> 1) | (mr << 31);
+    const uint32_t uW = (u << 1) | (ul >> 31), uE = (u >> 1) | (ur << 31);
+    const uint32_t dW = (d << 1) | (dl >> 31), dE = (d >> 1) | (dr << 31);
+    const uint32_t any = mW | mE | uW | u | uE | dW | d | dE;
+    iso = m & ~any;
+    uint32_t bp = m & ~(mW & mE & u & d) & any;
+    if (y & Rm) {
+        const uint32_t outer = m & ~mW & ~uW & ~u & ~uE, hole = m & ~mE & uE;
+        const uint32_t cols = 0xFFFFFFFFu / ((Rm >= 31) ? 0xFFFFFFFFu : ((2u << Rm) - 1u));     // bits with (b & Rm) == 0
+        bp &= outer | hole | cols;
+    }
+    return bp;
+}
+
+// Walk from anchor state (x,y,s) to the next anchor.  len = number of states of the segment
+// (SEG_OVERFLOW once more than max_len steps were taken), minkey / minoff = smallest start key
+// among the segment's start-eligible states and its offset (A_NONE if none); (x,y,s) and w9 are
+// left at the next anchor.
+template <class Win>
+B2A_HD void seg_walk(const Win &win, const uint16_t *__restrict__ succ, int KS, int Rm, int max_len,
+                     int &x, int &y, int &s, unsigned &w9, uint32_t &len, uint32_t &minkey, uint32_t &minoff)
+{
+    unsigned e = succ[win.win9(x, y) | ((unsigned)s << 9)];
+    uint32_t n = 0;
+    minkey = A_NONE; minoff = 0;
     for (;;) {
-        xf += dir_dx(so); yf += dir_dy(so); sf = so ^ 4;
+        if (e & WT_ELIG) { const uint32_t k = key_of(x, y, e, KS); if (k < minkey) { minkey = k; minoff = n; } }
+        const int so = (int)(e & 7u);
+        x += dir_dx(so); y += dir_dy(so); s = so ^ 4;
         ++n;
-        if (xf == xb && yf == yb && sf == sb) return n;
-        const int xp = xb + dir_dx(sb), yp = yb + dir_dy(sb);
-        const unsigned wf = win.win9(xf, yf), wp = win.win9(xp, yp);       // twelve independent loads in flight
-        const unsigned ef = succ[wf | ((unsigned)sf << 9)], ep = pred[wp | ((unsigned)(sb ^ 4) << 9)];
-        if ((ef & WT_ELIG) && key_of(xf, yf, ef, KS) < key0) return 0;
-        if (n > max_len) return -1;
-        sb = (int)(ep & 7u); xb = xp; yb = yp;
-        ++n;
-        if (xf == xb && yf == yb && sf == sb) return n;
-        if ((ep & WT_ELIG) && key_of(xb, yb, ep, KS) < key0) return 0;
-        if (n > max_len) return -1;
-        so = (int)(ef & 7u);
+        w9 = win.win9(x, y);
+        e = succ[w9 | ((unsigned)s << 9)];
+        if (is_anchor(e, x, y, Rm)) { len = n; return; }
+        if (n > (uint32_t)max_len) { len = SEG_OVERFLOW; return; }
     }
 }
-// Emit the n border points (x | y << 16) starting at state (x0,y0,s0), filling from both ends.
+// Emit the len points of the segment that starts at anchor state (x,y,s): point k goes to
+// out[pos + k] (+ n when negative: only the leader's segment wraps)
 template <class Win>
-B2A_HD void walk_write(const Win &win, const uint8_t *__restrict__ succ, const uint8_t *__restrict__ pred,
-                       int x0, int y0, int s0, int n, uint32_t *__restrict__ out)
+B2A_HD void seg_emit(const Win &win, const uint16_t *__restrict__ succ, int x, int y, int s, int len, int pos, int n, uint32_t *__restrict__ out)
 {
-    int xf = x0, yf = y0, sf = s0, xb = x0, yb = y0, sb = s0;
-    out[0] = (uint32_t)x0 | ((uint32_t)y0 << 16);
-    int lo = 1, hi = n - 1;
-    int so = succ[win.win9(x0, y0) | ((unsigned)s0 << 9)] & 7;
-    while (lo <= hi) {
-        xf += dir_dx(so); yf += dir_dy(so); sf = so ^ 4;
-        out[lo++] = (uint32_t)xf | ((uint32_t)yf << 16);
-        if (lo > hi) break;
-        const int xp = xb + dir_dx(sb), yp = yb + dir_dy(sb);
-        const unsigned wf = win.win9(xf, yf), wp = win.win9(xp, yp);
-        so = succ[wf | ((unsigned)sf << 9)] & 7;
-        sb = pred[wp | ((unsigned)(sb ^ 4) << 9)] & 7;
-        xb = xp; yb = yp;
-        out[hi--] = (uint32_t)xb | ((uint32_t)yb << 16);
+    for (int k = 0;; ) {
+        const int q = pos + k;
+        out[q < 0 ? q + n : q] = (uint32_t)x | ((uint32_t)y << 16);
+        if (++k >= len) break;
+        const int so = (int)(succ[win.win9(x, y) | ((unsigned)s << 9)] & 7u);
+        x += dir_dx(so); y += dir_dy(so); s = so ^ 4;
+    }
+}
+// seg[i] = (next anchor, previous anchor, segment length, segment min key).
+// Hop over the anchors of anchor i's border in both directions.  Returns the border length if
+// i's segment holds the border's smallest start key (i is the border's leader), 0 otherwise
+// (also when the border is longer than max_len or a segment overflowed).
+struct Seg { uint32_t next, prev, len, minkey; };
+template <class SegAt>
+B2A_HD uint32_t cycle_leader(const SegAt &seg_at, uint32_t i, int max_len)
+{
+    const Seg me = seg_at(i);
+    if (me.minkey == A_NONE || me.len == SEG_OVERFLOW) return 0;
+    uint32_t total = me.len, f = i, b = i, fn = me.next, bp = me.prev;
+    for (;;) {
+        if (fn == A_NONE || bp == A_NONE) return 0;
+        if (fn == b) break;
+        const Seg sf = seg_at(fn), sb = seg_at(bp);
+        if (sf.minkey < me.minkey || sf.len == SEG_OVERFLOW) return 0;
+        total += sf.len; f = fn; fn = sf.next;
+        if (total > (uint32_t)max_len) return 0;
+        if (bp == f) break;
+        if (sb.minkey < me.minkey || sb.len == SEG_OVERFLOW) return 0;
+        total += sb.len; b = bp; bp = sb.prev;
+        if (total > (uint32_t)max_len) return 0;
+    }
+    return total;
+}
+// Leader i of a kept border of n points whose first point sits minoff states into i's segment:
+// give every anchor of the border the position of its segment's first state (set(a, pos)).
+template <class SegAt, class Set>
+B2A_HD void cycle_assign(const SegAt &seg_at, const Set &set, uint32_t i, int n, int minoff)
+{
+    const Seg me = seg_at(i);
+    set(i, -minoff);
+    int pf = (int)me.len - minoff, pb = n - minoff;
+    uint32_t f = i, b = i, fn = me.next, bp = me.prev;
+    for (;;) {
+        if (fn == b) break;
+        const Seg sf = seg_at(fn), sb = seg_at(bp);
+        set(fn, pf); pf += (int)sf.len; f = fn; fn = sf.next;
+        if (bp == f) break;
+        pb -= (int)sb.len; set(bp, pb); b = bp; bp = sb.prev;
     }
 }
 

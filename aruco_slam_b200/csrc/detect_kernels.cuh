@@ -5,10 +5,11 @@
 //   k_bgr2gray        A1   bgr8 -> gray (15-bit fixed point)
 //   k_threshold       A2   gray -> nScales bit-packed adaptive-threshold masks, one pass, shared-memory
 //                          staged row-prefix tile, ballot-packed output
-//   k_starts          A3a  word-parallel search for border start candidates on the packed masks
-//   k_walk_count      A3a  bidirectional border walks: canonical start test + border length
+//   k_anchors         A3a  word-parallel enumeration of the border graph's anchor states
+//   k_segments        A3a  every anchor walks to the next anchor (short, independent walks)
+//   k_cycles          A3a  hop over each border's anchors: leader (first point), border length
 //   k_sort_scan       A3a  per (frame,scale): order kept borders like cv2.findContours, offsets
-//   k_walk_write      A3a  emit border points
+//   k_assign, k_emit  A3a  position of every segment inside its border; emit the border points
 //   k_approx          A3b  warp-cooperative approxPolyDP + quad gates
 //   k_group           A4-5 per frame: grouping / selection / hierarchy (frame_logic.h)
 //   k_identify        A7   per candidate: homography, NN warp, Otsu, bits, dictionary match
@@ -36,7 +37,6 @@ struct DetGeom {
     int minPerim, maxPerim, maxWH;
     double approxRate, minCornerDistRate;
     int surv_cap, pts_cap;
-    unsigned starts_cap;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -173,102 +173,158 @@ __global__ void k_unpack_masks(const uint32_t *__restrict__ masks, uint8_t *__re
 }
 
 // ---------------------------------------------------------------------------------------------
-// A3a step 1: start candidates, 32 pixels per thread with word-level logic.
-//   outer start: pixel set, W / NW / N / NE clear, at least one other neighbour
-//   hole  start: pixel set, E clear, NE set
-// entries: .x = (frame*nScales+scale) << 1 | type, .y = x | y << 16
+// A3a step 1: anchors of the border graph (core.h), one mask word (32 pixels) per thread.
+//   ast[i]  = (x | y << 16, (frame*nScales+scale) << 3 | s_in)
+//   amap[(fs*H + y)*W + x] = index of the pixel's first anchor (anchors of one pixel are consecutive)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_starts(const uint32_t *__restrict__ masks, uint2 *__restrict__ starts, unsigned *__restrict__ n_starts,
-                         int *__restrict__ iso_count, DetGeom g)
+struct BorderGraph {
+    uint2 *ast;          // anchor states
+    Seg *seg;            // (next, prev, len, minkey)
+    uint32_t *minoff;    // offset of the segment's min-key state
+    int4 *emit;          // (index of the border's first point in pts, position of the segment's first state, border length, -)
+    uint32_t *amap;      // per pixel of every (frame,scale): first anchor index
+    unsigned *n_anchors; // this sub-batch's counter
+    unsigned cap;
+};
+
+__device__ __forceinline__ void load_walk_tables(const WalkTables *__restrict__ g, uint16_t *s_succ, uint32_t *s_pix)
 {
+    const uint4 *src = reinterpret_cast<const uint4 *>(g);
+    if (s_succ) for (int i = threadIdx.x; i < 512; i += blockDim.x) reinterpret_cast<uint4 *>(s_succ)[i] = __ldg(src + i);
+    if (s_pix) for (int i = threadIdx.x; i < 128; i += blockDim.x) reinterpret_cast<uint4 *>(s_pix)[i] = __ldg(src + 512 + i);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+k_anchors(const uint32_t *__restrict__ masks, BorderGraph bg, int *__restrict__ iso_count, const WalkTables *__restrict__ tables, int Rm, DetGeom g)
+{
+    __shared__ __align__(16) uint32_t s_pix[512];
+    load_walk_tables(tables, nullptr, s_pix);
     const long long words_per_plane = (long long)g.H * g.WW;
     const long long total = (long long)g.B * g.nScales * words_per_plane;
     const int lane = threadIdx.x & 31;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    // all lanes of a warp run the same number of iterations (warp-aggregated append below)
     const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    for (long long i0 = first - lane; i0 < total; i0 += stride) {
+    for (long long i0 = first - lane; i0 < total; i0 += stride) {      // whole warps iterate together (warp-aggregated append)
         const long long i = i0 + lane;
-        unsigned outer = 0, hole = 0;
+        uint32_t bp = 0, m = 0, ml = 0, mr = 0, u = 0, ul = 0, ur = 0, d = 0, dl = 0, dr = 0;
         int fs = 0, y = 0, wx = 0;
         if (i < total) {
             fs = (int)(i / words_per_plane);
             const long long rem = i - (long long)fs * words_per_plane;
             y = (int)(rem / g.WW); wx = (int)(rem - (long long)y * g.WW);
             const uint32_t *row = masks + (size_t)fs * g.mask_plane + (size_t)(y + 1) * g.PWW + wx + 1;
-            const uint32_t m = __ldg(row);
+            m = __ldg(row);
             if (m) {
-                const uint32_t ml = __ldg(row - 1), mr = __ldg(row + 1);
-                const uint32_t u = __ldg(row - g.PWW), ul = __ldg(row - g.PWW - 1), ur = __ldg(row - g.PWW + 1);
-                const uint32_t d = __ldg(row + g.PWW), dl = __ldg(row + g.PWW - 1), dr = __ldg(row + g.PWW + 1);
+                ml = __ldg(row - 1); mr = __ldg(row + 1);
+                u = __ldg(row - g.PWW); ul = __ldg(row - g.PWW - 1); ur = __ldg(row - g.PWW + 1);
+                d = __ldg(row + g.PWW); dl = __ldg(row + g.PWW - 1); dr = __ldg(row + g.PWW + 1);
                 uint32_t iso;
-                start_candidate_words(m, ml, mr, u, ul, ur, d, dl, dr, outer, hole, iso);
+                bp = anchor_pixel_candidates(m, ml, mr, u, ul, ur, d, dl, dr, y, Rm, iso);
                 if (iso) atomicAdd(&iso_count[fs], __popc(iso));
             }
         }
-        const int cnt = __popc(outer) + __popc(hole);
+        // pass 1: count this word's anchors
+        int cnt = 0;
+        for (uint32_t bits = bp; bits; bits &= bits - 1) {
+            const int b = __ffs(bits) - 1, x = wx * 32 + b;
+            const unsigned w9 = win3_words(ul, u, ur, b) | (win3_words(ml, m, mr, b) << 3) | (win3_words(dl, d, dr, b) << 6);
+            const uint32_t p = s_pix[w9];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned e = (p >> (8 * k)) & 0xFFu;
+                cnt += ((e & 0x80u) && is_anchor((e << 2) & (ST_ROW | ST_COL | ST_UNC), x, y, Rm)) ? 1 : 0;
+            }
+        }
         int incl = cnt;
 #pragma unroll
         for (int dd = 1; dd < 32; dd <<= 1) { const int o = __shfl_up_sync(0xFFFFFFFFu, incl, dd); if (lane >= dd) incl += o; }
         const int tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
         if (tot == 0) continue;
         unsigned base = 0;
-        if (lane == 0) base = atomicAdd(n_starts, (unsigned)tot);
+        if (lane == 0) base = atomicAdd(bg.n_anchors, (unsigned)tot);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         unsigned pos = base + (unsigned)(incl - cnt);
-        while (outer) {
-            const int bpos = __ffs(outer) - 1; outer &= outer - 1;
-            if (pos < g.starts_cap) starts[pos] = make_uint2((unsigned)fs << 1, (unsigned)(wx * 32 + bpos) | ((unsigned)y << 16));
-            ++pos;
-        }
-        while (hole) {
-            const int bpos = __ffs(hole) - 1; hole &= hole - 1;
-            if (pos < g.starts_cap) starts[pos] = make_uint2(((unsigned)fs << 1) | 1u, (unsigned)(wx * 32 + bpos) | ((unsigned)y << 16));
-            ++pos;
+        // pass 2: write them
+        for (uint32_t bits = bp; bits; bits &= bits - 1) {
+            const int b = __ffs(bits) - 1, x = wx * 32 + b;
+            const unsigned w9 = win3_words(ul, u, ur, b) | (win3_words(ml, m, mr, b) << 3) | (win3_words(dl, d, dr, b) << 6);
+            const uint32_t p = s_pix[w9];
+            bool first_of_pixel = true;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned e = (p >> (8 * k)) & 0xFFu;
+                if (!((e & 0x80u) && is_anchor((e << 2) & (ST_ROW | ST_COL | ST_UNC), x, y, Rm))) continue;
+                if (pos < bg.cap) {
+                    bg.ast[pos] = make_uint2((unsigned)x | ((unsigned)y << 16), ((unsigned)fs << 3) | (e & 7u));
+                    bg.seg[pos] = Seg{A_NONE, A_NONE, 0u, A_NONE};
+                    bg.emit[pos] = make_int4(0, 0, 0, 0);
+                    if (first_of_pixel) bg.amap[((size_t)fs * g.H + y) * g.W + x] = pos;
+                }
+                first_of_pixel = false;
+                ++pos;
+            }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// A3a step 2: one thread per start candidate walks its border both ways.
-//   surv[(fs)*surv_cap + slot] = (key, length, x | y<<16, 0)
+// A3a step 2: one thread per anchor walks its segment to the next anchor and links the two.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_walk_tables(const WalkTables *__restrict__ g, uint8_t *s_succ, uint8_t *s_pred)
+__global__ void __launch_bounds__(256)
+k_segments(const uint32_t *__restrict__ masks, BorderGraph bg, int max_len, const WalkTables *__restrict__ tables, int Rm, DetGeom g)
 {
-    const uint4 *src = reinterpret_cast<const uint4 *>(g);
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        reinterpret_cast<uint4 *>(s_succ)[i] = __ldg(src + i);
-        reinterpret_cast<uint4 *>(s_pred)[i] = __ldg(src + 256 + i);
+    __shared__ __align__(16) uint16_t s_succ[4096];
+    __shared__ __align__(16) uint32_t s_pix[512];
+    unsigned n = *bg.n_anchors;
+    if (n > bg.cap) n = bg.cap;
+    if (blockIdx.x * blockDim.x >= n) return;
+    load_walk_tables(tables, s_succ, s_pix);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint2 a = bg.ast[i];
+        const int fs = (int)(a.y >> 3);
+        int x = (int)(a.x & 0xFFFFu), y = (int)(a.x >> 16), s = (int)(a.y & 7u);
+        MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
+        unsigned w9; uint32_t len, minkey, moff;
+        seg_walk(rd, s_succ, g.KS, Rm, max_len, x, y, s, w9, len, minkey, moff);
+        uint32_t j = A_NONE;
+        if (len != SEG_OVERFLOW) {
+            j = bg.amap[((size_t)fs * g.H + y) * g.W + x] + (uint32_t)anchor_rank(s_pix[w9], s, x, y, Rm);
+            if (j >= n) j = A_NONE;                                   // only after an anchor-list overflow (status 3)
+        }
+        bg.seg[i].next = j; bg.seg[i].len = len; bg.seg[i].minkey = minkey;
+        bg.minoff[i] = moff;
+        if (j != A_NONE) bg.seg[j].prev = i;
     }
-    __syncthreads();
 }
+
+// ---------------------------------------------------------------------------------------------
+// A3a step 3: one thread per anchor hops over its border's anchors; the leader (smallest start key)
+// reports the border.   surv[fs*surv_cap + slot] = (key, length, leader anchor, offset of the first point)
+// ---------------------------------------------------------------------------------------------
+struct SegLoad {
+    const Seg *seg;
+    __device__ __forceinline__ Seg operator()(uint32_t i) const
+    {
+        const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(seg) + i);
+        return Seg{v.x, v.y, v.z, v.w};
+    }
+};
 
 __global__ void __launch_bounds__(256)
-k_walk_count(const uint32_t *__restrict__ masks, const uint2 *__restrict__ starts, const unsigned *__restrict__ n_starts,
-             uint4 *__restrict__ surv, int *__restrict__ surv_count, int *__restrict__ contour_count, int max_len,
-             const WalkTables *__restrict__ tables, DetGeom g)
+k_cycles(BorderGraph bg, uint4 *__restrict__ surv, int *__restrict__ surv_count, int *__restrict__ contour_count, int max_len, DetGeom g)
 {
-    __shared__ __align__(16) uint8_t s_succ[4096];
-    __shared__ __align__(16) uint8_t s_pred[4096];
-    unsigned n = *n_starts;
-    if (n > g.starts_cap) n = g.starts_cap;
-    if (blockIdx.x * blockDim.x >= n) return;
-    load_walk_tables(tables, s_succ, s_pred);
+    unsigned n = *bg.n_anchors;
+    if (n > bg.cap) n = bg.cap;
+    const SegLoad seg_at{bg.seg};
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint2 e = starts[i];
-        const int fs = (int)(e.x >> 1), type = (int)(e.x & 1u);
-        const int x = (int)(e.y & 0xFFFFu), y = (int)(e.y >> 16);
-        MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
-        const unsigned c0 = rd(x, y);
-        int s0; uint32_t key0;
-        if (!start_state(c0, x, y, type, g.KS, s0, key0)) continue;
-        const int len = walk_count(rd, s_succ, s_pred, g.KS, x, y, s0, key0, max_len);
-        if (len > 0) {
-            atomicAdd(&contour_count[fs], 1);
-            if (len >= g.minPerim && len <= g.maxPerim) {
-                const int slot = atomicAdd(&surv_count[fs], 1);
-                if (slot < g.surv_cap) surv[(size_t)fs * g.surv_cap + slot] = make_uint4(key0, (unsigned)len, e.y, (unsigned)s0);
-            }
+        const uint32_t len = cycle_leader(seg_at, i, max_len);
+        if (!len) continue;
+        const int fs = (int)(bg.ast[i].y >> 3);
+        atomicAdd(&contour_count[fs], 1);
+        if ((int)len >= g.minPerim && (int)len <= g.maxPerim) {
+            const int slot = atomicAdd(&surv_count[fs], 1);
+            if (slot < g.surv_cap) surv[(size_t)fs * g.surv_cap + slot] = make_uint4(bg.seg[i].minkey, len, i, bg.minoff[i]);
         }
     }
 }
@@ -279,7 +335,7 @@ k_walk_count(const uint32_t *__restrict__ masks, const uint2 *__restrict__ start
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 k_sort_scan(const uint4 *__restrict__ surv, int *__restrict__ surv_count, uint4 *__restrict__ sorted,
-            int *__restrict__ pts_off, int *__restrict__ status, DetGeom g)
+            int *__restrict__ pts_off, int *__restrict__ status, const unsigned *__restrict__ n_anchors, unsigned anchors_cap, DetGeom g)
 {
     __shared__ uint32_t s_key[SORT_CAP];
     __shared__ uint16_t s_idx[SORT_CAP];
@@ -287,10 +343,13 @@ k_sort_scan(const uint4 *__restrict__ surv, int *__restrict__ surv_count, uint4 
     const int fs = blockIdx.x;
     int n = surv_count[fs];
     if (n > g.surv_cap) { n = g.surv_cap; if (threadIdx.x == 0) status[fs / g.nScales] = 3; }
+    if (threadIdx.x == 0 && *n_anchors > anchors_cap) status[fs / g.nScales] = 3;       // anchor list overflowed: borders are missing
     int N = 32; while (N < n) N <<= 1;
     const uint4 *in = surv + (size_t)fs * g.surv_cap;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        s_key[i] = (i < n) ? ~in[i].x : 0xFFFFFFFFu;      // ascending sort of ~key == descending key; pads last
+        // ascending sort of (0xFFFFFFFE - key) == descending key; pads (0xFFFFFFFF) strictly last even
+        // for key 0 (an outer border that starts at pixel (0,0)); keys are <= 2 * 32767 * 32768 + 1
+        s_key[i] = (i < n) ? 0xFFFFFFFEu - in[i].x : 0xFFFFFFFFu;
         s_idx[i] = (uint16_t)i;
     }
     __syncthreads();
@@ -332,23 +391,42 @@ k_sort_scan(const uint4 *__restrict__ surv, int *__restrict__ surv_count, uint4 
     if (threadIdx.x == 0) surv_count[fs] = n;
 }
 
-// A3a step 4: emit the border points of the kept borders
+struct EmitSet {
+    int4 *emit; int base, len;
+    __device__ __forceinline__ void operator()(uint32_t a, int pos) const { emit[a] = make_int4(base, pos, len, 0); }
+};
+
+// A3a step 5: the leader of every kept border tells the border's anchors where their segments go
 __global__ void __launch_bounds__(128)
-k_walk_write(const uint32_t *__restrict__ masks, const uint4 *__restrict__ sorted, const int *__restrict__ surv_count,
-             const int *__restrict__ pts_off, uint32_t *__restrict__ pts, const WalkTables *__restrict__ tables, DetGeom g)
+k_assign(BorderGraph bg, const uint4 *__restrict__ sorted, const int *__restrict__ surv_count, const int *__restrict__ pts_off, DetGeom g)
 {
-    __shared__ __align__(16) uint8_t s_succ[4096];
-    __shared__ __align__(16) uint8_t s_pred[4096];
     const int fs = blockIdx.y;
     const int n = surv_count[fs];
-    if ((int)(blockIdx.x * blockDim.x) >= n) return;
-    load_walk_tables(tables, s_succ, s_pred);
-    MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
+    const SegLoad seg_at{bg.seg};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int off = pts_off[(size_t)fs * g.surv_cap + i];
         if (off < 0) continue;
         const uint4 e = sorted[(size_t)fs * g.surv_cap + i];
-        walk_write(rd, s_succ, s_pred, (int)(e.z & 0xFFFFu), (int)(e.z >> 16), (int)e.w, (int)e.y, pts + (size_t)fs * g.pts_cap + off);
+        const int base = fs * g.pts_cap + off, len = (int)e.y;
+        cycle_assign(seg_at, EmitSet{bg.emit, base, len}, e.z, len, (int)e.w);
+    }
+}
+
+// A3a step 6: every anchor of a kept border re-walks its segment and writes the points
+__global__ void __launch_bounds__(256)
+k_emit(const uint32_t *__restrict__ masks, BorderGraph bg, uint32_t *__restrict__ pts, const WalkTables *__restrict__ tables, DetGeom g)
+{
+    __shared__ __align__(16) uint16_t s_succ[4096];
+    unsigned n = *bg.n_anchors;
+    if (n > bg.cap) n = bg.cap;
+    if (blockIdx.x * blockDim.x >= n) return;
+    load_walk_tables(tables, s_succ, nullptr);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 e = bg.emit[i];
+        if (e.z == 0) continue;
+        const uint2 a = bg.ast[i];
+        MaskView rd{masks + (size_t)(a.y >> 3) * g.mask_plane, g.PWW};
+        seg_emit(rd, s_succ, (int)(a.x & 0xFFFFu), (int)(a.x >> 16), (int)(a.y & 7u), (int)bg.seg[i].len, e.y, e.z, pts + e.x);
     }
 }
 

@@ -64,7 +64,7 @@ def params_for(dic, max_cand=2048, max_markers=256, surv_cap=4096):
     return p
 
 
-def detect(gray, dic, masks=None, dbg_scale=-1):
+def detect(gray, dic, masks=None, dbg_scale=-1, anchor_R=8):
     gray = np.ascontiguousarray(gray, np.uint8)
     H, W = gray.shape
     p = params_for(dic)
@@ -84,7 +84,7 @@ def detect(gray, dic, masks=None, dbg_scale=-1):
         mp = mk.ctypes.data_as(C.c_void_p)
     P = lambda a: a.ctypes.data_as(C.c_void_p)
     st = lib().emu_detect(P(gray), W, H, mp, P(d), C.byref(p), C.byref(n_acc), C.byref(n_rej), P(corners), P(ids), P(rej),
-                          P(ncont), C.byref(n_cand), P(cand), dbg_scale, C.byref(nk), P(dlen), cap, P(dpts), pcap)
+                          P(ncont), C.byref(n_cand), P(cand), dbg_scale, C.byref(nk), P(dlen), cap, P(dpts), pcap, anchor_R)
     out = dict(status=st, corners=corners[:n_acc.value].copy(), ids=ids[:n_acc.value].copy(), rejected=rej[:n_rej.value].copy(),
                n_contours=ncont, cand=cand[:n_cand.value].copy())
     if dbg_scale >= 0:

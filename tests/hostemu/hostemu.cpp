@@ -22,6 +22,16 @@ struct HostCtx {
     int exclusive_scan(int flag, int &total) const { total = flag ? 1 : 0; return 0; }
 };
 
+// MaskView with a bounds check (a walk must never leave the padded plane)
+struct CheckedView {
+    const uint32_t *plane; int PWW, W, H; mutable bool bad = false;
+    unsigned win9(int x, int y) const
+    {
+        if (x < 0 || x >= W || y < 0 || y >= H) { bad = true; return 0; }
+        return MaskView{plane, PWW}.win9(x, y);
+    }
+};
+
 struct EmuParams {
     int nScales; int radius[8]; int Cfloor;
     double minPerimRate, maxPerimRate, approxRate, minCornerDistRate;
@@ -56,7 +66,7 @@ extern "C" {
 int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const unsigned long long *dict, const EmuParams *ep,
                int *n_acc, int *n_rej, float *corners, int32_t *ids, float *rejected,
                int *n_contours, int *n_cand, float *cand,
-               int dbg_scale, int *dbg_nkept, int *dbg_len, int dbg_cap, int16_t *dbg_pts, int dbg_pts_cap)
+               int dbg_scale, int *dbg_nkept, int *dbg_len, int dbg_cap, int16_t *dbg_pts, int dbg_pts_cap, int anchor_R)
 {
     const int nS = ep->nScales, WW = (W + 31) / 32, PWW = WW + 2, KS = W + 1;
     const size_t plane_words = (size_t)PWW * (H + 2);
@@ -79,33 +89,70 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
     for (int s = 0; s < nS; ++s) {
         const uint32_t *pl = masks.data() + plane_words * s;
         MaskView mv{pl, PWW};
-        struct Surv { uint32_t key; int len, x, y, s0; };
+        struct Surv { uint32_t key; int len; uint32_t leader; int minoff; };
         std::vector<Surv> surv;
         int ncont = 0;
+        // --- anchors (k_anchors, one word at a time) ---
+        const bool device_like = anchor_R < 0;
+        const int Rm = (device_like ? -anchor_R : anchor_R) - 1;
+        std::vector<uint32_t> ax, ay, as_;
+        std::vector<Seg> seg;
+        std::vector<uint32_t> amap((size_t)W * H, A_NONE), minoff;
         for (int y = 0; y < H; ++y)
             for (int wx = 0; wx < WW; ++wx) {
                 const uint32_t *row = pl + (size_t)(y + 1) * PWW + wx + 1;
                 const uint32_t m = row[0];
                 if (!m) continue;
-                uint32_t outer, hole, iso;
-                start_candidate_words(m, row[-1], row[1], row[-PWW], row[-PWW - 1], row[-PWW + 1], row[PWW], row[PWW - 1], row[PWW + 1], outer, hole, iso);
+                uint32_t iso;
+                uint32_t bp = anchor_pixel_candidates(m, row[-1], row[1], row[-PWW], row[-PWW - 1], row[-PWW + 1], row[PWW], row[PWW - 1], row[PWW + 1], y, Rm, iso);
                 ncont += __builtin_popcount(iso);
-                for (int type = 0; type < 2; ++type) {
-                    uint32_t bits = type ? hole : outer;
-                    while (bits) {
-                        const int b = __builtin_ffs(bits) - 1; bits &= bits - 1;
-                        const int x = wx * 32 + b;
-                        const unsigned c0 = mv(x, y);
-                        int s0; uint32_t key0;
-                        if (!start_state(c0, x, y, type, KS, s0, key0)) continue;
-                        const int len = walk_count(mv, wt.succ, wt.pred, KS, x, y, s0, key0, 2 * W * H + 16);
-                        if (len > 0) {
-                            ++ncont;
-                            if (len >= minPerim && len <= maxPerim) surv.push_back({key0, len, x, y, s0});
-                        }
+                for (; bp; bp &= bp - 1) {
+                    const int b = __builtin_ffs(bp) - 1, x = wx * 32 + b;
+                    const unsigned w9 = win3_words(row[-PWW - 1], row[-PWW], row[-PWW + 1], b) | (win3_words(row[-1], m, row[1], b) << 3) |
+                                        (win3_words(row[PWW - 1], row[PWW], row[PWW + 1], b) << 6);
+                    if (w9 != mv.win9(x, y)) return -100;
+                    const uint32_t p = wt.pix[w9];
+                    bool first = true;
+                    for (int k = 0; k < 4; ++k) {
+                        const unsigned e = (p >> (8 * k)) & 0xFFu;
+                        if (!((e & 0x80u) && is_anchor((e << 2) & (ST_ROW | ST_COL | ST_UNC), x, y, Rm))) continue;
+                        if (first) amap[(size_t)y * W + x] = (uint32_t)ax.size();
+                        first = false;
+                        ax.push_back(x); ay.push_back(y); as_.push_back(e & 7u);
                     }
                 }
             }
+        const uint32_t nA = (uint32_t)ax.size();
+        seg.assign(nA, Seg{A_NONE, A_NONE, 0u, A_NONE});
+        minoff.assign(nA, 0);
+        // anchor_R < 0: behave like the product call (walks give up after maxPerimeter steps; overflowed
+        // segments and their borders are dropped) instead of the exact-count debug mode
+        const int max_len = device_like ? maxPerim : 2 * W * H + 16;
+        // --- segments (k_segments) ---
+        for (uint32_t i = 0; i < nA; ++i) {
+            int x = (int)ax[i], y = (int)ay[i], st = (int)as_[i];
+            unsigned w9; uint32_t len, mk, mo;
+            CheckedView cv{pl, PWW, W, H};
+            seg_walk(cv, wt.succ, KS, Rm, max_len, x, y, st, w9, len, mk, mo);
+            if (cv.bad) return -106;
+            seg[i].len = len; seg[i].minkey = mk; minoff[i] = mo;
+            if (len == SEG_OVERFLOW) { if (device_like) continue; return -101; }
+            const uint32_t base = amap[(size_t)y * W + x];
+            if (base == A_NONE) return -102;
+            const uint32_t j = base + (uint32_t)anchor_rank(wt.pix[w9], st, x, y, Rm);
+            if (j >= nA || (int)ax[j] != x || (int)ay[j] != y || (int)as_[j] != st) return -103;
+            seg[i].next = j; seg[i].len = len; seg[i].minkey = mk; minoff[i] = mo;
+            if (seg[j].prev != A_NONE) return -104;
+            seg[j].prev = i;
+        }
+        // --- cycles (k_cycles) ---
+        auto seg_at = [&](uint32_t i) { return seg[i]; };
+        for (uint32_t i = 0; i < nA; ++i) {
+            const uint32_t len = cycle_leader(seg_at, i, max_len);
+            if (!len) continue;
+            ++ncont;
+            if ((int)len >= minPerim && (int)len <= maxPerim) surv.push_back({seg[i].minkey, (int)len, i, (int)minoff[i]});
+        }
         if (n_contours) n_contours[s] = ncont;
         std::sort(surv.begin(), surv.end(), [](const Surv &a, const Surv &b) { return a.key > b.key; });
         if ((int)surv.size() > surv_cap) { surv.resize(surv_cap); status = 3; }
@@ -114,8 +161,13 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
         if (s == dbg_scale && dbg_nkept) *dbg_nkept = (int)surv.size();
         for (size_t i = 0; i < surv.size(); ++i) {
             const Surv &e = surv[i];
-            std::vector<uint32_t> pts(e.len);
-            walk_write(mv, wt.succ, wt.pred, e.x, e.y, e.s0, e.len, pts.data());
+            // --- assign + emit (k_assign, k_emit) ---
+            std::vector<uint32_t> pts(e.len, 0xFFFFFFFFu);
+            std::vector<std::pair<uint32_t, int>> placed;
+            cycle_assign(seg_at, [&](uint32_t a, int pos) { placed.push_back({a, pos}); }, e.leader, e.len, e.minoff);
+            for (auto &pr : placed)
+                seg_emit(mv, wt.succ, (int)ax[pr.first], (int)ay[pr.first], (int)as_[pr.first], (int)seg[pr.first].len, pr.second, e.len, pts.data());
+            for (int k = 0; k < e.len; ++k) if (pts[k] == 0xFFFFFFFFu) return -105;
             if (s == dbg_scale) {
                 if (dbg_len && (int)i < dbg_cap) dbg_len[i] = e.len;
                 if (dbg_pts) for (int k = 0; k < e.len && w < dbg_pts_cap; ++k, ++w) { dbg_pts[2 * w] = (int16_t)px_of(pts[k]); dbg_pts[2 * w + 1] = (int16_t)py_of(pts[k]); }

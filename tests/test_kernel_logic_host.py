@@ -45,12 +45,16 @@ def test_contour_points_match_golden(name):
         assert np.array_equal(r["kept_pts"], want)
 
 
+@pytest.mark.parametrize("R", [1, 4, 8, 32])
 @pytest.mark.parametrize("p", [0.2, 0.5, 0.8])
-def test_contours_random_masks_vs_oracle(oracle, p):
+def test_contours_random_masks_vs_oracle(oracle, p, R):
+    """border graph (anchors every R rows / columns -> segments -> cycles -> emit) vs the oracle's
+    findContours restatement on random masks: contour count, kept lengths, every point"""
     rng = np.random.default_rng(int(p * 10))
     m = ((rng.random((97, 131)) < p) * 255).astype(np.uint8)
     dic = D.getPredefinedDictionary(0)
-    r = emu.detect(m, dic, masks=np.stack([m, m, m]), dbg_scale=0)
+    r = emu.detect(m, dic, masks=np.stack([m, m, m]), dbg_scale=0, anchor_R=R)
+    assert r["status"] >= 0             # negative = the emulation's own consistency checks; 3 = candidate capacity (irrelevant here)
     cs = oracle.find_contours(m)
     mn, mx = int(0.03 * 131), 4 * 131
     kept = [c for c in cs if mn <= len(c) <= mx]
