@@ -167,7 +167,7 @@ struct b2a_detector {
     uint8_t *d_in = nullptr, *d_gray = nullptr;
     uint32_t *d_masks = nullptr; size_t masks_words = 0;
     // border graph (core.h): anchors of all (frame,scale) masks of a sub-batch share one slice of these arrays
-    uint2 *d_ast = nullptr; Seg *d_seg = nullptr; uint32_t *d_minoff = nullptr; int4 *d_emit = nullptr; uint32_t *d_amap = nullptr;
+    uint2 *d_ast = nullptr; Seg *d_seg = nullptr, *d_sseg = nullptr; uint32_t *d_minoff = nullptr, *d_ssoff = nullptr; int4 *d_emit = nullptr; uint32_t *d_amap = nullptr;
     unsigned anchors_cap = 0; int anchor_R = 8;
     int *d_counters = nullptr;               // [sub-batch] n_anchors (unsigned), then per-(f,s) arrays
     int *d_surv_count = nullptr, *d_contour_count = nullptr, *d_iso_count = nullptr, *d_status = nullptr;
@@ -256,6 +256,7 @@ static int create_impl(b2a_detector *d)
     d->anchors_cap = (unsigned)std::min<size_t>(std::max<size_t>((size_t)B * nS * (P / 4), 1u << 20), 0x7FFFFFF0u);
     TRY(dev_alloc(d, &d->d_ast, d->anchors_cap)); TRY(dev_alloc(d, &d->d_seg, d->anchors_cap));
     TRY(dev_alloc(d, &d->d_minoff, d->anchors_cap)); TRY(dev_alloc(d, &d->d_emit, d->anchors_cap));
+    TRY(dev_alloc(d, &d->d_sseg, d->anchors_cap)); TRY(dev_alloc(d, &d->d_ssoff, d->anchors_cap));
     TRY(dev_alloc(d, &d->d_amap, (size_t)B * nS * P));
     if (const char *e = std::getenv("B2A_ANCHOR_R")) { const int r = std::atoi(e); if (r >= 1 && r <= 32 && !(r & (r - 1))) d->anchor_R = r; }
     const size_t FS = (size_t)B * nS;
@@ -477,6 +478,7 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     const unsigned slice = d->anchors_cap / (unsigned)d->n_sub_max;
     BorderGraph bg;
     bg.ast = d->d_ast + (size_t)s.sb * slice; bg.seg = d->d_seg + (size_t)s.sb * slice; bg.minoff = d->d_minoff + (size_t)s.sb * slice;
+    bg.sseg = d->d_sseg + (size_t)s.sb * slice; bg.ssoff = d->d_ssoff + (size_t)s.sb * slice;
     bg.emit = d->d_emit + (size_t)s.sb * slice; bg.amap = d->d_amap + fs0 * (size_t)W * H;
     bg.n_anchors = (unsigned *)d->d_counters + s.sb; bg.cap = slice;
     const int Rm = d->anchor_R - 1, max_len = walk_max_len > 0 ? walk_max_len : g.maxPerim;
@@ -495,6 +497,8 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     k_segments<<<walk_grid, 256, 0, st>>>(masks, bg, max_len, d->d_tables, Rm, g);
     d->launches++; DBG_SYNC(st);
     stage_mark(d, s, ST_CYCLES);
+    k_skip<<<walk_grid, 256, 0, st>>>(bg, max_len);
+    d->launches++; DBG_SYNC(st);
     k_cycles<<<walk_grid, 256, 0, st>>>(bg, d->d_surv + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_contour_count + fs0, max_len, g);
     d->launches++; DBG_SYNC(st);
     stage_mark(d, s, ST_SORT);
@@ -503,6 +507,8 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     d->launches++; DBG_SYNC(st);
     stage_mark(d, s, ST_ASSIGN);
     k_assign<<<dim3(8, (unsigned)FS), 128, 0, st>>>(bg, d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap, g);
+    d->launches++; DBG_SYNC(st);
+    k_assign_sub<<<walk_grid, 256, 0, st>>>(bg);
     d->launches++; DBG_SYNC(st);
     stage_mark(d, s, ST_EMIT);
     k_emit<<<walk_grid, 256, 0, st>>>(masks, bg, d->d_pts + fs0 * (size_t)g.pts_cap, d->d_tables, g);

@@ -274,10 +274,12 @@ B2A_HD void seg_emit(const Win &win, const uint16_t *__restrict__ succ, int x, i
 // seg[i] = (next anchor, previous anchor, segment length, segment min key).
 // Hop over the anchors of anchor i's border in both directions.  Returns the border length if
 // i's segment holds the border's smallest start key (i is the border's leader), 0 otherwise
-// (also when the border is longer than max_len or a segment overflowed).
+// (also when the border is longer than max_len, a segment overflowed, or stop(anchor) is true
+// for an anchor of the border other than i).
 struct Seg { uint32_t next, prev, len, minkey; };
-template <class SegAt>
-B2A_HD uint32_t cycle_leader(const SegAt &seg_at, uint32_t i, int max_len)
+struct NeverStop { B2A_HD bool operator()(uint32_t) const { return false; } };
+template <class SegAt, class Stop>
+B2A_HD uint32_t cycle_leader(const SegAt &seg_at, const Stop &stop, uint32_t i, int max_len)
 {
     const Seg me = seg_at(i);
     if (me.minkey == A_NONE || me.len == SEG_OVERFLOW) return 0;
@@ -285,6 +287,7 @@ B2A_HD uint32_t cycle_leader(const SegAt &seg_at, uint32_t i, int max_len)
     for (;;) {
         if (fn == A_NONE || bp == A_NONE) return 0;
         if (fn == b) break;
+        if (stop(fn) || stop(bp)) return 0;
         const Seg sf = seg_at(fn), sb = seg_at(bp);
         if (sf.minkey < me.minkey || sf.len == SEG_OVERFLOW) return 0;
         total += sf.len; f = fn; fn = sf.next;
@@ -311,6 +314,42 @@ B2A_HD void cycle_assign(const SegAt &seg_at, const Set &set, uint32_t i, int n,
         set(fn, pf); pf += (int)sf.len; f = fn; fn = sf.next;
         if (bp == f) break;
         pb -= (int)sb.len; set(bp, pb); b = bp; bp = sb.prev;
+    }
+}
+// Second level: a pseudo-random 1/16 of the anchors are "super" anchors.  A super anchor's
+// segment runs to the next super anchor of its border (super_skip hops over the plain anchors in
+// between), so the leader / assign hops over a long border touch 16x fewer nodes; borders
+// without a super anchor are resolved on the plain anchors.
+B2A_HD bool is_super(uint32_t i) { return (((i ^ (i >> 9)) * 0x9E3779B1u) >> 28) == 0u; }
+struct IsSuper { B2A_HD bool operator()(uint32_t i) const { return is_super(i); } };
+// out: next super anchor (A_NONE on overflow), super segment length, min key, offset of the min-key state
+template <class SegAt, class MinoffAt>
+B2A_HD void super_skip(const SegAt &seg_at, const MinoffAt &minoff_at, uint32_t S, int max_len,
+                       uint32_t &snext, uint32_t &slen, uint32_t &smin, uint32_t &soff)
+{
+    uint32_t cur = S;
+    slen = 0; smin = A_NONE; soff = 0;
+    for (;;) {
+        const Seg sg = seg_at(cur);
+        if (sg.len == SEG_OVERFLOW || sg.next == A_NONE) { snext = A_NONE; slen = SEG_OVERFLOW; return; }
+        if (sg.minkey < smin) { smin = sg.minkey; soff = slen + minoff_at(cur); }
+        slen += sg.len;
+        if (slen > (uint32_t)max_len) { snext = A_NONE; slen = SEG_OVERFLOW; return; }
+        cur = sg.next;
+        if (is_super(cur)) { snext = cur; return; }
+    }
+}
+// positions of the plain anchors behind super anchor S (whose own position is pos)
+template <class SegAt, class Set>
+B2A_HD void super_assign(const SegAt &seg_at, const Set &set, uint32_t S, int pos)
+{
+    Seg sg = seg_at(S);
+    for (;;) {
+        pos += (int)sg.len;
+        const uint32_t cur = sg.next;
+        if (is_super(cur)) return;
+        set(cur, pos);
+        sg = seg_at(cur);
     }
 }
 

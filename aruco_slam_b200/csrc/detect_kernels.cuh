@@ -181,6 +181,8 @@ struct BorderGraph {
     uint2 *ast;          // anchor states
     Seg *seg;            // (next, prev, len, minkey)
     uint32_t *minoff;    // offset of the segment's min-key state
+    Seg *sseg;           // super anchors only: (next super, previous super, length up to it, min key)
+    uint32_t *ssoff;     // super anchors only: offset of the min-key state from the super anchor
     int4 *emit;          // (index of the border's first point in pts, position of the segment's first state, border length, -)
     uint32_t *amap;      // per pixel of every (frame,scale): first anchor index
     unsigned *n_anchors; // this sub-batch's counter
@@ -258,6 +260,7 @@ k_anchors(const uint32_t *__restrict__ masks, BorderGraph bg, int *__restrict__ 
                 if (pos < bg.cap) {
                     bg.ast[pos] = make_uint2((unsigned)x | ((unsigned)y << 16), ((unsigned)fs << 3) | (e & 7u));
                     bg.seg[pos] = Seg{A_NONE, A_NONE, 0u, A_NONE};
+                    if (is_super(pos)) bg.sseg[pos] = Seg{A_NONE, A_NONE, 0u, A_NONE};
                     bg.emit[pos] = make_int4(0, 0, 0, 0);
                     if (first_of_pixel) bg.amap[((size_t)fs * g.H + y) * g.W + x] = pos;
                 }
@@ -311,20 +314,45 @@ struct SegLoad {
     }
 };
 
+struct MinoffLoad {
+    const uint32_t *m;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return __ldcg(m + i); }
+};
+
+// super anchors skip to the next super anchor of their border
+__global__ void __launch_bounds__(256)
+k_skip(BorderGraph bg, int max_len)
+{
+    unsigned n = *bg.n_anchors;
+    if (n > bg.cap) n = bg.cap;
+    const SegLoad seg_at{bg.seg};
+    const MinoffLoad minoff_at{bg.minoff};
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (!is_super(i)) continue;
+        uint32_t snext, slen, smin, soff;
+        super_skip(seg_at, minoff_at, i, max_len, snext, slen, smin, soff);
+        bg.sseg[i].next = snext; bg.sseg[i].len = slen; bg.sseg[i].minkey = smin;
+        bg.ssoff[i] = soff;
+        if (snext != A_NONE) bg.sseg[snext].prev = i;
+    }
+}
+
+// surv[fs*surv_cap + slot] = (key, length, leader anchor, 1 if the leader is a super anchor)
 __global__ void __launch_bounds__(256)
 k_cycles(BorderGraph bg, uint4 *__restrict__ surv, int *__restrict__ surv_count, int *__restrict__ contour_count, int max_len, DetGeom g)
 {
     unsigned n = *bg.n_anchors;
     if (n > bg.cap) n = bg.cap;
-    const SegLoad seg_at{bg.seg};
+    const SegLoad seg_at{bg.seg}, sseg_at{bg.sseg};
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t len = cycle_leader(seg_at, i, max_len);
+        const bool sup = is_super(i);
+        const uint32_t len = sup ? cycle_leader(sseg_at, NeverStop{}, i, max_len) : cycle_leader(seg_at, IsSuper{}, i, max_len);
         if (!len) continue;
         const int fs = (int)(bg.ast[i].y >> 3);
         atomicAdd(&contour_count[fs], 1);
         if ((int)len >= g.minPerim && (int)len <= g.maxPerim) {
             const int slot = atomicAdd(&surv_count[fs], 1);
-            if (slot < g.surv_cap) surv[(size_t)fs * g.surv_cap + slot] = make_uint4(bg.seg[i].minkey, len, i, bg.minoff[i]);
+            if (slot < g.surv_cap) surv[(size_t)fs * g.surv_cap + slot] = make_uint4(sup ? bg.sseg[i].minkey : bg.seg[i].minkey, len, i, sup ? 1u : 0u);
         }
     }
 }
@@ -408,7 +436,23 @@ k_assign(BorderGraph bg, const uint4 *__restrict__ sorted, const int *__restrict
         if (off < 0) continue;
         const uint4 e = sorted[(size_t)fs * g.surv_cap + i];
         const int base = fs * g.pts_cap + off, len = (int)e.y;
-        cycle_assign(seg_at, EmitSet{bg.emit, base, len}, e.z, len, (int)e.w);
+        if (e.w) cycle_assign(SegLoad{bg.sseg}, EmitSet{bg.emit, base, len}, e.z, len, (int)bg.ssoff[e.z]);
+        else cycle_assign(seg_at, EmitSet{bg.emit, base, len}, e.z, len, (int)bg.minoff[e.z]);
+    }
+}
+
+// ... and every super anchor of a kept border passes the positions on to the plain anchors behind it
+__global__ void __launch_bounds__(256)
+k_assign_sub(BorderGraph bg)
+{
+    unsigned n = *bg.n_anchors;
+    if (n > bg.cap) n = bg.cap;
+    const SegLoad seg_at{bg.seg};
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (!is_super(i)) continue;
+        const int4 e = bg.emit[i];
+        if (e.z == 0) continue;
+        super_assign(seg_at, EmitSet{bg.emit, e.x, e.z}, i, e.y);
     }
 }
 

@@ -89,7 +89,7 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
     for (int s = 0; s < nS; ++s) {
         const uint32_t *pl = masks.data() + plane_words * s;
         MaskView mv{pl, PWW};
-        struct Surv { uint32_t key; int len; uint32_t leader; int minoff; };
+        struct Surv { uint32_t key; int len; uint32_t leader; int super; };
         std::vector<Surv> surv;
         int ncont = 0;
         // --- anchors (k_anchors, one word at a time) ---
@@ -145,13 +145,26 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
             if (seg[j].prev != A_NONE) return -104;
             seg[j].prev = i;
         }
-        // --- cycles (k_cycles) ---
+        // --- super anchors (k_skip) ---
         auto seg_at = [&](uint32_t i) { return seg[i]; };
+        auto minoff_at = [&](uint32_t i) { return minoff[i]; };
+        std::vector<Seg> sseg(nA, Seg{A_NONE, A_NONE, 0u, A_NONE});
+        std::vector<uint32_t> ssoff(nA, 0);
         for (uint32_t i = 0; i < nA; ++i) {
-            const uint32_t len = cycle_leader(seg_at, i, max_len);
+            if (!is_super(i)) continue;
+            uint32_t snext, slen, smin, soff;
+            super_skip(seg_at, minoff_at, i, max_len, snext, slen, smin, soff);
+            sseg[i].next = snext; sseg[i].len = slen; sseg[i].minkey = smin; ssoff[i] = soff;
+            if (snext != A_NONE) { if (sseg[snext].prev != A_NONE) return -107; sseg[snext].prev = i; }
+        }
+        auto sseg_at = [&](uint32_t i) { return sseg[i]; };
+        // --- cycles (k_cycles) ---
+        for (uint32_t i = 0; i < nA; ++i) {
+            const bool sup = is_super(i);
+            const uint32_t len = sup ? cycle_leader(sseg_at, NeverStop{}, i, max_len) : cycle_leader(seg_at, IsSuper{}, i, max_len);
             if (!len) continue;
             ++ncont;
-            if ((int)len >= minPerim && (int)len <= maxPerim) surv.push_back({seg[i].minkey, (int)len, i, (int)minoff[i]});
+            if ((int)len >= minPerim && (int)len <= maxPerim) surv.push_back({sup ? sseg[i].minkey : seg[i].minkey, (int)len, i, sup ? 1 : 0});
         }
         if (n_contours) n_contours[s] = ncont;
         std::sort(surv.begin(), surv.end(), [](const Surv &a, const Surv &b) { return a.key > b.key; });
@@ -164,7 +177,12 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
             // --- assign + emit (k_assign, k_emit) ---
             std::vector<uint32_t> pts(e.len, 0xFFFFFFFFu);
             std::vector<std::pair<uint32_t, int>> placed;
-            cycle_assign(seg_at, [&](uint32_t a, int pos) { placed.push_back({a, pos}); }, e.leader, e.len, e.minoff);
+            auto place = [&](uint32_t a, int pos) { placed.push_back({a, pos}); };
+            if (e.super) {
+                cycle_assign(sseg_at, place, e.leader, e.len, (int)ssoff[e.leader]);
+                const size_t nsup = placed.size();
+                for (size_t k = 0; k < nsup; ++k) super_assign(seg_at, place, placed[k].first, placed[k].second);
+            } else cycle_assign(seg_at, place, e.leader, e.len, (int)minoff[e.leader]);
             for (auto &pr : placed)
                 seg_emit(mv, wt.succ, (int)ax[pr.first], (int)ay[pr.first], (int)as_[pr.first], (int)seg[pr.first].len, pr.second, e.len, pts.data());
             for (int k = 0; k < e.len; ++k) if (pts[k] == 0xFFFFFFFFu) return -105;
