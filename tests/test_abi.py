@@ -51,3 +51,53 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.lower(), f
+
+
+def _build_demo(so_path, tmp_path):
+    import subprocess
+    exe = str(tmp_path / "b2a_demo")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "b2a_demo.cpp"),
+                           "-L" + os.path.dirname(so_path), "-lb2aruco", "-Wl,-rpath," + os.path.dirname(so_path), "-o", exe])
+    return exe
+
+
+def test_cpp_shim_compiles_and_fails_loudly_without_gpu(so_path, tmp_path):
+    """include/b2aruco.hpp (the cv::aruco-shaped C++ surface) builds against the C ABI with plain g++;
+    without a GPU the demo exits 1 with the library's error instead of falling back to anything."""
+    import subprocess
+    import torch
+    exe = _build_demo(so_path, tmp_path)
+    pgm = tmp_path / "f.pgm"
+    with open(pgm, "wb") as f:
+        f.write(b"P5\n64 48\n255\n" + bytes(64 * 48))
+    r = subprocess.run([exe, str(pgm), "0"], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "0 markers" in r.stdout
+    else:
+        assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_shim_matches_python_surface(so_path, tmp_path):
+    """the C++ shim's detectMarkers / estimatePoseSingleMarkers print the same ids, corners and poses
+    as the Python mirror on a rendered frame"""
+    import subprocess
+    import numpy as np
+    from aruco_slam_b200 import aruco, synth, dictionaries as D
+    exe = _build_demo(so_path, tmp_path)
+    fr = synth.render_config("C1", 1).image
+    H, W = fr.shape
+    pgm = tmp_path / "c1.pgm"
+    with open(pgm, "wb") as f:
+        f.write(b"P5\n%d %d\n255\n" % (W, H) + fr.tobytes())
+    out = subprocess.run([exe, str(pgm), "0", "0.27"], capture_output=True, text=True, check=True).stdout.splitlines()
+    det = aruco.ArucoDetector(D.getPredefinedDictionary(0), max_shape=fr.shape)
+    K = np.array([[1400.0, 0, W / 2.0], [0, 1400.0, H / 2.0], [0, 0, 1]])
+    r = det.detect_pose_batch(fr, 0.27, K, np.zeros(0))
+    assert out[0].startswith("%d markers, %d rejected" % (len(r.ids[0]), len(r.rejected[0])))
+    for line, mid, c, rv, tv in zip(out[1:], r.ids[0], r.corners[0], r.rvecs[0], r.tvecs[0]):
+        nums = [float(x) for x in re.findall(r"-?\d+\.\d+", line)]
+        assert line.startswith("id %d " % mid)
+        assert np.allclose(nums[:8], c.reshape(-1), atol=0.051)
+        assert np.allclose(nums[8:11], rv.reshape(-1), atol=2e-5) and np.allclose(nums[11:14], tv.reshape(-1), atol=2e-5)
+    det.close()
