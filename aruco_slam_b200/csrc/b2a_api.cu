@@ -113,15 +113,24 @@ extern "C" int b2a_get_predefined_dictionary(int dict_id, b2a_dictionary *out)
 // ------------------------------------------------------------------------------------------------
 // pose / observation kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void k_pose(const float *__restrict__ corners, const int32_t *__restrict__ n_acc, int B, int max_markers,
-                       Camera cam, float marker_length, double *__restrict__ rvecs, double *__restrict__ tvecs)
+// 8 lanes per marker (one per row of the reprojection system), 16 markers per CTA
+constexpr int POSE_THREADS = 128;
+struct Lanes8 {
+    __device__ __forceinline__ int lane() const { return threadIdx.x & 7; }
+    __device__ __forceinline__ int nlanes() const { return 8; }
+    __device__ __forceinline__ void sync() const { __syncwarp(0xFFu << (threadIdx.x & 24)); }
+};
+__global__ void __launch_bounds__(POSE_THREADS)
+k_pose(const float *__restrict__ corners, const int32_t *__restrict__ n_acc, int B, int max_markers,
+       Camera cam, float marker_length, double *__restrict__ rvecs, double *__restrict__ tvecs)
 {
+    __shared__ double s_sh[POSE_THREADS / 8][POSE_SH];
     const int total = B * max_markers;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-        const int f = t / max_markers, m = t - f * max_markers;
-        if (n_acc && m >= n_acc[f]) continue;
-        solve_marker_pose(cam, marker_length, corners + (size_t)t * 8, rvecs + (size_t)t * 3, tvecs + (size_t)t * 3);
-    }
+    const int t = (int)((blockIdx.x * (unsigned)POSE_THREADS + threadIdx.x) >> 3);      // marker slot of this lane group
+    if (t >= total) return;
+    const int f = t / max_markers, m = t - f * max_markers;
+    if (n_acc && m >= n_acc[f]) return;
+    solve_marker_pose(Lanes8{}, cam, marker_length, corners + (size_t)t * 8, s_sh[threadIdx.x >> 3], rvecs + (size_t)t * 3, tvecs + (size_t)t * 3);
 }
 
 __global__ void k_observations(const float *__restrict__ corners, const int32_t *__restrict__ ids, const double *__restrict__ rvecs,
@@ -556,7 +565,7 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
     ip.nMarkers = d->dict.nMarkers; ip.maxCorr = (int)((double)d->dict.maxCorrectionBits * d->prm.errorCorrectionRate);
     ip.maxBorderErr = (int)(d->dict.markerSize * d->dict.markerSize * d->prm.maxErroneousBitsInBorderRate);
     ip.minOtsuStdDev = d->prm.minOtsuStdDev; ip.W = g.W; ip.H = g.H; ip.pitch = s.pitch; ip.frame_stride = s.frame_stride; ip.max_cand = d->max_cand;
-    k_identify<<<dim3(128, nb), ID_THREADS, 0, st>>>(s.gray, d->d_dict, fa, ip);
+    k_identify<<<dim3(32, nb), ID_THREADS, 0, st>>>(s.gray, d->d_dict, fa, ip);
     d->launches++;
     stage_mark(d, s, ST_FINAL);
     k_finalize<<<nb, 128, 8 * sizeof(int32_t) * d->max_cand, st>>>(fa, fp);
@@ -574,7 +583,7 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
     }
     stage_mark(d, s, ST_POSE);
     if (cam) {
-        k_pose<<<(nb * (int)K + 31) / 32, 32, 0, st>>>(corners, fa.fo0.n_accepted, nb, d->max_markers, to_camera(cam), cam->marker_length,
+        k_pose<<<(nb * (int)K * 8 + POSE_THREADS - 1) / POSE_THREADS, POSE_THREADS, 0, st>>>(corners, fa.fo0.n_accepted, nb, d->max_markers, to_camera(cam), cam->marker_length,
                                                         d->d_rvecs + (size_t)b0 * K * 3, d->d_tvecs + (size_t)b0 * K * 3);
         d->launches++;
     }
@@ -682,7 +691,7 @@ extern "C" int b2a_estimate_pose_single_markers(b2a_detector *d, const float *co
     CU(cudaMalloc(&dt, (size_t)n * 3 * sizeof(double)));
     cudaStream_t st = d->stream;
     cudaMemcpyAsync(dc, corners, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice, st);
-    k_pose<<<(n + 31) / 32, 32, 0, st>>>(dc, nullptr, 1, n, to_camera(cam), cam->marker_length, dr, dt);
+    k_pose<<<(n * 8 + POSE_THREADS - 1) / POSE_THREADS, POSE_THREADS, 0, st>>>(dc, nullptr, 1, n, to_camera(cam), cam->marker_length, dr, dt);
     cudaMemcpyAsync(rvecs, dr, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(tvecs, dt, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);

@@ -706,33 +706,54 @@ B2A_HD unsigned warp_sample(const uint8_t *__restrict__ gray, int W, int H, size
     const long long X = (long long)rint(fx), Y = (long long)rint(fy);
     return (X >= 0 && X < W && Y >= 0 && Y < H) ? gray[(size_t)Y * pitch + (size_t)X] : 0u;
 }
-// OpenCV's Otsu between-class-variance scan over a 256-bin histogram of n samples
-B2A_HD int otsu_threshold(const int *h, int n)
+// OpenCV's Otsu between-class-variance scan over a 256-bin histogram of n samples, cut in two so
+// that only the loop-carried recurrence on (q1, mu1) is sequential:
+//   otsu_chain  : one lane; per bin q1s[i] = q1 after the bin (or -1 where OpenCV `continue`s), mu1s[i]
+//   otsu_sigma  : any lane; the between-class variance of bin i from (mu, q1s[i], mu1s[i])
+// The threshold is the first bin (strict '>') with the largest sigma.
+B2A_HD double otsu_chain(const int *h, int n, double *q1s, double *mu1s)
 {
-    double mu = 0, scale = d_div(1.0, (double)n);
+    double mu = 0;
+    const double scale = d_div(1.0, (double)n);
     for (int i = 0; i < 256; ++i) mu = d_add(mu, d_mul((double)i, (double)h[i]));
     mu = d_mul(mu, scale);
-    double mu1 = 0, q1 = 0, max_sigma = 0;
-    int max_val = 0;
+    double mu1 = 0, q1 = 0;
     for (int i = 0; i < 256; ++i) {
-        double p_i = d_mul((double)h[i], scale);
+        const double p_i = d_mul((double)h[i], scale);
         mu1 = d_mul(mu1, q1);
         q1 = d_add(q1, p_i);
-        double q2 = d_sub(1.0, q1);
-        double mn = q1 < q2 ? q1 : q2, mx = q1 > q2 ? q1 : q2;
-        if (mn < (double)FLT_EPSILON || mx > 1.0 - (double)FLT_EPSILON) continue;
+        const double q2 = d_sub(1.0, q1);
+        const double mn = q1 < q2 ? q1 : q2, mx = q1 > q2 ? q1 : q2;
+        if (mn < (double)FLT_EPSILON || mx > 1.0 - (double)FLT_EPSILON) { q1s[i] = -1.0; continue; }
         mu1 = d_div(d_add(mu1, d_mul((double)i, p_i)), q1);
-        double mu2 = d_div(d_sub(mu, d_mul(q1, mu1)), q2);
-        double dm = d_sub(mu1, mu2);
-        double sigma = d_mul(d_mul(d_mul(q1, q2), dm), dm);
+        q1s[i] = q1; mu1s[i] = mu1;
+    }
+    return mu;
+}
+B2A_HD double otsu_sigma(double mu, double q1, double mu1)
+{
+    if (q1 < 0) return 0.0;                      // never beats max_sigma's initial 0 under strict '>'
+    const double q2 = d_sub(1.0, q1);
+    const double mu2 = d_div(d_sub(mu, d_mul(q1, mu1)), q2);
+    const double dm = d_sub(mu1, mu2);
+    return d_mul(d_mul(d_mul(q1, q2), dm), dm);
+}
+B2A_HD int otsu_threshold(const int *h, int n)
+{
+    double q1s[256], mu1s[256];
+    const double mu = otsu_chain(h, n, q1s, mu1s);
+    double max_sigma = 0;
+    int max_val = 0;
+    for (int i = 0; i < 256; ++i) {
+        const double sigma = otsu_sigma(mu, q1s[i], q1s[i] < 0 ? 0.0 : mu1s[i]);
         if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
     }
     return max_val;
 }
 
 // ---- A7 glue shared by k_identify and the host emulation ----
-// mode: 0 / 1 = every bit is 0 / 1 (flat patch), 2 = Otsu threshold thr
-B2A_HD void ident_decide(long long sum, long long sq, int S, int m0, double minOtsuStdDev, const int *hist, int &mode, int &thr)
+// mode: 0 / 1 = every bit is 0 / 1 (flat patch), 2 = Otsu threshold needed
+B2A_HD int ident_mode(long long sum, long long sq, int S, int m0, double minOtsuStdDev)
 {
     const int cnt = (S - 2 * m0) * (S - 2 * m0);
     const double scale = d_div(1.0, (double)cnt);
@@ -740,9 +761,13 @@ B2A_HD void ident_decide(long long sum, long long sq, int S, int m0, double minO
     double var = d_sub(d_mul((double)sq, scale), d_mul(mean, mean));
     if (var < 0) var = 0;
     const double sd = sqrt(var);
-    thr = 0;
-    if (sd < minOtsuStdDev) mode = (mean > 127.0) ? 1 : 0;
-    else { mode = 2; thr = otsu_threshold(hist, S * S); }
+    if (sd < minOtsuStdDev) return (mean > 127.0) ? 1 : 0;
+    return 2;
+}
+B2A_HD void ident_decide(long long sum, long long sq, int S, int m0, double minOtsuStdDev, const int *hist, int &mode, int &thr)
+{
+    mode = ident_mode(sum, sq, S, m0, minOtsuStdDev);
+    thr = (mode == 2) ? otsu_threshold(hist, S * S) : 0;
 }
 B2A_HD int ident_cell_bit(const uint8_t *patch, int S, int cellSize, int cellMargin, int cy, int cx, int thr)
 {

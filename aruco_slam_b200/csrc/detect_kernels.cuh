@@ -623,80 +623,102 @@ struct IdentParams {
     int max_cand;
 };
 
-constexpr int ID_THREADS = 128;
+constexpr int ID_WARPS = 4;         // work items in flight per CTA (one warp each)
+constexpr int ID_THREADS = ID_WARPS * 32;
 constexpr int ID_MAX_S = 9 * 8;     // (7 + 2) cells * up to 8 px
 
+// One WARP per work item: the sequential pieces of A7 (cv2's 8x8 LU, the Otsu recurrence, the border
+// check) run on lane 0 while the other warps of the SM work on other candidates; sampling, the
+// between-class variances, the cell votes and the dictionary scan are spread over the 32 lanes.
 __global__ void __launch_bounds__(ID_THREADS)
 k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restrict__ dict, FrameArrays fa, IdentParams ip)
 {
-    __shared__ double s_M[9];
-    __shared__ uint8_t s_patch[ID_MAX_S * ID_MAX_S];
-    __shared__ int s_hist[256];
-    __shared__ int s_sum, s_sq, s_thr, s_mode, s_best;
-    __shared__ unsigned long long s_code;
-    __shared__ uint8_t s_bits[81];
+    __shared__ double s_M[ID_WARPS][9];
+    __shared__ double s_q1[ID_WARPS][256], s_mu1[ID_WARPS][256];
+    __shared__ __align__(16) uint8_t s_patch[ID_WARPS][ID_MAX_S * ID_MAX_S];
+    __shared__ int s_hist[ID_WARPS][256];
+    __shared__ uint8_t s_bits[ID_WARPS][96];
 
     const int f = blockIdx.y;
     const int *counters = fa.fs0.counters + (size_t)f * 8;
     const int nw = counters[FC_NWORK];
     const int nb = ip.markerSize + 2 * ip.borderBits;
     const int S = nb * ip.cellSize;
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const uint8_t *img = gray + (size_t)f * ip.frame_stride;
-    for (int w = blockIdx.x; w < nw; w += gridDim.x) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    for (int w = blockIdx.x * ID_WARPS + wp; w < nw; w += gridDim.x * ID_WARPS) {
         const float *corners = fa.fs0.wq + ((size_t)f * ip.max_cand + w) * 8;
-        if (tid == 0) { perspective_inverse(corners, S, s_M); s_sum = 0; s_sq = 0; s_best = 0x7FFFFFFF; }
-        for (int i = tid; i < 256; i += ID_THREADS) s_hist[i] = 0;
-        __syncthreads();
+        if (lane == 0) perspective_inverse(corners, S, s_M[wp]);
+        for (int i = lane; i < 256; i += 32) s_hist[wp][i] = 0;
+        __syncwarp();
         double M[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) M[i] = s_M[i];
+        for (int i = 0; i < 9; ++i) M[i] = s_M[wp][i];
         const int m0 = ip.cellSize / 2;
         int ls = 0, lq = 0;
-        for (int p = tid; p < S * S; p += ID_THREADS) {
+        for (int p = lane; p < S * S; p += 32) {
             const int y = p / S, x = p - y * S;
             const unsigned v = warp_sample(img, ip.W, ip.H, ip.pitch, M, x, y);
-            s_patch[p] = (uint8_t)v;
-            atomicAdd(&s_hist[v], 1);
+            s_patch[wp][p] = (uint8_t)v;
+            atomicAdd(&s_hist[wp][v], 1);
             if (x >= m0 && x < S - m0 && y >= m0 && y < S - m0) { ls += (int)v; lq += (int)(v * v); }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { ls += __shfl_xor_sync(0xFFFFFFFFu, ls, o); lq += __shfl_xor_sync(0xFFFFFFFFu, lq, o); }
-        if ((tid & 31) == 0) { atomicAdd(&s_sum, ls); atomicAdd(&s_sq, lq); }
-        __syncthreads();
-        if (tid == 0) { int mode, thr; ident_decide(s_sum, s_sq, S, m0, ip.minOtsuStdDev, s_hist, mode, thr); s_mode = mode; s_thr = thr; }
-        __syncthreads();
-        for (int cidx = tid; cidx < nb * nb; cidx += ID_THREADS) {
-            const int cy = cidx / nb, cx = cidx - cy * nb;
-            s_bits[cidx] = (uint8_t)((s_mode < 2) ? s_mode : ident_cell_bit(s_patch, S, ip.cellSize, ip.cellMargin, cy, cx, s_thr));
-        }
-        __syncthreads();
-        if (tid == 0) {
-            unsigned long long code;
-            const bool ok = ident_border_code(s_bits, ip.markerSize, ip.borderBits, ip.maxBorderErr, code);
-            s_code = code;
-            s_mode = ok ? 0 : -1;
-        }
-        __syncthreads();
-        if (s_mode == 0) {
-            const unsigned long long code = s_code;
-            for (int m = tid; m < ip.nMarkers; m += ID_THREADS) {
-                int rot;
-                if (ident_marker_distance(dict + (size_t)m * 4, code, ip.markerSize, rot) <= ip.maxCorr) { atomicMin(&s_best, m); break; }   // later m of this thread are larger
+        for (int o = 16; o > 0; o >>= 1) { ls += __shfl_xor_sync(FULL, ls, o); lq += __shfl_xor_sync(FULL, lq, o); }
+        __syncwarp();
+        const int mode = ident_mode(ls, lq, S, m0, ip.minOtsuStdDev);          // same value on every lane
+        int thr = 0;
+        if (mode == 2) {
+            double mu = 0;
+            if (lane == 0) mu = otsu_chain(s_hist[wp], S * S, s_q1[wp], s_mu1[wp]);
+            __syncwarp();
+            mu = __shfl_sync(FULL, mu, 0);
+            double best = 0; int bi = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {                                        // lane owns 8 consecutive bins: order kept
+                const int i = lane * 8 + k;
+                const double q1 = s_q1[wp][i];
+                const double sg = otsu_sigma(mu, q1, q1 < 0 ? 0.0 : s_mu1[wp][i]);
+                if (sg > best) { best = sg; bi = i; }
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(FULL, best, o);
+                const int oi = __shfl_xor_sync(FULL, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            thr = best > 0 ? bi : 0;
         }
-        __syncthreads();
-        if (tid == 0) {
-            int res = 0;
-            if (s_mode == 0 && s_best != 0x7FFFFFFF) {
-                const int m = s_best;
+        for (int cidx = lane; cidx < nb * nb; cidx += 32) {
+            const int cy = cidx / nb, cx = cidx - cy * nb;
+            s_bits[wp][cidx] = (uint8_t)((mode < 2) ? mode : ident_cell_bit(s_patch[wp], S, ip.cellSize, ip.cellMargin, cy, cx, thr));
+        }
+        __syncwarp();
+        unsigned long long code = 0;
+        int ok = 0;
+        if (lane == 0) ok = ident_border_code(s_bits[wp], ip.markerSize, ip.borderBits, ip.maxBorderErr, code) ? 1 : 0;
+        ok = __shfl_sync(FULL, ok, 0);
+        code = __shfl_sync(FULL, code, 0);
+        int best_m = 0x7FFFFFFF;
+        if (ok) {
+            for (int m = lane; m < ip.nMarkers; m += 32) {
                 int rot;
-                ident_marker_distance(dict + (size_t)m * 4, s_code, ip.markerSize, rot);
-                res = (int)(0x80000000u | ((unsigned)m << 8) | (unsigned)rot);
+                if (ident_marker_distance(dict + (size_t)m * 4, code, ip.markerSize, rot) <= ip.maxCorr) { best_m = m; break; }   // later m of this lane are larger
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best_m = min(best_m, __shfl_xor_sync(FULL, best_m, o));
+        }
+        if (lane == 0) {
+            int res = 0;
+            if (ok && best_m != 0x7FFFFFFF) {
+                int rot;
+                ident_marker_distance(dict + (size_t)best_m * 4, code, ip.markerSize, rot);
+                res = (int)(0x80000000u | ((unsigned)best_m << 8) | (unsigned)rot);
             }
             fa.fs0.wres[(size_t)f * ip.max_cand + w] = res;
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 

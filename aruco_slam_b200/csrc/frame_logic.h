@@ -131,34 +131,65 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
         M[t] = bits;
     }
     ctx.sync();
-    // ---- 4. sequential group assignment in (i, j) order (A5), one lane ----
-    if (tid == 0) {
-        int ng = 0;
-        for (int i = 0; i < n; ++i) {
-            for (int w = i >> 5; w < wpr; ++w) {
-                uint32_t bits = M[i * wpr + w];
-                while (bits) {
-                    const int b = ffs32(bits) - 1;
-                    bits &= bits - 1;
-                    const int j = w * 32 + b;
-                    fs.sel[i] = 0; fs.sel[j] = 0;
-                    const int gi = fs.gid[i], gj = fs.gid[j];
-                    if (gi < 0 && gj < 0) { fs.gid[i] = fs.gid[j] = ng; ++ng; }
-                    else if (gi > -1 && gj == -1) fs.gid[j] = gi;
-                    else if (gj > -1 && gi == -1) fs.gid[i] = gj;
-                }
-            }
-        }
-        // group segments: members grouped by gid, ascending T index inside a group
-        for (int g = 0; g <= ng; ++g) fs.gstart[g] = 0;
-        for (int i = 0; i < n; ++i) if (fs.gid[i] >= 0) fs.gstart[fs.gid[i] + 1]++;
-        for (int g = 0; g < ng; ++g) fs.gstart[g + 1] += fs.gstart[g];
-        for (int g = 0; g < ng; ++g) { fs.closeCnt[g] = 0; fs.gfill[g] = fs.gstart[g]; }
-        for (int i = 0; i < n; ++i) if (fs.gid[i] >= 0) fs.members[fs.gfill[fs.gid[i]]++] = i;
-        fs.counters[4] = ng;
+    // ---- 4. group assignment (A5).  OpenCV walks the close pairs (i, j), i < j, in lexicographic order:
+    //   both ungrouped -> new group; one grouped -> the other joins it; both grouped -> nothing (no merge).
+    // A candidate is therefore decided at its first pair in that order, which gives the closed form
+    //   pm(x) = smallest close neighbour < x,  jm(x) = smallest close neighbour > x
+    //   par(x) = pm(x)                      if it exists
+    //          = ROOT (opens a group)       if pm(jm(x)) == x
+    //          = pm(jm(x))                  if x has only larger neighbours and jm(x) was taken by a smaller one
+    //          = ISOLATED                   without neighbours
+    //   gid(x) = gid(par(x)), par(x) < x;  groups are numbered in the order of their roots
+    // (checked against the sequential loop on random graphs and by the golden frames).
+    const int G_ROOT = -2, G_ISO = -3;
+    int32_t *pm = fs.closeIdx, *jm = fs.closeCnt, *par = fs.gfill, *rootrank = fs.members;      // temporaries
+    for (int x = tid; x < n; x += nt) {
+        int p = -1, j = -1;
+        const int xw = x >> 5; const uint32_t xb = 1u << (x & 31);
+        for (int i = 0; i < x; ++i) if (M[i * wpr + xw] & xb) { p = i; break; }
+        for (int w = xw; w < wpr; ++w) { const uint32_t bits = M[x * wpr + w]; if (bits) { j = w * 32 + ffs32(bits) - 1; break; } }
+        pm[x] = p; jm[x] = j;
     }
     ctx.sync();
-    const int ng = fs.counters[4];
+    int ng = 0;
+    for (int base = 0; base < n; base += nt) {
+        const int x = base + tid;
+        int pr = G_ISO;
+        if (x < n) {
+            if (pm[x] >= 0) pr = pm[x];
+            else if (jm[x] >= 0) pr = (pm[jm[x]] == x) ? G_ROOT : pm[jm[x]];
+            par[x] = pr;
+        }
+        int total;
+        const int pos = ctx.exclusive_scan(x < n && pr == G_ROOT, total);
+        if (x < n) rootrank[x] = ng + pos;
+        ng += total;
+    }
+    ctx.sync();
+    for (int x = tid; x < n; x += nt) {
+        int r = x;
+        while (par[r] >= 0) r = par[r];
+        fs.gid[x] = (par[r] == G_ROOT) ? rootrank[r] : -1;
+        fs.sel[x] = (par[x] == G_ISO) ? 1 : 0;
+    }
+    ctx.sync();
+    // group segments: members grouped by gid, ascending T index inside a group
+    for (int g = tid; g <= ng; g += nt) {
+        int c = 0;
+        for (int i = 0; i < n; ++i) c += (fs.gid[i] >= 0 && fs.gid[i] < g);
+        fs.gstart[g] = c;
+    }
+    ctx.sync();
+    for (int x = tid; x < n; x += nt) {
+        const int g = fs.gid[x];
+        if (g < 0) continue;
+        int rank = 0;
+        for (int i = 0; i < x; ++i) rank += (fs.gid[i] == g);
+        par[x] = fs.gstart[g] + rank;                    // par is dead; members still holds rootrank
+    }
+    ctx.sync();
+    for (int x = tid; x < n; x += nt) if (fs.gid[x] >= 0) fs.members[par[x]] = x;
+    ctx.sync();
     // ---- 5. per group: representative + close contours ----
     for (int g = tid; g < ng; g += nt) {
         const int b = fs.gstart[g], e = fs.gstart[g + 1];
@@ -174,6 +205,12 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
         fs.closeCnt[g] = nc;
     }
     ctx.sync();
+    // the closeness matrix is dead: its shared-memory region now holds the selected-candidate arrays
+    const int mc = fp.max_cand;
+    const bool sm6 = smemM && smemM_words >= 6 * mc;
+    int32_t *S = sm6 ? (int32_t *)smemM : fs.S, *selGroup = sm6 ? (int32_t *)smemM + mc : fs.selGroup;
+    int32_t *parent = sm6 ? (int32_t *)smemM + 2 * mc : fs.parent, *depth = sm6 ? (int32_t *)smemM + 3 * mc : fs.depth;
+    int32_t *closeStart = sm6 ? (int32_t *)smemM + 4 * mc : fs.closeStart, *closeNum = sm6 ? (int32_t *)smemM + 5 * mc : fs.closeNum;
     // ---- 6. selected candidates (minus the ones near the image border), in T order ----
     int nS = 0;
     for (int base = 0; base < n; base += nt) {
@@ -181,49 +218,55 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
         const int flag = (i < n) && fs.sel[i] && !quad_near_border(fs.tq + (size_t)i * 8, fp.W, fp.H, fp.minDistanceToBorder);
         int total;
         const int pos = ctx.exclusive_scan(flag, total);
-        if (flag) { fs.S[nS + pos] = i; fs.selGroup[nS + pos] = fs.gid[i]; }
+        if (flag) { S[nS + pos] = i; selGroup[nS + pos] = fs.gid[i]; }
         nS += total;
     }
     ctx.sync();
     // ---- 7. containment hierarchy ----
     for (int i = tid; i < nS; i += nt) {
-        int par = -1;
-        const float *a = fs.tq + (size_t)fs.S[i] * 8;
+        int pr = -1;
+        const float *a = fs.tq + (size_t)S[i] * 8;
         for (int j = i - 1; j >= 0; --j)
-            if (quad_inside_quad(a, fs.tq + (size_t)fs.S[j] * 8)) { par = j; break; }
-        fs.parent[i] = par;
-        fs.depth[i] = 0;
+            if (quad_inside_quad(a, fs.tq + (size_t)S[j] * 8)) { pr = j; break; }
+        parent[i] = pr;
+        depth[i] = 0;
     }
     ctx.sync();
     if (tid == 0) {
         for (int i = nS - 1; i >= 0; --i) {
-            const int par = fs.parent[i];
-            if (par >= 0 && fs.depth[par] < fs.depth[i] + 1) fs.depth[par] = fs.depth[i] + 1;
+            const int pr = parent[i];
+            if (pr >= 0 && depth[pr] < depth[i] + 1) depth[pr] = depth[i] + 1;
         }
         // ---- 8. identification work list ----
         int nw = nS;
         for (int v = 0; v < nS; ++v) {
-            const int g = fs.selGroup[v];
+            const int g = selGroup[v];
             int cnt = 0;
             // only a group's representative (its first member) owns the close list
-            if (g >= 0 && fs.members[fs.gstart[g]] == fs.S[v]) cnt = fs.closeCnt[g];
-            fs.closeStart[v] = nw;
+            if (g >= 0 && fs.members[fs.gstart[g]] == S[v]) cnt = fs.closeCnt[g];
+            closeStart[v] = nw;
             if (nw + cnt > fp.max_cand) { cnt = fp.max_cand - nw; fs.counters[FC_STATUS] = 3; }
-            fs.closeNum[v] = cnt;
+            closeNum[v] = cnt;
             nw += cnt;
         }
         fs.counters[FC_NCAND] = n;
         fs.counters[FC_NSEL] = nS;
         fs.counters[FC_NWORK] = nw;
+        fs.counters[4] = ng;
     }
     ctx.sync();
+    if (sm6)
+        for (int v = tid; v < nS; v += nt) {
+            fs.S[v] = S[v]; fs.selGroup[v] = selGroup[v]; fs.parent[v] = parent[v]; fs.depth[v] = depth[v];
+            fs.closeStart[v] = closeStart[v]; fs.closeNum[v] = closeNum[v];
+        }
     const int nw = fs.counters[FC_NWORK];
     for (int v = tid; v < nS; v += nt) {
-        for (int k = 0; k < 8; ++k) fs.wq[(size_t)v * 8 + k] = fs.tq[(size_t)fs.S[v] * 8 + k];
-        const int g = fs.selGroup[v];
-        for (int c = 0; c < fs.closeNum[v]; ++c) {
+        for (int k = 0; k < 8; ++k) fs.wq[(size_t)v * 8 + k] = fs.tq[(size_t)S[v] * 8 + k];
+        const int g = selGroup[v];
+        for (int c = 0; c < closeNum[v]; ++c) {
             const int id = fs.closeIdx[fs.gstart[g] + c];
-            for (int k = 0; k < 8; ++k) fs.wq[(size_t)(fs.closeStart[v] + c) * 8 + k] = fs.tq[(size_t)id * 8 + k];
+            for (int k = 0; k < 8; ++k) fs.wq[(size_t)(closeStart[v] + c) * 8 + k] = fs.tq[(size_t)id * 8 + k];
         }
     }
     for (int w = tid; w < nw; w += nt) fs.wres[w] = 0;

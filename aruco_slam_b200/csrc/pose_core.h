@@ -173,41 +173,34 @@ B2A_HD void rodrigues_with_jacobian(const double *rv, double *R, double *dR)
     }
 }
 
-// reprojection residuals (8) at (rvec, tvec) = p[0..5]; optionally the 8x6 Jacobian d res / d p
-// (cv::projectPoints' dpdr | dpdt).  Returns the L2 norm of the residual vector.
-B2A_HD double pose_residuals(const Camera &cam, const double *obj, const double *ip, const double *p, double *res, double *J)
+// One row of the reprojection system at (rvec, tvec) = p[0..5] with R (and dR) = Rodrigues(p[0..2]):
+// row r = 2 i + c is coordinate c (0 = u, 1 = v) of corner i.  out[6] = residual; with dR also
+// out[0..5] = d residual / d p (cv::projectPoints' dpdr | dpdt).
+B2A_HD void pose_row(const Camera &cam, const double *obj, const double *ip, const double *p, const double *R, const double *dR, int r, double *out)
 {
-    double R[9], dR[27];
-    if (J) rodrigues_with_jacobian(p, R, dR); else rodrigues_to_R(p, R);
-    double e = 0;
-    for (int i = 0; i < 4; ++i) {
-        const double *X = obj + 3 * i;
-        const double Px = R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + p[3];
-        const double Py = R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + p[4];
-        const double Pz = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + p[5];
-        const double iz = Pz != 0 ? 1. / Pz : 1;
-        const double x = Px * iz, y = Py * iz;
-        double u, v, Jd[4];
-        distort_project(cam, x, y, u, v, J ? Jd : nullptr);
-        res[2 * i] = u - ip[2 * i]; res[2 * i + 1] = v - ip[2 * i + 1];
-        e += res[2 * i] * res[2 * i] + res[2 * i + 1] * res[2 * i + 1];
-        if (J) {
-            for (int k = 0; k < 6; ++k) {
-                double dP[3];
-                if (k < 3) {
-                    const double *d = dR + k * 9;
-                    dP[0] = d[0] * X[0] + d[1] * X[1] + d[2] * X[2];
-                    dP[1] = d[3] * X[0] + d[4] * X[1] + d[5] * X[2];
-                    dP[2] = d[6] * X[0] + d[7] * X[1] + d[8] * X[2];
-                } else { dP[0] = (k == 3); dP[1] = (k == 4); dP[2] = (k == 5); }
-                const double dx = iz * (dP[0] - x * dP[2]);
-                const double dy = iz * (dP[1] - y * dP[2]);
-                J[(2 * i) * 6 + k] = Jd[0] * dx + Jd[1] * dy;
-                J[(2 * i + 1) * 6 + k] = Jd[2] * dx + Jd[3] * dy;
-            }
-        }
+    const int i = r >> 1, c = r & 1;
+    const double *X = obj + 3 * i;
+    const double Px = R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + p[3];
+    const double Py = R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + p[4];
+    const double Pz = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + p[5];
+    const double iz = Pz != 0 ? 1. / Pz : 1;
+    const double x = Px * iz, y = Py * iz;
+    double u, v, Jd[4];
+    distort_project(cam, x, y, u, v, dR ? Jd : nullptr);
+    out[6] = (c ? v : u) - ip[r];
+    if (!dR) return;
+    for (int k = 0; k < 6; ++k) {
+        double dP[3];
+        if (k < 3) {
+            const double *d = dR + k * 9;
+            dP[0] = d[0] * X[0] + d[1] * X[1] + d[2] * X[2];
+            dP[1] = d[3] * X[0] + d[4] * X[1] + d[5] * X[2];
+            dP[2] = d[6] * X[0] + d[7] * X[1] + d[8] * X[2];
+        } else { dP[0] = (k == 3); dP[1] = (k == 4); dP[2] = (k == 5); }
+        const double dx = iz * (dP[0] - x * dP[2]);
+        const double dy = iz * (dP[1] - y * dP[2]);
+        out[k] = c ? (Jd[2] * dx + Jd[3] * dy) : (Jd[0] * dx + Jd[1] * dy);
     }
-    return sqrt(e);
 }
 
 // one LM trial step of OpenCV's CvLevMarq::step(): p = prev - (JtJ with diagonal * (1 + 10^lg))^-1 JtErr
@@ -221,67 +214,105 @@ B2A_HD void lm_step(const double *JtJ, const double *JtErr, int lambdaLg10, cons
     for (int a = 0; a < 6; ++a) p[a] = prev[a] - d[a];
 }
 
+// A group of lanes that solves one marker together: the 8 rows of the reprojection system and the
+// 6 rows of the normal equations are spread over the lanes; everything else (Rodrigues, the 6x6
+// solve, the schedule) is computed redundantly by every lane from the same shared values, so the
+// control flow is identical on all lanes.  `sh` = POSE_SH doubles visible to the whole group.
+struct OneLane {
+    B2A_HD int lane() const { return 0; }
+    B2A_HD int nlanes() const { return 1; }
+    B2A_HD void sync() const {}
+};
+constexpr int POSE_SH = 8 * 7 + 6 * 7;
+
+// L2 norm of the residual vector at p (every lane returns the same value)
+template <class LG>
+B2A_HD double pose_error(const LG &lg, const Camera &cam, const double *obj, const double *ip, const double *p, double *shJ)
+{
+    double R[9];
+    rodrigues_to_R(p, R);
+    for (int r = lg.lane(); r < 8; r += lg.nlanes()) pose_row(cam, obj, ip, p, R, nullptr, r, shJ + r * 7);
+    lg.sync();
+    double e = 0;
+    for (int i = 0; i < 4; ++i) { const double a = shJ[(2 * i) * 7 + 6], b = shJ[(2 * i + 1) * 7 + 6]; e += a * a + b * b; }
+    lg.sync();
+    return sqrt(e);
+}
+
 // one marker: corners (4x2, image pixels) -> rvec, tvec.  Follows cv::solvePnP(SOLVEPNP_ITERATIVE)
 // for 4 coplanar points: homography initialisation, then OpenCV's Levenberg-Marquardt schedule
 // (CvLevMarq: lambda = 10^-3 start, x10 on a worse step (up to 10^16), /10 after every accepted
 // iteration, at most 20 iterations, stop when the relative parameter change < FLT_EPSILON) on the
 // rotation *vector* and translation, so that the same local minimum and rvec branch are reached.
-B2A_HD void solve_marker_pose(const Camera &cam, float marker_length, const float *corners, double *rvec, double *tvec)
+template <class LG>
+B2A_HD void solve_marker_pose(const LG &lg, const Camera &cam, float marker_length, const float *corners, double *sh, double *rvec, double *tvec)
 {
     const float hf = marker_length / 2.f;                         // Vec3f(-L/2.f, L/2.f, 0) ...
     const double h = (double)hf;
     const double obj[12] = {-h, h, 0, h, h, 0, h, -h, 0, -h, -h, 0};
     double ip[8];
     for (int i = 0; i < 8; ++i) ip[i] = (double)corners[i];
-    // ---- initialisation: homography obj.xy -> undistorted normalised points ----
-    double A[64], b[8];
-    for (int i = 0; i < 64; ++i) A[i] = 0;
-    for (int i = 0; i < 4; ++i) {
-        double u, v;
-        undistort_point(cam, ip[2 * i], ip[2 * i + 1], u, v);
-        const double X = obj[3 * i], Y = obj[3 * i + 1];
-        double *r0 = A + (2 * i) * 8, *r1 = A + (2 * i + 1) * 8;
-        r0[0] = X; r0[1] = Y; r0[2] = 1; r0[6] = -u * X; r0[7] = -u * Y; b[2 * i] = u;
-        r1[3] = X; r1[4] = Y; r1[5] = 1; r1[6] = -v * X; r1[7] = -v * Y; b[2 * i + 1] = v;
-    }
-    solve_linear<8>(A, b);
-    const double hm[9] = {b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], 1.0};
-    const double n1 = sqrt(hm[0] * hm[0] + hm[3] * hm[3] + hm[6] * hm[6]);
-    const double n2 = sqrt(hm[1] * hm[1] + hm[4] * hm[4] + hm[7] * hm[7]);
-    const double a1[3] = {hm[0] / n1, hm[3] / n1, hm[6] / n1}, a2[3] = {hm[1] / n2, hm[4] / n2, hm[7] / n2};
-    const double a3[3] = {a1[1] * a2[2] - a1[2] * a2[1], a1[2] * a2[0] - a1[0] * a2[2], a1[0] * a2[1] - a1[1] * a2[0]};
-    double R[9];
-    for (int i = 0; i < 3; ++i) { R[3 * i] = a1[i]; R[3 * i + 1] = a2[i]; R[3 * i + 2] = a3[i]; }
-    nearest_rotation(R);
+    // ---- initialisation: homography obj.xy -> undistorted normalised points (every lane) ----
     double p[6], prev[6];
-    R_to_rodrigues(R, p);
-    const double sc = 2. / (n1 + n2);
-    p[3] = hm[2] * sc; p[4] = hm[5] * sc; p[5] = hm[8] * sc;
+    {
+        double A[64], b[8];
+        for (int i = 0; i < 64; ++i) A[i] = 0;
+        for (int i = 0; i < 4; ++i) {
+            double u, v;
+            undistort_point(cam, ip[2 * i], ip[2 * i + 1], u, v);
+            const double X = obj[3 * i], Y = obj[3 * i + 1];
+            double *r0 = A + (2 * i) * 8, *r1 = A + (2 * i + 1) * 8;
+            r0[0] = X; r0[1] = Y; r0[2] = 1; r0[6] = -u * X; r0[7] = -u * Y; b[2 * i] = u;
+            r1[3] = X; r1[4] = Y; r1[5] = 1; r1[6] = -v * X; r1[7] = -v * Y; b[2 * i + 1] = v;
+        }
+        solve_linear<8>(A, b);
+        const double hm[9] = {b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], 1.0};
+        const double n1 = sqrt(hm[0] * hm[0] + hm[3] * hm[3] + hm[6] * hm[6]);
+        const double n2 = sqrt(hm[1] * hm[1] + hm[4] * hm[4] + hm[7] * hm[7]);
+        const double a1[3] = {hm[0] / n1, hm[3] / n1, hm[6] / n1}, a2[3] = {hm[1] / n2, hm[4] / n2, hm[7] / n2};
+        const double a3[3] = {a1[1] * a2[2] - a1[2] * a2[1], a1[2] * a2[0] - a1[0] * a2[2], a1[0] * a2[1] - a1[1] * a2[0]};
+        double R[9];
+        for (int i = 0; i < 3; ++i) { R[3 * i] = a1[i]; R[3 * i + 1] = a2[i]; R[3 * i + 2] = a3[i]; }
+        nearest_rotation(R);
+        R_to_rodrigues(R, p);
+        const double sc = 2. / (n1 + n2);
+        p[3] = hm[2] * sc; p[4] = hm[5] * sc; p[5] = hm[8] * sc;
+    }
     // ---- Levenberg-Marquardt, CvLevMarq schedule ----
-    double res[8], J[48], JtJ[36], JtErr[6];
+    double *shJ = sh, *shN = sh + 56;
+    double JtJ[36], JtErr[6];
     int lambdaLg10 = -3, iters = 0;
     double prevErr = 0;
     const int max_iter = 20;
     for (;;) {
-        const double errAtP = pose_residuals(cam, obj, ip, p, res, J);
-        for (int a = 0; a < 6; ++a) {
+        {
+            double R[9], dR[27];
+            rodrigues_with_jacobian(p, R, dR);
+            for (int r = lg.lane(); r < 8; r += lg.nlanes()) pose_row(cam, obj, ip, p, R, dR, r, shJ + r * 7);
+        }
+        lg.sync();
+        double e = 0;
+        for (int i = 0; i < 4; ++i) { const double a = shJ[(2 * i) * 7 + 6], b = shJ[(2 * i + 1) * 7 + 6]; e += a * a + b * b; }
+        const double errAtP = sqrt(e);
+        for (int a = lg.lane(); a < 6; a += lg.nlanes()) {
             double s = 0;
-            for (int i = 0; i < 8; ++i) s += J[i * 6 + a] * res[i];
-            JtErr[a] = s;
-            for (int c = a; c < 6; ++c) {
+            for (int i = 0; i < 8; ++i) s += shJ[i * 7 + a] * shJ[i * 7 + 6];
+            shN[a * 7 + 6] = s;
+            for (int c = 0; c < 6; ++c) {
                 double q = 0;
-                for (int i = 0; i < 8; ++i) q += J[i * 6 + a] * J[i * 6 + c];
-                JtJ[a * 6 + c] = q; JtJ[c * 6 + a] = q;
+                for (int i = 0; i < 8; ++i) q += shJ[i * 7 + a] * shJ[i * 7 + c];
+                shN[a * 7 + c] = q;
             }
         }
+        lg.sync();
+        for (int a = 0; a < 6; ++a) { JtErr[a] = shN[a * 7 + 6]; for (int c = 0; c < 6; ++c) JtJ[a * 6 + c] = shN[a * 7 + c]; }
         for (int a = 0; a < 6; ++a) prev[a] = p[a];
         lm_step(JtJ, JtErr, lambdaLg10, prev, p);
         if (iters == 0) prevErr = errAtP;
-        double r2[8];
-        double err = pose_residuals(cam, obj, ip, p, r2, nullptr);
+        double err = pose_error(lg, cam, obj, ip, p, shJ);
         while (err > prevErr && ++lambdaLg10 <= 16) {
             lm_step(JtJ, JtErr, lambdaLg10, prev, p);
-            err = pose_residuals(cam, obj, ip, p, r2, nullptr);
+            err = pose_error(lg, cam, obj, ip, p, shJ);
         }
         lambdaLg10 = lambdaLg10 - 1 > -16 ? lambdaLg10 - 1 : -16;
         double dn = 0, pn = 0;
@@ -289,8 +320,10 @@ B2A_HD void solve_marker_pose(const Camera &cam, float marker_length, const floa
         if (++iters >= max_iter || sqrt(dn) < (double)FLT_EPSILON * sqrt(pn)) break;
         prevErr = err;
     }
-    rvec[0] = p[0]; rvec[1] = p[1]; rvec[2] = p[2];
-    tvec[0] = p[3]; tvec[1] = p[4]; tvec[2] = p[5];
+    if (lg.lane() == 0) {
+        rvec[0] = p[0]; rvec[1] = p[1]; rvec[2] = p[2];
+        tvec[0] = p[3]; tvec[1] = p[4]; tvec[2] = p[5];
+    }
 }
 
 // ---- observation mapping (reference src/aruco_slam.cpp:325-374, 437-471) ----

@@ -253,7 +253,8 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
 void emu_pose(const float *corners, int n, const double *K9, const double *D5, float marker_length, double *rvecs, double *tvecs)
 {
     Camera cam{K9[0], K9[4], K9[2], K9[5], D5[0], D5[1], D5[2], D5[3], D5[4]};
-    for (int i = 0; i < n; ++i) solve_marker_pose(cam, marker_length, corners + 8 * i, rvecs + 3 * i, tvecs + 3 * i);
+    double sh[POSE_SH];
+    for (int i = 0; i < n; ++i) solve_marker_pose(OneLane{}, cam, marker_length, corners + 8 * i, sh, rvecs + 3 * i, tvecs + 3 * i);
 }
 
 // returns kept flag; obs = (x, y, theta, cov[9])
