@@ -184,6 +184,7 @@ struct b2a_detector {
     int *d_pts_off = nullptr; uint32_t *d_pts = nullptr; int pts_cap = 0;
     uint8_t *d_quad_ok = nullptr; int32_t *d_quad_xy = nullptr, *d_quad_len = nullptr;
     unsigned long long *d_dict = nullptr;
+    double *d_wM = nullptr;                   // inverse perspective map of every identification work item
     WalkTables *d_tables = nullptr;
     FrameScratch fs0{};                       // frame-0 pointers
     FrameOutputs fo0{};
@@ -306,6 +307,7 @@ static int create_impl(b2a_detector *d)
     TRY(dev_alloc(d, &fs.closeM, BM * ((MC + 31) / 32)));
     TRY(dev_alloc(d, &fs.wq, BM * 8)); TRY(dev_alloc(d, &fs.wres, BM)); TRY(dev_alloc(d, &fs.closeStart, BM)); TRY(dev_alloc(d, &fs.closeNum, BM));
     TRY(dev_alloc(d, &fs.counters, (size_t)B * 8));
+    TRY(dev_alloc(d, &d->d_wM, BM * 9));
     const size_t BK = (size_t)B * d->max_markers;
     FrameOutputs &fo = d->fo0;
     TRY(dev_alloc(d, &fo.n_accepted, B)); TRY(dev_alloc(d, &fo.n_rejected, B)); TRY(dev_alloc(d, &fo.status, B));
@@ -565,7 +567,10 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
     ip.nMarkers = d->dict.nMarkers; ip.maxCorr = (int)((double)d->dict.maxCorrectionBits * d->prm.errorCorrectionRate);
     ip.maxBorderErr = (int)(d->dict.markerSize * d->dict.markerSize * d->prm.maxErroneousBitsInBorderRate);
     ip.minOtsuStdDev = d->prm.minOtsuStdDev; ip.W = g.W; ip.H = g.H; ip.pitch = s.pitch; ip.frame_stride = s.frame_stride; ip.max_cand = d->max_cand;
-    k_identify<<<dim3(32, nb), ID_THREADS, 0, st>>>(s.gray, d->d_dict, fa, ip);
+    double *wM = d->d_wM + (size_t)b0 * d->max_cand * 9;
+    k_homography<<<dim3(4, nb), 64, 0, st>>>(fa, wM, (ip.markerSize + 2 * ip.borderBits) * ip.cellSize, d->max_cand);
+    d->launches++;
+    k_identify<<<dim3(32, nb), ID_THREADS, 0, st>>>(s.gray, d->d_dict, wM, fa, ip);
     d->launches++;
     stage_mark(d, s, ST_FINAL);
     k_finalize<<<nb, 128, 8 * sizeof(int32_t) * d->max_cand, st>>>(fa, fp);

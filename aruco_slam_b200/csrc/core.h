@@ -21,6 +21,12 @@
 #else
 #define B2A_HD inline
 #endif
+// full unrolling where compile-time indices keep small arrays in registers on the device
+#if defined(__CUDA_ARCH__)
+#define B2A_UNROLL _Pragma("unroll")
+#else
+#define B2A_UNROLL
+#endif
 
 namespace b2a {
 
@@ -658,22 +664,34 @@ B2A_HD void perspective_inverse(const float *src, int S, double *M)
         A[i + 4][6] = d_mul(-sx, dy); A[i + 4][7] = d_mul(-sy, dy);
         b[i] = dx; b[i + 4] = dy;
     }
+    // cv::LU with partial pivoting; compile-time indices only (the row exchange is a predicated swap
+    // against every candidate row) so that the 8x8 system stays in registers on the device
+    B2A_UNROLL
     for (int i = 0; i < 8; ++i) {
         int k = i;
-        for (int j = i + 1; j < 8; ++j) if (fabs(A[j][i]) > fabs(A[k][i])) k = j;
-        if (k != i) {
-            for (int j = i; j < 8; ++j) { double t = A[i][j]; A[i][j] = A[k][j]; A[k][j] = t; }
-            double t = b[i]; b[i] = b[k]; b[k] = t;
+        double best = fabs(A[i][i]);
+    B2A_UNROLL
+        for (int j = i + 1; j < 8; ++j) { const double v = fabs(A[j][i]); if (v > best) { best = v; k = j; } }
+    B2A_UNROLL
+        for (int j = i + 1; j < 8; ++j) {
+            const bool sw = (k == j);
+    B2A_UNROLL
+            for (int c = 0; c < 8; ++c) { const double x = A[i][c], y = A[j][c]; A[i][c] = sw ? y : x; A[j][c] = sw ? x : y; }
+            const double x = b[i], y = b[j]; b[i] = sw ? y : x; b[j] = sw ? x : y;
         }
         double d = d_div(-1.0, A[i][i]);
+    B2A_UNROLL
         for (int j = i + 1; j < 8; ++j) {
             double alpha = d_mul(A[j][i], d);
+    B2A_UNROLL
             for (int kk = i + 1; kk < 8; ++kk) A[j][kk] = d_add(A[j][kk], d_mul(alpha, A[i][kk]));
             b[j] = d_add(b[j], d_mul(alpha, b[i]));
         }
     }
+    B2A_UNROLL
     for (int i = 7; i >= 0; --i) {
         double s = b[i];
+    B2A_UNROLL
         for (int k = i + 1; k < 8; ++k) s = d_sub(s, d_mul(A[i][k], b[k]));
         b[i] = d_div(s, A[i][i]);
     }
@@ -711,14 +729,15 @@ B2A_HD unsigned warp_sample(const uint8_t *__restrict__ gray, int W, int H, size
 //   otsu_chain  : one lane; per bin q1s[i] = q1 after the bin (or -1 where OpenCV `continue`s), mu1s[i]
 //   otsu_sigma  : any lane; the between-class variance of bin i from (mu, q1s[i], mu1s[i])
 // The threshold is the first bin (strict '>') with the largest sigma.
-B2A_HD double otsu_chain(const int *h, int n, double *q1s, double *mu1s)
+// Bins below the first and above the last non-empty bin cannot change the recurrence (mu1 = q1 = 0
+// before; OpenCV `continue`s after), and sum(i * h[i]) is an exact integer, so the chain runs over
+// [lo, hi] only and the caller pre-fills q1s with -1 outside.
+B2A_HD double otsu_mu(long long isum, int n) { return d_mul((double)isum, d_div(1.0, (double)n)); }
+B2A_HD void otsu_chain(const int *h, int n, int lo, int hi, double *q1s, double *mu1s)
 {
-    double mu = 0;
     const double scale = d_div(1.0, (double)n);
-    for (int i = 0; i < 256; ++i) mu = d_add(mu, d_mul((double)i, (double)h[i]));
-    mu = d_mul(mu, scale);
     double mu1 = 0, q1 = 0;
-    for (int i = 0; i < 256; ++i) {
+    for (int i = lo; i <= hi; ++i) {
         const double p_i = d_mul((double)h[i], scale);
         mu1 = d_mul(mu1, q1);
         q1 = d_add(q1, p_i);
@@ -728,7 +747,6 @@ B2A_HD double otsu_chain(const int *h, int n, double *q1s, double *mu1s)
         mu1 = d_div(d_add(mu1, d_mul((double)i, p_i)), q1);
         q1s[i] = q1; mu1s[i] = mu1;
     }
-    return mu;
 }
 B2A_HD double otsu_sigma(double mu, double q1, double mu1)
 {
@@ -741,7 +759,11 @@ B2A_HD double otsu_sigma(double mu, double q1, double mu1)
 B2A_HD int otsu_threshold(const int *h, int n)
 {
     double q1s[256], mu1s[256];
-    const double mu = otsu_chain(h, n, q1s, mu1s);
+    long long isum = 0;
+    int lo = 256, hi = -1;
+    for (int i = 0; i < 256; ++i) { q1s[i] = -1.0; mu1s[i] = 0.0; isum += (long long)i * h[i]; if (h[i]) { if (lo == 256) lo = i; hi = i; } }
+    const double mu = otsu_mu(isum, n);
+    otsu_chain(h, n, lo, hi, q1s, mu1s);
     double max_sigma = 0;
     int max_val = 0;
     for (int i = 0; i < 256; ++i) {

@@ -623,17 +623,31 @@ struct IdentParams {
     int max_cand;
 };
 
+// A7 step 1: the inverse perspective map of every work item, one thread each (cv2's 8x8 LU lives in
+// ~150 registers; keeping it out of k_identify lets that kernel run many more warps per SM)
+__global__ void __launch_bounds__(64)
+k_homography(FrameArrays fa, double *__restrict__ wM, int S, int max_cand)
+{
+    const int f = blockIdx.y;
+    const int nw = fa.fs0.counters[(size_t)f * 8 + FC_NWORK];
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += gridDim.x * blockDim.x) {
+        double M[9];
+        perspective_inverse(fa.fs0.wq + ((size_t)f * max_cand + w) * 8, S, M);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) wM[((size_t)f * max_cand + w) * 9 + i] = M[i];
+    }
+}
+
 constexpr int ID_WARPS = 4;         // work items in flight per CTA (one warp each)
 constexpr int ID_THREADS = ID_WARPS * 32;
 constexpr int ID_MAX_S = 9 * 8;     // (7 + 2) cells * up to 8 px
 
-// One WARP per work item: the sequential pieces of A7 (cv2's 8x8 LU, the Otsu recurrence, the border
+// A7 step 2.  One WARP per work item: the sequential pieces (the Otsu recurrence, the border
 // check) run on lane 0 while the other warps of the SM work on other candidates; sampling, the
 // between-class variances, the cell votes and the dictionary scan are spread over the 32 lanes.
 __global__ void __launch_bounds__(ID_THREADS)
-k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restrict__ dict, FrameArrays fa, IdentParams ip)
+k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restrict__ dict, const double *__restrict__ wM, FrameArrays fa, IdentParams ip)
 {
-    __shared__ double s_M[ID_WARPS][9];
     __shared__ double s_q1[ID_WARPS][256], s_mu1[ID_WARPS][256];
     __shared__ __align__(16) uint8_t s_patch[ID_WARPS][ID_MAX_S * ID_MAX_S];
     __shared__ int s_hist[ID_WARPS][256];
@@ -648,13 +662,11 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
     const uint8_t *img = gray + (size_t)f * ip.frame_stride;
     const unsigned FULL = 0xFFFFFFFFu;
     for (int w = blockIdx.x * ID_WARPS + wp; w < nw; w += gridDim.x * ID_WARPS) {
-        const float *corners = fa.fs0.wq + ((size_t)f * ip.max_cand + w) * 8;
-        if (lane == 0) perspective_inverse(corners, S, s_M[wp]);
         for (int i = lane; i < 256; i += 32) s_hist[wp][i] = 0;
         __syncwarp();
         double M[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) M[i] = s_M[wp][i];
+        for (int i = 0; i < 9; ++i) M[i] = __ldg(wM + ((size_t)f * ip.max_cand + w) * 9 + i);
         const int m0 = ip.cellSize / 2;
         int ls = 0, lq = 0;
         for (int p = lane; p < S * S; p += 32) {
@@ -670,10 +682,24 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
         const int mode = ident_mode(ls, lq, S, m0, ip.minOtsuStdDev);          // same value on every lane
         int thr = 0;
         if (mode == 2) {
-            double mu = 0;
-            if (lane == 0) mu = otsu_chain(s_hist[wp], S * S, s_q1[wp], s_mu1[wp]);
+            // histogram range and first moment on all lanes (8 consecutive bins each), chain on lane 0
+            int isum = 0, nzmask = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = lane * 8 + k, hv = s_hist[wp][i];
+                isum += i * hv; nzmask |= (hv != 0) << k;
+                s_q1[wp][i] = -1.0;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) isum += __shfl_xor_sync(FULL, isum, o);
+            const unsigned nzl = __ballot_sync(FULL, nzmask != 0);              // lanes that own a non-empty bin (never 0 here)
+            const int l_lo = __ffs(nzl) - 1, l_hi = 31 - __clz(nzl);
+            const int lo = l_lo * 8 + __ffs(__shfl_sync(FULL, nzmask, l_lo)) - 1;
+            const int hi = l_hi * 8 + 31 - __clz(__shfl_sync(FULL, nzmask, l_hi));
+            const double mu = otsu_mu(isum, S * S);
             __syncwarp();
-            mu = __shfl_sync(FULL, mu, 0);
+            if (lane == 0) otsu_chain(s_hist[wp], S * S, lo, hi, s_q1[wp], s_mu1[wp]);
+            __syncwarp();
             double best = 0; int bi = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {                                        // lane owns 8 consecutive bins: order kept

@@ -98,25 +98,38 @@ B2A_HD void undistort_point(const Camera &cam, double u, double v, double &xo, d
     xo = x; yo = y;
 }
 
+// Gaussian elimination with partial pivoting (first largest |pivot|), written with compile-time
+// indices only -- the row exchange is a predicated swap against every candidate row -- so that the
+// system lives in registers instead of a dynamically indexed local-memory array.
 template <int N>
 B2A_HD bool solve_linear(double *A, double *b)
 {
+    B2A_UNROLL
     for (int i = 0; i < N; ++i) {
         int k = i;
-        for (int j = i + 1; j < N; ++j) if (fabs(A[j * N + i]) > fabs(A[k * N + i])) k = j;
-        if (fabs(A[k * N + i]) < 1e-300) return false;
-        if (k != i) {
-            for (int j = 0; j < N; ++j) { const double t = A[i * N + j]; A[i * N + j] = A[k * N + j]; A[k * N + j] = t; }
-            const double t = b[i]; b[i] = b[k]; b[k] = t;
+        double best = fabs(A[i * N + i]);
+    B2A_UNROLL
+        for (int j = i + 1; j < N; ++j) { const double v = fabs(A[j * N + i]); if (v > best) { best = v; k = j; } }
+        if (best < 1e-300) return false;
+    B2A_UNROLL
+        for (int j = i + 1; j < N; ++j) {
+            const bool sw = (k == j);
+    B2A_UNROLL
+            for (int c = 0; c < N; ++c) { const double x = A[i * N + c], y = A[j * N + c]; A[i * N + c] = sw ? y : x; A[j * N + c] = sw ? x : y; }
+            const double x = b[i], y = b[j]; b[i] = sw ? y : x; b[j] = sw ? x : y;
         }
+    B2A_UNROLL
         for (int j = i + 1; j < N; ++j) {
             const double a = A[j * N + i] / A[i * N + i];
+    B2A_UNROLL
             for (int c = i; c < N; ++c) A[j * N + c] -= a * A[i * N + c];
             b[j] -= a * b[i];
         }
     }
+    B2A_UNROLL
     for (int i = N - 1; i >= 0; --i) {
         double s = b[i];
+    B2A_UNROLL
         for (int k = i + 1; k < N; ++k) s -= A[i * N + k] * b[k];
         b[i] = s / A[i * N + i];
     }
@@ -125,8 +138,10 @@ B2A_HD bool solve_linear(double *A, double *b)
 
 B2A_HD void nearest_rotation(double *R)
 {
+    B2A_UNROLL
     for (int it = 0; it < 60; ++it) {
         double a[9];
+        B2A_UNROLL
         for (int i = 0; i < 9; ++i) a[i] = R[i];
         const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
         const double id = 1 / det;
@@ -135,6 +150,7 @@ B2A_HD void nearest_rotation(double *R)
         iT[3] = (a[2] * a[7] - a[1] * a[8]) * id; iT[4] = (a[0] * a[8] - a[2] * a[6]) * id; iT[5] = (a[1] * a[6] - a[0] * a[7]) * id;
         iT[6] = (a[1] * a[5] - a[2] * a[4]) * id; iT[7] = (a[2] * a[3] - a[0] * a[5]) * id; iT[8] = (a[0] * a[4] - a[1] * a[3]) * id;
         double diff = 0;
+        B2A_UNROLL
         for (int i = 0; i < 9; ++i) { const double v = 0.5 * (a[i] + iT[i]); diff += fabs(v - a[i]); R[i] = v; }
         if (diff < 1e-15) break;
     }
@@ -145,8 +161,10 @@ B2A_HD void rodrigues_with_jacobian(const double *rv, double *R, double *dR)
 {
     const double th = sqrt(rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2]);
     if (th < DBL_EPSILON) {
+        B2A_UNROLL
         for (int i = 0; i < 9; ++i) R[i] = 0;
         R[0] = R[4] = R[8] = 1;
+        B2A_UNROLL
         for (int i = 0; i < 27; ++i) dR[i] = 0;
         dR[5] = dR[15] = dR[19] = -1;
         dR[7] = dR[11] = dR[21] = 1;
@@ -157,6 +175,7 @@ B2A_HD void rodrigues_with_jacobian(const double *rv, double *R, double *dR)
     const double rrt[9] = {rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz};
     const double r_x[9] = {0, -rz, ry, rz, 0, -rx, -ry, rx, 0};
     const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    B2A_UNROLL
     for (int k = 0; k < 9; ++k) R[k] = c * I[k] + c1 * rrt[k] + s * r_x[k];
     const double drrt[27] = {rx + rx, ry, rz, ry, 0, 0, rz, 0, 0,
                              0, rx, 0, rx, ry + ry, rz, 0, rz, 0,
@@ -165,9 +184,11 @@ B2A_HD void rodrigues_with_jacobian(const double *rv, double *R, double *dR)
                               0, 0, 1, 0, 0, 0, -1, 0, 0,
                               0, -1, 0, 1, 0, 0, 0, 0, 0};
     const double rr[3] = {rx, ry, rz};
+    B2A_UNROLL
     for (int i = 0; i < 3; ++i) {
         const double ri = rr[i];
         const double a0 = -s * ri, a1 = (s - 2 * c1 * it) * ri, a2 = c1 * it, a3 = (c - s * it) * ri, a4 = s * it;
+        B2A_UNROLL
         for (int k = 0; k < 9; ++k)
             dR[i * 9 + k] = a0 * I[k] + a1 * rrt[k] + a2 * drrt[i * 9 + k] + a3 * r_x[k] + a4 * d_r_x[i * 9 + k];
     }
@@ -176,10 +197,11 @@ B2A_HD void rodrigues_with_jacobian(const double *rv, double *R, double *dR)
 // One row of the reprojection system at (rvec, tvec) = p[0..5] with R (and dR) = Rodrigues(p[0..2]):
 // row r = 2 i + c is coordinate c (0 = u, 1 = v) of corner i.  out[6] = residual; with dR also
 // out[0..5] = d residual / d p (cv::projectPoints' dpdr | dpdt).
-B2A_HD void pose_row(const Camera &cam, const double *obj, const double *ip, const double *p, const double *R, const double *dR, int r, double *out)
+B2A_HD void pose_row(const Camera &cam, double h, const float *corners, const double *p, const double *R, const double *dR, int r, double *out)
 {
     const int i = r >> 1, c = r & 1;
-    const double *X = obj + 3 * i;
+    // object corner i of the marker square (Vec3f(-L/2, L/2, 0), (L/2, L/2, 0), (L/2, -L/2, 0), (-L/2, -L/2, 0))
+    const double X[3] = {(i == 1 || i == 2) ? h : -h, (i < 2) ? h : -h, 0.0};
     const double Px = R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + p[3];
     const double Py = R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + p[4];
     const double Pz = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + p[5];
@@ -187,8 +209,9 @@ B2A_HD void pose_row(const Camera &cam, const double *obj, const double *ip, con
     const double x = Px * iz, y = Py * iz;
     double u, v, Jd[4];
     distort_project(cam, x, y, u, v, dR ? Jd : nullptr);
-    out[6] = (c ? v : u) - ip[r];
+    out[6] = (c ? v : u) - (double)corners[r];
     if (!dR) return;
+    B2A_UNROLL
     for (int k = 0; k < 6; ++k) {
         double dP[3];
         if (k < 3) {
@@ -204,13 +227,19 @@ B2A_HD void pose_row(const Camera &cam, const double *obj, const double *ip, con
 }
 
 // one LM trial step of OpenCV's CvLevMarq::step(): p = prev - (JtJ with diagonal * (1 + 10^lg))^-1 JtErr
-B2A_HD void lm_step(const double *JtJ, const double *JtErr, int lambdaLg10, const double *prev, double *p)
+B2A_HD void lm_step(const double *shN /* [6][7]: JtJ row | JtErr */, int lambdaLg10, const double *prev, double *p)
 {
     double M[36], d[6];
-    const double lambda = exp(lambdaLg10 * 2.302585092994046);
-    for (int i = 0; i < 36; ++i) M[i] = JtJ[i];
-    for (int a = 0; a < 6; ++a) { M[a * 6 + a] *= 1. + lambda; d[a] = JtErr[a]; }
-    if (!solve_linear<6>(M, d)) for (int a = 0; a < 6; ++a) d[a] = 0;
+    const double lambda = exp(lambdaLg10 * 2.302585092994046);      // CvLevMarq: exp(lambdaLg10 * log(10))
+    B2A_UNROLL
+    for (int a = 0; a < 6; ++a) {
+        B2A_UNROLL
+        for (int c = 0; c < 6; ++c) M[a * 6 + c] = shN[a * 7 + c];
+        M[a * 6 + a] *= 1. + lambda;
+        d[a] = shN[a * 7 + 6];
+    }
+    if (!solve_linear<6>(M, d)) { B2A_UNROLL for (int a = 0; a < 6; ++a) d[a] = 0; }
+    B2A_UNROLL
     for (int a = 0; a < 6; ++a) p[a] = prev[a] - d[a];
 }
 
@@ -227,13 +256,15 @@ constexpr int POSE_SH = 8 * 7 + 6 * 7;
 
 // L2 norm of the residual vector at p (every lane returns the same value)
 template <class LG>
-B2A_HD double pose_error(const LG &lg, const Camera &cam, const double *obj, const double *ip, const double *p, double *shJ)
+B2A_HD double pose_error(const LG &lg, const Camera &cam, double h, const float *corners, const double *p, double *shJ)
 {
     double R[9];
     rodrigues_to_R(p, R);
-    for (int r = lg.lane(); r < 8; r += lg.nlanes()) pose_row(cam, obj, ip, p, R, nullptr, r, shJ + r * 7);
+    B2A_UNROLL
+    for (int r = lg.lane(); r < 8; r += lg.nlanes()) pose_row(cam, h, corners, p, R, nullptr, r, shJ + r * 7);
     lg.sync();
     double e = 0;
+    B2A_UNROLL
     for (int i = 0; i < 4; ++i) { const double a = shJ[(2 * i) * 7 + 6], b = shJ[(2 * i + 1) * 7 + 6]; e += a * a + b * b; }
     lg.sync();
     return sqrt(e);
@@ -249,24 +280,27 @@ B2A_HD void solve_marker_pose(const LG &lg, const Camera &cam, float marker_leng
 {
     const float hf = marker_length / 2.f;                         // Vec3f(-L/2.f, L/2.f, 0) ...
     const double h = (double)hf;
-    const double obj[12] = {-h, h, 0, h, h, 0, h, -h, 0, -h, -h, 0};
-    double ip[8];
-    for (int i = 0; i < 8; ++i) ip[i] = (double)corners[i];
     // ---- initialisation: homography obj.xy -> undistorted normalised points (every lane) ----
     double p[6], prev[6];
     {
-        double A[64], b[8];
-        for (int i = 0; i < 64; ++i) A[i] = 0;
-        for (int i = 0; i < 4; ++i) {
-            double u, v;
-            undistort_point(cam, ip[2 * i], ip[2 * i + 1], u, v);
-            const double X = obj[3 * i], Y = obj[3 * i + 1];
-            double *r0 = A + (2 * i) * 8, *r1 = A + (2 * i + 1) * 8;
-            r0[0] = X; r0[1] = Y; r0[2] = 1; r0[6] = -u * X; r0[7] = -u * Y; b[2 * i] = u;
-            r1[3] = X; r1[4] = Y; r1[5] = 1; r1[6] = -v * X; r1[7] = -v * Y; b[2 * i + 1] = v;
-        }
-        solve_linear<8>(A, b);
-        const double hm[9] = {b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], 1.0};
+        // homography obj.xy -> undistorted normalised points, h33 = 1.  The object points are the corners
+        // of a square, so the 8x8 system has the closed form of the unit-square -> quadrilateral map
+        // (s = (X + h) / 2h, t = (h - Y) / 2h sends corners 0..3 to (0,0), (1,0), (1,1), (0,1)).
+        double qx[4], qy[4];
+        B2A_UNROLL
+        for (int i = 0; i < 4; ++i) undistort_point(cam, (double)corners[2 * i], (double)corners[2 * i + 1], qx[i], qy[i]);
+        const double dx1 = qx[1] - qx[2], dx2 = qx[3] - qx[2], sx = qx[0] - qx[1] + qx[2] - qx[3];
+        const double dy1 = qy[1] - qy[2], dy2 = qy[3] - qy[2], sy = qy[0] - qy[1] + qy[2] - qy[3];
+        const double den = dx1 * dy2 - dx2 * dy1;
+        const double g = (sx * dy2 - dx2 * sy) / den, k = (dx1 * sy - sx * dy1) / den;
+        const double a = qx[1] - qx[0] + g * qx[1], b = qx[3] - qx[0] + k * qx[3], c = qx[0];
+        const double d = qy[1] - qy[0] + g * qy[1], e = qy[3] - qy[0] + k * qy[3], f = qy[0];
+        const double i2h = 1. / (2. * h);
+        // H = Hs * [[i2h, 0, 1/2], [0, -i2h, 1/2], [0, 0, 1]], then scaled to h33 = 1
+        const double w = 1. / (0.5 * (g + k) + 1.);
+        const double hm[9] = {a * i2h * w, -b * i2h * w, (0.5 * (a + b) + c) * w,
+                              d * i2h * w, -e * i2h * w, (0.5 * (d + e) + f) * w,
+                              g * i2h * w, -k * i2h * w, 1.0};
         const double n1 = sqrt(hm[0] * hm[0] + hm[3] * hm[3] + hm[6] * hm[6]);
         const double n2 = sqrt(hm[1] * hm[1] + hm[4] * hm[4] + hm[7] * hm[7]);
         const double a1[3] = {hm[0] / n1, hm[3] / n1, hm[6] / n1}, a2[3] = {hm[1] / n2, hm[4] / n2, hm[7] / n2};
@@ -280,7 +314,6 @@ B2A_HD void solve_marker_pose(const LG &lg, const Camera &cam, float marker_leng
     }
     // ---- Levenberg-Marquardt, CvLevMarq schedule ----
     double *shJ = sh, *shN = sh + 56;
-    double JtJ[36], JtErr[6];
     int lambdaLg10 = -3, iters = 0;
     double prevErr = 0;
     const int max_iter = 20;
@@ -288,34 +321,39 @@ B2A_HD void solve_marker_pose(const LG &lg, const Camera &cam, float marker_leng
         {
             double R[9], dR[27];
             rodrigues_with_jacobian(p, R, dR);
-            for (int r = lg.lane(); r < 8; r += lg.nlanes()) pose_row(cam, obj, ip, p, R, dR, r, shJ + r * 7);
+            for (int r = lg.lane(); r < 8; r += lg.nlanes()) pose_row(cam, h, corners, p, R, dR, r, shJ + r * 7);
         }
         lg.sync();
         double e = 0;
+        B2A_UNROLL
         for (int i = 0; i < 4; ++i) { const double a = shJ[(2 * i) * 7 + 6], b = shJ[(2 * i + 1) * 7 + 6]; e += a * a + b * b; }
         const double errAtP = sqrt(e);
         for (int a = lg.lane(); a < 6; a += lg.nlanes()) {
             double s = 0;
+            B2A_UNROLL
             for (int i = 0; i < 8; ++i) s += shJ[i * 7 + a] * shJ[i * 7 + 6];
             shN[a * 7 + 6] = s;
+            B2A_UNROLL
             for (int c = 0; c < 6; ++c) {
                 double q = 0;
+                B2A_UNROLL
                 for (int i = 0; i < 8; ++i) q += shJ[i * 7 + a] * shJ[i * 7 + c];
                 shN[a * 7 + c] = q;
             }
         }
         lg.sync();
-        for (int a = 0; a < 6; ++a) { JtErr[a] = shN[a * 7 + 6]; for (int c = 0; c < 6; ++c) JtJ[a * 6 + c] = shN[a * 7 + c]; }
+        B2A_UNROLL
         for (int a = 0; a < 6; ++a) prev[a] = p[a];
-        lm_step(JtJ, JtErr, lambdaLg10, prev, p);
+        lm_step(shN, lambdaLg10, prev, p);
         if (iters == 0) prevErr = errAtP;
-        double err = pose_error(lg, cam, obj, ip, p, shJ);
+        double err = pose_error(lg, cam, h, corners, p, shJ);
         while (err > prevErr && ++lambdaLg10 <= 16) {
-            lm_step(JtJ, JtErr, lambdaLg10, prev, p);
-            err = pose_error(lg, cam, obj, ip, p, shJ);
+            lm_step(shN, lambdaLg10, prev, p);
+            err = pose_error(lg, cam, h, corners, p, shJ);
         }
         lambdaLg10 = lambdaLg10 - 1 > -16 ? lambdaLg10 - 1 : -16;
         double dn = 0, pn = 0;
+        B2A_UNROLL
         for (int a = 0; a < 6; ++a) { dn += (p[a] - prev[a]) * (p[a] - prev[a]); pn += prev[a] * prev[a]; }
         if (++iters >= max_iter || sqrt(dn) < (double)FLT_EPSILON * sqrt(pn)) break;
         prevErr = err;
