@@ -318,6 +318,7 @@ static int create_impl(b2a_detector *d)
     TRY(pin_alloc(d, &d->h_corners, BK * 8)); TRY(pin_alloc(d, &d->h_ids, BK)); TRY(pin_alloc(d, &d->h_rejected, BK * 8));
     TRY(pin_alloc(d, &d->h_rvecs, BK * 3)); TRY(pin_alloc(d, &d->h_tvecs, BK * 3));
     CU(cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_threshold3<1, 6, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3_SMEM));
     CU(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (int)sizeof(int32_t) * d->max_cand));
     CU(cudaStreamSynchronize(d->stream));
     return B2A_OK;
@@ -497,8 +498,14 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     uint32_t *masks = d->d_masks + fs0 * g.mask_plane;
     stage_mark(d, s, ST_THRESH);
     {
-        dim3 grid((W + TH_TW - 1) / TH_TW, (H + TH_TH - 1) / TH_TH, nb);
-        k_threshold<<<grid, TH_THREADS, 0, st>>>(s.gray, s.pitch, s.frame_stride, masks, g);
+        const bool default_windows = g.nScales == 3 && g.radius[0] == 1 && g.radius[1] == 6 && g.radius[2] == 11 && std::abs(g.Cfloor) <= 2048;
+        if (default_windows) {
+            dim3 grid((W + T3_TW - 1) / T3_TW, (H + T3_TH - 1) / T3_TH, nb);
+            k_threshold3<1, 6, 11><<<grid, T3_THREADS, T3_SMEM, st>>>(s.gray, s.pitch, s.frame_stride, masks, g);
+        } else {
+            dim3 grid((W + TH_TW - 1) / TH_TW, (H + TH_TH - 1) / TH_TH, nb);
+            k_threshold<<<grid, TH_THREADS, 0, st>>>(s.gray, s.pitch, s.frame_stride, masks, g);
+        }
         d->launches++;
     }
     stage_mark(d, s, ST_ANCHORS);

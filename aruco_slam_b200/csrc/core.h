@@ -387,13 +387,16 @@ B2A_HD int approx_closed(const LG &lg, const uint32_t *__restrict__ P, int count
         startp = pos;
         const int sx = px_of(P[pos]), sy = py_of(P[pos]);
         pos = (pos + 1) % count;
-        long long bd = 0; int bj = 0x7FFFFFFF;
+        // coordinates are below 2^15: squared distances fit 32 bits
+        uint32_t bd32 = 0; int bj = 0x7FFFFFFF;
         for (int j = 1 + lane; j < count; j += nl) {
             int idx = pos + j - 1; if (idx >= count) idx -= count;
             const uint32_t q = P[idx];
-            long long dx = px_of(q) - sx, dy = py_of(q) - sy, d = dx * dx + dy * dy;
-            if (d > bd) { bd = d; bj = j; }
+            const int dx = px_of(q) - sx, dy = py_of(q) - sy;
+            const uint32_t d = (uint32_t)(dx * dx) + (uint32_t)(dy * dy);
+            if (d > bd32) { bd32 = d; bj = j; }
         }
+        long long bd = (long long)bd32;
         lg.argmax_first(bd, bj);
         maxd = bd;
         if (bd > 0) right = bj;
@@ -415,19 +418,24 @@ B2A_HD int approx_closed(const LG &lg, const uint32_t *__restrict__ P, int count
         bool le = true;
         int split = 0;
         if (inner > 0) {
-            const long long dx = ex - sx, dy = ey - sy, L2 = dx * dx + dy * dy;
-            long long bd = 0; int bt = 0x7FFFFFFF;
+            // |coordinate differences| < 2^15: dot and cross products fit int32 (|a b + c d| < 2^31), squared
+            // lengths fit uint32; only the final products need 64 bits (one widening multiply each)
+            const int dx = ex - sx, dy = ey - sy;
+            const uint32_t L2u = (uint32_t)(dx * dx) + (uint32_t)(dy * dy);
+            const long long L2 = (long long)L2u;
+            unsigned long long bdu = 0; int bt = 0x7FFFFFFF;
             for (int t = lane; t < inner; t += nl) {
                 int idx = s + 1 + t; if (idx >= count) idx -= count;
                 const uint32_t q = P[idx];
-                const long long px = px_of(q) - sx, py = py_of(q) - sy;
-                const long long dot = px * dx + py * dy;
-                long long d;
-                if (dot < 0) d = (px * px + py * py) * L2;
-                else if (dot > L2) { long long qx = px - dx, qy = py - dy; d = (qx * qx + qy * qy) * L2; }
-                else { long long cr = py * dx - px * dy; d = cr * cr; }
-                if (d > bd) { bd = d; bt = t; }
+                const int px = px_of(q) - sx, py = py_of(q) - sy;
+                const int dot = px * dx + py * dy;
+                unsigned long long d;
+                if (dot < 0) d = (unsigned long long)((uint32_t)(px * px) + (uint32_t)(py * py)) * L2u;
+                else if ((uint32_t)dot > L2u) { const int qx = px - dx, qy = py - dy; d = (unsigned long long)((uint32_t)(qx * qx) + (uint32_t)(qy * qy)) * L2u; }
+                else { const int cr = py * dx - px * dy; const uint32_t a = (uint32_t)(cr < 0 ? -cr : cr); d = (unsigned long long)a * a; }
+                if (d > bdu) { bdu = d; bt = t; }
             }
+            long long bd = (long long)bdu;
             lg.argmax_first(bd, bt);
             if (bd > 0) { split = s + 1 + bt; if (split >= count) split -= count; }
             le = (double)bd <= eps2 * (double)L2;

@@ -227,6 +227,45 @@ B2A_HD void pose_row(const Camera &cam, double h, const float *corners, const do
 }
 
 // one LM trial step of OpenCV's CvLevMarq::step(): p = prev - (JtJ with diagonal * (1 + 10^lg))^-1 JtErr
+// LDL^T solve of the 6x6 symmetric positive definite LM system (upper part of M is not read);
+// false if a pivot is not positive.  (CvLevMarq solves the same system by SVD; only the solution matters.)
+B2A_HD bool solve_spd6(const double *M, double *d)
+{
+    double L[36], D[6];
+    B2A_UNROLL
+    for (int j = 0; j < 6; ++j) {
+        double v = M[j * 6 + j];
+        B2A_UNROLL
+        for (int k = 0; k < j; ++k) v -= L[j * 6 + k] * L[j * 6 + k] * D[k];
+        if (!(v > 0)) return false;
+        D[j] = v;
+        const double inv = 1. / v;
+        B2A_UNROLL
+        for (int i = j + 1; i < 6; ++i) {
+            double t = M[i * 6 + j];
+            B2A_UNROLL
+            for (int k = 0; k < j; ++k) t -= L[i * 6 + k] * L[j * 6 + k] * D[k];
+            L[i * 6 + j] = t * inv;
+        }
+        // forward substitution and the division by D folded in
+        double y = d[j];
+        B2A_UNROLL
+        for (int k = 0; k < j; ++k) y -= L[j * 6 + k] * d[k];
+        d[j] = y;
+    }
+    B2A_UNROLL
+    for (int j = 0; j < 6; ++j) d[j] = d[j] / D[j];
+    B2A_UNROLL
+    for (int j = 5; j >= 0; --j) {
+        double x = d[j];
+        B2A_UNROLL
+        for (int k = j + 1; k < 6; ++k) x -= L[k * 6 + j] * d[k];
+        d[j] = x;
+    }
+    return true;
+}
+
+// one LM trial step of OpenCV's CvLevMarq::step(): p = prev - (JtJ with diagonal * (1 + 10^lg))^-1 JtErr
 B2A_HD void lm_step(const double *shN /* [6][7]: JtJ row | JtErr */, int lambdaLg10, const double *prev, double *p)
 {
     double M[36], d[6];
@@ -238,7 +277,11 @@ B2A_HD void lm_step(const double *shN /* [6][7]: JtJ row | JtErr */, int lambdaL
         M[a * 6 + a] *= 1. + lambda;
         d[a] = shN[a * 7 + 6];
     }
-    if (!solve_linear<6>(M, d)) { B2A_UNROLL for (int a = 0; a < 6; ++a) d[a] = 0; }
+    if (!solve_spd6(M, d)) {                        // not positive definite (degenerate corners): pivoted elimination
+        B2A_UNROLL
+        for (int a = 0; a < 6; ++a) d[a] = shN[a * 7 + 6];
+        if (!solve_linear<6>(M, d)) { B2A_UNROLL for (int a = 0; a < 6; ++a) d[a] = 0; }
+    }
     B2A_UNROLL
     for (int a = 0; a < 6; ++a) p[a] = prev[a] - d[a];
 }
