@@ -176,7 +176,7 @@ struct b2a_detector {
     uint8_t *d_in = nullptr, *d_gray = nullptr;
     uint32_t *d_masks = nullptr; size_t masks_words = 0;
     // border graph (core.h): anchors of all (frame,scale) masks of a sub-batch share one slice of these arrays
-    uint2 *d_ast = nullptr; Seg *d_seg = nullptr, *d_sseg = nullptr; uint32_t *d_minoff = nullptr, *d_ssoff = nullptr; int4 *d_emit = nullptr; uint32_t *d_amap = nullptr;
+    uint2 *d_ast = nullptr; Seg *d_seg = nullptr, *d_sseg = nullptr; uint32_t *d_minoff = nullptr, *d_ssoff = nullptr; int2 *d_emit = nullptr; uint32_t *d_amap = nullptr;
     unsigned anchors_cap = 0; int anchor_R = 8;
     int *d_counters = nullptr;               // [sub-batch] n_anchors (unsigned), then per-(f,s) arrays
     int *d_surv_count = nullptr, *d_contour_count = nullptr, *d_iso_count = nullptr, *d_status = nullptr;
@@ -509,7 +509,7 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
         d->launches++;
     }
     stage_mark(d, s, ST_ANCHORS);
-    k_anchors<<<d->num_sms * 4, 256, 0, st>>>(masks, bg, d->d_iso_count + fs0, d->d_tables, Rm, g);
+    k_anchors<<<d->num_sms * 8, 256, 0, st>>>(masks, bg, d->d_iso_count + fs0, Rm, g);
     d->launches++; DBG_SYNC(st);
     stage_mark(d, s, ST_SEGMENTS);
     k_segments<<<walk_grid, 256, 0, st>>>(masks, bg, max_len, d->d_tables, Rm, g);
@@ -529,7 +529,7 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     k_assign_sub<<<walk_grid, 256, 0, st>>>(bg);
     d->launches++; DBG_SYNC(st);
     stage_mark(d, s, ST_EMIT);
-    k_emit<<<walk_grid, 256, 0, st>>>(masks, bg, d->d_pts + fs0 * (size_t)g.pts_cap, d->d_tables, g);
+    k_emit<<<walk_grid, 256, 0, st>>>(masks, bg, d->d_sorted + fs0 * g.surv_cap, d->d_pts_off + fs0 * g.surv_cap, d->d_pts + fs0 * (size_t)g.pts_cap, d->d_tables, g);
     d->launches++; DBG_SYNC(st);
     stage_mark(d, s, ST_APPROX);
     k_approx<<<dim3(8, (unsigned)FS), 256, 0, st>>>(d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,

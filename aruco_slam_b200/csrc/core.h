@@ -242,6 +242,36 @@ B2A_HD uint32_t anchor_pixel_candidates(uint32_t m, uint32_t ml, uint32_t mr, ui
     return bp;
 }
 
+// Word-parallel anchor enumeration for the 32 pixels of mask word m (no per-pixel table lookups):
+// A[k] = pixels whose state with canonical D = 2k (E, N, W, S) is an anchor; for those, hi[k] tells
+// whether s_in = D - 1 (bit set) or D - 2.  Same sets as pix[] + is_anchor(); a pixel's anchors are
+// ordered by k (anchor_rank).  rowflag: y % R == 0; cols: bits with x % R == 0.
+B2A_HD void anchor_words(uint32_t m, uint32_t ml, uint32_t mr, uint32_t u, uint32_t ul, uint32_t ur, uint32_t d, uint32_t dl, uint32_t dr,
+                         bool rowflag, uint32_t cols, uint32_t A[4], uint32_t hi[4], uint32_t &iso)
+{
+    uint32_t n[8];
+    n[0] = (m >> 1) | (mr << 31); n[1] = (u >> 1) | (ur << 31); n[2] = u; n[3] = (u << 1) | (ul >> 31);
+    n[4] = (m << 1) | (ml >> 31); n[5] = (d << 1) | (dl >> 31); n[6] = d; n[7] = (d >> 1) | (dr << 31);
+    iso = m & ~(n[0] | n[1] | n[2] | n[3] | n[4] | n[5] | n[6] | n[7]);
+    const uint32_t outerCand = ~(n[1] | n[2] | n[3] | n[4]), holeCand = ~n[0] & n[1];
+    const uint32_t rows = rowflag ? 0xFFFFFFFFu : 0u;
+    B2A_UNROLL
+    for (int k = 0; k < 4; ++k) {
+        const int D = 2 * k;
+        const uint32_t canon = m & ~n[D] & (n[(D + 7) & 7] | n[(D + 6) & 7]);
+        // 4-neighbours inside the state's clear run, walking counter-clockwise from D
+        const uint32_t c2 = canon & ~n[(D + 1) & 7] & ~n[(D + 2) & 7];
+        const uint32_t c4 = c2 & ~n[(D + 3) & 7] & ~n[(D + 4) & 7];
+        const uint32_t c6 = c4 & ~n[(D + 5) & 7] & ~n[(D + 6) & 7];
+        uint32_t has[4];                         // has[j]: run contains direction 2 j
+        has[k] = canon; has[(k + 1) & 3] = c2; has[(k + 2) & 3] = c4; has[(k + 3) & 3] = c6;
+        const uint32_t row_t = has[0] | has[2], col_t = has[1] | has[3];
+        const uint32_t unc = (has[2] & outerCand) | (has[0] & ~has[2] & holeCand);
+        A[k] = canon & (unc | (row_t & rows) | (col_t & cols));
+        hi[k] = n[(D + 7) & 7];
+    }
+}
+
 // Walk from anchor state (x,y,s) to the next anchor.  len = number of states of the segment
 // (SEG_OVERFLOW once more than max_len steps were taken), minkey / minoff = smallest start key
 // among the segment's start-eligible states and its offset (A_NONE if none); (x,y,s) and w9 are
@@ -741,20 +771,25 @@ B2A_HD unsigned warp_sample(const uint8_t *__restrict__ gray, int W, int H, size
 // before; OpenCV `continue`s after), and sum(i * h[i]) is an exact integer, so the chain runs over
 // [lo, hi] only and the caller pre-fills q1s with -1 outside.
 B2A_HD double otsu_mu(long long isum, int n) { return d_mul((double)isum, d_div(1.0, (double)n)); }
-B2A_HD void otsu_chain(const int *h, int n, int lo, int hi, double *q1s, double *mu1s)
+// in: q1s[i] = p_i = h[i] / n, mu1s[i] = i * p_i for lo <= i <= hi;  out: q1s[i] = q1 (or -1), mu1s[i] = mu1
+B2A_HD void otsu_chain(int lo, int hi, double *q1s, double *mu1s)
 {
-    const double scale = d_div(1.0, (double)n);
     double mu1 = 0, q1 = 0;
     for (int i = lo; i <= hi; ++i) {
-        const double p_i = d_mul((double)h[i], scale);
+        const double p_i = q1s[i], ip_i = mu1s[i];
         mu1 = d_mul(mu1, q1);
         q1 = d_add(q1, p_i);
         const double q2 = d_sub(1.0, q1);
         const double mn = q1 < q2 ? q1 : q2, mx = q1 > q2 ? q1 : q2;
         if (mn < (double)FLT_EPSILON || mx > 1.0 - (double)FLT_EPSILON) { q1s[i] = -1.0; continue; }
-        mu1 = d_div(d_add(mu1, d_mul((double)i, p_i)), q1);
+        mu1 = d_div(d_add(mu1, ip_i), q1);
         q1s[i] = q1; mu1s[i] = mu1;
     }
+}
+B2A_HD void otsu_bin_inputs(int i, int hv, int n, double &p_i, double &ip_i)
+{
+    p_i = d_mul((double)hv, d_div(1.0, (double)n));
+    ip_i = d_mul((double)i, p_i);
 }
 B2A_HD double otsu_sigma(double mu, double q1, double mu1)
 {
@@ -771,7 +806,8 @@ B2A_HD int otsu_threshold(const int *h, int n)
     int lo = 256, hi = -1;
     for (int i = 0; i < 256; ++i) { q1s[i] = -1.0; mu1s[i] = 0.0; isum += (long long)i * h[i]; if (h[i]) { if (lo == 256) lo = i; hi = i; } }
     const double mu = otsu_mu(isum, n);
-    otsu_chain(h, n, lo, hi, q1s, mu1s);
+    for (int i = lo; i <= hi; ++i) otsu_bin_inputs(i, h[i], n, q1s[i], mu1s[i]);
+    otsu_chain(lo, hi, q1s, mu1s);
     double max_sigma = 0;
     int max_val = 0;
     for (int i = 0; i < 256; ++i) {

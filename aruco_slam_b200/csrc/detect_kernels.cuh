@@ -290,7 +290,7 @@ struct BorderGraph {
     uint32_t *minoff;    // offset of the segment's min-key state
     Seg *sseg;           // super anchors only: (next super, previous super, length up to it, min key)
     uint32_t *ssoff;     // super anchors only: offset of the min-key state from the super anchor
-    int4 *emit;          // (index of the border's first point in pts, position of the segment's first state, border length, -)
+    int2 *emit;          // (position of the segment's first state in its border, 1 + slot of the border in `sorted`; 0 = not kept)
     uint32_t *amap;      // per pixel of every (frame,scale): first anchor index
     unsigned *n_anchors; // this sub-batch's counter
     unsigned cap;
@@ -305,46 +305,34 @@ __device__ __forceinline__ void load_walk_tables(const WalkTables *__restrict__ 
 }
 
 __global__ void __launch_bounds__(256)
-k_anchors(const uint32_t *__restrict__ masks, BorderGraph bg, int *__restrict__ iso_count, const WalkTables *__restrict__ tables, int Rm, DetGeom g)
+k_anchors(const uint32_t *__restrict__ masks, BorderGraph bg, int *__restrict__ iso_count, int Rm, DetGeom g)
 {
-    __shared__ __align__(16) uint32_t s_pix[512];
-    load_walk_tables(tables, nullptr, s_pix);
-    const long long words_per_plane = (long long)g.H * g.WW;
-    const long long total = (long long)g.B * g.nScales * words_per_plane;
+    const unsigned words_per_plane = (unsigned)g.H * (unsigned)g.WW;
+    const unsigned total = (unsigned)(g.B * g.nScales) * words_per_plane;
     const int lane = threadIdx.x & 31;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    for (long long i0 = first - lane; i0 < total; i0 += stride) {      // whole warps iterate together (warp-aggregated append)
-        const long long i = i0 + lane;
-        uint32_t bp = 0, m = 0, ml = 0, mr = 0, u = 0, ul = 0, ur = 0, d = 0, dl = 0, dr = 0;
+    const unsigned stride = gridDim.x * blockDim.x;
+    const uint32_t cols = 0xFFFFFFFFu / ((Rm >= 31) ? 0xFFFFFFFFu : ((2u << Rm) - 1u));       // bits with (b & Rm) == 0
+    // whole warps iterate together (warp-aggregated append); word index = (fs * H + y) * WW + wx
+    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < total; i0 += stride) {
+        const unsigned i = i0 + lane;
+        uint32_t A[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
         int fs = 0, y = 0, wx = 0;
         if (i < total) {
             fs = (int)(i / words_per_plane);
-            const long long rem = i - (long long)fs * words_per_plane;
-            y = (int)(rem / g.WW); wx = (int)(rem - (long long)y * g.WW);
+            const unsigned rem = i - (unsigned)fs * words_per_plane;
+            y = (int)(rem / (unsigned)g.WW); wx = (int)(rem - (unsigned)y * (unsigned)g.WW);
             const uint32_t *row = masks + (size_t)fs * g.mask_plane + (size_t)(y + 1) * g.PWW + wx + 1;
-            m = __ldg(row);
+            const uint32_t m = __ldg(row);
             if (m) {
-                ml = __ldg(row - 1); mr = __ldg(row + 1);
-                u = __ldg(row - g.PWW); ul = __ldg(row - g.PWW - 1); ur = __ldg(row - g.PWW + 1);
-                d = __ldg(row + g.PWW); dl = __ldg(row + g.PWW - 1); dr = __ldg(row + g.PWW + 1);
+                const uint32_t ml = __ldg(row - 1), mr = __ldg(row + 1);
+                const uint32_t u = __ldg(row - g.PWW), ul = __ldg(row - g.PWW - 1), ur = __ldg(row - g.PWW + 1);
+                const uint32_t d = __ldg(row + g.PWW), dl = __ldg(row + g.PWW - 1), dr = __ldg(row + g.PWW + 1);
                 uint32_t iso;
-                bp = anchor_pixel_candidates(m, ml, mr, u, ul, ur, d, dl, dr, y, Rm, iso);
+                anchor_words(m, ml, mr, u, ul, ur, d, dl, dr, !(y & Rm), cols, A, hi, iso);
                 if (iso) atomicAdd(&iso_count[fs], __popc(iso));
             }
         }
-        // pass 1: count this word's anchors
-        int cnt = 0;
-        for (uint32_t bits = bp; bits; bits &= bits - 1) {
-            const int b = __ffs(bits) - 1, x = wx * 32 + b;
-            const unsigned w9 = win3_words(ul, u, ur, b) | (win3_words(ml, m, mr, b) << 3) | (win3_words(dl, d, dr, b) << 6);
-            const uint32_t p = s_pix[w9];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const unsigned e = (p >> (8 * k)) & 0xFFu;
-                cnt += ((e & 0x80u) && is_anchor((e << 2) & (ST_ROW | ST_COL | ST_UNC), x, y, Rm)) ? 1 : 0;
-            }
-        }
+        const int cnt = __popc(A[0]) + __popc(A[1]) + __popc(A[2]) + __popc(A[3]);
         int incl = cnt;
 #pragma unroll
         for (int dd = 1; dd < 32; dd <<= 1) { const int o = __shfl_up_sync(0xFFFFFFFFu, incl, dd); if (lane >= dd) incl += o; }
@@ -354,24 +342,20 @@ k_anchors(const uint32_t *__restrict__ masks, BorderGraph bg, int *__restrict__ 
         if (lane == 0) base = atomicAdd(bg.n_anchors, (unsigned)tot);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         unsigned pos = base + (unsigned)(incl - cnt);
-        // pass 2: write them
-        for (uint32_t bits = bp; bits; bits &= bits - 1) {
-            const int b = __ffs(bits) - 1, x = wx * 32 + b;
-            const unsigned w9 = win3_words(ul, u, ur, b) | (win3_words(ml, m, mr, b) << 3) | (win3_words(dl, d, dr, b) << 6);
-            const uint32_t p = s_pix[w9];
-            bool first_of_pixel = true;
+        // the word's anchors, pixel by pixel, canonical directions E, N, W, S inside a pixel
+        for (uint32_t px = A[0] | A[1] | A[2] | A[3]; px; px &= px - 1) {
+            const int b = __ffs(px) - 1, x = wx * 32 + b;
+            if (pos < bg.cap) bg.amap[((size_t)fs * g.H + y) * g.W + x] = pos;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const unsigned e = (p >> (8 * k)) & 0xFFu;
-                if (!((e & 0x80u) && is_anchor((e << 2) & (ST_ROW | ST_COL | ST_UNC), x, y, Rm))) continue;
+                if (!((A[k] >> b) & 1u)) continue;
                 if (pos < bg.cap) {
-                    bg.ast[pos] = make_uint2((unsigned)x | ((unsigned)y << 16), ((unsigned)fs << 3) | (e & 7u));
+                    const unsigned s_in = (unsigned)(2 * k + (((hi[k] >> b) & 1u) ? 7 : 6)) & 7u;
+                    bg.ast[pos] = make_uint2((unsigned)x | ((unsigned)y << 16), ((unsigned)fs << 3) | s_in);
                     bg.seg[pos] = Seg{A_NONE, A_NONE, 0u, A_NONE};
+                    bg.emit[pos] = make_int2(0, 0);
                     if (is_super(pos)) bg.sseg[pos] = Seg{A_NONE, A_NONE, 0u, A_NONE};
-                    bg.emit[pos] = make_int4(0, 0, 0, 0);
-                    if (first_of_pixel) bg.amap[((size_t)fs * g.H + y) * g.W + x] = pos;
                 }
-                first_of_pixel = false;
                 ++pos;
             }
         }
@@ -527,8 +511,8 @@ k_sort_scan(const uint4 *__restrict__ surv, int *__restrict__ surv_count, uint4 
 }
 
 struct EmitSet {
-    int4 *emit; int base, len;
-    __device__ __forceinline__ void operator()(uint32_t a, int pos) const { emit[a] = make_int4(base, pos, len, 0); }
+    int2 *emit; int slot1;
+    __device__ __forceinline__ void operator()(uint32_t a, int pos) const { emit[a] = make_int2(pos, slot1); }
 };
 
 // A3a step 5: the leader of every kept border tells the border's anchors where their segments go
@@ -542,9 +526,9 @@ k_assign(BorderGraph bg, const uint4 *__restrict__ sorted, const int *__restrict
         const int off = pts_off[(size_t)fs * g.surv_cap + i];
         if (off < 0) continue;
         const uint4 e = sorted[(size_t)fs * g.surv_cap + i];
-        const int base = fs * g.pts_cap + off, len = (int)e.y;
-        if (e.w) cycle_assign(SegLoad{bg.sseg}, EmitSet{bg.emit, base, len}, e.z, len, (int)bg.ssoff[e.z]);
-        else cycle_assign(seg_at, EmitSet{bg.emit, base, len}, e.z, len, (int)bg.minoff[e.z]);
+        const int slot1 = fs * g.surv_cap + i + 1, len = (int)e.y;
+        if (e.w) cycle_assign(SegLoad{bg.sseg}, EmitSet{bg.emit, slot1}, e.z, len, (int)bg.ssoff[e.z]);
+        else cycle_assign(seg_at, EmitSet{bg.emit, slot1}, e.z, len, (int)bg.minoff[e.z]);
     }
 }
 
@@ -557,15 +541,16 @@ k_assign_sub(BorderGraph bg)
     const SegLoad seg_at{bg.seg};
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (!is_super(i)) continue;
-        const int4 e = bg.emit[i];
-        if (e.z == 0) continue;
-        super_assign(seg_at, EmitSet{bg.emit, e.x, e.z}, i, e.y);
+        const int2 e = bg.emit[i];
+        if (e.y == 0) continue;
+        super_assign(seg_at, EmitSet{bg.emit, e.y}, i, e.x);
     }
 }
 
 // A3a step 6: every anchor of a kept border re-walks its segment and writes the points
 __global__ void __launch_bounds__(256)
-k_emit(const uint32_t *__restrict__ masks, BorderGraph bg, uint32_t *__restrict__ pts, const WalkTables *__restrict__ tables, DetGeom g)
+k_emit(const uint32_t *__restrict__ masks, BorderGraph bg, const uint4 *__restrict__ sorted, const int *__restrict__ pts_off,
+       uint32_t *__restrict__ pts, const WalkTables *__restrict__ tables, DetGeom g)
 {
     __shared__ __align__(16) uint16_t s_succ[4096];
     unsigned n = *bg.n_anchors;
@@ -573,11 +558,13 @@ k_emit(const uint32_t *__restrict__ masks, BorderGraph bg, uint32_t *__restrict_
     if (blockIdx.x * blockDim.x >= n) return;
     load_walk_tables(tables, s_succ, nullptr);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int4 e = bg.emit[i];
-        if (e.z == 0) continue;
+        const int2 e = bg.emit[i];
+        if (e.y == 0) continue;
         const uint2 a = bg.ast[i];
-        MaskView rd{masks + (size_t)(a.y >> 3) * g.mask_plane, g.PWW};
-        seg_emit(rd, s_succ, (int)(a.x & 0xFFFFu), (int)(a.x >> 16), (int)(a.y & 7u), (int)bg.seg[i].len, e.y, e.z, pts + e.x);
+        const int fs = (int)(a.y >> 3);
+        const int len = (int)__ldg(&sorted[e.y - 1].y), off = __ldg(&pts_off[e.y - 1]);
+        MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
+        seg_emit(rd, s_succ, (int)(a.x & 0xFFFFu), (int)(a.x >> 16), (int)(a.y & 7u), (int)bg.seg[i].len, e.x, len, pts + (size_t)fs * g.pts_cap + off);
     }
 }
 
@@ -776,12 +763,20 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
         for (int i = 0; i < 9; ++i) M[i] = __ldg(wM + ((size_t)f * ip.max_cand + w) * 9 + i);
         const int m0 = ip.cellSize / 2;
         int ls = 0, lq = 0;
-        for (int p = lane; p < S * S; p += 32) {
-            const int y = p / S, x = p - y * S;
-            const unsigned v = warp_sample(img, ip.W, ip.H, ip.pitch, M, x, y);
-            s_patch[wp][p] = (uint8_t)v;
-            atomicAdd(&s_hist[wp][v], 1);
-            if (x >= m0 && x < S - m0 && y >= m0 && y < S - m0) { ls += (int)v; lq += (int)(v * v); }
+#pragma unroll 2
+        for (int base = 0; base < S * S; base += 32) {
+            const int p = base + lane;
+            unsigned v = 256u;                                                 // sentinel for the lanes past the patch
+            if (p < S * S) {
+                const int y = p / S, x = p - y * S;
+                v = warp_sample(img, ip.W, ip.H, ip.pitch, M, x, y);
+                s_patch[wp][p] = (uint8_t)v;
+                if (x >= m0 && x < S - m0 && y >= m0 && y < S - m0) { ls += (int)v; lq += (int)(v * v); }
+            }
+            // warp-aggregated histogram: a marker patch has two dominant levels, so plain shared atomics serialise
+            const unsigned peers = __match_any_sync(FULL, v);
+            if (v < 256u && lane == __ffs(peers) - 1) s_hist[wp][v] += __popc(peers);
+            __syncwarp();
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { ls += __shfl_xor_sync(FULL, ls, o); lq += __shfl_xor_sync(FULL, lq, o); }
@@ -795,7 +790,10 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
             for (int k = 0; k < 8; ++k) {
                 const int i = lane * 8 + k, hv = s_hist[wp][i];
                 isum += i * hv; nzmask |= (hv != 0) << k;
-                s_q1[wp][i] = -1.0;
+                double p_i, ip_i;
+                otsu_bin_inputs(i, hv, S * S, p_i, ip_i);
+                s_q1[wp][i] = hv ? p_i : -1.0;                                  // empty bins outside [lo, hi] stay -1; inside, 0 is restored below
+                s_mu1[wp][i] = ip_i;
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) isum += __shfl_xor_sync(FULL, isum, o);
@@ -803,9 +801,11 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
             const int l_lo = __ffs(nzl) - 1, l_hi = 31 - __clz(nzl);
             const int lo = l_lo * 8 + __ffs(__shfl_sync(FULL, nzmask, l_lo)) - 1;
             const int hi = l_hi * 8 + 31 - __clz(__shfl_sync(FULL, nzmask, l_hi));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const int i = lane * 8 + k; if (i > lo && i < hi && s_q1[wp][i] < 0) s_q1[wp][i] = 0.0; }
             const double mu = otsu_mu(isum, S * S);
             __syncwarp();
-            if (lane == 0) otsu_chain(s_hist[wp], S * S, lo, hi, s_q1[wp], s_mu1[wp]);
+            if (lane == 0) otsu_chain(lo, hi, s_q1[wp], s_mu1[wp]);
             __syncwarp();
             double best = 0; int bi = 0;
 #pragma unroll

@@ -98,32 +98,47 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
         fs.members[i] = rank;       // temp: candidate i -> T position
     }
     ctx.sync();
+    // shared-memory staging (device): T-order quads, per-candidate (4 * centroid, threshold), then the matrix
+    const int wpr = (n + 31) >> 5;
+    float *tqs = nullptr, *cent = nullptr;
+    uint32_t *Msm = smemM;
+    int Mwords = smemM_words;
+    if (smemM && 11 * n + 6 * fp.max_cand <= smemM_words) {
+        tqs = reinterpret_cast<float *>(smemM); cent = tqs + 8 * n;
+        Msm = smemM + 11 * n; Mwords = smemM_words - 11 * n;
+    }
     for (int i = tid; i < n; i += nt) {
         const int r = fs.members[i];
-        for (int k = 0; k < 8; ++k) fs.tq[(size_t)r * 8 + k] = fs.cq[(size_t)i * 8 + k];
+        for (int k = 0; k < 8; ++k) { const float v = fs.cq[(size_t)i * 8 + k]; fs.tq[(size_t)r * 8 + k] = v; if (tqs) tqs[r * 8 + k] = v; }
         fs.gfill[r] = i;            // temp: T position -> candidate index
     }
     ctx.sync();
-    for (int i = tid; i < n; i += nt) { fs.gid[i] = -1; fs.sel[i] = 1; }
-    ctx.sync();
-    for (int i = tid; i < n; i += nt) fs.tper[i] = quad_perimeter(fs.tq + (size_t)i * 8);
+    const float *tq = tqs ? tqs : fs.tq;
+    for (int i = tid; i < n; i += nt) {
+        fs.gid[i] = -1; fs.sel[i] = 1;
+        const float *a = tq + (size_t)i * 8;
+        const float per = quad_perimeter(a);
+        fs.tper[i] = per;
+        if (cent) { cent[3 * i] = (a[0] + a[2]) + (a[4] + a[6]); cent[3 * i + 1] = (a[1] + a[3]) + (a[5] + a[7]); cent[3 * i + 2] = f_mul(per, fp.minMarkerDistanceRate); }
+    }
     ctx.sync();
     // ---- 3. closeness bit matrix: bit j of row i (j > i) iff avgDist(T[i],T[j]) < perimeter_j * rate ----
-    const int wpr = (n + 31) >> 5;
-    uint32_t *M = ((long long)n * wpr <= (long long)smemM_words) ? smemM : fs.closeM;
+    uint32_t *M = ((long long)n * wpr <= (long long)Mwords) ? Msm : fs.closeM;
     for (int t = tid; t < n * wpr; t += nt) {
         const int i = t / wpr, w = t - i * wpr;
         uint32_t bits = 0;
         if (w * 32 + 31 > i) {
-            const float *a = fs.tq + (size_t)i * 8;
+            const float *a = tq + (size_t)i * 8;
             const float acx = (a[0] + a[2]) + (a[4] + a[6]), acy = (a[1] + a[3]) + (a[5] + a[7]);   // 4 * centroid
             for (int b = 0; b < 32; ++b) {
                 const int j = w * 32 + b;
                 if (j <= i || j >= n) continue;
-                const float *q = fs.tq + (size_t)j * 8;
-                const float thr = f_mul(fs.tper[j], fp.minMarkerDistanceRate);
+                const float *q = tq + (size_t)j * 8;
+                float qcx, qcy, thr;
+                if (cent) { qcx = cent[3 * j]; qcy = cent[3 * j + 1]; thr = cent[3 * j + 2]; }
+                else { qcx = (q[0] + q[2]) + (q[4] + q[6]); qcy = (q[1] + q[3]) + (q[5] + q[7]); thr = f_mul(fs.tper[j], fp.minMarkerDistanceRate); }
                 // |centroid_a - centroid_b| <= avgDist: cheap exact-safe rejection (integer coordinates)
-                const float dcx = (acx - ((q[0] + q[2]) + (q[4] + q[6]))) * 0.25f, dcy = (acy - ((q[1] + q[3]) + (q[5] + q[7]))) * 0.25f;
+                const float dcx = (acx - qcx) * 0.25f, dcy = (acy - qcy) * 0.25f;
                 if (dcx * dcx + dcy * dcy > thr * thr * 1.01f + 1.0f) continue;
                 if (quad_avg_distance(a, q) < thr) bits |= 1u << b;
             }
@@ -198,8 +213,8 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
         int nc = 0;
         for (int k = b + 1; k < e; ++k) {
             const int id = fs.members[k];
-            const float dist = quad_avg_distance(fs.tq + (size_t)id * 8, fs.tq + (size_t)cur * 8);
-            const float ms = quad_module_size(fs.tq + (size_t)id * 8, fp.markerSize, fp.borderBits);
+            const float dist = quad_avg_distance(tq + (size_t)id * 8, tq + (size_t)cur * 8);
+            const float ms = quad_module_size(tq + (size_t)id * 8, fp.markerSize, fp.borderBits);
             if (dist > f_mul(fp.minGroupDistance, ms)) { cur = id; fs.closeIdx[b + nc] = id; ++nc; }
         }
         fs.closeCnt[g] = nc;
@@ -207,15 +222,15 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
     ctx.sync();
     // the closeness matrix is dead: its shared-memory region now holds the selected-candidate arrays
     const int mc = fp.max_cand;
-    const bool sm6 = smemM && smemM_words >= 6 * mc;
-    int32_t *S = sm6 ? (int32_t *)smemM : fs.S, *selGroup = sm6 ? (int32_t *)smemM + mc : fs.selGroup;
-    int32_t *parent = sm6 ? (int32_t *)smemM + 2 * mc : fs.parent, *depth = sm6 ? (int32_t *)smemM + 3 * mc : fs.depth;
-    int32_t *closeStart = sm6 ? (int32_t *)smemM + 4 * mc : fs.closeStart, *closeNum = sm6 ? (int32_t *)smemM + 5 * mc : fs.closeNum;
+    const bool sm6 = Msm && Mwords >= 6 * mc;
+    int32_t *S = sm6 ? (int32_t *)Msm : fs.S, *selGroup = sm6 ? (int32_t *)Msm + mc : fs.selGroup;
+    int32_t *parent = sm6 ? (int32_t *)Msm + 2 * mc : fs.parent, *depth = sm6 ? (int32_t *)Msm + 3 * mc : fs.depth;
+    int32_t *closeStart = sm6 ? (int32_t *)Msm + 4 * mc : fs.closeStart, *closeNum = sm6 ? (int32_t *)Msm + 5 * mc : fs.closeNum;
     // ---- 6. selected candidates (minus the ones near the image border), in T order ----
     int nS = 0;
     for (int base = 0; base < n; base += nt) {
         const int i = base + tid;
-        const int flag = (i < n) && fs.sel[i] && !quad_near_border(fs.tq + (size_t)i * 8, fp.W, fp.H, fp.minDistanceToBorder);
+        const int flag = (i < n) && fs.sel[i] && !quad_near_border(tq + (size_t)i * 8, fp.W, fp.H, fp.minDistanceToBorder);
         int total;
         const int pos = ctx.exclusive_scan(flag, total);
         if (flag) { S[nS + pos] = i; selGroup[nS + pos] = fs.gid[i]; }
@@ -225,9 +240,9 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
     // ---- 7. containment hierarchy ----
     for (int i = tid; i < nS; i += nt) {
         int pr = -1;
-        const float *a = fs.tq + (size_t)S[i] * 8;
+        const float *a = tq + (size_t)S[i] * 8;
         for (int j = i - 1; j >= 0; --j)
-            if (quad_inside_quad(a, fs.tq + (size_t)S[j] * 8)) { pr = j; break; }
+            if (quad_inside_quad(a, tq + (size_t)S[j] * 8)) { pr = j; break; }
         parent[i] = pr;
         depth[i] = 0;
     }
@@ -262,11 +277,11 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
         }
     const int nw = fs.counters[FC_NWORK];
     for (int v = tid; v < nS; v += nt) {
-        for (int k = 0; k < 8; ++k) fs.wq[(size_t)v * 8 + k] = fs.tq[(size_t)S[v] * 8 + k];
+        for (int k = 0; k < 8; ++k) fs.wq[(size_t)v * 8 + k] = tq[(size_t)S[v] * 8 + k];
         const int g = selGroup[v];
         for (int c = 0; c < closeNum[v]; ++c) {
             const int id = fs.closeIdx[fs.gstart[g] + c];
-            for (int k = 0; k < 8; ++k) fs.wq[(size_t)(closeStart[v] + c) * 8 + k] = fs.tq[(size_t)id * 8 + k];
+            for (int k = 0; k < 8; ++k) fs.wq[(size_t)(closeStart[v] + c) * 8 + k] = tq[(size_t)id * 8 + k];
         }
     }
     for (int w = tid; w < nw; w += nt) fs.wres[w] = 0;

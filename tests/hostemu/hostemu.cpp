@@ -103,19 +103,27 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
                 const uint32_t *row = pl + (size_t)(y + 1) * PWW + wx + 1;
                 const uint32_t m = row[0];
                 if (!m) continue;
-                uint32_t iso;
-                uint32_t bp = anchor_pixel_candidates(m, row[-1], row[1], row[-PWW], row[-PWW - 1], row[-PWW + 1], row[PWW], row[PWW - 1], row[PWW + 1], y, Rm, iso);
+                // word-parallel enumeration (k_anchors) ...
+                uint32_t A[4], hi[4], iso;
+                const uint32_t cols = 0xFFFFFFFFu / ((Rm >= 31) ? 0xFFFFFFFFu : ((2u << Rm) - 1u));
+                anchor_words(m, row[-1], row[1], row[-PWW], row[-PWW - 1], row[-PWW + 1], row[PWW], row[PWW - 1], row[PWW + 1], !(y & Rm), cols, A, hi, iso);
                 ncont += __builtin_popcount(iso);
-                for (; bp; bp &= bp - 1) {
-                    const int b = __builtin_ffs(bp) - 1, x = wx * 32 + b;
-                    const unsigned w9 = win3_words(row[-PWW - 1], row[-PWW], row[-PWW + 1], b) | (win3_words(row[-1], m, row[1], b) << 3) |
-                                        (win3_words(row[PWW - 1], row[PWW], row[PWW + 1], b) << 6);
-                    if (w9 != mv.win9(x, y)) return -100;
-                    const uint32_t p = wt.pix[w9];
+                // ... cross-checked against the per-pixel window tables the walkers use
+                uint32_t iso2;
+                const uint32_t bp = anchor_pixel_candidates(m, row[-1], row[1], row[-PWW], row[-PWW - 1], row[-PWW + 1], row[PWW], row[PWW - 1], row[PWW + 1], y, Rm, iso2);
+                if (iso2 != iso || ((A[0] | A[1] | A[2] | A[3]) & ~bp)) return -108;
+                for (int b = 0; b < 32; ++b) {
+                    const int x = wx * 32 + b;
+                    if (x >= W) break;
+                    const unsigned w9 = mv.win9(x, y);
+                    const uint32_t p = ((w9 >> 4) & 1u) ? wt.pix[w9] : 0u;
                     bool first = true;
                     for (int k = 0; k < 4; ++k) {
                         const unsigned e = (p >> (8 * k)) & 0xFFu;
-                        if (!((e & 0x80u) && is_anchor((e << 2) & (ST_ROW | ST_COL | ST_UNC), x, y, Rm))) continue;
+                        const bool anchor = (e & 0x80u) && is_anchor((e << 2) & (ST_ROW | ST_COL | ST_UNC), x, y, Rm);
+                        if (anchor != (bool)((A[k] >> b) & 1u)) return -109;
+                        if (!anchor) continue;
+                        if ((int)(e & 7u) != ((2 * k + (((hi[k] >> b) & 1u) ? 7 : 6)) & 7)) return -110;
                         if (first) amap[(size_t)y * W + x] = (uint32_t)ax.size();
                         first = false;
                         ax.push_back(x); ay.push_back(y); as_.push_back(e & 7u);
