@@ -304,7 +304,7 @@ static int create_impl(b2a_detector *d)
     TRY(dev_alloc(d, &fs.gid, BM)); TRY(dev_alloc(d, &fs.sel, BM)); TRY(dev_alloc(d, &fs.gstart, (size_t)B * (MC + 1))); TRY(dev_alloc(d, &fs.gfill, BM));
     TRY(dev_alloc(d, &fs.members, BM)); TRY(dev_alloc(d, &fs.closeIdx, BM)); TRY(dev_alloc(d, &fs.closeCnt, BM));
     TRY(dev_alloc(d, &fs.S, BM)); TRY(dev_alloc(d, &fs.parent, BM)); TRY(dev_alloc(d, &fs.depth, BM)); TRY(dev_alloc(d, &fs.selGroup, BM));
-    TRY(dev_alloc(d, &fs.closeM, BM * ((MC + 31) / 32)));
+    TRY(dev_alloc(d, &fs.closeM, BM * 2 * ((MC + 31) / 32)));       // M and its transpose
     TRY(dev_alloc(d, &fs.wq, BM * 8)); TRY(dev_alloc(d, &fs.wres, BM)); TRY(dev_alloc(d, &fs.closeStart, BM)); TRY(dev_alloc(d, &fs.closeNum, BM));
     TRY(dev_alloc(d, &fs.counters, (size_t)B * 8));
     TRY(dev_alloc(d, &d->d_wM, BM * 9));
@@ -318,6 +318,7 @@ static int create_impl(b2a_detector *d)
     TRY(pin_alloc(d, &d->h_corners, BK * 8)); TRY(pin_alloc(d, &d->h_ids, BK)); TRY(pin_alloc(d, &d->h_rejected, BK * 8));
     TRY(pin_alloc(d, &d->h_rvecs, BK * 3)); TRY(pin_alloc(d, &d->h_tvecs, BK * 3));
     CU(cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_identify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)identify_smem_bytes(ID_MAX_S)));
     CU(cudaFuncSetAttribute(k_threshold3<1, 6, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3_SMEM));
     CU(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (int)sizeof(int32_t) * d->max_cand));
     CU(cudaStreamSynchronize(d->stream));
@@ -453,7 +454,7 @@ static FrameScratch offset_scratch(const FrameScratch &b, size_t f, size_t mc)
     s.cq += o * 8; s.clen += o; s.tq += o * 8; s.tper += o; s.gid += o; s.sel += o;
     s.gstart += f * (mc + 1); s.gfill += o; s.members += o; s.closeIdx += o; s.closeCnt += o;
     s.S += o; s.parent += o; s.depth += o; s.selGroup += o;
-    s.closeM += o * ((mc + 31) / 32);
+    s.closeM += o * 2 * ((mc + 31) / 32);
     s.wq += o * 8; s.wres += o; s.closeStart += o; s.closeNum += o;
     s.counters += f * 8;
     return s;
@@ -561,11 +562,26 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
     fa.fo0.status = d->d_status + b0;
     fa.surv_count = d->d_surv_count + fs0; fa.quad_ok = d->d_quad_ok + fs0 * g.surv_cap; fa.quad_xy = d->d_quad_xy + fs0 * g.surv_cap * 8;
     fa.quad_len = d->d_quad_len + fs0 * g.surv_cap;
+    fa.marks = nullptr;
+    static long long *dbg_marks = nullptr;
+    if (std::getenv("B2A_GROUP_MARKS")) {
+        if (!dbg_marks) { cudaMalloc(&dbg_marks, (size_t)d->cfg.max_batch * 32 * sizeof(long long)); }
+        cudaMemsetAsync(dbg_marks, 0, (size_t)d->cfg.max_batch * 32 * sizeof(long long), st);
+        fa.marks = dbg_marks + (size_t)b0 * 32;
+    }
     const FrameParams fp = frame_params(d, g);
     stage_mark(d, s, ST_GROUP);
     const int smem_words = 50 * 1024;                       // 200 KB: per-candidate arrays + closeness matrix
-    k_group<<<nb, 256, smem_words * sizeof(uint32_t), st>>>(fa, fp, smem_words);
+    k_group<<<nb, 1024, smem_words * sizeof(uint32_t), st>>>(fa, fp, smem_words);
     d->launches++;
+    if (fa.marks && s.sb == 0) {
+        long long hm[32];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hm, fa.marks, sizeof(hm), cudaMemcpyDeviceToHost);
+        std::fprintf(stderr, "k_group frame %d sync-to-sync cycles:", b0);
+        for (int i = 1; i < 32 && hm[i]; ++i) std::fprintf(stderr, hm[i] < 0 ? " (%lld)" : " %lld", std::llabs(hm[i]) - std::llabs(hm[i - 1]));
+        std::fprintf(stderr, "\n");
+    }
     if (stop_after_group) return launch_err("k_group");
     stage_mark(d, s, ST_IDENT);
     IdentParams ip;
@@ -574,11 +590,36 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
     ip.nMarkers = d->dict.nMarkers; ip.maxCorr = (int)((double)d->dict.maxCorrectionBits * d->prm.errorCorrectionRate);
     ip.maxBorderErr = (int)(d->dict.markerSize * d->dict.markerSize * d->prm.maxErroneousBitsInBorderRate);
     ip.minOtsuStdDev = d->prm.minOtsuStdDev; ip.W = g.W; ip.H = g.H; ip.pitch = s.pitch; ip.frame_stride = s.frame_stride; ip.max_cand = d->max_cand;
+    ip.marks = nullptr;
+    static long long *id_marks = nullptr;
+    if (std::getenv("B2A_IDENT_MARKS") && s.sb == 0) {
+        const size_t nrec = 16 + (size_t)d->cfg.max_batch * 128 * 3;
+        if (!id_marks) cudaMalloc(&id_marks, nrec * sizeof(long long));
+        cudaMemsetAsync(id_marks, 0, nrec * sizeof(long long), st);
+        ip.marks = id_marks;
+    }
     double *wM = d->d_wM + (size_t)b0 * d->max_cand * 9;
     k_homography<<<dim3(4, nb), 64, 0, st>>>(fa, wM, (ip.markerSize + 2 * ip.borderBits) * ip.cellSize, d->max_cand);
     d->launches++;
-    k_identify<<<dim3(32, nb), ID_THREADS, 0, st>>>(s.gray, d->d_dict, wM, fa, ip);
+    k_identify<<<dim3(32, nb), ID_THREADS, identify_smem_bytes((ip.markerSize + 2 * ip.borderBits) * ip.cellSize), st>>>(s.gray, d->d_dict, wM, fa, ip);
     d->launches++;
+    if (ip.marks) {
+        long long hm[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hm, ip.marks, sizeof(hm), cudaMemcpyDeviceToHost);
+        std::fprintf(stderr, "k_identify item 0 phase cycles (sample, hist, otsu-prep, chain, sigma, rest):");
+        for (int i = 1; i < 16 && hm[i]; ++i) std::fprintf(stderr, " %lld", hm[i] - hm[i - 1]);
+        std::fprintf(stderr, "\n");
+        std::vector<long long> rec((size_t)nb * 128 * 3);
+        cudaMemcpy(rec.data(), ip.marks + 16, rec.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        long long t0 = 0, t1 = 0; int cnt = 0; std::vector<long long> dur;
+        for (size_t i = 0; i < rec.size(); i += 3) if (rec[i]) { if (!t0 || rec[i] < t0) t0 = rec[i]; if (rec[i + 1] > t1) t1 = rec[i + 1]; dur.push_back(rec[i + 1] - rec[i]); ++cnt; }
+        std::sort(dur.begin(), dur.end());
+        long long latest_start = 0;
+        for (size_t i = 0; i < rec.size(); i += 3) if (rec[i] && rec[i] - t0 > latest_start) latest_start = rec[i] - t0;
+        if (cnt) std::fprintf(stderr, "k_identify items %d: span %lld ns, item ns min %lld median %lld p90 %lld max %lld, latest start +%lld ns\n", cnt, t1 - t0, dur[0], dur[cnt / 2],
+                              dur[cnt * 9 / 10], dur[cnt - 1], latest_start);
+    }
     stage_mark(d, s, ST_FINAL);
     k_finalize<<<nb, 128, 8 * sizeof(int32_t) * d->max_cand, st>>>(fa, fp);
     d->launches++;

@@ -677,6 +677,23 @@ B2A_HD double d_sub(double a, double b)
     return a - b;
 #endif
 }
+// correctly rounded reciprocal (== 1.0 / a in IEEE arithmetic, cheaper than a general division on the device)
+B2A_HD double d_rcp(double a)
+{
+#if defined(__CUDA_ARCH__)
+    return __drcp_rn(a);
+#else
+    return 1.0 / a;
+#endif
+}
+B2A_HD double d_fma(double a, double b, double c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return fma(a, b, c);
+#endif
+}
 B2A_HD double d_div(double a, double b)
 {
 #if defined(__CUDA_ARCH__)
@@ -748,52 +765,78 @@ B2A_HD void perspective_inverse(const float *src, int S, double *M)
     M[8] = d_mul(d_sub(d_mul(a0, a4), d_mul(a1, a3)), det);
 }
 // source pixel of destination (x,y) under INTER_NEAREST (round half to even); returns 0 outside
-B2A_HD unsigned warp_sample(const uint8_t *__restrict__ gray, int W, int H, size_t pitch, const double *M, int x, int y)
+// offset of the source pixel inside the frame, or -1 when it falls outside (INTER_NEAREST reads 0 there)
+B2A_HD long long warp_source(int W, int H, size_t pitch, const double *M, int x, int y)
 {
     const double X0 = d_add(d_mul(M[1], (double)y), M[2]);
     const double Y0 = d_add(d_mul(M[4], (double)y), M[5]);
     const double W0 = d_add(d_mul(M[7], (double)y), M[8]);
     double w = d_add(W0, d_mul(M[6], (double)x));
-    w = (w != 0.0) ? d_div(1.0, w) : 0.0;
+    w = (w != 0.0) ? d_rcp(w) : 0.0;
     double fx = d_mul(d_add(X0, d_mul(M[0], (double)x)), w);
     double fy = d_mul(d_add(Y0, d_mul(M[3], (double)x)), w);
     fx = fx < -2147483648.0 ? -2147483648.0 : (fx > 2147483647.0 ? 2147483647.0 : fx);
     fy = fy < -2147483648.0 ? -2147483648.0 : (fy > 2147483647.0 ? 2147483647.0 : fy);
     const long long X = (long long)rint(fx), Y = (long long)rint(fy);
-    return (X >= 0 && X < W && Y >= 0 && Y < H) ? gray[(size_t)Y * pitch + (size_t)X] : 0u;
+    return (X >= 0 && X < W && Y >= 0 && Y < H) ? (long long)((size_t)Y * pitch + (size_t)X) : -1;
 }
-// OpenCV's Otsu between-class-variance scan over a 256-bin histogram of n samples, cut in two so
-// that only the loop-carried recurrence on (q1, mu1) is sequential:
-//   otsu_chain  : one lane; per bin q1s[i] = q1 after the bin (or -1 where OpenCV `continue`s), mu1s[i]
-//   otsu_sigma  : any lane; the between-class variance of bin i from (mu, q1s[i], mu1s[i])
-// The threshold is the first bin (strict '>') with the largest sigma.
-// Bins below the first and above the last non-empty bin cannot change the recurrence (mu1 = q1 = 0
-// before; OpenCV `continue`s after), and sum(i * h[i]) is an exact integer, so the chain runs over
-// [lo, hi] only and the caller pre-fills q1s with -1 outside.
-B2A_HD double otsu_mu(long long isum, int n) { return d_mul((double)isum, d_div(1.0, (double)n)); }
-// in: q1s[i] = p_i = h[i] / n, mu1s[i] = i * p_i for lo <= i <= hi;  out: q1s[i] = q1 (or -1), mu1s[i] = mu1
-B2A_HD void otsu_chain(int lo, int hi, double *q1s, double *mu1s)
+B2A_HD unsigned warp_sample(const uint8_t *__restrict__ gray, int W, int H, size_t pitch, const double *M, int x, int y)
 {
-    double mu1 = 0, q1 = 0;
-    for (int i = lo; i <= hi; ++i) {
-        const double p_i = q1s[i], ip_i = mu1s[i];
-        mu1 = d_mul(mu1, q1);
-        q1 = d_add(q1, p_i);
-        const double q2 = d_sub(1.0, q1);
-        const double mn = q1 < q2 ? q1 : q2, mx = q1 > q2 ? q1 : q2;
-        if (mn < (double)FLT_EPSILON || mx > 1.0 - (double)FLT_EPSILON) { q1s[i] = -1.0; continue; }
-        mu1 = d_div(d_add(mu1, ip_i), q1);
-        q1s[i] = q1; mu1s[i] = mu1;
-    }
+    const long long o = warp_source(W, H, pitch, M, x, y);
+    return o >= 0 ? gray[o] : 0u;
 }
+// OpenCV's Otsu between-class-variance scan over a 256-bin histogram of n samples (getThreshVal_Otsu_8u):
+//     mu = sum(i h[i]) / n;  per bin:  p = h[i] / n;  mu1 *= q1;  q1 += p;  q2 = 1 - q1;
+//     if (min(q1,q2) < FLT_EPSILON || max(q1,q2) > 1 - FLT_EPSILON) continue;
+//     mu1 = (mu1 + i p) / q1;  mu2 = (mu - q1 mu1) / q2;  sigma = q1 q2 (mu1 - mu2)^2;  first strict maximum wins
+// restated so that the results are bit-identical but the loop-carried part is as short as possible:
+//   * bins below the first / above the last non-empty bin cannot change anything (mu1 = q1 = 0 before; every
+//     later bin `continue`s), and sum(i h[i]) is an exact integer  ->  only [lo, hi] is walked;
+//   * q1 does not depend on mu1: a first one-lane pass leaves the running sums (otsu_prefix);
+//   * validity, 1 - q1 and the correctly rounded reciprocal y = RN(1 / q1) are per-bin work for any lane (otsu_bin);
+//   * the mu1 recurrence (otsu_chain) then needs no division: with y = RN(1/b), q = RN(a y), r = a - b q (exact, fma),
+//     RN(q + r y) is the correctly rounded quotient a / b (Markstein's theorem; no overflow / underflow here);
+//   * the variances are again per-bin work (otsu_sigma).
+B2A_HD double otsu_mu(long long isum, int n) { return d_mul((double)isum, d_div(1.0, (double)n)); }
 B2A_HD void otsu_bin_inputs(int i, int hv, int n, double &p_i, double &ip_i)
 {
     p_i = d_mul((double)hv, d_div(1.0, (double)n));
     ip_i = d_mul((double)i, p_i);
 }
-B2A_HD double otsu_sigma(double mu, double q1, double mu1)
+// in: q1s[i] = p_i for lo <= i <= hi;  out: q1s[i] = q1 after bin i
+B2A_HD void otsu_prefix(int lo, int hi, double *q1s)
 {
-    if (q1 < 0) return 0.0;                      // never beats max_sigma's initial 0 under strict '>'
+    double q1 = 0;
+    for (int i = lo; i <= hi; ++i) { q1 = d_add(q1, q1s[i]); q1s[i] = q1; }
+}
+// per bin: y = RN(1 / q1), or -1 where OpenCV skips the bin
+B2A_HD double otsu_bin(double q1)
+{
+    const double q2 = d_sub(1.0, q1);
+    const double mn = q1 < q2 ? q1 : q2, mx = q1 > q2 ? q1 : q2;
+    if (mn < (double)FLT_EPSILON || mx > 1.0 - (double)FLT_EPSILON) return -1.0;
+    return d_rcp(q1);
+}
+// in: q1s = running sums, ys = otsu_bin(q1s), mu1s[i] = i * p_i;  out: mu1s[i] = mu1 after bin i (valid bins)
+B2A_HD void otsu_chain(int lo, int hi, const double *q1s, const double *ys, double *mu1s)
+{
+    double mu1 = 0, q1prev = 0;
+    for (int i = lo; i <= hi; ++i) {
+        const double b = q1s[i], y = ys[i];
+        const double t = d_mul(mu1, q1prev);
+        q1prev = b;
+        if (y < 0) { mu1 = t; continue; }
+        const double a = d_add(t, mu1s[i]);
+        const double q = d_mul(a, y);
+        const double r = d_fma(-b, q, a);
+        mu1 = d_fma(r, y, q);
+        mu1s[i] = mu1;
+    }
+}
+// variance of bin i (0 for skipped bins: never beats max_sigma's initial 0 under strict '>')
+B2A_HD double otsu_sigma(double mu, double q1, double y, double mu1)
+{
+    if (y < 0) return 0.0;
     const double q2 = d_sub(1.0, q1);
     const double mu2 = d_div(d_sub(mu, d_mul(q1, mu1)), q2);
     const double dm = d_sub(mu1, mu2);
@@ -801,17 +844,42 @@ B2A_HD double otsu_sigma(double mu, double q1, double mu1)
 }
 B2A_HD int otsu_threshold(const int *h, int n)
 {
-    double q1s[256], mu1s[256];
+    double q1s[256], ys[256], mu1s[256];
     long long isum = 0;
     int lo = 256, hi = -1;
-    for (int i = 0; i < 256; ++i) { q1s[i] = -1.0; mu1s[i] = 0.0; isum += (long long)i * h[i]; if (h[i]) { if (lo == 256) lo = i; hi = i; } }
+    for (int i = 0; i < 256; ++i) { ys[i] = -1.0; q1s[i] = 0.0; mu1s[i] = 0.0; isum += (long long)i * h[i]; if (h[i]) { if (lo == 256) lo = i; hi = i; } }
     const double mu = otsu_mu(isum, n);
     for (int i = lo; i <= hi; ++i) otsu_bin_inputs(i, h[i], n, q1s[i], mu1s[i]);
-    otsu_chain(lo, hi, q1s, mu1s);
+    otsu_prefix(lo, hi, q1s);
+    for (int i = lo; i <= hi; ++i) ys[i] = otsu_bin(q1s[i]);
+    otsu_chain(lo, hi, q1s, ys, mu1s);
     double max_sigma = 0;
     int max_val = 0;
     for (int i = 0; i < 256; ++i) {
-        const double sigma = otsu_sigma(mu, q1s[i], q1s[i] < 0 ? 0.0 : mu1s[i]);
+        const double sigma = otsu_sigma(mu, q1s[i], ys[i], mu1s[i]);
+        if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+    }
+    return max_val;
+}
+// the textbook loop (test reference for the restatement above)
+B2A_HD int otsu_threshold_sequential(const int *h, int n)
+{
+    double mu = 0, scale = d_div(1.0, (double)n);
+    for (int i = 0; i < 256; ++i) mu = d_add(mu, d_mul((double)i, (double)h[i]));
+    mu = d_mul(mu, scale);
+    double mu1 = 0, q1 = 0, max_sigma = 0;
+    int max_val = 0;
+    for (int i = 0; i < 256; ++i) {
+        const double p_i = d_mul((double)h[i], scale);
+        mu1 = d_mul(mu1, q1);
+        q1 = d_add(q1, p_i);
+        const double q2 = d_sub(1.0, q1);
+        const double mn = q1 < q2 ? q1 : q2, mx = q1 > q2 ? q1 : q2;
+        if (mn < (double)FLT_EPSILON || mx > 1.0 - (double)FLT_EPSILON) continue;
+        mu1 = d_div(d_add(mu1, d_mul((double)i, p_i)), q1);
+        const double mu2 = d_div(d_sub(mu, d_mul(q1, mu1)), q2);
+        const double dm = d_sub(mu1, mu2);
+        const double sigma = d_mul(d_mul(d_mul(q1, q2), dm), dm);
         if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
     }
     return max_val;

@@ -616,9 +616,23 @@ __global__ void k_approx(const uint4 *__restrict__ sorted, const int *__restrict
 // ---------------------------------------------------------------------------------------------
 struct BlockCtx {
     int *s_warp;   // [33] shared scratch
+    long long *marks = nullptr;   // optional (debug): clock64 of thread 0 after every sync()
+    mutable int nmark = 0;
     __device__ __forceinline__ int tid() const { return threadIdx.x; }
     __device__ __forceinline__ int nthreads() const { return blockDim.x; }
-    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ void sync() const
+    {
+        __syncthreads();
+        if (marks && threadIdx.x == 0 && nmark < 32) marks[nmark++] = clock64();
+    }
+    __device__ __forceinline__ void mark() const { if (marks && threadIdx.x == 0 && nmark < 32) marks[nmark++] = -clock64(); }
+    __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+    __device__ __forceinline__ int lanes() const { return 32; }
+    __device__ __forceinline__ int warp() const { return threadIdx.x >> 5; }
+    __device__ __forceinline__ int warps() const { return blockDim.x >> 5; }
+    __device__ __forceinline__ uint32_t ballot(bool p) const { return __ballot_sync(0xFFFFFFFFu, p); }
+    __device__ __forceinline__ uint32_t warp_or(uint32_t v) const { return __reduce_or_sync(0xFFFFFFFFu, v); }
+    __device__ __forceinline__ void atomic_or(uint32_t *p, uint32_t v) const { atomicOr(p, v); }
     __device__ __forceinline__ int exclusive_scan(int flag, int &total) const
     {
         const unsigned m = __ballot_sync(0xFFFFFFFFu, flag != 0);
@@ -640,6 +654,7 @@ struct FrameArrays {             // device base pointers; frame f uses offset f 
     const uint8_t *quad_ok;      // [B*nScales*surv_cap]
     const int32_t *quad_xy;
     const int32_t *quad_len;
+    long long *marks;            // debug: per frame 32 sync timestamps of k_group (null = off)
 };
 
 __device__ __forceinline__ FrameScratch frame_scratch(const FrameScratch &b, int f, int mc)
@@ -649,7 +664,7 @@ __device__ __forceinline__ FrameScratch frame_scratch(const FrameScratch &b, int
     s.cq += o * 8; s.clen += o; s.tq += o * 8; s.tper += o; s.gid += o; s.sel += o;
     s.gstart += (size_t)f * (mc + 1); s.gfill += o; s.members += o; s.closeIdx += o; s.closeCnt += o;
     s.S += o; s.parent += o; s.depth += o; s.selGroup += o;
-    s.closeM += o * (size_t)((mc + 31) / 32);
+    s.closeM += o * 2 * (size_t)((mc + 31) / 32);
     s.wq += o * 8; s.wres += o; s.closeStart += o; s.closeNum += o;
     s.counters += (size_t)f * 8;
     return s;
@@ -658,13 +673,14 @@ __device__ __forceinline__ FrameScratch frame_scratch(const FrameScratch &b, int
 // dynamic shared memory of k_group: 8 per-candidate arrays (gid, sel, gstart, gfill, members,
 // closeIdx, closeCnt, tper) that the sequential grouping section hammers, then the closeness
 // bit matrix in whatever is left (global fallback when it does not fit)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_group(FrameArrays fa, FrameParams fp, int smem_words)
 {
     extern __shared__ uint32_t s_dyn[];
     __shared__ int s_warp[33];
     const int f = blockIdx.x;
     BlockCtx ctx{s_warp};
+    if (fa.marks) { ctx.marks = fa.marks + (size_t)f * 32; if (threadIdx.x == 0) ctx.marks[ctx.nmark++] = clock64(); }
     FrameScratch fs = frame_scratch(fa.fs0, f, fp.max_cand);
     const int mc1 = fp.max_cand + 1;
     int32_t *base = reinterpret_cast<int32_t *>(s_dyn);
@@ -715,6 +731,7 @@ struct IdentParams {
     int W, H;
     size_t pitch, frame_stride;
     int max_cand;
+    long long *marks;            // debug: clock64 after each phase of work item 0 of frame 0 (null = off)
 };
 
 // A7 step 1: the inverse perspective map of every work item, one thread each (cv2's 8x8 LU lives in
@@ -735,6 +752,7 @@ k_homography(FrameArrays fa, double *__restrict__ wM, int S, int max_cand)
 constexpr int ID_WARPS = 4;         // work items in flight per CTA (one warp each)
 constexpr int ID_THREADS = ID_WARPS * 32;
 constexpr int ID_MAX_S = 9 * 8;     // (7 + 2) cells * up to 8 px
+inline size_t identify_smem_bytes(int S) { return (size_t)ID_WARPS * (3 * 256 * sizeof(double) + 256 * sizeof(int) + (size_t)((S * S + 15) & ~15) + 96); }
 
 // A7 step 2.  One WARP per work item: the sequential pieces (the Otsu recurrence, the border
 // check) run on lane 0 while the other warps of the SM work on other candidates; sampling, the
@@ -742,11 +760,14 @@ constexpr int ID_MAX_S = 9 * 8;     // (7 + 2) cells * up to 8 px
 __global__ void __launch_bounds__(ID_THREADS)
 k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restrict__ dict, const double *__restrict__ wM, FrameArrays fa, IdentParams ip)
 {
-    __shared__ double s_q1[ID_WARPS][256], s_mu1[ID_WARPS][256];
-    __shared__ __align__(16) uint8_t s_patch[ID_WARPS][ID_MAX_S * ID_MAX_S];
-    __shared__ int s_hist[ID_WARPS][256];
-    __shared__ uint8_t s_bits[ID_WARPS][96];
-
+    // dynamic shared memory, per warp: q1 / mu1 / y [256] f64, histogram [256] i32, patch [S*S rounded up to 16] u8, bits [96] u8
+    extern __shared__ __align__(16) uint8_t id_smem[];
+    const int patch_bytes = (((ip.markerSize + 2 * ip.borderBits) * ip.cellSize) * ((ip.markerSize + 2 * ip.borderBits) * ip.cellSize) + 15) & ~15;
+    const size_t per_warp = 3 * 256 * sizeof(double) + 256 * sizeof(int) + (size_t)patch_bytes + 96;
+    uint8_t *wbase = id_smem + (size_t)(threadIdx.x >> 5) * per_warp;
+    double *const q1w = reinterpret_cast<double *>(wbase), *const mu1w = q1w + 256, *const yw = mu1w + 256;
+    int *const histw = reinterpret_cast<int *>(yw + 256);
+    uint8_t *const patchw = reinterpret_cast<uint8_t *>(histw + 256), *const bitsw = patchw + patch_bytes;
     const int f = blockIdx.y;
     const int *counters = fa.fs0.counters + (size_t)f * 8;
     const int nw = counters[FC_NWORK];
@@ -756,28 +777,52 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
     const uint8_t *img = gray + (size_t)f * ip.frame_stride;
     const unsigned FULL = 0xFFFFFFFFu;
     for (int w = blockIdx.x * ID_WARPS + wp; w < nw; w += gridDim.x * ID_WARPS) {
-        for (int i = lane; i < 256; i += 32) s_hist[wp][i] = 0;
+        for (int i = lane; i < 256; i += 32) histw[i] = 0;
         __syncwarp();
         double M[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) M[i] = __ldg(wM + ((size_t)f * ip.max_cand + w) * 9 + i);
         const int m0 = ip.cellSize / 2;
+        long long *mk = (ip.marks && f == 0 && w == 0 && lane == 0) ? ip.marks : nullptr;
+        int nmk = 0;
+        long long t_start = 0;
+        if (ip.marks && lane == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start)); }
+#define ID_MARK() do { if (mk) mk[nmk++] = clock64(); } while (0)
+        ID_MARK();
         int ls = 0, lq = 0;
-#pragma unroll 2
+        // sampling: no dependence between iterations, so the (uncached) gathers of several pixels are in flight together
+        // 4 pixels per lane at a time: four independent FP64 coordinate chains, then four gathers in flight
+        for (int base = 0; base < S * S; base += 128) {
+            long long off[4];
+            int pp[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                pp[k] = base + k * 32 + lane;
+                const int y = pp[k] / S, x = pp[k] - y * S;
+                off[k] = pp[k] < S * S ? warp_source(ip.W, ip.H, ip.pitch, M, x, y) : -1;
+            }
+            unsigned v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = off[k] >= 0 ? (unsigned)__ldg(img + off[k]) : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (pp[k] >= S * S) continue;
+                const int y = pp[k] / S, x = pp[k] - y * S;
+                patchw[pp[k]] = (uint8_t)v[k];
+                if (x >= m0 && x < S - m0 && y >= m0 && y < S - m0) { ls += (int)v[k]; lq += (int)(v[k] * v[k]); }
+            }
+        }
+        __syncwarp();
+        ID_MARK();
+        // warp-aggregated histogram: a marker patch has two dominant levels, so plain shared atomics serialise
         for (int base = 0; base < S * S; base += 32) {
             const int p = base + lane;
-            unsigned v = 256u;                                                 // sentinel for the lanes past the patch
-            if (p < S * S) {
-                const int y = p / S, x = p - y * S;
-                v = warp_sample(img, ip.W, ip.H, ip.pitch, M, x, y);
-                s_patch[wp][p] = (uint8_t)v;
-                if (x >= m0 && x < S - m0 && y >= m0 && y < S - m0) { ls += (int)v; lq += (int)(v * v); }
-            }
-            // warp-aggregated histogram: a marker patch has two dominant levels, so plain shared atomics serialise
+            const unsigned v = (p < S * S) ? patchw[p] : 256u;            // sentinel for the lanes past the patch
             const unsigned peers = __match_any_sync(FULL, v);
-            if (v < 256u && lane == __ffs(peers) - 1) s_hist[wp][v] += __popc(peers);
+            if (v < 256u && lane == __ffs(peers) - 1) histw[v] += __popc(peers);
             __syncwarp();
         }
+        ID_MARK();
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { ls += __shfl_xor_sync(FULL, ls, o); lq += __shfl_xor_sync(FULL, lq, o); }
         __syncwarp();
@@ -788,12 +833,11 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
             int isum = 0, nzmask = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const int i = lane * 8 + k, hv = s_hist[wp][i];
+                const int i = lane * 8 + k, hv = histw[i];
                 isum += i * hv; nzmask |= (hv != 0) << k;
                 double p_i, ip_i;
                 otsu_bin_inputs(i, hv, S * S, p_i, ip_i);
-                s_q1[wp][i] = hv ? p_i : -1.0;                                  // empty bins outside [lo, hi] stay -1; inside, 0 is restored below
-                s_mu1[wp][i] = ip_i;
+                q1w[i] = p_i; mu1w[i] = ip_i; yw[i] = -1.0;
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) isum += __shfl_xor_sync(FULL, isum, o);
@@ -801,18 +845,22 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
             const int l_lo = __ffs(nzl) - 1, l_hi = 31 - __clz(nzl);
             const int lo = l_lo * 8 + __ffs(__shfl_sync(FULL, nzmask, l_lo)) - 1;
             const int hi = l_hi * 8 + 31 - __clz(__shfl_sync(FULL, nzmask, l_hi));
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { const int i = lane * 8 + k; if (i > lo && i < hi && s_q1[wp][i] < 0) s_q1[wp][i] = 0.0; }
             const double mu = otsu_mu(isum, S * S);
             __syncwarp();
-            if (lane == 0) otsu_chain(lo, hi, s_q1[wp], s_mu1[wp]);
+            ID_MARK();
+            if (lane == 0) otsu_prefix(lo, hi, q1w);                       // running sums q1 (one add per bin)
             __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const int i = lane * 8 + k; if (i >= lo && i <= hi) yw[i] = otsu_bin(q1w[i]); }
+            __syncwarp();
+            if (lane == 0) otsu_chain(lo, hi, q1w, yw, mu1w);    // the mu1 recurrence, division-free
+            __syncwarp();
+            ID_MARK();
             double best = 0; int bi = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {                                        // lane owns 8 consecutive bins: order kept
                 const int i = lane * 8 + k;
-                const double q1 = s_q1[wp][i];
-                const double sg = otsu_sigma(mu, q1, q1 < 0 ? 0.0 : s_mu1[wp][i]);
+                const double sg = otsu_sigma(mu, q1w[i], yw[i], mu1w[i]);
                 if (sg > best) { best = sg; bi = i; }
             }
 #pragma unroll
@@ -823,14 +871,15 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
             }
             thr = best > 0 ? bi : 0;
         }
+        ID_MARK();
         for (int cidx = lane; cidx < nb * nb; cidx += 32) {
             const int cy = cidx / nb, cx = cidx - cy * nb;
-            s_bits[wp][cidx] = (uint8_t)((mode < 2) ? mode : ident_cell_bit(s_patch[wp], S, ip.cellSize, ip.cellMargin, cy, cx, thr));
+            bitsw[cidx] = (uint8_t)((mode < 2) ? mode : ident_cell_bit(patchw, S, ip.cellSize, ip.cellMargin, cy, cx, thr));
         }
         __syncwarp();
         unsigned long long code = 0;
         int ok = 0;
-        if (lane == 0) ok = ident_border_code(s_bits[wp], ip.markerSize, ip.borderBits, ip.maxBorderErr, code) ? 1 : 0;
+        if (lane == 0) ok = ident_border_code(bitsw, ip.markerSize, ip.borderBits, ip.maxBorderErr, code) ? 1 : 0;
         ok = __shfl_sync(FULL, ok, 0);
         code = __shfl_sync(FULL, code, 0);
         int best_m = 0x7FFFFFFF;
@@ -850,6 +899,14 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
                 res = (int)(0x80000000u | ((unsigned)best_m << 8) | (unsigned)rot);
             }
             fa.fs0.wres[(size_t)f * ip.max_cand + w] = res;
+        }
+        ID_MARK();
+        if (ip.marks && lane == 0) {
+            long long t_end; unsigned smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            long long *rec = ip.marks + 16 + ((size_t)f * 128 + (w & 127)) * 3;
+            rec[0] = t_start; rec[1] = t_end; rec[2] = smid;
         }
         __syncwarp();
     }

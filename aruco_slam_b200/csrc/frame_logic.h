@@ -48,7 +48,7 @@ struct FrameScratch {
     int32_t *parent;    // [max_cand]
     int32_t *depth;     // [max_cand]
     int32_t *selGroup;  // [max_cand]  selected -> group id or -1
-    uint32_t *closeM;   // [max_cand][max_cand/32] closeness bit matrix (row i: bits j > i), global fallback
+    uint32_t *closeM;   // 2 x [max_cand][max_cand/32] closeness bit matrix (row i: bits j > i) and its transpose, global fallback
     // identification work list: item w < n_sel is selected candidate w; then the close candidates
     float   *wq;        // [max_cand][8]
     int32_t *wres;      // [max_cand]  result: bit 31 valid, bits 8..: id, bits 0..1: rot   (written by identify)
@@ -123,14 +123,20 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
     }
     ctx.sync();
     // ---- 3. closeness bit matrix: bit j of row i (j > i) iff avgDist(T[i],T[j]) < perimeter_j * rate ----
-    uint32_t *M = ((long long)n * wpr <= (long long)Mwords) ? Msm : fs.closeM;
-    for (int t = tid; t < n * wpr; t += nt) {
+    // M: row i, bits j > i.  MT: the transposed bits (row j, bits i < j), so that both "smallest close
+    // neighbour below" and "above" are first-set-bit scans.  One warp per (row, word): lane = candidate j.
+    const bool Msmem = (long long)2 * n * wpr <= (long long)Mwords;
+    uint32_t *M = Msmem ? Msm : fs.closeM, *MT = M + (size_t)n * wpr;
+    for (int t = tid; t < n * wpr; t += nt) MT[t] = 0;
+    ctx.sync();
+    const int lane = ctx.lane(), nl = ctx.lanes();
+    for (int t = ctx.warp(); t < n * wpr; t += ctx.warps()) {
         const int i = t / wpr, w = t - i * wpr;
         uint32_t bits = 0;
         if (w * 32 + 31 > i) {
             const float *a = tq + (size_t)i * 8;
             const float acx = (a[0] + a[2]) + (a[4] + a[6]), acy = (a[1] + a[3]) + (a[5] + a[7]);   // 4 * centroid
-            for (int b = 0; b < 32; ++b) {
+            for (int b = lane; b < 32; b += nl) {
                 const int j = w * 32 + b;
                 if (j <= i || j >= n) continue;
                 const float *q = tq + (size_t)j * 8;
@@ -140,10 +146,11 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
                 // |centroid_a - centroid_b| <= avgDist: cheap exact-safe rejection (integer coordinates)
                 const float dcx = (acx - qcx) * 0.25f, dcy = (acy - qcy) * 0.25f;
                 if (dcx * dcx + dcy * dcy > thr * thr * 1.01f + 1.0f) continue;
-                if (quad_avg_distance(a, q) < thr) bits |= 1u << b;
+                if (quad_avg_distance(a, q) < thr) { bits |= 1u << b; ctx.atomic_or(&MT[j * wpr + (i >> 5)], 1u << (i & 31)); }
             }
         }
-        M[t] = bits;
+        bits = ctx.warp_or(bits);
+        if (lane == 0) M[t] = bits;
     }
     ctx.sync();
     // ---- 4. group assignment (A5).  OpenCV walks the close pairs (i, j), i < j, in lexicographic order:
@@ -160,8 +167,8 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
     int32_t *pm = fs.closeIdx, *jm = fs.closeCnt, *par = fs.gfill, *rootrank = fs.members;      // temporaries
     for (int x = tid; x < n; x += nt) {
         int p = -1, j = -1;
-        const int xw = x >> 5; const uint32_t xb = 1u << (x & 31);
-        for (int i = 0; i < x; ++i) if (M[i * wpr + xw] & xb) { p = i; break; }
+        const int xw = x >> 5;
+        for (int w = 0; w <= xw; ++w) { const uint32_t bits = MT[x * wpr + w]; if (bits) { p = w * 32 + ffs32(bits) - 1; break; } }
         for (int w = xw; w < wpr; ++w) { const uint32_t bits = M[x * wpr + w]; if (bits) { j = w * 32 + ffs32(bits) - 1; break; } }
         pm[x] = p; jm[x] = j;
     }
@@ -238,20 +245,30 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
     }
     ctx.sync();
     // ---- 7. containment hierarchy ----
-    for (int i = tid; i < nS; i += nt) {
+    for (int i = ctx.warp(); i < nS; i += ctx.warps()) {           // one warp per selected candidate, lanes scan the earlier ones
         int pr = -1;
         const float *a = tq + (size_t)S[i] * 8;
-        for (int j = i - 1; j >= 0; --j)
-            if (quad_inside_quad(a, tq + (size_t)S[j] * 8)) { pr = j; break; }
-        parent[i] = pr;
-        depth[i] = 0;
+        for (int jb = i - 1; jb >= 0 && pr < 0; jb -= nl) {
+            const int j = jb - lane;
+            const bool in = j >= 0 && quad_inside_quad(a, tq + (size_t)S[j] * 8);
+            const uint32_t hit = ctx.ballot(in);
+            if (hit) pr = jb - (ffs32(hit) - 1);                   // the closest earlier candidate that contains it
+        }
+        if (lane == 0) parent[i] = pr;
+    }
+    ctx.sync();
+    // depth = height of the containment subtree (children always come after their parent)
+    for (int i = tid; i < nS; i += nt) {
+        int dmax = 0;
+        for (int j = i + 1; j < nS; ++j) {
+            int a = j, k = 0;
+            while (a > i) { a = parent[a]; ++k; }
+            if (a == i && k > dmax) dmax = k;
+        }
+        depth[i] = dmax;
     }
     ctx.sync();
     if (tid == 0) {
-        for (int i = nS - 1; i >= 0; --i) {
-            const int pr = parent[i];
-            if (pr >= 0 && depth[pr] < depth[i] + 1) depth[pr] = depth[i] + 1;
-        }
         // ---- 8. identification work list ----
         int nw = nS;
         for (int v = 0; v < nS; ++v) {

@@ -112,3 +112,12 @@ def observation(corners, mid, rvec, tvec, K, D, sp):
                               P(np.ascontiguousarray(tvec, np.float64)), P(np.ascontiguousarray(K, np.float64).reshape(9)), P(D5),
                               sp.R_x, sp.R_y, sp.R_theta, sp.marker_length, sp.r2c_tx, sp.r2c_ty, sp.useful_distance_threshold, P(out))
     return bool(k), out
+
+
+def otsu(hist):
+    """(threshold of the product's restated Otsu, threshold of the textbook sequential loop)"""
+    h = np.ascontiguousarray(hist, np.int32)
+    assert h.shape == (256,)
+    a, b = C.c_int(), C.c_int()
+    lib().emu_otsu(h.ctypes.data_as(C.c_void_p), int(h.sum()), C.byref(a), C.byref(b))
+    return a.value, b.value

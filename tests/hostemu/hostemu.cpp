@@ -19,6 +19,14 @@ struct HostCtx {
     int tid() const { return 0; }
     int nthreads() const { return 1; }
     void sync() const {}
+    void mark() const {}
+    int lane() const { return 0; }
+    int lanes() const { return 1; }
+    int warp() const { return 0; }
+    int warps() const { return 1; }
+    uint32_t ballot(bool p) const { return p ? 1u : 0u; }
+    uint32_t warp_or(uint32_t v) const { return v; }
+    void atomic_or(uint32_t *p, uint32_t v) const { *p |= v; }
     int exclusive_scan(int flag, int &total) const { total = flag ? 1 : 0; return 0; }
 };
 
@@ -212,7 +220,7 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
     std::vector<float> cq((size_t)MC * 8), tq((size_t)MC * 8), tper(MC), wq((size_t)MC * 8);
     std::vector<int32_t> clen(MC), gid(MC), sel(MC), gstart(MC + 1), gfill(MC), members(MC), closeIdx(MC), closeCnt(MC), S(MC), parent(MC), depth(MC),
         selGroup(MC), wres(MC), closeStart(MC), closeNum(MC), counters(8, 0);
-    std::vector<uint32_t> closeM((size_t)MC * ((MC + 31) / 32));
+    std::vector<uint32_t> closeM((size_t)MC * 2 * ((MC + 31) / 32));
     FrameScratch fs{cq.data(), clen.data(), tq.data(), tper.data(), gid.data(), sel.data(), gstart.data(), gfill.data(), members.data(),
                     closeIdx.data(), closeCnt.data(), S.data(), parent.data(), depth.data(), selGroup.data(), closeM.data(),
                     wq.data(), wres.data(), closeStart.data(), closeNum.data(), counters.data()};
@@ -256,6 +264,13 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
     FrameOutputs fo{n_acc, n_rej, corners, ids, rejected, &st};
     frame_finalize(ctx, fp, fs, fo);
     return st;
+}
+
+// restated Otsu vs the textbook loop on one histogram
+void emu_otsu(const int *h, int n, int *thr_new, int *thr_seq)
+{
+    *thr_new = otsu_threshold(h, n);
+    *thr_seq = otsu_threshold_sequential(h, n);
 }
 
 void emu_pose(const float *corners, int n, const double *K9, const double *D5, float marker_length, double *rvecs, double *tvecs)

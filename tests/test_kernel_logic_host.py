@@ -102,3 +102,25 @@ def test_pose_logic_detected_markers():
     assert np.abs(t - rows[:, 13:16]).max() < 1e-4                                                   # m
     assert max(synth.rvec_distance(a, b) for a, b in zip(r, rows[:, 10:13])) < 1e-4                  # rad (rotation)
     assert np.abs(r - rows[:, 10:13]).max() < 5e-4                                                   # same rvec branch
+
+
+def test_otsu_restatement_matches_textbook_loop():
+    """The division-free, range-restricted Otsu (prefix sums + reciprocal + fma correction) must pick the same
+    threshold as OpenCV's sequential loop, including the plateau / tie cases of two-level patches."""
+    rng = np.random.default_rng(11)
+    cases = []
+    for _ in range(400):                                    # random sparse / dense histograms of 1024 samples
+        k = int(rng.integers(1, 200))
+        bins = rng.choice(256, size=k, replace=False)
+        cases.append(np.bincount(rng.choice(bins, size=1024), minlength=256))
+    for a, b in ((0, 255), (30, 220), (100, 101), (5, 6), (254, 255), (0, 1)):      # two spikes (plateau between them)
+        for na in (1, 17, 512, 1023):
+            h = np.zeros(256, int); h[a] = na; h[b] = 1024 - na; cases.append(h)
+    h = np.zeros(256, int); h[77] = 576; cases.append(h)                            # flat patch
+    cases.append(np.full(256, 4))                                                   # uniform
+    for _ in range(100):                                    # blurred two-level patches like a warped marker
+        v = np.clip(np.concatenate([rng.normal(40, 6, 500), rng.normal(210, 9, 400), rng.uniform(40, 210, 124)]), 0, 255).astype(int)
+        cases.append(np.bincount(v, minlength=256))
+    for h in cases:
+        new, seq = emu.otsu(h)
+        assert new == seq, (new, seq, np.nonzero(h)[0][:8])
