@@ -133,6 +133,26 @@ k_pose(const float *__restrict__ corners, const int32_t *__restrict__ n_acc, int
     solve_marker_pose(Lanes8{}, cam, marker_length, corners + (size_t)t * 8, s_sh[threadIdx.x >> 3], rvecs + (size_t)t * 3, tvecs + (size_t)t * 3);
 }
 
+// Results go straight into the caller-visible pinned host arrays (device-accessible under unified
+// addressing): one small launch that writes only the filled entries instead of eight capacity-sized copies.
+struct ExportPtrs {
+    const int32_t *n_acc, *n_rej, *status, *ids; const float *corners, *rejected; const double *rvecs, *tvecs;    // device
+    int32_t *h_nacc, *h_nrej, *h_status, *h_ids; float *h_corners, *h_rejected; double *h_rvecs, *h_tvecs;        // pinned host
+};
+__global__ void __launch_bounds__(128)
+k_export(ExportPtrs p, int max_markers, int with_pose)
+{
+    const int f = blockIdx.x, K = max_markers;
+    const int na = p.n_acc[f], nr = p.n_rej[f];
+    if (threadIdx.x == 0) { p.h_nacc[f] = na; p.h_nrej[f] = nr; p.h_status[f] = p.status[f]; }
+    const size_t o = (size_t)f * K;
+    for (int i = threadIdx.x; i < na; i += blockDim.x) p.h_ids[o + i] = p.ids[o + i];
+    for (int i = threadIdx.x; i < na * 8; i += blockDim.x) p.h_corners[o * 8 + i] = p.corners[o * 8 + i];
+    for (int i = threadIdx.x; i < nr * 8; i += blockDim.x) p.h_rejected[o * 8 + i] = p.rejected[o * 8 + i];
+    if (with_pose)
+        for (int i = threadIdx.x; i < na * 3; i += blockDim.x) { p.h_rvecs[o * 3 + i] = p.rvecs[o * 3 + i]; p.h_tvecs[o * 3 + i] = p.tvecs[o * 3 + i]; }
+}
+
 __global__ void k_observations(const float *__restrict__ corners, const int32_t *__restrict__ ids, const double *__restrict__ rvecs,
                                const double *__restrict__ tvecs, int n, Camera cam, ObsParams op, Observation *__restrict__ out,
                                int *__restrict__ keep)
@@ -641,16 +661,15 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
         d->launches++;
     }
     stage_mark(d, s, ST_D2H);
-    const size_t BK = (size_t)nb * K, o = (size_t)b0 * K;
-    CU(cudaMemcpyAsync(d->h_nacc + b0, fa.fo0.n_accepted, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(d->h_nrej + b0, fa.fo0.n_rejected, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(d->h_status + b0, d->d_status + b0, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(d->h_corners + o * 8, corners, BK * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(d->h_ids + o, fa.fo0.ids, BK * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(d->h_rejected + o * 8, fa.fo0.rejected, BK * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (cam) {
-        CU(cudaMemcpyAsync(d->h_rvecs + o * 3, d->d_rvecs + o * 3, BK * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(d->h_tvecs + o * 3, d->d_tvecs + o * 3, BK * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    {
+        const size_t o = (size_t)b0 * K;
+        ExportPtrs ep;
+        ep.n_acc = fa.fo0.n_accepted; ep.n_rej = fa.fo0.n_rejected; ep.status = d->d_status + b0; ep.ids = fa.fo0.ids;
+        ep.corners = corners; ep.rejected = fa.fo0.rejected; ep.rvecs = d->d_rvecs + o * 3; ep.tvecs = d->d_tvecs + o * 3;
+        ep.h_nacc = d->h_nacc + b0; ep.h_nrej = d->h_nrej + b0; ep.h_status = d->h_status + b0; ep.h_ids = d->h_ids + o;
+        ep.h_corners = d->h_corners + o * 8; ep.h_rejected = d->h_rejected + o * 8; ep.h_rvecs = d->h_rvecs + o * 3; ep.h_tvecs = d->h_tvecs + o * 3;
+        k_export<<<nb, 128, 0, st>>>(ep, d->max_markers, cam ? 1 : 0);
+        d->launches++;
     }
     if (s.timed) cudaEventRecord(d->ev[ST_COUNT], st);
     return launch_err("back-end kernels");

@@ -315,62 +315,65 @@ struct FrameOutputs {
     int32_t *status;       // [1]
 };
 
-// A6 + output (single lane: the per-frame lists are a few dozen entries)
+// A6 + output: the acceptance order is decided by one lane (a few dozen entries), then all threads
+// copy the accepted / rejected quads to their output slots
 template <class Ctx>
 B2A_HD void frame_finalize(Ctx &ctx, const FrameParams &fp, const FrameScratch &fs, const FrameOutputs &fo)
 {
-    if (ctx.tid() != 0) return;
     const int nS = fs.counters[FC_NSEL];
-    // valid / was flags live in gid / sel (free after grouping); chosen work item in gfill
+    // valid / was flags live in gid / sel (free after grouping); chosen work item in gfill; after the
+    // decision `was` is reused as the output slot: >= 0 accepted slot, <= -2 rejected slot -(slot + 2), -1 dropped
     int32_t *valid = fs.gid, *was = fs.sel, *chosen = fs.gfill;
-    int maxDepth = 0;
-    for (int v = 0; v < nS; ++v) { valid[v] = 0; was[v] = 0; chosen[v] = v; if (fs.depth[v] > maxDepth) maxDepth = fs.depth[v]; }
-    int counter = 0;
-    for (int depth = 0; counter < nS && depth <= maxDepth; ++depth) {
-        for (int v = 0; v < nS; ++v) {
-            if (fs.depth[v] != depth) continue;
-            was[v] = 1;
-            if (fs.wres[v] < 0) valid[v] = 1;
-            else
-                for (int c = 0; c < fs.closeNum[v]; ++c)
-                    if (fs.wres[fs.closeStart[v] + c] < 0) { valid[v] = 1; chosen[v] = fs.closeStart[v] + c; break; }
-        }
-        for (int v = 0; v < nS; ++v) {
-            if (fs.depth[v] != depth) continue;
-            if (valid[v]) {
-                int par = fs.parent[v];
-                while (par != -1) { if (!was[par]) { was[par] = 1; ++counter; } par = fs.parent[par]; }
+    if (ctx.tid() == 0) {
+        int maxDepth = 0;
+        for (int v = 0; v < nS; ++v) { valid[v] = 0; was[v] = 0; chosen[v] = v; if (fs.depth[v] > maxDepth) maxDepth = fs.depth[v]; }
+        int counter = 0;
+        for (int depth = 0; counter < nS && depth <= maxDepth; ++depth) {
+            for (int v = 0; v < nS; ++v) {
+                if (fs.depth[v] != depth) continue;
+                was[v] = 1;
+                if (fs.wres[v] < 0) valid[v] = 1;
+                else
+                    for (int c = 0; c < fs.closeNum[v]; ++c)
+                        if (fs.wres[fs.closeStart[v] + c] < 0) { valid[v] = 1; chosen[v] = fs.closeStart[v] + c; break; }
             }
-            ++counter;
+            for (int v = 0; v < nS; ++v) {
+                if (fs.depth[v] != depth) continue;
+                if (valid[v]) {
+                    int par = fs.parent[v];
+                    while (par != -1) { if (!was[par]) { was[par] = 1; ++counter; } par = fs.parent[par]; }
+                }
+                ++counter;
+            }
         }
+        int na = 0, nr = 0, status = fs.counters[FC_STATUS];
+        if (*fo.status != 0) status = *fo.status;               // overflow flagged by an earlier stage
+        for (int v = 0; v < nS; ++v) {
+            if (valid[v]) { if (na < fp.max_markers) was[v] = na++; else { was[v] = -1; status = 3; } }
+            else { if (nr < fp.max_markers) was[v] = -(nr++) - 2; else { was[v] = -1; status = 3; } }
+        }
+        *fo.n_accepted = na; *fo.n_rejected = nr; *fo.status = status;
     }
-    int na = 0, nr = 0, status = fs.counters[FC_STATUS];
-    if (*fo.status != 0) status = *fo.status;               // overflow flagged by an earlier stage
-    for (int v = 0; v < nS; ++v) {
-        if (valid[v]) {
+    ctx.sync();
+    for (int v = ctx.tid(); v < nS; v += ctx.nthreads()) {
+        const int slot = was[v];
+        if (slot >= 0) {
             const int w = chosen[v];
             const uint32_t res = (uint32_t)fs.wres[w];
             const int rot = (int)(res & 3u), id = (int)((res >> 8) & 0x7FFFFFu);
-            if (na < fp.max_markers) {
-                const float *c = fs.wq + (size_t)w * 8;
-                float *o = fo.corners + (size_t)na * 8;
-                for (int j = 0; j < 4; ++j) {       // std::rotate(begin, begin + 4 - rot, end)
-                    const int src = (j + 4 - rot) & 3;
-                    o[2 * j] = c[2 * src]; o[2 * j + 1] = c[2 * src + 1];
-                }
-                fo.ids[na] = id;
-                ++na;
-            } else status = 3;
-        } else {
-            if (nr < fp.max_markers) {
-                const float *c = fs.wq + (size_t)v * 8;
-                float *o = fo.rejected + (size_t)nr * 8;
-                for (int k = 0; k < 8; ++k) o[k] = c[k];
-                ++nr;
-            } else status = 3;
+            const float *c = fs.wq + (size_t)w * 8;
+            float *o = fo.corners + (size_t)slot * 8;
+            for (int j = 0; j < 4; ++j) {       // std::rotate(begin, begin + 4 - rot, end)
+                const int src = (j + 4 - rot) & 3;
+                o[2 * j] = c[2 * src]; o[2 * j + 1] = c[2 * src + 1];
+            }
+            fo.ids[slot] = id;
+        } else if (slot <= -2) {
+            const float *c = fs.wq + (size_t)v * 8;
+            float *o = fo.rejected + (size_t)(-slot - 2) * 8;
+            for (int k = 0; k < 8; ++k) o[k] = c[k];
         }
     }
-    *fo.n_accepted = na; *fo.n_rejected = nr; *fo.status = status;
 }
 
 }  // namespace b2a
