@@ -116,13 +116,15 @@ extern "C" int b2a_get_predefined_dictionary(int dict_id, b2a_dictionary *out)
 // 8 lanes per marker (one per row of the reprojection system), 16 markers per CTA
 constexpr int POSE_THREADS = 128;
 struct Lanes8 {
+    long long *marks = nullptr; mutable int nmark = 0;       // debug: clock64 trace of one marker
+    __device__ __forceinline__ void mark() const { if (marks && (threadIdx.x & 7) == 0 && nmark < 30) marks[nmark++] = clock64(); }
     __device__ __forceinline__ int lane() const { return threadIdx.x & 7; }
     __device__ __forceinline__ int nlanes() const { return 8; }
     __device__ __forceinline__ void sync() const { __syncwarp(0xFFu << (threadIdx.x & 24)); }
 };
 __global__ void __launch_bounds__(POSE_THREADS)
 k_pose(const float *__restrict__ corners, const int32_t *__restrict__ n_acc, int B, int max_markers,
-       Camera cam, float marker_length, double *__restrict__ rvecs, double *__restrict__ tvecs)
+       Camera cam, float marker_length, double *__restrict__ rvecs, double *__restrict__ tvecs, long long *marks)
 {
     __shared__ double s_sh[POSE_THREADS / 8][POSE_SH];
     const int total = B * max_markers;
@@ -130,7 +132,9 @@ k_pose(const float *__restrict__ corners, const int32_t *__restrict__ n_acc, int
     if (t >= total) return;
     const int f = t / max_markers, m = t - f * max_markers;
     if (n_acc && m >= n_acc[f]) return;
-    solve_marker_pose(Lanes8{}, cam, marker_length, corners + (size_t)t * 8, s_sh[threadIdx.x >> 3], rvecs + (size_t)t * 3, tvecs + (size_t)t * 3);
+    Lanes8 lg;
+    if (marks && t == 0) { lg.marks = marks; lg.mark(); }
+    solve_marker_pose(lg, cam, marker_length, corners + (size_t)t * 8, s_sh[threadIdx.x >> 3], rvecs + (size_t)t * 3, tvecs + (size_t)t * 3);
 }
 
 // Results go straight into the caller-visible pinned host arrays (device-accessible under unified
@@ -557,6 +561,10 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
                                                     d->d_pts + fs0 * (size_t)g.pts_cap, d->d_quad_ok + fs0 * g.surv_cap, d->d_quad_xy + fs0 * g.surv_cap * 8,
                                                     d->d_quad_len + fs0 * g.surv_cap, g);
     d->launches++; DBG_SYNC(st);
+    k_approx_long<<<dim3(APPROX_LONG_CTAS, (unsigned)FS), 256, 0, st>>>(d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,
+                                                         d->d_pts + fs0 * (size_t)g.pts_cap, d->d_quad_ok + fs0 * g.surv_cap, d->d_quad_xy + fs0 * g.surv_cap * 8,
+                                                         d->d_quad_len + fs0 * g.surv_cap, g);
+    d->launches++; DBG_SYNC(st);
     return launch_err("front-end kernels");
 }
 
@@ -655,10 +663,25 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
         corners = c2;
     }
     stage_mark(d, s, ST_POSE);
+    static long long *pose_marks_buf = nullptr;
+    long long *pose_marks = nullptr;
+    if (std::getenv("B2A_POSE_MARKS") && s.sb == 0) {
+        if (!pose_marks_buf) cudaMalloc(&pose_marks_buf, 32 * sizeof(long long));
+        cudaMemsetAsync(pose_marks_buf, 0, 32 * sizeof(long long), st);
+        pose_marks = pose_marks_buf;
+    }
     if (cam) {
         k_pose<<<(nb * (int)K * 8 + POSE_THREADS - 1) / POSE_THREADS, POSE_THREADS, 0, st>>>(corners, fa.fo0.n_accepted, nb, d->max_markers, to_camera(cam), cam->marker_length,
-                                                        d->d_rvecs + (size_t)b0 * K * 3, d->d_tvecs + (size_t)b0 * K * 3);
+                                                        d->d_rvecs + (size_t)b0 * K * 3, d->d_tvecs + (size_t)b0 * K * 3, pose_marks);
         d->launches++;
+        if (pose_marks) {
+            long long hm[32];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(hm, pose_marks, sizeof(hm), cudaMemcpyDeviceToHost);
+            std::fprintf(stderr, "k_pose marker 0 cycles (init, first rows, then per LM iteration):");
+            for (int i = 1; i < 32 && hm[i]; ++i) std::fprintf(stderr, " %lld", hm[i] - hm[i - 1]);
+            std::fprintf(stderr, "\n");
+        }
     }
     stage_mark(d, s, ST_D2H);
     {
@@ -763,7 +786,7 @@ extern "C" int b2a_estimate_pose_single_markers(b2a_detector *d, const float *co
     CU(cudaMalloc(&dt, (size_t)n * 3 * sizeof(double)));
     cudaStream_t st = d->stream;
     cudaMemcpyAsync(dc, corners, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice, st);
-    k_pose<<<(n * 8 + POSE_THREADS - 1) / POSE_THREADS, POSE_THREADS, 0, st>>>(dc, nullptr, 1, n, to_camera(cam), cam->marker_length, dr, dt);
+    k_pose<<<(n * 8 + POSE_THREADS - 1) / POSE_THREADS, POSE_THREADS, 0, st>>>(dc, nullptr, 1, n, to_camera(cam), cam->marker_length, dr, dt, nullptr);
     cudaMemcpyAsync(rvecs, dr, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(tvecs, dt, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);

@@ -21,6 +21,13 @@
 #else
 #define B2A_HD inline
 #endif
+// big helpers that are called from several places: one copy keeps the instruction footprint (and the cold
+// instruction-cache misses of latency-bound kernels) small
+#if defined(__CUDACC__)
+#define B2A_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define B2A_HD_NOINLINE inline
+#endif
 // full unrolling where compile-time indices keep small arrays in registers on the device
 #if defined(__CUDA_ARCH__)
 #define B2A_UNROLL _Pragma("unroll")
@@ -419,12 +426,21 @@ B2A_HD int approx_closed(const LG &lg, const uint32_t *__restrict__ P, int count
         pos = (pos + 1) % count;
         // coordinates are below 2^15: squared distances fit 32 bits
         uint32_t bd32 = 0; int bj = 0x7FFFFFFF;
-        for (int j = 1 + lane; j < count; j += nl) {
-            int idx = pos + j - 1; if (idx >= count) idx -= count;
-            const uint32_t q = P[idx];
-            const int dx = px_of(q) - sx, dy = py_of(q) - sy;
-            const uint32_t d = (uint32_t)(dx * dx) + (uint32_t)(dy * dy);
-            if (d > bd32) { bd32 = d; bj = j; }
+        for (int j0 = 1 + lane; j0 < count; j0 += 4 * nl) {          // four points per lane in flight
+            uint32_t q[4];
+            B2A_UNROLL
+            for (int k = 0; k < 4; ++k) {
+                const int j = j0 + k * nl;
+                int idx = pos + j - 1; if (idx >= count) idx -= count;
+                q[k] = j < count ? P[idx] : 0u;
+            }
+            B2A_UNROLL
+            for (int k = 0; k < 4; ++k) {
+                const int j = j0 + k * nl;
+                const int dx = px_of(q[k]) - sx, dy = py_of(q[k]) - sy;
+                const uint32_t d = (uint32_t)(dx * dx) + (uint32_t)(dy * dy);
+                if (j < count && d > bd32) { bd32 = d; bj = j; }
+            }
         }
         long long bd = (long long)bd32;
         lg.argmax_first(bd, bj);
@@ -454,16 +470,25 @@ B2A_HD int approx_closed(const LG &lg, const uint32_t *__restrict__ P, int count
             const uint32_t L2u = (uint32_t)(dx * dx) + (uint32_t)(dy * dy);
             const long long L2 = (long long)L2u;
             unsigned long long bdu = 0; int bt = 0x7FFFFFFF;
-            for (int t = lane; t < inner; t += nl) {
-                int idx = s + 1 + t; if (idx >= count) idx -= count;
-                const uint32_t q = P[idx];
-                const int px = px_of(q) - sx, py = py_of(q) - sy;
-                const int dot = px * dx + py * dy;
-                unsigned long long d;
-                if (dot < 0) d = (unsigned long long)((uint32_t)(px * px) + (uint32_t)(py * py)) * L2u;
-                else if ((uint32_t)dot > L2u) { const int qx = px - dx, qy = py - dy; d = (unsigned long long)((uint32_t)(qx * qx) + (uint32_t)(qy * qy)) * L2u; }
-                else { const int cr = py * dx - px * dy; const uint32_t a = (uint32_t)(cr < 0 ? -cr : cr); d = (unsigned long long)a * a; }
-                if (d > bdu) { bdu = d; bt = t; }
+            for (int t0 = lane; t0 < inner; t0 += 4 * nl) {            // four points per lane in flight
+                uint32_t qq[4];
+                B2A_UNROLL
+                for (int k = 0; k < 4; ++k) {
+                    const int t = t0 + k * nl;
+                    int idx = s + 1 + t; if (idx >= count) idx -= count;
+                    qq[k] = t < inner ? P[idx] : 0u;
+                }
+                B2A_UNROLL
+                for (int k = 0; k < 4; ++k) {
+                    const int t = t0 + k * nl;
+                    const int px = px_of(qq[k]) - sx, py = py_of(qq[k]) - sy;
+                    const int dot = px * dx + py * dy;
+                    unsigned long long d;
+                    if (dot < 0) d = (unsigned long long)((uint32_t)(px * px) + (uint32_t)(py * py)) * L2u;
+                    else if ((uint32_t)dot > L2u) { const int qx = px - dx, qy = py - dy; d = (unsigned long long)((uint32_t)(qx * qx) + (uint32_t)(qy * qy)) * L2u; }
+                    else { const int cr = py * dx - px * dy; const uint32_t a = (uint32_t)(cr < 0 ? -cr : cr); d = (unsigned long long)a * a; }
+                    if (t < inner && d > bdu) { bdu = d; bt = t; }
+                }
             }
             long long bd = (long long)bdu;
             lg.argmax_first(bd, bt);

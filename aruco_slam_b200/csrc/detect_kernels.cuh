@@ -585,9 +585,21 @@ struct WarpLanes {
     }
 };
 
-__global__ void k_approx(const uint4 *__restrict__ sorted, const int *__restrict__ surv_count, const int *__restrict__ pts_off,
-                         const uint32_t *__restrict__ pts, uint8_t *__restrict__ quad_ok, int32_t *__restrict__ quad_xy,
-                         int32_t *__restrict__ quad_len, DetGeom g)
+// borders of at least this many points are left to k_approx_long (a whole CTA per border)
+constexpr int APPROX_LONG = 2048;
+constexpr int APPROX_LONG_CTAS = 16;          // CTAs per (frame,scale) of k_approx_long
+
+__device__ __forceinline__ void approx_store(bool ok, int len, const int *ox, const int *oy, size_t slot, uint8_t *quad_ok, int32_t *quad_xy, int32_t *quad_len)
+{
+    quad_ok[slot] = ok ? 1 : 0;
+    quad_len[slot] = len;
+    if (ok) for (int k = 0; k < 4; ++k) { quad_xy[slot * 8 + 2 * k] = ox[k]; quad_xy[slot * 8 + 2 * k + 1] = oy[k]; }
+}
+
+__global__ void __launch_bounds__(256)
+k_approx(const uint4 *__restrict__ sorted, const int *__restrict__ surv_count, const int *__restrict__ pts_off,
+         const uint32_t *__restrict__ pts, uint8_t *__restrict__ quad_ok, int32_t *__restrict__ quad_xy,
+         int32_t *__restrict__ quad_len, DetGeom g)
 {
     const int fs = blockIdx.y;
     const int n = surv_count[fs];
@@ -597,17 +609,64 @@ __global__ void k_approx(const uint4 *__restrict__ sorted, const int *__restrict
         const size_t slot = (size_t)fs * g.surv_cap + i;
         const int off = pts_off[slot];
         const int len = (int)sorted[slot].y;
+        if (len >= APPROX_LONG && off >= 0) continue;
         bool ok = false;
         int ox[8], oy[8];
         if (off >= 0) {
             const int m = approx_closed(lg, pts + (size_t)fs * g.pts_cap + off, len, (double)len * g.approxRate, ox, oy);
             ok = (m == 4) && quad_passes(ox, oy, m, len, g.maxWH, g.minCornerDistRate);
         }
-        if (lg.lane() == 0) {
-            quad_ok[slot] = ok ? 1 : 0;
-            quad_len[slot] = len;
-            if (ok) for (int k = 0; k < 4; ++k) { quad_xy[slot * 8 + 2 * k] = ox[k]; quad_xy[slot * 8 + 2 * k + 1] = oy[k]; }
-        }
+        if (lg.lane() == 0) approx_store(ok, len, ox, oy, slot, quad_ok, quad_xy, quad_len);
+    }
+}
+
+// the same algorithm with the lanes of a whole CTA on one (long) border: the sweeps over the points
+// are the parallel part, the recursion is shared control flow
+struct BlockLanes {
+    long long *s_d; int *s_p;           // [warps] reduction scratch
+    __device__ __forceinline__ int lane() const { return threadIdx.x; }
+    __device__ __forceinline__ int nlanes() const { return blockDim.x; }
+    __device__ __forceinline__ void argmax_first(long long &d, int &pos) const
+    {
+        WarpLanes{}.argmax_first(d, pos);
+        const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        __syncthreads();                                     // previous round's scratch has been read by everyone
+        if ((threadIdx.x & 31) == 0) { s_d[w] = d; s_p[w] = pos; }
+        __syncthreads();
+        d = s_d[0]; pos = s_p[0];
+        for (int k = 1; k < nw; ++k) { const long long od = s_d[k]; const int op = s_p[k]; if (od > d || (od == d && op < pos)) { d = od; pos = op; } }
+    }
+};
+
+__global__ void __launch_bounds__(256)
+k_approx_long(const uint4 *__restrict__ sorted, const int *__restrict__ surv_count, const int *__restrict__ pts_off,
+              const uint32_t *__restrict__ pts, uint8_t *__restrict__ quad_ok, int32_t *__restrict__ quad_xy,
+              int32_t *__restrict__ quad_len, DetGeom g)
+{
+    __shared__ long long s_d[8];
+    __shared__ int s_p[8];
+    __shared__ int s_list[SORT_CAP / APPROX_LONG_CTAS], s_n;     // every gridDim.x-th border index can belong to this CTA
+    const int fs = blockIdx.y;
+    const int n = surv_count[fs];
+    BlockLanes lg{s_d, s_p};
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    // this CTA's long borders (every gridDim.x-th border index), found by all threads at once
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if ((i % (int)gridDim.x) != (int)blockIdx.x) continue;
+        const size_t slot = (size_t)fs * g.surv_cap + i;
+        if ((int)__ldg(&sorted[slot].y) >= APPROX_LONG && pts_off[slot] >= 0) { s_list[atomicAdd(&s_n, 1)] = i; }
+    }
+    __syncthreads();
+    const int nlong = s_n;
+    for (int k = 0; k < nlong; ++k) {
+        const int i = s_list[k];
+        const size_t slot = (size_t)fs * g.surv_cap + i;
+        const int len = (int)sorted[slot].y, off = pts_off[slot];
+        int ox[8], oy[8];
+        const int m = approx_closed(lg, pts + (size_t)fs * g.pts_cap + off, len, (double)len * g.approxRate, ox, oy);
+        const bool ok = (m == 4) && quad_passes(ox, oy, m, len, g.maxWH, g.minCornerDistRate);
+        if (threadIdx.x == 0) approx_store(ok, len, ox, oy, slot, quad_ok, quad_xy, quad_len);
     }
 }
 
@@ -752,22 +811,23 @@ k_homography(FrameArrays fa, double *__restrict__ wM, int S, int max_cand)
 constexpr int ID_WARPS = 4;         // work items in flight per CTA (one warp each)
 constexpr int ID_THREADS = ID_WARPS * 32;
 constexpr int ID_MAX_S = 9 * 8;     // (7 + 2) cells * up to 8 px
-inline size_t identify_smem_bytes(int S) { return (size_t)ID_WARPS * (3 * 256 * sizeof(double) + 256 * sizeof(int) + (size_t)((S * S + 15) & ~15) + 96); }
+inline size_t identify_smem_bytes(int S) { return (size_t)ID_WARPS * (3 * 256 * sizeof(double) + (size_t)((S * S + 15) & ~15) + 96); }
 
 // A7 step 2.  One WARP per work item: the sequential pieces (the Otsu recurrence, the border
 // check) run on lane 0 while the other warps of the SM work on other candidates; sampling, the
 // between-class variances, the cell votes and the dictionary scan are spread over the 32 lanes.
-__global__ void __launch_bounds__(ID_THREADS)
+__global__ void __launch_bounds__(ID_THREADS, 7)
 k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restrict__ dict, const double *__restrict__ wM, FrameArrays fa, IdentParams ip)
 {
-    // dynamic shared memory, per warp: q1 / mu1 / y [256] f64, histogram [256] i32, patch [S*S rounded up to 16] u8, bits [96] u8
+    // dynamic shared memory, per warp: q1 / mu1 / y [256] f64 (the histogram [256] i32 lives in y until Otsu starts),
+    // patch [S*S rounded up to 16] u8, bits [96] u8
     extern __shared__ __align__(16) uint8_t id_smem[];
     const int patch_bytes = (((ip.markerSize + 2 * ip.borderBits) * ip.cellSize) * ((ip.markerSize + 2 * ip.borderBits) * ip.cellSize) + 15) & ~15;
-    const size_t per_warp = 3 * 256 * sizeof(double) + 256 * sizeof(int) + (size_t)patch_bytes + 96;
+    const size_t per_warp = 3 * 256 * sizeof(double) + (size_t)patch_bytes + 96;
     uint8_t *wbase = id_smem + (size_t)(threadIdx.x >> 5) * per_warp;
     double *const q1w = reinterpret_cast<double *>(wbase), *const mu1w = q1w + 256, *const yw = mu1w + 256;
-    int *const histw = reinterpret_cast<int *>(yw + 256);
-    uint8_t *const patchw = reinterpret_cast<uint8_t *>(histw + 256), *const bitsw = patchw + patch_bytes;
+    int *const histw = reinterpret_cast<int *>(yw);
+    uint8_t *const patchw = reinterpret_cast<uint8_t *>(yw + 256), *const bitsw = patchw + patch_bytes;
     const int f = blockIdx.y;
     const int *counters = fa.fs0.counters + (size_t)f * 8;
     const int nw = counters[FC_NWORK];
@@ -830,13 +890,16 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
         int thr = 0;
         if (mode == 2) {
             // histogram range and first moment on all lanes (8 consecutive bins each), chain on lane 0
-            int isum = 0, nzmask = 0;
+            int isum = 0, nzmask = 0, hv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) hv[k] = histw[lane * 8 + k];
+            __syncwarp();                                                       // the histogram shares its storage with y
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const int i = lane * 8 + k, hv = histw[i];
-                isum += i * hv; nzmask |= (hv != 0) << k;
+                const int i = lane * 8 + k;
+                isum += i * hv[k]; nzmask |= (hv[k] != 0) << k;
                 double p_i, ip_i;
-                otsu_bin_inputs(i, hv, S * S, p_i, ip_i);
+                otsu_bin_inputs(i, hv[k], S * S, p_i, ip_i);
                 q1w[i] = p_i; mu1w[i] = ip_i; yw[i] = -1.0;
             }
 #pragma unroll

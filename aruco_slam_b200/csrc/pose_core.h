@@ -22,7 +22,9 @@ B2A_HD void rodrigues_to_R(const double *r, double *R)
 {
     const double th = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
     if (th < DBL_EPSILON) { for (int i = 0; i < 9; ++i) R[i] = 0; R[0] = R[4] = R[8] = 1; return; }
-    const double c = cos(th), s = sin(th), c1 = 1 - c, it = 1 / th;
+    double s, c;
+    sincos(th, &s, &c);
+    const double c1 = 1 - c, it = 1 / th;
     const double x = r[0] * it, y = r[1] * it, z = r[2] * it;
     R[0] = c + c1 * x * x;     R[1] = c1 * x * y - s * z; R[2] = c1 * x * z + s * y;
     R[3] = c1 * x * y + s * z; R[4] = c + c1 * y * y;     R[5] = c1 * y * z - s * x;
@@ -102,7 +104,7 @@ B2A_HD void undistort_point(const Camera &cam, double u, double v, double &xo, d
 // indices only -- the row exchange is a predicated swap against every candidate row -- so that the
 // system lives in registers instead of a dynamically indexed local-memory array.
 template <int N>
-B2A_HD bool solve_linear(double *A, double *b)
+B2A_HD_NOINLINE bool solve_linear(double *A, double *b)
 {
     B2A_UNROLL
     for (int i = 0; i < N; ++i) {
@@ -170,7 +172,9 @@ B2A_HD void rodrigues_with_jacobian(const double *rv, double *R, double *dR)
         dR[7] = dR[11] = dR[21] = 1;
         return;
     }
-    const double c = cos(th), s = sin(th), c1 = 1. - c, it = 1. / th;
+    double s, c;
+    sincos(th, &s, &c);
+    const double c1 = 1. - c, it = 1. / th;
     const double rx = rv[0] * it, ry = rv[1] * it, rz = rv[2] * it;
     const double rrt[9] = {rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz};
     const double r_x[9] = {0, -rz, ry, rz, 0, -rx, -ry, rx, 0};
@@ -269,7 +273,11 @@ B2A_HD bool solve_spd6(const double *M, double *d)
 B2A_HD void lm_step(const double *shN /* [6][7]: JtJ row | JtErr */, int lambdaLg10, const double *prev, double *p)
 {
     double M[36], d[6];
-    const double lambda = exp(lambdaLg10 * 2.302585092994046);      // CvLevMarq: exp(lambdaLg10 * log(10))
+    // CvLevMarq: lambda = exp(lambdaLg10 * log(10)), lambdaLg10 in [-16, 16]
+    const double p10[33] = {1e-16, 1e-15, 1e-14, 1e-13, 1e-12, 1e-11, 1e-10, 1e-9, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, 1e0,
+                            1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16};
+    const int li = lambdaLg10 < -16 ? -16 : (lambdaLg10 > 16 ? 16 : lambdaLg10);
+    const double lambda = p10[li + 16];
     B2A_UNROLL
     for (int a = 0; a < 6; ++a) {
         B2A_UNROLL
@@ -294,22 +302,25 @@ struct OneLane {
     B2A_HD int lane() const { return 0; }
     B2A_HD int nlanes() const { return 1; }
     B2A_HD void sync() const {}
+    B2A_HD void mark() const {}
 };
 constexpr int POSE_SH = 8 * 7 + 6 * 7;
 
-// L2 norm of the residual vector at p (every lane returns the same value)
+// rows of the reprojection system at p into shJ (lane r computes row r); returns the L2 norm of the
+// residual vector (the same value on every lane)
 template <class LG>
-B2A_HD double pose_error(const LG &lg, const Camera &cam, double h, const float *corners, const double *p, double *shJ)
+B2A_HD double pose_rows(const LG &lg, const Camera &cam, double h, const float *corners, const double *p, double *shJ)
 {
-    double R[9];
-    rodrigues_to_R(p, R);
-    B2A_UNROLL
-    for (int r = lg.lane(); r < 8; r += lg.nlanes()) pose_row(cam, h, corners, p, R, nullptr, r, shJ + r * 7);
+    lg.sync();                                   // the previous contents have been consumed by every lane
+    {
+        double R[9], dR[27];
+        rodrigues_with_jacobian(p, R, dR);
+        for (int r = lg.lane(); r < 8; r += lg.nlanes()) pose_row(cam, h, corners, p, R, dR, r, shJ + r * 7);
+    }
     lg.sync();
     double e = 0;
     B2A_UNROLL
     for (int i = 0; i < 4; ++i) { const double a = shJ[(2 * i) * 7 + 6], b = shJ[(2 * i + 1) * 7 + 6]; e += a * a + b * b; }
-    lg.sync();
     return sqrt(e);
 }
 
@@ -360,17 +371,11 @@ B2A_HD void solve_marker_pose(const LG &lg, const Camera &cam, float marker_leng
     int lambdaLg10 = -3, iters = 0;
     double prevErr = 0;
     const int max_iter = 20;
+    lg.mark();
+    // rows (Jacobian + residual) of the current estimate; every trial step below leaves the rows of the
+    // accepted estimate in shJ, so Rodrigues and the projection are evaluated once per trial
+    double err = pose_rows(lg, cam, h, corners, p, shJ);
     for (;;) {
-        {
-            double R[9], dR[27];
-            rodrigues_with_jacobian(p, R, dR);
-            for (int r = lg.lane(); r < 8; r += lg.nlanes()) pose_row(cam, h, corners, p, R, dR, r, shJ + r * 7);
-        }
-        lg.sync();
-        double e = 0;
-        B2A_UNROLL
-        for (int i = 0; i < 4; ++i) { const double a = shJ[(2 * i) * 7 + 6], b = shJ[(2 * i + 1) * 7 + 6]; e += a * a + b * b; }
-        const double errAtP = sqrt(e);
         for (int a = lg.lane(); a < 6; a += lg.nlanes()) {
             double s = 0;
             B2A_UNROLL
@@ -387,17 +392,18 @@ B2A_HD void solve_marker_pose(const LG &lg, const Camera &cam, float marker_leng
         lg.sync();
         B2A_UNROLL
         for (int a = 0; a < 6; ++a) prev[a] = p[a];
+        if (iters == 0) prevErr = err;
         lm_step(shN, lambdaLg10, prev, p);
-        if (iters == 0) prevErr = errAtP;
-        double err = pose_error(lg, cam, h, corners, p, shJ);
+        err = pose_rows(lg, cam, h, corners, p, shJ);
         while (err > prevErr && ++lambdaLg10 <= 16) {
             lm_step(shN, lambdaLg10, prev, p);
-            err = pose_error(lg, cam, h, corners, p, shJ);
+            err = pose_rows(lg, cam, h, corners, p, shJ);
         }
         lambdaLg10 = lambdaLg10 - 1 > -16 ? lambdaLg10 - 1 : -16;
         double dn = 0, pn = 0;
         B2A_UNROLL
         for (int a = 0; a < 6; ++a) { dn += (p[a] - prev[a]) * (p[a] - prev[a]); pn += prev[a] * prev[a]; }
+        lg.mark();
         if (++iters >= max_iter || sqrt(dn) < (double)FLT_EPSILON * sqrt(pn)) break;
         prevErr = err;
     }
