@@ -201,8 +201,10 @@ struct b2a_detector {
     uint32_t *d_masks = nullptr; size_t masks_words = 0;
     // border graph (core.h): anchors of all (frame,scale) masks of a sub-batch share one slice of these arrays
     uint2 *d_ast = nullptr; Seg *d_seg = nullptr, *d_sseg = nullptr; uint32_t *d_minoff = nullptr, *d_ssoff = nullptr; int2 *d_emit = nullptr; uint32_t *d_amap = nullptr;
-    unsigned anchors_cap = 0; int anchor_R = 8;
+    uint2 *d_starts = nullptr;
+    unsigned anchors_cap = 0, starts_cap = 0; int anchor_R = 32;
     int *d_counters = nullptr;               // [sub-batch] n_anchors (unsigned), then per-(f,s) arrays
+    unsigned *d_counters2 = nullptr;         // [sub-batch] n_starts
     int *d_surv_count = nullptr, *d_contour_count = nullptr, *d_iso_count = nullptr, *d_status = nullptr;
     uint4 *d_surv = nullptr, *d_sorted = nullptr;
     int *d_pts_off = nullptr; uint32_t *d_pts = nullptr; int pts_cap = 0;
@@ -291,8 +293,11 @@ static int create_impl(b2a_detector *d)
     TRY(dev_alloc(d, &d->d_ast, d->anchors_cap)); TRY(dev_alloc(d, &d->d_seg, d->anchors_cap));
     TRY(dev_alloc(d, &d->d_minoff, d->anchors_cap)); TRY(dev_alloc(d, &d->d_emit, d->anchors_cap));
     TRY(dev_alloc(d, &d->d_sseg, d->anchors_cap)); TRY(dev_alloc(d, &d->d_ssoff, d->anchors_cap));
-    TRY(dev_alloc(d, &d->d_amap, (size_t)B * nS * P));
+    TRY(dev_alloc(d, &d->d_amap, (size_t)B * nS * H * ((W + 31) / 32)));
+    d->starts_cap = d->anchors_cap;
+    TRY(dev_alloc(d, &d->d_starts, d->starts_cap));
     if (const char *e = std::getenv("B2A_ANCHOR_R")) { const int r = std::atoi(e); if (r >= 1 && r <= 32 && !(r & (r - 1))) d->anchor_R = r; }
+    TRY(dev_alloc(d, &d->d_counters2, d->n_sub_max));
     const size_t FS = (size_t)B * nS;
     TRY(dev_alloc(d, &d->d_counters, d->n_sub_max + 3 * FS + B));
     d->d_surv_count = d->d_counters + d->n_sub_max; d->d_contour_count = d->d_surv_count + FS; d->d_iso_count = d->d_contour_count + FS;
@@ -516,9 +521,11 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     BorderGraph bg;
     bg.ast = d->d_ast + (size_t)s.sb * slice; bg.seg = d->d_seg + (size_t)s.sb * slice; bg.minoff = d->d_minoff + (size_t)s.sb * slice;
     bg.sseg = d->d_sseg + (size_t)s.sb * slice; bg.ssoff = d->d_ssoff + (size_t)s.sb * slice;
-    bg.emit = d->d_emit + (size_t)s.sb * slice; bg.amap = d->d_amap + fs0 * (size_t)W * H;
+    bg.emit = d->d_emit + (size_t)s.sb * slice; bg.amap = d->d_amap + fs0 * (size_t)H * g.WW;
     bg.n_anchors = (unsigned *)d->d_counters + s.sb; bg.cap = slice;
-    const int Rm = d->anchor_R - 1, max_len = walk_max_len > 0 ? walk_max_len : g.maxPerim;
+    bg.starts = d->d_starts + (size_t)s.sb * (d->starts_cap / (unsigned)d->n_sub_max); bg.n_starts = d->d_counters2 + s.sb;
+    bg.starts_cap = d->starts_cap / (unsigned)d->n_sub_max;
+    const int Rm = d->anchor_R - 1, Rm2 = 8 * d->anchor_R - 1, max_len = walk_max_len > 0 ? walk_max_len : g.maxPerim;
     const unsigned walk_grid = (unsigned)d->num_sms * 8;
     uint32_t *masks = d->d_masks + fs0 * g.mask_plane;
     stage_mark(d, s, ST_THRESH);
@@ -534,7 +541,7 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
         d->launches++;
     }
     stage_mark(d, s, ST_ANCHORS);
-    k_anchors<<<d->num_sms * 8, 256, 0, st>>>(masks, bg, d->d_iso_count + fs0, Rm, g);
+    k_anchors<<<d->num_sms * 8, 256, 0, st>>>(masks, bg, d->d_iso_count + fs0, Rm, Rm2, g);
     d->launches++; DBG_SYNC(st);
     stage_mark(d, s, ST_SEGMENTS);
     k_segments<<<walk_grid, 256, 0, st>>>(masks, bg, max_len, d->d_tables, Rm, g);
@@ -542,14 +549,15 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     stage_mark(d, s, ST_CYCLES);
     k_skip<<<walk_grid, 256, 0, st>>>(bg, max_len);
     d->launches++; DBG_SYNC(st);
-    k_cycles<<<walk_grid, 256, 0, st>>>(bg, d->d_surv + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_contour_count + fs0, max_len, g);
+    k_cycles<<<walk_grid, 256, 0, st>>>(masks, bg, d->d_surv + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_contour_count + fs0, max_len, d->d_tables, Rm, g);
     d->launches++; DBG_SYNC(st);
     stage_mark(d, s, ST_SORT);
     k_sort_scan<<<(unsigned)FS, 1024, 0, st>>>(d->d_surv + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_sorted + fs0 * g.surv_cap,
-                                               d->d_pts_off + fs0 * g.surv_cap, d->d_status + b0, bg.n_anchors, bg.cap, g);
+                                               d->d_pts_off + fs0 * g.surv_cap, d->d_status + b0, bg.n_anchors, bg.cap, bg.n_starts, bg.starts_cap, g);
     d->launches++; DBG_SYNC(st);
     stage_mark(d, s, ST_ASSIGN);
-    k_assign<<<dim3(8, (unsigned)FS), 128, 0, st>>>(bg, d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap, g);
+    k_assign<<<dim3(8, (unsigned)FS), 128, 0, st>>>(masks, bg, d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,
+                                                    d->d_pts + fs0 * (size_t)g.pts_cap, d->d_tables, g);
     d->launches++; DBG_SYNC(st);
     k_assign_sub<<<walk_grid, 256, 0, st>>>(bg);
     d->launches++; DBG_SYNC(st);
@@ -713,6 +721,7 @@ static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *
     }
     const size_t FSmax = (size_t)d->cfg.max_batch * d->nScales;
     CU(cudaMemsetAsync(d->d_counters, 0, (d->n_sub_max + 3 * FSmax + d->cfg.max_batch) * sizeof(int), s0));
+    CU(cudaMemsetAsync(d->d_counters2, 0, d->n_sub_max * sizeof(unsigned), s0));
     // sub-batches
     const int nsub = std::max(1, std::min(std::min(d->n_streams, d->n_sub_max), B));
     std::vector<Sub> subs(nsub);

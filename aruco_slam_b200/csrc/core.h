@@ -127,6 +127,7 @@ struct MaskView {
         return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (bit & 31)) & 7u;
 #endif
     }
+    B2A_HD uint32_t word(int wx, int y) const { return ld_ro(plane + (size_t)(y + 1) * PWW + wx + 1); }   // wx = -1 / WW are the zero pads
     // 3x3 window of pixel (x,y) as 9 bits: rows y-1, y, y+1 at bits 0-2, 3-5, 6-8 (bit j = column x-1+j)
     B2A_HD unsigned win9(int x, int y) const { return win3(x, y - 1) | (win3(x, y) << 3) | (win3(x, y + 1) << 6); }
     // neighbour code of pixel (x,y): bit d = neighbour in direction d
@@ -147,21 +148,30 @@ struct MaskView {
 //     a set pixel c with code != 0 carries one state per maximal run of clear neighbours around
 //     its 8-ring that contains a 4-neighbour D in {E, N, W, S};  s_in = first_cw(code, D).
 // The run's clockwise-most 4-neighbour is the state's "canonical" D: D clear and (D-1 set or D-2 set).
-// A sparse, locally decidable subset of the states are ANCHORS:
-//     - the state hugs a clear W or E neighbour and y % R == 0, or a clear N or S neighbour and x % R == 0
-//     - or it satisfies the local necessary conditions of a border's first state (so every border
-//       carries at least one anchor whatever R is)
-// The stage then runs as   anchors -> segments (walk anchor to next anchor, all in parallel)
-//                                   -> cycles (hop over the anchors of a border: leader, length)
-//                                   -> order / offsets -> assign (position of each segment) -> emit points.
-// Tables, indexed by the 3x3 window w9 (and the incoming direction):
-//   succ[w9 | s_in << 9] : bits 0-2 successor direction, WT_OUTER / WT_HOLE start eligibility,
-//                          ST_ROW / ST_COL / ST_UNC anchor classes, ST_VALID
-//   pix[w9]              : byte k (canonical D = 2k): 0x80 present | ST_ROW/COL/UNC >> 2 | s_in
+// Two nested, locally decidable grids of states structure every border that is long enough to cross them:
+//     ANCHORS        the state hugs a clear W or E neighbour and y % R == 0, or a clear N or S neighbour and x % R == 0
+//     SUPER ANCHORS  the same with R2 = 8 R (a subset of the anchors)
+// and the borders that carry no anchor at all (confined to a grid cell) are found from the
+//     START CANDIDATES  states with the local necessary conditions of a border's first state.
+// The stage runs as
+//     anchors    : enumerate anchors (+ super flag) and start candidates, word-parallel
+//     segments   : every anchor walks to the next anchor (<= ~R steps, all in parallel)
+//     skip       : every super anchor hops over the plain anchors to the next super anchor
+//     cycles     : leader (= the segment holding the border's smallest start key = cv2's first point) and length,
+//                  by hops over the super anchors (or the plain anchors of a border without super anchors)
+//     direct     : every start candidate walks its border both ways and gives up at the first anchor or smaller
+//                  key; what closes is a border without anchors, reported with its length
+//     order / offsets, assign (position of every segment inside its border), emit (points)
+// Tables, indexed by the 3x3 window w9 and a direction:
+//   succ[w9 | s_in << 9] : successor direction of state (pixel, s_in) | its flags
+//   pred[w9 | t    << 9] : w9 = window of the previous border pixel p, t = direction p -> c:
+//                          s_in of the predecessor state (p, .) | that state's flags
+//   pix[w9]              : byte k (canonical D = 2k): 0x80 present | flags >> 2 | s_in   (host cross-check only)
+// flags: WT_OUTER / WT_HOLE start eligibility, ST_ROW / ST_COL grid classes, ST_UNC start candidate, ST_VALID
 // ---------------------------------------------------------------------------------------------
 enum { WT_OUTER = 8, WT_HOLE = 16, WT_ELIG = 24, ST_ROW = 32, ST_COL = 64, ST_UNC = 128, ST_VALID = 256 };
-enum : uint32_t { A_NONE = 0xFFFFFFFFu, SEG_OVERFLOW = 0x7FFFFFFFu };
-struct WalkTables { uint16_t succ[4096]; uint32_t pix[512]; };
+enum : uint32_t { A_NONE = 0xFFFFFFFFu, SEG_OVERFLOW = 0x7FFFFFFFu, SEG_LEN = 0x7FFFFFFFu, SEG_SUPER = 0x80000000u };
+struct WalkTables { uint16_t succ[4096]; uint16_t pred[4096]; uint32_t pix[512]; };
 
 B2A_HD unsigned state_eligibility(unsigned code, int s)
 {
@@ -190,6 +200,11 @@ B2A_HD void build_walk_table_entry(WalkTables &t, int idx)
     const int s = idx >> 9;
     const unsigned f = state_flags(code, s);
     t.succ[idx] = (uint16_t)(f ? ((unsigned)succ_dir(code, s) | f) : 0u);
+    {   // here s plays the role of t (direction p -> c); the predecessor state is (p, sp)
+        const int cw = first_cw(code, s);
+        const int sp = cw < 0 ? s : cw;
+        t.pred[idx] = (uint16_t)(code ? ((unsigned)sp | state_flags(code, sp)) : 0u);
+    }
     if (s == 0) {
         uint32_t p = 0;
         for (int k = 0; k < 4; ++k) {
@@ -207,61 +222,35 @@ B2A_HD uint32_t key_of(int x, int y, unsigned elig, int KS)
 {
     return (elig & WT_OUTER) ? (uint32_t)((y * KS + x) * 2) : (uint32_t)((y * KS + x + 1) * 2 + 1);
 }
-// Rm = R - 1 (R a power of two <= 32); flags carry ST_ROW / ST_COL / ST_UNC
+// Rm = R - 1 (R a power of two); flags carry ST_ROW / ST_COL
 B2A_HD bool is_anchor(unsigned flags, int x, int y, int Rm)
 {
-    return (flags & ST_UNC) || ((flags & ST_ROW) && !(y & Rm)) || ((flags & ST_COL) && !(x & Rm));
+    return ((flags & ST_ROW) && !(y & Rm)) || ((flags & ST_COL) && !(x & Rm));
 }
-// rank of state (pixel, s) among the anchors of its pixel (ordered by canonical D); pixword = pix[w9]
-B2A_HD int anchor_rank(uint32_t pixword, int s, int x, int y, int Rm)
+// bits of a mask word whose pixel x = 32 wx + b has x % R == 0 (R = Rm + 1, a power of two)
+B2A_HD uint32_t grid_cols(int wx, int Rm)
 {
-    int r = 0;
-    for (int k = 0; k < 4; ++k) {
-        const unsigned b = (pixword >> (8 * k)) & 0xFFu;
-        if (!(b & 0x80u)) continue;
-        if ((int)(b & 7u) == s) return r;
-        r += is_anchor((b << 2) & (ST_ROW | ST_COL | ST_UNC), x, y, Rm) ? 1 : 0;
-    }
-    return r;
-}
-// bits b-1, b, b+1 of the row whose words left / at / right of the pixel's word are ml, m, mr
-B2A_HD unsigned win3_words(uint32_t ml, uint32_t m, uint32_t mr, int b)
-{
-    const unsigned long long t = ((unsigned long long)m << 1) | (ml >> 31) | ((unsigned long long)(mr & 1u) << 33);
-    return (unsigned)(t >> b) & 7u;
-}
-// Pixels of mask word m (row y; ml / mr = the words left / right of it, u* the row above, d* the row below; bit i = pixel 32*w + i) that can carry an anchor:
-// border pixels (a clear 4-neighbour, at least one neighbour) on the R-grid or with the start conditions.
-B2A_HD uint32_t anchor_pixel_candidates(uint32_t m, uint32_t ml, uint32_t mr, uint32_t u, uint32_t ul, uint32_t ur,
-                                        uint32_t d, uint32_t dl, uint32_t dr, int y, int Rm, uint32_t &iso)
-{
-    const uint32_t mW = (m << 1) | (ml >> 31), mE = (m >> 1) | (mr << 31);
-    const uint32_t uW = (u << 1) | (ul >> 31), uE = (u >> 1) | (ur << 31);
-    const uint32_t dW = (d << 1) | (dl >> 31), dE = (d >> 1) | (dr << 31);
-    const uint32_t any = mW | mE | uW | u | uE | dW | d | dE;
-    iso = m & ~any;
-    uint32_t bp = m & ~(mW & mE & u & d) & any;
-    if (y & Rm) {
-        const uint32_t outer = m & ~mW & ~uW & ~u & ~uE, hole = m & ~mE & uE;
-        const uint32_t cols = 0xFFFFFFFFu / ((Rm >= 31) ? 0xFFFFFFFFu : ((2u << Rm) - 1u));     // bits with (b & Rm) == 0
-        bp &= outer | hole | cols;
-    }
-    return bp;
+    if (Rm >= 32) return ((wx << 5) & Rm) ? 0u : 1u;
+    return 0xFFFFFFFFu / ((Rm >= 31) ? 0xFFFFFFFFu : ((2u << Rm) - 1u));
 }
 
-// Word-parallel anchor enumeration for the 32 pixels of mask word m (no per-pixel table lookups):
-// A[k] = pixels whose state with canonical D = 2k (E, N, W, S) is an anchor; for those, hi[k] tells
-// whether s_in = D - 1 (bit set) or D - 2.  Same sets as pix[] + is_anchor(); a pixel's anchors are
-// ordered by k (anchor_rank).  rowflag: y % R == 0; cols: bits with x % R == 0.
+// Word-parallel enumeration for the 32 pixels of mask word m (row y; ml / mr = the words left / right of
+// it, u* the row above, d* the row below; bit i = pixel 32 w + i), per canonical direction D = 2k:
+//   A[k]  pixels whose state k is an anchor (rowflag: y % R == 0, cols: bits with x % R == 0)
+//   SU[k] ... is a super anchor (rowflag2 / cols2 for R2); a subset of A[k]
+//   U[k]  ... is a start candidate
+//   hi[k] s_in = D - 1 where set, else D - 2
+// A pixel's states are ordered by k; the states of a word by pixel, then k.
 B2A_HD void anchor_words(uint32_t m, uint32_t ml, uint32_t mr, uint32_t u, uint32_t ul, uint32_t ur, uint32_t d, uint32_t dl, uint32_t dr,
-                         bool rowflag, uint32_t cols, uint32_t A[4], uint32_t hi[4], uint32_t &iso)
+                         bool rowflag, uint32_t cols, bool rowflag2, uint32_t cols2,
+                         uint32_t A[4], uint32_t SU[4], uint32_t U[4], uint32_t hi[4], uint32_t &iso)
 {
     uint32_t n[8];
     n[0] = (m >> 1) | (mr << 31); n[1] = (u >> 1) | (ur << 31); n[2] = u; n[3] = (u << 1) | (ul >> 31);
     n[4] = (m << 1) | (ml >> 31); n[5] = (d << 1) | (dl >> 31); n[6] = d; n[7] = (d >> 1) | (dr << 31);
     iso = m & ~(n[0] | n[1] | n[2] | n[3] | n[4] | n[5] | n[6] | n[7]);
     const uint32_t outerCand = ~(n[1] | n[2] | n[3] | n[4]), holeCand = ~n[0] & n[1];
-    const uint32_t rows = rowflag ? 0xFFFFFFFFu : 0u;
+    const uint32_t rows = rowflag ? 0xFFFFFFFFu : 0u, rows2 = rowflag2 ? 0xFFFFFFFFu : 0u;
     B2A_UNROLL
     for (int k = 0; k < 4; ++k) {
         const int D = 2 * k;
@@ -273,19 +262,47 @@ B2A_HD void anchor_words(uint32_t m, uint32_t ml, uint32_t mr, uint32_t u, uint3
         uint32_t has[4];                         // has[j]: run contains direction 2 j
         has[k] = canon; has[(k + 1) & 3] = c2; has[(k + 2) & 3] = c4; has[(k + 3) & 3] = c6;
         const uint32_t row_t = has[0] | has[2], col_t = has[1] | has[3];
-        const uint32_t unc = (has[2] & outerCand) | (has[0] & ~has[2] & holeCand);
-        A[k] = canon & (unc | (row_t & rows) | (col_t & cols));
+        A[k] = canon & ((row_t & rows) | (col_t & cols));
+        SU[k] = canon & ((row_t & rows2) | (col_t & cols2));
+        U[k] = (has[2] & outerCand) | (has[0] & ~has[2] & holeCand);
         hi[k] = n[(D + 7) & 7];
     }
+}
+B2A_HD int state_dir(int k, uint32_t hi_k, int b) { return (2 * k + (((hi_k >> b) & 1u) ? 7 : 6)) & 7; }
+B2A_HD int popc32(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+// Rank of anchor state (x, y, s) among the anchors of its mask word (the word map holds the index of the
+// word's first anchor); -1 if the state is not an anchor of the word.  word(wx, y) reads a mask word.
+template <class Mask>
+B2A_HD int anchor_rank_in_word(const Mask &mk, int x, int y, int s, int Rm)
+{
+    const int wx = x >> 5, b = x & 31;
+    uint32_t A[4], SU[4], U[4], hi[4], iso;
+    anchor_words(mk.word(wx, y), mk.word(wx - 1, y), mk.word(wx + 1, y), mk.word(wx, y - 1), mk.word(wx - 1, y - 1), mk.word(wx + 1, y - 1),
+                 mk.word(wx, y + 1), mk.word(wx - 1, y + 1), mk.word(wx + 1, y + 1), !(y & Rm), grid_cols(wx, Rm), false, 0u, A, SU, U, hi, iso);
+    const uint32_t below = (1u << b) - 1u;
+    int r = popc32(A[0] & below) + popc32(A[1] & below) + popc32(A[2] & below) + popc32(A[3] & below);
+    B2A_UNROLL
+    for (int k = 0; k < 4; ++k) {
+        if (!((A[k] >> b) & 1u)) continue;
+        if (state_dir(k, hi[k], b) == s) return r;
+        ++r;
+    }
+    return -1;
 }
 
 // Walk from anchor state (x,y,s) to the next anchor.  len = number of states of the segment
 // (SEG_OVERFLOW once more than max_len steps were taken), minkey / minoff = smallest start key
-// among the segment's start-eligible states and its offset (A_NONE if none); (x,y,s) and w9 are
-// left at the next anchor.
+// among the segment's start-eligible states and its offset (A_NONE if none); (x,y,s) is left at the next anchor.
 template <class Win>
 B2A_HD void seg_walk(const Win &win, const uint16_t *__restrict__ succ, int KS, int Rm, int max_len,
-                     int &x, int &y, int &s, unsigned &w9, uint32_t &len, uint32_t &minkey, uint32_t &minoff)
+                     int &x, int &y, int &s, uint32_t &len, uint32_t &minkey, uint32_t &minoff)
 {
     unsigned e = succ[win.win9(x, y) | ((unsigned)s << 9)];
     uint32_t n = 0;
@@ -295,13 +312,12 @@ B2A_HD void seg_walk(const Win &win, const uint16_t *__restrict__ succ, int KS, 
         const int so = (int)(e & 7u);
         x += dir_dx(so); y += dir_dy(so); s = so ^ 4;
         ++n;
-        w9 = win.win9(x, y);
-        e = succ[w9 | ((unsigned)s << 9)];
+        e = succ[win.win9(x, y) | ((unsigned)s << 9)];
         if (is_anchor(e, x, y, Rm)) { len = n; return; }
         if (n > (uint32_t)max_len) { len = SEG_OVERFLOW; return; }
     }
 }
-// Emit the len points of the segment that starts at anchor state (x,y,s): point k goes to
+// Emit the len points of the segment that starts at state (x,y,s): point k goes to
 // out[pos + k] (+ n when negative: only the leader's segment wraps)
 template <class Win>
 B2A_HD void seg_emit(const Win &win, const uint16_t *__restrict__ succ, int x, int y, int s, int len, int pos, int n, uint32_t *__restrict__ out)
@@ -314,30 +330,59 @@ B2A_HD void seg_emit(const Win &win, const uint16_t *__restrict__ succ, int x, i
         x += dir_dx(so); y += dir_dy(so); s = so ^ 4;
     }
 }
-// seg[i] = (next anchor, previous anchor, segment length, segment min key).
+// A start candidate (x0,y0,s0) with start key key0 walks its border in both directions at once.
+// Returns the border length if the border carries no anchor and (x0,y0,s0) is its first state;
+// 0 as soon as an anchor or a start-eligible state with a smaller key is met (the border is then
+// reported through its anchors, or by that other state) or after max_len steps.
+template <class Win>
+B2A_HD int direct_walk(const Win &win, const uint16_t *__restrict__ succ, const uint16_t *__restrict__ pred, int KS, int Rm,
+                       int x0, int y0, int s0, uint32_t key0, int max_len)
+{
+    int xf = x0, yf = y0, sf = s0, xb = x0, yb = y0, sb = s0;
+    const unsigned e0 = succ[win.win9(x0, y0) | ((unsigned)s0 << 9)];
+    if (is_anchor(e0, x0, y0, Rm)) return 0;
+    int so = (int)(e0 & 7u);
+    int n = 0;
+    for (;;) {
+        xf += dir_dx(so); yf += dir_dy(so); sf = so ^ 4;
+        ++n;
+        if (xf == xb && yf == yb && sf == sb) return n;
+        const int xp = xb + dir_dx(sb), yp = yb + dir_dy(sb);
+        const unsigned wf = win.win9(xf, yf), wp = win.win9(xp, yp);       // twelve independent loads in flight
+        const unsigned ef = succ[wf | ((unsigned)sf << 9)], ep = pred[wp | ((unsigned)(sb ^ 4) << 9)];
+        if (is_anchor(ef, xf, yf, Rm) || ((ef & WT_ELIG) && key_of(xf, yf, ef, KS) < key0) || n > max_len) return 0;
+        sb = (int)(ep & 7u); xb = xp; yb = yp;
+        ++n;
+        if (xf == xb && yf == yb && sf == sb) return n;
+        if (is_anchor(ep, xb, yb, Rm) || ((ep & WT_ELIG) && key_of(xb, yb, ep, KS) < key0) || n > max_len) return 0;
+        so = (int)(ef & 7u);
+    }
+}
+
+// seg[i] = (next anchor, previous anchor, segment length | SEG_SUPER, segment min key).
 // Hop over the anchors of anchor i's border in both directions.  Returns the border length if
 // i's segment holds the border's smallest start key (i is the border's leader), 0 otherwise
-// (also when the border is longer than max_len, a segment overflowed, or stop(anchor) is true
+// (also when the border is longer than max_len, a segment overflowed, or stop(segment) is true
 // for an anchor of the border other than i).
 struct Seg { uint32_t next, prev, len, minkey; };
-struct NeverStop { B2A_HD bool operator()(uint32_t) const { return false; } };
+struct NeverStop { B2A_HD bool operator()(const Seg &) const { return false; } };
+struct StopAtSuper { B2A_HD bool operator()(const Seg &s) const { return (s.len & SEG_SUPER) != 0; } };
 template <class SegAt, class Stop>
 B2A_HD uint32_t cycle_leader(const SegAt &seg_at, const Stop &stop, uint32_t i, int max_len)
 {
     const Seg me = seg_at(i);
-    if (me.minkey == A_NONE || me.len == SEG_OVERFLOW) return 0;
-    uint32_t total = me.len, f = i, b = i, fn = me.next, bp = me.prev;
+    if (me.minkey == A_NONE || (me.len & SEG_LEN) == SEG_OVERFLOW) return 0;
+    uint32_t total = me.len & SEG_LEN, f = i, b = i, fn = me.next, bp = me.prev;
     for (;;) {
         if (fn == A_NONE || bp == A_NONE) return 0;
         if (fn == b) break;
-        if (stop(fn) || stop(bp)) return 0;
         const Seg sf = seg_at(fn), sb = seg_at(bp);
-        if (sf.minkey < me.minkey || sf.len == SEG_OVERFLOW) return 0;
-        total += sf.len; f = fn; fn = sf.next;
+        if (stop(sf) || sf.minkey < me.minkey || (sf.len & SEG_LEN) == SEG_OVERFLOW) return 0;
+        total += sf.len & SEG_LEN; f = fn; fn = sf.next;
         if (total > (uint32_t)max_len) return 0;
         if (bp == f) break;
-        if (sb.minkey < me.minkey || sb.len == SEG_OVERFLOW) return 0;
-        total += sb.len; b = bp; bp = sb.prev;
+        if (stop(sb) || sb.minkey < me.minkey || (sb.len & SEG_LEN) == SEG_OVERFLOW) return 0;
+        total += sb.len & SEG_LEN; b = bp; bp = sb.prev;
         if (total > (uint32_t)max_len) return 0;
     }
     return total;
@@ -349,37 +394,35 @@ B2A_HD void cycle_assign(const SegAt &seg_at, const Set &set, uint32_t i, int n,
 {
     const Seg me = seg_at(i);
     set(i, -minoff);
-    int pf = (int)me.len - minoff, pb = n - minoff;
+    int pf = (int)(me.len & SEG_LEN) - minoff, pb = n - minoff;
     uint32_t f = i, b = i, fn = me.next, bp = me.prev;
     for (;;) {
         if (fn == b) break;
         const Seg sf = seg_at(fn), sb = seg_at(bp);
-        set(fn, pf); pf += (int)sf.len; f = fn; fn = sf.next;
+        set(fn, pf); pf += (int)(sf.len & SEG_LEN); f = fn; fn = sf.next;
         if (bp == f) break;
-        pb -= (int)sb.len; set(bp, pb); b = bp; bp = sb.prev;
+        pb -= (int)(sb.len & SEG_LEN); set(bp, pb); b = bp; bp = sb.prev;
     }
 }
-// Second level: a pseudo-random 1/16 of the anchors are "super" anchors.  A super anchor's
-// segment runs to the next super anchor of its border (super_skip hops over the plain anchors in
-// between), so the leader / assign hops over a long border touch 16x fewer nodes; borders
-// without a super anchor are resolved on the plain anchors.
-B2A_HD bool is_super(uint32_t i) { return (((i ^ (i >> 9)) * 0x9E3779B1u) >> 28) == 0u; }
-struct IsSuper { B2A_HD bool operator()(uint32_t i) const { return is_super(i); } };
+// Second level: a super anchor's segment runs to the next super anchor of its border (super_skip hops over
+// the plain anchors in between; the R2 grid bounds their number), so the leader / assign hops over a long
+// border touch ~8x fewer nodes; borders without a super anchor are resolved on the plain anchors.
 // out: next super anchor (A_NONE on overflow), super segment length, min key, offset of the min-key state
 template <class SegAt, class MinoffAt>
 B2A_HD void super_skip(const SegAt &seg_at, const MinoffAt &minoff_at, uint32_t S, int max_len,
                        uint32_t &snext, uint32_t &slen, uint32_t &smin, uint32_t &soff)
 {
     uint32_t cur = S;
+    Seg sg = seg_at(S);
     slen = 0; smin = A_NONE; soff = 0;
     for (;;) {
-        const Seg sg = seg_at(cur);
-        if (sg.len == SEG_OVERFLOW || sg.next == A_NONE) { snext = A_NONE; slen = SEG_OVERFLOW; return; }
+        if ((sg.len & SEG_LEN) == SEG_OVERFLOW || sg.next == A_NONE) { snext = A_NONE; slen = SEG_OVERFLOW; return; }
         if (sg.minkey < smin) { smin = sg.minkey; soff = slen + minoff_at(cur); }
-        slen += sg.len;
+        slen += sg.len & SEG_LEN;
         if (slen > (uint32_t)max_len) { snext = A_NONE; slen = SEG_OVERFLOW; return; }
         cur = sg.next;
-        if (is_super(cur)) { snext = cur; return; }
+        sg = seg_at(cur);
+        if (sg.len & SEG_SUPER) { snext = cur; return; }
     }
 }
 // positions of the plain anchors behind super anchor S (whose own position is pos)
@@ -388,11 +431,11 @@ B2A_HD void super_assign(const SegAt &seg_at, const Set &set, uint32_t S, int po
 {
     Seg sg = seg_at(S);
     for (;;) {
-        pos += (int)sg.len;
+        pos += (int)(sg.len & SEG_LEN);
         const uint32_t cur = sg.next;
-        if (is_super(cur)) return;
-        set(cur, pos);
         sg = seg_at(cur);
+        if (sg.len & SEG_SUPER) return;
+        set(cur, pos);
     }
 }
 

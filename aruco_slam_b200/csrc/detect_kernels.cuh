@@ -5,9 +5,10 @@
 //   k_bgr2gray        A1   bgr8 -> gray (15-bit fixed point)
 //   k_threshold       A2   gray -> nScales bit-packed adaptive-threshold masks, one pass, shared-memory
 //                          staged row-prefix tile, ballot-packed output
-//   k_anchors         A3a  word-parallel enumeration of the border graph's anchor states
+//   k_anchors         A3a  word-parallel enumeration of the border graph's anchor states and start candidates
 //   k_segments        A3a  every anchor walks to the next anchor (short, independent walks)
-//   k_cycles          A3a  hop over each border's anchors: leader (first point), border length
+//   k_skip, k_cycles  A3a  hop over each border's (super) anchors: leader (first point), border length;
+//                          borders without anchors from their start candidates
 //   k_sort_scan       A3a  per (frame,scale): order kept borders like cv2.findContours, offsets
 //   k_assign, k_emit  A3a  position of every segment inside its border; emit the border points
 //   k_approx          A3b  warp-cooperative approxPolyDP + quad gates
@@ -280,42 +281,60 @@ __global__ void k_unpack_masks(const uint32_t *__restrict__ masks, uint8_t *__re
 }
 
 // ---------------------------------------------------------------------------------------------
-// A3a step 1: anchors of the border graph (core.h), one mask word (32 pixels) per thread.
-//   ast[i]  = (x | y << 16, (frame*nScales+scale) << 3 | s_in)
-//   amap[(fs*H + y)*W + x] = index of the pixel's first anchor (anchors of one pixel are consecutive)
+// A3a step 1: anchors and start candidates of the border graph (core.h), one mask word (32 pixels) per thread.
+//   ast[i]    = (x | y << 16, (frame*nScales+scale) << 4 | super << 3 | s_in)
+//   starts[j] = (x | y << 16, (frame*nScales+scale) << 4 | s_in)
+//   amap[(fs*H + y)*WW + wx] = index of the word's first anchor (anchors of one word are consecutive)
 // ---------------------------------------------------------------------------------------------
 struct BorderGraph {
     uint2 *ast;          // anchor states
-    Seg *seg;            // (next, prev, len, minkey)
+    Seg *seg;            // (next, prev, len | SEG_SUPER, minkey)
     uint32_t *minoff;    // offset of the segment's min-key state
     Seg *sseg;           // super anchors only: (next super, previous super, length up to it, min key)
     uint32_t *ssoff;     // super anchors only: offset of the min-key state from the super anchor
     int2 *emit;          // (position of the segment's first state in its border, 1 + slot of the border in `sorted`; 0 = not kept)
-    uint32_t *amap;      // per pixel of every (frame,scale): first anchor index
+    uint32_t *amap;      // per mask word of every (frame,scale): first anchor index
     unsigned *n_anchors; // this sub-batch's counter
     unsigned cap;
+    uint2 *starts;       // start candidates
+    unsigned *n_starts;
+    unsigned starts_cap;
 };
 
-__device__ __forceinline__ void load_walk_tables(const WalkTables *__restrict__ g, uint16_t *s_succ, uint32_t *s_pix)
+__device__ __forceinline__ void load_walk_tables(const WalkTables *__restrict__ g, uint16_t *s_succ, uint16_t *s_pred)
 {
     const uint4 *src = reinterpret_cast<const uint4 *>(g);
     if (s_succ) for (int i = threadIdx.x; i < 512; i += blockDim.x) reinterpret_cast<uint4 *>(s_succ)[i] = __ldg(src + i);
-    if (s_pix) for (int i = threadIdx.x; i < 128; i += blockDim.x) reinterpret_cast<uint4 *>(s_pix)[i] = __ldg(src + 512 + i);
+    if (s_pred) for (int i = threadIdx.x; i < 512; i += blockDim.x) reinterpret_cast<uint4 *>(s_pred)[i] = __ldg(src + 512 + i);
     __syncthreads();
 }
 
+// warp-aggregated append of cnt items per lane: returns the lane's first slot
+__device__ __forceinline__ unsigned warp_append(unsigned *counter, int cnt, int lane)
+{
+    int incl = cnt;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) { const int o = __shfl_up_sync(0xFFFFFFFFu, incl, dd); if (lane >= dd) incl += o; }
+    const int tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    unsigned base = 0;
+    if (tot) {
+        if (lane == 0) base = atomicAdd(counter, (unsigned)tot);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    }
+    return base + (unsigned)(incl - cnt);
+}
+
 __global__ void __launch_bounds__(256)
-k_anchors(const uint32_t *__restrict__ masks, BorderGraph bg, int *__restrict__ iso_count, int Rm, DetGeom g)
+k_anchors(const uint32_t *__restrict__ masks, BorderGraph bg, int *__restrict__ iso_count, int Rm, int Rm2, DetGeom g)
 {
     const unsigned words_per_plane = (unsigned)g.H * (unsigned)g.WW;
     const unsigned total = (unsigned)(g.B * g.nScales) * words_per_plane;
     const int lane = threadIdx.x & 31;
     const unsigned stride = gridDim.x * blockDim.x;
-    const uint32_t cols = 0xFFFFFFFFu / ((Rm >= 31) ? 0xFFFFFFFFu : ((2u << Rm) - 1u));       // bits with (b & Rm) == 0
-    // whole warps iterate together (warp-aggregated append); word index = (fs * H + y) * WW + wx
+    // whole warps iterate together (warp-aggregated appends); word index = (fs * H + y) * WW + wx
     for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < total; i0 += stride) {
         const unsigned i = i0 + lane;
-        uint32_t A[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+        uint32_t A[4] = {0, 0, 0, 0}, SU[4] = {0, 0, 0, 0}, U[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
         int fs = 0, y = 0, wx = 0;
         if (i < total) {
             fs = (int)(i / words_per_plane);
@@ -328,37 +347,39 @@ k_anchors(const uint32_t *__restrict__ masks, BorderGraph bg, int *__restrict__ 
                 const uint32_t u = __ldg(row - g.PWW), ul = __ldg(row - g.PWW - 1), ur = __ldg(row - g.PWW + 1);
                 const uint32_t d = __ldg(row + g.PWW), dl = __ldg(row + g.PWW - 1), dr = __ldg(row + g.PWW + 1);
                 uint32_t iso;
-                anchor_words(m, ml, mr, u, ul, ur, d, dl, dr, !(y & Rm), cols, A, hi, iso);
+                anchor_words(m, ml, mr, u, ul, ur, d, dl, dr, !(y & Rm), grid_cols(wx, Rm), !(y & Rm2), grid_cols(wx, Rm2), A, SU, U, hi, iso);
                 if (iso) atomicAdd(&iso_count[fs], __popc(iso));
             }
         }
+        // anchors: pixel by pixel, canonical directions E, N, W, S inside a pixel
         const int cnt = __popc(A[0]) + __popc(A[1]) + __popc(A[2]) + __popc(A[3]);
-        int incl = cnt;
-#pragma unroll
-        for (int dd = 1; dd < 32; dd <<= 1) { const int o = __shfl_up_sync(0xFFFFFFFFu, incl, dd); if (lane >= dd) incl += o; }
-        const int tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        if (tot == 0) continue;
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(bg.n_anchors, (unsigned)tot);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        unsigned pos = base + (unsigned)(incl - cnt);
-        // the word's anchors, pixel by pixel, canonical directions E, N, W, S inside a pixel
+        unsigned pos = warp_append(bg.n_anchors, cnt, lane);
+        if (cnt && pos < bg.cap) bg.amap[((size_t)fs * g.H + y) * g.WW + wx] = pos;
         for (uint32_t px = A[0] | A[1] | A[2] | A[3]; px; px &= px - 1) {
             const int b = __ffs(px) - 1, x = wx * 32 + b;
-            if (pos < bg.cap) bg.amap[((size_t)fs * g.H + y) * g.W + x] = pos;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (!((A[k] >> b) & 1u)) continue;
                 if (pos < bg.cap) {
-                    const unsigned s_in = (unsigned)(2 * k + (((hi[k] >> b) & 1u) ? 7 : 6)) & 7u;
-                    bg.ast[pos] = make_uint2((unsigned)x | ((unsigned)y << 16), ((unsigned)fs << 3) | s_in);
+                    const unsigned sup = (SU[k] >> b) & 1u;
+                    bg.ast[pos] = make_uint2((unsigned)x | ((unsigned)y << 16), ((unsigned)fs << 4) | (sup << 3) | (unsigned)state_dir(k, hi[k], b));
                     bg.seg[pos] = Seg{A_NONE, A_NONE, 0u, A_NONE};
                     bg.emit[pos] = make_int2(0, 0);
-                    if (is_super(pos)) bg.sseg[pos] = Seg{A_NONE, A_NONE, 0u, A_NONE};
+                    if (sup) bg.sseg[pos] = Seg{A_NONE, A_NONE, 0u, A_NONE};
                 }
                 ++pos;
             }
         }
+        // start candidates
+        const int ucnt = __popc(U[0]) + __popc(U[1]) + __popc(U[2]) + __popc(U[3]);
+        unsigned upos = warp_append(bg.n_starts, ucnt, lane);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            for (uint32_t px = U[k]; px; px &= px - 1) {
+                const int b = __ffs(px) - 1;
+                if (upos < bg.starts_cap) bg.starts[upos] = make_uint2((unsigned)(wx * 32 + b) | ((unsigned)y << 16), ((unsigned)fs << 4) | (unsigned)state_dir(k, hi[k], b));
+                ++upos;
+            }
     }
 }
 
@@ -369,32 +390,34 @@ __global__ void __launch_bounds__(256)
 k_segments(const uint32_t *__restrict__ masks, BorderGraph bg, int max_len, const WalkTables *__restrict__ tables, int Rm, DetGeom g)
 {
     __shared__ __align__(16) uint16_t s_succ[4096];
-    __shared__ __align__(16) uint32_t s_pix[512];
     unsigned n = *bg.n_anchors;
     if (n > bg.cap) n = bg.cap;
     if (blockIdx.x * blockDim.x >= n) return;
-    load_walk_tables(tables, s_succ, s_pix);
+    load_walk_tables(tables, s_succ, nullptr);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint2 a = bg.ast[i];
-        const int fs = (int)(a.y >> 3);
+        const int fs = (int)(a.y >> 4);
         int x = (int)(a.x & 0xFFFFu), y = (int)(a.x >> 16), s = (int)(a.y & 7u);
         MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
-        unsigned w9; uint32_t len, minkey, moff;
-        seg_walk(rd, s_succ, g.KS, Rm, max_len, x, y, s, w9, len, minkey, moff);
+        uint32_t len, minkey, moff;
+        seg_walk(rd, s_succ, g.KS, Rm, max_len, x, y, s, len, minkey, moff);
         uint32_t j = A_NONE;
         if (len != SEG_OVERFLOW) {
-            j = bg.amap[((size_t)fs * g.H + y) * g.W + x] + (uint32_t)anchor_rank(s_pix[w9], s, x, y, Rm);
-            if (j >= n) j = A_NONE;                                   // only after an anchor-list overflow (status 3)
+            const int r = anchor_rank_in_word(rd, x, y, s, Rm);
+            j = bg.amap[((size_t)fs * g.H + y) * g.WW + (x >> 5)] + (uint32_t)r;
+            if (r < 0 || j >= n) j = A_NONE;                          // only after an anchor-list overflow (status 3)
         }
-        bg.seg[i].next = j; bg.seg[i].len = len; bg.seg[i].minkey = minkey;
+        bg.seg[i].next = j; bg.seg[i].len = len | ((a.y & 8u) ? SEG_SUPER : 0u); bg.seg[i].minkey = minkey;
         bg.minoff[i] = moff;
         if (j != A_NONE) bg.seg[j].prev = i;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// A3a step 3: one thread per anchor hops over its border's anchors; the leader (smallest start key)
-// reports the border.   surv[fs*surv_cap + slot] = (key, length, leader anchor, offset of the first point)
+// A3a step 3: super anchors skip to the next super anchor; then one thread per anchor hops over its
+// border's (super) anchors and one thread per start candidate walks the borders without anchors; the
+// leaders report.   surv[fs*surv_cap + slot] = (key, length, leader anchor | x + (y << 16), kind)
+//   kind 0: leader is a plain anchor, 1: a super anchor, 2 | s_in << 8: a border without anchors from its first state
 // ---------------------------------------------------------------------------------------------
 struct SegLoad {
     const Seg *seg;
@@ -404,13 +427,11 @@ struct SegLoad {
         return Seg{v.x, v.y, v.z, v.w};
     }
 };
-
 struct MinoffLoad {
     const uint32_t *m;
     __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return __ldcg(m + i); }
 };
 
-// super anchors skip to the next super anchor of their border
 __global__ void __launch_bounds__(256)
 k_skip(BorderGraph bg, int max_len)
 {
@@ -419,7 +440,7 @@ k_skip(BorderGraph bg, int max_len)
     const SegLoad seg_at{bg.seg};
     const MinoffLoad minoff_at{bg.minoff};
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (!is_super(i)) continue;
+        if (!(bg.ast[i].y & 8u)) continue;
         uint32_t snext, slen, smin, soff;
         super_skip(seg_at, minoff_at, i, max_len, snext, slen, smin, soff);
         bg.sseg[i].next = snext; bg.sseg[i].len = slen; bg.sseg[i].minkey = smin;
@@ -428,23 +449,42 @@ k_skip(BorderGraph bg, int max_len)
     }
 }
 
-// surv[fs*surv_cap + slot] = (key, length, leader anchor, 1 if the leader is a super anchor)
-__global__ void __launch_bounds__(256)
-k_cycles(BorderGraph bg, uint4 *__restrict__ surv, int *__restrict__ surv_count, int *__restrict__ contour_count, int max_len, DetGeom g)
+__device__ __forceinline__ void report_border(uint4 *__restrict__ surv, int *__restrict__ surv_count, int *__restrict__ contour_count,
+                                              int fs, uint32_t key, uint32_t len, uint32_t who, uint32_t kind, const DetGeom &g)
 {
-    unsigned n = *bg.n_anchors;
+    atomicAdd(&contour_count[fs], 1);
+    if ((int)len >= g.minPerim && (int)len <= g.maxPerim) {
+        const int slot = atomicAdd(&surv_count[fs], 1);
+        if (slot < g.surv_cap) surv[(size_t)fs * g.surv_cap + slot] = make_uint4(key, len, who, kind);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_cycles(const uint32_t *__restrict__ masks, BorderGraph bg, uint4 *__restrict__ surv, int *__restrict__ surv_count, int *__restrict__ contour_count,
+         int max_len, const WalkTables *__restrict__ tables, int Rm, DetGeom g)
+{
+    __shared__ __align__(16) uint16_t s_succ[4096];
+    __shared__ __align__(16) uint16_t s_pred[4096];
+    unsigned n = *bg.n_anchors, ns = *bg.n_starts;
     if (n > bg.cap) n = bg.cap;
+    if (ns > bg.starts_cap) ns = bg.starts_cap;
+    load_walk_tables(tables, s_succ, s_pred);
     const SegLoad seg_at{bg.seg}, sseg_at{bg.sseg};
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const bool sup = is_super(i);
-        const uint32_t len = sup ? cycle_leader(sseg_at, NeverStop{}, i, max_len) : cycle_leader(seg_at, IsSuper{}, i, max_len);
-        if (!len) continue;
-        const int fs = (int)(bg.ast[i].y >> 3);
-        atomicAdd(&contour_count[fs], 1);
-        if ((int)len >= g.minPerim && (int)len <= g.maxPerim) {
-            const int slot = atomicAdd(&surv_count[fs], 1);
-            if (slot < g.surv_cap) surv[(size_t)fs * g.surv_cap + slot] = make_uint4(sup ? bg.sseg[i].minkey : bg.seg[i].minkey, len, i, sup ? 1u : 0u);
-        }
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    for (unsigned i = tid; i < n; i += nthr) {
+        const uint2 a = bg.ast[i];
+        const bool sup = (a.y & 8u) != 0;
+        const uint32_t len = sup ? cycle_leader(sseg_at, NeverStop{}, i, max_len) : cycle_leader(seg_at, StopAtSuper{}, i, max_len);
+        if (len) report_border(surv, surv_count, contour_count, (int)(a.y >> 4), sup ? bg.sseg[i].minkey : bg.seg[i].minkey, len, i, sup ? 1u : 0u, g);
+    }
+    for (unsigned i = tid; i < ns; i += nthr) {
+        const uint2 c = bg.starts[i];
+        const int fs = (int)(c.y >> 4), x = (int)(c.x & 0xFFFFu), y = (int)(c.x >> 16), s0 = (int)(c.y & 7u);
+        MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
+        const unsigned e0 = s_succ[rd.win9(x, y) | ((unsigned)s0 << 9)];
+        const uint32_t key0 = key_of(x, y, e0, g.KS);
+        const int len = direct_walk(rd, s_succ, s_pred, g.KS, Rm, x, y, s0, key0, max_len);
+        if (len > 0) report_border(surv, surv_count, contour_count, fs, key0, (uint32_t)len, c.x, 2u | ((unsigned)s0 << 8), g);
     }
 }
 
@@ -454,7 +494,8 @@ k_cycles(BorderGraph bg, uint4 *__restrict__ surv, int *__restrict__ surv_count,
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 k_sort_scan(const uint4 *__restrict__ surv, int *__restrict__ surv_count, uint4 *__restrict__ sorted,
-            int *__restrict__ pts_off, int *__restrict__ status, const unsigned *__restrict__ n_anchors, unsigned anchors_cap, DetGeom g)
+            int *__restrict__ pts_off, int *__restrict__ status, const unsigned *__restrict__ n_anchors, unsigned anchors_cap,
+            const unsigned *__restrict__ n_starts, unsigned starts_cap, DetGeom g)
 {
     __shared__ uint32_t s_key[SORT_CAP];
     __shared__ uint16_t s_idx[SORT_CAP];
@@ -462,7 +503,7 @@ k_sort_scan(const uint4 *__restrict__ surv, int *__restrict__ surv_count, uint4 
     const int fs = blockIdx.x;
     int n = surv_count[fs];
     if (n > g.surv_cap) { n = g.surv_cap; if (threadIdx.x == 0) status[fs / g.nScales] = 3; }
-    if (threadIdx.x == 0 && *n_anchors > anchors_cap) status[fs / g.nScales] = 3;       // anchor list overflowed: borders are missing
+    if (threadIdx.x == 0 && (*n_anchors > anchors_cap || *n_starts > starts_cap)) status[fs / g.nScales] = 3;   // a list overflowed: borders are missing
     int N = 32; while (N < n) N <<= 1;
     const uint4 *in = surv + (size_t)fs * g.surv_cap;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
@@ -515,20 +556,30 @@ struct EmitSet {
     __device__ __forceinline__ void operator()(uint32_t a, int pos) const { emit[a] = make_int2(pos, slot1); }
 };
 
-// A3a step 5: the leader of every kept border tells the border's anchors where their segments go
+// A3a step 5: the leader of every kept border tells the border's (super) anchors where their segments go;
+// a border without anchors is written out directly from its first state
 __global__ void __launch_bounds__(128)
-k_assign(BorderGraph bg, const uint4 *__restrict__ sorted, const int *__restrict__ surv_count, const int *__restrict__ pts_off, DetGeom g)
+k_assign(const uint32_t *__restrict__ masks, BorderGraph bg, const uint4 *__restrict__ sorted, const int *__restrict__ surv_count,
+         const int *__restrict__ pts_off, uint32_t *__restrict__ pts, const WalkTables *__restrict__ tables, DetGeom g)
 {
+    __shared__ __align__(16) uint16_t s_succ[4096];
     const int fs = blockIdx.y;
     const int n = surv_count[fs];
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    load_walk_tables(tables, s_succ, nullptr);
     const SegLoad seg_at{bg.seg};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int off = pts_off[(size_t)fs * g.surv_cap + i];
         if (off < 0) continue;
         const uint4 e = sorted[(size_t)fs * g.surv_cap + i];
         const int slot1 = fs * g.surv_cap + i + 1, len = (int)e.y;
-        if (e.w) cycle_assign(SegLoad{bg.sseg}, EmitSet{bg.emit, slot1}, e.z, len, (int)bg.ssoff[e.z]);
-        else cycle_assign(seg_at, EmitSet{bg.emit, slot1}, e.z, len, (int)bg.minoff[e.z]);
+        const unsigned kind = e.w & 3u;
+        if (kind == 1u) cycle_assign(SegLoad{bg.sseg}, EmitSet{bg.emit, slot1}, e.z, len, (int)bg.ssoff[e.z]);
+        else if (kind == 0u) cycle_assign(seg_at, EmitSet{bg.emit, slot1}, e.z, len, (int)bg.minoff[e.z]);
+        else {
+            MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
+            seg_emit(rd, s_succ, (int)(e.z & 0xFFFFu), (int)(e.z >> 16), (int)(e.w >> 8), len, 0, len, pts + (size_t)fs * g.pts_cap + off);
+        }
     }
 }
 
@@ -540,7 +591,7 @@ k_assign_sub(BorderGraph bg)
     if (n > bg.cap) n = bg.cap;
     const SegLoad seg_at{bg.seg};
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (!is_super(i)) continue;
+        if (!(bg.ast[i].y & 8u)) continue;
         const int2 e = bg.emit[i];
         if (e.y == 0) continue;
         super_assign(seg_at, EmitSet{bg.emit, e.y}, i, e.x);
@@ -561,10 +612,10 @@ k_emit(const uint32_t *__restrict__ masks, BorderGraph bg, const uint4 *__restri
         const int2 e = bg.emit[i];
         if (e.y == 0) continue;
         const uint2 a = bg.ast[i];
-        const int fs = (int)(a.y >> 3);
+        const int fs = (int)(a.y >> 4);
         const int len = (int)__ldg(&sorted[e.y - 1].y), off = __ldg(&pts_off[e.y - 1]);
         MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
-        seg_emit(rd, s_succ, (int)(a.x & 0xFFFFu), (int)(a.x >> 16), (int)(a.y & 7u), (int)bg.seg[i].len, e.x, len, pts + (size_t)fs * g.pts_cap + off);
+        seg_emit(rd, s_succ, (int)(a.x & 0xFFFFu), (int)(a.x >> 16), (int)(a.y & 7u), (int)(bg.seg[i].len & SEG_LEN), e.x, len, pts + (size_t)fs * g.pts_cap + off);
     }
 }
 

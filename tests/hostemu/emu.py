@@ -64,7 +64,7 @@ def params_for(dic, max_cand=2048, max_markers=256, surv_cap=4096):
     return p
 
 
-def detect(gray, dic, masks=None, dbg_scale=-1, anchor_R=8):
+def detect(gray, dic, masks=None, dbg_scale=-1, anchor_R=32):
     gray = np.ascontiguousarray(gray, np.uint8)
     H, W = gray.shape
     p = params_for(dic)

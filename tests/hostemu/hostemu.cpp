@@ -97,44 +97,44 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
     for (int s = 0; s < nS; ++s) {
         const uint32_t *pl = masks.data() + plane_words * s;
         MaskView mv{pl, PWW};
-        struct Surv { uint32_t key; int len; uint32_t leader; int super; };
+        struct Surv { uint32_t key; int len; uint32_t who; unsigned kind; };
         std::vector<Surv> surv;
         int ncont = 0;
-        // --- anchors (k_anchors, one word at a time) ---
+        // --- anchors and start candidates (k_anchors, one word at a time) ---
         const bool device_like = anchor_R < 0;
-        const int Rm = (device_like ? -anchor_R : anchor_R) - 1;
-        std::vector<uint32_t> ax, ay, as_;
+        const int R = device_like ? -anchor_R : anchor_R;
+        const int Rm = R - 1, Rm2 = 8 * R - 1;
+        std::vector<uint32_t> ax, ay, as_, asup, cx, cy, cs;
         std::vector<Seg> seg;
-        std::vector<uint32_t> amap((size_t)W * H, A_NONE), minoff;
+        std::vector<uint32_t> amap((size_t)WW * H, A_NONE), minoff;
         for (int y = 0; y < H; ++y)
             for (int wx = 0; wx < WW; ++wx) {
                 const uint32_t *row = pl + (size_t)(y + 1) * PWW + wx + 1;
                 const uint32_t m = row[0];
                 if (!m) continue;
                 // word-parallel enumeration (k_anchors) ...
-                uint32_t A[4], hi[4], iso;
-                const uint32_t cols = 0xFFFFFFFFu / ((Rm >= 31) ? 0xFFFFFFFFu : ((2u << Rm) - 1u));
-                anchor_words(m, row[-1], row[1], row[-PWW], row[-PWW - 1], row[-PWW + 1], row[PWW], row[PWW - 1], row[PWW + 1], !(y & Rm), cols, A, hi, iso);
+                uint32_t A[4], SU[4], U[4], hi[4], iso;
+                anchor_words(m, row[-1], row[1], row[-PWW], row[-PWW - 1], row[-PWW + 1], row[PWW], row[PWW - 1], row[PWW + 1],
+                             !(y & Rm), grid_cols(wx, Rm), !(y & Rm2), grid_cols(wx, Rm2), A, SU, U, hi, iso);
                 ncont += __builtin_popcount(iso);
+                if (A[0] | A[1] | A[2] | A[3]) amap[(size_t)y * WW + wx] = (uint32_t)ax.size();
                 // ... cross-checked against the per-pixel window tables the walkers use
-                uint32_t iso2;
-                const uint32_t bp = anchor_pixel_candidates(m, row[-1], row[1], row[-PWW], row[-PWW - 1], row[-PWW + 1], row[PWW], row[PWW - 1], row[PWW + 1], y, Rm, iso2);
-                if (iso2 != iso || ((A[0] | A[1] | A[2] | A[3]) & ~bp)) return -108;
                 for (int b = 0; b < 32; ++b) {
                     const int x = wx * 32 + b;
                     if (x >= W) break;
                     const unsigned w9 = mv.win9(x, y);
                     const uint32_t p = ((w9 >> 4) & 1u) ? wt.pix[w9] : 0u;
-                    bool first = true;
+                    if ((bool)((iso >> b) & 1u) != (((w9 >> 4) & 1u) && MaskView::code_of_win9(w9) == 0)) return -108;
                     for (int k = 0; k < 4; ++k) {
                         const unsigned e = (p >> (8 * k)) & 0xFFu;
-                        const bool anchor = (e & 0x80u) && is_anchor((e << 2) & (ST_ROW | ST_COL | ST_UNC), x, y, Rm);
-                        if (anchor != (bool)((A[k] >> b) & 1u)) return -109;
-                        if (!anchor) continue;
-                        if ((int)(e & 7u) != ((2 * k + (((hi[k] >> b) & 1u) ? 7 : 6)) & 7)) return -110;
-                        if (first) amap[(size_t)y * W + x] = (uint32_t)ax.size();
-                        first = false;
-                        ax.push_back(x); ay.push_back(y); as_.push_back(e & 7u);
+                        const unsigned fl = (e << 2) & (ST_ROW | ST_COL | ST_UNC);
+                        const bool anchor = (e & 0x80u) && is_anchor(fl, x, y, Rm), sup = (e & 0x80u) && is_anchor(fl, x, y, Rm2);
+                        const bool cand = (e & 0x80u) && (fl & ST_UNC);
+                        if (anchor != (bool)((A[k] >> b) & 1u) || sup != (bool)((SU[k] >> b) & 1u) || cand != (bool)((U[k] >> b) & 1u)) return -109;
+                        if ((anchor || cand) && (int)(e & 7u) != state_dir(k, hi[k], b)) return -110;
+                        if (sup && !anchor) return -111;
+                        if (anchor) { ax.push_back(x); ay.push_back(y); as_.push_back(e & 7u); asup.push_back(sup); }
+                        if (cand) { cx.push_back(x); cy.push_back(y); cs.push_back(e & 7u); }
                     }
                 }
             }
@@ -147,17 +147,19 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
         // --- segments (k_segments) ---
         for (uint32_t i = 0; i < nA; ++i) {
             int x = (int)ax[i], y = (int)ay[i], st = (int)as_[i];
-            unsigned w9; uint32_t len, mk, mo;
+            uint32_t len, mk, mo;
             CheckedView cv{pl, PWW, W, H};
-            seg_walk(cv, wt.succ, KS, Rm, max_len, x, y, st, w9, len, mk, mo);
+            seg_walk(cv, wt.succ, KS, Rm, max_len, x, y, st, len, mk, mo);
             if (cv.bad) return -106;
-            seg[i].len = len; seg[i].minkey = mk; minoff[i] = mo;
+            seg[i].len = len | (asup[i] ? SEG_SUPER : 0u); seg[i].minkey = mk; minoff[i] = mo;
             if (len == SEG_OVERFLOW) { if (device_like) continue; return -101; }
-            const uint32_t base = amap[(size_t)y * W + x];
+            const uint32_t base = amap[(size_t)y * WW + (x >> 5)];
             if (base == A_NONE) return -102;
-            const uint32_t j = base + (uint32_t)anchor_rank(wt.pix[w9], st, x, y, Rm);
+            const int r = anchor_rank_in_word(mv, x, y, st, Rm);
+            if (r < 0) return -112;
+            const uint32_t j = base + (uint32_t)r;
             if (j >= nA || (int)ax[j] != x || (int)ay[j] != y || (int)as_[j] != st) return -103;
-            seg[i].next = j; seg[i].len = len; seg[i].minkey = mk; minoff[i] = mo;
+            seg[i].next = j;
             if (seg[j].prev != A_NONE) return -104;
             seg[j].prev = i;
         }
@@ -167,20 +169,32 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
         std::vector<Seg> sseg(nA, Seg{A_NONE, A_NONE, 0u, A_NONE});
         std::vector<uint32_t> ssoff(nA, 0);
         for (uint32_t i = 0; i < nA; ++i) {
-            if (!is_super(i)) continue;
+            if (!asup[i]) continue;
             uint32_t snext, slen, smin, soff;
             super_skip(seg_at, minoff_at, i, max_len, snext, slen, smin, soff);
             sseg[i].next = snext; sseg[i].len = slen; sseg[i].minkey = smin; ssoff[i] = soff;
             if (snext != A_NONE) { if (sseg[snext].prev != A_NONE) return -107; sseg[snext].prev = i; }
         }
         auto sseg_at = [&](uint32_t i) { return sseg[i]; };
-        // --- cycles (k_cycles) ---
+        // --- cycles (k_cycles): borders with anchors from their leaders, the others from their start candidates ---
         for (uint32_t i = 0; i < nA; ++i) {
-            const bool sup = is_super(i);
-            const uint32_t len = sup ? cycle_leader(sseg_at, NeverStop{}, i, max_len) : cycle_leader(seg_at, IsSuper{}, i, max_len);
+            const bool sup = asup[i];
+            const uint32_t len = sup ? cycle_leader(sseg_at, NeverStop{}, i, max_len) : cycle_leader(seg_at, StopAtSuper{}, i, max_len);
             if (!len) continue;
             ++ncont;
-            if ((int)len >= minPerim && (int)len <= maxPerim) surv.push_back({sup ? sseg[i].minkey : seg[i].minkey, (int)len, i, sup ? 1 : 0});
+            if ((int)len >= minPerim && (int)len <= maxPerim) surv.push_back({sup ? sseg[i].minkey : seg[i].minkey, (int)len, i, sup ? 1u : 0u});
+        }
+        for (size_t c = 0; c < cx.size(); ++c) {
+            const int x = (int)cx[c], y = (int)cy[c], s0 = (int)cs[c];
+            const unsigned e0 = wt.succ[mv.win9(x, y) | ((unsigned)s0 << 9)];
+            if (!(e0 & WT_ELIG)) return -113;
+            const uint32_t key0 = key_of(x, y, e0, KS);
+            CheckedView cv{pl, PWW, W, H};
+            const int len = direct_walk(cv, wt.succ, wt.pred, KS, Rm, x, y, s0, key0, max_len);
+            if (cv.bad) return -114;
+            if (len <= 0) continue;
+            ++ncont;
+            if (len >= minPerim && len <= maxPerim) surv.push_back({key0, len, (uint32_t)x | ((uint32_t)y << 16), 2u | ((unsigned)s0 << 8)});
         }
         if (n_contours) n_contours[s] = ncont;
         std::sort(surv.begin(), surv.end(), [](const Surv &a, const Surv &b) { return a.key > b.key; });
@@ -190,17 +204,18 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
         if (s == dbg_scale && dbg_nkept) *dbg_nkept = (int)surv.size();
         for (size_t i = 0; i < surv.size(); ++i) {
             const Surv &e = surv[i];
-            // --- assign + emit (k_assign, k_emit) ---
+            // --- assign + emit (k_assign, k_assign_sub, k_emit) ---
             std::vector<uint32_t> pts(e.len, 0xFFFFFFFFu);
             std::vector<std::pair<uint32_t, int>> placed;
             auto place = [&](uint32_t a, int pos) { placed.push_back({a, pos}); };
-            if (e.super) {
-                cycle_assign(sseg_at, place, e.leader, e.len, (int)ssoff[e.leader]);
+            if ((e.kind & 3u) == 1u) {
+                cycle_assign(sseg_at, place, e.who, e.len, (int)ssoff[e.who]);
                 const size_t nsup = placed.size();
                 for (size_t k = 0; k < nsup; ++k) super_assign(seg_at, place, placed[k].first, placed[k].second);
-            } else cycle_assign(seg_at, place, e.leader, e.len, (int)minoff[e.leader]);
+            } else if ((e.kind & 3u) == 0u) cycle_assign(seg_at, place, e.who, e.len, (int)minoff[e.who]);
+            else seg_emit(mv, wt.succ, (int)(e.who & 0xFFFFu), (int)(e.who >> 16), (int)(e.kind >> 8), e.len, 0, e.len, pts.data());
             for (auto &pr : placed)
-                seg_emit(mv, wt.succ, (int)ax[pr.first], (int)ay[pr.first], (int)as_[pr.first], (int)seg[pr.first].len, pr.second, e.len, pts.data());
+                seg_emit(mv, wt.succ, (int)ax[pr.first], (int)ay[pr.first], (int)as_[pr.first], (int)(seg[pr.first].len & SEG_LEN), pr.second, e.len, pts.data());
             for (int k = 0; k < e.len; ++k) if (pts[k] == 0xFFFFFFFFu) return -105;
             if (s == dbg_scale) {
                 if (dbg_len && (int)i < dbg_cap) dbg_len[i] = e.len;
