@@ -201,7 +201,7 @@ struct b2a_detector {
     uint32_t *d_masks = nullptr; size_t masks_words = 0;
     // border graph (core.h): anchors of all (frame,scale) masks of a sub-batch share one slice of these arrays
     uint2 *d_ast = nullptr; Seg *d_seg = nullptr, *d_sseg = nullptr; uint32_t *d_minoff = nullptr, *d_ssoff = nullptr; int2 *d_emit = nullptr; uint32_t *d_amap = nullptr;
-    uint2 *d_starts = nullptr;
+    uint2 *d_starts = nullptr; uint32_t *d_codes = nullptr;
     unsigned anchors_cap = 0, starts_cap = 0; int anchor_R = 32;
     int *d_counters = nullptr;               // [sub-batch] n_anchors (unsigned), then per-(f,s) arrays
     unsigned *d_counters2 = nullptr;         // [sub-batch] n_starts
@@ -289,14 +289,17 @@ static int create_impl(b2a_detector *d)
     const int WW = (W + 31) / 32, PWW = WW + 2;
     d->masks_words = (size_t)B * nS * PWW * (H + 2);
     TRY(dev_alloc(d, &d->d_masks, d->masks_words));
-    d->anchors_cap = (unsigned)std::min<size_t>(std::max<size_t>((size_t)B * nS * (P / 4), 1u << 20), 0x7FFFFFF0u);
+    if (const char *e = std::getenv("B2A_ANCHOR_R")) { const int r = std::atoi(e); if (r >= 1 && r <= 32 && !(r & (r - 1))) d->anchor_R = r; }
+    // anchors: a state is an anchor on every R-th row or column, so even a pure-noise mask (~0.8 states per pixel)
+    // stays below 2 P / R per mask; start candidates: below P / 4 per mask
+    d->anchors_cap = (unsigned)std::min<size_t>(std::max<size_t>((size_t)B * nS * (2 * P / (size_t)d->anchor_R), 1u << 20), 0x7FFFFFF0u);
     TRY(dev_alloc(d, &d->d_ast, d->anchors_cap)); TRY(dev_alloc(d, &d->d_seg, d->anchors_cap));
     TRY(dev_alloc(d, &d->d_minoff, d->anchors_cap)); TRY(dev_alloc(d, &d->d_emit, d->anchors_cap));
     TRY(dev_alloc(d, &d->d_sseg, d->anchors_cap)); TRY(dev_alloc(d, &d->d_ssoff, d->anchors_cap));
     TRY(dev_alloc(d, &d->d_amap, (size_t)B * nS * H * ((W + 31) / 32)));
-    d->starts_cap = d->anchors_cap;
+    d->starts_cap = (unsigned)std::min<size_t>(std::max<size_t>((size_t)B * nS * (P / 4), 1u << 20), 0x7FFFFFF0u);
     TRY(dev_alloc(d, &d->d_starts, d->starts_cap));
-    if (const char *e = std::getenv("B2A_ANCHOR_R")) { const int r = std::atoi(e); if (r >= 1 && r <= 32 && !(r & (r - 1))) d->anchor_R = r; }
+    TRY(dev_alloc(d, &d->d_codes, (size_t)d->anchors_cap * SEG_CODE_WORDS));
     TRY(dev_alloc(d, &d->d_counters2, d->n_sub_max));
     const size_t FS = (size_t)B * nS;
     TRY(dev_alloc(d, &d->d_counters, d->n_sub_max + 3 * FS + B));
@@ -523,6 +526,7 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     bg.sseg = d->d_sseg + (size_t)s.sb * slice; bg.ssoff = d->d_ssoff + (size_t)s.sb * slice;
     bg.emit = d->d_emit + (size_t)s.sb * slice; bg.amap = d->d_amap + fs0 * (size_t)H * g.WW;
     bg.n_anchors = (unsigned *)d->d_counters + s.sb; bg.cap = slice;
+    bg.codes = d->d_codes + (size_t)s.sb * slice * SEG_CODE_WORDS;
     bg.starts = d->d_starts + (size_t)s.sb * (d->starts_cap / (unsigned)d->n_sub_max); bg.n_starts = d->d_counters2 + s.sb;
     bg.starts_cap = d->starts_cap / (unsigned)d->n_sub_max;
     const int Rm = d->anchor_R - 1, Rm2 = 8 * d->anchor_R - 1, max_len = walk_max_len > 0 ? walk_max_len : g.maxPerim;

@@ -300,21 +300,41 @@ B2A_HD int anchor_rank_in_word(const Mask &mk, int x, int y, int s, int Rm)
 // Walk from anchor state (x,y,s) to the next anchor.  len = number of states of the segment
 // (SEG_OVERFLOW once more than max_len steps were taken), minkey / minoff = smallest start key
 // among the segment's start-eligible states and its offset (A_NONE if none); (x,y,s) is left at the next anchor.
+// The first SEG_CODE_WORDS * 10 successor directions of the segment are also left in `codes` (3 bits each,
+// 10 per word) when it is not null: the emit pass then rebuilds the points without touching the mask.
+constexpr int SEG_CODE_WORDS = 8;
 template <class Win>
 B2A_HD void seg_walk(const Win &win, const uint16_t *__restrict__ succ, int KS, int Rm, int max_len,
-                     int &x, int &y, int &s, uint32_t &len, uint32_t &minkey, uint32_t &minoff)
+                     int &x, int &y, int &s, uint32_t &len, uint32_t &minkey, uint32_t &minoff, uint32_t *__restrict__ codes)
 {
     unsigned e = succ[win.win9(x, y) | ((unsigned)s << 9)];
-    uint32_t n = 0;
+    uint32_t n = 0, cw = 0;
+    int ci = 0, cshift = 0;
     minkey = A_NONE; minoff = 0;
     for (;;) {
         if (e & WT_ELIG) { const uint32_t k = key_of(x, y, e, KS); if (k < minkey) { minkey = k; minoff = n; } }
         const int so = (int)(e & 7u);
+        cw |= (uint32_t)so << cshift; cshift += 3;
+        if (cshift == 30) { if (codes && ci < SEG_CODE_WORDS) codes[ci] = cw; ++ci; cw = 0; cshift = 0; }
         x += dir_dx(so); y += dir_dy(so); s = so ^ 4;
         ++n;
         e = succ[win.win9(x, y) | ((unsigned)s << 9)];
-        if (is_anchor(e, x, y, Rm)) { len = n; return; }
-        if (n > (uint32_t)max_len) { len = SEG_OVERFLOW; return; }
+        if (is_anchor(e, x, y, Rm)) { len = n; break; }
+        if (n > (uint32_t)max_len) { len = SEG_OVERFLOW; break; }
+    }
+    if (codes && cshift && ci < SEG_CODE_WORDS) codes[ci] = cw;
+}
+// points of a segment from its stored direction codes (len <= SEG_CODE_WORDS * 10)
+B2A_HD void seg_emit_codes(const uint32_t *__restrict__ codes, int x, int y, int len, int pos, int n, uint32_t *__restrict__ out)
+{
+    uint32_t cw = 0;
+    for (int k = 0; k < len; ++k) {
+        const int q = pos + k;
+        out[q < 0 ? q + n : q] = (uint32_t)x | ((uint32_t)y << 16);
+        const int r = k % 10;
+        if (r == 0) cw = codes[k / 10];
+        const int so = (int)((cw >> (3 * r)) & 7u);
+        x += dir_dx(so); y += dir_dy(so);
     }
 }
 // Emit the len points of the segment that starts at state (x,y,s): point k goes to
@@ -333,7 +353,7 @@ B2A_HD void seg_emit(const Win &win, const uint16_t *__restrict__ succ, int x, i
 // A start candidate (x0,y0,s0) with start key key0 walks its border in both directions at once.
 // Returns the border length if the border carries no anchor and (x0,y0,s0) is its first state;
 // 0 as soon as an anchor or a start-eligible state with a smaller key is met (the border is then
-// reported through its anchors, or by that other state) or after max_len steps.
+// reported through its anchors, or by that other state); -1 when undecided after max_len steps.
 template <class Win>
 B2A_HD int direct_walk(const Win &win, const uint16_t *__restrict__ succ, const uint16_t *__restrict__ pred, int KS, int Rm,
                        int x0, int y0, int s0, uint32_t key0, int max_len)
@@ -350,11 +370,13 @@ B2A_HD int direct_walk(const Win &win, const uint16_t *__restrict__ succ, const 
         const int xp = xb + dir_dx(sb), yp = yb + dir_dy(sb);
         const unsigned wf = win.win9(xf, yf), wp = win.win9(xp, yp);       // twelve independent loads in flight
         const unsigned ef = succ[wf | ((unsigned)sf << 9)], ep = pred[wp | ((unsigned)(sb ^ 4) << 9)];
-        if (is_anchor(ef, xf, yf, Rm) || ((ef & WT_ELIG) && key_of(xf, yf, ef, KS) < key0) || n > max_len) return 0;
+        if (is_anchor(ef, xf, yf, Rm) || ((ef & WT_ELIG) && key_of(xf, yf, ef, KS) < key0)) return 0;
+        if (n > max_len) return -1;
         sb = (int)(ep & 7u); xb = xp; yb = yp;
         ++n;
         if (xf == xb && yf == yb && sf == sb) return n;
-        if (is_anchor(ep, xb, yb, Rm) || ((ep & WT_ELIG) && key_of(xb, yb, ep, KS) < key0) || n > max_len) return 0;
+        if (is_anchor(ep, xb, yb, Rm) || ((ep & WT_ELIG) && key_of(xb, yb, ep, KS) < key0)) return 0;
+        if (n > max_len) return -1;
         so = (int)(ef & 7u);
     }
 }

@@ -293,6 +293,7 @@ struct BorderGraph {
     Seg *sseg;           // super anchors only: (next super, previous super, length up to it, min key)
     uint32_t *ssoff;     // super anchors only: offset of the min-key state from the super anchor
     int2 *emit;          // (position of the segment's first state in its border, 1 + slot of the border in `sorted`; 0 = not kept)
+    uint32_t *codes;     // per anchor SEG_CODE_WORDS words: the segment's first successor directions, 3 bits each
     uint32_t *amap;      // per mask word of every (frame,scale): first anchor index
     unsigned *n_anchors; // this sub-batch's counter
     unsigned cap;
@@ -324,63 +325,98 @@ __device__ __forceinline__ unsigned warp_append(unsigned *counter, int cnt, int 
     return base + (unsigned)(incl - cnt);
 }
 
+// The word logic costs a few hundred instructions but only ~10 % of the mask words touch a border, so a
+// warp first filters 32 words per lane-iteration with three loads each (empty words and words in the
+// interior of a region are dropped) and queues the others in shared memory; whenever 32 are queued
+// every lane takes one, so the logic always runs on full warps.
+__device__ __forceinline__ void anchors_of_word(const uint32_t *__restrict__ masks, const BorderGraph &bg, int *__restrict__ iso_count,
+                                                int Rm, int Rm2, const DetGeom &g, unsigned widx, bool valid, int lane)
+{
+    uint32_t A[4] = {0, 0, 0, 0}, SU[4] = {0, 0, 0, 0}, U[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+    int fs = 0, y = 0, wx = 0;
+    if (valid) {
+        const unsigned words_per_plane = (unsigned)g.H * (unsigned)g.WW;
+        fs = (int)(widx / words_per_plane);
+        const unsigned rem = widx - (unsigned)fs * words_per_plane;
+        y = (int)(rem / (unsigned)g.WW); wx = (int)(rem - (unsigned)y * (unsigned)g.WW);
+        const uint32_t *row = masks + (size_t)fs * g.mask_plane + (size_t)(y + 1) * g.PWW + wx + 1;
+        const uint32_t m = __ldg(row), ml = __ldg(row - 1), mr = __ldg(row + 1);
+        const uint32_t u = __ldg(row - g.PWW), ul = __ldg(row - g.PWW - 1), ur = __ldg(row - g.PWW + 1);
+        const uint32_t d = __ldg(row + g.PWW), dl = __ldg(row + g.PWW - 1), dr = __ldg(row + g.PWW + 1);
+        uint32_t iso;
+        anchor_words(m, ml, mr, u, ul, ur, d, dl, dr, !(y & Rm), grid_cols(wx, Rm), !(y & Rm2), grid_cols(wx, Rm2), A, SU, U, hi, iso);
+        if (iso) atomicAdd(&iso_count[fs], __popc(iso));
+    }
+    // anchors: pixel by pixel, canonical directions E, N, W, S inside a pixel
+    const int cnt = __popc(A[0]) + __popc(A[1]) + __popc(A[2]) + __popc(A[3]);
+    unsigned pos = warp_append(bg.n_anchors, cnt, lane);
+    if (cnt && pos < bg.cap) bg.amap[((size_t)fs * g.H + y) * g.WW + wx] = pos;
+    for (uint32_t px = A[0] | A[1] | A[2] | A[3]; px; px &= px - 1) {
+        const int b = __ffs(px) - 1, x = wx * 32 + b;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!((A[k] >> b) & 1u)) continue;
+            if (pos < bg.cap) {
+                const unsigned sup = (SU[k] >> b) & 1u;
+                bg.ast[pos] = make_uint2((unsigned)x | ((unsigned)y << 16), ((unsigned)fs << 4) | (sup << 3) | (unsigned)state_dir(k, hi[k], b));
+                bg.seg[pos] = Seg{A_NONE, A_NONE, 0u, A_NONE};
+                bg.emit[pos] = make_int2(0, 0);
+                if (sup) bg.sseg[pos] = Seg{A_NONE, A_NONE, 0u, A_NONE};
+            }
+            ++pos;
+        }
+    }
+    // start candidates
+    const int ucnt = __popc(U[0]) + __popc(U[1]) + __popc(U[2]) + __popc(U[3]);
+    unsigned upos = warp_append(bg.n_starts, ucnt, lane);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        for (uint32_t px = U[k]; px; px &= px - 1) {
+            const int b = __ffs(px) - 1;
+            if (upos < bg.starts_cap) bg.starts[upos] = make_uint2((unsigned)(wx * 32 + b) | ((unsigned)y << 16), ((unsigned)fs << 4) | (unsigned)state_dir(k, hi[k], b));
+            ++upos;
+        }
+}
+
 __global__ void __launch_bounds__(256)
 k_anchors(const uint32_t *__restrict__ masks, BorderGraph bg, int *__restrict__ iso_count, int Rm, int Rm2, DetGeom g)
 {
+    __shared__ unsigned s_queue[8][64];                       // per warp: word indices waiting for the logic
     const unsigned words_per_plane = (unsigned)g.H * (unsigned)g.WW;
     const unsigned total = (unsigned)(g.B * g.nScales) * words_per_plane;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const unsigned stride = gridDim.x * blockDim.x;
-    // whole warps iterate together (warp-aggregated appends); word index = (fs * H + y) * WW + wx
+    unsigned *queue = s_queue[wp];
+    int queued = 0;                                           // same value on every lane
+    // word index = (fs * H + y) * WW + wx; the word above / below is WW indices away inside a plane
     for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < total; i0 += stride) {
         const unsigned i = i0 + lane;
-        uint32_t A[4] = {0, 0, 0, 0}, SU[4] = {0, 0, 0, 0}, U[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
-        int fs = 0, y = 0, wx = 0;
+        bool keep = false;
         if (i < total) {
-            fs = (int)(i / words_per_plane);
-            const unsigned rem = i - (unsigned)fs * words_per_plane;
-            y = (int)(rem / (unsigned)g.WW); wx = (int)(rem - (unsigned)y * (unsigned)g.WW);
+            const unsigned fs = i / words_per_plane, rem = i - fs * words_per_plane;
+            const unsigned y = rem / (unsigned)g.WW, wx = rem - y * (unsigned)g.WW;
             const uint32_t *row = masks + (size_t)fs * g.mask_plane + (size_t)(y + 1) * g.PWW + wx + 1;
             const uint32_t m = __ldg(row);
             if (m) {
-                const uint32_t ml = __ldg(row - 1), mr = __ldg(row + 1);
-                const uint32_t u = __ldg(row - g.PWW), ul = __ldg(row - g.PWW - 1), ur = __ldg(row - g.PWW + 1);
-                const uint32_t d = __ldg(row + g.PWW), dl = __ldg(row + g.PWW - 1), dr = __ldg(row + g.PWW + 1);
-                uint32_t iso;
-                anchor_words(m, ml, mr, u, ul, ur, d, dl, dr, !(y & Rm), grid_cols(wx, Rm), !(y & Rm2), grid_cols(wx, Rm2), A, SU, U, hi, iso);
-                if (iso) atomicAdd(&iso_count[fs], __popc(iso));
+                // interior of a region: the word, the words above and below are full and so are the two flanking bits
+                const uint32_t u = __ldg(row - g.PWW), d = __ldg(row + g.PWW);
+                keep = (m & u & d) != 0xFFFFFFFFu || !(__ldg(row - 1) >> 31) || !(__ldg(row + 1) & 1u) ||
+                       !(__ldg(row - g.PWW - 1) >> 31) || !(__ldg(row - g.PWW + 1) & 1u) || !(__ldg(row + g.PWW - 1) >> 31) || !(__ldg(row + g.PWW + 1) & 1u);
             }
         }
-        // anchors: pixel by pixel, canonical directions E, N, W, S inside a pixel
-        const int cnt = __popc(A[0]) + __popc(A[1]) + __popc(A[2]) + __popc(A[3]);
-        unsigned pos = warp_append(bg.n_anchors, cnt, lane);
-        if (cnt && pos < bg.cap) bg.amap[((size_t)fs * g.H + y) * g.WW + wx] = pos;
-        for (uint32_t px = A[0] | A[1] | A[2] | A[3]; px; px &= px - 1) {
-            const int b = __ffs(px) - 1, x = wx * 32 + b;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (!((A[k] >> b) & 1u)) continue;
-                if (pos < bg.cap) {
-                    const unsigned sup = (SU[k] >> b) & 1u;
-                    bg.ast[pos] = make_uint2((unsigned)x | ((unsigned)y << 16), ((unsigned)fs << 4) | (sup << 3) | (unsigned)state_dir(k, hi[k], b));
-                    bg.seg[pos] = Seg{A_NONE, A_NONE, 0u, A_NONE};
-                    bg.emit[pos] = make_int2(0, 0);
-                    if (sup) bg.sseg[pos] = Seg{A_NONE, A_NONE, 0u, A_NONE};
-                }
-                ++pos;
-            }
+        const unsigned km = __ballot_sync(0xFFFFFFFFu, keep);
+        if (keep) queue[queued + __popc(km & ((1u << lane) - 1u))] = i;
+        queued += __popc(km);
+        __syncwarp();
+        if (queued >= 32) {
+            anchors_of_word(masks, bg, iso_count, Rm, Rm2, g, queue[lane], true, lane);
+            __syncwarp();
+            if (lane < queued - 32) queue[lane] = queue[32 + lane];
+            queued -= 32;
+            __syncwarp();
         }
-        // start candidates
-        const int ucnt = __popc(U[0]) + __popc(U[1]) + __popc(U[2]) + __popc(U[3]);
-        unsigned upos = warp_append(bg.n_starts, ucnt, lane);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            for (uint32_t px = U[k]; px; px &= px - 1) {
-                const int b = __ffs(px) - 1;
-                if (upos < bg.starts_cap) bg.starts[upos] = make_uint2((unsigned)(wx * 32 + b) | ((unsigned)y << 16), ((unsigned)fs << 4) | (unsigned)state_dir(k, hi[k], b));
-                ++upos;
-            }
     }
+    if (queued > 0) anchors_of_word(masks, bg, iso_count, Rm, Rm2, g, lane < queued ? queue[lane] : 0u, lane < queued, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -400,7 +436,7 @@ k_segments(const uint32_t *__restrict__ masks, BorderGraph bg, int max_len, cons
         int x = (int)(a.x & 0xFFFFu), y = (int)(a.x >> 16), s = (int)(a.y & 7u);
         MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
         uint32_t len, minkey, moff;
-        seg_walk(rd, s_succ, g.KS, Rm, max_len, x, y, s, len, minkey, moff);
+        seg_walk(rd, s_succ, g.KS, Rm, max_len, x, y, s, len, minkey, moff, bg.codes + (size_t)i * SEG_CODE_WORDS);
         uint32_t j = A_NONE;
         if (len != SEG_OVERFLOW) {
             const int r = anchor_rank_in_word(rd, x, y, s, Rm);
@@ -477,14 +513,35 @@ k_cycles(const uint32_t *__restrict__ masks, BorderGraph bg, uint4 *__restrict__
         const uint32_t len = sup ? cycle_leader(sseg_at, NeverStop{}, i, max_len) : cycle_leader(seg_at, StopAtSuper{}, i, max_len);
         if (len) report_border(surv, surv_count, contour_count, (int)(a.y >> 4), sup ? bg.sseg[i].minkey : bg.seg[i].minkey, len, i, sup ? 1u : 0u, g);
     }
-    for (unsigned i = tid; i < ns; i += nthr) {
-        const uint2 c = bg.starts[i];
-        const int fs = (int)(c.y >> 4), x = (int)(c.x & 0xFFFFu), y = (int)(c.x >> 16), s0 = (int)(c.y & 7u);
-        MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
-        const unsigned e0 = s_succ[rd.win9(x, y) | ((unsigned)s0 << 9)];
-        const uint32_t key0 = key_of(x, y, e0, g.KS);
-        const int len = direct_walk(rd, s_succ, s_pred, g.KS, Rm, x, y, s0, key0, max_len);
-        if (len > 0) report_border(surv, surv_count, contour_count, fs, key0, (uint32_t)len, c.x, 2u | ((unsigned)s0 << 8), g);
+    // start candidates: a short probe decides almost all of them (the next candidate up the edge has a smaller
+    // key); the few that are still undecided are queued and walked by the first threads of the CTA together
+    __shared__ unsigned s_q[256];
+    __shared__ int s_nq;
+    for (unsigned base = blockIdx.x * blockDim.x; base < ns; base += nthr) {
+        if (threadIdx.x == 0) s_nq = 0;
+        __syncthreads();
+        const unsigned i = base + threadIdx.x;
+        if (i < ns) {
+            const uint2 c = bg.starts[i];
+            const int fs = (int)(c.y >> 4), x = (int)(c.x & 0xFFFFu), y = (int)(c.x >> 16), s0 = (int)(c.y & 7u);
+            MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
+            const unsigned e0 = s_succ[rd.win9(x, y) | ((unsigned)s0 << 9)];
+            const uint32_t key0 = key_of(x, y, e0, g.KS);
+            const int len = direct_walk(rd, s_succ, s_pred, g.KS, Rm, x, y, s0, key0, max_len < 4 ? max_len : 4);
+            if (len > 0) report_border(surv, surv_count, contour_count, fs, key0, (uint32_t)len, c.x, 2u | ((unsigned)s0 << 8), g);
+            else if (len < 0 && max_len > 4) s_q[atomicAdd(&s_nq, 1)] = i;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < s_nq) {
+            const uint2 c = bg.starts[s_q[threadIdx.x]];
+            const int fs = (int)(c.y >> 4), x = (int)(c.x & 0xFFFFu), y = (int)(c.x >> 16), s0 = (int)(c.y & 7u);
+            MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
+            const unsigned e0 = s_succ[rd.win9(x, y) | ((unsigned)s0 << 9)];
+            const uint32_t key0 = key_of(x, y, e0, g.KS);
+            const int len = direct_walk(rd, s_succ, s_pred, g.KS, Rm, x, y, s0, key0, max_len);
+            if (len > 0) report_border(surv, surv_count, contour_count, fs, key0, (uint32_t)len, c.x, 2u | ((unsigned)s0 << 8), g);
+        }
+        __syncthreads();
     }
 }
 
@@ -614,8 +671,13 @@ k_emit(const uint32_t *__restrict__ masks, BorderGraph bg, const uint4 *__restri
         const uint2 a = bg.ast[i];
         const int fs = (int)(a.y >> 4);
         const int len = (int)__ldg(&sorted[e.y - 1].y), off = __ldg(&pts_off[e.y - 1]);
-        MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
-        seg_emit(rd, s_succ, (int)(a.x & 0xFFFFu), (int)(a.x >> 16), (int)(a.y & 7u), (int)(bg.seg[i].len & SEG_LEN), e.x, len, pts + (size_t)fs * g.pts_cap + off);
+        const int slen = (int)(bg.seg[i].len & SEG_LEN);
+        uint32_t *out = pts + (size_t)fs * g.pts_cap + off;
+        if (slen <= SEG_CODE_WORDS * 10) seg_emit_codes(bg.codes + (size_t)i * SEG_CODE_WORDS, (int)(a.x & 0xFFFFu), (int)(a.x >> 16), slen, e.x, len, out);
+        else {
+            MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
+            seg_emit(rd, s_succ, (int)(a.x & 0xFFFFu), (int)(a.x >> 16), (int)(a.y & 7u), slen, e.x, len, out);
+        }
     }
 }
 

@@ -141,6 +141,7 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
         const uint32_t nA = (uint32_t)ax.size();
         seg.assign(nA, Seg{A_NONE, A_NONE, 0u, A_NONE});
         minoff.assign(nA, 0);
+        std::vector<uint32_t> codes((size_t)nA * SEG_CODE_WORDS + 1, 0);
         // anchor_R < 0: behave like the product call (walks give up after maxPerimeter steps; overflowed
         // segments and their borders are dropped) instead of the exact-count debug mode
         const int max_len = device_like ? maxPerim : 2 * W * H + 16;
@@ -149,7 +150,7 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
             int x = (int)ax[i], y = (int)ay[i], st = (int)as_[i];
             uint32_t len, mk, mo;
             CheckedView cv{pl, PWW, W, H};
-            seg_walk(cv, wt.succ, KS, Rm, max_len, x, y, st, len, mk, mo);
+            seg_walk(cv, wt.succ, KS, Rm, max_len, x, y, st, len, mk, mo, codes.data() + (size_t)i * SEG_CODE_WORDS);
             if (cv.bad) return -106;
             seg[i].len = len | (asup[i] ? SEG_SUPER : 0u); seg[i].minkey = mk; minoff[i] = mo;
             if (len == SEG_OVERFLOW) { if (device_like) continue; return -101; }
@@ -214,8 +215,11 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
                 for (size_t k = 0; k < nsup; ++k) super_assign(seg_at, place, placed[k].first, placed[k].second);
             } else if ((e.kind & 3u) == 0u) cycle_assign(seg_at, place, e.who, e.len, (int)minoff[e.who]);
             else seg_emit(mv, wt.succ, (int)(e.who & 0xFFFFu), (int)(e.who >> 16), (int)(e.kind >> 8), e.len, 0, e.len, pts.data());
-            for (auto &pr : placed)
-                seg_emit(mv, wt.succ, (int)ax[pr.first], (int)ay[pr.first], (int)as_[pr.first], (int)(seg[pr.first].len & SEG_LEN), pr.second, e.len, pts.data());
+            for (auto &pr : placed) {
+                const int slen = (int)(seg[pr.first].len & SEG_LEN);
+                if (slen <= SEG_CODE_WORDS * 10) seg_emit_codes(codes.data() + (size_t)pr.first * SEG_CODE_WORDS, (int)ax[pr.first], (int)ay[pr.first], slen, pr.second, e.len, pts.data());
+                else seg_emit(mv, wt.succ, (int)ax[pr.first], (int)ay[pr.first], (int)as_[pr.first], slen, pr.second, e.len, pts.data());
+            }
             for (int k = 0; k < e.len; ++k) if (pts[k] == 0xFFFFFFFFu) return -105;
             if (s == dbg_scale) {
                 if (dbg_len && (int)i < dbg_cap) dbg_len[i] = e.len;
