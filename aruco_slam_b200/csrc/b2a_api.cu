@@ -569,13 +569,9 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     k_emit<<<walk_grid, 256, 0, st>>>(masks, bg, d->d_sorted + fs0 * g.surv_cap, d->d_pts_off + fs0 * g.surv_cap, d->d_pts + fs0 * (size_t)g.pts_cap, d->d_tables, g);
     d->launches++; DBG_SYNC(st);
     stage_mark(d, s, ST_APPROX);
-    k_approx<<<dim3(8, (unsigned)FS), 256, 0, st>>>(d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,
-                                                    d->d_pts + fs0 * (size_t)g.pts_cap, d->d_quad_ok + fs0 * g.surv_cap, d->d_quad_xy + fs0 * g.surv_cap * 8,
-                                                    d->d_quad_len + fs0 * g.surv_cap, g);
-    d->launches++; DBG_SYNC(st);
-    k_approx_long<<<dim3(APPROX_LONG_CTAS, (unsigned)FS), 256, 0, st>>>(d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,
-                                                         d->d_pts + fs0 * (size_t)g.pts_cap, d->d_quad_ok + fs0 * g.surv_cap, d->d_quad_xy + fs0 * g.surv_cap * 8,
-                                                         d->d_quad_len + fs0 * g.surv_cap, g);
+    k_approx<<<dim3(APPROX_LONG_CTAS + 8, (unsigned)FS), 256, 0, st>>>(d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,
+                                                                       d->d_pts + fs0 * (size_t)g.pts_cap, d->d_quad_ok + fs0 * g.surv_cap, d->d_quad_xy + fs0 * g.surv_cap * 8,
+                                                                       d->d_quad_len + fs0 * g.surv_cap, g);
     d->launches++; DBG_SYNC(st);
     return launch_err("front-end kernels");
 }
@@ -727,11 +723,32 @@ static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *
     CU(cudaMemsetAsync(d->d_counters, 0, (d->n_sub_max + 3 * FSmax + d->cfg.max_batch) * sizeof(int), s0));
     CU(cudaMemsetAsync(d->d_counters2, 0, d->n_sub_max * sizeof(unsigned), s0));
     // sub-batches
-    const int nsub = std::max(1, std::min(std::min(d->n_streams, d->n_sub_max), B));
+    int nsub = std::max(1, std::min(std::min(d->n_streams, d->n_sub_max), B));
+    // sub-batch boundaries.  Frames that still have to cross PCIe are cut unevenly: a small first sub-batch lets the
+    // kernels start early and a small last one shortens the tail that nothing overlaps (B2A_SPLIT="2,6,8,8,6,2" overrides)
+    std::vector<int> bounds;
+    if (const char *e = std::getenv("B2A_SPLIT")) {
+        std::vector<int> w;
+        for (const char *p = e; *p;) { w.push_back(std::max(1, std::atoi(p))); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+        if ((int)w.size() > d->n_sub_max) w.resize(d->n_sub_max);
+        int tot = 0; for (int v : w) tot += v;
+        bounds.push_back(0);
+        int acc = 0;
+        for (size_t i = 0; i < w.size(); ++i) { acc += w[i]; const int b = (int)((long long)B * acc / tot); if (b > bounds.back()) bounds.push_back(b); }
+        if (bounds.back() != B) bounds.push_back(B);
+    } else if (!f->on_device && nsub >= 4 && B >= 4 * nsub) {
+        // weights 1 : 2 : ... : 2 : 1
+        const int tot = 2 * nsub - 2;
+        bounds.push_back(0);
+        for (int i = 1; i <= nsub; ++i) { const int acc = (i == nsub) ? tot : 2 * i - 1; bounds.push_back((int)((long long)B * acc / tot)); }
+    } else {
+        for (int i = 0; i <= nsub; ++i) bounds.push_back((int)((long long)B * i / nsub));
+    }
+    nsub = (int)bounds.size() - 1;
     std::vector<Sub> subs(nsub);
     for (int i = 0; i < nsub; ++i) {
         Sub &s = subs[i];
-        s.sb = i; s.b0 = (int)((long long)B * i / nsub); s.nb = (int)((long long)B * (i + 1) / nsub) - s.b0;
+        s.sb = i; s.b0 = bounds[i]; s.nb = bounds[i + 1] - bounds[i];
         s.st = d->streams[i]; s.timed = (i == 0);
     }
     CU(cudaEventRecord(d->ev_fork, s0));

@@ -326,11 +326,37 @@ __device__ __forceinline__ unsigned warp_append(unsigned *counter, int cnt, int 
 }
 
 // The word logic costs a few hundred instructions but only ~10 % of the mask words touch a border, so a
-// warp first filters 32 words per lane-iteration with three loads each (empty words and words in the
-// interior of a region are dropped) and queues the others in shared memory; whenever 32 are queued
-// every lane takes one, so the logic always runs on full warps.
-__device__ __forceinline__ void anchors_of_word(const uint32_t *__restrict__ masks, const BorderGraph &bg, int *__restrict__ iso_count,
-                                                int Rm, int Rm2, const DetGeom &g, unsigned widx, bool valid, int lane)
+// CTA first filters 256 words per iteration with three loads each (empty words and words in the
+// interior of a region are dropped) and queues the others in shared memory; whenever 256 are queued
+// every thread takes one, so the logic always runs on full warps, and the two global list counters see
+// one atomic per 256 words (same-address atomics serialise in L2: one per warp was 60 % of this kernel).
+struct AnchorBlock {
+    unsigned queue[512];
+    int nq;
+    int wsum[2][8];
+    unsigned base[2];
+};
+
+// exclusive position of this thread's cnt items in the CTA-wide append to *counter (which = 0 anchors, 1 starts)
+__device__ __forceinline__ unsigned block_append(AnchorBlock &sb, int which, unsigned *counter, int cnt)
+{
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    int incl = cnt;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) { const int o = __shfl_up_sync(0xFFFFFFFFu, incl, dd); if (lane >= dd) incl += o; }
+    if (lane == 31) sb.wsum[which][wp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) { const int v = sb.wsum[which][w]; sb.wsum[which][w] = tot; tot += v; }
+        sb.base[which] = tot ? atomicAdd(counter, (unsigned)tot) : 0u;
+    }
+    __syncthreads();
+    return sb.base[which] + (unsigned)sb.wsum[which][wp] + (unsigned)(incl - cnt);
+}
+
+__device__ __forceinline__ void anchors_of_word(AnchorBlock &sb, const uint32_t *__restrict__ masks, const BorderGraph &bg, int *__restrict__ iso_count,
+                                                int Rm, int Rm2, const DetGeom &g, unsigned widx, bool valid)
 {
     uint32_t A[4] = {0, 0, 0, 0}, SU[4] = {0, 0, 0, 0}, U[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
     int fs = 0, y = 0, wx = 0;
@@ -349,7 +375,7 @@ __device__ __forceinline__ void anchors_of_word(const uint32_t *__restrict__ mas
     }
     // anchors: pixel by pixel, canonical directions E, N, W, S inside a pixel
     const int cnt = __popc(A[0]) + __popc(A[1]) + __popc(A[2]) + __popc(A[3]);
-    unsigned pos = warp_append(bg.n_anchors, cnt, lane);
+    unsigned pos = block_append(sb, 0, bg.n_anchors, cnt);
     if (cnt && pos < bg.cap) bg.amap[((size_t)fs * g.H + y) * g.WW + wx] = pos;
     for (uint32_t px = A[0] | A[1] | A[2] | A[3]; px; px &= px - 1) {
         const int b = __ffs(px) - 1, x = wx * 32 + b;
@@ -368,7 +394,7 @@ __device__ __forceinline__ void anchors_of_word(const uint32_t *__restrict__ mas
     }
     // start candidates
     const int ucnt = __popc(U[0]) + __popc(U[1]) + __popc(U[2]) + __popc(U[3]);
-    unsigned upos = warp_append(bg.n_starts, ucnt, lane);
+    unsigned upos = block_append(sb, 1, bg.n_starts, ucnt);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         for (uint32_t px = U[k]; px; px &= px - 1) {
@@ -381,16 +407,16 @@ __device__ __forceinline__ void anchors_of_word(const uint32_t *__restrict__ mas
 __global__ void __launch_bounds__(256)
 k_anchors(const uint32_t *__restrict__ masks, BorderGraph bg, int *__restrict__ iso_count, int Rm, int Rm2, DetGeom g)
 {
-    __shared__ unsigned s_queue[8][64];                       // per warp: word indices waiting for the logic
+    __shared__ AnchorBlock sb;
     const unsigned words_per_plane = (unsigned)g.H * (unsigned)g.WW;
     const unsigned total = (unsigned)(g.B * g.nScales) * words_per_plane;
-    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const unsigned stride = gridDim.x * blockDim.x;
-    unsigned *queue = s_queue[wp];
-    int queued = 0;                                           // same value on every lane
-    // word index = (fs * H + y) * WW + wx; the word above / below is WW indices away inside a plane
-    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < total; i0 += stride) {
-        const unsigned i = i0 + lane;
+    if (threadIdx.x == 0) sb.nq = 0;
+    __syncthreads();
+    // word index = (fs * H + y) * WW + wx; every thread of the CTA runs the same number of iterations
+    for (unsigned i0 = blockIdx.x * blockDim.x; i0 < total; i0 += stride) {
+        const unsigned i = i0 + threadIdx.x;
         bool keep = false;
         if (i < total) {
             const unsigned fs = i / words_per_plane, rem = i - fs * words_per_plane;
@@ -398,25 +424,29 @@ k_anchors(const uint32_t *__restrict__ masks, BorderGraph bg, int *__restrict__ 
             const uint32_t *row = masks + (size_t)fs * g.mask_plane + (size_t)(y + 1) * g.PWW + wx + 1;
             const uint32_t m = __ldg(row);
             if (m) {
-                // interior of a region: the word, the words above and below are full and so are the two flanking bits
+                // interior of a region: the word, the words above and below are full and so are the six flanking bits
                 const uint32_t u = __ldg(row - g.PWW), d = __ldg(row + g.PWW);
                 keep = (m & u & d) != 0xFFFFFFFFu || !(__ldg(row - 1) >> 31) || !(__ldg(row + 1) & 1u) ||
                        !(__ldg(row - g.PWW - 1) >> 31) || !(__ldg(row - g.PWW + 1) & 1u) || !(__ldg(row + g.PWW - 1) >> 31) || !(__ldg(row + g.PWW + 1) & 1u);
             }
         }
         const unsigned km = __ballot_sync(0xFFFFFFFFu, keep);
-        if (keep) queue[queued + __popc(km & ((1u << lane) - 1u))] = i;
-        queued += __popc(km);
-        __syncwarp();
-        if (queued >= 32) {
-            anchors_of_word(masks, bg, iso_count, Rm, Rm2, g, queue[lane], true, lane);
-            __syncwarp();
-            if (lane < queued - 32) queue[lane] = queue[32 + lane];
-            queued -= 32;
-            __syncwarp();
+        int wbase = 0;
+        if (lane == 0 && km) wbase = atomicAdd(&sb.nq, __popc(km));
+        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+        if (keep) sb.queue[wbase + __popc(km & ((1u << lane) - 1u))] = i;          // nq < 256 before: never past 511
+        __syncthreads();
+        const int nq = sb.nq;
+        if (nq >= 256) {
+            const unsigned widx = sb.queue[nq - 256 + threadIdx.x];                  // take the last 256: the rest stays in place
+            __syncthreads();
+            if (threadIdx.x == 0) sb.nq = nq - 256;
+            anchors_of_word(sb, masks, bg, iso_count, Rm, Rm2, g, widx, true);
         }
+        __syncthreads();
     }
-    if (queued > 0) anchors_of_word(masks, bg, iso_count, Rm, Rm2, g, lane < queued ? queue[lane] : 0u, lane < queued, lane);
+    const int nq = sb.nq;
+    if (nq > 0) anchors_of_word(sb, masks, bg, iso_count, Rm, Rm2, g, (int)threadIdx.x < nq ? sb.queue[threadIdx.x] : 0u, (int)threadIdx.x < nq);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -699,38 +729,20 @@ struct WarpLanes {
 };
 
 // borders of at least this many points are left to k_approx_long (a whole CTA per border)
-constexpr int APPROX_LONG = 2048;
-constexpr int APPROX_LONG_CTAS = 16;          // CTAs per (frame,scale) of k_approx_long
+#ifndef B2A_APPROX_LONG
+#define B2A_APPROX_LONG 2048
+#endif
+constexpr int APPROX_LONG = B2A_APPROX_LONG;
+#ifndef B2A_APPROX_CTAS
+#define B2A_APPROX_CTAS 16
+#endif
+constexpr int APPROX_LONG_CTAS = B2A_APPROX_CTAS;          // CTAs per (frame,scale) of k_approx_long
 
 __device__ __forceinline__ void approx_store(bool ok, int len, const int *ox, const int *oy, size_t slot, uint8_t *quad_ok, int32_t *quad_xy, int32_t *quad_len)
 {
     quad_ok[slot] = ok ? 1 : 0;
     quad_len[slot] = len;
     if (ok) for (int k = 0; k < 4; ++k) { quad_xy[slot * 8 + 2 * k] = ox[k]; quad_xy[slot * 8 + 2 * k + 1] = oy[k]; }
-}
-
-__global__ void __launch_bounds__(256)
-k_approx(const uint4 *__restrict__ sorted, const int *__restrict__ surv_count, const int *__restrict__ pts_off,
-         const uint32_t *__restrict__ pts, uint8_t *__restrict__ quad_ok, int32_t *__restrict__ quad_xy,
-         int32_t *__restrict__ quad_len, DetGeom g)
-{
-    const int fs = blockIdx.y;
-    const int n = surv_count[fs];
-    const int warps_per_block = blockDim.x >> 5;
-    WarpLanes lg;
-    for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_block) {
-        const size_t slot = (size_t)fs * g.surv_cap + i;
-        const int off = pts_off[slot];
-        const int len = (int)sorted[slot].y;
-        if (len >= APPROX_LONG && off >= 0) continue;
-        bool ok = false;
-        int ox[8], oy[8];
-        if (off >= 0) {
-            const int m = approx_closed(lg, pts + (size_t)fs * g.pts_cap + off, len, (double)len * g.approxRate, ox, oy);
-            ok = (m == 4) && quad_passes(ox, oy, m, len, g.maxWH, g.minCornerDistRate);
-        }
-        if (lg.lane() == 0) approx_store(ok, len, ox, oy, slot, quad_ok, quad_xy, quad_len);
-    }
 }
 
 // the same algorithm with the lanes of a whole CTA on one (long) border: the sweeps over the points
@@ -751,24 +763,45 @@ struct BlockLanes {
     }
 };
 
+// One launch, two roles: the first APPROX_LONG_CTAS CTAs of every (frame,scale) take the long borders
+// (a whole CTA per border), the other CTAs take the rest (one warp per border), so a frame's few long
+// borders are worked on while the many short ones are.
 __global__ void __launch_bounds__(256)
-k_approx_long(const uint4 *__restrict__ sorted, const int *__restrict__ surv_count, const int *__restrict__ pts_off,
-              const uint32_t *__restrict__ pts, uint8_t *__restrict__ quad_ok, int32_t *__restrict__ quad_xy,
-              int32_t *__restrict__ quad_len, DetGeom g)
+k_approx(const uint4 *__restrict__ sorted, const int *__restrict__ surv_count, const int *__restrict__ pts_off,
+         const uint32_t *__restrict__ pts, uint8_t *__restrict__ quad_ok, int32_t *__restrict__ quad_xy,
+         int32_t *__restrict__ quad_len, DetGeom g)
 {
     __shared__ long long s_d[8];
     __shared__ int s_p[8];
-    __shared__ int s_list[SORT_CAP / APPROX_LONG_CTAS], s_n;     // every gridDim.x-th border index can belong to this CTA
+    __shared__ int s_list[SORT_CAP / APPROX_LONG_CTAS], s_n;     // every APPROX_LONG_CTAS-th border index can belong to this CTA
     const int fs = blockIdx.y;
     const int n = surv_count[fs];
+    if ((int)blockIdx.x >= APPROX_LONG_CTAS) {
+        const int warps_per_block = blockDim.x >> 5, nblk = (int)gridDim.x - APPROX_LONG_CTAS;
+        WarpLanes lg;
+        for (int i = ((int)blockIdx.x - APPROX_LONG_CTAS) * warps_per_block + (threadIdx.x >> 5); i < n; i += nblk * warps_per_block) {
+            const size_t slot = (size_t)fs * g.surv_cap + i;
+            const int off = pts_off[slot];
+            const int len = (int)sorted[slot].y;
+            if (len >= APPROX_LONG && off >= 0) continue;
+            bool ok = false;
+            int ox[8], oy[8];
+            if (off >= 0) {
+                const int m = approx_closed(lg, pts + (size_t)fs * g.pts_cap + off, len, (double)len * g.approxRate, ox, oy);
+                ok = (m == 4) && quad_passes(ox, oy, m, len, g.maxWH, g.minCornerDistRate);
+            }
+            if (lg.lane() == 0) approx_store(ok, len, ox, oy, slot, quad_ok, quad_xy, quad_len);
+        }
+        return;
+    }
     BlockLanes lg{s_d, s_p};
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    // this CTA's long borders (every gridDim.x-th border index), found by all threads at once
+    // this CTA's long borders (every APPROX_LONG_CTAS-th border index), found by all threads at once
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        if ((i % (int)gridDim.x) != (int)blockIdx.x) continue;
+        if ((i % APPROX_LONG_CTAS) != (int)blockIdx.x) continue;
         const size_t slot = (size_t)fs * g.surv_cap + i;
-        if ((int)__ldg(&sorted[slot].y) >= APPROX_LONG && pts_off[slot] >= 0) { s_list[atomicAdd(&s_n, 1)] = i; }
+        if ((int)__ldg(&sorted[slot].y) >= APPROX_LONG && pts_off[slot] >= 0) s_list[atomicAdd(&s_n, 1)] = i;
     }
     __syncthreads();
     const int nlong = s_n;

@@ -12,7 +12,8 @@ for the barrier and the max-over-ranks of the timed region.
            stream around K steps, detections copied back to pinned host memory inside the region).
   e2e    : the same through the public API with HOST (pinned) frames: H2D of the frames and D2H of
            the detections inside the timed region.
-  roofline    : the adaptive-threshold kernel (the streaming stage), algorithmic bytes / its CUDA-event time.
+  roofline    : the adaptive-threshold kernel (the streaming stage): algorithmic bytes per launch / its average
+           CUDA-event duration over K extra steps run with ONE sub-batch stream (so that one launch covers the batch).
   cpu_baseline: the reference's CPU path (cv2 4.13 wheel = the library the reference calls) or, if cv2 is
            not importable, the C port in oracle/, on a bounded sample of the same frames.
 """
@@ -261,6 +262,14 @@ def main():
     ms_dev, stages, launches = run(fr_dev, args.steps, args.warmup)
     ms_e2e, stages_e2e, _ = run(fr_host, args.steps, args.warmup)
     clocks = sampler.result() if rank == 0 else None
+    # roofline pass: one stream = one k_threshold launch over the whole batch, timed by the library's CUDA events
+    # on the launching stream (L2 flushed before every step like the main runs)
+    n_streams = int(os.environ.get("B2A_STREAMS", "4"))
+    det.set_streams(1)
+    _, stages_1s, _ = run(fr_dev, max(3, min(args.steps, 10)), 1)
+    det.set_streams(n_streams)
+    na = np.ctypeslib.as_array(det.detect_raw(fr_dev, cam).n_accepted, (B,)).copy()
+    nr = np.ctypeslib.as_array(det.detect_raw(fr_dev, cam).n_rejected, (B,)).copy()
 
     if rank == 0:
         total_frames = world * B * args.steps
@@ -270,10 +279,15 @@ def main():
         nS = det.num_scales
         peak, which = measured_peak_gbs()
         thr_bytes = B * (P + nS * (P // 8))                    # read gray + write nS bit-packed masks
-        thr_ms = stages.get("threshold", 0.0)
+        thr_ms = stages_1s.get("threshold", 0.0)
         achieved = thr_bytes / (thr_ms * 1e-3) / 1e9 if thr_ms > 0 else 0.0
-        K = det.max_markers
-        d2h = B * (3 * 4 + K * (32 + 4 + 32 + 24 + 24))
+        # the export kernel writes only the filled entries into the pinned host arrays
+        d2h = int(B * 12 + na.sum() * (4 + 32 + 24 + 24) + nr.sum() * 32)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_threshold3"]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         out = {
             "metric": "frames/sec detect+pose (1080p, DICT_6X6_250)" if args.workload == "C2" else "frames/sec detect+pose (%s)" % args.workload,
             "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -281,11 +295,13 @@ def main():
             "dtype": "u8 (detect) / f64 (pose)", "data": "synthetic", "config": config,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * P, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "roofline": {"kernel": "k_threshold", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": which,
-                         "algorithmic_bytes_per_launch": thr_bytes,
-                         "note": "bytes = B*(P + nScales*P/8): gray read once, bit-packed masks written; SURVEY's 4P/frame assumes byte masks",
+            "roofline": {"kernel": "k_threshold3<1,6,11>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else which,
+                         "algorithmic_bytes_per_launch": thr_bytes, "launch_ms": thr_ms,
+                         "note": "bytes = B*(P + nScales*P/8): gray read once, bit-packed masks written (SURVEY's 4P/frame assumes byte masks); "
+                                 "launch_ms = average CUDA-event duration of the one-stream pass; traffic = dram bytes of one ncu --set full capture (profiles/)",
                          "pipeline_frac_7P": (value / world) * 7 * P / (peak * 1e9)},
+            "stages_ms_per_step_one_stream": {k: round(v, 4) for k, v in stages_1s.items()},
             "stages_ms_per_step": {k: round(v, 4) for k, v in stages.items()},
             "stages_ms_per_step_e2e": {k: round(v, 4) for k, v in stages_e2e.items()},
             "parity": parity, "markers_per_step": n_markers,

@@ -11,6 +11,8 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 using namespace b2a;
@@ -32,9 +34,10 @@ struct HostCtx {
 
 // MaskView with a bounds check (a walk must never leave the padded plane)
 struct CheckedView {
-    const uint32_t *plane; int PWW, W, H; mutable bool bad = false;
+    const uint32_t *plane; int PWW, W, H; mutable bool bad = false; mutable long calls = 0;
     unsigned win9(int x, int y) const
     {
+        ++calls;
         if (x < 0 || x >= W || y < 0 || y >= H) { bad = true; return 0; }
         return MaskView{plane, PWW}.win9(x, y);
     }
@@ -193,6 +196,8 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
             CheckedView cv{pl, PWW, W, H};
             const int len = direct_walk(cv, wt.succ, wt.pred, KS, Rm, x, y, s0, key0, max_len);
             if (cv.bad) return -114;
+            if (std::getenv("EMU_WALK_STATS")) { static long tot = 0, mx = 0, cnt = 0, big = 0; tot += cv.calls; cnt++; if (cv.calls > mx) mx = cv.calls; if (cv.calls > 40) big++;
+                if (c + 1 == cx.size()) std::fprintf(stderr, "scale %d: %ld candidates, window reads total %ld max %ld, >40 reads: %ld\n", s, cnt, tot, mx, big); }
             if (len <= 0) continue;
             ++ncont;
             if (len >= minPerim && len <= maxPerim) surv.push_back({key0, len, (uint32_t)x | ((uint32_t)y << 16), 2u | ((unsigned)s0 << 8)});

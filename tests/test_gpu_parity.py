@@ -235,3 +235,50 @@ def test_contours_random_masks(aruco, oracle):
             want = np.concatenate(keep).astype(np.int16) if keep else np.zeros((0, 2), np.int16)
             assert np.array_equal(pts[0, si, :len(want)], want)
         det.close()
+
+
+def test_results_do_not_depend_on_streams_or_anchor_grid(aruco, oracle):
+    """sub-batch streams and uneven host splits are scheduling only: identical detections for 1, 4 and 8 streams,
+    device-resident and host frames"""
+    B = 12
+    frames = synth.render_batch("C2", B, base_seed=40)
+    dic = D.getPredefinedDictionary(D.DICT_6X6_250)
+    det = _detector(aruco, dic, frames.shape[1:], batch=B)
+    ref = None
+    for n in (1, 4, 8):
+        det.set_streams(n)
+        r = det.detect_batch(frames)
+        if ref is None:
+            ref = r
+            for b in (0, B - 1):
+                oc, oi, orj = oracle.detect(frames[b], dic)
+                assert np.array_equal(r.ids[b], oi) and np.array_equal(r.corners[b], oc) and np.array_equal(r.rejected[b], orj)
+        else:
+            for b in range(B):
+                assert np.array_equal(r.ids[b], ref.ids[b]) and np.array_equal(r.corners[b], ref.corners[b])
+                assert np.array_equal(r.rejected[b], ref.rejected[b])
+    det.close()
+
+
+def test_border_starting_at_the_first_pixel(aruco, oracle):
+    """a border whose first point is pixel (0,0) has start key 0 (regression: it used to collide with the sort padding)"""
+    g = np.full((96, 128), 255, np.uint8)
+    g[0:2, 0:60] = 0                        # a thin dark L hugging the top-left corner: every window size thresholds it
+    g[0:60, 0:2] = 0                        # to a region whose outer border starts at pixel (0,0)
+    g[30:32, 40:110] = 0; g[70:72, 40:110] = 0; g[30:72, 40:42] = 0; g[30:72, 108:110] = 0      # and a thin ring elsewhere
+    assert oracle.adaptive_threshold(g, 13, 7.0)[0, 0] == 255
+    dic = D.getPredefinedDictionary(0)
+    det = _detector(aruco, dic, g.shape)
+    for _ in range(2):                      # twice: the second call sees stale scratch from the first
+        counts, n_kept, kept_len, pts = det.debug_contours(g)
+        for si, k in enumerate((3, 13, 23)):
+            mk = oracle.adaptive_threshold(g, k, 7.0)
+            cs = oracle.find_contours(mk)
+            mn, mx = int(0.03 * 128), 4 * 128
+            kept = [c for c in cs if mn <= len(c) <= mx]
+            assert counts[0, si] == len(cs)
+            assert n_kept[0, si] == len(kept)
+            assert np.array_equal(kept_len[0, si, :len(kept)], [len(c) for c in kept])
+            want = np.concatenate(kept).astype(np.int16) if kept else np.zeros((0, 2), np.int16)
+            assert np.array_equal(pts[0, si, :len(want)], want)
+    det.close()
