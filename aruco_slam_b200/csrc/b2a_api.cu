@@ -332,7 +332,7 @@ static int create_impl(b2a_detector *d)
     }
     const size_t MC = d->max_cand, BM = (size_t)B * MC;
     FrameScratch &fs = d->fs0;
-    TRY(dev_alloc(d, &fs.cq, BM * 8)); TRY(dev_alloc(d, &fs.clen, BM)); TRY(dev_alloc(d, &fs.tq, BM * 8)); TRY(dev_alloc(d, &fs.tper, BM));
+    TRY(dev_alloc(d, &fs.cq, BM * 8)); TRY(dev_alloc(d, &fs.clen, BM)); TRY(dev_alloc(d, &fs.tq, BM * 8)); TRY(dev_alloc(d, &fs.tper, BM)); TRY(dev_alloc(d, &fs.cent, BM * 3));
     TRY(dev_alloc(d, &fs.gid, BM)); TRY(dev_alloc(d, &fs.sel, BM)); TRY(dev_alloc(d, &fs.gstart, (size_t)B * (MC + 1))); TRY(dev_alloc(d, &fs.gfill, BM));
     TRY(dev_alloc(d, &fs.members, BM)); TRY(dev_alloc(d, &fs.closeIdx, BM)); TRY(dev_alloc(d, &fs.closeCnt, BM));
     TRY(dev_alloc(d, &fs.S, BM)); TRY(dev_alloc(d, &fs.parent, BM)); TRY(dev_alloc(d, &fs.depth, BM)); TRY(dev_alloc(d, &fs.selGroup, BM));
@@ -350,6 +350,7 @@ static int create_impl(b2a_detector *d)
     TRY(pin_alloc(d, &d->h_corners, BK * 8)); TRY(pin_alloc(d, &d->h_ids, BK)); TRY(pin_alloc(d, &d->h_rejected, BK * 8));
     TRY(pin_alloc(d, &d->h_rvecs, BK * 3)); TRY(pin_alloc(d, &d->h_tvecs, BK * 3));
     CU(cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_group_a, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (d->max_cand + 1) * (int)sizeof(uint32_t)));
     CU(cudaFuncSetAttribute(k_identify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)identify_smem_bytes(ID_MAX_S)));
     CU(cudaFuncSetAttribute(k_threshold3<1, 6, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3_SMEM));
     CU(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (int)sizeof(int32_t) * d->max_cand));
@@ -483,7 +484,7 @@ static FrameScratch offset_scratch(const FrameScratch &b, size_t f, size_t mc)
 {
     FrameScratch s = b;
     const size_t o = f * mc;
-    s.cq += o * 8; s.clen += o; s.tq += o * 8; s.tper += o; s.gid += o; s.sel += o;
+    s.cq += o * 8; s.clen += o; s.tq += o * 8; s.tper += o; s.cent += o * 3; s.gid += o; s.sel += o;
     s.gstart += f * (mc + 1); s.gfill += o; s.members += o; s.closeIdx += o; s.closeCnt += o;
     s.S += o; s.parent += o; s.depth += o; s.selGroup += o;
     s.closeM += o * 2 * ((mc + 31) / 32);
@@ -608,8 +609,10 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
     const FrameParams fp = frame_params(d, g);
     stage_mark(d, s, ST_GROUP);
     const int smem_words = 50 * 1024;                       // 200 KB: per-candidate arrays + closeness matrix
+    k_group_a<<<nb, 1024, 8 * (d->max_cand + 1) * sizeof(uint32_t), st>>>(fa, fp);
+    k_close<<<dim3(CLOSE_CTAS, nb), 256, 0, st>>>(fa, fp);
     k_group<<<nb, 1024, smem_words * sizeof(uint32_t), st>>>(fa, fp, smem_words);
-    d->launches++;
+    d->launches += 3;
     if (fa.marks && s.sb == 0) {
         long long hm[32];
         cudaStreamSynchronize(st);

@@ -866,7 +866,7 @@ __device__ __forceinline__ FrameScratch frame_scratch(const FrameScratch &b, int
 {
     FrameScratch s = b;
     const size_t o = (size_t)f * mc;
-    s.cq += o * 8; s.clen += o; s.tq += o * 8; s.tper += o; s.gid += o; s.sel += o;
+    s.cq += o * 8; s.clen += o; s.tq += o * 8; s.tper += o; s.cent += o * 3; s.gid += o; s.sel += o;
     s.gstart += (size_t)f * (mc + 1); s.gfill += o; s.members += o; s.closeIdx += o; s.closeCnt += o;
     s.S += o; s.parent += o; s.depth += o; s.selGroup += o;
     s.closeM += o * 2 * (size_t)((mc + 31) / 32);
@@ -875,9 +875,48 @@ __device__ __forceinline__ FrameScratch frame_scratch(const FrameScratch &b, int
     return s;
 }
 
-// dynamic shared memory of k_group: 8 per-candidate arrays (gid, sel, gstart, gfill, members,
-// closeIdx, closeCnt, tper) that the sequential grouping section hammers, then the closeness
-// bit matrix in whatever is left (global fallback when it does not fit)
+// A4-A5 in three launches: k_group_a (one CTA per frame: candidates in T order), k_close (many CTAs per frame:
+// the O(n^2) closeness matrix), k_group (one CTA per frame: grouping, selection, hierarchy, work list).
+// dynamic shared memory of k_group_a / k_group: 8 per-candidate arrays (gid, sel, gstart, gfill, members,
+// closeIdx, closeCnt, tper), then (k_group) the T-order quads, the two bit matrices and the selected-candidate arrays
+__device__ __forceinline__ void group_setup(const FrameArrays &fa, const FrameParams &fp, int f, uint32_t *s_dyn, FrameScratch &fs, ScaleQuads &sq)
+{
+    fs = frame_scratch(fa.fs0, f, fp.max_cand);
+    const int mc1 = fp.max_cand + 1;
+    int32_t *base = reinterpret_cast<int32_t *>(s_dyn);
+    fs.gid = base; fs.sel = base + mc1; fs.gstart = base + 2 * mc1; fs.gfill = base + 3 * mc1;
+    fs.members = base + 4 * mc1; fs.closeIdx = base + 5 * mc1; fs.closeCnt = base + 6 * mc1;
+    fs.tper = reinterpret_cast<float *>(base + 7 * mc1);
+    sq.count = fa.surv_count + (size_t)f * fp.nScales;
+    sq.quad_ok = fa.quad_ok + (size_t)f * fp.nScales * fp.surv_cap;
+    sq.quad_xy = fa.quad_xy + (size_t)f * fp.nScales * fp.surv_cap * 8;
+    sq.len = fa.quad_len + (size_t)f * fp.nScales * fp.surv_cap;
+}
+
+__global__ void __launch_bounds__(1024)
+k_group_a(FrameArrays fa, FrameParams fp)
+{
+    extern __shared__ uint32_t s_dyn[];
+    __shared__ int s_warp[33];
+    BlockCtx ctx{s_warp};
+    FrameScratch fs; ScaleQuads sq;
+    group_setup(fa, fp, blockIdx.x, s_dyn, fs, sq);
+    frame_group(ctx, fp, sq, fs, nullptr, 0, 1);
+}
+
+constexpr int CLOSE_CTAS = 16;
+__global__ void __launch_bounds__(256)
+k_close(FrameArrays fa, FrameParams fp)
+{
+    __shared__ int s_warp[33];
+    BlockCtx ctx{s_warp};
+    const FrameScratch fs = frame_scratch(fa.fs0, blockIdx.y, fp.max_cand);
+    const int n = fs.counters[FC_NCAND], wpr = (n + 31) >> 5;
+    const int nwarps = (int)gridDim.x * (blockDim.x >> 5);
+    for (int t = (int)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n * wpr; t += nwarps)
+        close_task(ctx, fp, fs.tq, fs.cent, n, wpr, t, fs.closeM, fs.closeM + (size_t)n * wpr);
+}
+
 __global__ void __launch_bounds__(1024)
 k_group(FrameArrays fa, FrameParams fp, int smem_words)
 {
@@ -886,18 +925,10 @@ k_group(FrameArrays fa, FrameParams fp, int smem_words)
     const int f = blockIdx.x;
     BlockCtx ctx{s_warp};
     if (fa.marks) { ctx.marks = fa.marks + (size_t)f * 32; if (threadIdx.x == 0) ctx.marks[ctx.nmark++] = clock64(); }
-    FrameScratch fs = frame_scratch(fa.fs0, f, fp.max_cand);
+    FrameScratch fs; ScaleQuads sq;
+    group_setup(fa, fp, f, s_dyn, fs, sq);
     const int mc1 = fp.max_cand + 1;
-    int32_t *base = reinterpret_cast<int32_t *>(s_dyn);
-    fs.gid = base; fs.sel = base + mc1; fs.gstart = base + 2 * mc1; fs.gfill = base + 3 * mc1;
-    fs.members = base + 4 * mc1; fs.closeIdx = base + 5 * mc1; fs.closeCnt = base + 6 * mc1;
-    fs.tper = reinterpret_cast<float *>(base + 7 * mc1);
-    ScaleQuads sq;
-    sq.count = fa.surv_count + (size_t)f * fp.nScales;
-    sq.quad_ok = fa.quad_ok + (size_t)f * fp.nScales * fp.surv_cap;
-    sq.quad_xy = fa.quad_xy + (size_t)f * fp.nScales * fp.surv_cap * 8;
-    sq.len = fa.quad_len + (size_t)f * fp.nScales * fp.surv_cap;
-    frame_group(ctx, fp, sq, fs, s_dyn + 8 * mc1, smem_words - 8 * mc1);
+    frame_group(ctx, fp, sq, fs, s_dyn + 8 * mc1, smem_words - 8 * mc1, 2);
 }
 
 // dynamic shared memory of k_finalize: copies of depth, parent, closeStart, closeNum (n_sel entries),

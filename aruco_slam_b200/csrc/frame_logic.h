@@ -37,6 +37,7 @@ struct FrameScratch {
     int32_t *clen;      // [max_cand]
     float   *tq;        // [max_cand][8] quads in T order (sorted by perimeter, descending, stable)
     float   *tper;      // [max_cand]
+    float   *cent;      // [max_cand][3]  T order: 4 * centroid x, 4 * centroid y, perimeter * minMarkerDistanceRate
     int32_t *gid;       // [max_cand]
     int32_t *sel;       // [max_cand]
     int32_t *gstart;    // [max_cand + 1]
@@ -60,15 +61,43 @@ struct FrameScratch {
 enum { FC_NCAND = 0, FC_NSEL = 1, FC_NWORK = 2, FC_STATUS = 3 };
 
 // --------------------------------------------------------------------------------------------
+// One row-word of the closeness matrix: bits j (in word w) of row i, j > i, and the transposed bits.
+// lane = candidate j; tq / cent are the T-order quads and (4 * centroid, threshold) of part A.
+template <class Ctx>
+B2A_HD void close_task(Ctx &ctx, const FrameParams &fp, const float *tq, const float *cent, int n, int wpr, int t, uint32_t *M, uint32_t *MT)
+{
+    const int lane = ctx.lane(), nl = ctx.lanes();
+    const int i = t / wpr, w = t - i * wpr;
+    uint32_t bits = 0;
+    if (w * 32 + 31 > i) {
+        const float *a = tq + (size_t)i * 8;
+        const float acx = cent[3 * i], acy = cent[3 * i + 1];
+        for (int b = lane; b < 32; b += nl) {
+            const int j = w * 32 + b;
+            if (j <= i || j >= n) continue;
+            const float thr = cent[3 * j + 2];
+            // |centroid_a - centroid_b| <= avgDist: cheap exact-safe rejection (integer coordinates)
+            const float dcx = (acx - cent[3 * j]) * 0.25f, dcy = (acy - cent[3 * j + 1]) * 0.25f;
+            if (dcx * dcx + dcy * dcy > thr * thr * 1.01f + 1.0f) continue;
+            if (quad_avg_distance(a, tq + (size_t)j * 8) < thr) { bits |= 1u << b; ctx.atomic_or(&MT[j * wpr + (i >> 5)], 1u << (i & 31)); }
+        }
+    }
+    bits = ctx.warp_or(bits);
+    if (lane == 0) M[t] = bits;
+}
+
+// phase 0: the whole stage in one go (host emulation); on the device the closeness matrix is filled by many
+// CTAs per frame in between: phase 1 = up to the T-order staging, [k_close], phase 2 = the rest.
 template <class Ctx>
 B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, const FrameScratch &fs,
-                        uint32_t *smemM, int smemM_words)
+                        uint32_t *smemM, int smemM_words, int phase)
 {
     const int tid = ctx.tid(), nt = ctx.nthreads();
+    int n = 0;
+    if (phase != 2) {
     if (tid == 0) fs.counters[FC_STATUS] = 0;
     ctx.sync();
     // ---- 1. gather candidates in reference order (scale by scale, contour list order) + A4 ----
-    int n = 0;
     for (int s = 0; s < fp.nScales; ++s) {
         const int cnt = sq.count[s] < fp.surv_cap ? sq.count[s] : fp.surv_cap;
         for (int base = 0; base < cnt; base += nt) {
@@ -98,60 +127,53 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
         fs.members[i] = rank;       // temp: candidate i -> T position
     }
     ctx.sync();
-    // shared-memory staging (device): T-order quads, per-candidate (4 * centroid, threshold), then the matrix
-    const int wpr = (n + 31) >> 5;
-    float *tqs = nullptr, *cent = nullptr;
-    uint32_t *Msm = smemM;
-    int Mwords = smemM_words;
-    if (smemM && 11 * n + 6 * fp.max_cand <= smemM_words) {
-        tqs = reinterpret_cast<float *>(smemM); cent = tqs + 8 * n;
-        Msm = smemM + 11 * n; Mwords = smemM_words - 11 * n;
-    }
+    // T order: quads, perimeters, (4 * centroid, threshold) in global memory
     for (int i = tid; i < n; i += nt) {
         const int r = fs.members[i];
-        for (int k = 0; k < 8; ++k) { const float v = fs.cq[(size_t)i * 8 + k]; fs.tq[(size_t)r * 8 + k] = v; if (tqs) tqs[r * 8 + k] = v; }
-        fs.gfill[r] = i;            // temp: T position -> candidate index
+        for (int k = 0; k < 8; ++k) fs.tq[(size_t)r * 8 + k] = fs.cq[(size_t)i * 8 + k];
     }
     ctx.sync();
-    const float *tq = tqs ? tqs : fs.tq;
     for (int i = tid; i < n; i += nt) {
-        fs.gid[i] = -1; fs.sel[i] = 1;
-        const float *a = tq + (size_t)i * 8;
+        const float *a = fs.tq + (size_t)i * 8;
         const float per = quad_perimeter(a);
         fs.tper[i] = per;
-        if (cent) { cent[3 * i] = (a[0] + a[2]) + (a[4] + a[6]); cent[3 * i + 1] = (a[1] + a[3]) + (a[5] + a[7]); cent[3 * i + 2] = f_mul(per, fp.minMarkerDistanceRate); }
+        fs.cent[3 * i] = (a[0] + a[2]) + (a[4] + a[6]); fs.cent[3 * i + 1] = (a[1] + a[3]) + (a[5] + a[7]); fs.cent[3 * i + 2] = f_mul(per, fp.minMarkerDistanceRate);
     }
+    {   // the transposed matrix is filled with atomic ORs: clear it
+        const int wpr0 = (n + 31) >> 5;
+        uint32_t *MT0 = fs.closeM + (size_t)n * wpr0;
+        for (int t = tid; t < n * wpr0; t += nt) MT0[t] = 0;
+    }
+    if (tid == 0) fs.counters[FC_NCAND] = n;
     ctx.sync();
-    // ---- 3. closeness bit matrix: bit j of row i (j > i) iff avgDist(T[i],T[j]) < perimeter_j * rate ----
-    // M: row i, bits j > i.  MT: the transposed bits (row j, bits i < j), so that both "smallest close
-    // neighbour below" and "above" are first-set-bit scans.  One warp per (row, word): lane = candidate j.
-    const bool Msmem = (long long)2 * n * wpr <= (long long)Mwords;
-    uint32_t *M = Msmem ? Msm : fs.closeM, *MT = M + (size_t)n * wpr;
-    for (int t = tid; t < n * wpr; t += nt) MT[t] = 0;
-    ctx.sync();
+    if (phase == 1) return;
+    }   // phase != 2
+    else n = fs.counters[FC_NCAND];
+    const int wpr = (n + 31) >> 5;
+    // ---- 3. closeness bit matrix (global): M row i, bits j > i iff avgDist(T[i],T[j]) < perimeter_j * rate; MT the transposed
+    // bits (row j, bits i < j), so that both "smallest close neighbour below" and "above" are first-set-bit scans.
+    if (phase == 0) {
+        for (int t = ctx.warp(); t < n * wpr; t += ctx.warps()) close_task(ctx, fp, fs.tq, fs.cent, n, wpr, t, fs.closeM, fs.closeM + (size_t)n * wpr);
+        ctx.sync();
+    }
+    // shared-memory staging (device): T-order quads, the two matrices, later the selected-candidate arrays
     const int lane = ctx.lane(), nl = ctx.lanes();
-    for (int t = ctx.warp(); t < n * wpr; t += ctx.warps()) {
-        const int i = t / wpr, w = t - i * wpr;
-        uint32_t bits = 0;
-        if (w * 32 + 31 > i) {
-            const float *a = tq + (size_t)i * 8;
-            const float acx = (a[0] + a[2]) + (a[4] + a[6]), acy = (a[1] + a[3]) + (a[5] + a[7]);   // 4 * centroid
-            for (int b = lane; b < 32; b += nl) {
-                const int j = w * 32 + b;
-                if (j <= i || j >= n) continue;
-                const float *q = tq + (size_t)j * 8;
-                float qcx, qcy, thr;
-                if (cent) { qcx = cent[3 * j]; qcy = cent[3 * j + 1]; thr = cent[3 * j + 2]; }
-                else { qcx = (q[0] + q[2]) + (q[4] + q[6]); qcy = (q[1] + q[3]) + (q[5] + q[7]); thr = f_mul(fs.tper[j], fp.minMarkerDistanceRate); }
-                // |centroid_a - centroid_b| <= avgDist: cheap exact-safe rejection (integer coordinates)
-                const float dcx = (acx - qcx) * 0.25f, dcy = (acy - qcy) * 0.25f;
-                if (dcx * dcx + dcy * dcy > thr * thr * 1.01f + 1.0f) continue;
-                if (quad_avg_distance(a, q) < thr) { bits |= 1u << b; ctx.atomic_or(&MT[j * wpr + (i >> 5)], 1u << (i & 31)); }
-            }
-        }
-        bits = ctx.warp_or(bits);
-        if (lane == 0) M[t] = bits;
+    float *tqs = nullptr;
+    uint32_t *Msm = smemM;
+    int Mwords = smemM_words;
+    if (smemM && 8 * n + 6 * fp.max_cand <= smemM_words) {
+        tqs = reinterpret_cast<float *>(smemM);
+        Msm = smemM + 8 * n; Mwords = smemM_words - 8 * n;
+        for (int t = tid; t < 8 * n; t += nt) tqs[t] = fs.tq[t];
     }
+    const float *tq = tqs ? tqs : fs.tq;
+    uint32_t *M = fs.closeM, *MT = fs.closeM + (size_t)n * wpr;
+    if (Msm && (long long)2 * n * wpr + 6 * fp.max_cand <= (long long)Mwords) {
+        for (int t = tid; t < 2 * n * wpr; t += nt) Msm[t] = fs.closeM[t];
+        M = Msm; MT = Msm + (size_t)n * wpr;
+        Msm += 2 * n * wpr; Mwords -= 2 * n * wpr;
+    }
+    for (int i = tid; i < n; i += nt) { fs.gid[i] = -1; fs.sel[i] = 1; }
     ctx.sync();
     // ---- 4. group assignment (A5).  OpenCV walks the close pairs (i, j), i < j, in lexicographic order:
     //   both ungrouped -> new group; one grouped -> the other joins it; both grouped -> nothing (no merge).

@@ -241,11 +241,11 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
     }
     // per-frame logic
     const int MC = ep->max_cand;
-    std::vector<float> cq((size_t)MC * 8), tq((size_t)MC * 8), tper(MC), wq((size_t)MC * 8);
+    std::vector<float> cq((size_t)MC * 8), tq((size_t)MC * 8), tper(MC), cent((size_t)MC * 3), wq((size_t)MC * 8);
     std::vector<int32_t> clen(MC), gid(MC), sel(MC), gstart(MC + 1), gfill(MC), members(MC), closeIdx(MC), closeCnt(MC), S(MC), parent(MC), depth(MC),
         selGroup(MC), wres(MC), closeStart(MC), closeNum(MC), counters(8, 0);
     std::vector<uint32_t> closeM((size_t)MC * 2 * ((MC + 31) / 32));
-    FrameScratch fs{cq.data(), clen.data(), tq.data(), tper.data(), gid.data(), sel.data(), gstart.data(), gfill.data(), members.data(),
+    FrameScratch fs{cq.data(), clen.data(), tq.data(), tper.data(), cent.data(), gid.data(), sel.data(), gstart.data(), gfill.data(), members.data(),
                     closeIdx.data(), closeCnt.data(), S.data(), parent.data(), depth.data(), selGroup.data(), closeM.data(),
                     wq.data(), wres.data(), closeStart.data(), closeNum.data(), counters.data()};
     FrameParams fp;
@@ -254,7 +254,7 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
     fp.minMarkerDistanceRate = ep->minMarkerDistanceRate; fp.minGroupDistance = ep->minGroupDistance;
     ScaleQuads sq{s_count.data(), q_ok.data(), q_xy.data(), q_len.data()};
     HostCtx ctx;
-    frame_group(ctx, fp, sq, fs, nullptr, 0);
+    frame_group(ctx, fp, sq, fs, nullptr, 0, 0);
     if (n_cand) *n_cand = counters[FC_NCAND];
     if (cand) std::memcpy(cand, cq.data(), (size_t)counters[FC_NCAND] * 8 * sizeof(float));
     // identification of every work item (k_identify's body, one lane)
