@@ -81,7 +81,7 @@ SYMBOLS = [
     "b2a_estimate_pose_single_markers", "b2a_debug_threshold", "b2a_debug_contours", "b2a_debug_candidates",
     "b2a_detector_num_scales", "b2a_detector_set_streams", "b2a_last_stage_times", "b2a_last_launch_count", "b2a_detector_stream",
     "b2a_default_slam_params", "b2a_slam_create", "b2a_slam_destroy", "b2a_slam_dim", "b2a_slam_get_state",
-    "b2a_slam_set_state", "b2a_slam_add_encoder", "b2a_slam_make_observations", "b2a_slam_update", "b2a_slam_add_image",
+    "b2a_slam_set_state", "b2a_slam_add_encoder", "b2a_slam_make_observations", "b2a_slam_update", "b2a_slam_add_image", "b2a_slam_synchronize",
 ]
 
 _lib = None
@@ -107,7 +107,7 @@ def lib():
         L.b2a_version.restype = C.c_char_p
         L.b2a_detector_stream.restype = C.c_void_p
         for name in ("b2a_detector_destroy", "b2a_detector_num_scales", "b2a_last_launch_count", "b2a_detector_stream",
-                     "b2a_slam_destroy", "b2a_slam_dim"):
+                     "b2a_slam_destroy", "b2a_slam_dim", "b2a_slam_synchronize"):
             getattr(L, name).argtypes = [C.c_void_p]
         L.b2a_detector_set_streams.argtypes = [C.c_void_p, C.c_int]
         L.b2a_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]

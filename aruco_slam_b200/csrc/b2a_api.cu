@@ -962,6 +962,14 @@ extern "C" int b2a_slam_create(int device, const b2a_slam_params *p, b2a_slam **
 
 extern "C" int b2a_slam_dim(const b2a_slam *s) { return s ? s->N : 0; }
 
+extern "C" int b2a_slam_synchronize(b2a_slam *s)
+{
+    if (!s) return set_err(B2A_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    return B2A_OK;
+}
+
 extern "C" int b2a_slam_get_state(b2a_slam *s, double *mu, double *sigma, int32_t *ids)
 {
     if (!s) return set_err(B2A_ERR_INVALID, "null handle");

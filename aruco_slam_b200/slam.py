@@ -86,6 +86,10 @@ class ArucoSlam:
         arr = (_lib.Observation * max(n, 1))(*observations)
         _lib.check(_lib.lib().b2a_slam_update(self._h, arr, n))
 
+    def synchronize(self):
+        """wait for the EKF kernels enqueued so far"""
+        _lib.check(_lib.lib().b2a_slam_synchronize(self._h))
+
     @property
     def dim(self) -> int:
         return _lib.lib().b2a_slam_dim(self._h)

@@ -36,6 +36,84 @@ from aruco_slam_b200 import synth, dictionaries as D  # noqa: E402
 K_CAM = np.array([[1400.0, 0, 960], [0, 1400.0, 540], [0, 0, 1]])
 D_CAM = np.array([0.05, -0.1, 0.001, -0.002, 0.02])
 MARKER_LENGTH = 0.27                    # reference parameters.yaml:17
+# C5 (BASELINE.json config 5): EKF correction only, 500 landmarks = 1503-dimensional state (the reference's state is
+# 3 + 3 n, include/aruco_slam/aruco_slam.h:182; the "1003" of BASELINE.json would be 2-D landmarks), 30 observations of
+# distinct known landmarks per frame.  python bench.py --workload C5 [--ekf-landmarks 500]
+def bench_ekf(args):
+    from aruco_slam_b200 import slam, _lib
+    from oracle import oracle as O
+    n_lm, n_obs = args.ekf_landmarks, 30
+    N = 3 + 3 * n_lm
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(N, N))
+    sigma0 = A @ A.T / N + 0.1 * np.eye(N)
+    mu0 = np.concatenate([[0.3, -0.2, 0.4], rng.uniform(-4, 4, 3 * n_lm)])
+    ids = np.arange(n_lm, dtype=np.int32)
+
+    def frame_obs(cls, step):
+        r = np.random.default_rng(100 + step)
+        out = []
+        for k in r.choice(n_lm, n_obs, replace=False):
+            L = 3 + 3 * k
+            c, sn = np.cos(mu0[2]), np.sin(mu0[2])
+            dx, dy = mu0[L] - mu0[0], mu0[L + 1] - mu0[1]
+            z = np.array([dx * c + dy * sn, -dx * sn + dy * c, mu0[L + 2] - mu0[2]]) + r.normal(0, 0.02, 3)
+            o = cls()
+            o.aruco_id, o.aruco_index, o.x, o.y, o.theta = int(k), -1, z[0], z[1], z[2]
+            for i, v in enumerate([0.02, 0, 0, 0, 0.02, 0, 0, 0, 0.003]):
+                o.cov[i] = v
+            out.append(o)
+        return out
+
+    s = slam.ArucoSlam(image_shape=(64, 64), max_landmarks=n_lm + 4)
+    s.set_state(mu0, sigma0, ids)
+    frames = [frame_obs(_lib.Observation, k) for k in range(args.warmup + args.steps)]
+    for k in range(args.warmup):
+        s.update(frames[k])
+    s.synchronize()
+    t0 = time.perf_counter()
+    for k in range(args.warmup, args.warmup + args.steps):
+        s.update(frames[k])
+    s.synchronize()
+    dt = time.perf_counter() - t0
+    obs_s = args.steps * n_obs / dt
+    # parity of the final state against the CPU port run over the same frames
+    e = O.Ekf(O.slam_params())
+    e.set_state(mu0, sigma0, ids)
+    t1 = time.perf_counter()
+    for k in range(args.warmup + args.steps):
+        e.update(frame_obs(O.Observation, k), dense=False)
+    cpu_rank3 = (args.warmup + args.steps) * n_obs / (time.perf_counter() - t1)
+    mu, sg, _ = s.get_state()
+    omu, osg, _ = e.get_state()
+    parity = "ok" if (np.abs(mu - omu).max() < 1e-9 and np.abs(sg - osg).max() < 1e-9) else "MISMATCH"
+    # the reference evaluates (I - K Gx) Sigma as a dense N x N product (src/aruco_slam.cpp:204): time a few of those
+    e2 = O.Ekf(O.slam_params())
+    e2.set_state(mu0, sigma0, ids)
+    t2 = time.perf_counter()
+    nd = 0
+    while time.perf_counter() - t2 < 10.0 and nd < 3:
+        e2.update(frame_obs(O.Observation, nd)[:2], dense=True)
+        nd += 1
+    cpu_dense = nd * 2 / (time.perf_counter() - t2)
+    peak, which = measured_peak_gbs()
+    bytes_per_obs = 16 * N * N
+    achieved = obs_s * bytes_per_obs / 1e9
+    print(json.dumps({
+        "metric": "EKF landmark updates/sec (N = %d)" % N, "value": obs_s, "unit": "observations/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C5: EKF correction, %d landmarks (state dimension %d), %d observations of known landmarks per frame" % (n_lm, N, n_obs),
+                   "timing": "wall clock around K frames of b2a_slam_update + stream synchronize (observations passed from the host each frame)"},
+        "roofline": {"kernel": "k_ekf_rank3 (+ k_ekf_gain)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": which, "algorithmic_bytes_per_launch": bytes_per_obs,
+                     "note": "16 N^2 bytes per observation (read + write Sigma, FP64); includes the gain kernel and launch gaps of the sequential per-observation updates"},
+        "cpu_baseline": {"value": cpu_rank3, "unit": "observations/s", "cores": 1, "kind": "port",
+                         "sample": "oracle/ C port, rank-3 form, %d observations" % ((args.warmup + args.steps) * n_obs),
+                         "reference_dense_form": {"value": cpu_dense, "unit": "observations/s", "sample": "%d observations with the reference's dense (I - K Gx) Sigma product (aruco_slam.cpp:204)" % (nd * 2)}},
+        "parity": parity, "gpu_launches": 2 * n_obs * args.steps}))
+    s.close()
+
+
 WORKLOADS = {
     "C1": ("640x480 gray, 4 DICT_4X4_50 markers", D.DICT_4X4_50),
     "C2": ("1920x1080 gray, 30 DICT_6X6_250 markers", D.DICT_6X6_250),
@@ -149,7 +227,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="C2", choices=list(WORKLOADS) + ["C5"])
+    ap.add_argument("--ekf-landmarks", type=int, default=500)
     ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -157,6 +236,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "C5":
+        if rank == 0:
+            bench_ekf(args)
+        return
     desc, dict_id = WORKLOADS[args.workload]
     cfg = synth.CONFIGS[args.workload]
     W, H, B = cfg["W"], cfg["H"], args.batch

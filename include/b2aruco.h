@@ -188,6 +188,8 @@ int  b2a_slam_make_observations(b2a_slam *s, const float *corners, const int32_t
                                 b2a_observation *out, int *n_out);
 /* The EKF loop of addImage (aruco_slam.cpp:88-263) for one frame's observations. */
 int  b2a_slam_update(b2a_slam *s, const b2a_observation *obs, int n);
+/* The EKF kernels are enqueued on the handle's stream; get_state waits for them, and so does this (used to time updates). */
+int  b2a_slam_synchronize(b2a_slam *s);
 /* addImage(img): detect + pose + observations + EKF update for one frame (aruco_slam.cpp:76-263). */
 int  b2a_slam_add_image(b2a_slam *s, b2a_detector *d, const b2a_frames *frame, const b2a_camera *cam);
 

@@ -1,0 +1,110 @@
+"""-m gpu: the SLAM half of the path (observation mapping, EKF predict / correct / augment with the
+covariance resident in HBM) through the C ABI, against the CPU oracle (a line-by-line restatement of
+reference src/aruco_slam.cpp:21-74,88-263,325-374,437-471; the reference has no tests for it, so this
+part of the parity is unpinned beyond oracle == independent NumPy restatement, tests/test_oracle_ekf.py).
+Tolerances: FP64 throughout, same update order -> 1e-9 absolute on mu and Sigma (north_star asks 1e-4)."""
+import numpy as np
+import pytest
+
+from test_oracle_ekf import _scenario
+from aruco_slam_b200 import dictionaries as D, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _obs_struct(cls, aid, x, y, th, R):
+    o = cls()
+    o.aruco_id, o.aruco_index, o.x, o.y, o.theta = int(aid), -1, float(x), float(y), float(th)
+    for i in range(9):
+        o.cov[i] = float(np.asarray(R).reshape(9)[i])
+    return o
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_ekf_scenario_vs_oracle(oracle, seed):
+    """predict + correct + augment over 25 frames, duplicates and repeated observations included"""
+    from aruco_slam_b200 import slam, _lib
+    s = slam.ArucoSlam(image_shape=(64, 64))
+    e = oracle.Ekf(oracle.slam_params())
+    for (wl, wr, dt), obs in _scenario(seed):
+        s.addEncoder(wl, wr, dt)
+        e.predict(wl, wr, dt)
+        s.update([_obs_struct(_lib.Observation, *o) for o in obs])
+        e.update([_obs_struct(oracle.Observation, *o) for o in obs])
+        mu, sg, ids = s.get_state()
+        omu, osg, oids = e.get_state()
+        assert np.array_equal(ids, oids)
+        assert np.abs(mu - omu).max() < 1e-9
+        assert np.abs(sg - osg).max() < 1e-9
+    assert len(mu) > 3 + 3 * 8
+    s.close()
+
+
+@pytest.mark.parametrize("n_lm", [334, 500])          # state dimension 1005 and 1503 (BASELINE config 5, both readings)
+def test_ekf_large_state_vs_oracle(oracle, n_lm):
+    """30 observations of distinct known landmarks on a 1003+ / 1503-dimensional filter (set_state / get_state round trip)"""
+    from aruco_slam_b200 import slam, _lib
+    rng = np.random.default_rng(5)
+    N = 3 + 3 * n_lm
+    A = rng.normal(size=(N, N))
+    sigma0 = A @ A.T / N + 0.1 * np.eye(N)
+    mu0 = np.concatenate([[0.3, -0.2, 0.4], rng.uniform(-4, 4, 3 * n_lm)])
+    ids = np.arange(n_lm, dtype=np.int32) * 2 + 1
+    s = slam.ArucoSlam(image_shape=(64, 64), max_landmarks=n_lm + 4)
+    e = oracle.Ekf(oracle.slam_params())
+    s.set_state(mu0, sigma0, ids)
+    e.set_state(mu0, sigma0, ids)
+    mu, sg, gi = s.get_state()
+    assert np.array_equal(mu, mu0) and np.array_equal(sg, sigma0) and np.array_equal(gi, ids)
+    obs = []
+    for k in rng.choice(n_lm, 30, replace=False):
+        L = 3 + 3 * k
+        c, sn = np.cos(mu0[2]), np.sin(mu0[2])
+        dx, dy = mu0[L] - mu0[0], mu0[L + 1] - mu0[1]
+        z = np.array([dx * c + dy * sn, -dx * sn + dy * c, mu0[L + 2] - mu0[2]]) + rng.normal(0, 0.02, 3)
+        obs.append((ids[k], z[0], z[1], z[2], np.diag([0.02, 0.02, 0.003])))
+    obs.append((9999, 1.0, 0.5, 0.2, np.diag([0.02, 0.02, 0.003])))          # and one new landmark
+    s.update([_obs_struct(_lib.Observation, *o) for o in obs])
+    e.update([_obs_struct(oracle.Observation, *o) for o in obs])
+    mu, sg, gi = s.get_state()
+    omu, osg, oi = e.get_state()
+    assert len(mu) == N + 3 and np.array_equal(gi, oi)
+    assert np.abs(mu - omu).max() < 1e-9
+    assert np.abs(sg - osg).max() < 1e-9
+    s.close()
+
+
+def test_add_image_vs_oracle_pipeline(oracle):
+    """addImage(img): detect + pose + observation mapping + EKF on the GPU == the same chain through the oracle"""
+    from aruco_slam_b200 import slam
+    dic_id = D.DICT_4X4_50
+    K = np.array([[600.0, 0, 320], [0, 600.0, 240], [0, 0, 1]])
+    Dist = np.array([0.05, -0.1, 0.001, -0.002, 0.02])
+    L = 0.27
+    # four markers at true 3-D poses (planar squares), so the reprojection error and hence the observation covariance are small
+    # (a marker facing the camera has a rotation of about pi around x: object y points up, image y down)
+    poses = [(3, [3.0, -0.3, 0.05], [-0.6, -0.3, 2.2]), (11, [2.8, 0.4, 0.3], [0.7, -0.2, 2.6]),
+             (24, [3.05, 0.2, -0.4], [-0.5, 0.45, 2.0]), (40, [2.9, 0.1, 0.2], [0.6, 0.4, 2.4])]
+    fr = synth.render_scene(640, 480, dic_id, K, Dist, L, poses).image
+    s = slam.ArucoSlam(dic_id, L, image_shape=fr.shape, useful_distance_threshold=50.0)
+    s.setCameraParameters(K, Dist)
+    s.addImage(fr)                                   # before the first encoder message: ignored (aruco_slam.cpp:84-85)
+    assert s.dim == 3
+    s.addEncoder(0, 0, None)
+    sp = oracle.slam_params(marker_length=L, useful_distance_threshold=50.0)
+    e = oracle.Ekf(sp)
+    dic = D.getPredefinedDictionary(dic_id)
+    for step in range(3):
+        s.addEncoder(2.0, 2.5, 0.1)
+        e.predict(2.0, 2.5, 0.1)
+        s.addImage(fr)
+        oc, oi, _ = oracle.detect(fr, dic)
+        orv, otv = oracle.estimate_pose_single_markers(oc, L, K, Dist)
+        obs = oracle.make_observations(oc, oi, orv, otv, K, Dist, sp)
+        e.update(obs)
+        mu, sg, ids = s.get_state()
+        omu, osg, oids = e.get_state()
+        assert len(oids) == 4 and np.array_equal(ids, oids)
+        assert np.abs(mu - omu).max() < 1e-4        # north_star: 1e-4 m / rad (poses come from two LM implementations)
+        assert np.abs(sg - osg).max() < 1e-4
+    s.close()
