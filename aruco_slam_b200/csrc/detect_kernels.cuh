@@ -243,26 +243,30 @@ k_threshold3(const uint8_t *__restrict__ gray, size_t pitch, size_t frame_stride
     constexpr int K0 = (2 * R0 + 1) * (2 * R0 + 1), K1 = (2 * R1 + 1) * (2 * R1 + 1), K2 = (2 * R2 + 1) * (2 * R2 + 1);
     const int c2 = 2 * g.Cfloor - 1;
     const int wi = (x0 >> 5) + (c >> 5) + 1;                      // padded word index of this warp's 32 columns
-    const bool store = (lane == 0) && (wi <= g.WW);
-    uint32_t *out0 = masks + ((size_t)b * 3 + 0) * g.mask_plane + (size_t)(y0 + j0 + 1) * g.PWW + wi;
-    uint32_t *out1 = out0 + g.mask_plane, *out2 = out1 + g.mask_plane;
+    // the 24 mask words of 8 rows x 3 scales are parked on lanes 0..23 (lane = scale * 8 + row) and leave in one store
+    const int my_u = lane & 7, my_s = lane >> 3;
+    uint32_t *outp = masks + ((size_t)b * 3 + (my_s < 3 ? my_s : 0)) * g.mask_plane + (size_t)(y0 + j0 + my_u + 1) * g.PWW + wi;
+    const bool lane_stores = (lane < 24) && (wi <= g.WW);
     for (int jb = 0; jb < T3_TH / 2; jb += 8) {
+        unsigned mine = 0;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int gy = y0 + j0 + jb + u;
             const int t = 2 * (int)pin[u * T3_COLS] + c2;         // 2 (g + C) - 1
-            const bool ok = col_ok && gy < g.H;
+            const bool ok = col_ok && (y0 + j0 + jb + u < g.H);
             const unsigned w0 = __ballot_sync(0xFFFFFFFFu, ok && (2 * V0 - t * K0 >= 0));
             const unsigned w1 = __ballot_sync(0xFFFFFFFFu, ok && (2 * V1 - t * K1 >= 0));
             const unsigned w2 = __ballot_sync(0xFFFFFFFFu, ok && (2 * V2 - t * K2 >= 0));
-            if (store && gy < g.H) { out0[(size_t)u * g.PWW] = w0; out1[(size_t)u * g.PWW] = w1; out2[(size_t)u * g.PWW] = w2; }
+            if (lane == u) mine = w0;
+            if (lane == 8 + u) mine = w1;
+            if (lane == 16 + u) mine = w2;
             // slide to the next row
             V0 += t3_hsum<R0>(e + (u + 1 + R0) * T3_EPITCH) - t3_hsum<R0>(e + (u - R0) * T3_EPITCH);
             V1 += t3_hsum<R1>(e + (u + 1 + R1) * T3_EPITCH) - t3_hsum<R1>(e + (u - R1) * T3_EPITCH);
             V2 += t3_hsum<R2>(e + (u + 1 + R2) * T3_EPITCH) - t3_hsum<R2>(e + (u - R2) * T3_EPITCH);
         }
+        if (lane_stores && y0 + j0 + jb + my_u < g.H) *outp = mine;
         e += 8 * T3_EPITCH; pin += 8 * T3_COLS;
-        out0 += (size_t)8 * g.PWW; out1 += (size_t)8 * g.PWW; out2 += (size_t)8 * g.PWW;
+        outp += (size_t)8 * g.PWW;
     }
 }
 

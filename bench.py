@@ -270,7 +270,7 @@ def main():
         kind = "reference" if use_cv2 else "port"
         sample = ("cv2 4.13 detectMarkers + per-marker solvePnP" if use_cv2 else "oracle/ C port") + \
                  ", %d steps x %d frames, %d worker processes x 1 thread" % (args.steps, B, cores)
-        print(json.dumps({"impl": "reference", "metric": "frames/sec detect+pose", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        print(json.dumps({"impl": "reference", "metric": "frames/sec detect+pose (1080p, DICT_6X6_250)" if args.workload == "C2" else "frames/sec detect+pose (%s)" % args.workload, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
