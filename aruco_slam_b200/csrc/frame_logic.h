@@ -346,28 +346,37 @@ B2A_HD void frame_finalize(Ctx &ctx, const FrameParams &fp, const FrameScratch &
     // valid / was flags live in gid / sel (free after grouping); chosen work item in gfill; after the
     // decision `was` is reused as the output slot: >= 0 accepted slot, <= -2 rejected slot -(slot + 2), -1 dropped
     int32_t *valid = fs.gid, *was = fs.sel, *chosen = fs.gfill;
+    // whether a candidate (or one of its close contours, first match) identifies is independent of the order:
+    // all threads; valid = 2 marks "would be valid", the single-lane loop below decides which of them are reached
+    for (int v = ctx.tid(); v < nS; v += ctx.nthreads()) {
+        int ok = 0, ch = v;
+        if (fs.wres[v] < 0) ok = 2;
+        else
+            for (int c = 0; c < fs.closeNum[v]; ++c)
+                if (fs.wres[fs.closeStart[v] + c] < 0) { ok = 2; ch = fs.closeStart[v] + c; break; }
+        valid[v] = ok; chosen[v] = ch; was[v] = 0;
+    }
+    ctx.sync();
     if (ctx.tid() == 0) {
         int maxDepth = 0;
-        for (int v = 0; v < nS; ++v) { valid[v] = 0; was[v] = 0; chosen[v] = v; if (fs.depth[v] > maxDepth) maxDepth = fs.depth[v]; }
+        for (int v = 0; v < nS; ++v) if (fs.depth[v] > maxDepth) maxDepth = fs.depth[v];
         int counter = 0;
         for (int depth = 0; counter < nS && depth <= maxDepth; ++depth) {
             for (int v = 0; v < nS; ++v) {
                 if (fs.depth[v] != depth) continue;
                 was[v] = 1;
-                if (fs.wres[v] < 0) valid[v] = 1;
-                else
-                    for (int c = 0; c < fs.closeNum[v]; ++c)
-                        if (fs.wres[fs.closeStart[v] + c] < 0) { valid[v] = 1; chosen[v] = fs.closeStart[v] + c; break; }
+                if (valid[v] == 2) valid[v] = 1;
             }
             for (int v = 0; v < nS; ++v) {
                 if (fs.depth[v] != depth) continue;
-                if (valid[v]) {
+                if (valid[v] == 1) {
                     int par = fs.parent[v];
                     while (par != -1) { if (!was[par]) { was[par] = 1; ++counter; } par = fs.parent[par]; }
                 }
                 ++counter;
             }
         }
+        for (int v = 0; v < nS; ++v) if (valid[v] != 1) valid[v] = 0;        // never reached (the counter ran out first)
         int na = 0, nr = 0, status = fs.counters[FC_STATUS];
         if (*fo.status != 0) status = *fo.status;               // overflow flagged by an earlier stage
         for (int v = 0; v < nS; ++v) {

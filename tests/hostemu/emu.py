@@ -121,3 +121,12 @@ def otsu(hist):
     a, b = C.c_int(), C.c_int()
     lib().emu_otsu(h.ctypes.data_as(C.c_void_p), int(h.sum()), C.byref(a), C.byref(b))
     return a.value, b.value
+
+
+def approx(contour, eps):
+    """product approxPolyDP(closed=True) on an (n,2) integer contour -> (m,2) vertices, or None when it gave up (> 8 vertices)"""
+    c = np.ascontiguousarray(contour, np.int32).reshape(-1, 2)
+    out = np.zeros((8, 2), np.int32)
+    lib().emu_approx.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+    m = lib().emu_approx(c.ctypes.data_as(C.c_void_p), len(c), float(eps), out.ctypes.data_as(C.c_void_p))
+    return None if m < 0 else out[:m].copy()

@@ -290,6 +290,18 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
     return st;
 }
 
+// approxPolyDP(closed) of the product (one lane) on an integer contour; returns the vertex count (-1: gave up, > 8 vertices)
+int emu_approx(const int32_t *xy, int n, double eps, int32_t *out_xy)
+{
+    std::vector<uint32_t> P(n);
+    for (int i = 0; i < n; ++i) P[i] = (uint32_t)xy[2 * i] | ((uint32_t)xy[2 * i + 1] << 16);
+    int ox[8], oy[8];
+    SingleLane lg;
+    const int m = approx_closed(lg, P.data(), n, eps, ox, oy);
+    for (int k = 0; k < m && k < 8; ++k) { out_xy[2 * k] = ox[k]; out_xy[2 * k + 1] = oy[k]; }
+    return m;
+}
+
 // restated Otsu vs the textbook loop on one histogram
 void emu_otsu(const int *h, int n, int *thr_new, int *thr_seq)
 {

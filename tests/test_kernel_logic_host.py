@@ -124,3 +124,36 @@ def test_otsu_restatement_matches_textbook_loop():
     for h in cases:
         new, seq = emu.otsu(h)
         assert new == seq, (new, seq, np.nonzero(h)[0][:8])
+
+
+def test_approx_closed_vs_oracle_on_many_contours(oracle):
+    """the product's approxPolyDP(closed) (32-bit proxies, two trackers, first-maximum rule) against the oracle's
+    restatement of OpenCV 4.13 on every contour of noisy / blobby masks, at the detector's epsilon and a finer one"""
+    rng = np.random.default_rng(21)
+    masks = []
+    for p in (0.35, 0.55, 0.7):
+        masks.append(((rng.random((120, 160)) < p) * 255).astype(np.uint8))
+    yy, xx = np.mgrid[0:200, 0:260]
+    blob = np.zeros((200, 260), np.uint8)
+    for _ in range(25):                                 # overlapping rotated rectangles and discs: long borders with straight runs
+        cx, cy, a, b, th = rng.uniform(20, 240), rng.uniform(20, 180), rng.uniform(5, 45), rng.uniform(5, 45), rng.uniform(0, 3.14)
+        u = (xx - cx) * np.cos(th) + (yy - cy) * np.sin(th); v = -(xx - cx) * np.sin(th) + (yy - cy) * np.cos(th)
+        blob |= ((np.abs(u) < a) & (np.abs(v) < b)).astype(np.uint8) * 255 if rng.random() < 0.7 else ((u * u + v * v) < a * a).astype(np.uint8) * 255
+    masks.append(blob)
+    checked = quads = 0
+    for m in masks:
+        for c in oracle.find_contours(m):
+            n = len(c)
+            if n < 8:
+                continue
+            for rate in (0.03, 0.01):
+                want = oracle.approx_poly_dp(c, n * rate)
+                got = emu.approx(c, n * rate)
+                if got is None:                         # the product stops once more than 8 vertices are certain
+                    assert len(want) > 4
+                else:
+                    if len(want) <= 4 or len(got) <= 4:
+                        assert np.array_equal(got, want), (n, rate)
+                    quads += len(want) == 4
+                checked += 1
+    assert checked > 300 and quads > 10
