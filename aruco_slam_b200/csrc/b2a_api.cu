@@ -476,7 +476,7 @@ static DetGeom make_geom(const b2a_detector *d, int W, int H, int B)
     g.minPerim = (int)(unsigned)(d->prm.minMarkerPerimeterRate * g.maxWH);
     g.maxPerim = (int)(unsigned)(d->prm.maxMarkerPerimeterRate * g.maxWH);
     g.approxRate = d->prm.polygonalApproxAccuracyRate; g.minCornerDistRate = d->prm.minCornerDistanceRate;
-    g.surv_cap = d->surv_cap; g.pts_cap = d->pts_cap;
+    g.surv_cap = d->surv_cap; g.pts_cap = d->pts_cap; g.count_all = 0;
     return g;
 }
 
@@ -519,6 +519,7 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     } else { s.gray = src; s.pitch = src_pitch; s.frame_stride = src_frame; }
     s.g = make_geom(d, W, H, nb);
     DetGeom &g = s.g;
+    g.count_all = walk_max_len > 0 ? 1 : 0;          // the contour tap (exact counts, no give-up length) is the only caller that asks
     // this sub-batch's slice of the anchor arrays, and its per-(frame,scale) arrays addressed from frame b0
     const size_t fs0 = (size_t)b0 * g.nScales, FS = (size_t)nb * g.nScales;
     const unsigned slice = d->anchors_cap / (unsigned)d->n_sub_max;

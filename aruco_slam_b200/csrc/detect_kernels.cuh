@@ -38,6 +38,7 @@ struct DetGeom {
     int minPerim, maxPerim, maxWH;
     double approxRate, minCornerDistRate;
     int surv_cap, pts_cap;
+    int count_all;                  // debug tap only: count every border (also the ones the perimeter gate drops) and the one-pixel regions
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -375,7 +376,7 @@ __device__ __forceinline__ void anchors_of_word(AnchorBlock &sb, const uint32_t 
         const uint32_t d = __ldg(row + g.PWW), dl = __ldg(row + g.PWW - 1), dr = __ldg(row + g.PWW + 1);
         uint32_t iso;
         anchor_words(m, ml, mr, u, ul, ur, d, dl, dr, !(y & Rm), grid_cols(wx, Rm), !(y & Rm2), grid_cols(wx, Rm2), A, SU, U, hi, iso);
-        if (iso) atomicAdd(&iso_count[fs], __popc(iso));
+        if (iso && g.count_all) atomicAdd(&iso_count[fs], __popc(iso));       // one hot address per mask: never in the product call
     }
     // anchors: pixel by pixel, canonical directions E, N, W, S inside a pixel
     const int cnt = __popc(A[0]) + __popc(A[1]) + __popc(A[2]) + __popc(A[3]);
@@ -522,7 +523,7 @@ k_skip(BorderGraph bg, int max_len)
 __device__ __forceinline__ void report_border(uint4 *__restrict__ surv, int *__restrict__ surv_count, int *__restrict__ contour_count,
                                               int fs, uint32_t key, uint32_t len, uint32_t who, uint32_t kind, const DetGeom &g)
 {
-    atomicAdd(&contour_count[fs], 1);
+    if (g.count_all) atomicAdd(&contour_count[fs], 1);                          // one hot address per mask: never in the product call
     if ((int)len >= g.minPerim && (int)len <= g.maxPerim) {
         const int slot = atomicAdd(&surv_count[fs], 1);
         if (slot < g.surv_cap) surv[(size_t)fs * g.surv_cap + slot] = make_uint4(key, len, who, kind);

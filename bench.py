@@ -33,8 +33,16 @@ sys.path.insert(0, ROOT)
 
 from aruco_slam_b200 import synth, dictionaries as D  # noqa: E402
 
-K_CAM = np.array([[1400.0, 0, 960], [0, 1400.0, 540], [0, 0, 1]])
 D_CAM = np.array([0.05, -0.1, 0.001, -0.002, 0.02])
+
+
+def camera_matrix(W, H):
+    """pinhole with a ~70 degree horizontal field of view centred on the frame (the distortion model is only sane inside it)"""
+    f = 1400.0 * W / 1920.0
+    return np.array([[f, 0, W / 2.0], [0, f, H / 2.0], [0, 0, 1]])
+
+
+K_CAM = camera_matrix(1920, 1080)          # replaced per workload in main()
 MARKER_LENGTH = 0.27                    # reference parameters.yaml:17
 # C5 (BASELINE.json config 5): EKF correction only, 500 landmarks = 1503-dimensional state (the reference's state is
 # 3 + 3 n, include/aruco_slam/aruco_slam.h:182; the "1003" of BASELINE.json would be 2-D landmarks), 30 observations of
@@ -243,6 +251,8 @@ def main():
     desc, dict_id = WORKLOADS[args.workload]
     cfg = synth.CONFIGS[args.workload]
     W, H, B = cfg["W"], cfg["H"], args.batch
+    global K_CAM
+    K_CAM = camera_matrix(W, H)
     config = {"workload": "%s: %s, batch %d per GPU, detect+pose" % (args.workload, desc, B), "batch_per_gpu": B,
               "l2": "L2 flushed (256 MiB write) between timed steps", "parallelism": "frame shards, %d GPU(s), no collective" % world}
 
