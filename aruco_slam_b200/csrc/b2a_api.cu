@@ -424,6 +424,7 @@ struct Sub {
     int b0, nb;              // first frame, number of frames
     cudaStream_t st;
     bool timed;              // stage events are recorded for sub-batch 0 only
+    cudaEvent_t tl_after_h2d = nullptr;   // debug timeline
     DetGeom g;               // geometry with B = nb
     const uint8_t *gray; size_t pitch, frame_stride;      // gray frames of this sub-batch
 };
@@ -506,10 +507,12 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     if (!f->on_device) {
         const size_t rowbytes = (size_t)W * f->channels;
         uint8_t *dst = d->d_in + (size_t)b0 * rowbytes * H;
-        if (in_frame == in_pitch * H) CU(cudaMemcpy2DAsync(dst, rowbytes, src, in_pitch, rowbytes, (size_t)H * nb, cudaMemcpyHostToDevice, st));
+        if (in_frame == in_pitch * H && in_pitch == rowbytes) CU(cudaMemcpyAsync(dst, src, rowbytes * H * nb, cudaMemcpyHostToDevice, st));      // contiguous frames: one linear copy
+        else if (in_frame == in_pitch * H) CU(cudaMemcpy2DAsync(dst, rowbytes, src, in_pitch, rowbytes, (size_t)H * nb, cudaMemcpyHostToDevice, st));
         else for (int b = 0; b < nb; ++b) CU(cudaMemcpy2DAsync(dst + (size_t)b * rowbytes * H, rowbytes, src + (size_t)b * in_frame, in_pitch, rowbytes, H, cudaMemcpyHostToDevice, st));
         src = dst; src_pitch = rowbytes; src_frame = rowbytes * H;
     }
+    if (s.tl_after_h2d) cudaEventRecord(s.tl_after_h2d, st);
     stage_mark(d, s, ST_GRAY);
     if (f->channels == 3) {
         uint8_t *gdst = d->d_gray + (size_t)b0 * d->gray_pitch * H;
@@ -757,12 +760,30 @@ static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *
     }
     CU(cudaEventRecord(d->ev_fork, s0));
     for (int i = 1; i < nsub; ++i) CU(cudaStreamWaitEvent(subs[i].st, d->ev_fork, 0));
+    // B2A_TIMELINE=1: per sub-batch, when its frames were in HBM and when its results were out (ms after the call began)
+    static const bool timeline = std::getenv("B2A_TIMELINE") != nullptr;
+    static cudaEvent_t tl_ev[1 + 2 * b2a_detector::MAX_SUB] = {};
+    if (timeline) {
+        if (!tl_ev[0]) for (auto &e : tl_ev) cudaEventCreate(&e);
+        cudaEventRecord(tl_ev[0], s0);
+    }
     for (int i = 0; i < nsub; ++i) {
+        subs[i].tl_after_h2d = timeline ? tl_ev[1 + 2 * i] : nullptr;
         TRY(run_front(d, f, subs[i], walk_max_len));
         if (mode != 1) TRY(run_back(d, subs[i], cam, mode == 2));
+        if (timeline) cudaEventRecord(tl_ev[2 + 2 * i], subs[i].st);
     }
     for (int i = 1; i < nsub; ++i) { CU(cudaEventRecord(d->ev_join[i], subs[i].st)); CU(cudaStreamWaitEvent(s0, d->ev_join[i], 0)); }
     CU(cudaStreamSynchronize(s0));
+    if (timeline && mode == 0) {
+        std::fprintf(stderr, "timeline (ms): ");
+        for (int i = 0; i < nsub; ++i) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, tl_ev[0], tl_ev[1 + 2 * i]); cudaEventElapsedTime(&b, tl_ev[0], tl_ev[2 + 2 * i]);
+            std::fprintf(stderr, "[%d frames: in %.3f out %.3f] ", subs[i].nb, a, b);
+        }
+        std::fprintf(stderr, "\n");
+    }
     if (mode == 0) {
         int prev = -1;
         for (int i = 0; i < ST_COUNT; ++i) d->stage_ms[i] = 0.f;
