@@ -932,7 +932,10 @@ struct b2a_slam {
     int device = 0;
     cudaStream_t stream = nullptr;
     int N = 3, LD = 0, cap_lm = 0;
+    double *d_sigma2 = nullptr;                      // ping-pong partner of d_sigma (cooperative kernel)
     double *d_mu = nullptr, *d_mus = nullptr, *d_sigma = nullptr, *d_K = nullptr, *d_GS = nullptr, *d_scratch = nullptr;
+    EkfObs *d_obs = nullptr; int obs_cap = 0;       // known-landmark corrections of one frame (cooperative kernel)
+    int coop_grid = 0;                               // co-resident CTAs of k_ekf_frame (0 = use the per-observation kernels)
     std::vector<int32_t> ids;                       // landmark k -> aruco id (aruco_id_map, aruco_slam.h:164)
     std::vector<int32_t> last_ids; std::vector<double> last_obs;   // last_observed_marker_ (NaN = unset)
     bool is_init = false;
@@ -952,6 +955,7 @@ extern "C" void b2a_slam_destroy(b2a_slam *s)
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_obs); cudaFree(s->d_sigma2);
     cudaFree(s->d_mu); cudaFree(s->d_mus); cudaFree(s->d_sigma); cudaFree(s->d_K); cudaFree(s->d_GS); cudaFree(s->d_scratch);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -975,6 +979,18 @@ extern "C" int b2a_slam_create(int device, const b2a_slam_params *p, b2a_slam **
     if (cudaMalloc(&s->d_mu, LD * 8) || cudaMalloc(&s->d_mus, LD * 8) || cudaMalloc(&s->d_sigma, LD * LD * 8) ||
         cudaMalloc(&s->d_K, LD * 3 * 8) || cudaMalloc(&s->d_GS, LD * 3 * 8) || cudaMalloc(&s->d_scratch, LD * 6 * 8))
         return fail("cudaMalloc (EKF state)");
+    {   // one cooperative launch per frame needs all CTAs resident at once
+        int coop = 0, per_sm = 0, sms = 0;
+        const size_t smem = 3 * LD * sizeof(double);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (coop && cudaFuncSetAttribute(k_ekf_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ekf_frame, 512, smem) == cudaSuccess && per_sm > 0 && !std::getenv("B2A_EKF_PER_OBS"))
+            s->coop_grid = sms * std::min(per_sm, 2);
+        if (s->coop_grid > 0 && cudaMalloc(&s->d_sigma2, LD * LD * 8) != cudaSuccess) { s->coop_grid = 0; s->d_sigma2 = nullptr; }
+        if (s->d_sigma2) cudaMemsetAsync(s->d_sigma2, 0, LD * LD * 8, s->stream);
+        (void)cudaGetLastError();
+    }
     cudaMemsetAsync(s->d_mu, 0, LD * 8, s->stream);
     cudaMemsetAsync(s->d_sigma, 0, LD * LD * 8, s->stream);
     if (cudaStreamSynchronize(s->stream) != cudaSuccess) return fail("memset");
@@ -1087,6 +1103,31 @@ extern "C" int b2a_slam_update(b2a_slam *s, const b2a_observation *obs, int n)
     CU(cudaMemcpyAsync(s->d_mus, s->d_mu, (size_t)s->N * 8, cudaMemcpyDeviceToDevice, st));      // mu snapshot (:88)
     std::vector<int32_t> new_last_ids(n);
     std::vector<double> new_last_obs((size_t)n * 3, NAN);
+    std::vector<EkfObs> batch;                                         // consecutive known-landmark corrections
+    auto flush = [&]() -> int {
+        if (batch.empty()) return B2A_OK;
+        const int N = s->N, nb = (int)batch.size();
+        if (s->coop_grid > 0 && (N + s->coop_grid - 1) / s->coop_grid <= 64) {
+            if (nb > s->obs_cap) { cudaFree(s->d_obs); s->obs_cap = std::max(nb, 64); CU(cudaMalloc(&s->d_obs, (size_t)s->obs_cap * sizeof(EkfObs))); }
+            // the batch vector lives until the copy has been consumed: the stream is synchronised below before it goes away
+            CU(cudaMemcpyAsync(s->d_obs, batch.data(), (size_t)nb * sizeof(EkfObs), cudaMemcpyHostToDevice, st));
+            int LD = s->LD, n_obs = nb;
+            const EkfObs *obs_p = s->d_obs;
+            int N_ = N;
+            void *args[] = {&s->d_sigma, &s->d_sigma2, &s->d_mu, &s->d_mus, &N_, &LD, &obs_p, &n_obs};
+            CU(cudaLaunchCooperativeKernel((void *)k_ekf_frame, dim3(s->coop_grid), dim3(512), args, 3 * (size_t)s->LD * sizeof(double), st));
+            CU(cudaStreamSynchronize(st));
+            if (nb & 1) std::swap(s->d_sigma, s->d_sigma2);             // an odd number of ping-pongs ends in the other buffer
+        } else {
+            for (const EkfObs &eo : batch) {
+                k_ekf_gain<<<(N + 255) / 256, 256, 0, st>>>(s->d_sigma, s->d_mus, N, s->LD, eo, s->d_K, s->d_GS);
+                dim3 grid((N + 2 * EK_TX - 1) / (2 * EK_TX), (N + EK_ROWS - 1) / EK_ROWS);
+                k_ekf_rank3<<<grid, dim3(EK_TX, EK_TY), 0, st>>>(s->d_sigma, s->d_mu, s->d_mus, N, s->LD, eo, s->d_K, s->d_GS);
+            }
+        }
+        batch.clear();
+        return B2A_OK;
+    };
     for (int qi = 0; qi < n; ++qi) {
         const b2a_observation &o = obs[q[qi].seq];
         EkfObs eo;
@@ -1103,18 +1144,17 @@ extern "C" int b2a_slam_update(b2a_slam *s, const b2a_observation *obs, int n)
                 }
             if (!stationary) {
                 new_last_obs[3 * qi] = o.x; new_last_obs[3 * qi + 1] = o.y; new_last_obs[3 * qi + 2] = o.theta;
-                const int N = s->N;
-                k_ekf_gain<<<(N + 255) / 256, 256, 0, st>>>(s->d_sigma, s->d_mus, N, s->LD, eo, s->d_K, s->d_GS);
-                dim3 grid((N + 2 * EK_TX - 1) / (2 * EK_TX), (N + EK_ROWS - 1) / EK_ROWS);
-                k_ekf_rank3<<<grid, dim3(EK_TX, EK_TY), 0, st>>>(s->d_sigma, s->d_mu, s->d_mus, N, s->LD, eo, s->d_K, s->d_GS);
+                batch.push_back(eo);
             }
         } else {
+            TRY(flush());
             k_ekf_augment<<<1, 256, 0, st>>>(s->d_sigma, s->d_mu, s->d_mus, s->N, s->LD, eo);
             s->N += 3;
             s->ids.push_back(o.aruco_id);                              // :256
         }
         new_last_ids[qi] = o.aruco_id;
     }
+    TRY(flush());
     s->last_ids.swap(new_last_ids); s->last_obs.swap(new_last_obs);    // :263
     return launch_err("EKF kernels");
 }

@@ -11,6 +11,7 @@
 // Sigma is row-major with leading dimension LD (capacity), mu has LD entries.
 #pragma once
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 #include "pose_core.h"
 
@@ -126,6 +127,101 @@ k_ekf_rank3(double *__restrict__ sigma, double *__restrict__ mu, const double *_
         v.x -= k0 * g0a + k1 * g1a + k2 * g2a;
         if (two) v.y -= k0 * g0b + k1 * g1b + k2 * g2b;
         *p = v;
+    }
+}
+
+// All known-landmark corrections of one frame in ONE cooperative launch (the per-observation launches of
+// k_ekf_gain + k_ekf_rank3 spend as long in launch gaps as in the 16 N^2-byte streaming pass).  Every CTA owns a
+// block of rows of Sigma.  Per observation:
+//   phase A  every CTA forms GS = Gx Sigma (3 x N, needs six *old* rows of Sigma) in shared memory and the gain rows
+//            K[i] of its own rows;                                   -- grid barrier (nobody may still read old rows)
+//   phase B  mu[i] += K[i] ze and Sigma[i][:] -= K[i] GS for its own rows (the streaming pass);   -- grid barrier
+// Same expressions, in the same order, as k_ekf_gain / k_ekf_rank3.  Sigma ping-pongs between two buffers (observation o
+// reads buffer o % 2 and writes the other), so nobody overwrites rows that another CTA still reads and one grid barrier
+// per observation is enough.
+__global__ void __launch_bounds__(512)
+k_ekf_frame(double *__restrict__ sigma_a, double *__restrict__ sigma_b, double *__restrict__ mu, const double *__restrict__ mu_s, int N, int LD,
+            const EkfObs *__restrict__ obs, int n_obs)
+{
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    extern __shared__ double s_gs[];                 // [3][LD]  GS of the current observation
+    __shared__ double s_G[18], s_Si[9], s_ze[3], s_blk[36];
+    __shared__ double s_K[64][3];                    // gain rows of this CTA's rows (rows_per_cta <= 64)
+    const int rows_per_cta = (N + gridDim.x - 1) / gridDim.x;
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+    for (int o = 0; o < n_obs; ++o) {
+        const EkfObs ob = obs[o];
+        const int L = 3 + 3 * ob.index;
+        const int cols[6] = {0, 1, 2, L, L + 1, L + 2};
+        const double *__restrict__ sigma = (o & 1) ? sigma_b : sigma_a;        // read
+        double *__restrict__ sigma_out = (o & 1) ? sigma_a : sigma_b;          // written
+        if (threadIdx.x < 36) s_blk[threadIdx.x] = sigma[(size_t)cols[threadIdx.x / 6] * LD + cols[threadIdx.x % 6]];      // the 6 x 6 block, loads in parallel
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double G[18], ze[3];
+            ekf_linearise(mu_s, ob, G, ze);
+            double SGc[18];                          // (Sigma Gx^T)[cols[j]][r]
+            for (int j = 0; j < 6; ++j) for (int r = 0; r < 3; ++r) {
+                double a = 0;
+                for (int k = 0; k < 6; ++k) a += s_blk[6 * j + k] * G[6 * r + k];
+                SGc[3 * j + r] = a;
+            }
+            double S[9];
+            for (int r = 0; r < 3; ++r) for (int c2 = 0; c2 < 3; ++c2) {
+                double a = 0;
+                for (int j = 0; j < 6; ++j) a += G[6 * r + j] * SGc[3 * j + c2];
+                S[3 * r + c2] = a + ob.Rk[3 * r + c2];
+            }
+            inv3x3(S, s_Si);
+            for (int i = 0; i < 18; ++i) s_G[i] = G[i];
+            for (int i = 0; i < 3; ++i) s_ze[i] = ze[i];
+        }
+        __syncthreads();
+        // phase A: GS for every column (each CTA its own copy), K for the CTA's rows
+        for (int j = threadIdx.x; j < N; j += blockDim.x) {
+            double gs[3] = {0, 0, 0};
+            for (int k = 0; k < 6; ++k) {
+                const double row = sigma[(size_t)cols[k] * LD + j];
+                for (int r = 0; r < 3; ++r) gs[r] += s_G[6 * r + k] * row;
+            }
+            s_gs[j] = gs[0]; s_gs[LD + j] = gs[1]; s_gs[2 * LD + j] = gs[2];
+        }
+        for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+            double sg[3] = {0, 0, 0};
+            for (int k = 0; k < 6; ++k) {
+                const double col = sigma[(size_t)i * LD + cols[k]];
+                for (int r = 0; r < 3; ++r) sg[r] += col * s_G[6 * r + k];
+            }
+            for (int c2 = 0; c2 < 3; ++c2) s_K[i - r0][c2] = sg[0] * s_Si[c2] + sg[1] * s_Si[3 + c2] + sg[2] * s_Si[6 + c2];
+        }
+        __syncthreads();
+        // phase B: the streaming pass over the CTA's rows
+        for (int i = r0 + (threadIdx.x >> 7); i < r1; i += (blockDim.x >> 7)) {      // 128 threads per row, two columns each per step
+            const double k0 = s_K[i - r0][0], k1 = s_K[i - r0][1], k2 = s_K[i - r0][2];
+            if ((threadIdx.x & 127) == 0) mu[i] += k0 * s_ze[0] + k1 * s_ze[1] + k2 * s_ze[2];
+            const double *row = sigma + (size_t)i * LD;
+            double *row_out = sigma_out + (size_t)i * LD;
+            // up to 8 column pairs per thread (N <= 2048): all loads first, then the updates
+            double2 v[8];
+            const int j0 = 2 * (threadIdx.x & 127);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int j = j0 + 256 * u; if (j < N) v[u] = *reinterpret_cast<const double2 *>(row + j); }     // LD even, j even: 16-byte aligned
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + 256 * u;
+                if (j >= N) break;
+                v[u].x -= k0 * s_gs[j] + k1 * s_gs[LD + j] + k2 * s_gs[2 * LD + j];
+                if (j + 1 < N) v[u].y -= k0 * s_gs[j + 1] + k1 * s_gs[LD + j + 1] + k2 * s_gs[2 * LD + j + 1];
+                *reinterpret_cast<double2 *>(row_out + j) = v[u];
+            }
+            for (int j = j0 + 2048; j < N; j += 256) {                                 // larger states: the plain loop
+                double2 w = *reinterpret_cast<const double2 *>(row + j);
+                w.x -= k0 * s_gs[j] + k1 * s_gs[LD + j] + k2 * s_gs[2 * LD + j];
+                if (j + 1 < N) w.y -= k0 * s_gs[j + 1] + k1 * s_gs[LD + j + 1] + k2 * s_gs[2 * LD + j + 1];
+                *reinterpret_cast<double2 *>(row_out + j) = w;
+            }
+        }
+        grid.sync();
     }
 }
 
