@@ -194,6 +194,7 @@ struct b2a_detector {
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
     int n_sub_max = MAX_SUB, n_streams = 4;
     int nScales = 0, radius[MAX_SCALES];
+    bool thresh_tiles = false;
     int max_cand = 0, max_markers = 0, surv_cap = 0;
     size_t gray_pitch = 0;
     // device memory
@@ -284,7 +285,7 @@ static int create_impl(b2a_detector *d)
     const int B = c.max_batch, W = c.max_width, H = c.max_height, nS = d->nScales;
     const size_t P = (size_t)W * H;
     d->gray_pitch = ((size_t)W + 15) & ~(size_t)15;
-    TRY(dev_alloc(d, &d->d_in, (size_t)B * P * 3));
+    TRY(dev_alloc(d, &d->d_in, (size_t)B * std::max(P * 3, (((size_t)W + 3) & ~(size_t)3) * H)));
     TRY(dev_alloc(d, &d->d_gray, (size_t)B * d->gray_pitch * H));
     const int WW = (W + 31) / 32, PWW = WW + 2;
     d->masks_words = (size_t)B * nS * PWW * (H + 2);
@@ -353,6 +354,8 @@ static int create_impl(b2a_detector *d)
     CU(cudaFuncSetAttribute(k_group_a, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (d->max_cand + 1) * (int)sizeof(uint32_t)));
     CU(cudaFuncSetAttribute(k_identify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)identify_smem_bytes(ID_MAX_S)));
     CU(cudaFuncSetAttribute(k_threshold3<1, 6, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3_SMEM));
+    CU(cudaFuncSetAttribute(k_threshold_march<1, 6, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM));
+    d->thresh_tiles = std::getenv("B2A_THRESH_TILES") != nullptr;          // A/B switch: the tiled kernel (k_threshold3) instead of the marching one
     CU(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (int)sizeof(int32_t) * d->max_cand));
     CU(cudaStreamSynchronize(d->stream));
     return B2A_OK;
@@ -506,11 +509,12 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     size_t src_pitch = in_pitch, src_frame = in_frame;
     if (!f->on_device) {
         const size_t rowbytes = (size_t)W * f->channels;
-        uint8_t *dst = d->d_in + (size_t)b0 * rowbytes * H;
-        if (in_frame == in_pitch * H && in_pitch == rowbytes) CU(cudaMemcpyAsync(dst, src, rowbytes * H * nb, cudaMemcpyHostToDevice, st));      // contiguous frames: one linear copy
-        else if (in_frame == in_pitch * H) CU(cudaMemcpy2DAsync(dst, rowbytes, src, in_pitch, rowbytes, (size_t)H * nb, cudaMemcpyHostToDevice, st));
-        else for (int b = 0; b < nb; ++b) CU(cudaMemcpy2DAsync(dst + (size_t)b * rowbytes * H, rowbytes, src + (size_t)b * in_frame, in_pitch, rowbytes, H, cudaMemcpyHostToDevice, st));
-        src = dst; src_pitch = rowbytes; src_frame = rowbytes * H;
+        const size_t dpitch = f->channels == 1 ? ((rowbytes + 3) & ~(size_t)3) : rowbytes;        // gray rows land 4-byte aligned (the marching threshold kernel loads words)
+        uint8_t *dst = d->d_in + (size_t)b0 * dpitch * H;
+        if (in_frame == in_pitch * H && in_pitch == rowbytes && dpitch == rowbytes) CU(cudaMemcpyAsync(dst, src, rowbytes * H * nb, cudaMemcpyHostToDevice, st));      // contiguous frames: one linear copy
+        else if (in_frame == in_pitch * H) CU(cudaMemcpy2DAsync(dst, dpitch, src, in_pitch, rowbytes, (size_t)H * nb, cudaMemcpyHostToDevice, st));
+        else for (int b = 0; b < nb; ++b) CU(cudaMemcpy2DAsync(dst + (size_t)b * dpitch * H, dpitch, src + (size_t)b * in_frame, in_pitch, rowbytes, H, cudaMemcpyHostToDevice, st));
+        src = dst; src_pitch = dpitch; src_frame = dpitch * H;
     }
     if (s.tl_after_h2d) cudaEventRecord(s.tl_after_h2d, st);
     stage_mark(d, s, ST_GRAY);
@@ -540,7 +544,17 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     stage_mark(d, s, ST_THRESH);
     {
         const bool default_windows = g.nScales == 3 && g.radius[0] == 1 && g.radius[1] == 6 && g.radius[2] == 11 && std::abs(g.Cfloor) <= 2048;
-        if (default_windows) {
+        const bool aligned4 = (s.pitch & 3) == 0 && (s.frame_stride & 3) == 0 && (((size_t)s.gray) & 3) == 0 && s.pitch < (1ull << 32);
+        if (default_windows && aligned4 && !d->thresh_tiles) {
+            // marching kernel: work items = (frame, 320-column strip, Hs-row segment); Hs is the tallest segment that still gives every
+            // resident CTA slot an item (a segment costs 22 rows of prefix warm-up)
+            const int n_sx = (W + TM_WT - 1) / TM_WT, slots = d->num_sms * 3;
+            int Hs = TM_RC;
+            for (int h = 5 * TM_RC; h >= TM_RC; h -= TM_RC)
+                if (nb * n_sx * ((H + h - 1) / h) >= slots) { Hs = h; break; }
+            const int n_sy = (H + Hs - 1) / Hs, n_items = nb * n_sx * n_sy;
+            k_threshold_march<1, 6, 11><<<std::min(n_items, slots), TM_THREADS, TM_SMEM, st>>>(s.gray, (uint32_t)s.pitch, s.frame_stride, masks, g, Hs, n_sy, n_sx, n_items);
+        } else if (default_windows) {
             dim3 grid((W + T3_TW - 1) / T3_TW, (H + T3_TH - 1) / T3_TH, nb);
             k_threshold3<1, 6, 11><<<grid, T3_THREADS, T3_SMEM, st>>>(s.gray, s.pitch, s.frame_stride, masks, g);
         } else {

@@ -271,6 +271,243 @@ k_threshold3(const uint8_t *__restrict__ gray, size_t pitch, size_t frame_stride
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// A2, marching form for three windows (radii <= 11): the instruction count per pixel, not the memory system,
+// bounds this stage, so the kernel is organised around the fewest instructions per pixel (~20 instead of ~50):
+//   work item  = a strip of TM_WT output columns x Hs rows of one frame; a CTA marches down it TM_RC rows at a time.
+//   V phase    thread t owns 4 neighbouring columns (one 32-bit load per row, straight from global memory) and keeps
+//              the running column prefix C (two registers of packed u16 pairs: even / odd bytes) of the last 24 rows
+//              in a register ring: every vertical window sum is ONE packed subtraction  V_r[m] = C[m+r] - C[m-r-1]
+//              (no borrow between the lanes: C is monotone and < 2^16 for Hs + 22 <= 257 rows).  The three V planes
+//              of the chunk go to shared memory as u16; the raw row goes to a small ring for the centre pixel.
+//   H phase    thread (row, 64-column segment) slides the three box sums along its row: dp2a adds the entering and
+//              subtracts the leaving u16 element (extract + accumulate in one instruction), every 16-byte piece of a
+//              plane row is loaded once and kept in registers while a window still needs it; the test
+//              S - k^2 g - c_k >= 0 (c_k = k^2 C - (k^2 - 1) / 2, exact integers, same as 2 S >= (2 (g + C) - 1) k^2)
+//              is one IMAD, and its sign bit enters the mask word through one funnel shift.
+// ---------------------------------------------------------------------------------------------
+constexpr int TM_WT = 320;                            // output columns of a strip (10 mask words)
+constexpr int TM_HALO = 12;                           // >= largest radius + 1, multiple of 4
+constexpr int TM_VCOLS = TM_WT + 2 * TM_HALO;         // 344 columns of V per strip row
+constexpr int TM_VG = TM_VCOLS / 4;                   // 86 four-column groups = V-phase threads
+constexpr int TM_RC = 24;                             // rows per chunk = length of the prefix ring
+constexpr int TM_SEG = 64;                            // output columns of one H-phase thread
+constexpr int TM_NSEG = TM_WT / TM_SEG;               // 5
+constexpr int TM_THREADS = 128;
+constexpr int TM_VPITCH = TM_VG * 8;                  // 688 bytes per plane row: 43 x 16 (odd => 16-byte loads of 8 rows hit 8 bank groups)
+constexpr int TM_GROWS = 48;                          // raw-row ring of the centre pixels: two chunks, so every slot is a compile-time offset
+constexpr int TM_GPITCH = TM_WT + 16;                 // 336 = 21 x 16
+constexpr int TM_MAX_HS = 216;                        // (Hs + 22) * 255 < 2^16
+constexpr size_t TM_SMEM = (size_t)3 * TM_RC * TM_VPITCH + (size_t)TM_GROWS * TM_GPITCH + (size_t)TM_RC * TM_VG * 4;
+static_assert((TM_VPITCH / 16) % 2 == 1 && (TM_GPITCH / 16) % 2 == 1 && TM_VPITCH % 16 == 0, "bank mapping");
+static_assert(TM_RC * TM_NSEG <= TM_THREADS && TM_VG <= TM_THREADS, "thread roles");
+
+__device__ __forceinline__ int tm_dp2a(uint32_t a, int sel, int c)      // c + s16(a.lo) * s8(sel.b0) + s16(a.hi) * s8(sel.b1)
+{
+    int d;
+    asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(sel), "r"(c));
+    return d;
+}
+// element e (0..7) of a 16-byte piece = two groups of four columns stored as (c0 | c2 << 16), (c1 | c3 << 16)
+__device__ __forceinline__ uint32_t tm_word(const uint4 &c, int e)
+{
+    const int wi = 2 * (e >> 2) + (e & 1);
+    return wi == 0 ? c.x : wi == 1 ? c.y : wi == 2 ? c.z : c.w;
+}
+__device__ __forceinline__ int tm_half(int e) { return (e >> 1) & 1; }
+
+// the box sums of one window along a row segment: pieces ch[] of the plane row are loaded on demand by the caller
+template <int R>
+struct TmWin {
+    static constexpr int K2 = (2 * R + 1) * (2 * R + 1);
+    static constexpr int first_piece = (TM_HALO - R) / 8;
+    static constexpr int __host__ __device__ newest_piece(int blk) { return (8 * blk + 8 + TM_HALO + R) / 8; }     // piece of the last entering element of block blk
+    uint4 ch[12];
+    int S;
+    __device__ __forceinline__ void load(const uint8_t *row, int from, int to)
+    {
+#pragma unroll
+        for (int c = 0; c < 12; ++c)
+            if (c >= from && c <= to) ch[c] = *reinterpret_cast<const uint4 *>(row + 16 * c);
+    }
+    __device__ __forceinline__ void init(int bias)                 // S at segment column 0: columns 12 - R .. 12 + R of the row
+    {
+        S = bias;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int wi = 0; wi < 4; ++wi) {
+                const int qa = 8 * c + 4 * (wi >> 1) + (wi & 1), qb = qa + 2;
+                const int sel = ((qa >= TM_HALO - R && qa <= TM_HALO + R) ? 1 : 0) | ((qb >= TM_HALO - R && qb <= TM_HALO + R) ? 0x100 : 0);
+                if (sel) S = tm_dp2a(wi == 0 ? ch[c].x : wi == 1 ? ch[c].y : wi == 2 ? ch[c].z : ch[c].w, sel, S);
+            }
+    }
+    __device__ __forceinline__ void slide(int i)                   // S(i) -> S(i + 1)
+    {
+        const int qn = i + TM_HALO + 1 + R, qo = i + TM_HALO - R;
+        S = tm_dp2a(tm_word(ch[qn >> 3], qn & 7), tm_half(qn & 7) ? 0x0100 : 0x0001, S);
+        S = tm_dp2a(tm_word(ch[qo >> 3], qo & 7), tm_half(qo & 7) ? 0xFF00 : 0x00FF, S);
+    }
+};
+
+// one 4-byte asynchronous copy global -> shared (LDGSTS): the V phase prefetches the next chunk's rows with it
+__device__ __forceinline__ void tm_cp_async4(uint32_t dst_shared, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst_shared), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tm_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tm_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// requires pitch, frame_stride and the base pointer to be multiples of 4 (the host checks and falls back to k_threshold3)
+template <int R0, int R1, int R2>
+__global__ void __launch_bounds__(TM_THREADS, 3)
+k_threshold_march(const uint8_t *__restrict__ gray, uint32_t pitch, size_t frame_stride, uint32_t *__restrict__ masks, DetGeom g,
+                  int Hs, int n_sy, int n_sx, int n_items)
+{
+    static_assert(R0 <= 11 && R1 <= 11 && R2 <= 11 && R0 >= 1 && R1 >= 1 && R2 >= 1, "radii");
+    extern __shared__ __align__(16) uint8_t tm_smem[];
+    uint8_t *pl0 = tm_smem, *pl1 = pl0 + TM_RC * TM_VPITCH, *pl2 = pl1 + TM_RC * TM_VPITCH;
+    uint8_t *stash = pl2 + TM_RC * TM_VPITCH;                       // raw rows of the output columns, slot = (raw index + 26) % 48
+    uint8_t *stage = stash + TM_GROWS * TM_GPITCH;                  // [24][86] words: the chunk's raw rows, each word private to its V thread
+    const int tid = threadIdx.x;
+    const bool vthread = tid < TM_VG;
+    const bool stash_ok = tid >= TM_HALO / 4 && tid < TM_VG - TM_HALO / 4;
+    uint8_t *my_stash = stash + 4 * (tid - TM_HALO / 4);
+    uint8_t *my_stage = stage + 4 * tid;
+    const uint32_t my_stage_s = (uint32_t)__cvta_generic_to_shared(my_stage);
+    const int rho = tid % TM_RC, sigma = tid / TM_RC;
+    const bool hthread = tid < TM_RC * TM_NSEG;
+    const int bias0 = -(TmWin<R0>::K2 * g.Cfloor - (TmWin<R0>::K2 - 1) / 2);
+    const int bias1 = -(TmWin<R1>::K2 * g.Cfloor - (TmWin<R1>::K2 - 1) / 2);
+    const int bias2 = -(TmWin<R2>::K2 * g.Cfloor - (TmWin<R2>::K2 - 1) / 2);
+    const int wmax = (g.W - 1) >> 2;                                // last 4-column word that starts inside a row
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int sy = item % n_sy;
+        const int t2 = item / n_sy;
+        const int sx = t2 % n_sx, b = t2 / n_sx;
+        const int X0 = sx * TM_WT, Y0 = sy * Hs;
+        const int rows = min(Hs, g.H - Y0);
+        const int ytop = Y0 - (TM_HALO - 1);                        // image row of raw index 0
+        // this thread's word of every row: replicate border = clamp the word index, then pick the bytes with the two
+        // unpack permutes (even columns -> Ce lanes, odd columns -> Co lanes); a selector nibble of 4 reads a zero byte
+        const int wcol = (X0 - TM_HALO) / 4 + tid;
+        const int wc = min(max(wcol, 0), wmax);
+        uint32_t sel_e, sel_o;
+        {
+            int bj[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bj[j] = min(max(4 * wcol + j, 0), g.W - 1) - 4 * wc;
+            sel_e = (uint32_t)bj[0] | 0x40u | ((uint32_t)bj[2] << 8) | 0x4000u;
+            sel_o = (uint32_t)bj[1] | 0x40u | ((uint32_t)bj[3] << 8) | 0x4000u;
+        }
+        const uint8_t *colp = gray + (size_t)b * frame_stride + 4 * (size_t)wc;
+
+        // prefix ring: slot (j + 1) % 24 holds the column prefix through raw index j; slot 0 starts as C[-1] = 0
+        uint32_t Ce[TM_RC], Co[TM_RC];
+#pragma unroll
+        for (int k = 0; k < TM_RC; ++k) { Ce[k] = 0; Co[k] = 0; }
+        uint32_t ce = 0, co = 0;
+        if (vthread) {
+            // chunk 0's rows (raw index 22 .. 45) start towards shared memory, then the 22 warm-up rows come through registers
+#pragma unroll
+            for (int u = 0; u < TM_RC; ++u) {
+                const int gy = min(max(ytop + u + 22, 0), g.H - 1);
+                tm_cp_async4(my_stage_s + u * (TM_VG * 4), colp + (size_t)((uint32_t)gy * (uint64_t)pitch));
+            }
+            tm_cp_async_commit();
+            uint32_t w[22];
+#pragma unroll
+            for (int i = 0; i < 22; ++i) {
+                const int gy = min(max(ytop + i, 0), g.H - 1);
+                w[i] = __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)((uint32_t)gy * (uint64_t)pitch)));
+            }
+#pragma unroll
+            for (int i = 0; i < 22; ++i) {
+                ce += __byte_perm(w[i], 0, sel_e); co += __byte_perm(w[i], 0, sel_o);
+                Ce[i + 1] = ce; Co[i + 1] = co;
+                if (stash_ok) *reinterpret_cast<uint32_t *>(my_stash + ((i + 26) % TM_GROWS) * TM_GPITCH) = w[i];
+            }
+        }
+        for (int m0 = 0, par = 0; m0 < rows; m0 += TM_RC, par ^= 1) {
+            if (vthread) {
+                uint32_t w[TM_RC];
+                tm_cp_async_wait_all();
+#pragma unroll
+                for (int u = 0; u < TM_RC; ++u) w[u] = *reinterpret_cast<const volatile uint32_t *>(my_stage + u * (TM_VG * 4));
+                uint8_t *st = my_stash + par * (TM_RC * TM_GPITCH);                           // raw index m0 + 22 + u -> slot 24 par + u
+#pragma unroll
+                for (int u = 0; u < TM_RC; ++u) {
+                    ce += __byte_perm(w[u], 0, sel_e); co += __byte_perm(w[u], 0, sel_o);
+                    Ce[(u + 23) % TM_RC] = ce; Co[(u + 23) % TM_RC] = co;                    // C[m + 22]
+                    if (stash_ok) *reinterpret_cast<uint32_t *>(st + u * TM_GPITCH) = w[u];
+                    // V_r[m] = C[m + r + 11] - C[m - r + 10]   (raw index = output row + 11)
+                    *reinterpret_cast<uint2 *>(pl0 + u * TM_VPITCH + 8 * tid) =
+                        make_uint2(Ce[(u + R0 + 12) % TM_RC] - Ce[(u + 11 - R0) % TM_RC], Co[(u + R0 + 12) % TM_RC] - Co[(u + 11 - R0) % TM_RC]);
+                    *reinterpret_cast<uint2 *>(pl1 + u * TM_VPITCH + 8 * tid) =
+                        make_uint2(Ce[(u + R1 + 12) % TM_RC] - Ce[(u + 11 - R1) % TM_RC], Co[(u + R1 + 12) % TM_RC] - Co[(u + 11 - R1) % TM_RC]);
+                    *reinterpret_cast<uint2 *>(pl2 + u * TM_VPITCH + 8 * tid) =
+                        make_uint2(Ce[(u + R2 + 12) % TM_RC] - Ce[(u + 11 - R2) % TM_RC], Co[(u + R2 + 12) % TM_RC] - Co[(u + 11 - R2) % TM_RC]);
+                }
+                if (m0 + TM_RC < rows) {                                                      // the next chunk's rows fly during this chunk's H phase
+#pragma unroll
+                    for (int u = 0; u < TM_RC; ++u) {
+                        const int gy = min(max(ytop + m0 + TM_RC + u + 22, 0), g.H - 1);
+                        tm_cp_async4(my_stage_s + u * (TM_VG * 4), colp + (size_t)((uint32_t)gy * (uint64_t)pitch));
+                    }
+                    tm_cp_async_commit();
+                }
+            }
+            __syncthreads();
+            const int y = Y0 + m0 + rho;
+            if (hthread && y < g.H && X0 + TM_SEG * sigma < g.W) {
+                const uint8_t *row0 = pl0 + rho * TM_VPITCH + 2 * TM_SEG * sigma;
+                const uint8_t *row1 = pl1 + rho * TM_VPITCH + 2 * TM_SEG * sigma;
+                const uint8_t *row2 = pl2 + rho * TM_VPITCH + 2 * TM_SEG * sigma;
+                const uint8_t *grow = stash + ((m0 + rho + 11 + 26) % TM_GROWS) * TM_GPITCH + TM_SEG * sigma;   // the centre pixels: raw index = row + 11
+                TmWin<R0> w0; TmWin<R1> w1; TmWin<R2> w2;
+                w0.load(row0, TmWin<R0>::first_piece, TmWin<R0>::newest_piece(0) - 1);
+                w1.load(row1, TmWin<R1>::first_piece, TmWin<R1>::newest_piece(0) - 1);
+                w2.load(row2, TmWin<R2>::first_piece, TmWin<R2>::newest_piece(0) - 1);
+                w0.init(bias0); w1.init(bias1); w2.init(bias2);
+                uint32_t m_0 = 0, m_1 = 0, m_2 = 0;
+                uint32_t *mrow = masks + (size_t)b * 3 * g.mask_plane + (size_t)(y + 1) * g.PWW + 1 + X0 / 32 + 2 * sigma;
+                uint4 gq;
+#pragma unroll
+                for (int blk = 0; blk < TM_SEG / 8; ++blk) {
+                    w0.load(row0, blk == 0 ? TmWin<R0>::newest_piece(0) : TmWin<R0>::newest_piece(blk - 1) + 1, TmWin<R0>::newest_piece(blk));
+                    w1.load(row1, blk == 0 ? TmWin<R1>::newest_piece(0) : TmWin<R1>::newest_piece(blk - 1) + 1, TmWin<R1>::newest_piece(blk));
+                    w2.load(row2, blk == 0 ? TmWin<R2>::newest_piece(0) : TmWin<R2>::newest_piece(blk - 1) + 1, TmWin<R2>::newest_piece(blk));
+                    if ((blk & 1) == 0) gq = *reinterpret_cast<const uint4 *>(grow + 8 * blk);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int i = 8 * blk + j;
+                        const int e = i & 15;
+                        const uint32_t gw = (e >> 2) == 0 ? gq.x : (e >> 2) == 1 ? gq.y : (e >> 2) == 2 ? gq.z : gq.w;
+                        const int gv = (int)__byte_perm(gw, 0, 0x4440 + (e & 3));
+                        const int d0 = w0.S - TmWin<R0>::K2 * gv, d1 = w1.S - TmWin<R1>::K2 * gv, d2 = w2.S - TmWin<R2>::K2 * gv;
+                        m_0 = __funnelshift_l((uint32_t)d0, m_0, 1);                 // (m << 1) | sign(d)
+                        m_1 = __funnelshift_l((uint32_t)d1, m_1, 1);
+                        m_2 = __funnelshift_l((uint32_t)d2, m_2, 1);
+                        if (i + 1 < TM_SEG) { w0.slide(i); w1.slide(i); w2.slide(i); }
+                    }
+                    if ((blk & 3) == 3) {                                            // 32 columns done: first column ends up in bit 0, set = test passed
+                        const int wd = blk >> 2;
+                        const int left = g.W - (X0 + TM_SEG * sigma + 32 * wd);
+                        if (left > 0) {
+                            const uint32_t valid = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
+                            mrow[wd] = ~__brev(m_0) & valid;
+                            mrow[g.mask_plane + wd] = ~__brev(m_1) & valid;
+                            mrow[2 * g.mask_plane + wd] = ~__brev(m_2) & valid;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // expand packed masks to 0/255 bytes (debug / parity tap)
 __global__ void k_unpack_masks(const uint32_t *__restrict__ masks, uint8_t *__restrict__ out, DetGeom g)
 {

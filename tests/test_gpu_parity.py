@@ -196,7 +196,7 @@ def test_threshold_edge_shapes(aruco, oracle):
     """ragged sizes: widths not multiples of 16/32/128, tiny frames, non-default window list."""
     rng = np.random.default_rng(3)
     dic = D.getPredefinedDictionary(0)
-    for (H, W) in ((31, 33), (64, 129), (95, 257), (130, 64), (7, 300)):
+    for (H, W) in ((31, 33), (64, 129), (95, 257), (130, 64), (7, 300), (50, 324), (26, 644), (100, 12), (49, 963), (241, 5)):
         img = rng.integers(0, 256, (H, W)).astype(np.uint8)
         det = _detector(aruco, dic, (H, W))
         _, masks = det.debug_threshold(img)
