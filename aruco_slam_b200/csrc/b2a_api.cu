@@ -550,8 +550,13 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
             // resident CTA slot an item (a segment costs 22 rows of prefix warm-up)
             const int n_sx = (W + TM_WT - 1) / TM_WT, slots = d->num_sms * 3;
             int Hs = TM_RC;
-            for (int h = 5 * TM_RC; h >= TM_RC; h -= TM_RC)
-                if (nb * n_sx * ((H + h - 1) / h) >= slots) { Hs = h; break; }
+            double best = -1.0;
+            for (int h = TM_RC; h <= TM_MAX_HS; h += TM_RC) {
+                // share of the resident slots that is busy over the whole launch (items run in waves) x share of rows that are not warm-up
+                const int n = nb * n_sx * ((H + h - 1) / h);
+                const double score = (double)n / ((double)((n + slots - 1) / slots) * slots) / (1.0 + 0.3 * 22.0 / h);
+                if (score > best * 1.0001) { best = score; Hs = h; }
+            }
             const int n_sy = (H + Hs - 1) / Hs, n_items = nb * n_sx * n_sy;
             k_threshold_march<1, 6, 11><<<std::min(n_items, slots), TM_THREADS, TM_SMEM, st>>>(s.gray, (uint32_t)s.pitch, s.frame_stride, masks, g, Hs, n_sy, n_sx, n_items);
         } else if (default_windows) {

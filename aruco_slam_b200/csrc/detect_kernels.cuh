@@ -450,10 +450,17 @@ k_threshold_march(const uint8_t *__restrict__ gray, uint32_t pitch, size_t frame
                         make_uint2(Ce[(u + R2 + 12) % TM_RC] - Ce[(u + 11 - R2) % TM_RC], Co[(u + R2 + 12) % TM_RC] - Co[(u + 11 - R2) % TM_RC]);
                 }
                 if (m0 + TM_RC < rows) {                                                      // the next chunk's rows fly during this chunk's H phase
+                    const int r_first = ytop + m0 + TM_RC + 22;
+                    if (r_first >= 0 && r_first + TM_RC - 1 <= g.H - 1) {                     // no clamping inside the frame
+                        const uint8_t *p = colp + (size_t)((uint32_t)r_first * (uint64_t)pitch);
 #pragma unroll
-                    for (int u = 0; u < TM_RC; ++u) {
-                        const int gy = min(max(ytop + m0 + TM_RC + u + 22, 0), g.H - 1);
-                        tm_cp_async4(my_stage_s + u * (TM_VG * 4), colp + (size_t)((uint32_t)gy * (uint64_t)pitch));
+                        for (int u = 0; u < TM_RC; ++u) tm_cp_async4(my_stage_s + u * (TM_VG * 4), p + (size_t)((uint32_t)u * (uint64_t)pitch));
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < TM_RC; ++u) {
+                            const int gy = min(max(r_first + u, 0), g.H - 1);
+                            tm_cp_async4(my_stage_s + u * (TM_VG * 4), colp + (size_t)((uint32_t)gy * (uint64_t)pitch));
+                        }
                     }
                     tm_cp_async_commit();
                 }
