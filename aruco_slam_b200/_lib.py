@@ -74,6 +74,15 @@ class Observation(C.Structure):
                 ("theta", C.c_double), ("cov", C.c_double * 9)]
 
 
+class MapMarker(C.Structure):
+    _fields_ = [("id", C.c_int32), ("length", C.c_double), ("x", C.c_double), ("y", C.c_double), ("z", C.c_double),
+                ("roll", C.c_double), ("pitch", C.c_double), ("yaw", C.c_double), ("q", C.c_double * 4)]
+
+
+class PoseWithCovariance(C.Structure):
+    _fields_ = [("position", C.c_double * 3), ("orientation", C.c_double * 4), ("covariance", C.c_double * 36)]
+
+
 # every symbol include/b2aruco.h declares
 SYMBOLS = [
     "b2a_last_error", "b2a_version", "b2a_default_detector_params", "b2a_get_predefined_dictionary",
@@ -82,6 +91,7 @@ SYMBOLS = [
     "b2a_detector_num_scales", "b2a_detector_set_streams", "b2a_last_stage_times", "b2a_last_launch_count", "b2a_detector_stream",
     "b2a_default_slam_params", "b2a_slam_create", "b2a_slam_destroy", "b2a_slam_dim", "b2a_slam_get_state",
     "b2a_slam_set_state", "b2a_slam_add_encoder", "b2a_slam_make_observations", "b2a_slam_update", "b2a_slam_add_image", "b2a_slam_synchronize",
+    "b2a_quaternion_from_rpy", "b2a_map_parse", "b2a_map_load", "b2a_slam_robot_pose", "b2a_slam_detected_map",
 ]
 
 _lib = None
@@ -109,6 +119,12 @@ def lib():
         for name in ("b2a_detector_destroy", "b2a_detector_num_scales", "b2a_last_launch_count", "b2a_detector_stream",
                      "b2a_slam_destroy", "b2a_slam_dim", "b2a_slam_synchronize"):
             getattr(L, name).argtypes = [C.c_void_p]
+        L.b2a_quaternion_from_rpy.argtypes = [C.c_double, C.c_double, C.c_double, C.c_void_p]
+        L.b2a_quaternion_from_rpy.restype = None
+        L.b2a_map_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
+        L.b2a_map_load.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.b2a_slam_robot_pose.argtypes = [C.c_void_p, C.c_void_p]
+        L.b2a_slam_detected_map.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p]
         L.b2a_detector_set_streams.argtypes = [C.c_void_p, C.c_int]
         L.b2a_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2a_detect_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

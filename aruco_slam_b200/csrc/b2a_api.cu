@@ -8,6 +8,7 @@
 #include "pose_core.h"
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1024,6 +1025,134 @@ extern "C" int b2a_slam_synchronize(b2a_slam *s)
     if (!s) return set_err(B2A_ERR_INVALID, "null handle");
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
+    return B2A_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// wire / on-disk formats either side of the path (host only): landmark map text, pose + covariance record, map cubes
+// ------------------------------------------------------------------------------------------------
+extern "C" void b2a_quaternion_from_rpy(double roll, double pitch, double yaw, double q[4])
+{   // tf2::Quaternion::setRPY (the library the reference calls at map_loader.cpp:90 and aruco_slam.cpp:273,387)
+    const double hy = yaw * 0.5, hp = pitch * 0.5, hr = roll * 0.5;
+    const double cy = std::cos(hy), sy = std::sin(hy), cp = std::cos(hp), sp = std::sin(hp), cr = std::cos(hr), sr = std::sin(hr);
+    q[0] = sr * cp * cy - cr * sp * sy;
+    q[1] = cr * sp * cy + sr * cp * sy;
+    q[2] = cr * cp * sy - sr * sp * cy;
+    q[3] = cr * cp * cy + sr * sp * sy;
+}
+
+namespace {
+// formatted extraction the way `std::istringstream >> int / double` behaves on one line: skip blanks, convert the longest
+// prefix, and once one extraction has failed every later one fails too
+struct LineCursor {
+    const char *p, *end;
+    bool failed = false;
+    void skip() { while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\v' || *p == '\f')) ++p; }
+    bool get_int(int &v)
+    {
+        if (failed) return false;
+        skip();
+        std::string tok(p, end);
+        char *e = nullptr;
+        const long r = std::strtol(tok.c_str(), &e, 10);
+        if (e == tok.c_str()) { failed = true; return false; }
+        v = (int)r; p += e - tok.c_str();
+        return true;
+    }
+    bool get_double(double &v)
+    {
+        if (failed) return false;
+        skip();
+        std::string tok(p, end);
+        char *e = nullptr;
+        const double r = std::strtod(tok.c_str(), &e);
+        if (e == tok.c_str()) { failed = true; return false; }
+        v = r; p += e - tok.c_str();
+        return true;
+    }
+};
+}  // namespace
+
+extern "C" int b2a_map_parse(const char *text, size_t len, b2a_map_marker *out, int cap, int *n_out)
+{
+    if (!text || !n_out || (cap > 0 && !out)) return set_err(B2A_ERR_INVALID, "null argument");
+    int n = 0;
+    const char *p = text, *end = text + len;
+    while (p < end) {
+        const char *eol = (const char *)std::memchr(p, '\n', (size_t)(end - p));
+        if (!eol) eol = end;
+        LineCursor c{p, eol};
+        p = eol < end ? eol + 1 : end;
+        c.skip();
+        if (c.p >= c.end) continue;                                   // blank line (map_loader.cpp:26-30)
+        if (*c.p == '#') continue;                                    // comment (:32-36)
+        if (!std::isdigit((unsigned char)*c.p)) { *n_out = 0; return B2A_OK; }   // malformed: the whole map is dropped (:44-50)
+        b2a_map_marker m;
+        std::memset(&m, 0, sizeof(m));
+        int id = 0;
+        if (!(c.get_int(id) && c.get_double(m.length) && c.get_double(m.x) && c.get_double(m.y))) continue;   // (:52-58)
+        m.id = id;
+        if (!c.get_double(m.z)) m.z = 0;                              // (:60-64)
+        if (!c.get_double(m.roll)) m.roll = 0;                        // 6th field (:65-69 zeroes yaw and leaves roll unset; 0 is the intent)
+        if (!c.get_double(m.pitch)) m.pitch = 0;                      // (:70-74)
+        if (!c.get_double(m.yaw)) m.yaw = 0;                          // 8th field (:75-79)
+        b2a_quaternion_from_rpy(m.roll, m.pitch, m.yaw, m.q);         // addMarker (:86-94)
+        if (n < cap) out[n] = m;
+        ++n;
+    }
+    *n_out = n;
+    if (n > cap) return set_err(B2A_ERR_CAPACITY, "map has more markers than the output array");
+    return B2A_OK;
+}
+
+extern "C" int b2a_map_load(const char *path, b2a_map_marker *out, int cap, int *n_out)
+{
+    if (!path || !n_out) return set_err(B2A_ERR_INVALID, "null argument");
+    std::FILE *f = std::fopen(path, "rb");
+    if (!f) { *n_out = 0; return set_err(B2A_ERR_INVALID, std::string("cannot open map file ") + path); }
+    std::string text;
+    char buf[4096];
+    size_t got;
+    while ((got = std::fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, got);
+    std::fclose(f);
+    return b2a_map_parse(text.data(), text.size(), out, cap, n_out);
+}
+
+extern "C" int b2a_slam_robot_pose(b2a_slam *s, b2a_pose_with_covariance *out)
+{
+    if (!s || !out) return set_err(B2A_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    double mu[3], S[9];
+    CU(cudaMemcpy(mu, s->d_mu, sizeof(mu), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy2D(S, 3 * 8, s->d_sigma, (size_t)s->LD * 8, 3 * 8, 3, cudaMemcpyDeviceToHost));
+    std::memset(out, 0, sizeof(*out));
+    out->position[0] = mu[0]; out->position[1] = mu[1]; out->position[2] = 0.1;                    // aruco_slam.cpp:381-383
+    b2a_quaternion_from_rpy(0, 0, mu[2], out->orientation);                                        // :386-388
+    static const int at[9] = {0, 1, 5, 6, 7, 11, 30, 31, 35};                                      // :397-405
+    for (int i = 0; i < 9; ++i) out->covariance[at[i]] = S[i];
+    return B2A_OK;
+}
+
+extern "C" int b2a_slam_detected_map(b2a_slam *s, double marker_length, b2a_map_marker *out, int cap, int *n_out)
+{
+    if (!s || !n_out || (cap > 0 && !out)) return set_err(B2A_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    const int n = (s->N - 3) / 3;
+    std::vector<double> mu((size_t)s->N);
+    CU(cudaMemcpy(mu.data(), s->d_mu, (size_t)s->N * 8, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n && i < cap; ++i) {                                                       // aruco_slam.cpp:266-281
+        b2a_map_marker m;
+        std::memset(&m, 0, sizeof(m));
+        m.id = i; m.length = marker_length;
+        m.x = mu[3 + 3 * i]; m.y = mu[4 + 3 * i]; m.z = 0.3;
+        m.roll = 0; m.pitch = 1.5708; m.yaw = mu[5 + 3 * i];
+        b2a_quaternion_from_rpy(m.roll, m.pitch, m.yaw, m.q);
+        out[i] = m;
+    }
+    *n_out = n;
+    if (n > cap) return set_err(B2A_ERR_CAPACITY, "more landmarks than the output array");
     return B2A_OK;
 }
 

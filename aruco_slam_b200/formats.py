@@ -1,0 +1,75 @@
+"""Wire / on-disk formats either side of the path, as plain records (no ROS types).
+
+  load_map / parse_map     <-> MapLoader::loadMap              (reference src/map_loader.cpp:7-84, map/map.txt)
+  quaternion_from_rpy      <-> tf2::Quaternion::setRPY         (map_loader.cpp:90, aruco_slam.cpp:273,387)
+  robot_pose(slam)         <-> ArucoSlam::toRosPose            (aruco_slam.cpp:376-407)
+  detected_map(slam)       <-> detected_map_ of addImage       (aruco_slam.cpp:266-281)
+
+Thin ctypes wrappers over the host-side entry points of libb2aruco.so (include/b2aruco.h)."""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+
+@dataclass
+class MapMarker:
+    """one cube of the reference's MarkerArray: frame "world", scale (length, length, 0.01)"""
+    id: int
+    length: float
+    x: float
+    y: float
+    z: float
+    roll: float
+    pitch: float
+    yaw: float
+    q: tuple          # orientation (x, y, z, w)
+
+
+@dataclass
+class PoseWithCovariance:
+    position: np.ndarray       # (3,)
+    orientation: np.ndarray    # (4,) x, y, z, w
+    covariance: np.ndarray     # (6, 6)
+
+
+def quaternion_from_rpy(roll: float, pitch: float, yaw: float) -> np.ndarray:
+    q = (C.c_double * 4)()
+    _lib.lib().b2a_quaternion_from_rpy(roll, pitch, yaw, q)
+    return np.array(q[:])
+
+
+def _markers(arr, n):
+    return [MapMarker(m.id, m.length, m.x, m.y, m.z, m.roll, m.pitch, m.yaw, tuple(m.q[:])) for m in arr[:n]]
+
+
+def parse_map(text, cap: int = 4096):
+    """the markers a map text defines, under the reference loader's acceptance rules (see include/b2aruco.h)"""
+    data = text.encode() if isinstance(text, str) else bytes(text)
+    arr = (_lib.MapMarker * cap)()
+    n = C.c_int(0)
+    _lib.check(_lib.lib().b2a_map_parse(data, len(data), arr, cap, C.byref(n)))
+    return _markers(arr, n.value)
+
+
+def load_map(path: str, cap: int = 4096):
+    arr = (_lib.MapMarker * cap)()
+    n = C.c_int(0)
+    _lib.check(_lib.lib().b2a_map_load(str(path).encode(), arr, cap, C.byref(n)))
+    return _markers(arr, n.value)
+
+
+def robot_pose(slam) -> PoseWithCovariance:
+    out = _lib.PoseWithCovariance()
+    _lib.check(_lib.lib().b2a_slam_robot_pose(slam._h, C.byref(out)))
+    return PoseWithCovariance(np.array(out.position[:]), np.array(out.orientation[:]), np.array(out.covariance[:]).reshape(6, 6))
+
+
+def detected_map(slam, marker_length: float = None):
+    n_lm = (slam.dim - 3) // 3
+    arr = (_lib.MapMarker * max(1, n_lm))()
+    n = C.c_int(0)
+    _lib.check(_lib.lib().b2a_slam_detected_map(slam._h, float(marker_length if marker_length is not None else slam.marker_length), arr, max(1, n_lm), C.byref(n)))
+    return _markers(arr, n.value)

@@ -193,6 +193,37 @@ int  b2a_slam_synchronize(b2a_slam *s);
 /* addImage(img): detect + pose + observations + EKF update for one frame (aruco_slam.cpp:76-263). */
 int  b2a_slam_add_image(b2a_slam *s, b2a_detector *d, const b2a_frames *frame, const b2a_camera *cam);
 
+/* ---- wire / on-disk formats either side of the path (host only, no ROS types) ---- */
+/* One line of the landmark map (reference map/map.txt:1 "id length x y z roll_x pitch_y yaw_z") and, equally, one cube of the
+ * reference's MarkerArray messages (visualization_msgs::Marker fields the reference fills, map_loader.cpp:96-117 and
+ * aruco_slam.cpp:289-305): frame "world", scale (length, length, 0.01), pose position (x, y, z), orientation q = (qx, qy, qz, qw). */
+typedef struct {
+    int32_t id;
+    double  length, x, y, z, roll, pitch, yaw;
+    double  q[4];                    /* tf2::Quaternion::setRPY(roll, pitch, yaw) as (x, y, z, w) */
+} b2a_map_marker;
+/* tf2::Quaternion::setRPY (fixed axes: roll about X, then pitch about Y, then yaw about Z); q = (x, y, z, w). */
+void b2a_quaternion_from_rpy(double roll, double pitch, double yaw, double q[4]);
+/* MapLoader::loadMap (map_loader.cpp:7-84) on a text buffer: blank lines and lines whose first non-blank character is '#'
+ * are skipped; a line whose first non-blank character is not a digit aborts the load with an EMPTY map (:44-50); a line with
+ * fewer than the four fields id length x y is skipped (:52-58); missing z / roll / pitch / yaw read as 0 (the reference leaves
+ * roll and yaw uninitialised in that case, :65-79 -- 0 is its evident intent).  Returns B2A_OK and *n_out = markers written
+ * (B2A_ERR_CAPACITY if cap is too small; *n_out then holds the number the text defines). */
+int  b2a_map_parse(const char *text, size_t len, b2a_map_marker *out, int cap, int *n_out);
+/* the same from a file; B2A_ERR_INVALID when the file cannot be opened (the reference logs and leaves the map empty, :13-17) */
+int  b2a_map_load(const char *path, b2a_map_marker *out, int cap, int *n_out);
+/* ArucoSlam::toRosPose (aruco_slam.cpp:376-407): position (mu0, mu1, 0.1), orientation setRPY(0, 0, mu2), and the 6x6 row-major
+ * covariance with Sigma[0:3,0:3] scattered to entries 0,1,5 / 6,7,11 / 30,31,35 (all others 0). */
+typedef struct {
+    double position[3];
+    double orientation[4];           /* (x, y, z, w) */
+    double covariance[36];
+} b2a_pose_with_covariance;
+int  b2a_slam_robot_pose(b2a_slam *s, b2a_pose_with_covariance *out);
+/* detected_map_ of addImage (aruco_slam.cpp:266-281): one cube per landmark i: id = i (the landmark index, not the aruco id),
+ * length = marker_length, position (mu[3+3i], mu[4+3i], 0.3), orientation setRPY(0, 1.5708, mu[5+3i]). */
+int  b2a_slam_detected_map(b2a_slam *s, double marker_length, b2a_map_marker *out, int cap, int *n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,66 @@
+"""Wire / on-disk formats: the landmark map text, tf2's setRPY, the robot pose record and the map cubes.
+Host-only entry points of the C ABI, checked against independent restatements (SciPy rotations, NumPy packing); the GPU-side
+records are checked in test_gpu_slam.py::test_pose_and_map_records."""
+import numpy as np
+import pytest
+from scipy.spatial.transform import Rotation
+
+from aruco_slam_b200 import formats
+from aruco_slam_b200._lib import B2AError
+
+# same layout as the reference's map/map.txt (header comment, tabs and blanks mixed, trailing blanks); values are ours
+MAP_TEXT = """# id    length\tx\ty\tz\troll_x\tpitch_y\tyaw_z
+0   0.27\t5.10375 0       0.3     0    -1.5708   0
+1\t0.27\t5.10375 -1.5    0.3     0    -1.5708   0
+
+7\t0.2\t4   0.6025 0.3 \t1.5708 \t-0\t0.25  
+   # an indented comment
+12 0.15 -2.5 1e-1
+13 0.15 1 2 3
+14 0.15 1 2 3 0.1
+15 0.15 1 2 3 0.1 0.2
+16 0.15 1 2
+"""
+
+
+def test_quaternion_matches_fixed_axis_rpy():
+    rng = np.random.default_rng(0)
+    for r, p, y in rng.uniform(-np.pi, np.pi, (50, 3)):
+        q = formats.quaternion_from_rpy(r, p, y)
+        want = Rotation.from_euler("xyz", [r, p, y]).as_quat()          # extrinsic x-y-z = tf2::Quaternion::setRPY
+        if np.dot(q, want) < 0:
+            want = -want
+        assert np.allclose(q, want, atol=1e-14)
+    assert np.allclose(formats.quaternion_from_rpy(0, 0, 0), [0, 0, 0, 1])
+
+
+def test_parse_map_rules(tmp_path):
+    ms = formats.parse_map(MAP_TEXT)
+    assert [m.id for m in ms] == [0, 1, 7, 12, 13, 14, 15, 16]
+    by = {m.id: m for m in ms}
+    assert by[0].length == 0.27 and by[0].x == 5.10375 and by[0].y == 0 and by[0].z == 0.3
+    assert (by[0].roll, by[0].pitch, by[0].yaw) == (0, -1.5708, 0)
+    assert (by[7].roll, by[7].pitch, by[7].yaw) == (1.5708, 0, 0.25) and by[7].length == 0.2
+    assert (by[12].x, by[12].y, by[12].z, by[12].roll, by[12].pitch, by[12].yaw) == (-2.5, 0.1, 0, 0, 0, 0)
+    assert (by[13].z, by[13].roll, by[13].pitch, by[13].yaw) == (3, 0, 0, 0)
+    assert (by[14].roll, by[14].pitch, by[14].yaw) == (0.1, 0, 0)
+    assert (by[15].roll, by[15].pitch, by[15].yaw) == (0.1, 0.2, 0)
+    assert (by[16].x, by[16].y, by[16].z, by[16].yaw) == (1, 2, 0, 0)                  # exactly the four mandatory fields
+    for m in ms:
+        want = Rotation.from_euler("xyz", [m.roll, m.pitch, m.yaw]).as_quat()
+        assert np.allclose(m.q, want if np.dot(m.q, want) >= 0 else -want, atol=1e-14)
+    # the same through a file
+    f = tmp_path / "map.txt"
+    f.write_text(MAP_TEXT)
+    assert formats.load_map(str(f)) == ms
+    with pytest.raises(B2AError):
+        formats.load_map(str(tmp_path / "missing.txt"))
+
+
+def test_parse_map_short_and_malformed_lines():
+    assert [m.id for m in formats.parse_map("3 0.27 1\n4 0.27 1 2\n")] == [4]          # fewer than id length x y: line skipped
+    assert formats.parse_map("1 0.27 1 2\n-2 0.27 1 2\n3 0.27 1 2\n") == []            # first character not a digit: the whole map is dropped
+    assert formats.parse_map("") == [] and formats.parse_map("\n\n# only comments\n") == []
+    assert [m.id for m in formats.parse_map("5 0.27 1 2")] == [5]                      # no trailing newline
+    with pytest.raises(B2AError):
+        formats.parse_map("1 1 1 1\n2 1 1 1\n", cap=1)

@@ -108,3 +108,31 @@ def test_add_image_vs_oracle_pipeline(oracle):
         assert np.abs(mu - omu).max() < 1e-4        # north_star: 1e-4 m / rad (poses come from two LM implementations)
         assert np.abs(sg - osg).max() < 1e-4
     s.close()
+
+
+def test_pose_and_map_records():
+    """the ROS-free records of the filter state: toRosPose's packing (aruco_slam.cpp:376-407) and the detected-map cubes (:266-281)"""
+    from scipy.spatial.transform import Rotation
+    from aruco_slam_b200 import slam, formats
+    rng = np.random.default_rng(5)
+    n_lm = 4
+    N = 3 + 3 * n_lm
+    A = rng.normal(size=(N, N))
+    sigma = A @ A.T / N + 0.1 * np.eye(N)
+    mu = rng.uniform(-2, 2, N)
+    s = slam.ArucoSlam(marker_length=0.27, image_shape=(64, 64))
+    s.set_state(mu, sigma, np.arange(10, 10 + n_lm, dtype=np.int32))
+    p = formats.robot_pose(s)
+    assert np.array_equal(p.position, [mu[0], mu[1], 0.1])
+    q = Rotation.from_euler("xyz", [0, 0, mu[2]]).as_quat()
+    assert np.allclose(p.orientation, q if np.dot(q, p.orientation) >= 0 else -q, atol=1e-14)
+    want = np.zeros((6, 6))
+    want[np.ix_([0, 1, 5], [0, 1, 5])] = sigma[:3, :3]
+    assert np.array_equal(p.covariance, want)
+    cubes = formats.detected_map(s)
+    assert [c.id for c in cubes] == list(range(n_lm))             # the landmark index, as the reference publishes it
+    for i, c in enumerate(cubes):
+        assert (c.length, c.x, c.y, c.z) == (0.27, mu[3 + 3 * i], mu[4 + 3 * i], 0.3)
+        q = Rotation.from_euler("xyz", [0, 1.5708, mu[5 + 3 * i]]).as_quat()
+        assert np.allclose(c.q, q if np.dot(q, c.q) >= 0 else -q, atol=1e-14)
+    s.close()
