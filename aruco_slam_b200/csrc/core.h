@@ -548,10 +548,14 @@ B2A_HD int approx_closed(const LG &lg, const uint32_t *__restrict__ P, int count
                     const int t = t0 + k * nl;
                     const int px = px_of(qq[k]) - sx, py = py_of(qq[k]) - sy;
                     const int dot = px * dx + py * dy;
-                    unsigned long long d;
-                    if (dot < 0) d = (unsigned long long)((uint32_t)(px * px) + (uint32_t)(py * py)) * L2u;
-                    else if ((uint32_t)dot > L2u) { const int qx = px - dx, qy = py - dy; d = (unsigned long long)((uint32_t)(qx * qx) + (uint32_t)(qy * qy)) * L2u; }
-                    else { const int cr = py * dx - px * dy; const uint32_t a = (uint32_t)(cr < 0 ? -cr : cr); d = (unsigned long long)a * a; }
+                    // one widening multiply a * b with selected factors, no divergent branch: before the segment |p - s|^2 * L2,
+                    // past it |p - e|^2 * L2, beside it cross^2
+                    const int qx = px - dx, qy = py - dy, cr = py * dx - px * dy;
+                    const uint32_t acr = (uint32_t)(cr < 0 ? -cr : cr);
+                    const bool before = dot < 0, past = !before && (uint32_t)dot > L2u;
+                    const uint32_t fa = before ? (uint32_t)(px * px) + (uint32_t)(py * py) : past ? (uint32_t)(qx * qx) + (uint32_t)(qy * qy) : acr;
+                    const uint32_t fb = (before || past) ? L2u : acr;
+                    const unsigned long long d = (unsigned long long)fa * fb;
                     if (t < inner && d > bdu) { bdu = d; bt = t; }
                 }
             }
@@ -911,6 +915,9 @@ B2A_HD double otsu_bin(double q1)
 B2A_HD void otsu_chain(int lo, int hi, const double *q1s, const double *ys, double *mu1s)
 {
     double mu1 = 0, q1prev = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
     for (int i = lo; i <= hi; ++i) {
         const double b = q1s[i], y = ys[i];
         const double t = d_mul(mu1, q1prev);
@@ -1002,20 +1009,25 @@ B2A_HD int ident_cell_bit(const uint8_t *patch, int S, int cellSize, int cellMar
             nz += patch[(cy * cellSize + cellMargin + yy) * S + cx * cellSize + cellMargin + xx] > thr;
     return nz > (cw * cw) / 2;
 }
-// border check + code word (byte k of the cv2 byte list in bits 8k..8k+7); false = border wrong
+// one cell of the bit matrix: a border cell adds to the error count, an inner cell to the code word (byte k of the cv2 byte
+// list in bits 8k..8k+7); the cells are independent, so the kernel spreads them over the lanes and reduces
+B2A_HD void ident_cell_accumulate(int cidx, unsigned bit, int markerSize, int bb, int &err, unsigned long long &code)
+{
+    const int nb = markerSize + 2 * bb;
+    const int cy = cidx / nb, cx = cidx - cy * nb;
+    if (cy < bb || cy >= nb - bb || cx < bb || cx >= nb - bb) { err += bit != 0; return; }
+    const int ms = markerSize, nbits = ms * ms, nby = (nbits + 7) / 8;
+    const int i = (cy - bb) * ms + (cx - bb), byte = i >> 3;
+    const int shift = (byte == nby - 1 && (nbits & 7)) ? ((nbits & 7) - 1 - (i & 7)) : (7 - (i & 7));
+    code |= (unsigned long long)(bit != 0) << (8 * byte + shift);
+}
+// border check + code word; false = border wrong
 B2A_HD bool ident_border_code(const uint8_t *bits, int markerSize, int bb, int maxBorderErr, unsigned long long &code)
 {
     const int nb = markerSize + 2 * bb;
     int err = 0;
-    for (int y = 0; y < nb; ++y) for (int k = 0; k < bb; ++k) { err += bits[y * nb + k] != 0; err += bits[y * nb + nb - 1 - k] != 0; }
-    for (int x = bb; x < nb - bb; ++x) for (int k = 0; k < bb; ++k) { err += bits[k * nb + x] != 0; err += bits[(nb - 1 - k) * nb + x] != 0; }
     code = 0;
-    const int ms = markerSize, nbits = ms * ms, nby = (nbits + 7) / 8;
-    for (int i = 0; i < nbits; ++i) {
-        const int y = i / ms, x = i - y * ms, byte = i >> 3;
-        const int shift = (byte == nby - 1 && (nbits & 7)) ? ((nbits & 7) - 1 - (i & 7)) : (7 - (i & 7));
-        code |= (unsigned long long)bits[(y + bb) * nb + x + bb] << (8 * byte + shift);
-    }
+    for (int c = 0; c < nb * nb; ++c) ident_cell_accumulate(c, bits[c], markerSize, bb, err, code);
     return err <= maxBorderErr;
 }
 // smallest Hamming distance of marker m over its 4 rotations (first minimum wins)

@@ -934,28 +934,67 @@ k_assign_sub(BorderGraph bg)
     }
 }
 
-// A3a step 6: every anchor of a kept border re-walks its segment and writes the points
+// A3a step 6: the points of every kept border.  The lanes of a warp first read the records of 32 anchors, then the warp takes
+// the segments one at a time with one lane per point: the positions are an exclusive warp scan of the stored direction codes
+// ((dx + 1) and (dy + 1) packed in one word), so the 4-byte points of a segment leave as one coalesced store per 32 points
+// instead of one 32-byte sector per point and lane.  (A segment longer than its 80 stored codes is re-walked by its own lane.)
 __global__ void __launch_bounds__(256)
 k_emit(const uint32_t *__restrict__ masks, BorderGraph bg, const uint4 *__restrict__ sorted, const int *__restrict__ pts_off,
        uint32_t *__restrict__ pts, const WalkTables *__restrict__ tables, DetGeom g)
 {
     __shared__ __align__(16) uint16_t s_succ[4096];
+    constexpr unsigned FULL = 0xFFFFFFFFu;
     unsigned n = *bg.n_anchors;
     if (n > bg.cap) n = bg.cap;
     if (blockIdx.x * blockDim.x >= n) return;
     load_walk_tables(tables, s_succ, nullptr);
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int2 e = bg.emit[i];
-        if (e.y == 0) continue;
-        const uint2 a = bg.ast[i];
-        const int fs = (int)(a.y >> 4);
-        const int len = (int)__ldg(&sorted[e.y - 1].y), off = __ldg(&pts_off[e.y - 1]);
-        const int slen = (int)(bg.seg[i].len & SEG_LEN);
-        uint32_t *out = pts + (size_t)fs * g.pts_cap + off;
-        if (slen <= SEG_CODE_WORDS * 10) seg_emit_codes(bg.codes + (size_t)i * SEG_CODE_WORDS, (int)(a.x & 0xFFFFu), (int)(a.x >> 16), slen, e.x, len, out);
-        else {
-            MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
-            seg_emit(rd, s_succ, (int)(a.x & 0xFFFFu), (int)(a.x >> 16), (int)(a.y & 7u), slen, e.x, len, out);
+    const int lane = threadIdx.x & 31;
+    for (unsigned base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+        const unsigned i = base + lane;
+        int pos = 0, len = 0, off = 0, slen = 0, fs = 0, x0 = 0, y0 = 0;
+        bool coop = false;
+        if (i < n) {
+            const int2 e = bg.emit[i];
+            if (e.y != 0) {
+                const uint2 a = bg.ast[i];
+                fs = (int)(a.y >> 4);
+                len = (int)__ldg(&sorted[e.y - 1].y); off = __ldg(&pts_off[e.y - 1]);
+                slen = (int)(bg.seg[i].len & SEG_LEN);
+                pos = e.x; x0 = (int)(a.x & 0xFFFFu); y0 = (int)(a.x >> 16);
+                coop = slen <= SEG_CODE_WORDS * 10;
+                if (!coop) {
+                    MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
+                    seg_emit(rd, s_succ, x0, y0, (int)(a.y & 7u), slen, pos, len, pts + (size_t)fs * g.pts_cap + off);
+                }
+            }
+        }
+        unsigned todo = __ballot_sync(FULL, coop);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int jpos = __shfl_sync(FULL, pos, j), jlen = __shfl_sync(FULL, len, j), jslen = __shfl_sync(FULL, slen, j);
+            int cx = __shfl_sync(FULL, x0, j), cy = __shfl_sync(FULL, y0, j);            // point 32 * round of the segment
+            uint32_t *out = pts + (size_t)__shfl_sync(FULL, fs, j) * g.pts_cap + __shfl_sync(FULL, off, j);
+            const uint32_t *codes = bg.codes + (size_t)(base + j) * SEG_CODE_WORDS;
+            for (int t0 = 0; t0 < jslen; t0 += 32) {
+                const int t = t0 + lane;
+                unsigned v = 0;
+                if (t < jslen) {
+                    const int so = (int)((codes[t / 10] >> (3 * (t % 10))) & 7u);
+                    v = (unsigned)(dir_dx(so) + 1) | ((unsigned)(dir_dy(so) + 1) << 16);
+                }
+                unsigned incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += u; }
+                if (t < jslen) {
+                    const unsigned excl = incl - v;                                      // sums of (d + 1) over the lane earlier points of this round
+                    const int px = cx + (int)(excl & 0xFFFFu) - lane, py = cy + (int)(excl >> 16) - lane;
+                    const int q = jpos + t;
+                    out[q < 0 ? q + jlen : q] = (uint32_t)px | ((uint32_t)py << 16);
+                }
+                const unsigned tot = __shfl_sync(FULL, incl, 31);
+                cx += (int)(tot & 0xFFFFu) - 32; cy += (int)(tot >> 16) - 32;
+            }
         }
     }
 }
@@ -966,14 +1005,15 @@ k_emit(const uint32_t *__restrict__ masks, BorderGraph bg, const uint4 *__restri
 struct WarpLanes {
     __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
     __device__ __forceinline__ int nlanes() const { return 32; }
+    // largest d (d >= 0), smallest pos among equals, on every lane: three warp reductions (REDUX) instead of five shuffle rounds
     __device__ __forceinline__ void argmax_first(long long &d, int &pos) const
     {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const long long od = __shfl_xor_sync(0xFFFFFFFFu, d, o);
-            const int op = __shfl_xor_sync(0xFFFFFFFFu, pos, o);
-            if (od > d || (od == d && op < pos)) { d = od; pos = op; }
-        }
+        const unsigned hi = (unsigned)((unsigned long long)d >> 32), lo = (unsigned)d;
+        const unsigned mh = __reduce_max_sync(0xFFFFFFFFu, hi);
+        const unsigned ml = __reduce_max_sync(0xFFFFFFFFu, hi == mh ? lo : 0u);
+        const unsigned mp = __reduce_min_sync(0xFFFFFFFFu, (hi == mh && lo == ml) ? (unsigned)pos : 0xFFFFFFFFu);
+        d = (long long)(((unsigned long long)mh << 32) | ml);
+        pos = (int)mp;
     }
 };
 
@@ -1337,7 +1377,20 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
             const double mu = otsu_mu(isum, S * S);
             __syncwarp();
             ID_MARK();
-            if (lane == 0) otsu_prefix(lo, hi, q1w);                       // running sums q1 (one add per bin)
+            if (((S * S) & (S * S - 1)) == 0) {
+                // the patch has a power-of-two number of pixels (S = 32 for the 6x6 dictionaries): 1 / n and every p_i = h_i / n are
+                // exact, so are their running sums, and the one-lane pass below equals the integer prefix scaled once
+                int run = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) run += hv[k];
+                int incl = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+                int acc = incl - run;
+                const double scale = d_div(1.0, (double)(S * S));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { acc += hv[k]; q1w[lane * 8 + k] = d_mul((double)acc, scale); }
+            } else if (lane == 0) otsu_prefix(lo, hi, q1w);                // running sums q1 (one add per bin)
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < 8; ++k) { const int i = lane * 8 + k; if (i >= lo && i <= hi) yw[i] = otsu_bin(q1w[i]); }
@@ -1361,16 +1414,16 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
             thr = best > 0 ? bi : 0;
         }
         ID_MARK();
+        unsigned long long code = 0;
+        int berr = 0;
         for (int cidx = lane; cidx < nb * nb; cidx += 32) {
             const int cy = cidx / nb, cx = cidx - cy * nb;
-            bitsw[cidx] = (uint8_t)((mode < 2) ? mode : ident_cell_bit(patchw, S, ip.cellSize, ip.cellMargin, cy, cx, thr));
+            const unsigned bit = (unsigned)((mode < 2) ? mode : ident_cell_bit(patchw, S, ip.cellSize, ip.cellMargin, cy, cx, thr));
+            ident_cell_accumulate(cidx, bit, ip.markerSize, ip.borderBits, berr, code);
         }
-        __syncwarp();
-        unsigned long long code = 0;
-        int ok = 0;
-        if (lane == 0) ok = ident_border_code(bitsw, ip.markerSize, ip.borderBits, ip.maxBorderErr, code) ? 1 : 0;
-        ok = __shfl_sync(FULL, ok, 0);
-        code = __shfl_sync(FULL, code, 0);
+        berr = __reduce_add_sync(FULL, berr);
+        code = ((unsigned long long)__reduce_or_sync(FULL, (unsigned)(code >> 32)) << 32) | __reduce_or_sync(FULL, (unsigned)code);
+        const int ok = berr <= ip.maxBorderErr;
         int best_m = 0x7FFFFFFF;
         if (ok) {
             for (int m = lane; m < ip.nMarkers; m += 32) {

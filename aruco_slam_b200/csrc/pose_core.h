@@ -230,12 +230,28 @@ B2A_HD void pose_row(const Camera &cam, double h, const float *corners, const do
     }
 }
 
+// 10^k for k in [-16, 16] (a table in constant memory on the device: building it on the stack in every LM step cost 6 % of k_pose)
+#define B2A_P10_VALUES {1e-16, 1e-15, 1e-14, 1e-13, 1e-12, 1e-11, 1e-10, 1e-9, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, 1e0, \
+                        1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16}
+#if defined(__CUDACC__)
+__device__ __constant__ double k_p10_device[33] = B2A_P10_VALUES;
+#endif
+B2A_HD double pow10_table(int k)
+{
+#if defined(__CUDA_ARCH__)
+    return k_p10_device[k + 16];
+#else
+    const double p10[33] = B2A_P10_VALUES;
+    return p10[k + 16];
+#endif
+}
+
 // one LM trial step of OpenCV's CvLevMarq::step(): p = prev - (JtJ with diagonal * (1 + 10^lg))^-1 JtErr
 // LDL^T solve of the 6x6 symmetric positive definite LM system (upper part of M is not read);
 // false if a pivot is not positive.  (CvLevMarq solves the same system by SVD; only the solution matters.)
 B2A_HD bool solve_spd6(const double *M, double *d)
 {
-    double L[36], D[6];
+    double L[36], D[6], Dinv[6];
     B2A_UNROLL
     for (int j = 0; j < 6; ++j) {
         double v = M[j * 6 + j];
@@ -244,6 +260,7 @@ B2A_HD bool solve_spd6(const double *M, double *d)
         if (!(v > 0)) return false;
         D[j] = v;
         const double inv = 1. / v;
+        Dinv[j] = inv;
         B2A_UNROLL
         for (int i = j + 1; i < 6; ++i) {
             double t = M[i * 6 + j];
@@ -258,7 +275,7 @@ B2A_HD bool solve_spd6(const double *M, double *d)
         d[j] = y;
     }
     B2A_UNROLL
-    for (int j = 0; j < 6; ++j) d[j] = d[j] / D[j];
+    for (int j = 0; j < 6; ++j) d[j] = d[j] * Dinv[j];                 // the pivots' reciprocals are already there (one rounding more than a division; the LM iteration absorbs it)
     B2A_UNROLL
     for (int j = 5; j >= 0; --j) {
         double x = d[j];
@@ -274,10 +291,8 @@ B2A_HD void lm_step(const double *shN /* [6][7]: JtJ row | JtErr */, int lambdaL
 {
     double M[36], d[6];
     // CvLevMarq: lambda = exp(lambdaLg10 * log(10)), lambdaLg10 in [-16, 16]
-    const double p10[33] = {1e-16, 1e-15, 1e-14, 1e-13, 1e-12, 1e-11, 1e-10, 1e-9, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, 1e0,
-                            1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16};
     const int li = lambdaLg10 < -16 ? -16 : (lambdaLg10 > 16 ? 16 : lambdaLg10);
-    const double lambda = p10[li + 16];
+    const double lambda = pow10_table(li);
     B2A_UNROLL
     for (int a = 0; a < 6; ++a) {
         B2A_UNROLL
