@@ -943,44 +943,62 @@ k_emit(const uint32_t *__restrict__ masks, BorderGraph bg, const uint4 *__restri
        uint32_t *__restrict__ pts, const WalkTables *__restrict__ tables, DetGeom g)
 {
     __shared__ __align__(16) uint16_t s_succ[4096];
+    __shared__ __align__(16) uint32_t s_codes[8][32][SEG_CODE_WORDS];       // the direction codes of the 32 anchors a warp is working on
     constexpr unsigned FULL = 0xFFFFFFFFu;
     unsigned n = *bg.n_anchors;
     if (n > bg.cap) n = bg.cap;
     if (blockIdx.x * blockDim.x >= n) return;
     load_walk_tables(tables, s_succ, nullptr);
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // code word and shift of the points lane, lane + 32, lane + 64 of a segment
+    int cw_idx[3], cw_sh[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { const int t = 32 * r + lane; cw_idx[r] = t / 10; cw_sh[r] = 3 * (t - 10 * cw_idx[r]); }
     for (unsigned base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
         const unsigned i = base + lane;
-        int pos = 0, len = 0, off = 0, slen = 0, fs = 0, x0 = 0, y0 = 0;
+        int pos = 0, lens = 0;                 // lens = border length | segment length << 24
+        uint32_t xy = 0, obase = 0;
         bool coop = false;
+        __syncwarp();                           // the previous 32 anchors' codes have been consumed
         if (i < n) {
             const int2 e = bg.emit[i];
             if (e.y != 0) {
                 const uint2 a = bg.ast[i];
-                fs = (int)(a.y >> 4);
-                len = (int)__ldg(&sorted[e.y - 1].y); off = __ldg(&pts_off[e.y - 1]);
-                slen = (int)(bg.seg[i].len & SEG_LEN);
-                pos = e.x; x0 = (int)(a.x & 0xFFFFu); y0 = (int)(a.x >> 16);
+                const int fs = (int)(a.y >> 4);
+                const int len = (int)__ldg(&sorted[e.y - 1].y), off = __ldg(&pts_off[e.y - 1]);
+                const int slen = (int)(bg.seg[i].len & SEG_LEN);
+                pos = e.x; xy = a.x;
+                obase = (uint32_t)fs * (uint32_t)g.pts_cap + (uint32_t)off;
                 coop = slen <= SEG_CODE_WORDS * 10;
-                if (!coop) {
+                if (coop) {
+                    lens = len | (slen << 24);
+                    const uint4 *cp = reinterpret_cast<const uint4 *>(bg.codes + (size_t)i * SEG_CODE_WORDS);
+                    uint4 *sp = reinterpret_cast<uint4 *>(&s_codes[warp][lane][0]);
+                    sp[0] = __ldg(cp);
+                    if (slen > 40) sp[1] = __ldg(cp + 1);
+                } else {
                     MaskView rd{masks + (size_t)fs * g.mask_plane, g.PWW};
-                    seg_emit(rd, s_succ, x0, y0, (int)(a.y & 7u), slen, pos, len, pts + (size_t)fs * g.pts_cap + off);
+                    seg_emit(rd, s_succ, (int)(a.x & 0xFFFFu), (int)(a.x >> 16), (int)(a.y & 7u), slen, pos, len, pts + obase);
                 }
             }
         }
+        __syncwarp();
         unsigned todo = __ballot_sync(FULL, coop);
         while (todo) {
             const int j = __ffs(todo) - 1;
             todo &= todo - 1;
-            const int jpos = __shfl_sync(FULL, pos, j), jlen = __shfl_sync(FULL, len, j), jslen = __shfl_sync(FULL, slen, j);
-            int cx = __shfl_sync(FULL, x0, j), cy = __shfl_sync(FULL, y0, j);            // point 32 * round of the segment
-            uint32_t *out = pts + (size_t)__shfl_sync(FULL, fs, j) * g.pts_cap + __shfl_sync(FULL, off, j);
-            const uint32_t *codes = bg.codes + (size_t)(base + j) * SEG_CODE_WORDS;
-            for (int t0 = 0; t0 < jslen; t0 += 32) {
-                const int t = t0 + lane;
+            const int jpos = __shfl_sync(FULL, pos, j), jl = __shfl_sync(FULL, lens, j);
+            const uint32_t jxy = __shfl_sync(FULL, xy, j);
+            uint32_t *out = pts + __shfl_sync(FULL, obase, j);
+            const int jlen = jl & 0xFFFFFF, jslen = jl >> 24;
+            int cx = (int)(jxy & 0xFFFFu), cy = (int)(jxy >> 16);                          // point 32 * round of the segment
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                if (32 * r >= jslen) break;
+                const int t = 32 * r + lane;
                 unsigned v = 0;
                 if (t < jslen) {
-                    const int so = (int)((codes[t / 10] >> (3 * (t % 10))) & 7u);
+                    const int so = (int)((s_codes[warp][j][cw_idx[r]] >> cw_sh[r]) & 7u);
                     v = (unsigned)(dir_dx(so) + 1) | ((unsigned)(dir_dy(so) + 1) << 16);
                 }
                 unsigned incl = v;
@@ -992,8 +1010,10 @@ k_emit(const uint32_t *__restrict__ masks, BorderGraph bg, const uint4 *__restri
                     const int q = jpos + t;
                     out[q < 0 ? q + jlen : q] = (uint32_t)px | ((uint32_t)py << 16);
                 }
-                const unsigned tot = __shfl_sync(FULL, incl, 31);
-                cx += (int)(tot & 0xFFFFu) - 32; cy += (int)(tot >> 16) - 32;
+                if (32 * (r + 1) < jslen) {
+                    const unsigned tot = __shfl_sync(FULL, incl, 31);
+                    cx += (int)(tot & 0xFFFFu) - 32; cy += (int)(tot >> 16) - 32;
+                }
             }
         }
     }
