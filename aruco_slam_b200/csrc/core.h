@@ -140,6 +140,36 @@ struct MaskView {
     }
 };
 
+// The same 3x3 window for a border walk: consecutive pixels of a walk are neighbours, so the three 64-bit row pieces of the
+// previous step are kept and a step loads at most one new row (two words) instead of six words with three row addresses.
+// A piece covers the pixels 32 w - 31 .. 32 w + 32; it is kept while the window's first bit stays inside its first 62 bits
+// (hysteresis: a border that wiggles across a word boundary does not reload every step).
+struct CachedMaskView {
+    const uint32_t *plane;
+    int PWW;
+    mutable int cy, cw;                           // rows cy - 1, cy, cy + 1 from word index cw (cw < 0: nothing cached)
+    mutable unsigned long long r0, r1, r2;
+    B2A_HD CachedMaskView(const uint32_t *plane_, int PWW_) : plane(plane_), PWW(PWW_), cy(0), cw(-1), r0(0), r1(0), r2(0) {}
+    B2A_HD unsigned long long piece(int y, int w) const
+    {
+        const uint32_t *row = plane + (size_t)(y + 1) * PWW + w;
+        return (unsigned long long)ld_ro(row) | ((unsigned long long)ld_ro(row + 1) << 32);
+    }
+    B2A_HD unsigned win9(int x, int y) const
+    {
+        const int bit = x + 31;                                   // padded bit position of pixel x - 1
+        int rel = bit - (cw << 5);
+        const int dy = y - cy;
+        if (cw < 0 || (unsigned)rel > 61u || (unsigned)(dy + 1) > 2u) {
+            cw = bit >> 5; rel = bit & 31;
+            r0 = piece(y - 1, cw); r1 = piece(y, cw); r2 = piece(y + 1, cw);
+        } else if (dy == 1) { r0 = r1; r1 = r2; r2 = piece(y + 1, cw); }
+        else if (dy == -1) { r2 = r1; r1 = r0; r0 = piece(y - 1, cw); }
+        cy = y;
+        return ((unsigned)(r0 >> rel) & 7u) | (((unsigned)(r1 >> rel) & 7u) << 3) | (((unsigned)(r2 >> rel) & 7u) << 6);
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Border graph.  The states that lie on borders are locally enumerable (checked against
 // cv2.findContours on every golden mask and on random masks: the state set below has exactly
@@ -354,12 +384,14 @@ B2A_HD void seg_emit(const Win &win, const uint16_t *__restrict__ succ, int x, i
 // Returns the border length if the border carries no anchor and (x0,y0,s0) is its first state;
 // 0 as soon as an anchor or a start-eligible state with a smaller key is met (the border is then
 // reported through its anchors, or by that other state); -1 when undecided after max_len steps.
+// (winf / winb: the window views of the forward and of the backward walker -- two objects so that a caching view keeps one
+// neighbourhood per walker; a stateless view can be passed twice)
 template <class Win>
-B2A_HD int direct_walk(const Win &win, const uint16_t *__restrict__ succ, const uint16_t *__restrict__ pred, int KS, int Rm,
+B2A_HD int direct_walk(const Win &winf, const Win &winb, const uint16_t *__restrict__ succ, const uint16_t *__restrict__ pred, int KS, int Rm,
                        int x0, int y0, int s0, uint32_t key0, int max_len)
 {
     int xf = x0, yf = y0, sf = s0, xb = x0, yb = y0, sb = s0;
-    const unsigned e0 = succ[win.win9(x0, y0) | ((unsigned)s0 << 9)];
+    const unsigned e0 = succ[winf.win9(x0, y0) | ((unsigned)s0 << 9)];
     if (is_anchor(e0, x0, y0, Rm)) return 0;
     int so = (int)(e0 & 7u);
     int n = 0;
@@ -368,7 +400,7 @@ B2A_HD int direct_walk(const Win &win, const uint16_t *__restrict__ succ, const 
         ++n;
         if (xf == xb && yf == yb && sf == sb) return n;
         const int xp = xb + dir_dx(sb), yp = yb + dir_dy(sb);
-        const unsigned wf = win.win9(xf, yf), wp = win.win9(xp, yp);       // twelve independent loads in flight
+        const unsigned wf = winf.win9(xf, yf), wp = winb.win9(xp, yp);
         const unsigned ef = succ[wf | ((unsigned)sf << 9)], ep = pred[wp | ((unsigned)(sb ^ 4) << 9)];
         if (is_anchor(ef, xf, yf, Rm) || ((ef & WT_ELIG) && key_of(xf, yf, ef, KS) < key0)) return 0;
         if (n > max_len) return -1;

@@ -155,6 +155,15 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
             CheckedView cv{pl, PWW, W, H};
             seg_walk(cv, wt.succ, KS, Rm, max_len, x, y, st, len, mk, mo, codes.data() + (size_t)i * SEG_CODE_WORDS);
             if (cv.bad) return -106;
+            {   // the kernel walks with the cached window (CachedMaskView): same segment, same codes
+                int x2 = (int)ax[i], y2 = (int)ay[i], st2 = (int)as_[i];
+                uint32_t len2, mk2, mo2, codes2[SEG_CODE_WORDS] = {0};
+                CachedMaskView cached(pl, PWW);
+                seg_walk(cached, wt.succ, KS, Rm, max_len, x2, y2, st2, len2, mk2, mo2, codes2);
+                if (len2 != len || mk2 != mk || mo2 != mo || x2 != x || y2 != y || st2 != st) return -116;
+                const int nw = len < (uint32_t)(SEG_CODE_WORDS * 10) ? (int)((len + 9) / 10) : SEG_CODE_WORDS;
+                for (int k = 0; k < nw; ++k) if (codes2[k] != codes[(size_t)i * SEG_CODE_WORDS + k]) return -117;
+            }
             seg[i].len = len | (asup[i] ? SEG_SUPER : 0u); seg[i].minkey = mk; minoff[i] = mo;
             if (len == SEG_OVERFLOW) { if (device_like) continue; return -101; }
             const uint32_t base = amap[(size_t)y * WW + (x >> 5)];
@@ -194,8 +203,12 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
             if (!(e0 & WT_ELIG)) return -113;
             const uint32_t key0 = key_of(x, y, e0, KS);
             CheckedView cv{pl, PWW, W, H};
-            const int len = direct_walk(cv, wt.succ, wt.pred, KS, Rm, x, y, s0, key0, max_len);
+            const int len = direct_walk(cv, cv, wt.succ, wt.pred, KS, Rm, x, y, s0, key0, max_len);
             if (cv.bad) return -114;
+            {   // the kernel's dense walks use one cached window per walker
+                const CachedMaskView wf(pl, PWW), wb(pl, PWW);
+                if (direct_walk(wf, wb, wt.succ, wt.pred, KS, Rm, x, y, s0, key0, max_len) != len) return -118;
+            }
             if (std::getenv("EMU_WALK_STATS")) { static long tot = 0, mx = 0, cnt = 0, big = 0; tot += cv.calls; cnt++; if (cv.calls > mx) mx = cv.calls; if (cv.calls > 40) big++;
                 if (c + 1 == cx.size()) std::fprintf(stderr, "scale %d: %ld candidates, window reads total %ld max %ld, >40 reads: %ld\n", s, cnt, tot, mx, big); }
             if (len <= 0) continue;
