@@ -525,14 +525,17 @@ B2A_HD int approx_closed(const LG &lg, const uint32_t *__restrict__ P, int count
         uint32_t bd32 = 0; int bj = 0x7FFFFFFF;
         for (int j0 = 1 + lane; j0 < count; j0 += 4 * nl) {          // four points per lane in flight
             uint32_t q[4];
+            const int jb = j0 - lane;                                // same on every lane: slots past the end are skipped by the whole group
             B2A_UNROLL
             for (int k = 0; k < 4; ++k) {
+                if (jb + k * nl >= count) break;
                 const int j = j0 + k * nl;
                 int idx = pos + j - 1; if (idx >= count) idx -= count;
                 q[k] = j < count ? P[idx] : 0u;
             }
             B2A_UNROLL
             for (int k = 0; k < 4; ++k) {
+                if (jb + k * nl >= count) break;
                 const int j = j0 + k * nl;
                 const int dx = px_of(q[k]) - sx, dy = py_of(q[k]) - sy;
                 const uint32_t d = (uint32_t)(dx * dx) + (uint32_t)(dy * dy);
@@ -569,14 +572,17 @@ B2A_HD int approx_closed(const LG &lg, const uint32_t *__restrict__ P, int count
             unsigned long long bdu = 0; int bt = 0x7FFFFFFF;
             for (int t0 = lane; t0 < inner; t0 += 4 * nl) {            // four points per lane in flight
                 uint32_t qq[4];
+                const int tb = t0 - lane;                            // same on every lane
                 B2A_UNROLL
                 for (int k = 0; k < 4; ++k) {
+                    if (tb + k * nl >= inner) break;
                     const int t = t0 + k * nl;
                     int idx = s + 1 + t; if (idx >= count) idx -= count;
                     qq[k] = t < inner ? P[idx] : 0u;
                 }
                 B2A_UNROLL
                 for (int k = 0; k < 4; ++k) {
+                    if (tb + k * nl >= inner) break;
                     const int t = t0 + k * nl;
                     const int px = px_of(qq[k]) - sx, py = py_of(qq[k]) - sy;
                     const int dot = px * dx + py * dy;
