@@ -540,7 +540,8 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     bg.starts = d->d_starts + (size_t)s.sb * (d->starts_cap / (unsigned)d->n_sub_max); bg.n_starts = d->d_counters2 + s.sb;
     bg.starts_cap = d->starts_cap / (unsigned)d->n_sub_max;
     const int Rm = d->anchor_R - 1, Rm2 = 8 * d->anchor_R - 1, max_len = walk_max_len > 0 ? walk_max_len : g.maxPerim;
-    const unsigned walk_grid = (unsigned)d->num_sms * 8;
+    static const int walk_ctas = std::getenv("B2A_WALK_CTAS") ? std::max(1, std::atoi(std::getenv("B2A_WALK_CTAS"))) : 8;   // resident 256-thread CTAs per SM of the grid-stride kernels
+    const unsigned walk_grid = (unsigned)d->num_sms * walk_ctas;
     uint32_t *masks = d->d_masks + fs0 * g.mask_plane;
     stage_mark(d, s, ST_THRESH);
     {
@@ -570,7 +571,7 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
         d->launches++;
     }
     stage_mark(d, s, ST_ANCHORS);
-    k_anchors<<<d->num_sms * 8, 256, 0, st>>>(masks, bg, d->d_iso_count + fs0, Rm, Rm2, g);
+    k_anchors<<<walk_grid, 256, 0, st>>>(masks, bg, d->d_iso_count + fs0, Rm, Rm2, g);
     d->launches++; DBG_SYNC(st);
     stage_mark(d, s, ST_SEGMENTS);
     k_segments<<<walk_grid, 256, 0, st>>>(masks, bg, max_len, d->d_tables, Rm, g);

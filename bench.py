@@ -241,6 +241,7 @@ def main():
     ap.add_argument("--ekf-landmarks", type=int, default=500)
     ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipelined", action="store_true", help="skip the two-handle / two-thread extra (use under ncu: the profiler serialises the two threads' launches)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -371,7 +372,7 @@ def main():
     # pinned memory), so one batch's PCIe copy overlaps the other's kernels -- the streaming / multi-camera way to drive
     # the same public call.  Wall clock around K steps with all results read; reported beside e2e, not instead of it.
     e2e_pipelined = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_pipelined:
         from concurrent.futures import ThreadPoolExecutor
         det2 = aruco.ArucoDetector(dic, max_shape=(H, W), max_batch=B, device=local_rank)
         dets = (det, det2)
