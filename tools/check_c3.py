@@ -9,7 +9,9 @@ seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 frames = np.stack([synth.render_config("C3", seed0 + i).image for i in range(B)])
 dic = D.getPredefinedDictionary(D.DICT_6X6_250)
 det = aruco.ArucoDetector(dic, max_shape=frames.shape[1:], max_batch=B, device=0)
-K = np.array([[1400.0, 0, 960], [0, 1400.0, 540], [0, 0, 1]]); Dc = np.array([0.05, -0.1, 0.001, -0.002, 0.02])
+_H, _W = frames.shape[1:]
+_f = 1400.0 * _W / 1920.0                                  # the bench's camera: ~70 degree field of view centred on the frame (the distortion model is only sane inside it)
+K = np.array([[_f, 0, _W / 2.0], [0, _f, _H / 2.0], [0, 0, 1]]); Dc = np.array([0.05, -0.1, 0.001, -0.002, 0.02])
 r = det.detect_pose_batch(frames, 0.27, K, Dc)
 bad = []
 for b in range(B):
