@@ -1149,6 +1149,18 @@ struct BlockCtx {
     __device__ __forceinline__ uint32_t ballot(bool p) const { return __ballot_sync(0xFFFFFFFFu, p); }
     __device__ __forceinline__ uint32_t warp_or(uint32_t v) const { return __reduce_or_sync(0xFFFFFFFFu, v); }
     __device__ __forceinline__ void atomic_or(uint32_t *p, uint32_t v) const { atomicOr(p, v); }
+    __device__ __forceinline__ int block_sum(int v) const        // same value on every thread
+    {
+        v = __reduce_add_sync(0xFFFFFFFFu, v);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        __syncthreads();
+        if (lane == 0) s_warp[warp] = v;
+        __syncthreads();
+        int tot = 0;
+        for (int w = 0; w < nw; ++w) tot += s_warp[w];
+        __syncthreads();
+        return tot;
+    }
     __device__ __forceinline__ int exclusive_scan(int flag, int &total) const
     {
         const unsigned m = __ballot_sync(0xFFFFFFFFu, flag != 0);

@@ -337,8 +337,8 @@ struct FrameOutputs {
     int32_t *status;       // [1]
 };
 
-// A6 + output: the acceptance order is decided by one lane (a few dozen entries), then all threads
-// copy the accepted / rejected quads to their output slots
+// A6 + output: the depth-ordered acceptance and the output slots by all threads (parallel steps per depth level, ranks by
+// block-wide scans), then all threads copy the accepted / rejected quads to their output slots
 template <class Ctx>
 B2A_HD void frame_finalize(Ctx &ctx, const FrameParams &fp, const FrameScratch &fs, const FrameOutputs &fo)
 {
@@ -357,33 +357,49 @@ B2A_HD void frame_finalize(Ctx &ctx, const FrameParams &fp, const FrameScratch &
         valid[v] = ok; chosen[v] = ch; was[v] = 0;
     }
     ctx.sync();
+    // The depth-ordered loop of identifyCandidates, all threads.  What the order decides is only `counter` (a candidate counts
+    // once at its own depth level and once more when a valid descendant marks it first) and with it how many depth levels are
+    // reached; within a level the marks are a set union, so the level is done in three parallel steps.
+    int maxDepth = 0;
+    for (int v = 0; v < nS; ++v) if (fs.depth[v] > maxDepth) maxDepth = fs.depth[v];
+    int counter = 0;
+    for (int depth = 0; counter < nS && depth <= maxDepth; ++depth) {
+        int mine = 0;
+        for (int v = ctx.tid(); v < nS; v += ctx.nthreads()) {
+            if (fs.depth[v] != depth) continue;
+            was[v] = 1;
+            if (valid[v] == 2) valid[v] = 1;
+            ++mine;
+        }
+        ctx.sync();
+        for (int v = ctx.tid(); v < nS; v += ctx.nthreads()) {
+            if (fs.depth[v] != depth || valid[v] != 1) continue;
+            for (int par = fs.parent[v]; par != -1; par = fs.parent[par]) if (was[par] == 0) was[par] = 2;     // 2 = first marked in this level (racing writers agree)
+        }
+        ctx.sync();
+        for (int v = ctx.tid(); v < nS; v += ctx.nthreads()) if (was[v] == 2) { was[v] = 1; ++mine; }
+        counter += ctx.block_sum(mine);
+    }
+    for (int v = ctx.tid(); v < nS; v += ctx.nthreads()) if (valid[v] != 1) valid[v] = 0;        // never reached (the counter ran out first)
+    ctx.sync();
+    // output slots in candidate order: accepted and rejected candidates each get their rank
+    int na = 0, nr = 0;
+    for (int base = 0; base < nS; base += ctx.nthreads()) {
+        const int v = base + ctx.tid();
+        const bool isv = v < nS && valid[v] != 0, isr = v < nS && valid[v] == 0;
+        int totv, totr;
+        const int rv = ctx.exclusive_scan(isv ? 1 : 0, totv), rr = ctx.exclusive_scan(isr ? 1 : 0, totr);
+        if (isv) was[v] = (na + rv < fp.max_markers) ? na + rv : -1;
+        if (isr) was[v] = (nr + rr < fp.max_markers) ? -(nr + rr) - 2 : -1;
+        na += totv; nr += totr;
+    }
     if (ctx.tid() == 0) {
-        int maxDepth = 0;
-        for (int v = 0; v < nS; ++v) if (fs.depth[v] > maxDepth) maxDepth = fs.depth[v];
-        int counter = 0;
-        for (int depth = 0; counter < nS && depth <= maxDepth; ++depth) {
-            for (int v = 0; v < nS; ++v) {
-                if (fs.depth[v] != depth) continue;
-                was[v] = 1;
-                if (valid[v] == 2) valid[v] = 1;
-            }
-            for (int v = 0; v < nS; ++v) {
-                if (fs.depth[v] != depth) continue;
-                if (valid[v] == 1) {
-                    int par = fs.parent[v];
-                    while (par != -1) { if (!was[par]) { was[par] = 1; ++counter; } par = fs.parent[par]; }
-                }
-                ++counter;
-            }
-        }
-        for (int v = 0; v < nS; ++v) if (valid[v] != 1) valid[v] = 0;        // never reached (the counter ran out first)
-        int na = 0, nr = 0, status = fs.counters[FC_STATUS];
+        int status = fs.counters[FC_STATUS];
         if (*fo.status != 0) status = *fo.status;               // overflow flagged by an earlier stage
-        for (int v = 0; v < nS; ++v) {
-            if (valid[v]) { if (na < fp.max_markers) was[v] = na++; else { was[v] = -1; status = 3; } }
-            else { if (nr < fp.max_markers) was[v] = -(nr++) - 2; else { was[v] = -1; status = 3; } }
-        }
-        *fo.n_accepted = na; *fo.n_rejected = nr; *fo.status = status;
+        if (na > fp.max_markers || nr > fp.max_markers) status = 3;
+        *fo.n_accepted = na < fp.max_markers ? na : fp.max_markers;
+        *fo.n_rejected = nr < fp.max_markers ? nr : fp.max_markers;
+        *fo.status = status;
     }
     ctx.sync();
     for (int v = ctx.tid(); v < nS; v += ctx.nthreads()) {

@@ -30,6 +30,7 @@ struct HostCtx {
     uint32_t warp_or(uint32_t v) const { return v; }
     void atomic_or(uint32_t *p, uint32_t v) const { *p |= v; }
     int exclusive_scan(int flag, int &total) const { total = flag ? 1 : 0; return 0; }
+    int block_sum(int v) const { return v; }
 };
 
 // MaskView with a bounds check (a walk must never leave the padded plane)
