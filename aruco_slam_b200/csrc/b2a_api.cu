@@ -114,7 +114,7 @@ extern "C" int b2a_get_predefined_dictionary(int dict_id, b2a_dictionary *out)
 // ------------------------------------------------------------------------------------------------
 // pose / observation kernels
 // ------------------------------------------------------------------------------------------------
-// 8 lanes per marker (one per row of the reprojection system), 16 markers per CTA
+// 8 lanes per marker (one per row of the reprojection system), one marker per warp
 constexpr int POSE_THREADS = 128;
 struct Lanes8 {
     long long *marks = nullptr; mutable int nmark = 0;       // debug: clock64 trace of one marker
@@ -127,15 +127,17 @@ __global__ void __launch_bounds__(POSE_THREADS)
 k_pose(const float *__restrict__ corners, const int32_t *__restrict__ n_acc, int B, int max_markers,
        Camera cam, float marker_length, double *__restrict__ rvecs, double *__restrict__ tvecs, long long *marks)
 {
-    __shared__ double s_sh[POSE_THREADS / 8][POSE_SH];
+    // one marker per WARP (its lanes 0-7): markers take different numbers of LM trials, and four markers in one warp would
+    // execute each other's divergent paths one after the other
+    __shared__ double s_sh[POSE_THREADS / 32][POSE_SH];
     const int total = B * max_markers;
-    const int t = (int)((blockIdx.x * (unsigned)POSE_THREADS + threadIdx.x) >> 3);      // marker slot of this lane group
-    if (t >= total) return;
+    const int t = (int)((blockIdx.x * (unsigned)POSE_THREADS + threadIdx.x) >> 5);      // marker slot of this warp
+    if (t >= total || (threadIdx.x & 31) >= 8) return;
     const int f = t / max_markers, m = t - f * max_markers;
     if (n_acc && m >= n_acc[f]) return;
     Lanes8 lg;
     if (marks && t == 0) { lg.marks = marks; lg.mark(); }
-    solve_marker_pose(lg, cam, marker_length, corners + (size_t)t * 8, s_sh[threadIdx.x >> 3], rvecs + (size_t)t * 3, tvecs + (size_t)t * 3);
+    solve_marker_pose(lg, cam, marker_length, corners + (size_t)t * 8, s_sh[threadIdx.x >> 5], rvecs + (size_t)t * 3, tvecs + (size_t)t * 3);
 }
 
 // Results go straight into the caller-visible pinned host arrays (device-accessible under unified
@@ -707,7 +709,7 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
         pose_marks = pose_marks_buf;
     }
     if (cam) {
-        k_pose<<<(nb * (int)K * 8 + POSE_THREADS - 1) / POSE_THREADS, POSE_THREADS, 0, st>>>(corners, fa.fo0.n_accepted, nb, d->max_markers, to_camera(cam), cam->marker_length,
+        k_pose<<<(nb * (int)K * 32 + POSE_THREADS - 1) / POSE_THREADS, POSE_THREADS, 0, st>>>(corners, fa.fo0.n_accepted, nb, d->max_markers, to_camera(cam), cam->marker_length,
                                                         d->d_rvecs + (size_t)b0 * K * 3, d->d_tvecs + (size_t)b0 * K * 3, pose_marks);
         d->launches++;
         if (pose_marks) {
@@ -862,7 +864,7 @@ extern "C" int b2a_estimate_pose_single_markers(b2a_detector *d, const float *co
     CU(cudaMalloc(&dt, (size_t)n * 3 * sizeof(double)));
     cudaStream_t st = d->stream;
     cudaMemcpyAsync(dc, corners, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice, st);
-    k_pose<<<(n * 8 + POSE_THREADS - 1) / POSE_THREADS, POSE_THREADS, 0, st>>>(dc, nullptr, 1, n, to_camera(cam), cam->marker_length, dr, dt, nullptr);
+    k_pose<<<(n * 32 + POSE_THREADS - 1) / POSE_THREADS, POSE_THREADS, 0, st>>>(dc, nullptr, 1, n, to_camera(cam), cam->marker_length, dr, dt, nullptr);
     cudaMemcpyAsync(rvecs, dr, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(tvecs, dt, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
