@@ -374,7 +374,6 @@ extern "C" int b2a_detector_create(const b2a_detector_config *cfg, const b2a_dic
     if (cfg->device < 0 || cfg->device >= ndev) return set_err(B2A_ERR_INVALID, "bad device ordinal");
     b2a_detector_params prm;
     if (params) prm = *params; else b2a_default_detector_params(&prm);
-    if (prm.detectInvertedMarker) return set_err(B2A_ERR_UNSUPPORTED, "detectInvertedMarker");
     if (prm.markerBorderBits < 1) return set_err(B2A_ERR_INVALID, "markerBorderBits < 1");
     if (prm.adaptiveThreshWinSizeMin < 3 || prm.adaptiveThreshWinSizeMax < prm.adaptiveThreshWinSizeMin || prm.adaptiveThreshWinSizeStep <= 0)
         return set_err(B2A_ERR_INVALID, "adaptiveThreshWinSize*");
@@ -610,6 +609,7 @@ static FrameParams frame_params(const b2a_detector *d, const DetGeom &g)
     fp.W = g.W; fp.H = g.H; fp.nScales = g.nScales; fp.surv_cap = g.surv_cap; fp.max_cand = d->max_cand; fp.max_markers = d->max_markers;
     fp.markerSize = d->dict.markerSize; fp.borderBits = d->prm.markerBorderBits; fp.minDistanceToBorder = d->prm.minDistanceToBorder;
     fp.minMarkerDistanceRate = (float)d->prm.minMarkerDistanceRate; fp.minGroupDistance = d->prm.minGroupDistance;
+    fp.detectInverted = d->prm.detectInvertedMarker ? 1 : 0;
     return fp;
 }
 
@@ -655,6 +655,7 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
     ip.cellMargin = (int)(d->prm.perspectiveRemoveIgnoredMarginPerCell * ip.cellSize);
     ip.nMarkers = d->dict.nMarkers; ip.maxCorr = (int)((double)d->dict.maxCorrectionBits * d->prm.errorCorrectionRate);
     ip.maxBorderErr = (int)(d->dict.markerSize * d->dict.markerSize * d->prm.maxErroneousBitsInBorderRate);
+    ip.detectInverted = d->prm.detectInvertedMarker ? 1 : 0;
     ip.minOtsuStdDev = d->prm.minOtsuStdDev; ip.W = g.W; ip.H = g.H; ip.pitch = s.pitch; ip.frame_stride = s.frame_stride; ip.max_cand = d->max_cand;
     ip.marks = nullptr;
     static long long *id_marks = nullptr;

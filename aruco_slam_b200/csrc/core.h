@@ -1059,13 +1059,27 @@ B2A_HD void ident_cell_accumulate(int cidx, unsigned bit, int markerSize, int bb
     const int shift = (byte == nby - 1 && (nbits & 7)) ? ((nbits & 7) - 1 - (i & 7)) : (7 - (i & 7));
     code |= (unsigned long long)(bit != 0) << (8 * byte + shift);
 }
+// detectInvertedMarker (cv2 _identifyOneCandidate): a white marker on black is the same matrix with every bit flipped; the
+// flipped matrix is taken when its border has fewer errors.  Flipping all cells = (border cells - err) errors, code ^ all-ones.
+B2A_HD void ident_choose_inverted(int markerSize, int bb, int &err, unsigned long long &code)
+{
+    const int nb = markerSize + 2 * bb, nborder = nb * nb - markerSize * markerSize;
+    const int inv = nborder - err;
+    if (inv >= err) return;
+    err = inv;
+    int e2 = 0;
+    unsigned long long all = 0;
+    for (int c = 0; c < nb * nb; ++c) ident_cell_accumulate(c, 1u, markerSize, bb, e2, all);     // every inner cell's bit position
+    code ^= all;
+}
 // border check + code word; false = border wrong
-B2A_HD bool ident_border_code(const uint8_t *bits, int markerSize, int bb, int maxBorderErr, unsigned long long &code)
+B2A_HD bool ident_border_code(const uint8_t *bits, int markerSize, int bb, int maxBorderErr, unsigned long long &code, bool detectInverted = false)
 {
     const int nb = markerSize + 2 * bb;
     int err = 0;
     code = 0;
     for (int c = 0; c < nb * nb; ++c) ident_cell_accumulate(c, bits[c], markerSize, bb, err, code);
+    if (detectInverted) ident_choose_inverted(markerSize, bb, err, code);
     return err <= maxBorderErr;
 }
 // smallest Hamming distance of marker m over its 4 rotations (first minimum wins)

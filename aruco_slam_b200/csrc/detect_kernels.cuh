@@ -1285,7 +1285,7 @@ k_finalize(FrameArrays fa, FrameParams fp)
 // ---------------------------------------------------------------------------------------------
 struct IdentParams {
     int markerSize, borderBits, cellSize, cellMargin;
-    int nMarkers, maxCorr, maxBorderErr;
+    int nMarkers, maxCorr, maxBorderErr, detectInverted;
     double minOtsuStdDev;
     int W, H;
     size_t pitch, frame_stride;
@@ -1457,6 +1457,7 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
         }
         berr = __reduce_add_sync(FULL, berr);
         code = ((unsigned long long)__reduce_or_sync(FULL, (unsigned)(code >> 32)) << 32) | __reduce_or_sync(FULL, (unsigned)code);
+        if (ip.detectInverted) ident_choose_inverted(ip.markerSize, ip.borderBits, berr, code);
         const int ok = berr <= ip.maxBorderErr;
         int best_m = 0x7FFFFFFF;
         if (ok) {

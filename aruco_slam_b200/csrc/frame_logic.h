@@ -21,6 +21,7 @@ struct FrameParams {
     int minDistanceToBorder;
     float minMarkerDistanceRate;   // (float)params.minMarkerDistanceRate
     float minGroupDistance;
+    int detectInverted;      // detectInvertedMarker: a group is walked from its smallest contour (cv2 sorts the group descending)
 };
 
 // per-(frame,scale) outputs of the contour / polygon stages, in cv2.findContours list order
@@ -237,10 +238,12 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
     // ---- 5. per group: representative + close contours ----
     for (int g = tid; g < ng; g += nt) {
         const int b = fs.gstart[g], e = fs.gstart[g + 1];
-        int cur = fs.members[b];
+        const bool rev = fp.detectInverted != 0;
+        int cur = fs.members[rev ? e - 1 : b];
         fs.sel[cur] = 1;
         int nc = 0;
-        for (int k = b + 1; k < e; ++k) {
+        for (int kk = b + 1; kk < e; ++kk) {
+            const int k = rev ? (b + e - 1 - kk) : kk;
             const int id = fs.members[k];
             const float dist = quad_avg_distance(tq + (size_t)id * 8, tq + (size_t)cur * 8);
             const float ms = quad_module_size(tq + (size_t)id * 8, fp.markerSize, fp.borderBits);

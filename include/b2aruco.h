@@ -58,7 +58,7 @@ typedef struct {
     double relativeCornerRefinmentWinSize;        /* 0.3 */
     int    cornerRefinementMaxIterations;         /* 30 */
     double cornerRefinementMinAccuracy;           /* 0.1 */
-    int    detectInvertedMarker;                  /* 0 (1 is B2A_ERR_UNSUPPORTED) */
+    int    detectInvertedMarker;                  /* 0 */
 } b2a_detector_params;
 
 void b2a_default_detector_params(b2a_detector_params *p);

@@ -424,6 +424,11 @@ int orc_identify_one(const uint8_t *gray, int W, int H, const float *corners, co
     int err = 0;
     for (int y = 0; y < nb; y++) for (int k = 0; k < bb; k++) { err += bits[y * nb + k] != 0; err += bits[y * nb + nb - 1 - k] != 0; }
     for (int x = bb; x < nb - bb; x++) for (int k = 0; k < bb; k++) { err += bits[k * nb + x] != 0; err += bits[(nb - 1 - k) * nb + x] != 0; }
+    if (p->detectInvertedMarker) {
+        /* white marker: the inverted bit matrix is taken when its border has fewer errors (cv2 _identifyOneCandidate) */
+        int nborder = nb * nb - d->markerSize * d->markerSize, inv = nborder - err;
+        if (inv < err) { err = inv; for (int i = 0; i < nb * nb; i++) bits[i] = (uint8_t)!bits[i]; }
+    }
     if (err > maxErr) { free(bits); return 0; }
     /* pack inner bits row-major MSB first, last partial byte right-aligned */
     uint8_t code[16] = {0};

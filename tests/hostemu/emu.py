@@ -18,7 +18,7 @@ class EmuParams(C.Structure):
                 ("minMarkerDistanceRate", C.c_float), ("minGroupDistance", C.c_float),
                 ("markerSize", C.c_int), ("borderBits", C.c_int), ("cellSize", C.c_int), ("cellMargin", C.c_int),
                 ("nMarkers", C.c_int), ("maxCorr", C.c_int), ("maxBorderErr", C.c_int), ("minOtsuStdDev", C.c_double),
-                ("max_cand", C.c_int), ("max_markers", C.c_int), ("surv_cap", C.c_int)]
+                ("max_cand", C.c_int), ("max_markers", C.c_int), ("surv_cap", C.c_int), ("detectInverted", C.c_int)]
 
 
 def build():
@@ -46,7 +46,7 @@ def pack_dict(dic):
     return np.ascontiguousarray(out)
 
 
-def params_for(dic, max_cand=2048, max_markers=256, surv_cap=4096):
+def params_for(dic, max_cand=2048, max_markers=256, surv_cap=4096, detect_inverted=False):
     p = EmuParams()
     p.nScales = 3
     for i, r in enumerate((1, 6, 11)):
@@ -61,13 +61,14 @@ def params_for(dic, max_cand=2048, max_markers=256, surv_cap=4096):
     p.maxBorderErr = int(dic.marker_size * dic.marker_size * 0.35)
     p.minOtsuStdDev = 5.0
     p.max_cand, p.max_markers, p.surv_cap = max_cand, max_markers, surv_cap
+    p.detectInverted = 1 if detect_inverted else 0
     return p
 
 
-def detect(gray, dic, masks=None, dbg_scale=-1, anchor_R=32):
+def detect(gray, dic, masks=None, dbg_scale=-1, anchor_R=32, detect_inverted=False):
     gray = np.ascontiguousarray(gray, np.uint8)
     H, W = gray.shape
-    p = params_for(dic)
+    p = params_for(dic, detect_inverted=detect_inverted)
     d = pack_dict(dic)
     n_acc, n_rej, n_cand, nk = C.c_int(), C.c_int(), C.c_int(), C.c_int()
     corners = np.zeros((p.max_markers, 4, 2), np.float32)

@@ -51,6 +51,7 @@ struct EmuParams {
     int markerSize, borderBits, cellSize, cellMargin, nMarkers, maxCorr, maxBorderErr;
     double minOtsuStdDev;
     int max_cand, max_markers, surv_cap;
+    int detectInverted;
 };
 
 // packed masks exactly as the device lays them out (the bits themselves come from a plain loop:
@@ -266,6 +267,7 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
     fp.W = W; fp.H = H; fp.nScales = nS; fp.surv_cap = surv_cap; fp.max_cand = MC; fp.max_markers = ep->max_markers;
     fp.markerSize = ep->markerSize; fp.borderBits = ep->borderBits; fp.minDistanceToBorder = ep->minDistanceToBorder;
     fp.minMarkerDistanceRate = ep->minMarkerDistanceRate; fp.minGroupDistance = ep->minGroupDistance;
+    fp.detectInverted = ep->detectInverted;
     ScaleQuads sq{s_count.data(), q_ok.data(), q_xy.data(), q_len.data()};
     HostCtx ctx;
     frame_group(ctx, fp, sq, fs, nullptr, 0, 0);
@@ -291,7 +293,7 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
         for (int c = 0; c < nb * nb; ++c) bits[c] = (uint8_t)((mode < 2) ? mode : ident_cell_bit(patch.data(), Sz, ep->cellSize, ep->cellMargin, c / nb, c % nb, thr));
         unsigned long long code;
         int res = 0;
-        if (ident_border_code(bits.data(), ep->markerSize, ep->borderBits, ep->maxBorderErr, code))
+        if (ident_border_code(bits.data(), ep->markerSize, ep->borderBits, ep->maxBorderErr, code, ep->detectInverted != 0))
             for (int m = 0; m < ep->nMarkers; ++m) {
                 int rot;
                 if (ident_marker_distance(dict + (size_t)m * 4, code, ep->markerSize, rot) <= ep->maxCorr) { res = (int)(0x80000000u | ((unsigned)m << 8) | (unsigned)rot); break; }

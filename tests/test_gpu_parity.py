@@ -91,6 +91,20 @@ def test_detect_vs_golden(aruco, name):
     det.close()
 
 
+@pytest.mark.parametrize("name", golden_names("inverted_"))
+def test_detect_inverted_vs_golden(aruco, name):
+    """detectInvertedMarker = true on the GPU path against cv2's output (bit exact, same order)"""
+    g = golden(name)
+    gray = g["frame"]
+    dic = D.getPredefinedDictionary(int(g["dict_id"]))
+    det = _detector(aruco, dic, gray.shape, detectInvertedMarker=1)
+    r = det.detect_batch(gray)
+    assert np.array_equal(r.ids[0], g["ids"])
+    assert np.array_equal(r.corners[0], g["corners"])
+    assert np.array_equal(r.rejected[0], g["rejected"])
+    det.close()
+
+
 def test_legacy_free_functions(aruco):
     g = golden("detect_vga_4x4_s2")
     dic = D.getPredefinedDictionary(int(g["dict_id"]))

@@ -28,6 +28,18 @@ def test_detect_logic_matches_golden(name):
         assert np.array_equal(r["n_contours"], g["n_contours"])
 
 
+@pytest.mark.parametrize("name", golden_names("inverted_"))
+def test_detect_inverted_logic_matches_golden(name):
+    """detectInvertedMarker = true through the product's kernel-logic headers (group walk reversed, flipped bit matrix)"""
+    g = golden(name)
+    dic = D.getPredefinedDictionary(int(g["dict_id"]))
+    r = emu.detect(g["frame"], dic, detect_inverted=True)
+    assert r["status"] == 0
+    assert np.array_equal(r["ids"], g["ids"])
+    assert np.array_equal(r["corners"], g["corners"])
+    assert np.array_equal(r["rejected"], g["rejected"])
+
+
 @pytest.mark.parametrize("name", golden_names("stages_"))
 def test_contour_points_match_golden(name):
     g = golden(name)

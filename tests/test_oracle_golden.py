@@ -71,6 +71,19 @@ def test_detect(oracle, name):
         assert np.abs(c2 - g["subpix_corners"]).max() < 1e-3
 
 
+@pytest.mark.parametrize("name", golden_names("inverted_"))
+def test_detect_inverted(oracle, name):
+    """detectInvertedMarker = true: white markers on black (and the reversed walk of every candidate group), pinned to cv2"""
+    g = golden(name)
+    dic = D.getPredefinedDictionary(int(g["dict_id"]))
+    c, ids, rej = oracle.detect(g["frame"], dic, oracle.default_params(detectInvertedMarker=1))
+    assert np.array_equal(ids, g["ids"])
+    assert np.array_equal(c, g["corners"])
+    assert np.array_equal(rej, g["rejected"])
+    if "all" in name:                                   # without the flag none of the white markers identifies
+        assert len(oracle.detect(g["frame"], dic)[1]) == 0
+
+
 def test_nested_fixture_semantics(oracle):
     """SURVEY probe P16: the enclosing big marker is never identified."""
     g = golden("detect_vga_nested")

@@ -24,10 +24,11 @@ OUT = os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
 PROV = "cv2 %s (opencv-python-headless), tools/make_golden.py" % cv2.__version__
 
 
-def cv_detect(img, dict_id, subpix=False):
+def cv_detect(img, dict_id, subpix=False, inverted=False):
     prm = A.DetectorParameters()
     if subpix:
         prm.cornerRefinementMethod = A.CORNER_REFINE_SUBPIX
+    prm.detectInvertedMarker = bool(inverted)
     det = A.ArucoDetector(A.getPredefinedDictionary(dict_id), prm)
     c, ids, rej = det.detectMarkers(img)
     c = np.array(c, np.float32).reshape(-1, 4, 2)
@@ -93,6 +94,24 @@ def detect_fixture(name, gray, dict_id, store_mask_crc=True):
         kw["mask_crc"] = np.array([zlib.crc32(m.tobytes()) for m in ms], np.uint64)
         kw["n_contours"] = np.array([len(cv2.findContours(m, cv2.RETR_LIST, cv2.CHAIN_APPROX_NONE)[0]) for m in ms], np.int32)
     save(name, **kw)
+
+
+def inverted_fixture(name, gray, dict_id):
+    """detectInvertedMarker = true (white markers on black): ids / corners / rejected of cv2 on the committed frame"""
+    c, ids, rej = cv_detect(gray, dict_id, inverted=True)
+    save(name, frame=gray, dict_id=dict_id, corners=c, ids=ids, rejected=rej)
+
+
+def inverted_frames():
+    """(name, frame, dictionary): a fully inverted frame, one with only its left half inverted (both kinds of marker in one
+    frame), a noisy inverted 6x6 frame and the normal nested fixture under the flag (the group order is reversed by it)"""
+    a = 255 - synth.render_config("C1", 6).image
+    b = synth.render_config("C1", 7).image.copy()
+    b[:, :320] = 255 - b[:, :320]
+    cfg = dict(W=960, H=540, n_markers=12, dict_id=D.DICT_6X6_250, side_range=(50.0, 110.0), noise_sigma=4.0, blur_sigma=1.0)
+    c = 255 - synth.render_frame(seed=2, **cfg).image
+    return [("inverted_vga_4x4_all", a, D.DICT_4X4_50), ("inverted_vga_4x4_half", b, D.DICT_4X4_50),
+            ("inverted_540p_6x6_noisy", c, D.DICT_6X6_250), ("inverted_vga_nested", nested_fixture(), D.DICT_4X4_50)]
 
 
 def nested_fixture():
@@ -205,6 +224,8 @@ def main():
     cfg = dict(W=333, H=251, n_markers=2, dict_id=D.DICT_5X5_100, side_range=(50.0, 80.0))
     detect_fixture("detect_odd_5x5", synth.render_frame(seed=1, **cfg).image, D.DICT_5X5_100)
     detect_fixture("detect_blank", np.full((120, 160), 128, np.uint8), D.DICT_4X4_50)
+    for name, img, did in inverted_frames():
+        inverted_fixture(name, img, did)
     pose_fixture()
     pose_detected_fixture()
     prims_fixture()
