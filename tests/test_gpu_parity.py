@@ -226,6 +226,35 @@ def test_threshold_edge_shapes(aruco, oracle):
     det.close()
 
 
+def test_threshold_device_frames_pitches(aruco, oracle):
+    """frames already in device memory: an unaligned row pitch takes the tiled kernel, a padded (4-byte aligned) pitch and a
+    frame stride take the marching kernel; both must give the oracle's masks and the same detections as host frames"""
+    import ctypes as C
+    import torch
+    from aruco_slam_b200 import _lib
+    rng = np.random.default_rng(11)
+    dic = D.getPredefinedDictionary(0)
+    H, W = 95, 257
+    imgs = rng.integers(0, 256, (2, H, W)).astype(np.uint8)
+    det = _detector(aruco, dic, (H, W), batch=2)
+    want = [[oracle.adaptive_threshold(im, k, 7.0) for k in (3, 13, 23)] for im in imgs]
+    for pitch, fstride in ((W, W * H), (260, 260 * H + 64)):
+        buf = torch.zeros(2 * fstride + 64, dtype=torch.uint8, device="cuda")
+        for b in range(2):
+            view = buf[b * fstride: b * fstride + pitch * H].view(H, pitch)
+            view[:, :W] = torch.from_numpy(imgs[b]).cuda()
+            view[:, W:] = 0xEE                                   # padding bytes must never be read as pixels
+        fr = aruco.ArucoDetector.frames_device(buf.data_ptr(), 2, H, W, 1, pitch, fstride)
+        gray = np.zeros((2, H, W), np.uint8)
+        masks = np.zeros((2, 3, H, W), np.uint8)
+        _lib.check(_lib.lib().b2a_debug_threshold(det._h, C.byref(fr), gray.ctypes.data, masks.ctypes.data))
+        assert np.array_equal(gray, imgs)
+        for b in range(2):
+            for si in range(3):
+                assert np.array_equal(masks[b, si], want[b][si]), (pitch, b, si)
+    det.close()
+
+
 def test_contours_random_masks(aruco, oracle):
     """Bernoulli masks through the contour stages (threshold of a two-level image reproduces the mask)."""
     rng = np.random.default_rng(9)
