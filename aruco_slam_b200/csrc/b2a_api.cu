@@ -195,7 +195,7 @@ struct b2a_detector {
     static constexpr int MAX_SUB = 8;
     cudaStream_t streams[MAX_SUB] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
-    int n_sub_max = MAX_SUB, n_streams = 4;
+    int n_sub_max = MAX_SUB, n_streams = 0;       // 0 = automatic: 2 sub-batches for frames already in HBM, 4 when they still cross PCIe
     int nScales = 0, radius[MAX_SCALES];
     bool thresh_tiles = false;
     int max_cand = 0, max_markers = 0, surv_cap = 0;
@@ -754,7 +754,10 @@ static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *
     CU(cudaMemsetAsync(d->d_counters, 0, (d->n_sub_max + 3 * FSmax + d->cfg.max_batch) * sizeof(int), s0));
     CU(cudaMemsetAsync(d->d_counters2, 0, d->n_sub_max * sizeof(unsigned), s0));
     // sub-batches
-    int nsub = std::max(1, std::min(std::min(d->n_streams, d->n_sub_max), B));
+    // frames in HBM: two sub-batches overlap the latency-bound back end of one with the front end of the other (measured best:
+    // 29.5 k frames/s against 26.4 k with one and 28.4 k with four); host frames: four, so that kernels run under the PCIe copy
+    const int want_streams = d->n_streams > 0 ? d->n_streams : (f->on_device ? 2 : 4);
+    int nsub = std::max(1, std::min(std::min(want_streams, d->n_sub_max), B));
     // sub-batch boundaries.  Frames that still have to cross PCIe are cut unevenly: a small first sub-batch lets the
     // kernels start early and a small last one shortens the tail that nothing overlaps (B2A_SPLIT="2,6,8,8,6,2" overrides)
     std::vector<int> bounds;
@@ -848,7 +851,7 @@ extern "C" int b2a_detect_pose(b2a_detector *d, const b2a_frames *frames, const 
 
 extern "C" int b2a_detector_set_streams(b2a_detector *d, int n)
 {
-    if (!d || n < 1) return set_err(B2A_ERR_INVALID, "streams must be >= 1");
+    if (!d || n < 0) return set_err(B2A_ERR_INVALID, "streams must be >= 0 (0 = automatic)");
     d->n_streams = std::min(n, d->n_sub_max);
     return B2A_OK;
 }

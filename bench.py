@@ -361,7 +361,7 @@ def main():
     clocks = sampler.result() if rank == 0 else None
     # roofline pass: one stream = one k_threshold launch over the whole batch, timed by the library's CUDA events
     # on the launching stream (L2 flushed before every step like the main runs)
-    n_streams = int(os.environ.get("B2A_STREAMS", "4"))
+    n_streams = int(os.environ.get("B2A_STREAMS", "0"))          # 0 = the library's own choice (2 sub-batches for resident frames, 4 for host frames)
     det.set_streams(1)
     _, stages_1s, _ = run(fr_dev, max(3, min(args.steps, 10)), 1)
     det.set_streams(n_streams)

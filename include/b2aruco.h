@@ -149,8 +149,8 @@ int b2a_detector_num_scales(const b2a_detector *d);
 int b2a_last_stage_times(const b2a_detector *d, const char **names, float *ms, int cap);
 /* number of kernel launches issued by the last detect call (for bench.py's gpu_launches) */
 int b2a_last_launch_count(const b2a_detector *d);
-/* A call's batch is cut into up to n sub-batches that run on separate CUDA streams (default 4;
- * 1 = strictly serial stages, which is what per-stage timings / profiles want). */
+/* A call's batch is cut into up to n sub-batches that run on separate CUDA streams (default 0 = automatic: 2 for frames already
+ * in device memory, 4 for host frames; 1 = strictly serial stages, which is what per-stage timings / profiles want). */
 int b2a_detector_set_streams(b2a_detector *d, int n);
 /* the CUDA stream (cudaStream_t) the handle launches on (sub-batch 0; the others fork from / join into it) */
 void *b2a_detector_stream(const b2a_detector *d);
