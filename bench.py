@@ -297,7 +297,9 @@ def main():
         raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's own version / debug lines must not share stdout with the JSON line
+        # NCCL's own version / debug lines must not share stdout with the JSON line (the box exports NCCL_DEBUG=VERSION)
+        os.environ["NCCL_DEBUG"] = os.environ.get("B2A_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     frames = synth.render_batch(args.workload, B, base_seed=1000 * rank)          # this rank's shard
