@@ -184,4 +184,25 @@ inline void estimatePoseSingleMarkers(const std::vector<std::vector<Point2f>> &c
 }
 
 }  // namespace aruco
+
+// ---- wire / on-disk formats (reference src/map_loader.cpp, ArucoSlam::toRosPose) as plain records ----
+// MapLoader::loadMap(file_path): the cubes a map file defines, under the reference loader's acceptance rules (see b2aruco.h).
+// Like the reference, an unreadable file gives an empty map instead of an error.
+inline std::vector<b2a_map_marker> loadMap(const std::string &file_path)
+{
+    std::vector<b2a_map_marker> out(256);
+    int n = 0;
+    int rc = b2a_map_load(file_path.c_str(), out.data(), (int)out.size(), &n);
+    if (rc == B2A_ERR_CAPACITY) { out.resize((size_t)n); rc = b2a_map_load(file_path.c_str(), out.data(), (int)out.size(), &n); }
+    if (rc != B2A_OK) return {};
+    out.resize((size_t)n);
+    return out;
+}
+// ArucoSlam::toRosPose(): position, yaw quaternion and the 6x6 covariance packing of the filter's robot state
+inline b2a_pose_with_covariance robotPose(b2a_slam *slam)
+{
+    b2a_pose_with_covariance p;
+    check(b2a_slam_robot_pose(slam, &p));
+    return p;
+}
 }  // namespace b2a
