@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cctype>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -740,6 +741,7 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
 // mode: 0 full pipeline, 1 stop after the front end (taps), 2 stop after grouping (candidate tap)
 static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *cam, int mode, int walk_max_len, std::vector<Sub> *subs_out)
 {
+    const auto t_call = std::chrono::steady_clock::now();
     TRY(check_frames(d, f));
     CU(cudaSetDevice(d->device));
     const int B = f->batch, W = f->width, H = f->height;
@@ -801,7 +803,15 @@ static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *
         if (timeline) cudaEventRecord(tl_ev[2 + 2 * i], subs[i].st);
     }
     for (int i = 1; i < nsub; ++i) { CU(cudaEventRecord(d->ev_join[i], subs[i].st)); CU(cudaStreamWaitEvent(s0, d->ev_join[i], 0)); }
+    static const bool host_time = std::getenv("B2A_HOSTTIME") != nullptr;     // debug: host time spent enqueueing against the whole call
+    const auto t_enq = std::chrono::steady_clock::now();
     CU(cudaStreamSynchronize(s0));
+    if (host_time) {
+        static double acc_e = 0, acc_t = 0; static int cnt = 0;
+        const auto t_end = std::chrono::steady_clock::now();
+        acc_e += std::chrono::duration<double, std::milli>(t_enq - t_call).count(); acc_t += std::chrono::duration<double, std::milli>(t_end - t_call).count();
+        if (++cnt % 20 == 0) { std::fprintf(stderr, "host: enqueue %.3f ms of %.3f ms per call (%d launches)\n", acc_e / 20, acc_t / 20, d->launches); acc_e = acc_t = 0; }
+    }
     if (timeline && mode == 0) {
         std::fprintf(stderr, "timeline (ms): ");
         for (int i = 0; i < nsub; ++i) {
