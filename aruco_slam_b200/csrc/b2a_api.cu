@@ -669,7 +669,8 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
     double *wM = d->d_wM + (size_t)b0 * d->max_cand * 9;
     k_homography<<<dim3(4, nb), 64, 0, st>>>(fa, wM, (ip.markerSize + 2 * ip.borderBits) * ip.cellSize, d->max_cand);
     d->launches++;
-    k_identify<<<dim3(32, nb), ID_THREADS, identify_smem_bytes((ip.markerSize + 2 * ip.borderBits) * ip.cellSize), st>>>(s.gray, d->d_dict, wM, fa, ip);
+    static const int id_blocks = std::getenv("B2A_ID_BLOCKS") ? std::max(1, std::atoi(std::getenv("B2A_ID_BLOCKS"))) : 48;   // x 4 warps = work items of a frame in flight (a frame has ~124 of them; with 128 warps the frames that have more made a second round: 0.118 -> 0.102 ms)
+    k_identify<<<dim3(id_blocks, nb), ID_THREADS, identify_smem_bytes((ip.markerSize + 2 * ip.borderBits) * ip.cellSize), st>>>(s.gray, d->d_dict, wM, fa, ip);
     d->launches++;
     if (ip.marks) {
         long long hm[16];

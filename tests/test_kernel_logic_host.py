@@ -133,6 +133,11 @@ def test_otsu_restatement_matches_textbook_loop():
     for _ in range(100):                                    # blurred two-level patches like a warped marker
         v = np.clip(np.concatenate([rng.normal(40, 6, 500), rng.normal(210, 9, 400), rng.uniform(40, 210, 124)]), 0, 255).astype(int)
         cases.append(np.bincount(v, minlength=256))
+    for n in (576, 784, 5184):                              # patches whose pixel count is not a power of two (1 / n inexact): sparse histograms with long empty runs
+        for _ in range(150):
+            k = int(rng.integers(2, 40))
+            bins = rng.choice(256, size=k, replace=False)
+            cases.append(np.bincount(rng.choice(bins, size=n), minlength=256))
     for h in cases:
         new, seq = emu.otsu(h)
         assert new == seq, (new, seq, np.nonzero(h)[0][:8])
