@@ -588,7 +588,8 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
                                                d->d_pts_off + fs0 * g.surv_cap, d->d_status + b0, bg.n_anchors, bg.cap, bg.n_starts, bg.starts_cap, g);
     d->launches++; DBG_SYNC(st);
     stage_mark(d, s, ST_ASSIGN);
-    k_assign<<<dim3(8, (unsigned)FS), 128, 0, st>>>(masks, bg, d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,
+    static const int assign_ctas = std::getenv("B2A_ASSIGN_CTAS") ? std::max(1, std::atoi(std::getenv("B2A_ASSIGN_CTAS"))) : 8;
+    k_assign<<<dim3(assign_ctas, (unsigned)FS), 128, 0, st>>>(masks, bg, d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,
                                                     d->d_pts + fs0 * (size_t)g.pts_cap, d->d_tables, g);
     d->launches++; DBG_SYNC(st);
     k_assign_sub<<<walk_grid, 256, 0, st>>>(bg);
@@ -597,7 +598,8 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     k_emit<<<walk_grid, 256, 0, st>>>(masks, bg, d->d_sorted + fs0 * g.surv_cap, d->d_pts_off + fs0 * g.surv_cap, d->d_pts + fs0 * (size_t)g.pts_cap, d->d_tables, g);
     d->launches++; DBG_SYNC(st);
     stage_mark(d, s, ST_APPROX);
-    k_approx<<<dim3(APPROX_LONG_CTAS + 8, (unsigned)FS), 256, 0, st>>>(d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,
+    static const int approx_short = std::getenv("B2A_APPROX_SHORT") ? std::max(1, std::atoi(std::getenv("B2A_APPROX_SHORT"))) : 32;   // CTAs (8 warps each) per (frame,scale) for the warp-per-border role: a (frame,scale) has 200-350 kept borders of very different lengths, and with 64 warps the longest queue set the kernel's time (8 -> 32 CTAs: 0.185 -> 0.156 ms)
+    k_approx<<<dim3(APPROX_LONG_CTAS + approx_short, (unsigned)FS), 256, 0, st>>>(d->d_sorted + fs0 * g.surv_cap, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,
                                                                        d->d_pts + fs0 * (size_t)g.pts_cap, d->d_quad_ok + fs0 * g.surv_cap, d->d_quad_xy + fs0 * g.surv_cap * 8,
                                                                        d->d_quad_len + fs0 * g.surv_cap, g);
     d->launches++; DBG_SYNC(st);
