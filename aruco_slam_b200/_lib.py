@@ -92,6 +92,7 @@ SYMBOLS = [
     "b2a_default_slam_params", "b2a_slam_create", "b2a_slam_destroy", "b2a_slam_dim", "b2a_slam_get_state",
     "b2a_slam_set_state", "b2a_slam_add_encoder", "b2a_slam_make_observations", "b2a_slam_update", "b2a_slam_add_image", "b2a_slam_synchronize",
     "b2a_quaternion_from_rpy", "b2a_map_parse", "b2a_map_load", "b2a_slam_robot_pose", "b2a_slam_detected_map",
+    "b2a_pack_robot_pose", "b2a_pack_map_marker",
 ]
 
 _lib = None

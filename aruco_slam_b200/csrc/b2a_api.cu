@@ -14,7 +14,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
+#include <queue>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -161,10 +164,13 @@ k_export(ExportPtrs p, int max_markers, int with_pose)
         for (int i = threadIdx.x; i < na * 3; i += blockDim.x) { p.h_rvecs[o * 3 + i] = p.rvecs[o * 3 + i]; p.h_tvecs[o * 3 + i] = p.tvecs[o * 3 + i]; }
 }
 
+// n_dev (optional): the count lives on the device (the detector's n_accepted of the frame); the count is also written to *n_out
 __global__ void k_observations(const float *__restrict__ corners, const int32_t *__restrict__ ids, const double *__restrict__ rvecs,
-                               const double *__restrict__ tvecs, int n, Camera cam, ObsParams op, Observation *__restrict__ out,
-                               int *__restrict__ keep)
+                               const double *__restrict__ tvecs, int n, const int32_t *__restrict__ n_dev, int cap, Camera cam, ObsParams op,
+                               Observation *__restrict__ out, int *__restrict__ keep, int *__restrict__ n_out)
 {
+    if (n_dev) n = min(*n_dev, cap);
+    if (n_out && blockIdx.x == 0 && threadIdx.x == 0) *n_out = n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         keep[i] = make_observation(cam, op, corners + (size_t)i * 8, ids[i], rvecs + (size_t)i * 3, tvecs + (size_t)i * 3, out[i]) ? 1 : 0;
 }
@@ -296,13 +302,13 @@ static int create_impl(b2a_detector *d)
     TRY(dev_alloc(d, &d->d_masks, d->masks_words));
     if (const char *e = std::getenv("B2A_ANCHOR_R")) { const int r = std::atoi(e); if (r >= 1 && r <= 32 && !(r & (r - 1))) d->anchor_R = r; }
     // anchors: a state is an anchor on every R-th row or column, so even a pure-noise mask (~0.8 states per pixel)
-    // stays below 2 P / R per mask; start candidates: below P / 4 per mask
-    d->anchors_cap = (unsigned)std::min<size_t>(std::max<size_t>((size_t)B * nS * (2 * P / (size_t)d->anchor_R), 1u << 20), 0x7FFFFFF0u);
+    // stays below 2 P / R per mask; start candidates: below P / 4 per mask.  Both arrays are cut per FRAME (run_front)
+    d->anchors_cap = (unsigned)std::min<size_t>((size_t)B * std::max<size_t>(nS * (2 * P / (size_t)d->anchor_R), 1u << 16), 0x7FFFFFF0u);
     TRY(dev_alloc(d, &d->d_ast, d->anchors_cap)); TRY(dev_alloc(d, &d->d_seg, d->anchors_cap));
     TRY(dev_alloc(d, &d->d_minoff, d->anchors_cap)); TRY(dev_alloc(d, &d->d_emit, d->anchors_cap));
     TRY(dev_alloc(d, &d->d_sseg, d->anchors_cap)); TRY(dev_alloc(d, &d->d_ssoff, d->anchors_cap));
     TRY(dev_alloc(d, &d->d_amap, (size_t)B * nS * H * ((W + 31) / 32)));
-    d->starts_cap = (unsigned)std::min<size_t>(std::max<size_t>((size_t)B * nS * (P / 4), 1u << 20), 0x7FFFFFF0u);
+    d->starts_cap = (unsigned)std::min<size_t>((size_t)B * std::max<size_t>(nS * (P / 4), 1u << 16), 0x7FFFFFF0u);
     TRY(dev_alloc(d, &d->d_starts, d->starts_cap));
     TRY(dev_alloc(d, &d->d_codes, (size_t)d->anchors_cap * SEG_CODE_WORDS));
     TRY(dev_alloc(d, &d->d_counters2, d->n_sub_max));
@@ -532,15 +538,19 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     g.count_all = walk_max_len > 0 ? 1 : 0;          // the contour tap (exact counts, no give-up length) is the only caller that asks
     // this sub-batch's slice of the anchor arrays, and its per-(frame,scale) arrays addressed from frame b0
     const size_t fs0 = (size_t)b0 * g.nScales, FS = (size_t)nb * g.nScales;
-    const unsigned slice = d->anchors_cap / (unsigned)d->n_sub_max;
+    // a sub-batch owns the share of the anchor / start-candidate arrays that belongs to its frames: the arrays are sized per frame
+    // (2P/R anchors and P/4 start candidates per mask), so any cut of the batch leaves every frame its full capacity
+    const unsigned a_per = d->anchors_cap / (unsigned)d->cfg.max_batch, s_per = d->starts_cap / (unsigned)d->cfg.max_batch;
+    const size_t a_off = (size_t)b0 * a_per, s_off = (size_t)b0 * s_per;
+    const unsigned slice = a_per * (unsigned)nb;
     BorderGraph bg;
-    bg.ast = d->d_ast + (size_t)s.sb * slice; bg.seg = d->d_seg + (size_t)s.sb * slice; bg.minoff = d->d_minoff + (size_t)s.sb * slice;
-    bg.sseg = d->d_sseg + (size_t)s.sb * slice; bg.ssoff = d->d_ssoff + (size_t)s.sb * slice;
-    bg.emit = d->d_emit + (size_t)s.sb * slice; bg.amap = d->d_amap + fs0 * (size_t)H * g.WW;
+    bg.ast = d->d_ast + a_off; bg.seg = d->d_seg + a_off; bg.minoff = d->d_minoff + a_off;
+    bg.sseg = d->d_sseg + a_off; bg.ssoff = d->d_ssoff + a_off;
+    bg.emit = d->d_emit + a_off; bg.amap = d->d_amap + fs0 * (size_t)H * g.WW;
     bg.n_anchors = (unsigned *)d->d_counters + s.sb; bg.cap = slice;
-    bg.codes = d->d_codes + (size_t)s.sb * slice * SEG_CODE_WORDS;
-    bg.starts = d->d_starts + (size_t)s.sb * (d->starts_cap / (unsigned)d->n_sub_max); bg.n_starts = d->d_counters2 + s.sb;
-    bg.starts_cap = d->starts_cap / (unsigned)d->n_sub_max;
+    bg.codes = d->d_codes + a_off * SEG_CODE_WORDS;
+    bg.starts = d->d_starts + s_off; bg.n_starts = d->d_counters2 + s.sb;
+    bg.starts_cap = s_per * (unsigned)nb;
     const int Rm = d->anchor_R - 1, Rm2 = 8 * d->anchor_R - 1, max_len = walk_max_len > 0 ? walk_max_len : g.maxPerim;
     static const int walk_ctas = std::getenv("B2A_WALK_CTAS") ? std::max(1, std::atoi(std::getenv("B2A_WALK_CTAS"))) : 8;   // resident 256-thread CTAs per SM of the grid-stride kernels
     const unsigned walk_grid = (unsigned)d->num_sms * walk_ctas;
@@ -742,7 +752,9 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
 }
 
 // mode: 0 full pipeline, 1 stop after the front end (taps), 2 stop after grouping (candidate tap)
-static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *cam, int mode, int walk_max_len, std::vector<Sub> *subs_out)
+// post: work the caller appends on the handle's stream after the sub-batches have joined, before the one synchronisation of the call
+static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *cam, int mode, int walk_max_len, std::vector<Sub> *subs_out,
+                        const std::function<int(cudaStream_t)> *post = nullptr)
 {
     const auto t_call = std::chrono::steady_clock::now();
     TRY(check_frames(d, f));
@@ -806,6 +818,7 @@ static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *
         if (timeline) cudaEventRecord(tl_ev[2 + 2 * i], subs[i].st);
     }
     for (int i = 1; i < nsub; ++i) { CU(cudaEventRecord(d->ev_join[i], subs[i].st)); CU(cudaStreamWaitEvent(s0, d->ev_join[i], 0)); }
+    if (post) TRY((*post)(s0));
     static const bool host_time = std::getenv("B2A_HOSTTIME") != nullptr;     // debug: host time spent enqueueing against the whole call
     const auto t_enq = std::chrono::steady_clock::now();
     CU(cudaStreamSynchronize(s0));
@@ -974,9 +987,14 @@ struct b2a_slam {
     int N = 3, LD = 0, cap_lm = 0;
     double *d_sigma2 = nullptr;                      // ping-pong partner of d_sigma (cooperative kernel)
     double *d_mu = nullptr, *d_mus = nullptr, *d_sigma = nullptr, *d_K = nullptr, *d_GS = nullptr, *d_scratch = nullptr;
-    EkfObs *d_obs = nullptr; int obs_cap = 0;       // known-landmark corrections of one frame (cooperative kernel)
     int coop_grid = 0;                               // co-resident CTAs of k_ekf_frame (0 = use the per-observation kernels)
-    std::vector<int32_t> ids;                       // landmark k -> aruco id (aruco_id_map, aruco_slam.h:164)
+    // per-frame scratch, allocated once (grown only when a frame brings more markers than ever before)
+    int obs_cap = 0;
+    float *d_c = nullptr; int32_t *d_i = nullptr; double *d_r = nullptr, *d_t = nullptr;      // detections of the host-array entry point
+    Observation *h_obs = nullptr; int *h_keep = nullptr, *h_n = nullptr;                      // pinned, written by k_observations
+    EkfObs *d_ekf = nullptr, *h_ekf[2] = {nullptr, nullptr}; cudaEvent_t ev_ekf[2] = {nullptr, nullptr}; int ekf_buf = 0;   // corrections of a frame
+    std::vector<int32_t> ids;                       // landmark k -> aruco id
+    std::unordered_map<int32_t, int> id_index;      // aruco_id_map (aruco_slam.h:164): id -> landmark index, first insertion wins (:256)
     std::vector<int32_t> last_ids; std::vector<double> last_obs;   // last_observed_marker_ (NaN = unset)
     bool is_init = false;
 };
@@ -990,12 +1008,41 @@ extern "C" void b2a_default_slam_params(b2a_slam_params *p)
     p->max_landmarks = 512;
 }
 
+static void slam_free_scratch(b2a_slam *s)
+{
+    cudaFree(s->d_c); cudaFree(s->d_i); cudaFree(s->d_r); cudaFree(s->d_t); cudaFree(s->d_ekf);
+    cudaFreeHost(s->h_obs); cudaFreeHost(s->h_keep); cudaFreeHost(s->h_ekf[0]); cudaFreeHost(s->h_ekf[1]);
+    s->d_c = nullptr; s->d_i = nullptr; s->d_r = s->d_t = nullptr; s->d_ekf = nullptr; s->h_obs = nullptr; s->h_keep = nullptr; s->h_ekf[0] = s->h_ekf[1] = nullptr;
+    s->obs_cap = 0;
+}
+
+// scratch for n markers per frame; called with the stream idle (only grows, from 256)
+static int slam_reserve(b2a_slam *s, int n)
+{
+    if (n <= s->obs_cap) return B2A_OK;
+    CU(cudaStreamSynchronize(s->stream));
+    slam_free_scratch(s);
+    const size_t c = (size_t)std::max(256, 2 * n);
+    if (cudaMalloc(&s->d_c, c * 32) || cudaMalloc(&s->d_i, c * 4) || cudaMalloc(&s->d_r, c * 24) || cudaMalloc(&s->d_t, c * 24) ||
+        cudaMalloc(&s->d_ekf, c * sizeof(EkfObs)) || cudaMallocHost(&s->h_obs, c * sizeof(Observation)) || cudaMallocHost(&s->h_keep, c * 4) ||
+        cudaMallocHost(&s->h_ekf[0], c * sizeof(EkfObs)) || cudaMallocHost(&s->h_ekf[1], c * sizeof(EkfObs))) {
+        slam_free_scratch(s);
+        (void)cudaGetLastError();
+        return set_err(B2A_ERR_CUDA, "cudaMalloc (SLAM frame scratch)");
+    }
+    s->obs_cap = (int)c;
+    return B2A_OK;
+}
+
 extern "C" void b2a_slam_destroy(b2a_slam *s)
 {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    cudaFree(s->d_obs); cudaFree(s->d_sigma2);
+    slam_free_scratch(s);
+    cudaFreeHost(s->h_n);
+    for (cudaEvent_t e : s->ev_ekf) if (e) cudaEventDestroy(e);
+    cudaFree(s->d_sigma2);
     cudaFree(s->d_mu); cudaFree(s->d_mus); cudaFree(s->d_sigma); cudaFree(s->d_K); cudaFree(s->d_GS); cudaFree(s->d_scratch);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -1034,6 +1081,9 @@ extern "C" int b2a_slam_create(int device, const b2a_slam_params *p, b2a_slam **
     cudaMemsetAsync(s->d_mu, 0, LD * 8, s->stream);
     cudaMemsetAsync(s->d_sigma, 0, LD * LD * 8, s->stream);
     if (cudaStreamSynchronize(s->stream) != cudaSuccess) return fail("memset");
+    if (cudaMallocHost(&s->h_n, sizeof(int)) || cudaEventCreateWithFlags(&s->ev_ekf[0], cudaEventDisableTiming) ||
+        cudaEventCreateWithFlags(&s->ev_ekf[1], cudaEventDisableTiming) || slam_reserve(s, 256) != B2A_OK)
+        return fail("frame scratch");
     *out = s;
     return B2A_OK;
 }
@@ -1138,6 +1188,26 @@ extern "C" int b2a_map_load(const char *path, b2a_map_marker *out, int cap, int 
     return b2a_map_parse(text.data(), text.size(), out, cap, n_out);
 }
 
+extern "C" void b2a_pack_robot_pose(const double mu[3], const double S[9], b2a_pose_with_covariance *out)
+{
+    std::memset(out, 0, sizeof(*out));
+    out->position[0] = mu[0]; out->position[1] = mu[1]; out->position[2] = 0.1;                    // aruco_slam.cpp:381-385
+    b2a_quaternion_from_rpy(0, 0, mu[2], out->orientation);                                        // :388-390
+    static const int at[9] = {0, 1, 5, 6, 7, 11, 30, 31, 35};                                      // :399-407
+    for (int i = 0; i < 9; ++i) out->covariance[at[i]] = S[i];
+}
+
+extern "C" void b2a_pack_map_marker(int index, double marker_length, const double lm[3], b2a_map_marker *out)
+{   // aruco_slam.cpp:266-281
+    b2a_map_marker m;
+    std::memset(&m, 0, sizeof(m));
+    m.id = index; m.length = marker_length;
+    m.x = lm[0]; m.y = lm[1]; m.z = 0.3;
+    m.roll = 0; m.pitch = 1.5708; m.yaw = lm[2];
+    b2a_quaternion_from_rpy(m.roll, m.pitch, m.yaw, m.q);
+    *out = m;
+}
+
 extern "C" int b2a_slam_robot_pose(b2a_slam *s, b2a_pose_with_covariance *out)
 {
     if (!s || !out) return set_err(B2A_ERR_INVALID, "null argument");
@@ -1146,11 +1216,7 @@ extern "C" int b2a_slam_robot_pose(b2a_slam *s, b2a_pose_with_covariance *out)
     double mu[3], S[9];
     CU(cudaMemcpy(mu, s->d_mu, sizeof(mu), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy2D(S, 3 * 8, s->d_sigma, (size_t)s->LD * 8, 3 * 8, 3, cudaMemcpyDeviceToHost));
-    std::memset(out, 0, sizeof(*out));
-    out->position[0] = mu[0]; out->position[1] = mu[1]; out->position[2] = 0.1;                    // aruco_slam.cpp:381-383
-    b2a_quaternion_from_rpy(0, 0, mu[2], out->orientation);                                        // :386-388
-    static const int at[9] = {0, 1, 5, 6, 7, 11, 30, 31, 35};                                      // :397-405
-    for (int i = 0; i < 9; ++i) out->covariance[at[i]] = S[i];
+    b2a_pack_robot_pose(mu, S, out);
     return B2A_OK;
 }
 
@@ -1162,15 +1228,7 @@ extern "C" int b2a_slam_detected_map(b2a_slam *s, double marker_length, b2a_map_
     const int n = (s->N - 3) / 3;
     std::vector<double> mu((size_t)s->N);
     CU(cudaMemcpy(mu.data(), s->d_mu, (size_t)s->N * 8, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < n && i < cap; ++i) {                                                       // aruco_slam.cpp:266-281
-        b2a_map_marker m;
-        std::memset(&m, 0, sizeof(m));
-        m.id = i; m.length = marker_length;
-        m.x = mu[3 + 3 * i]; m.y = mu[4 + 3 * i]; m.z = 0.3;
-        m.roll = 0; m.pitch = 1.5708; m.yaw = mu[5 + 3 * i];
-        b2a_quaternion_from_rpy(m.roll, m.pitch, m.yaw, m.q);
-        out[i] = m;
-    }
+    for (int i = 0; i < n && i < cap; ++i) b2a_pack_map_marker(i, marker_length, &mu[3 + 3 * i], &out[i]);
     *n_out = n;
     if (n > cap) return set_err(B2A_ERR_CAPACITY, "more landmarks than the output array");
     return B2A_OK;
@@ -1199,6 +1257,8 @@ extern "C" int b2a_slam_set_state(b2a_slam *s, int N, const double *mu, const do
     CU(cudaMemcpy2D(s->d_sigma, (size_t)s->LD * 8, sigma, (size_t)N * 8, (size_t)N * 8, N, cudaMemcpyHostToDevice));
     s->N = N;
     s->ids.assign(ids, ids + (N - 3) / 3);
+    s->id_index.clear();
+    for (int k = 0; k < (N - 3) / 3; ++k) s->id_index.insert({ids[k], k});
     s->last_ids.clear(); s->last_obs.clear();
     s->is_init = true;
     return B2A_OK;
@@ -1208,9 +1268,31 @@ extern "C" int b2a_slam_add_encoder(b2a_slam *s, double wl, double wr, double dt
 {
     if (!s) return set_err(B2A_ERR_INVALID, "null handle");
     CU(cudaSetDevice(s->device));
-    s->is_init = true;
+    if (!s->is_init) { s->is_init = true; return B2A_OK; }           // the first message only latches the clock (:24-29)
     k_ekf_predict<<<1, 256, 0, s->stream>>>(s->d_sigma, s->d_mu, s->N, s->LD, wl, wr, dt, s->p.kl, s->p.kr, s->p.b, s->p.Q_k, s->d_scratch);
     return launch_err("k_ekf_predict");
+}
+
+static ObsParams obs_params(const b2a_slam *s, const b2a_camera *cam)
+{
+    ObsParams op;
+    op.R_x = s->p.R_x; op.R_y = s->p.R_y; op.R_theta = s->p.R_theta; op.marker_length = (double)cam->marker_length;
+    op.r2c_tx = s->p.r2c_tx; op.r2c_ty = s->p.r2c_ty; op.useful_distance_threshold = s->p.useful_distance_threshold;
+    return op;
+}
+
+// the observations k_observations left in the pinned arrays, gated ones dropped, detection order (:325-374)
+static int collect_observations(const b2a_slam *s, int n, b2a_observation *out)
+{
+    int k = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!s->h_keep[i]) continue;
+        b2a_observation &o = out[k++];
+        const Observation &h = s->h_obs[i];
+        o.aruco_id = h.aruco_id; o.aruco_index = -1; o.x = h.x; o.y = h.y; o.theta = h.theta;
+        std::memcpy(o.cov, h.cov, sizeof(o.cov));
+    }
+    return k;
 }
 
 extern "C" int b2a_slam_make_observations(b2a_slam *s, const float *corners, const int32_t *ids, const double *rvecs, const double *tvecs,
@@ -1220,32 +1302,15 @@ extern "C" int b2a_slam_make_observations(b2a_slam *s, const float *corners, con
     *n_out = 0;
     if (n <= 0) return B2A_OK;
     CU(cudaSetDevice(s->device));
-    float *dc; int32_t *di; double *dr, *dtv; Observation *dobs; int *dkeep;
-    CU(cudaMalloc(&dc, (size_t)n * 32)); CU(cudaMalloc(&di, (size_t)n * 4)); CU(cudaMalloc(&dr, (size_t)n * 24)); CU(cudaMalloc(&dtv, (size_t)n * 24));
-    CU(cudaMalloc(&dobs, (size_t)n * sizeof(Observation))); CU(cudaMalloc(&dkeep, (size_t)n * 4));
+    TRY(slam_reserve(s, n));
     cudaStream_t st = s->stream;
-    cudaMemcpyAsync(dc, corners, (size_t)n * 32, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(di, ids, (size_t)n * 4, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dr, rvecs, (size_t)n * 24, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dtv, tvecs, (size_t)n * 24, cudaMemcpyHostToDevice, st);
-    ObsParams op;
-    op.R_x = s->p.R_x; op.R_y = s->p.R_y; op.R_theta = s->p.R_theta; op.marker_length = (double)cam->marker_length;
-    op.r2c_tx = s->p.r2c_tx; op.r2c_ty = s->p.r2c_ty; op.useful_distance_threshold = s->p.useful_distance_threshold;
-    k_observations<<<(n + 63) / 64, 64, 0, st>>>(dc, di, dr, dtv, n, to_camera(cam), op, dobs, dkeep);
-    std::vector<Observation> ho(n); std::vector<int> hk(n);
-    cudaMemcpyAsync(ho.data(), dobs, (size_t)n * sizeof(Observation), cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(hk.data(), dkeep, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
-    cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(dc); cudaFree(di); cudaFree(dr); cudaFree(dtv); cudaFree(dobs); cudaFree(dkeep);
-    if (e != cudaSuccess) return set_err(B2A_ERR_CUDA, cudaGetErrorString(e));
-    int k = 0;
-    for (int i = 0; i < n; ++i) {
-        if (!hk[i]) continue;
-        b2a_observation &o = out[k++];
-        o.aruco_id = ho[i].aruco_id; o.aruco_index = -1; o.x = ho[i].x; o.y = ho[i].y; o.theta = ho[i].theta;
-        std::memcpy(o.cov, ho[i].cov, sizeof(o.cov));
-    }
-    *n_out = k;
+    CU(cudaMemcpyAsync(s->d_c, corners, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->d_i, ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->d_r, rvecs, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->d_t, tvecs, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    k_observations<<<(n + 63) / 64, 64, 0, st>>>(s->d_c, s->d_i, s->d_r, s->d_t, n, nullptr, n, to_camera(cam), obs_params(s, cam), s->h_obs, s->h_keep, nullptr);
+    CU(cudaStreamSynchronize(st));
+    *n_out = collect_observations(s, n, out);
     return launch_err("k_observations");
 }
 
@@ -1254,52 +1319,63 @@ extern "C" int b2a_slam_update(b2a_slam *s, const b2a_observation *obs, int n)
     if (!s || (n > 0 && !obs)) return set_err(B2A_ERR_INVALID, "null argument");
     CU(cudaSetDevice(s->device));
     if (n <= 0) { s->last_ids.clear(); s->last_obs.clear(); return B2A_OK; }
-    // checkLandmark (:423-435) + priority-queue order (aruco_slam.h:85-88): ascending index, new (-1) first;
-    // ties keep detection order (the reference's heap order among equals is implementation-defined)
-    struct Item { int index, seq; };
-    std::vector<Item> q(n);
-    for (int i = 0; i < n; ++i) {
-        int idx = -1;
-        for (size_t k = 0; k < s->ids.size(); ++k) if (s->ids[k] == obs[i].aruco_id) { idx = (int)k; break; }
-        q[i] = {idx, i};
-    }
-    std::stable_sort(q.begin(), q.end(), [](const Item &a, const Item &b) { return a.index < b.index; });
+    TRY(slam_reserve(s, n));
+    // checkLandmark (:423-435), then the reference's std::priority_queue<ArucoMarker> (aruco_slam.h:85-88,190): ascending
+    // landmark index, new landmarks (-1) first.  The order among equal indices is whatever libstdc++'s heap gives the
+    // reference (it is built with GCC); the same container with the same comparison and push order reproduces it -- pinned
+    // against a run of the reference itself in tests/golden/slam_*.npz.
+    struct Item {
+        int index, seq;
+        bool operator<(const Item &o) const { return index > o.index; }
+    };
+    std::priority_queue<Item> pq;
     int n_new = 0;
-    for (const Item &it : q) n_new += it.index < 0;
+    for (int i = 0; i < n; ++i) {
+        const auto it = s->id_index.find(obs[i].aruco_id);
+        const int idx = it == s->id_index.end() ? -1 : it->second;
+        n_new += idx < 0;
+        pq.push({idx, i});
+    }
     if ((int)s->ids.size() + n_new > s->cap_lm) return set_err(B2A_ERR_CAPACITY, "landmark capacity exceeded");
     cudaStream_t st = s->stream;
     CU(cudaMemcpyAsync(s->d_mus, s->d_mu, (size_t)s->N * 8, cudaMemcpyDeviceToDevice, st));      // mu snapshot (:88)
     std::vector<int32_t> new_last_ids(n);
     std::vector<double> new_last_obs((size_t)n * 3, NAN);
-    std::vector<EkfObs> batch;                                         // consecutive known-landmark corrections
+    // consecutive known-landmark corrections are staged in a pinned buffer (two of them, alternating by frame; a buffer is
+    // rewritten only after the copy that last read it has completed) and run as one launch; nothing here waits for the GPU
+    const int buf = s->ekf_buf;
+    s->ekf_buf ^= 1;
+    CU(cudaEventSynchronize(s->ev_ekf[buf]));
+    EkfObs *stage = s->h_ekf[buf];
+    int staged = 0, batch0 = 0;
     auto flush = [&]() -> int {
-        if (batch.empty()) return B2A_OK;
-        const int N = s->N, nb = (int)batch.size();
+        const int nb = staged - batch0;
+        if (nb <= 0) return B2A_OK;
+        const int N = s->N;
         if (s->coop_grid > 0 && (N + s->coop_grid - 1) / s->coop_grid <= 64) {
-            if (nb > s->obs_cap) { cudaFree(s->d_obs); s->obs_cap = std::max(nb, 64); CU(cudaMalloc(&s->d_obs, (size_t)s->obs_cap * sizeof(EkfObs))); }
-            // the batch vector lives until the copy has been consumed: the stream is synchronised below before it goes away
-            CU(cudaMemcpyAsync(s->d_obs, batch.data(), (size_t)nb * sizeof(EkfObs), cudaMemcpyHostToDevice, st));
-            int LD = s->LD, n_obs = nb;
-            const EkfObs *obs_p = s->d_obs;
-            int N_ = N;
+            CU(cudaMemcpyAsync(s->d_ekf + batch0, stage + batch0, (size_t)nb * sizeof(EkfObs), cudaMemcpyHostToDevice, st));
+            int LD = s->LD, n_obs = nb, N_ = N;
+            const EkfObs *obs_p = s->d_ekf + batch0;
             void *args[] = {&s->d_sigma, &s->d_sigma2, &s->d_mu, &s->d_mus, &N_, &LD, &obs_p, &n_obs};
             CU(cudaLaunchCooperativeKernel((void *)k_ekf_frame, dim3(s->coop_grid), dim3(512), args, 3 * (size_t)s->LD * sizeof(double), st));
-            CU(cudaStreamSynchronize(st));
             if (nb & 1) std::swap(s->d_sigma, s->d_sigma2);             // an odd number of ping-pongs ends in the other buffer
         } else {
-            for (const EkfObs &eo : batch) {
+            for (int k = batch0; k < staged; ++k) {
+                const EkfObs &eo = stage[k];
                 k_ekf_gain<<<(N + 255) / 256, 256, 0, st>>>(s->d_sigma, s->d_mus, N, s->LD, eo, s->d_K, s->d_GS);
                 dim3 grid((N + 2 * EK_TX - 1) / (2 * EK_TX), (N + EK_ROWS - 1) / EK_ROWS);
                 k_ekf_rank3<<<grid, dim3(EK_TX, EK_TY), 0, st>>>(s->d_sigma, s->d_mu, s->d_mus, N, s->LD, eo, s->d_K, s->d_GS);
             }
         }
-        batch.clear();
+        batch0 = staged;
         return B2A_OK;
     };
     for (int qi = 0; qi < n; ++qi) {
-        const b2a_observation &o = obs[q[qi].seq];
+        const Item it = pq.top();
+        pq.pop();
+        const b2a_observation &o = obs[it.seq];
         EkfObs eo;
-        eo.index = q[qi].index;
+        eo.index = it.index;
         eo.z[0] = o.x; eo.z[1] = o.y; eo.z[2] = o.theta;
         std::memcpy(eo.Rk, o.cov, sizeof(eo.Rk));
         if (eo.index >= 0) {
@@ -1312,17 +1388,19 @@ extern "C" int b2a_slam_update(b2a_slam *s, const b2a_observation *obs, int n)
                 }
             if (!stationary) {
                 new_last_obs[3 * qi] = o.x; new_last_obs[3 * qi + 1] = o.y; new_last_obs[3 * qi + 2] = o.theta;
-                batch.push_back(eo);
+                stage[staged++] = eo;
             }
         } else {
             TRY(flush());
             k_ekf_augment<<<1, 256, 0, st>>>(s->d_sigma, s->d_mu, s->d_mus, s->N, s->LD, eo);
             s->N += 3;
-            s->ids.push_back(o.aruco_id);                              // :256
+            s->id_index.insert({o.aruco_id, (int)s->ids.size()});      // :256 (insert: an id already in the map keeps its index)
+            s->ids.push_back(o.aruco_id);
         }
         new_last_ids[qi] = o.aruco_id;
     }
     TRY(flush());
+    CU(cudaEventRecord(s->ev_ekf[buf], st));
     s->last_ids.swap(new_last_ids); s->last_obs.swap(new_last_obs);    // :263
     return launch_err("EKF kernels");
 }
@@ -1331,12 +1409,22 @@ extern "C" int b2a_slam_add_image(b2a_slam *s, b2a_detector *d, const b2a_frames
 {
     if (!s || !d || !frame || !cam) return set_err(B2A_ERR_INVALID, "null argument");
     if (frame->batch != 1) return set_err(B2A_ERR_INVALID, "add_image takes one frame");
+    if (!(cam->marker_length > 0)) return set_err(B2A_ERR_INVALID, "markerLength <= 0");
+    if (s->device != d->device) return set_err(B2A_ERR_INVALID, "detector and filter live on different devices");
     if (!s->is_init) return B2A_OK;                                    // :84-85 (needs one encoder message first)
-    b2a_detections det;
-    TRY(b2a_detect_pose(d, frame, cam, &det));
-    const int n = det.n_accepted[0];
-    std::vector<b2a_observation> obs(std::max(n, 1));
-    int k = 0;
-    TRY(b2a_slam_make_observations(s, det.corners, det.ids, det.rvecs, det.tvecs, n, cam, obs.data(), &k));
+    TRY(slam_reserve(s, d->max_markers));
+    // detect + pose + observation mapping in one enqueue: k_observations reads the detector's device outputs and leaves
+    // the (few) observation records in pinned host memory; the call's one synchronisation covers it
+    const std::function<int(cudaStream_t)> post = [&](cudaStream_t st) -> int {
+        const float *corners = d->prm.cornerRefinementMethod == 1 ? d->d_corners2 : d->fo0.corners;
+        k_observations<<<(d->max_markers + 63) / 64, 64, 0, st>>>(corners, d->fo0.ids, d->d_rvecs, d->d_tvecs, 0, d->fo0.n_accepted, d->max_markers,
+                                                                  to_camera(cam), obs_params(s, cam), s->h_obs, s->h_keep, s->h_n);
+        d->launches++;
+        return launch_err("k_observations");
+    };
+    TRY(run_pipeline(d, frame, cam, 0, 0, nullptr, &post));
+    if (d->h_status[0] != 0) return set_err(B2A_ERR_CAPACITY, "an internal list overflowed (see b2a_detections.status)");
+    std::vector<b2a_observation> obs((size_t)std::max(*s->h_n, 1));
+    const int k = collect_observations(s, *s->h_n, obs.data());
     return b2a_slam_update(s, obs.data(), k);
 }

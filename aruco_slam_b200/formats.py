@@ -73,3 +73,24 @@ def detected_map(slam, marker_length: float = None):
     n = C.c_int(0)
     _lib.check(_lib.lib().b2a_slam_detected_map(slam._h, float(marker_length if marker_length is not None else slam.marker_length), arr, max(1, n_lm), C.byref(n)))
     return _markers(arr, n.value)
+
+
+def pose_record(mu, sigma):
+    """toRosPose's packing on host values (b2a_pack_robot_pose): position (3,), orientation (4,), covariance (36,)"""
+    m = (C.c_double * 3)(*[float(v) for v in np.asarray(mu).ravel()[:3]])
+    S = (C.c_double * 9)(*[float(v) for v in np.asarray(sigma)[:3, :3].ravel()])
+    out = _lib.PoseWithCovariance()
+    _lib.lib().b2a_pack_robot_pose(m, S, C.byref(out))
+    return np.array(out.position[:]), np.array(out.orientation[:]), np.array(out.covariance[:])
+
+
+def detected_map_records(mu, marker_length: float):
+    """the detected-map cubes of a state vector on host values (b2a_pack_map_marker)"""
+    mu = np.asarray(mu, float).ravel()
+    n = (len(mu) - 3) // 3
+    arr = (_lib.MapMarker * max(1, n))()
+    for i in range(n):
+        lm = (C.c_double * 3)(*mu[3 + 3 * i:6 + 3 * i])
+        _lib.lib().b2a_pack_map_marker.argtypes = [C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+        _lib.lib().b2a_pack_map_marker(i, float(marker_length), lm, C.byref(arr[i]))
+    return _markers(arr, n)

@@ -55,13 +55,9 @@ class ArucoSlam:
         self._cam = _camera(camera_matrix, dist_coeffs, self.marker_length)
 
     def addEncoder(self, wl: float, wr: float, dt: float):
-        """src/aruco_slam.cpp:21-74; the first call only latches time in the reference (:24-29):
-        pass dt=None for that call."""
-        if dt is None:
-            # latch: marks the filter initialised without moving it
-            _lib.check(_lib.lib().b2a_slam_add_encoder(self._h, 0.0, 0.0, 0.0))
-            return
-        _lib.check(_lib.lib().b2a_slam_add_encoder(self._h, float(wl), float(wr), float(dt)))
+        """src/aruco_slam.cpp:21-74.  As in the reference (:24-29) the first call on a fresh filter only marks it initialised
+        (there: latches the clock) whatever its arguments; dt=None reads as 0."""
+        _lib.check(_lib.lib().b2a_slam_add_encoder(self._h, float(wl), float(wr), 0.0 if dt is None else float(dt)))
 
     def addImage(self, image):
         """src/aruco_slam.cpp:76-263"""

@@ -233,3 +233,113 @@ def render_scene(W: int, H: int, dict_id: int, K: np.ndarray, D: np.ndarray, mar
     u8 = np.clip(np.rint(img), 0, 255).astype(np.uint8)
     return Frame(u8, np.array(ids, np.int32), np.array(cs, float).reshape(-1, 4, 2),
                  dict(W=W, H=H, dict_id=dict_id, seed=seed))
+
+
+# ----------------------------------------------------------------------------
+# World scenes (config C4): a landmark map in the reference's map.txt layout, a differential-drive robot with a
+# forward-looking camera, encoder readings.  Frames: robot X forward / Y left / Z up; camera optical X right /
+# Y down / Z forward (the mapping the reference's observation model assumes, src/aruco_slam.cpp:359-361:
+# x_obs = t_z + r2c.x, y_obs = -t_x + r2c.y, theta_obs = heading of the marker's normal).
+# ----------------------------------------------------------------------------
+
+R_CAM_TO_ROBOT = np.array([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])     # columns: camera axes in the robot frame
+
+
+def rvec_from_matrix(R: np.ndarray) -> np.ndarray:
+    """rotation vector of a rotation matrix (inverse of `rodrigues`)."""
+    c = (np.trace(R) - 1.0) / 2.0
+    th = float(np.arccos(np.clip(c, -1.0, 1.0)))
+    if th < 1e-12:
+        return np.zeros(3)
+    if np.pi - th < 1e-6:                       # half turn: axis from the symmetric part
+        A = (R + np.eye(3)) / 2.0
+        k = int(np.argmax(np.diag(A)))
+        ax = A[:, k] / np.sqrt(A[k, k])
+        return th * ax
+    ax = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / (2.0 * np.sin(th))
+    return th * ax
+
+
+def rpy_matrix(roll: float, pitch: float, yaw: float) -> np.ndarray:
+    """fixed-axes X-Y-Z rotation (tf2 setRPY)."""
+    cr, sr, cp, sp, cy, sy = np.cos(roll), np.sin(roll), np.cos(pitch), np.sin(pitch), np.cos(yaw), np.sin(yaw)
+    Rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
+    Ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+    Rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def quaternion_from_matrix(R: np.ndarray) -> np.ndarray:
+    """(x, y, z, w) of a rotation matrix."""
+    w = np.sqrt(max(0.0, 1.0 + R[0, 0] + R[1, 1] + R[2, 2])) / 2.0
+    if w > 1e-6:
+        return np.array([(R[2, 1] - R[1, 2]) / (4 * w), (R[0, 2] - R[2, 0]) / (4 * w), (R[1, 0] - R[0, 1]) / (4 * w), w])
+    r = rvec_from_matrix(R)
+    th = np.linalg.norm(r)
+    return np.append(np.sin(th / 2) * r / th, np.cos(th / 2))
+
+
+REFERENCE_MAP = (        # /root/reference/map/map.txt:2-8  (id, length, x, y, z, roll, pitch, yaw)
+    (0, 0.27, 5.10375, 0.0, 0.3, 0.0, -1.5708, 0.0),
+    (1, 0.27, 5.10375, -1.5, 0.3, 0.0, -1.5708, 0.0),
+    (2, 0.27, 5.10375, -3.0, 0.3, 0.0, -1.5708, 0.0),
+    (3, 0.27, 4.0, 0.6025, 0.3, 1.5708, -0.0, 0.0),
+    (4, 0.27, 2.0, 0.6025, 0.3, 1.5708, -0.0, 0.0),
+    (5, 0.27, 4.0, -4.09375, 0.3, -1.5708, -0.0, 0.0),
+    (6, 0.27, 2.0, -4.09375, 0.3, -1.5708, -0.0, 0.0),
+)
+
+
+def marker_world_frame(roll: float, pitch: float, yaw: float) -> np.ndarray:
+    """columns = the marker's x (right), y (up), z (normal, out of the printed face) axes in the world.  The map stores the
+    orientation of a thin cube whose local z is the face normal; the printed side is rendered upright (y = world up)."""
+    n = rpy_matrix(roll, pitch, yaw)[:, 2].copy()
+    n[2] = 0.0
+    n /= np.linalg.norm(n)
+    up = np.array([0.0, 0.0, 1.0])
+    x = np.cross(up, n)
+    return np.stack([x, up, n], axis=1)
+
+
+def scene_poses(map_markers, robot, r2c_t=(0.0, 0.0, 0.3), K=None, D=None, W=0, H=0, margin=12.0, max_incidence_deg=72.0):
+    """camera-frame (id, rvec, tvec) of the map markers the camera sees from robot = (x, y, theta)."""
+    rx, ry, rth = robot
+    c, s = np.cos(rth), np.sin(rth)
+    Rwr = np.array([[c, s, 0], [-s, c, 0], [0, 0, 1]])                 # world -> robot
+    out = []
+    for (mid, L, mx, my, mz, roll, pitch, yaw) in map_markers:
+        Rmw = marker_world_frame(roll, pitch, yaw)
+        R = R_CAM_TO_ROBOT.T @ Rwr @ Rmw
+        t = R_CAM_TO_ROBOT.T @ (Rwr @ (np.array([mx, my, mz]) - np.array([rx, ry, 0.0])) - np.asarray(r2c_t, float))
+        if t[2] < 0.35:
+            continue
+        nrm = R[:, 2]
+        cosi = -float(nrm @ t) / float(np.linalg.norm(t))
+        if cosi < np.cos(np.radians(max_incidence_deg)):
+            continue
+        rvec = rvec_from_matrix(R)
+        if K is not None:
+            q = project(marker_object_points(L), rvec, t, K, np.zeros(5) if D is None else D)
+            if q[:, 0].min() < margin or q[:, 1].min() < margin or q[:, 0].max() > W - 1 - margin or q[:, 1].max() > H - 1 - margin:
+                continue
+        out.append((int(mid), rvec, t))
+    return out
+
+
+def drive(pose, wl: float, wr: float, dt: float, kl: float = 0.05, kr: float = 0.05, b: float = 0.09):
+    """ground-truth motion of the differential drive for one encoder interval (the model of src/aruco_slam.cpp:35-52)."""
+    dsl, dsr = kl * wl * dt, kr * wr * dt
+    dth, ds = (dsr - dsl) / (2 * b), 0.5 * (dsr + dsl)
+    th = pose[2] + 0.5 * dth
+    return np.array([pose[0] + ds * np.cos(th), pose[1] + ds * np.sin(th), pose[2] + dth])
+
+
+def c5_state(n_lm: int, seed: int = 0):
+    """start state of the EKF-only workload C5: Sigma0 = A A^T / N + 0.1 I, landmarks uniform in an 8 m square,
+    aruco ids 100 .. 100 + n_lm - 1"""
+    N = 3 + 3 * n_lm
+    rng = np.random.default_rng(seed)
+    A = rng.normal(size=(N, N))
+    sigma0 = A @ A.T / N + 0.1 * np.eye(N)
+    mu0 = np.concatenate([[0.3, -0.2, 0.4], rng.uniform(-4, 4, 3 * n_lm)])
+    return mu0, sigma0, np.arange(100, 100 + n_lm, dtype=np.int32)

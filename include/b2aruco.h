@@ -179,14 +179,18 @@ int  b2a_slam_dim(const b2a_slam *s);                     /* 3 + 3*landmarks */
 /* mu [N], sigma [N][N] row-major, ids [n landmarks] (host). NULL pointers are skipped. */
 int  b2a_slam_get_state(b2a_slam *s, double *mu, double *sigma, int32_t *ids);
 int  b2a_slam_set_state(b2a_slam *s, int N, const double *mu, const double *sigma, const int32_t *ids);
-/* addEncoder(wl, wr) with an explicit dt (aruco_slam.cpp:21-74 reads ros::Time::now()). */
+/* addEncoder(wl, wr) with an explicit dt (aruco_slam.cpp:21-74 reads ros::Time::now()).  As in the reference (:24-29) the
+ * FIRST call on a fresh handle only marks the filter initialised (there it latches the clock) and predicts nothing;
+ * b2a_slam_set_state also marks it initialised. */
 int  b2a_slam_add_encoder(b2a_slam *s, double wl, double wr, double dt);
 /* getObservations' post-processing (aruco_slam.cpp:325-374) on host arrays; returns the kept
  * observations in detection order through out (capacity n), *n_out = count. */
 int  b2a_slam_make_observations(b2a_slam *s, const float *corners, const int32_t *ids, const double *rvecs,
                                 const double *tvecs, int n, const b2a_camera *cam,
                                 b2a_observation *out, int *n_out);
-/* The EKF loop of addImage (aruco_slam.cpp:88-263) for one frame's observations. */
+/* The EKF loop of addImage (aruco_slam.cpp:88-263) for one frame's observations, given in detection order (the order
+ * getObservations pushes them, :373); they are processed in the order the reference's priority queue pops them.  The
+ * kernels are enqueued on the handle's stream; the call does not wait for them. */
 int  b2a_slam_update(b2a_slam *s, const b2a_observation *obs, int n);
 /* The EKF kernels are enqueued on the handle's stream; get_state waits for them, and so does this (used to time updates). */
 int  b2a_slam_synchronize(b2a_slam *s);
@@ -220,9 +224,13 @@ typedef struct {
     double covariance[36];
 } b2a_pose_with_covariance;
 int  b2a_slam_robot_pose(b2a_slam *s, b2a_pose_with_covariance *out);
+/* the packing step alone, on host values: mu[0:3] and Sigma[0:3,0:3] row-major (no device access) */
+void b2a_pack_robot_pose(const double mu3[3], const double sigma33[9], b2a_pose_with_covariance *out);
 /* detected_map_ of addImage (aruco_slam.cpp:266-281): one cube per landmark i: id = i (the landmark index, not the aruco id),
  * length = marker_length, position (mu[3+3i], mu[4+3i], 0.3), orientation setRPY(0, 1.5708, mu[5+3i]). */
 int  b2a_slam_detected_map(b2a_slam *s, double marker_length, b2a_map_marker *out, int cap, int *n_out);
+/* one cube of that list from host values: landmark3 = (mu[3+3i], mu[4+3i], mu[5+3i]) (no device access) */
+void b2a_pack_map_marker(int index, double marker_length, const double landmark3[3], b2a_map_marker *out);
 
 #ifdef __cplusplus
 }

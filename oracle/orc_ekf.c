@@ -101,26 +101,53 @@ static void inv3(const double *a, double *t)
 }
 
 typedef struct { orc_observation o; int seq; } qitem;
-static int q_cmp(const void *a, const void *b)
-{   /* std::priority_queue with operator< = (a.index > b.index): pops ascending index.
-     * Order among equal indices is implementation-defined in the reference; ties here keep
-     * detection order (documented in DESIGN.md). */
-    const qitem *x = (const qitem *)a, *y = (const qitem *)b;
-    if (x->o.aruco_index != y->o.aruco_index) return x->o.aruco_index < y->o.aruco_index ? -1 : 1;
-    return x->seq - y->seq;
+/* std::priority_queue<ArucoMarker> (aruco_slam.h:190) with operator< = (a.index > b.index) (:85-88): pops ascending
+ * aruco_index_.  The order among EQUAL indices (all new landmarks carry -1) is decided by the heap algorithm; the
+ * reference is built with GCC, so this restates libstdc++'s std::push_heap / std::pop_heap (bits/stl_heap.h:
+ * __push_heap sift-up, __adjust_heap sift-down to a leaf then sift-up) -- pinned against the reference build
+ * (oracle/_ref) in tests/golden/slam_*.npz. */
+static int q_less(const qitem *a, const qitem *b) { return a->o.aruco_index > b->o.aruco_index; }
+static void heap_push_up(qitem *h, int hole, int top, qitem v)
+{
+    int parent = (hole - 1) / 2;
+    while (hole > top && q_less(&h[parent], &v)) { h[hole] = h[parent]; hole = parent; parent = (hole - 1) / 2; }
+    h[hole] = v;
+}
+static void heap_push(qitem *h, int *n, qitem v) { h[*n] = v; ++*n; heap_push_up(h, *n - 1, 0, v); }
+static qitem heap_pop(qitem *h, int *n)
+{
+    qitem top = h[0];
+    if (*n > 1) {
+        int len = *n - 1;                    /* the heap that remains; value = the old last element */
+        qitem v = h[len];
+        int hole = 0, child = 0;
+        while (child < (len - 1) / 2) {
+            child = 2 * (child + 1);
+            if (q_less(&h[child], &h[child - 1])) child--;
+            h[hole] = h[child]; hole = child;
+        }
+        if ((len & 1) == 0 && child == (len - 2) / 2) { child = 2 * (child + 1); h[hole] = h[child - 1]; hole = child - 1; }
+        heap_push_up(h, hole, 0, v);
+    }
+    --*n;
+    return top;
 }
 
 void orc_ekf_update(orc_ekf *e, const orc_observation *obs_in, int n, int dense)
 {
     if (n <= 0) { e->n_last = 0; return; }
-    qitem *q = (qitem *)malloc(sizeof(qitem) * (size_t)n);
+    qitem *heap = (qitem *)malloc(sizeof(qitem) * (size_t)n), *q = (qitem *)malloc(sizeof(qitem) * (size_t)n);
+    int nh = 0;
     for (int i = 0; i < n; i++) {
-        q[i].o = obs_in[i]; q[i].seq = i;
+        qitem it;
+        it.o = obs_in[i]; it.seq = i;
         int nl = (e->N - 3) / 3, idx = -1;                       /* checkLandmark :423-435 */
         for (int k = 0; k < nl; k++) if (e->ids[k] == obs_in[i].aruco_id) { idx = k; break; }
-        q[i].o.aruco_index = idx;
+        it.o.aruco_index = idx;
+        heap_push(heap, &nh, it);                                /* obs_.push(ob) :373 */
     }
-    qsort(q, (size_t)n, sizeof(qitem), q_cmp);
+    for (int i = 0; i < n; i++) q[i] = heap_pop(heap, &nh);      /* obs_.top(); obs_.pop() :94-95 */
+    free(heap);
     int N0 = e->N;
     double *mu = (double *)malloc(sizeof(double) * (size_t)N0);   /* snapshot :88 */
     memcpy(mu, e->mu, sizeof(double) * (size_t)N0);

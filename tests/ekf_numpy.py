@@ -14,13 +14,52 @@ def norm_angle(a):
     return a
 
 
+def _push_heap(h, v, less):
+    """libstdc++ std::push_heap (bits/stl_heap.h __push_heap): sift the new last element up"""
+    h.append(v)
+    hole = len(h) - 1
+    parent = (hole - 1) // 2
+    while hole > 0 and less(h[parent], v):
+        h[hole] = h[parent]
+        hole = parent
+        parent = (hole - 1) // 2
+    h[hole] = v
+
+
+def _pop_heap(h, less):
+    """libstdc++ std::pop_heap + pop_back (__adjust_heap: sift the hole down to a leaf, then the old last element up)"""
+    top = h[0]
+    v = h.pop()
+    n = len(h)
+    if n == 0:
+        return top
+    hole = child = 0
+    while child < (n - 1) // 2:
+        child = 2 * (child + 1)
+        if less(h[child], h[child - 1]):
+            child -= 1
+        h[hole] = h[child]
+        hole = child
+    if n % 2 == 0 and child == (n - 2) // 2:
+        child = 2 * (child + 1)
+        h[hole] = h[child - 1]
+        hole = child - 1
+    parent = (hole - 1) // 2
+    while hole > 0 and less(h[parent], v):
+        h[hole] = h[parent]
+        hole = parent
+        parent = (hole - 1) // 2
+    h[hole] = v
+    return top
+
+
 class NumpyEkf:
     def __init__(self, Q_k=0.01, kl=0.05, kr=0.05, b=0.09):
         self.Q_k, self.kl, self.kr, self.b = Q_k, kl, kr, b
         self.mu = np.zeros(3)
         self.sigma = np.zeros((3, 3))
         self.id_map = {}
-        self.last = {}     # id -> last_observation_ or None
+        self.last = []     # last_observed_marker_: (id, last_observation_ or None) in the order they were processed
 
     def predict(self, wl, wr, dt):
         dsl, dsr = self.kl * dt * wl, self.kr * dt * wr
@@ -41,13 +80,15 @@ class NumpyEkf:
         self.sigma = Hx @ self.sigma @ Hx.T + F @ (wkh @ su @ wkh.T) @ F.T
 
     def update(self, obs):
-        """obs: list of (id, x, y, theta, R 3x3) in detection order"""
-        items = []
+        """obs: list of (id, x, y, theta, R 3x3) in detection order; processed in the order the reference's
+        std::priority_queue (operator< = index greater, aruco_slam.h:85-88) pops them under libstdc++"""
+        heap = []
+        less = lambda a, b: a[0] > b[0]
         for seq, (aid, x, y, th, R) in enumerate(obs):
-            items.append((self.id_map.get(aid, -1), seq, aid, x, y, th, np.asarray(R, float).reshape(3, 3)))
-        items.sort(key=lambda t: (t[0], t[1]))
+            _push_heap(heap, (self.id_map.get(aid, -1), seq, aid, x, y, th, np.asarray(R, float).reshape(3, 3)), less)
+        items = [_pop_heap(heap, less) for _ in range(len(obs))]
         mu = self.mu.copy()
-        new_last = {}
+        new_last = []
         for idx, _, aid, ox, oy, oth, Rk in items:
             lastobs = None
             if idx >= 0:
@@ -68,8 +109,8 @@ class NumpyEkf:
                                 [0, 0, -1, 0, 0, 1]])
                 Gx = Gxm @ F
                 K = self.sigma @ Gx.T @ np.linalg.inv(Gx @ self.sigma @ Gx.T + Rk)
-                prev = self.last.get(aid, "absent")
-                stationary = (not isinstance(prev, str)) and prev is not None and np.linalg.norm(prev - z) < 0.01
+                prev = next((lo for (i, lo) in self.last if i == aid), None)          # std::find: the first entry with this id
+                stationary = prev is not None and np.linalg.norm(prev - z) < 0.01
                 if not stationary:
                     lastobs = z
                     self.mu = self.mu + K @ ze
@@ -94,5 +135,5 @@ class NumpyEkf:
                 self.sigma = ns
                 self.mu = np.concatenate([self.mu, [map_x, map_y, map_th]])
                 self.id_map.setdefault(aid, (len(self.mu) - 3) // 3 - 1)   # std::map::insert keeps the first
-            new_last[aid] = lastobs
+            new_last.append((aid, lastobs))
         self.last = new_last

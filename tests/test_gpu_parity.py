@@ -325,3 +325,68 @@ def test_border_starting_at_the_first_pixel(aruco, oracle):
             want = np.concatenate(kept).astype(np.int16) if kept else np.zeros((0, 2), np.int16)
             assert np.array_equal(pts[0, si, :len(want)], want)
     det.close()
+
+
+def test_capacity_overflow_is_reported(aruco):
+    """B2A_ERR_CAPACITY (status 3): more markers than max_markers, more quad candidates than max_candidates.  The call
+    fails loudly, the per-frame status names the frame, and the handle stays usable."""
+    from aruco_slam_b200._lib import B2AError
+    frames = np.stack([synth.render_config("C2", 7).image, synth.background(1920, 1080).astype(np.uint8)])
+    dic = D.getPredefinedDictionary(D.DICT_6X6_250)
+    det = aruco.ArucoDetector(dic, max_shape=frames.shape[1:], max_batch=2, max_markers=8)
+    with pytest.raises(B2AError) as e:
+        det.detect_batch(frames)
+    assert e.value.code == 3
+    r = det.detect_batch(frames[1:])                   # the blank frame alone is fine on the same handle
+    assert len(r.ids[0]) == 0
+    det.close()
+    det = aruco.ArucoDetector(dic, max_shape=frames.shape[1:], max_batch=2, max_candidates=32)
+    with pytest.raises(B2AError) as e:
+        det.detect_batch(frames)
+    assert e.value.code == 3
+    det.close()
+
+
+def test_speckled_1080p_batch_fits_at_default_streams(aruco, oracle):
+    """heavy sensor noise at 1080p (about 0.5 M border anchors per frame) at the default sub-batch count and at eight
+    sub-batches: every frame keeps its full share of the border-graph arrays whatever the cut (no B2A_ERR_CAPACITY),
+    and the results equal the oracle's"""
+    B = 3
+    rng = np.random.default_rng(11)
+    frames = np.stack([np.clip(synth.render_config("C2", 40 + b).image.astype(np.float64) + rng.normal(0, 22.0, (1080, 1920)), 0, 255).astype(np.uint8)
+                       for b in range(B)])
+    dic = D.getPredefinedDictionary(D.DICT_6X6_250)
+    det = _detector(aruco, dic, frames.shape[1:], batch=8)        # a handle sized for more frames than the call brings
+    for streams in (0, 8, 1):
+        det.set_streams(streams)
+        r = det.detect_batch(frames)
+        for b in range(B):
+            oc, oi, orj = oracle.detect(frames[b], dic)
+            assert np.array_equal(r.ids[b], oi) and np.array_equal(r.corners[b], oc) and np.array_equal(r.rejected[b], orj), (streams, b)
+    det.close()
+
+
+def test_bench_batch_all_frames(aruco, oracle):
+    """the exact batch bench.py times by default (C2, seeds 0-31), every frame against the oracle, host and device frames"""
+    import torch
+    B = 32
+    frames = synth.render_batch("C2", B, base_seed=0)
+    dic = D.getPredefinedDictionary(D.DICT_6X6_250)
+    det = _detector(aruco, dic, frames.shape[1:], batch=B)
+    K = np.array([[1400.0, 0, 960], [0, 1400.0, 540], [0, 0, 1]])
+    Dist = np.array([0.05, -0.1, 0.001, -0.002, 0.02])
+    r = det.detect_pose_batch(frames, 0.27, K, Dist)
+    dfr = torch.from_numpy(frames).cuda()
+    cam = aruco._camera(K, Dist, 0.27)
+    r2 = det._collect(det.detect_raw(aruco.ArucoDetector.frames_device(dfr.data_ptr(), B, 1080, 1920), cam), True)
+    total = 0
+    for b in range(B):
+        oc, oi, orj = oracle.detect(frames[b], dic)
+        assert np.array_equal(r.ids[b], oi) and np.array_equal(r.corners[b], oc) and np.array_equal(r.rejected[b], orj), b
+        assert np.array_equal(r2.ids[b], oi) and np.array_equal(r2.corners[b], oc) and np.array_equal(r2.rejected[b], orj), b
+        orv, otv = oracle.estimate_pose_single_markers(oc, 0.27, K, Dist)
+        assert np.abs(r.tvecs[b] - otv).max() < 1e-4 and max(synth.rvec_distance(a, c) for a, c in zip(r.rvecs[b], orv)) < 1e-4
+        assert np.array_equal(r.rvecs[b], r2.rvecs[b]) and np.array_equal(r.tvecs[b], r2.tvecs[b])
+        total += len(oi)
+    assert total > 28 * B
+    det.close()

@@ -1,11 +1,13 @@
 """-m gpu: the SLAM half of the path (observation mapping, EKF predict / correct / augment with the
-covariance resident in HBM) through the C ABI, against the CPU oracle (a line-by-line restatement of
-reference src/aruco_slam.cpp:21-74,88-263,325-374,437-471; the reference has no tests for it, so this
-part of the parity is unpinned beyond oracle == independent NumPy restatement, tests/test_oracle_ekf.py).
+covariance resident in HBM) through the C ABI, against
+  * tests/golden/slam_*.npz -- runs of the reference's own src/aruco_slam.cpp (compiled unmodified, oracle/_ref) with
+    cv2 4.13.0 behind its OpenCV calls (tools/make_golden_slam.py): observations, gates, queue order, mu / Sigma per frame;
+  * the CPU oracle (oracle/orc_ekf.c, itself pinned to those files in tests/test_slam_golden.py) on further scenarios.
 Tolerances: FP64 throughout, same update order -> 1e-9 absolute on mu and Sigma (north_star asks 1e-4)."""
 import numpy as np
 import pytest
 
+from conftest import golden
 from test_oracle_ekf import _scenario
 from aruco_slam_b200 import dictionaries as D, synth
 
@@ -26,6 +28,7 @@ def test_ekf_scenario_vs_oracle(oracle, seed):
     from aruco_slam_b200 import slam, _lib
     s = slam.ArucoSlam(image_shape=(64, 64))
     e = oracle.Ekf(oracle.slam_params())
+    s.addEncoder(0, 0, None)                         # the first message only latches (aruco_slam.cpp:24-29)
     for (wl, wr, dt), obs in _scenario(seed):
         s.addEncoder(wl, wr, dt)
         e.predict(wl, wr, dt)
@@ -135,4 +138,121 @@ def test_pose_and_map_records():
         assert (c.length, c.x, c.y, c.z) == (0.27, mu[3 + 3 * i], mu[4 + 3 * i], 0.3)
         q = Rotation.from_euler("xyz", [0, 1.5708, mu[5 + 3 * i]]).as_quat()
         assert np.allclose(c.q, q if np.dot(q, c.q) >= 0 else -q, atol=1e-14)
+    s.close()
+
+
+def _golden_slam(g, **kw):
+    from aruco_slam_b200 import slam
+    s = slam.ArucoSlam(int(g["dict_id"]) if "dict_id" in g else 16, float(g["marker_length"]), r2c_tx=float(g["r2c_t"][0]), r2c_ty=float(g["r2c_t"][1]),
+                       useful_distance_threshold=float(g["useful_distance_threshold"]), **kw)
+    s.setCameraParameters(g["K"], g["D"])
+    return s
+
+
+def _check_obs(obs, g, f):
+    """the kept observations == the reference's (its queue reorders them, so compare as a set keyed by id and x)"""
+    ref_ids, ref_xyt, ref_cov = g["obs_id_%d" % f], g["obs_xyt_%d" % f], g["obs_cov_%d" % f]
+    assert sorted(o.aruco_id for o in obs) == sorted(ref_ids.tolist()), f
+    for o in obs:
+        j = [k for k in range(len(ref_ids)) if ref_ids[k] == o.aruco_id and abs(ref_xyt[k, 0] - o.x) < 1e-6]
+        assert j, (f, o.aruco_id)
+        assert np.abs(ref_xyt[j[0]] - [o.x, o.y, o.theta]).max() < 1e-9
+        assert np.abs(ref_cov[j[0]] - np.array(o.cov[:])).max() < 1e-9
+
+
+def test_observations_and_ekf_vs_reference_run_synth():
+    """slam_synth: detections replayed into the reference -- range gate and covariance gate rejecting (aruco_slam.cpp:327-333,
+    367-368), >= 3 new landmarks in one frame (heap order), duplicates, repeated frames (stationary gate :192-198)"""
+    g = golden("slam_synth")
+    s = _golden_slam(g, image_shape=(64, 64))
+    s.update([])                                       # nothing before the first encoder message changes the state
+    s.addEncoder(1.0, 1.0, 0.05)                       # latch only (:24-29)
+    mu, sg, _ = s.get_state()
+    assert len(mu) == 3 and not mu.any() and not sg.any()
+    n_gated = 0
+    for f in range(int(g["n_frames"])):
+        for wl, wr, dt in g["enc_%d" % f]:
+            s.addEncoder(wl, wr, dt)
+        c, ids, rv, tv = (g["det_%s_%d" % (k, f)] for k in ("corners", "ids", "rvecs", "tvecs"))
+        obs = s.make_observations(c, ids, rv, tv)
+        n_gated += len(ids) - len(obs)
+        _check_obs(obs, g, f)
+        s.update(obs)
+        mu, sg, lm = s.get_state()
+        assert np.array_equal(lm, g["ids_%d" % f]), f          # landmark order = the reference's priority-queue order
+        assert np.abs(mu - g["mu_%d" % f]).max() < 1e-9 and np.abs(sg - g["sigma_%d" % f]).max() < 1e-9, f
+    assert n_gated >= 10
+    from aruco_slam_b200 import formats
+    p = formats.robot_pose(s)
+    rec = g["pose_%d" % (int(g["n_frames"]) - 1)]
+    assert np.abs(np.concatenate([p.position, p.orientation, p.covariance.ravel()]) - rec).max() < 1e-9
+    cubes = formats.detected_map(s)
+    assert [c.id for c in cubes] == g["map_id"].tolist()
+    assert np.abs(np.array([[c.x, c.y, c.z] for c in cubes]) - g["map_pos"]).max() < 1e-9
+    assert np.abs(np.array([c.q for c in cubes]) - g["map_q"]).max() < 1e-9
+    s.close()
+
+
+def test_add_image_vs_reference_run_scene():
+    """slam_scene: the reference's addImage on rendered frames of a map.txt-style room (DICT_ARUCO_ORIGINAL, the intrinsics
+    of /root/reference/default.yaml:10-20), cv2 behind its detectMarkers / solvePnP.  addImage on the GPU: ids / corners
+    bit-exact, poses 1e-4, and the filter state within what the pose tolerance allows (1e-4)."""
+    g = golden("slam_scene")
+    frames = g["frames"]
+    s = _golden_slam(g, image_shape=frames.shape[1:])
+    s.addEncoder(0, 0, None)
+    for f in range(int(g["n_frames"])):
+        for wl, wr, dt in g["enc_%d" % f]:
+            s.addEncoder(wl, wr, dt)
+        r = s.detector.detect_pose_batch(frames[f], float(g["marker_length"]), g["K"], g["D"])
+        assert np.array_equal(r.ids[0], g["det_ids_%d" % f]) and np.array_equal(r.corners[0], g["det_corners_%d" % f]), f
+        if len(r.ids[0]):
+            assert np.abs(r.tvecs[0] - g["det_tvecs_%d" % f]).max() < 1e-4
+            assert max(synth.rvec_distance(a, b) for a, b in zip(r.rvecs[0], g["det_rvecs_%d" % f])) < 1e-4
+        obs = s.make_observations(r.corners[0], r.ids[0], r.rvecs[0], r.tvecs[0])
+        assert sorted(o.aruco_id for o in obs) == sorted(g["obs_id_%d" % f].tolist()), f
+        s.addImage(frames[f])
+        mu, sg, lm = s.get_state()
+        assert np.array_equal(lm, g["ids_%d" % f]), f
+        assert np.abs(mu - g["mu_%d" % f]).max() < 1e-4 and np.abs(sg - g["sigma_%d" % f]).max() < 1e-4, f
+    s.close()
+
+
+def test_add_image_on_golden_detections_is_exact():
+    """the same scene with the reference run's own detections fed through make_observations + update: 1e-9"""
+    g = golden("slam_scene")
+    s = _golden_slam(g, image_shape=(64, 64))
+    s.addEncoder(0, 0, None)
+    for f in range(int(g["n_frames"])):
+        for wl, wr, dt in g["enc_%d" % f]:
+            s.addEncoder(wl, wr, dt)
+        obs = s.make_observations(*(g["det_%s_%d" % (k, f)] for k in ("corners", "ids", "rvecs", "tvecs")))
+        _check_obs(obs, g, f)
+        s.update(obs)
+        mu, sg, lm = s.get_state()
+        assert np.array_equal(lm, g["ids_%d" % f])
+        assert np.abs(mu - g["mu_%d" % f]).max() < 1e-9 and np.abs(sg - g["sigma_%d" % f]).max() < 1e-9, f
+    s.close()
+
+
+@pytest.mark.parametrize("name", ["slam_c5_n153", "slam_c5_n1503"])
+def test_c5_vs_reference_run(name):
+    """EKF-only workload (BASELINE config 5): 30 corrections of known landmarks per frame from a dense SPD Sigma0"""
+    g = golden(name)
+    n_lm = int(g["n_lm"])
+    s = _golden_slam(g, image_shape=(64, 64), max_landmarks=n_lm + 4)
+    s.set_state(*synth.c5_state(n_lm))
+    for f in range(int(g["n_frames"])):
+        obs = s.make_observations(*(g["det_%s_%d" % (k, f)] for k in ("corners", "ids", "rvecs", "tvecs")))
+        assert len(obs) == 30
+        s.update(obs)
+        mu, sg, _ = s.get_state()
+        assert np.abs(mu - g["mu_%d" % f]).max() < 1e-9
+        if "sigma_%d" % f in g:
+            assert np.abs(sg - g["sigma_%d" % f]).max() < 1e-9
+        else:
+            assert np.abs(np.diag(sg) - g["sigma_diag_%d" % f]).max() < 1e-9
+            assert np.abs(sg[[0, 1, 2, 3 + 3 * (n_lm // 2), len(mu) - 1]] - g["sigma_rows_%d" % f]).max() < 1e-9
+            assert np.abs(sg[::37, ::41] - g["sigma_sample_%d" % f]).max() < 1e-9
+            assert abs(np.linalg.norm(sg) - float(g["sigma_fro_%d" % f])) < 1e-7
     s.close()
