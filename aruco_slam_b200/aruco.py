@@ -155,6 +155,32 @@ class ArucoDetector:
             _lib.check(_lib.lib().b2a_detect_pose(self._h, C.byref(frames), C.byref(camera), C.byref(det)))
         return det
 
+    def submit_raw(self, frames, camera=None) -> int:
+        """enqueue one batch (H2D copies + kernels) and return its ticket; up to two batches in flight per handle"""
+        t = C.c_int(-1)
+        _lib.check(_lib.lib().b2a_detect_pose_submit(self._h, C.byref(frames), C.byref(camera) if camera is not None else None, C.byref(t)))
+        return t.value
+
+    def wait_raw(self, ticket: int):
+        """block until the batch of `ticket` is complete; the C struct's pinned buffers stay valid until the second next submit"""
+        det = _lib.Detections()
+        _lib.check(_lib.lib().b2a_detect_pose_wait(self._h, int(ticket), C.byref(det)))
+        return det
+
+    def detect_pose_stream(self, batches, marker_length, K, D):
+        """generator over an iterable of (B, H, W) host batches: batch k+1 is submitted before batch k is waited for, so its
+        PCIe copy runs under batch k's kernels (one host thread, one handle)"""
+        cam = _camera(K, D, marker_length)
+        pending = None
+        for images in batches:
+            fr, keep = self._frames_host(images) if not isinstance(images, _lib.Frames) else (images, None)
+            t = self.submit_raw(fr, cam)
+            if pending is not None:
+                yield self._collect(self.wait_raw(pending[0]), True)
+            pending = (t, fr, keep)
+        if pending is not None:
+            yield self._collect(self.wait_raw(pending[0]), True)
+
     def detect_batch(self, images) -> BatchDetections:
         fr, keep = self._frames_host(images) if not isinstance(images, _lib.Frames) else (images, None)
         return self._collect(self.detect_raw(fr), False)

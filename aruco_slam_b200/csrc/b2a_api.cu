@@ -238,6 +238,12 @@ struct b2a_detector {
     bool ev_used[ST_COUNT + 1];
     float stage_ms[ST_COUNT];
     int launches = 0;
+    int timed_mode = 0;
+    // asynchronous submit / wait: the handle owns a second, lazily created pipeline context (all buffers and streams); batches
+    // alternate between the two, so the H2D copy of one overlaps the kernels of the other
+    b2a_detector *twin = nullptr;
+    bool in_flight = false, pending_pose = false; int pending_batch = 0;
+    unsigned next_ticket = 0;
     std::vector<void *> allocs, pinned;
 };
 
@@ -266,6 +272,7 @@ static int pin_alloc(b2a_detector *d, T **p, size_t count)
 extern "C" void b2a_detector_destroy(b2a_detector *d)
 {
     if (!d) return;
+    if (d->twin) { b2a_detector_destroy(d->twin); d->twin = nullptr; }
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
     for (void *p : d->allocs) cudaFree(p);
@@ -319,7 +326,7 @@ static int create_impl(b2a_detector *d)
     TRY(dev_alloc(d, &d->d_surv, FS * d->surv_cap));
     TRY(dev_alloc(d, &d->d_sorted, FS * d->surv_cap));
     TRY(dev_alloc(d, &d->d_pts_off, FS * d->surv_cap));
-    d->pts_cap = (int)std::max<size_t>(P / 4, 1 << 16);
+    d->pts_cap = (int)std::max<size_t>(P, 1 << 16);          // points of the kept borders of one mask: a speckled 1080p mask reaches 0.3 P
     TRY(dev_alloc(d, &d->d_pts, FS * (size_t)d->pts_cap));
     TRY(dev_alloc(d, &d->d_quad_ok, FS * d->surv_cap));
     TRY(dev_alloc(d, &d->d_quad_xy, FS * d->surv_cap * 8));
@@ -640,12 +647,14 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
     fa.surv_count = d->d_surv_count + fs0; fa.quad_ok = d->d_quad_ok + fs0 * g.surv_cap; fa.quad_xy = d->d_quad_xy + fs0 * g.surv_cap * 8;
     fa.quad_len = d->d_quad_len + fs0 * g.surv_cap;
     fa.marks = nullptr;
+#ifdef B2A_DEBUG_TAPS
     static long long *dbg_marks = nullptr;
     if (std::getenv("B2A_GROUP_MARKS")) {
         if (!dbg_marks) { cudaMalloc(&dbg_marks, (size_t)d->cfg.max_batch * 32 * sizeof(long long)); }
         cudaMemsetAsync(dbg_marks, 0, (size_t)d->cfg.max_batch * 32 * sizeof(long long), st);
         fa.marks = dbg_marks + (size_t)b0 * 32;
     }
+#endif
     const FrameParams fp = frame_params(d, g);
     stage_mark(d, s, ST_GROUP);
     const int smem_words = 50 * 1024;                       // 200 KB: per-candidate arrays + closeness matrix
@@ -653,6 +662,7 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
     k_close<<<dim3(CLOSE_CTAS, nb), 256, 0, st>>>(fa, fp);
     k_group<<<nb, 1024, smem_words * sizeof(uint32_t), st>>>(fa, fp, smem_words);
     d->launches += 3;
+#ifdef B2A_DEBUG_TAPS
     if (fa.marks && s.sb == 0) {
         long long hm[32];
         cudaStreamSynchronize(st);
@@ -661,6 +671,7 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
         for (int i = 1; i < 32 && hm[i]; ++i) std::fprintf(stderr, hm[i] < 0 ? " (%lld)" : " %lld", std::llabs(hm[i]) - std::llabs(hm[i - 1]));
         std::fprintf(stderr, "\n");
     }
+#endif
     if (stop_after_group) return launch_err("k_group");
     stage_mark(d, s, ST_IDENT);
     IdentParams ip;
@@ -671,6 +682,7 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
     ip.detectInverted = d->prm.detectInvertedMarker ? 1 : 0;
     ip.minOtsuStdDev = d->prm.minOtsuStdDev; ip.W = g.W; ip.H = g.H; ip.pitch = s.pitch; ip.frame_stride = s.frame_stride; ip.max_cand = d->max_cand;
     ip.marks = nullptr;
+#ifdef B2A_DEBUG_TAPS
     static long long *id_marks = nullptr;
     if (std::getenv("B2A_IDENT_MARKS") && s.sb == 0) {
         const size_t nrec = 16 + (size_t)d->cfg.max_batch * 128 * 3;
@@ -678,12 +690,14 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
         cudaMemsetAsync(id_marks, 0, nrec * sizeof(long long), st);
         ip.marks = id_marks;
     }
+#endif
     double *wM = d->d_wM + (size_t)b0 * d->max_cand * 9;
     k_homography<<<dim3(4, nb), 64, 0, st>>>(fa, wM, (ip.markerSize + 2 * ip.borderBits) * ip.cellSize, d->max_cand);
     d->launches++;
     static const int id_blocks = std::getenv("B2A_ID_BLOCKS") ? std::max(1, std::atoi(std::getenv("B2A_ID_BLOCKS"))) : 48;   // x 4 warps = work items of a frame in flight (a frame has ~124 of them; with 128 warps the frames that have more made a second round: 0.118 -> 0.102 ms)
     k_identify<<<dim3(id_blocks, nb), ID_THREADS, identify_smem_bytes((ip.markerSize + 2 * ip.borderBits) * ip.cellSize), st>>>(s.gray, d->d_dict, wM, fa, ip);
     d->launches++;
+#ifdef B2A_DEBUG_TAPS
     if (ip.marks) {
         long long hm[16];
         cudaStreamSynchronize(st);
@@ -701,6 +715,7 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
         if (cnt) std::fprintf(stderr, "k_identify items %d: span %lld ns, item ns min %lld median %lld p90 %lld max %lld, latest start +%lld ns\n", cnt, t1 - t0, dur[0], dur[cnt / 2],
                               dur[cnt * 9 / 10], dur[cnt - 1], latest_start);
     }
+#endif
     stage_mark(d, s, ST_FINAL);
     k_finalize<<<nb, 128, 8 * sizeof(int32_t) * d->max_cand, st>>>(fa, fp);
     d->launches++;
@@ -716,17 +731,20 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
         corners = c2;
     }
     stage_mark(d, s, ST_POSE);
-    static long long *pose_marks_buf = nullptr;
     long long *pose_marks = nullptr;
+#ifdef B2A_DEBUG_TAPS
+    static long long *pose_marks_buf = nullptr;
     if (std::getenv("B2A_POSE_MARKS") && s.sb == 0) {
         if (!pose_marks_buf) cudaMalloc(&pose_marks_buf, 32 * sizeof(long long));
         cudaMemsetAsync(pose_marks_buf, 0, 32 * sizeof(long long), st);
         pose_marks = pose_marks_buf;
     }
+#endif
     if (cam) {
         k_pose<<<(nb * (int)K * 32 + POSE_THREADS - 1) / POSE_THREADS, POSE_THREADS, 0, st>>>(corners, fa.fo0.n_accepted, nb, d->max_markers, to_camera(cam), cam->marker_length,
                                                         d->d_rvecs + (size_t)b0 * K * 3, d->d_tvecs + (size_t)b0 * K * 3, pose_marks);
         d->launches++;
+#ifdef B2A_DEBUG_TAPS
         if (pose_marks) {
             long long hm[32];
             cudaStreamSynchronize(st);
@@ -735,6 +753,7 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
             for (int i = 1; i < 32 && hm[i]; ++i) std::fprintf(stderr, " %lld", hm[i] - hm[i - 1]);
             std::fprintf(stderr, "\n");
         }
+#endif
     }
     stage_mark(d, s, ST_D2H);
     {
@@ -752,16 +771,17 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
 }
 
 // mode: 0 full pipeline, 1 stop after the front end (taps), 2 stop after grouping (candidate tap)
-// post: work the caller appends on the handle's stream after the sub-batches have joined, before the one synchronisation of the call
-static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *cam, int mode, int walk_max_len, std::vector<Sub> *subs_out,
-                        const std::function<int(cudaStream_t)> *post = nullptr)
+// post: work the caller appends on the handle's stream after the sub-batches have joined
+// enqueue_pipeline returns as soon as everything is queued; finish_pipeline is the one synchronisation of a call
+static int enqueue_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *cam, int mode, int walk_max_len, std::vector<Sub> *subs_out,
+                            const std::function<int(cudaStream_t)> *post = nullptr)
 {
-    const auto t_call = std::chrono::steady_clock::now();
     TRY(check_frames(d, f));
     CU(cudaSetDevice(d->device));
     const int B = f->batch, W = f->width, H = f->height;
     std::memset(d->ev_used, 0, sizeof(d->ev_used));
     d->launches = 0;
+    d->timed_mode = mode;
     cudaStream_t s0 = d->stream;
     if (W != d->lastW || H != d->lastH || B > d->lastB) {       // padding words / rows of the masks must be zero
         CU(cudaMemsetAsync(d->d_masks, 0, d->masks_words * sizeof(uint32_t), s0));
@@ -778,9 +798,10 @@ static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *
     // sub-batch boundaries.  Frames that still have to cross PCIe are cut unevenly: a small first sub-batch lets the
     // kernels start early and a small last one shortens the tail that nothing overlaps (B2A_SPLIT="2,6,8,8,6,2" overrides)
     std::vector<int> bounds;
-    if (const char *e = std::getenv("B2A_SPLIT")) {
+    static const char *split_env = std::getenv("B2A_SPLIT");
+    if (split_env) {
         std::vector<int> w;
-        for (const char *p = e; *p;) { w.push_back(std::max(1, std::atoi(p))); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+        for (const char *p = split_env; *p;) { w.push_back(std::max(1, std::atoi(p))); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
         if ((int)w.size() > d->n_sub_max) w.resize(d->n_sub_max);
         int tot = 0; for (int v : w) tot += v;
         bounds.push_back(0);
@@ -804,6 +825,7 @@ static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *
     }
     CU(cudaEventRecord(d->ev_fork, s0));
     for (int i = 1; i < nsub; ++i) CU(cudaStreamWaitEvent(subs[i].st, d->ev_fork, 0));
+#ifdef B2A_DEBUG_TAPS
     // B2A_TIMELINE=1: per sub-batch, when its frames were in HBM and when its results were out (ms after the call began)
     static const bool timeline = std::getenv("B2A_TIMELINE") != nullptr;
     static cudaEvent_t tl_ev[1 + 2 * b2a_detector::MAX_SUB] = {};
@@ -811,24 +833,22 @@ static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *
         if (!tl_ev[0]) for (auto &e : tl_ev) cudaEventCreate(&e);
         cudaEventRecord(tl_ev[0], s0);
     }
+#endif
     for (int i = 0; i < nsub; ++i) {
+#ifdef B2A_DEBUG_TAPS
         subs[i].tl_after_h2d = timeline ? tl_ev[1 + 2 * i] : nullptr;
+#endif
         TRY(run_front(d, f, subs[i], walk_max_len));
         if (mode != 1) TRY(run_back(d, subs[i], cam, mode == 2));
+#ifdef B2A_DEBUG_TAPS
         if (timeline) cudaEventRecord(tl_ev[2 + 2 * i], subs[i].st);
+#endif
     }
     for (int i = 1; i < nsub; ++i) { CU(cudaEventRecord(d->ev_join[i], subs[i].st)); CU(cudaStreamWaitEvent(s0, d->ev_join[i], 0)); }
     if (post) TRY((*post)(s0));
-    static const bool host_time = std::getenv("B2A_HOSTTIME") != nullptr;     // debug: host time spent enqueueing against the whole call
-    const auto t_enq = std::chrono::steady_clock::now();
-    CU(cudaStreamSynchronize(s0));
-    if (host_time) {
-        static double acc_e = 0, acc_t = 0; static int cnt = 0;
-        const auto t_end = std::chrono::steady_clock::now();
-        acc_e += std::chrono::duration<double, std::milli>(t_enq - t_call).count(); acc_t += std::chrono::duration<double, std::milli>(t_end - t_call).count();
-        if (++cnt % 20 == 0) { std::fprintf(stderr, "host: enqueue %.3f ms of %.3f ms per call (%d launches)\n", acc_e / 20, acc_t / 20, d->launches); acc_e = acc_t = 0; }
-    }
+#ifdef B2A_DEBUG_TAPS
     if (timeline && mode == 0) {
+        cudaStreamSynchronize(s0);
         std::fprintf(stderr, "timeline (ms): ");
         for (int i = 0; i < nsub; ++i) {
             float a = 0, b = 0;
@@ -837,7 +857,16 @@ static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *
         }
         std::fprintf(stderr, "\n");
     }
-    if (mode == 0) {
+#endif
+    if (subs_out) *subs_out = subs;
+    return B2A_OK;
+}
+
+static int finish_pipeline(b2a_detector *d)
+{
+    CU(cudaSetDevice(d->device));
+    CU(cudaStreamSynchronize(d->stream));
+    if (d->timed_mode == 0) {
         int prev = -1;
         for (int i = 0; i < ST_COUNT; ++i) d->stage_ms[i] = 0.f;
         for (int i = 0; i <= ST_COUNT; ++i) {
@@ -846,7 +875,30 @@ static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *
             prev = i;
         }
     }
-    if (subs_out) *subs_out = subs;
+    return B2A_OK;
+}
+
+static int run_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *cam, int mode, int walk_max_len, std::vector<Sub> *subs_out,
+                        const std::function<int(cudaStream_t)> *post = nullptr)
+{
+    if (d && d->in_flight) return set_err(B2A_ERR_INVALID, "a submitted batch is still in flight on this handle (b2a_detect_pose_wait first)");
+#ifdef B2A_DEBUG_TAPS
+    static const bool host_time = std::getenv("B2A_HOSTTIME") != nullptr;     // debug: host time spent enqueueing against the whole call
+    const auto t_call = std::chrono::steady_clock::now();
+#endif
+    TRY(enqueue_pipeline(d, f, cam, mode, walk_max_len, subs_out, post));
+#ifdef B2A_DEBUG_TAPS
+    const auto t_enq = std::chrono::steady_clock::now();
+#endif
+    TRY(finish_pipeline(d));
+#ifdef B2A_DEBUG_TAPS
+    if (host_time) {
+        static double acc_e = 0, acc_t = 0; static int cnt = 0;
+        const auto t_end = std::chrono::steady_clock::now();
+        acc_e += std::chrono::duration<double, std::milli>(t_enq - t_call).count(); acc_t += std::chrono::duration<double, std::milli>(t_end - t_call).count();
+        if (++cnt % 20 == 0) { std::fprintf(stderr, "host: enqueue %.3f ms of %.3f ms per call (%d launches)\n", acc_e / 20, acc_t / 20, d->launches); acc_e = acc_t = 0; }
+    }
+#endif
     return B2A_OK;
 }
 
@@ -873,6 +925,37 @@ extern "C" int b2a_detect_pose(b2a_detector *d, const b2a_frames *frames, const 
     if (!(cam->marker_length > 0)) return set_err(B2A_ERR_INVALID, "markerLength <= 0");
     TRY(run_pipeline(d, frames, cam, 0, 0, nullptr));
     return fill_out(d, frames->batch, true, out);
+}
+
+extern "C" int b2a_detect_pose_submit(b2a_detector *d, const b2a_frames *frames, const b2a_camera *cam, int *ticket)
+{
+    if (!d || !frames || !ticket) return set_err(B2A_ERR_INVALID, "null argument");
+    if (cam && !(cam->marker_length > 0)) return set_err(B2A_ERR_INVALID, "markerLength <= 0");
+    b2a_detector *t = d;
+    if (d->next_ticket & 1u) {
+        if (!d->twin) {                                        // the second context is created on first use
+            TRY(b2a_detector_create(&d->cfg, &d->dict, &d->prm, &d->twin));
+        }
+        t = d->twin;
+        t->n_streams = d->n_streams;
+    }
+    if (t->in_flight) return set_err(B2A_ERR_INVALID, "two batches are already in flight on this handle (b2a_detect_pose_wait first)");
+    TRY(enqueue_pipeline(t, frames, cam, 0, 0, nullptr));
+    t->in_flight = true; t->pending_pose = cam != nullptr; t->pending_batch = frames->batch;
+    *ticket = (int)d->next_ticket++;
+    return B2A_OK;
+}
+
+extern "C" int b2a_detect_pose_wait(b2a_detector *d, int ticket, b2a_detections *out)
+{
+    if (!d || !out) return set_err(B2A_ERR_INVALID, "null argument");
+    b2a_detector *t = (ticket & 1) ? d->twin : d;
+    if (!t || !t->in_flight || (unsigned)ticket + 2 < d->next_ticket || (unsigned)ticket >= d->next_ticket)
+        return set_err(B2A_ERR_INVALID, "no batch in flight under this ticket");
+    t->in_flight = false;
+    TRY(finish_pipeline(t));
+    if (t != d) { d->launches = t->launches; std::memcpy(d->stage_ms, t->stage_ms, sizeof(d->stage_ms)); }
+    return fill_out(t, t->pending_batch, t->pending_pose, out);
 }
 
 extern "C" int b2a_detector_set_streams(b2a_detector *d, int n)

@@ -126,6 +126,17 @@ typedef struct {
 /* detectMarkers + estimatePoseSingleMarkers without leaving the device (aruco_slam.cpp:313-314). */
 int b2a_detect_pose(b2a_detector *d, const b2a_frames *frames, const b2a_camera *cam, b2a_detections *out);
 
+/* The same call split in two, so that one host thread keeps two batches in flight on ONE handle: submit enqueues the H2D
+ * copies and every kernel of a batch and returns at once (cam = NULL: detect only); wait blocks until that batch's results
+ * are in host memory and fills `out`.  Tickets alternate between two internal pipeline contexts (the second is created on
+ * the first odd ticket), so the PCIe copy of batch k+1 overlaps the kernels of batch k:
+ *     submit(k+1) ... wait(k) ... submit(k+2) ... wait(k+1) ...
+ * At most two batches in flight; waits in submission order; frames->data must stay valid until the matching wait; the
+ * arrays `out` points to stay valid until the second submit after it.  The synchronous calls above refuse to run while a
+ * batch is in flight on the first context. */
+int b2a_detect_pose_submit(b2a_detector *d, const b2a_frames *frames, const b2a_camera *cam, int *ticket);
+int b2a_detect_pose_wait(b2a_detector *d, int ticket, b2a_detections *out);
+
 /* estimatePoseSingleMarkers on caller-provided corners (host arrays): corners [n][4][2] f32,
  * rvecs/tvecs [n][3] f64.  (aruco_slam.cpp:314) */
 int b2a_estimate_pose_single_markers(b2a_detector *d, const float *corners, int n, const b2a_camera *cam,

@@ -390,3 +390,40 @@ def test_bench_batch_all_frames(aruco, oracle):
         total += len(oi)
     assert total > 28 * B
     det.close()
+
+
+def test_submit_wait_matches_synchronous_calls(aruco, oracle):
+    """b2a_detect_pose_submit / _wait: two batches in flight on one handle give the results of the synchronous call, in
+    order; the misuse cases fail loudly"""
+    from aruco_slam_b200._lib import B2AError
+    B = 4
+    batches = [synth.render_batch("C2", B, base_seed=200 + 10 * k) for k in range(5)]
+    dic = D.getPredefinedDictionary(D.DICT_6X6_250)
+    det = _detector(aruco, dic, batches[0].shape[1:], batch=B)
+    K = np.array([[1400.0, 0, 960], [0, 1400.0, 540], [0, 0, 1]])
+    Dist = np.array([0.05, -0.1, 0.001, -0.002, 0.02])
+    want = [det.detect_pose_batch(b, 0.27, K, Dist) for b in batches]
+    got = list(det.detect_pose_stream(batches, 0.27, K, Dist))
+    assert len(got) == len(want)
+    for w, g in zip(want, got):
+        for b in range(B):
+            assert np.array_equal(w.ids[b], g.ids[b]) and np.array_equal(w.corners[b], g.corners[b]) and np.array_equal(w.rejected[b], g.rejected[b])
+            assert np.array_equal(w.rvecs[b], g.rvecs[b]) and np.array_equal(w.tvecs[b], g.tvecs[b])
+    oc, oi, _ = oracle.detect(batches[3][1], dic)
+    assert np.array_equal(got[3].ids[1], oi) and np.array_equal(got[3].corners[1], oc)
+    # misuse: a third submit, a synchronous call while a batch is in flight, a stale ticket
+    cam = aruco._camera(K, Dist, 0.27)
+    fr, keep = det._frames_host(batches[0])
+    t0 = det.submit_raw(fr, cam)
+    t1 = det.submit_raw(fr, cam)
+    with pytest.raises(B2AError):
+        det.submit_raw(fr, cam)
+    with pytest.raises(B2AError):
+        det.detect_pose_batch(batches[0], 0.27, K, Dist)
+    det.wait_raw(t0)
+    with pytest.raises(B2AError):
+        det.wait_raw(t0)
+    r = det._collect(det.wait_raw(t1), True)
+    assert np.array_equal(r.ids[0], want[0].ids[0])
+    det.detect_pose_batch(batches[0], 0.27, K, Dist)          # and the synchronous call works again
+    det.close()
