@@ -205,6 +205,7 @@ struct b2a_detector {
     int n_sub_max = MAX_SUB, n_streams = 0;       // 0 = automatic: 2 sub-batches for frames already in HBM, 4 when they still cross PCIe
     int nScales = 0, radius[MAX_SCALES];
     bool thresh_tiles = false;
+    int tm_variant = 0;                           // marching threshold kernel: 0 = 24-row chunks (3 CTAs per SM), 1 / 2 = 12-row chunks (4 / 5 CTAs per SM)
     int max_cand = 0, max_markers = 0, surv_cap = 0;
     size_t gray_pitch = 0;
     // device memory
@@ -371,7 +372,10 @@ static int create_impl(b2a_detector *d)
     CU(cudaFuncSetAttribute(k_group_a, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (d->max_cand + 1) * (int)sizeof(uint32_t)));
     CU(cudaFuncSetAttribute(k_identify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)identify_smem_bytes(ID_MAX_S)));
     CU(cudaFuncSetAttribute(k_threshold3<1, 6, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3_SMEM));
-    CU(cudaFuncSetAttribute(k_threshold_march<1, 6, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM));
+    CU(cudaFuncSetAttribute(k_threshold_march<1, 6, 11, 24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmCfg<24>::SMEM));
+    CU(cudaFuncSetAttribute(k_threshold_march<1, 6, 11, 12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmCfg<12>::SMEM));
+    CU(cudaFuncSetAttribute(k_threshold_march<1, 6, 11, 12, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmCfg<12>::SMEM));
+    if (const char *e = std::getenv("B2A_TM_VARIANT")) d->tm_variant = std::atoi(e);
     d->thresh_tiles = std::getenv("B2A_THRESH_TILES") != nullptr;          // A/B switch: the tiled kernel (k_threshold3) instead of the marching one
     CU(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (int)sizeof(int32_t) * d->max_cand));
     CU(cudaStreamSynchronize(d->stream));
@@ -569,7 +573,8 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
         if (default_windows && aligned4 && !d->thresh_tiles) {
             // marching kernel: work items = (frame, 320-column strip, Hs-row segment); Hs is the tallest segment that still gives every
             // resident CTA slot an item (a segment costs 22 rows of prefix warm-up)
-            const int n_sx = (W + TM_WT - 1) / TM_WT, slots = d->num_sms * 3;
+            const int ctas_per_sm = d->tm_variant == 0 ? 3 : d->tm_variant == 1 ? 4 : 5;
+            const int n_sx = (W + TM_WT - 1) / TM_WT, slots = d->num_sms * ctas_per_sm;
             int Hs = TM_RC;
             double best = -1.0;
             for (int h = TM_RC; h <= TM_MAX_HS; h += TM_RC) {
@@ -579,7 +584,9 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
                 if (score > best * 1.0001) { best = score; Hs = h; }
             }
             const int n_sy = (H + Hs - 1) / Hs, n_items = nb * n_sx * n_sy;
-            k_threshold_march<1, 6, 11><<<std::min(n_items, slots), TM_THREADS, TM_SMEM, st>>>(s.gray, (uint32_t)s.pitch, s.frame_stride, masks, g, Hs, n_sy, n_sx, n_items);
+            if (d->tm_variant == 0) k_threshold_march<1, 6, 11, 24, 3><<<std::min(n_items, slots), TM_THREADS, TmCfg<24>::SMEM, st>>>(s.gray, (uint32_t)s.pitch, s.frame_stride, masks, g, Hs, n_sy, n_sx, n_items);
+            else if (d->tm_variant == 1) k_threshold_march<1, 6, 11, 12, 4><<<std::min(n_items, slots), TM_THREADS, TmCfg<12>::SMEM, st>>>(s.gray, (uint32_t)s.pitch, s.frame_stride, masks, g, Hs, n_sy, n_sx, n_items);
+            else k_threshold_march<1, 6, 11, 12, 5><<<std::min(n_items, slots), TM_THREADS, TmCfg<12>::SMEM, st>>>(s.gray, (uint32_t)s.pitch, s.frame_stride, masks, g, Hs, n_sy, n_sx, n_items);
         } else if (default_windows) {
             dim3 grid((W + T3_TW - 1) / T3_TW, (H + T3_TH - 1) / T3_TH, nb);
             k_threshold3<1, 6, 11><<<grid, T3_THREADS, T3_SMEM, st>>>(s.gray, s.pitch, s.frame_stride, masks, g);

@@ -290,17 +290,25 @@ constexpr int TM_WT = 320;                            // output columns of a str
 constexpr int TM_HALO = 12;                           // >= largest radius + 1, multiple of 4
 constexpr int TM_VCOLS = TM_WT + 2 * TM_HALO;         // 344 columns of V per strip row
 constexpr int TM_VG = TM_VCOLS / 4;                   // 86 four-column groups = V-phase threads
-constexpr int TM_RC = 24;                             // rows per chunk = length of the prefix ring
-constexpr int TM_SEG = 64;                            // output columns of one H-phase thread
-constexpr int TM_NSEG = TM_WT / TM_SEG;               // 5
+constexpr int TM_RING = 24;                           // length of the prefix ring (largest window + 1)
 constexpr int TM_THREADS = 128;
 constexpr int TM_VPITCH = TM_VG * 8;                  // 688 bytes per plane row: 43 x 16 (odd => 16-byte loads of 8 rows hit 8 bank groups)
-constexpr int TM_GROWS = 48;                          // raw-row ring of the centre pixels: two chunks, so every slot is a compile-time offset
 constexpr int TM_GPITCH = TM_WT + 16;                 // 336 = 21 x 16
 constexpr int TM_MAX_HS = 216;                        // (Hs + 22) * 255 < 2^16
-constexpr size_t TM_SMEM = (size_t)3 * TM_RC * TM_VPITCH + (size_t)TM_GROWS * TM_GPITCH + (size_t)TM_RC * TM_VG * 4;
+// RC = rows per chunk (24 or 12): the three u16 planes of a chunk are what shared memory holds, so 12-row chunks halve the
+// footprint (37 KB instead of 74 KB) and more CTAs share an SM; the H phase then covers a chunk with 12 rows x 10 segments of
+// 32 columns instead of 24 x 5 of 64.  The raw-row ring of the centre pixels holds two chunks.
+template <int RC> struct TmCfg {
+    static_assert(RC == 24 || RC == 12, "chunk rows");
+    static constexpr int SEG = 64 * RC / 24;              // output columns of one H-phase thread
+    static constexpr int NSEG = TM_WT / SEG;
+    static constexpr int GROWS = 2 * RC;
+    static constexpr size_t SMEM = (size_t)3 * RC * TM_VPITCH + (size_t)GROWS * TM_GPITCH + (size_t)RC * TM_VG * 4;
+    static_assert(RC * NSEG <= TM_THREADS, "thread roles");
+};
+constexpr int TM_RC = 24;                             // the chunk height the host sizes work items by (a multiple of both variants)
 static_assert((TM_VPITCH / 16) % 2 == 1 && (TM_GPITCH / 16) % 2 == 1 && TM_VPITCH % 16 == 0, "bank mapping");
-static_assert(TM_RC * TM_NSEG <= TM_THREADS && TM_VG <= TM_THREADS, "thread roles");
+static_assert(TM_VG <= TM_THREADS, "thread roles");
 
 __device__ __forceinline__ int tm_dp2a(uint32_t a, int sel, int c)      // c + s16(a.lo) * s8(sel.b0) + s16(a.hi) * s8(sel.b1)
 {
@@ -358,29 +366,68 @@ __device__ __forceinline__ void tm_cp_async4(uint32_t dst_shared, const void *sr
 __device__ __forceinline__ void tm_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tm_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// shared-memory views and per-thread constants of one CTA
+struct TmCtx {
+    uint8_t *pl0, *pl1, *pl2, *stash, *my_stash, *my_stage;
+    uint32_t my_stage_s;
+    int tid, wmax;
+    bool vthread, stash_ok;
+};
+
+// V phase of one chunk: the chunk's RC raw rows (already in the staging words) extend the prefix ring and leave the three
+// plane rows.  PAR = parity of the chunk: the ring position of a 12-row chunk ((first output row) mod 24) and the half of the
+// raw-row ring a chunk writes alternate, and the ring lives in registers, so the two parities are two instantiations.
+template <int R0, int R1, int R2, int RC, int PAR>
+__device__ __forceinline__ void tm_v_chunk(const TmCtx &c, uint32_t (&Ce)[TM_RING], uint32_t (&Co)[TM_RING], uint32_t &ce, uint32_t &co,
+                                           uint32_t sel_e, uint32_t sel_o)
+{
+    constexpr int G = TmCfg<RC>::GROWS, OFF = (RC * PAR) % TM_RING;
+    uint32_t w[RC];
+    tm_cp_async_wait_all();
+#pragma unroll
+    for (int u = 0; u < RC; ++u) w[u] = *reinterpret_cast<const volatile uint32_t *>(c.my_stage + u * (TM_VG * 4));
+#pragma unroll
+    for (int u = 0; u < RC; ++u) {
+        ce += __byte_perm(w[u], 0, sel_e); co += __byte_perm(w[u], 0, sel_o);
+        Ce[(OFF + u + 23) % TM_RING] = ce; Co[(OFF + u + 23) % TM_RING] = co;             // C[m + 22]: raw index m + 22 -> slot (m + 23) % 24
+        if (c.stash_ok) *reinterpret_cast<uint32_t *>(c.my_stash + ((RC * PAR + u + 22 + 26) % G) * TM_GPITCH) = w[u];   // raw index m0 + 22 + u
+        // V_r[m] = C[m + r + 11] - C[m - r + 10]   (raw index = output row + 11)
+        *reinterpret_cast<uint2 *>(c.pl0 + u * TM_VPITCH + 8 * c.tid) =
+            make_uint2(Ce[(OFF + u + R0 + 12) % TM_RING] - Ce[(OFF + u + 11 - R0) % TM_RING], Co[(OFF + u + R0 + 12) % TM_RING] - Co[(OFF + u + 11 - R0) % TM_RING]);
+        *reinterpret_cast<uint2 *>(c.pl1 + u * TM_VPITCH + 8 * c.tid) =
+            make_uint2(Ce[(OFF + u + R1 + 12) % TM_RING] - Ce[(OFF + u + 11 - R1) % TM_RING], Co[(OFF + u + R1 + 12) % TM_RING] - Co[(OFF + u + 11 - R1) % TM_RING]);
+        *reinterpret_cast<uint2 *>(c.pl2 + u * TM_VPITCH + 8 * c.tid) =
+            make_uint2(Ce[(OFF + u + R2 + 12) % TM_RING] - Ce[(OFF + u + 11 - R2) % TM_RING], Co[(OFF + u + R2 + 12) % TM_RING] - Co[(OFF + u + 11 - R2) % TM_RING]);
+    }
+}
+
 // requires pitch, frame_stride and the base pointer to be multiples of 4 (the host checks and falls back to k_threshold3)
-template <int R0, int R1, int R2>
-__global__ void __launch_bounds__(TM_THREADS, 3)
+template <int R0, int R1, int R2, int RC, int MINB>
+__global__ void __launch_bounds__(TM_THREADS, MINB)
 k_threshold_march(const uint8_t *__restrict__ gray, uint32_t pitch, size_t frame_stride, uint32_t *__restrict__ masks, DetGeom g,
                   int Hs, int n_sy, int n_sx, int n_items)
 {
     static_assert(R0 <= 11 && R1 <= 11 && R2 <= 11 && R0 >= 1 && R1 >= 1 && R2 >= 1, "radii");
+    using Cfg = TmCfg<RC>;
+    constexpr int SEG = Cfg::SEG;
     extern __shared__ __align__(16) uint8_t tm_smem[];
-    uint8_t *pl0 = tm_smem, *pl1 = pl0 + TM_RC * TM_VPITCH, *pl2 = pl1 + TM_RC * TM_VPITCH;
-    uint8_t *stash = pl2 + TM_RC * TM_VPITCH;                       // raw rows of the output columns, slot = (raw index + 26) % 48
-    uint8_t *stage = stash + TM_GROWS * TM_GPITCH;                  // [24][86] words: the chunk's raw rows, each word private to its V thread
+    TmCtx c;
+    c.pl0 = tm_smem; c.pl1 = c.pl0 + RC * TM_VPITCH; c.pl2 = c.pl1 + RC * TM_VPITCH;
+    c.stash = c.pl2 + RC * TM_VPITCH;                               // raw rows of the output columns, slot = (raw index + 26) % GROWS
+    uint8_t *stage = c.stash + Cfg::GROWS * TM_GPITCH;              // [RC][86] words: the chunk's raw rows, each word private to its V thread
     const int tid = threadIdx.x;
-    const bool vthread = tid < TM_VG;
-    const bool stash_ok = tid >= TM_HALO / 4 && tid < TM_VG - TM_HALO / 4;
-    uint8_t *my_stash = stash + 4 * (tid - TM_HALO / 4);
-    uint8_t *my_stage = stage + 4 * tid;
-    const uint32_t my_stage_s = (uint32_t)__cvta_generic_to_shared(my_stage);
-    const int rho = tid % TM_RC, sigma = tid / TM_RC;
-    const bool hthread = tid < TM_RC * TM_NSEG;
+    c.tid = tid;
+    c.vthread = tid < TM_VG;
+    c.stash_ok = tid >= TM_HALO / 4 && tid < TM_VG - TM_HALO / 4;
+    c.my_stash = c.stash + 4 * (tid - TM_HALO / 4);
+    c.my_stage = stage + 4 * tid;
+    c.my_stage_s = (uint32_t)__cvta_generic_to_shared(c.my_stage);
+    const int rho = tid % RC, sigma = tid / RC;
+    const bool hthread = tid < RC * Cfg::NSEG;
     const int bias0 = -(TmWin<R0>::K2 * g.Cfloor - (TmWin<R0>::K2 - 1) / 2);
     const int bias1 = -(TmWin<R1>::K2 * g.Cfloor - (TmWin<R1>::K2 - 1) / 2);
     const int bias2 = -(TmWin<R2>::K2 * g.Cfloor - (TmWin<R2>::K2 - 1) / 2);
-    const int wmax = (g.W - 1) >> 2;                                // last 4-column word that starts inside a row
+    c.wmax = (g.W - 1) >> 2;                                        // last 4-column word that starts inside a row
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int sy = item % n_sy;
@@ -392,7 +439,7 @@ k_threshold_march(const uint8_t *__restrict__ gray, uint32_t pitch, size_t frame
         // this thread's word of every row: replicate border = clamp the word index, then pick the bytes with the two
         // unpack permutes (even columns -> Ce lanes, odd columns -> Co lanes); a selector nibble of 4 reads a zero byte
         const int wcol = (X0 - TM_HALO) / 4 + tid;
-        const int wc = min(max(wcol, 0), wmax);
+        const int wc = min(max(wcol, 0), c.wmax);
         uint32_t sel_e, sel_o;
         {
             int bj[4];
@@ -404,18 +451,28 @@ k_threshold_march(const uint8_t *__restrict__ gray, uint32_t pitch, size_t frame
         const uint8_t *colp = gray + (size_t)b * frame_stride + 4 * (size_t)wc;
 
         // prefix ring: slot (j + 1) % 24 holds the column prefix through raw index j; slot 0 starts as C[-1] = 0
-        uint32_t Ce[TM_RC], Co[TM_RC];
+        uint32_t Ce[TM_RING], Co[TM_RING];
 #pragma unroll
-        for (int k = 0; k < TM_RC; ++k) { Ce[k] = 0; Co[k] = 0; }
+        for (int k = 0; k < TM_RING; ++k) { Ce[k] = 0; Co[k] = 0; }
         uint32_t ce = 0, co = 0;
-        if (vthread) {
-            // chunk 0's rows (raw index 22 .. 45) start towards shared memory, then the 22 warm-up rows come through registers
+        // rows raw index r_first .. r_first + RC - 1 start towards the staging words
+        auto prefetch = [&](int r_first) {
+            if (r_first >= 0 && r_first + RC - 1 <= g.H - 1) {                                // no clamping inside the frame
+                const uint8_t *p = colp + (size_t)((uint32_t)r_first * (uint64_t)pitch);
 #pragma unroll
-            for (int u = 0; u < TM_RC; ++u) {
-                const int gy = min(max(ytop + u + 22, 0), g.H - 1);
-                tm_cp_async4(my_stage_s + u * (TM_VG * 4), colp + (size_t)((uint32_t)gy * (uint64_t)pitch));
+                for (int u = 0; u < RC; ++u) tm_cp_async4(c.my_stage_s + u * (TM_VG * 4), p + (size_t)((uint32_t)u * (uint64_t)pitch));
+            } else {
+#pragma unroll
+                for (int u = 0; u < RC; ++u) {
+                    const int gy = min(max(r_first + u, 0), g.H - 1);
+                    tm_cp_async4(c.my_stage_s + u * (TM_VG * 4), colp + (size_t)((uint32_t)gy * (uint64_t)pitch));
+                }
             }
             tm_cp_async_commit();
+        };
+        if (c.vthread) {
+            // chunk 0's rows (raw index 22 .. 22 + RC - 1) start towards shared memory, then the 22 warm-up rows come through registers
+            prefetch(ytop + 22);
             uint32_t w[22];
 #pragma unroll
             for (int i = 0; i < 22; ++i) {
@@ -426,62 +483,32 @@ k_threshold_march(const uint8_t *__restrict__ gray, uint32_t pitch, size_t frame
             for (int i = 0; i < 22; ++i) {
                 ce += __byte_perm(w[i], 0, sel_e); co += __byte_perm(w[i], 0, sel_o);
                 Ce[i + 1] = ce; Co[i + 1] = co;
-                if (stash_ok) *reinterpret_cast<uint32_t *>(my_stash + ((i + 26) % TM_GROWS) * TM_GPITCH) = w[i];
+                if (c.stash_ok) *reinterpret_cast<uint32_t *>(c.my_stash + ((i + 26) % Cfg::GROWS) * TM_GPITCH) = w[i];
             }
         }
-        for (int m0 = 0, par = 0; m0 < rows; m0 += TM_RC, par ^= 1) {
-            if (vthread) {
-                uint32_t w[TM_RC];
-                tm_cp_async_wait_all();
-#pragma unroll
-                for (int u = 0; u < TM_RC; ++u) w[u] = *reinterpret_cast<const volatile uint32_t *>(my_stage + u * (TM_VG * 4));
-                uint8_t *st = my_stash + par * (TM_RC * TM_GPITCH);                           // raw index m0 + 22 + u -> slot 24 par + u
-#pragma unroll
-                for (int u = 0; u < TM_RC; ++u) {
-                    ce += __byte_perm(w[u], 0, sel_e); co += __byte_perm(w[u], 0, sel_o);
-                    Ce[(u + 23) % TM_RC] = ce; Co[(u + 23) % TM_RC] = co;                    // C[m + 22]
-                    if (stash_ok) *reinterpret_cast<uint32_t *>(st + u * TM_GPITCH) = w[u];
-                    // V_r[m] = C[m + r + 11] - C[m - r + 10]   (raw index = output row + 11)
-                    *reinterpret_cast<uint2 *>(pl0 + u * TM_VPITCH + 8 * tid) =
-                        make_uint2(Ce[(u + R0 + 12) % TM_RC] - Ce[(u + 11 - R0) % TM_RC], Co[(u + R0 + 12) % TM_RC] - Co[(u + 11 - R0) % TM_RC]);
-                    *reinterpret_cast<uint2 *>(pl1 + u * TM_VPITCH + 8 * tid) =
-                        make_uint2(Ce[(u + R1 + 12) % TM_RC] - Ce[(u + 11 - R1) % TM_RC], Co[(u + R1 + 12) % TM_RC] - Co[(u + 11 - R1) % TM_RC]);
-                    *reinterpret_cast<uint2 *>(pl2 + u * TM_VPITCH + 8 * tid) =
-                        make_uint2(Ce[(u + R2 + 12) % TM_RC] - Ce[(u + 11 - R2) % TM_RC], Co[(u + R2 + 12) % TM_RC] - Co[(u + 11 - R2) % TM_RC]);
-                }
-                if (m0 + TM_RC < rows) {                                                      // the next chunk's rows fly during this chunk's H phase
-                    const int r_first = ytop + m0 + TM_RC + 22;
-                    if (r_first >= 0 && r_first + TM_RC - 1 <= g.H - 1) {                     // no clamping inside the frame
-                        const uint8_t *p = colp + (size_t)((uint32_t)r_first * (uint64_t)pitch);
-#pragma unroll
-                        for (int u = 0; u < TM_RC; ++u) tm_cp_async4(my_stage_s + u * (TM_VG * 4), p + (size_t)((uint32_t)u * (uint64_t)pitch));
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < TM_RC; ++u) {
-                            const int gy = min(max(r_first + u, 0), g.H - 1);
-                            tm_cp_async4(my_stage_s + u * (TM_VG * 4), colp + (size_t)((uint32_t)gy * (uint64_t)pitch));
-                        }
-                    }
-                    tm_cp_async_commit();
-                }
+        for (int m0 = 0, par = 0; m0 < rows; m0 += RC, par ^= 1) {
+            if (c.vthread) {
+                if (par == 0) tm_v_chunk<R0, R1, R2, RC, 0>(c, Ce, Co, ce, co, sel_e, sel_o);
+                else tm_v_chunk<R0, R1, R2, RC, 1>(c, Ce, Co, ce, co, sel_e, sel_o);
+                if (m0 + RC < rows) prefetch(ytop + m0 + RC + 22);                            // the next chunk's rows fly during this chunk's H phase
             }
             __syncthreads();
             const int y = Y0 + m0 + rho;
-            if (hthread && y < g.H && X0 + TM_SEG * sigma < g.W) {
-                const uint8_t *row0 = pl0 + rho * TM_VPITCH + 2 * TM_SEG * sigma;
-                const uint8_t *row1 = pl1 + rho * TM_VPITCH + 2 * TM_SEG * sigma;
-                const uint8_t *row2 = pl2 + rho * TM_VPITCH + 2 * TM_SEG * sigma;
-                const uint8_t *grow = stash + ((m0 + rho + 11 + 26) % TM_GROWS) * TM_GPITCH + TM_SEG * sigma;   // the centre pixels: raw index = row + 11
+            if (hthread && y < g.H && X0 + SEG * sigma < g.W) {
+                const uint8_t *row0 = c.pl0 + rho * TM_VPITCH + 2 * SEG * sigma;
+                const uint8_t *row1 = c.pl1 + rho * TM_VPITCH + 2 * SEG * sigma;
+                const uint8_t *row2 = c.pl2 + rho * TM_VPITCH + 2 * SEG * sigma;
+                const uint8_t *grow = c.stash + ((m0 + rho + 11 + 26) % Cfg::GROWS) * TM_GPITCH + SEG * sigma;   // the centre pixels: raw index = row + 11
                 TmWin<R0> w0; TmWin<R1> w1; TmWin<R2> w2;
                 w0.load(row0, TmWin<R0>::first_piece, TmWin<R0>::newest_piece(0) - 1);
                 w1.load(row1, TmWin<R1>::first_piece, TmWin<R1>::newest_piece(0) - 1);
                 w2.load(row2, TmWin<R2>::first_piece, TmWin<R2>::newest_piece(0) - 1);
                 w0.init(bias0); w1.init(bias1); w2.init(bias2);
                 uint32_t m_0 = 0, m_1 = 0, m_2 = 0;
-                uint32_t *mrow = masks + (size_t)b * 3 * g.mask_plane + (size_t)(y + 1) * g.PWW + 1 + X0 / 32 + 2 * sigma;
+                uint32_t *mrow = masks + (size_t)b * 3 * g.mask_plane + (size_t)(y + 1) * g.PWW + 1 + X0 / 32 + (SEG / 32) * sigma;
                 uint4 gq;
 #pragma unroll
-                for (int blk = 0; blk < TM_SEG / 8; ++blk) {
+                for (int blk = 0; blk < SEG / 8; ++blk) {
                     w0.load(row0, blk == 0 ? TmWin<R0>::newest_piece(0) : TmWin<R0>::newest_piece(blk - 1) + 1, TmWin<R0>::newest_piece(blk));
                     w1.load(row1, blk == 0 ? TmWin<R1>::newest_piece(0) : TmWin<R1>::newest_piece(blk - 1) + 1, TmWin<R1>::newest_piece(blk));
                     w2.load(row2, blk == 0 ? TmWin<R2>::newest_piece(0) : TmWin<R2>::newest_piece(blk - 1) + 1, TmWin<R2>::newest_piece(blk));
@@ -496,11 +523,11 @@ k_threshold_march(const uint8_t *__restrict__ gray, uint32_t pitch, size_t frame
                         m_0 = __funnelshift_l((uint32_t)d0, m_0, 1);                 // (m << 1) | sign(d)
                         m_1 = __funnelshift_l((uint32_t)d1, m_1, 1);
                         m_2 = __funnelshift_l((uint32_t)d2, m_2, 1);
-                        if (i + 1 < TM_SEG) { w0.slide(i); w1.slide(i); w2.slide(i); }
+                        if (i + 1 < SEG) { w0.slide(i); w1.slide(i); w2.slide(i); }
                     }
                     if ((blk & 3) == 3) {                                            // 32 columns done: first column ends up in bit 0, set = test passed
                         const int wd = blk >> 2;
-                        const int left = g.W - (X0 + TM_SEG * sigma + 32 * wd);
+                        const int left = g.W - (X0 + SEG * sigma + 32 * wd);
                         if (left > 0) {
                             const uint32_t valid = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
                             mrow[wd] = ~__brev(m_0) & valid;
