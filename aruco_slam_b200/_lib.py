@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "csrc", "libb2aruco.so")
+SO_PATH = os.environ.get("B2A_LIB", os.path.join(_HERE, "csrc", "libb2aruco.so"))        # B2A_LIB: an instrumented build (profiling only)
 
 
 class B2AError(RuntimeError):
@@ -92,7 +92,7 @@ SYMBOLS = [
     "b2a_default_slam_params", "b2a_slam_create", "b2a_slam_destroy", "b2a_slam_dim", "b2a_slam_get_state",
     "b2a_slam_set_state", "b2a_slam_add_encoder", "b2a_slam_make_observations", "b2a_slam_update", "b2a_slam_add_image", "b2a_slam_synchronize",
     "b2a_quaternion_from_rpy", "b2a_map_parse", "b2a_map_load", "b2a_slam_robot_pose", "b2a_slam_detected_map",
-    "b2a_pack_robot_pose", "b2a_pack_map_marker",
+    "b2a_pack_robot_pose", "b2a_pack_map_marker", "b2a_slam_stream",
 ]
 
 _lib = None
@@ -129,6 +129,8 @@ def lib():
         L.b2a_detector_set_streams.argtypes = [C.c_void_p, C.c_int]
         L.b2a_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2a_detect_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2a_slam_stream.argtypes = [C.c_void_p]
+        L.b2a_slam_stream.restype = C.c_void_p
         L.b2a_detect_pose_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2a_detect_pose_wait.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.b2a_estimate_pose_single_markers.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -1078,6 +1078,8 @@ struct b2a_slam {
     double *d_sigma2 = nullptr;                      // ping-pong partner of d_sigma (cooperative kernel)
     double *d_mu = nullptr, *d_mus = nullptr, *d_sigma = nullptr, *d_K = nullptr, *d_GS = nullptr, *d_scratch = nullptr;
     int coop_grid = 0;                               // co-resident CTAs of k_ekf_frame (0 = use the per-observation kernels)
+    bool panel = true;                               // all corrections of a frame as one rank-3M update (B2A_EKF_PANEL=0: one pass per observation)
+    double *d_pze = nullptr, *d_pU0 = nullptr, *d_pK = nullptr, *d_pV0 = nullptr, *d_pV = nullptr, *d_pfac = nullptr, *d_pfacT = nullptr;
     // per-frame scratch, allocated once (grown only when a frame brings more markers than ever before)
     int obs_cap = 0;
     float *d_c = nullptr; int32_t *d_i = nullptr; double *d_r = nullptr, *d_t = nullptr;      // detections of the host-array entry point
@@ -1133,6 +1135,7 @@ extern "C" void b2a_slam_destroy(b2a_slam *s)
     cudaFreeHost(s->h_n);
     for (cudaEvent_t e : s->ev_ekf) if (e) cudaEventDestroy(e);
     cudaFree(s->d_sigma2);
+    cudaFree(s->d_pze); cudaFree(s->d_pU0); cudaFree(s->d_pK); cudaFree(s->d_pV0); cudaFree(s->d_pV); cudaFree(s->d_pfac); cudaFree(s->d_pfacT);
     cudaFree(s->d_mu); cudaFree(s->d_mus); cudaFree(s->d_sigma); cudaFree(s->d_K); cudaFree(s->d_GS); cudaFree(s->d_scratch);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -1168,6 +1171,17 @@ extern "C" int b2a_slam_create(int device, const b2a_slam_params *p, b2a_slam **
         if (s->d_sigma2) cudaMemsetAsync(s->d_sigma2, 0, LD * LD * 8, s->stream);
         (void)cudaGetLastError();
     }
+    {   // panel form: Jacobians, innovations, U0 / K (N x 96), V0 / V (96 x N), the 96 x 96 factors
+        if (const char *e = std::getenv("B2A_EKF_PANEL")) s->panel = std::atoi(e) != 0;
+        if (s->panel) {
+            if (cudaMalloc(&s->d_pze, EP_K * 8) || cudaMalloc(&s->d_pU0, LD * EP_K * 8) || cudaMalloc(&s->d_pK, LD * EP_K * 8) ||
+                cudaMalloc(&s->d_pV0, LD * EP_K * 8) || cudaMalloc(&s->d_pV, LD * EP_K * 8) || cudaMalloc(&s->d_pfac, EP_K * EP_K * 8) || cudaMalloc(&s->d_pfacT, EP_K * EP_K * 8))
+                return fail("cudaMalloc (EKF panel)");
+            if (cudaFuncSetAttribute(k_ekf_panel_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EP_SSMEM) ||
+                cudaFuncSetAttribute(k_ekf_panel_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EG_SMEM))
+                return fail("shared memory of the EKF panel kernels");
+        }
+    }
     cudaMemsetAsync(s->d_mu, 0, LD * 8, s->stream);
     cudaMemsetAsync(s->d_sigma, 0, LD * LD * 8, s->stream);
     if (cudaStreamSynchronize(s->stream) != cudaSuccess) return fail("memset");
@@ -1179,6 +1193,7 @@ extern "C" int b2a_slam_create(int device, const b2a_slam_params *p, b2a_slam **
 }
 
 extern "C" int b2a_slam_dim(const b2a_slam *s) { return s ? s->N : 0; }
+extern "C" void *b2a_slam_stream(const b2a_slam *s) { return s ? (void *)s->stream : nullptr; }
 
 extern "C" int b2a_slam_synchronize(b2a_slam *s)
 {
@@ -1442,7 +1457,22 @@ extern "C" int b2a_slam_update(b2a_slam *s, const b2a_observation *obs, int n)
         const int nb = staged - batch0;
         if (nb <= 0) return B2A_OK;
         const int N = s->N;
-        if (s->coop_grid > 0 && (N + s->coop_grid - 1) / s->coop_grid <= 64) {
+        if (s->panel) {
+            // one rank-3M update per (at most 32) corrections: Sigma is read and written once
+            CU(cudaMemcpyAsync(s->d_ekf + batch0, stage + batch0, (size_t)nb * sizeof(EkfObs), cudaMemcpyHostToDevice, st));
+            for (int o0 = 0; o0 < nb; o0 += EP_MAX_OBS) {
+                EkfPanel p;
+                p.obs = s->d_ekf + batch0 + o0; p.M = std::min(EP_MAX_OBS, nb - o0);
+                p.ze = s->d_pze; p.U0 = s->d_pU0; p.Kall = s->d_pK; p.V0 = s->d_pV0; p.Vall = s->d_pV; p.fac = s->d_pfac; p.facT = s->d_pfacT;
+                const int tiles = (N + EG_T - 1) / EG_T, kdim = (3 * p.M + 3) & ~3;
+                const int gx = std::max((N + 127) / 128, (EP_K * EP_K + 127) / 128);          // the y == M slice also clears the padding of the 96 x 96 matrix
+                k_ekf_panel_gather<<<dim3(gx, p.M + 1), 128, 0, st>>>(s->d_sigma, s->d_mus, N, s->LD, p);
+                k_ekf_panel_factor<<<1, EP_MAX_OBS * EP_MAX_OBS, 0, st>>>(p);
+                const int rc = (N + EP_SW * EP_SV - 1) / (EP_SW * EP_SV);
+                k_ekf_panel_solve<<<2 * rc, 32 * EP_SW, EP_SSMEM, st>>>(s->d_mu, N, s->LD, p, rc);
+                k_ekf_panel_gemm<<<dim3(tiles, tiles), 512, EG_SMEM, st>>>(s->d_sigma, N, s->LD, p, kdim);
+            }
+        } else if (s->coop_grid > 0 && (N + s->coop_grid - 1) / s->coop_grid <= 64) {
             CU(cudaMemcpyAsync(s->d_ekf + batch0, stage + batch0, (size_t)nb * sizeof(EkfObs), cudaMemcpyHostToDevice, st));
             int LD = s->LD, n_obs = nb, N_ = N;
             const EkfObs *obs_p = s->d_ekf + batch0;

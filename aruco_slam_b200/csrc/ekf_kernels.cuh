@@ -13,6 +13,9 @@
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <stdint.h>
+#ifdef B2A_EKF_CLOCKS
+#include <cstdio>
+#endif
 #include "pose_core.h"
 
 namespace b2a {
@@ -222,6 +225,328 @@ k_ekf_frame(double *__restrict__ sigma_a, double *__restrict__ sigma_b, double *
             }
         }
         grid.sync();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Panel form: all M known-landmark corrections of a frame as ONE rank-3M update of Sigma (reference loop :92-207, dense
+// product :204).  Every Jacobian G_m (3 x N, six non-zero columns) and innovation ze_m comes from the frame-start snapshot
+// (:88), so with  U0 = Sigma0 [G_0^T .. G_{M-1}^T]  (N x 3M),  V0 = [G_0; ..; G_{M-1}] Sigma0  (3M x N)  and the block LU
+// factorisation  G Sigma0 G^T + blockdiag(R_m) = L Uh  (3 x 3 blocks, L unit lower, Uh upper with the innovation
+// covariances S_m on its diagonal; elimination step m is exactly "apply correction m") the sequential gains are the block
+// columns of  K = U0 Uh^-1,  the rows G_m Sigma_m are the block rows of  V = L^-1 V0,  and
+//     Sigma_M = Sigma0 - K V,      mu_M = mu_0 + K [ze_0; ..; ze_{M-1}]          (the reference's mean: sequential gains, fixed innovations).
+// Sigma is read and written once per frame (16 N^2 bytes) instead of once per observation; the N x 3M x N contraction runs
+// on the FP64 tensor-core path (mma.sync m8n8k4 f64).  Same result as the sequential form up to rounding (tests: 1e-9).
+//   k_ekf_panel_gather   G_m, ze_m, U0, V0                       (N / 128 CTAs)
+//   k_ekf_panel_factor   C = G U0, block LU in shared memory     (1 CTA)
+//   k_ekf_panel_solve    K = U0 Uh^-1 (per row), mu += K ze, V = L^-1 V0 (per column)
+//   k_ekf_panel_gemm     Sigma -= K V                            (64 x 64 tiles, DMMA)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int EP_MAX_OBS = 32;                    // corrections per panel
+constexpr int EP_K = 3 * EP_MAX_OBS;              // 96: padded inner dimension (multiple of 4)
+struct EkfPanel {
+    const EkfObs *obs; int M;                     // device array of the panel's corrections
+    double *ze;                                   // [EP_K] innovations (zero padded)
+    double *U0, *Kall;                            // [N][EP_K]
+    double *V0;                                   // [N][EP_K]: the TRANSPOSE of V0 (row j = column j of the 3M x N matrix), one contiguous row per index
+    double *Vall;                                 // [EP_K][LD]: V as the contraction reads it
+    double *fac;                                  // [EP_K][EP_K]: G Sigma0 G^T on entry of k_ekf_panel_factor, the LU factors after it:
+                                                  // upper block triangle = Uh with S_m^-1 in the diagonal blocks, strict lower = L
+    double *facT;                                 // its transpose (the row solve walks columns of Uh)
+};
+
+// grid (ceil(N / 128), M + 1).  y < M: column block y of U0 and row block y of V0 (one thread per state index);
+// y == M: the zero padding, the innovations and the 3 x 3 blocks of G Sigma0 G^T (one thread per block pair)
+__global__ void __launch_bounds__(128)
+k_ekf_panel_gather(const double *__restrict__ sigma, const double *__restrict__ mu_s, int N, int LD, EkfPanel p)
+{
+    const int M = p.M;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int)blockIdx.y < M) {
+        __shared__ double s_G[18];
+        __shared__ int s_L;
+        const int m = blockIdx.y;
+        if (threadIdx.x == 0) {
+            double G[18], ze[3];
+            const EkfObs ob = p.obs[m];
+            ekf_linearise(mu_s, ob, G, ze);
+            for (int k = 0; k < 18; ++k) s_G[k] = G[k];
+            s_L = 3 + 3 * ob.index;
+        }
+        __syncthreads();
+        if (i >= N) return;
+        const int L = s_L;
+        const double *row = sigma + (size_t)i * LD;
+        const double c0 = row[0], c1 = row[1], c2 = row[2], c3 = row[L], c4 = row[L + 1], c5 = row[L + 2];          // Sigma[i][cols]
+        const double r0 = sigma[i], r1 = sigma[(size_t)LD + i], r2 = sigma[2 * (size_t)LD + i];                       // Sigma[cols][i]
+        const double r3 = sigma[(size_t)L * LD + i], r4 = sigma[(size_t)(L + 1) * LD + i], r5 = sigma[(size_t)(L + 2) * LD + i];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const double *g = s_G + 6 * r;
+            p.U0[(size_t)i * EP_K + 3 * m + r] = c0 * g[0] + c1 * g[1] + c2 * g[2] + c3 * g[3] + c4 * g[4] + c5 * g[5];
+            p.V0[(size_t)i * EP_K + 3 * m + r] = g[0] * r0 + g[1] * r1 + g[2] * r2 + g[3] * r3 + g[4] * r4 + g[5] * r5;
+        }
+        return;
+    }
+    if (i < N) for (int c = 3 * M; c < EP_K; ++c) { p.U0[(size_t)i * EP_K + c] = 0.0; p.V0[(size_t)i * EP_K + c] = 0.0; }
+    if (i < EP_K * EP_K && (i / EP_K >= 3 * M || i % EP_K >= 3 * M)) p.fac[i] = 0.0;
+    if (i < M * M) {
+        const int a = i / M, b = i - a * M;
+        double Ga[18], Gb[18], ze[3], zb[3];
+        const EkfObs oa = p.obs[a], ob = p.obs[b];
+        ekf_linearise(mu_s, oa, Ga, ze);
+        ekf_linearise(mu_s, ob, Gb, zb);
+        if (b == 0) for (int r = 0; r < 3; ++r) p.ze[3 * a + r] = ze[r];
+        const int La = 3 + 3 * oa.index, Lb = 3 + 3 * ob.index;
+        double T[18];                              // Sigma[cols_a][cols_b] G_b^T   (6 x 3)
+        for (int k = 0; k < 6; ++k) {
+            const double *row = sigma + (size_t)(k < 3 ? k : La + k - 3) * LD;
+            const double v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[Lb], v4 = row[Lb + 1], v5 = row[Lb + 2];
+            for (int c = 0; c < 3; ++c) T[3 * k + c] = v0 * Gb[6 * c] + v1 * Gb[6 * c + 1] + v2 * Gb[6 * c + 2] + v3 * Gb[6 * c + 3] + v4 * Gb[6 * c + 4] + v5 * Gb[6 * c + 5];
+        }
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+            double v = 0;
+            for (int k = 0; k < 6; ++k) v += Ga[6 * r + k] * T[3 * k + c];
+            p.fac[(size_t)(3 * a + r) * EP_K + 3 * b + c] = v;
+        }
+    }
+    if (i >= 3 * M && i < EP_K) p.ze[i] = 0.0;
+}
+
+// one CTA: block LU without pivoting of C + blockdiag(R_m) (symmetric positive definite up to rounding); elimination step m is
+// correction m of the reference's loop.  Thread (A, B) keeps the 3 x 3 block D_AB in registers for the whole factorisation:
+//   pivot      thread (m, m): S_m = D_mm + R_m (:146), inverted in closed form; threads (m, B > m) publish their finished Uh_mB
+//   multiplier threads (A > m, m): L_Am = D_Am S_m^-1, published
+//   update     threads (A > m, B > m): D_AB -= L_Am Uh_mB   (27 FMAs on registers)
+// Two barriers per step; the published blocks are double buffered by the step's parity.  (Measured alternatives, all slower on the
+// one SM this runs on: rows of a shared-memory matrix per warp, 51-85 us; 2 x 2 blocks per thread with one barrier per step, 47-58 us;
+// this form 42 us for 30 corrections.)
+__global__ void __launch_bounds__(EP_MAX_OBS * EP_MAX_OBS)
+k_ekf_panel_factor(EkfPanel p)
+{
+    __shared__ double s_L[2][EP_MAX_OBS][9], s_U[2][EP_MAX_OBS][9], s_Si[9];
+    const int M = p.M, t = threadIdx.x;
+    const int A = t / M, B = t - A * M;
+    const bool live = t < M * M;
+    double D[9], Rk[9];
+    if (live) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) D[3 * r + c] = p.fac[(size_t)(3 * A + r) * EP_K + 3 * B + c];
+        if (A == B) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) Rk[k] = p.obs[A].Rk[k];
+        }
+    }
+    for (int m = 0; m < M; ++m) {
+        const int par = m & 1;
+        if (live && A == m) {
+            if (B == m) {
+                double S[9], Si[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) S[k] = D[k] + Rk[k];
+                inv3x3(S, Si);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) { D[k] = Si[k]; s_Si[k] = Si[k]; }                     // the diagonal block keeps S_m^-1
+            } else if (B > m) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) s_U[par][B][k] = D[k];
+            }
+        }
+        __syncthreads();
+        if (live && B == m && A > m) {
+            double L[9];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) L[3 * r + c] = D[3 * r] * s_Si[c] + D[3 * r + 1] * s_Si[3 + c] + D[3 * r + 2] * s_Si[6 + c];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { D[k] = L[k]; s_L[par][A][k] = L[k]; }
+        }
+        __syncthreads();
+        if (live && A > m && B > m) {
+            double L[9], U[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { L[k] = s_L[par][A][k]; U[k] = s_U[par][B][k]; }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) D[3 * r + c] -= L[3 * r] * U[c] + L[3 * r + 1] * U[3 + c] + L[3 * r + 2] * U[6 + c];
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                p.fac[(size_t)(3 * A + r) * EP_K + 3 * B + c] = D[3 * r + c];
+                p.facT[(size_t)(3 * B + c) * EP_K + 3 * A + r] = D[3 * r + c];
+            }
+    }
+}
+
+// column-oriented triangular solves (no reductions).  A warp solves EP_SV state indices at once; lane l keeps block l (entries
+// 3l .. 3l + 2) of each of their vectors.
+//   rows     x = U0[i][:]:  K_m = x_m S_m^-1, then x_l -= K_m Uh[m][l] for the later blocks;  mu += K ze (:203)
+//   columns  x = V0[:][j]:  V_m = x_m,        then x_l -= L[l][m] V_m
+// The coefficients of a step are three rows of fac (rows) or of its transpose (columns).  A CTA stages that matrix in shared memory as
+// three planes (entry 3l + c of a row at plane c, word l), so a lane's three coefficients per row are conflict-free reads and the
+// four vectors of a warp share them (read through L1 instead, the 24-byte lane stride made every load seven cache lines wide).
+constexpr int EP_SW = 8, EP_SV = 4;               // warps per CTA, state indices per warp
+constexpr size_t EP_SSMEM = (size_t)(3 * EP_K * EP_MAX_OBS + 9 * EP_MAX_OBS + EP_K) * sizeof(double);
+__global__ void __launch_bounds__(32 * EP_SW)
+k_ekf_panel_solve(double *__restrict__ mu, int N, int LD, EkfPanel p, int row_ctas)
+{
+    extern __shared__ double s_F[];               // [3][EP_K][32] coefficient planes, [32][9] S^-1 blocks, [EP_K] ze
+    double *s_Si = s_F + 3 * EP_K * EP_MAX_OBS, *s_ze = s_Si + 9 * EP_MAX_OBS;
+    const int M = p.M, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool rows = (int)blockIdx.x < row_ctas;
+    {
+        const double *__restrict__ fm = rows ? p.fac : p.facT;
+        for (int t = threadIdx.x; t < 3 * M * EP_K; t += blockDim.x) {      // 8-byte asynchronous copies: all in flight at once
+            const int r = t / EP_K, c = t - r * EP_K;          // coalesced read of row r
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(s_F + ((c % 3) * EP_K + r) * EP_MAX_OBS + c / 3)),
+                         "l"(fm + (size_t)r * EP_K + c) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (int t = threadIdx.x; t < 9 * M; t += blockDim.x) { const int m = t / 9, k = t - 9 * m; s_Si[t] = p.fac[(size_t)(3 * m + k / 3) * EP_K + 3 * m + k % 3]; }
+        for (int t = threadIdx.x; t < EP_K; t += blockDim.x) s_ze[t] = p.ze[t];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int i0 = (((int)blockIdx.x - (rows ? 0 : row_ctas)) * EP_SW + warp) * EP_SV;
+    if (i0 >= N) return;
+    const double *__restrict__ src = rows ? p.U0 : p.V0;
+    double x[EP_SV][3], dmu[EP_SV];
+#pragma unroll
+    for (int v = 0; v < EP_SV; ++v) {
+        const int i = min(i0 + v, N - 1);
+        const double *in = src + (size_t)i * EP_K + 3 * lane;
+        x[v][0] = in[0]; x[v][1] = in[1]; x[v][2] = in[2];
+        dmu[v] = 0.0;
+    }
+    for (int m = 0; m < M; ++m) {
+        double f[3][3];                            // this lane's coefficients of the step: rows 3m + r, entries 3 lane + c
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) f[r][c] = s_F[(c * EP_K + 3 * m + r) * EP_MAX_OBS + lane];
+        double Si[9];
+        if (rows) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) Si[k] = s_Si[9 * m + k];
+        }
+#pragma unroll
+        for (int v = 0; v < EP_SV; ++v) {
+            double k0 = __shfl_sync(0xFFFFFFFFu, x[v][0], m), k1 = __shfl_sync(0xFFFFFFFFu, x[v][1], m), k2 = __shfl_sync(0xFFFFFFFFu, x[v][2], m);
+            if (rows) {                            // times S_m^-1 from the right
+                const double a0 = k0, a1 = k1, a2 = k2;
+                k0 = a0 * Si[0] + a1 * Si[3] + a2 * Si[6];
+                k1 = a0 * Si[1] + a1 * Si[4] + a2 * Si[7];
+                k2 = a0 * Si[2] + a1 * Si[5] + a2 * Si[8];
+                dmu[v] += k0 * s_ze[3 * m] + k1 * s_ze[3 * m + 1] + k2 * s_ze[3 * m + 2];
+            }
+            if (lane > m) {
+                x[v][0] -= k0 * f[0][0] + k1 * f[1][0] + k2 * f[2][0];
+                x[v][1] -= k0 * f[0][1] + k1 * f[1][1] + k2 * f[2][1];
+                x[v][2] -= k0 * f[0][2] + k1 * f[1][2] + k2 * f[2][2];
+            } else if (lane == m) { x[v][0] = k0; x[v][1] = k1; x[v][2] = k2; }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < EP_SV; ++v) {
+        const int i = i0 + v;
+        if (i >= N) break;
+        const double o0 = lane < M ? x[v][0] : 0.0, o1 = lane < M ? x[v][1] : 0.0, o2 = lane < M ? x[v][2] : 0.0;
+        if (rows) {
+            double *out = p.Kall + (size_t)i * EP_K + 3 * lane;
+            out[0] = o0; out[1] = o1; out[2] = o2;
+            if (lane == 0) mu[i] += dmu[v];
+        } else {
+            double *out = p.Vall + (size_t)(3 * lane) * LD + i;
+            out[0] = o0; out[LD] = o1; out[2 * (size_t)LD] = o2;
+        }
+    }
+}
+
+// Sigma -= K V on the FP64 tensor-core path: a CTA of 16 warps owns a 128 x 128 tile of Sigma (144 tiles at N = 1503: one per SM),
+// a warp a 32 x 32 part (4 x 4 mma tiles); the tile's K rows and V columns come to shared memory by 16-byte asynchronous copies
+// and stay for the whole contraction
+__device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void *dst_shared, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst_shared)), "l"(src) : "memory");
+}
+constexpr int EG_T = 128, EG_AP = EP_K + 4, EG_BP = EG_T + 4;     // pitches = 4 (mod 16) doubles: the fragment loads of a half-warp cover 16 distinct 8-byte banks
+constexpr size_t EG_SMEM = ((size_t)EG_T * EG_AP + (size_t)EP_K * EG_BP) * sizeof(double);
+__global__ void __launch_bounds__(512)
+k_ekf_panel_gemm(double *__restrict__ sigma, int N, int LD, EkfPanel p, int kdim)
+{
+    extern __shared__ __align__(16) double s_ab[];
+    double *sA = s_ab, *sB = s_ab + EG_T * EG_AP;
+    const int i0 = blockIdx.y * EG_T, j0 = blockIdx.x * EG_T, tid = threadIdx.x;
+    const int kd2 = kdim / 2;
+    for (int t = tid; t < EG_T * kd2; t += blockDim.x) {                    // K rows of the tile (rows beyond N: zeros)
+        const int r = t / kd2, c = 2 * (t - r * kd2);
+        if (i0 + r < N) cp_async16(sA + r * EG_AP + c, p.Kall + (size_t)(i0 + r) * EP_K + c);
+        else { sA[r * EG_AP + c] = 0.0; sA[r * EG_AP + c + 1] = 0.0; }
+    }
+    for (int t = tid; t < kdim * (EG_T / 2); t += blockDim.x) {             // V columns of the tile (columns beyond the array: zeros)
+        const int r = t / (EG_T / 2), c = 2 * (t - r * (EG_T / 2));
+        if (j0 + c + 1 < LD) cp_async16(sB + r * EG_BP + c, p.Vall + (size_t)r * LD + j0 + c);
+        else { sB[r * EG_BP + c] = 0.0; sB[r * EG_BP + c + 1] = 0.0; }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int warp = tid >> 5, lane = tid & 31, gr = lane >> 2, gc = lane & 3;
+    const int wi = (warp >> 2) * 32, wj = (warp & 3) * 32;
+    {   // the tile of Sigma itself is wanted at the end: start it towards L2 now
+        const int r = tid >> 2, q = tid & 3;                                // 128 rows x 4 quarter rows of 256 bytes
+        if (i0 + r < N && j0 + 32 * q < LD) {
+            const char *line = reinterpret_cast<const char *>(sigma + (size_t)(i0 + r) * LD + j0) + 256 * q;
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(line));
+            if (j0 + 32 * q + 16 < LD) asm volatile("prefetch.global.L2 [%0];" :: "l"(line + 128));
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int k0 = 0; k0 < kdim; k0 += 4) {
+        double fa[4], fb[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) fa[a] = sA[(wi + 8 * a + gr) * EG_AP + k0 + gc];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) fb[b] = sB[(k0 + gc) * EG_BP + wj + 8 * b + gr];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) dmma_8x8x4(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = i0 + wi + 8 * a + gr;
+        double2 v[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {                                       // four loads in flight, then the four updates
+            const int j = j0 + wj + 8 * b + 2 * gc;
+            v[b] = (i < N && j < N) ? *reinterpret_cast<const double2 *>(sigma + (size_t)i * LD + j) : make_double2(0.0, 0.0);      // LD even, j even: 16-byte aligned
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int j = j0 + wj + 8 * b + 2 * gc;
+            if (i >= N || j >= N) continue;
+            v[b].x -= acc[a][b][0];
+            if (j + 1 < N) v[b].y -= acc[a][b][1];
+            *reinterpret_cast<double2 *>(sigma + (size_t)i * LD + j) = v[b];
+        }
     }
 }
 

@@ -82,9 +82,23 @@ class ArucoSlam:
         arr = (_lib.Observation * max(n, 1))(*observations)
         _lib.check(_lib.lib().b2a_slam_update(self._h, arr, n))
 
+    @staticmethod
+    def pack_observations(observations):
+        """the C array b2a_slam_update takes (build it once when the same frame is replayed)"""
+        n = len(observations)
+        return (_lib.Observation * max(n, 1))(*observations), n
+
+    def update_packed(self, packed):
+        _lib.check(_lib.lib().b2a_slam_update(self._h, packed[0], packed[1]))
+
     def synchronize(self):
         """wait for the EKF kernels enqueued so far"""
         _lib.check(_lib.lib().b2a_slam_synchronize(self._h))
+
+    @property
+    def stream(self) -> int:
+        """the cudaStream_t the EKF kernels run on"""
+        return int(_lib.lib().b2a_slam_stream(self._h) or 0)
 
     @property
     def dim(self) -> int:

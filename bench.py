@@ -48,15 +48,12 @@ MARKER_LENGTH = 0.27                    # reference parameters.yaml:17
 # 3 + 3 n, include/aruco_slam/aruco_slam.h:182; the "1003" of BASELINE.json would be 2-D landmarks), 30 observations of
 # distinct known landmarks per frame.  python bench.py --workload C5 [--ekf-landmarks 500]
 def bench_ekf(args):
+    import torch
     from aruco_slam_b200 import slam, _lib
     from oracle import oracle as O
     n_lm, n_obs = args.ekf_landmarks, 30
     N = 3 + 3 * n_lm
-    rng = np.random.default_rng(0)
-    A = rng.normal(size=(N, N))
-    sigma0 = A @ A.T / N + 0.1 * np.eye(N)
-    mu0 = np.concatenate([[0.3, -0.2, 0.4], rng.uniform(-4, 4, 3 * n_lm)])
-    ids = np.arange(n_lm, dtype=np.int32)
+    mu0, sigma0, ids = synth.c5_state(n_lm)
 
     def frame_obs(cls, step):
         r = np.random.default_rng(100 + step)
@@ -67,7 +64,7 @@ def bench_ekf(args):
             dx, dy = mu0[L] - mu0[0], mu0[L + 1] - mu0[1]
             z = np.array([dx * c + dy * sn, -dx * sn + dy * c, mu0[L + 2] - mu0[2]]) + r.normal(0, 0.02, 3)
             o = cls()
-            o.aruco_id, o.aruco_index, o.x, o.y, o.theta = int(k), -1, z[0], z[1], z[2]
+            o.aruco_id, o.aruco_index, o.x, o.y, o.theta = int(ids[k]), -1, z[0], z[1], z[2]
             for i, v in enumerate([0.02, 0, 0, 0, 0.02, 0, 0, 0, 0.003]):
                 o.cov[i] = v
             out.append(o)
@@ -75,15 +72,23 @@ def bench_ekf(args):
 
     s = slam.ArucoSlam(image_shape=(64, 64), max_landmarks=n_lm + 4)
     s.set_state(mu0, sigma0, ids)
-    frames = [frame_obs(_lib.Observation, k) for k in range(args.warmup + args.steps)]
+    frames = [slam.ArucoSlam.pack_observations(frame_obs(_lib.Observation, k)) for k in range(args.warmup + args.steps)]
+    st = torch.cuda.ExternalStream(s.stream, device=0)
+    sampler = ClockSampler(0)
+    sampler.start()
     for k in range(args.warmup):
-        s.update(frames[k])
+        s.update_packed(frames[k])
     s.synchronize()
-    t0 = time.perf_counter()
+    # CUDA events on the filter's own stream around K frames of b2a_slam_update (each call enqueues the frame's kernels and
+    # returns; the observations cross PCIe inside the region)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
     for k in range(args.warmup, args.warmup + args.steps):
-        s.update(frames[k])
-    s.synchronize()
-    dt = time.perf_counter() - t0
+        s.update_packed(frames[k])
+    e1.record(st)
+    e1.synchronize()
+    dt = e0.elapsed_time(e1) * 1e-3
+    clocks = sampler.result()
     obs_s = args.steps * n_obs / dt
     # parity of the final state against the CPU port run over the same frames
     e = O.Ekf(O.slam_params())
@@ -94,7 +99,8 @@ def bench_ekf(args):
     cpu_rank3 = (args.warmup + args.steps) * n_obs / (time.perf_counter() - t1)
     mu, sg, _ = s.get_state()
     omu, osg, _ = e.get_state()
-    parity = "ok" if (np.abs(mu - omu).max() < 1e-9 and np.abs(sg - osg).max() < 1e-9) else "MISMATCH"
+    err = max(float(np.abs(mu - omu).max()), float(np.abs(sg - osg).max()))
+    parity = "ok" if err < 1e-9 else "MISMATCH"
     # the reference evaluates (I - K Gx) Sigma as a dense N x N product (src/aruco_slam.cpp:204): time a few of those
     e2 = O.Ekf(O.slam_params())
     e2.set_state(mu0, sigma0, ids)
@@ -105,22 +111,32 @@ def bench_ekf(args):
         nd += 1
     cpu_dense = nd * 2 / (time.perf_counter() - t2)
     peak, which = measured_peak_gbs()
-    coop = os.environ.get("B2A_EKF_PER_OBS") is None               # the library's default: all corrections of a frame in one cooperative launch
-    bytes_per_obs = 16 * N * N
-    achieved = obs_s * bytes_per_obs / 1e9
+    panel = os.environ.get("B2A_EKF_PANEL", "1") != "0"
+    coop = os.environ.get("B2A_EKF_PER_OBS") is None
+    bytes_frame = 16 * N * N
+    frames_s = args.steps / dt
+    achieved = frames_s * bytes_frame / 1e9 if panel else obs_s * bytes_frame / 1e9
+    flops = 2.0 * N * N * 3 * n_obs * frames_s
     print(json.dumps({
         "metric": "EKF landmark updates/sec (N = %d)" % N, "value": obs_s, "unit": "observations/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C5: EKF correction, %d landmarks (state dimension %d), %d observations of known landmarks per frame" % (n_lm, N, n_obs),
-                   "timing": "wall clock around K frames of b2a_slam_update + stream synchronize (observations passed from the host each frame)"},
-        "roofline": {"kernel": "k_ekf_frame (one cooperative launch per frame)" if coop else "k_ekf_rank3 (+ k_ekf_gain)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": which, "algorithmic_bytes_per_launch": bytes_per_obs,
-                     "note": "16 N^2 bytes per observation (read + write Sigma, FP64); wall clock per frame, so it includes the H2D copy of the observations, "
-                             "the gain rows, the grid barriers between observations and the host synchronisation at the end of every frame"},
+                   "timing": "CUDA events on the filter's stream around K frames of b2a_slam_update (observations passed from the host each frame)"},
+        "roofline": {"kernel": ("k_ekf_panel_gemm (+ gather / factor / solve): one rank-%d update per frame" % (3 * n_obs)) if panel else
+                               ("k_ekf_frame (one cooperative launch per frame)" if coop else "k_ekf_rank3 (+ k_ekf_gain)"),
+                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": which, "algorithmic_bytes_per_launch": bytes_frame,
+                     "fp64_tflops": flops / 1e12,
+                     "per_observation_form_gbs": obs_s * bytes_frame / 1e9,
+                     "note": ("panel form: Sigma is read and written once per FRAME (16 N^2 bytes), so achieved = frames/s x 16 N^2; the N x %d x N FP64 contraction "
+                              "(fp64_tflops) runs on mma.sync m8n8k4 f64; per_observation_form_gbs = what a pass per observation (SURVEY 8(d): 16 N^2 bytes per "
+                              "observation) would have had to stream at this rate" % (3 * n_obs)) if panel else
+                             "16 N^2 bytes per observation (read + write Sigma, FP64)"},
         "cpu_baseline": {"value": cpu_rank3, "unit": "observations/s", "cores": 1, "kind": "port",
                          "sample": "oracle/ C port, rank-3 form, %d observations" % ((args.warmup + args.steps) * n_obs),
                          "reference_dense_form": {"value": cpu_dense, "unit": "observations/s", "sample": "%d observations with the reference's dense (I - K Gx) Sigma product (aruco_slam.cpp:204)" % (nd * 2)}},
-        "parity": parity, "gpu_launches": (1 if coop else 2 * n_obs) * args.steps}))
+        "parity": parity, "parity_max_abs_err": err, "clocks": clocks,
+        "gpu_launches": (4 if panel else (1 if coop else 2 * n_obs)) * args.steps}))
     s.close()
 
 

@@ -205,6 +205,8 @@ int  b2a_slam_make_observations(b2a_slam *s, const float *corners, const int32_t
 int  b2a_slam_update(b2a_slam *s, const b2a_observation *obs, int n);
 /* The EKF kernels are enqueued on the handle's stream; get_state waits for them, and so does this (used to time updates). */
 int  b2a_slam_synchronize(b2a_slam *s);
+/* the CUDA stream (cudaStream_t) the filter's kernels run on (to time them with CUDA events) */
+void *b2a_slam_stream(const b2a_slam *s);
 /* addImage(img): detect + pose + observations + EKF update for one frame (aruco_slam.cpp:76-263). */
 int  b2a_slam_add_image(b2a_slam *s, b2a_detector *d, const b2a_frames *frame, const b2a_camera *cam);
 
