@@ -66,6 +66,12 @@ class ArucoSlam:
         fr, keep = ArucoDetector._frames_host(image)
         _lib.check(_lib.lib().b2a_slam_add_image(self._h, self.detector._h, C.byref(fr), C.byref(self._cam)))
 
+    def addImageFrames(self, frames):
+        """addImage on a one-frame b2a_frames descriptor (host or device memory, see ArucoDetector.frames_device)"""
+        if self._cam is None:
+            raise _lib.B2AError(1, "setCameraParameters first")
+        _lib.check(_lib.lib().b2a_slam_add_image(self._h, self.detector._h, C.byref(frames), C.byref(self._cam)))
+
     def make_observations(self, corners, ids, rvecs, tvecs):
         c = np.ascontiguousarray(corners, np.float32).reshape(-1, 8)
         n = len(c)

@@ -343,3 +343,52 @@ def c5_state(n_lm: int, seed: int = 0):
     sigma0 = A @ A.T / N + 0.1 * np.eye(N)
     mu0 = np.concatenate([[0.3, -0.2, 0.4], rng.uniform(-4, 4, 3 * n_lm)])
     return mu0, sigma0, np.arange(100, 100 + n_lm, dtype=np.int32)
+
+
+# ----------------------------------------------------------------------------
+# C4 (BASELINE.json config 4): camera streams of a robot driving through a room whose walls carry a map.txt-style landmark
+# map; 1080p pinhole camera (fx = fy = 1400) with the distortion of /root/reference/default.yaml:16-20, DICT_ARUCO_ORIGINAL
+# markers of 0.27 m (parameters.yaml:16-17), one encoder message and one frame per step.
+# ----------------------------------------------------------------------------
+C4_K = np.array([[1400.0, 0, 960.0], [0, 1400.0, 540.0], [0, 0, 1]])
+C4_D = np.array([0.04160142651680036, -0.04771035303381654, -0.0032638387781624705, -0.003985120051161831, 0.01110263483766991])
+C4_R2C = (0.12, 0.0, 0.25)
+C4_DICT = 16
+C4_MARKER_LENGTH = 0.27
+
+
+def c4_map():
+    """the reference's map/map.txt plus more markers in the same layout (id length x y z roll pitch yaw): the far wall (x = 5.1,
+    facing -x) in two rows, the side walls (y = 0.6 facing -y, y = -2.2 facing +y)"""
+    m = list(REFERENCE_MAP)
+    nid = 7
+    for y in (-0.55, -1.05, -2.0, -2.5, 0.45):
+        for z in (0.3, 0.75):
+            m.append((nid, 0.27, 5.10375, y, z, 0.0, -1.5708, 0.0)); nid += 1
+    for x in (2.6, 3.3, 4.6):
+        m.append((nid, 0.27, x, 0.6025, 0.55, 1.5708, -0.0, 0.0)); nid += 1
+    for x in (2.4, 3.1, 3.8, 4.5):
+        for z in (0.3, 0.8):
+            m.append((nid, 0.27, x, -2.2, z, -1.5708, -0.0, 0.0)); nid += 1
+    return tuple(m)
+
+
+def c4_stream(stream: int, n_frames: int, dt: float = 0.1):
+    """frames (n, 1080, 1920) u8, encoder readings (n, 3) = (wl, wr, dt) applied BEFORE each frame, ground-truth poses (n, 3)
+    of one camera stream; streams differ in start pose and wheel speeds"""
+    rng = np.random.default_rng(4000 + stream)
+    cmap = c4_map()
+    pose = np.array([2.45 + 0.12 * (stream % 4), -0.9 + 0.2 * (stream // 4) + rng.uniform(-0.1, 0.1), rng.uniform(-0.25, 0.1)])
+    frames, enc, truth = [], [], []
+    for f in range(n_frames):
+        turn = -1.0 if (f // 6) % 2 == 0 else 0.6
+        wl, wr = 2.0 + 0.5 * turn + rng.uniform(-0.2, 0.2), 2.0 - 0.5 * turn + rng.uniform(-0.2, 0.2)
+        if f % 9 == 4:
+            wl = wr = 0.0                                   # standing still: the reference's stationary gate
+        pose = drive(pose, wl, wr, dt)
+        poses = scene_poses(cmap, pose, C4_R2C, C4_K, C4_D, 1920, 1080)
+        fr = render_scene(1920, 1080, C4_DICT, C4_K, C4_D, C4_MARKER_LENGTH, poses, seed=1000 * stream + f, noise_sigma=1.0, blur_sigma=0.8)
+        frames.append(fr.image)
+        enc.append((wl, wr, dt))
+        truth.append(pose.copy())
+    return np.stack(frames), np.array(enc), np.array(truth)
