@@ -260,6 +260,41 @@ class ArucoDetector:
         return int(_lib.lib().b2a_detector_stream(self._h) or 0)
 
 
+class MultiDetector:
+    """Several GPUs of one box from one process: a batch of host frames is cut into contiguous blocks, one per device, each through
+    its own handle and host thread (inside the library); the detections come back gathered in frame order.  Frames are independent,
+    so there is no collective.  `devices` may list a device more than once (two handles on one GPU)."""
+
+    def __init__(self, dictionary: Dictionary, parameters: DetectorParams | None = None, *, devices=(0,), max_shape=(1080, 1920),
+                 max_batch: int = 1, max_markers: int = 256, max_candidates: int = 2048):
+        prm = parameters or DetectorParameters()
+        self._dict, self._keep = _cdict(dictionary)
+        cfg = _lib.DetectorConfig(0, int(max_shape[1]), int(max_shape[0]), int(max_batch), int(max_markers), int(max_candidates))
+        dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        _lib.check(_lib.lib().b2a_multi_create(dev, len(devices), C.byref(cfg), C.byref(self._dict), C.byref(prm), C.byref(h)))
+        self._h = h
+        self.devices = tuple(devices)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().b2a_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def detect_pose_batch(self, images, marker_length=None, K=None, D=None) -> BatchDetections:
+        fr, keep = ArucoDetector._frames_host(images)
+        det = _lib.Detections()
+        cam = _camera(K, D, marker_length) if K is not None else None
+        _lib.check(_lib.lib().b2a_multi_detect_pose(self._h, C.byref(fr), C.byref(cam) if cam is not None else None, C.byref(det)))
+        return ArucoDetector._collect(None, det, cam is not None)
+
+
 # ---- free functions shaped like the legacy cv::aruco API the reference calls -------------------------
 _detectors: dict = {}
 

@@ -19,6 +19,7 @@
 #include <queue>
 #include <unordered_map>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace b2a;
@@ -963,6 +964,102 @@ extern "C" int b2a_detect_pose_wait(b2a_detector *d, int ticket, b2a_detections 
     TRY(finish_pipeline(t));
     if (t != d) { d->launches = t->launches; std::memcpy(d->stage_ms, t->stage_ms, sizeof(d->stage_ms)); }
     return fill_out(t, t->pending_batch, t->pending_pose, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// several GPUs of one box from one process: frames are independent, so a batch is cut into contiguous blocks, one per
+// device, each block goes through its device's handle from its own host thread, and only the detections are gathered -- on the
+// host, in frame order.  No collective, no peer traffic.
+// ------------------------------------------------------------------------------------------------
+struct b2a_multi {
+    std::vector<b2a_detector *> dets;
+    int max_batch = 0, max_markers = 0;
+    std::vector<int32_t> nacc, nrej, status, ids;
+    std::vector<float> corners, rejected;
+    std::vector<double> rvecs, tvecs;
+};
+
+extern "C" void b2a_multi_destroy(b2a_multi *m)
+{
+    if (!m) return;
+    for (b2a_detector *d : m->dets) b2a_detector_destroy(d);
+    delete m;
+}
+
+extern "C" int b2a_multi_create(const int *devices, int n_devices, const b2a_detector_config *cfg, const b2a_dictionary *dict,
+                                const b2a_detector_params *params, b2a_multi **out)
+{
+    if (!devices || n_devices <= 0 || !cfg || !dict || !out) return set_err(B2A_ERR_INVALID, "null argument");
+    b2a_multi *m = new b2a_multi();
+    m->max_batch = cfg->max_batch;
+    const int per = (cfg->max_batch + n_devices - 1) / n_devices;
+    for (int g = 0; g < n_devices; ++g) {
+        b2a_detector_config c = *cfg;
+        c.device = devices[g]; c.max_batch = std::max(per, 1);
+        b2a_detector *d = nullptr;
+        const int rc = b2a_detector_create(&c, dict, params, &d);
+        if (rc != B2A_OK) { const std::string keep = g_err; b2a_multi_destroy(m); g_err = keep; return rc; }
+        m->dets.push_back(d);
+    }
+    m->max_markers = m->dets[0]->max_markers;
+    const size_t BK = (size_t)cfg->max_batch * m->max_markers;
+    m->nacc.resize(cfg->max_batch); m->nrej.resize(cfg->max_batch); m->status.resize(cfg->max_batch); m->ids.resize(BK);
+    m->corners.resize(BK * 8); m->rejected.resize(BK * 8); m->rvecs.resize(BK * 3); m->tvecs.resize(BK * 3);
+    *out = m;
+    return B2A_OK;
+}
+
+extern "C" int b2a_multi_num_devices(const b2a_multi *m) { return m ? (int)m->dets.size() : 0; }
+
+extern "C" int b2a_multi_detect_pose(b2a_multi *m, const b2a_frames *f, const b2a_camera *cam, b2a_detections *out)
+{
+    if (!m || !f || !out || !f->data) return set_err(B2A_ERR_INVALID, "null argument");
+    if (f->on_device) return set_err(B2A_ERR_INVALID, "the frames of a multi-device call live in host memory");
+    if (f->batch <= 0 || f->batch > m->max_batch) return set_err(B2A_ERR_INVALID, "batch outside [1, max_batch]");
+    if (cam && !(cam->marker_length > 0)) return set_err(B2A_ERR_INVALID, "markerLength <= 0");
+    const int G = (int)m->dets.size(), B = f->batch, K = m->max_markers;
+    const size_t in_pitch = f->row_stride ? f->row_stride : (size_t)f->width * f->channels;
+    const size_t in_frame = f->frame_stride ? f->frame_stride : in_pitch * f->height;
+    std::vector<int> rcs(G, B2A_OK);
+    std::vector<std::string> errs(G);
+    std::vector<b2a_detections> dets(G);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) {
+        const int b0 = (int)((long long)B * g / G), b1 = (int)((long long)B * (g + 1) / G);
+        if (b1 <= b0) continue;
+        th.emplace_back([&, g, b0, b1]() {
+            b2a_frames fr = *f;
+            fr.data = f->data + (size_t)b0 * in_frame; fr.batch = b1 - b0; fr.row_stride = in_pitch; fr.frame_stride = in_frame;
+            rcs[g] = cam ? b2a_detect_pose(m->dets[g], &fr, cam, &dets[g]) : b2a_detect(m->dets[g], &fr, &dets[g]);
+            if (rcs[g] != B2A_OK) errs[g] = g_err;             // the error text is thread local
+        });
+    }
+    for (std::thread &t : th) t.join();
+    // gather in frame order (only the filled entries move)
+    int rc = B2A_OK;
+    for (int g = 0; g < G; ++g) {
+        const int b0 = (int)((long long)B * g / G), b1 = (int)((long long)B * (g + 1) / G);
+        if (b1 <= b0) continue;
+        if (rcs[g] != B2A_OK && rcs[g] != B2A_ERR_CAPACITY) return set_err(rcs[g], "device block " + std::to_string(g) + ": " + errs[g]);
+        if (rcs[g] == B2A_ERR_CAPACITY) { rc = B2A_ERR_CAPACITY; g_err = errs[g]; }
+        const b2a_detector *d = m->dets[g];
+        for (int b = b0; b < b1; ++b) {
+            const int l = b - b0, na = d->h_nacc[l], nr = d->h_nrej[l];
+            m->nacc[b] = na; m->nrej[b] = nr; m->status[b] = d->h_status[l];
+            std::memcpy(&m->ids[(size_t)b * K], d->h_ids + (size_t)l * K, (size_t)na * sizeof(int32_t));
+            std::memcpy(&m->corners[(size_t)b * K * 8], d->h_corners + (size_t)l * K * 8, (size_t)na * 8 * sizeof(float));
+            std::memcpy(&m->rejected[(size_t)b * K * 8], d->h_rejected + (size_t)l * K * 8, (size_t)nr * 8 * sizeof(float));
+            if (cam) {
+                std::memcpy(&m->rvecs[(size_t)b * K * 3], d->h_rvecs + (size_t)l * K * 3, (size_t)na * 3 * sizeof(double));
+                std::memcpy(&m->tvecs[(size_t)b * K * 3], d->h_tvecs + (size_t)l * K * 3, (size_t)na * 3 * sizeof(double));
+            }
+        }
+    }
+    out->batch = B; out->max_markers = K;
+    out->n_accepted = m->nacc.data(); out->n_rejected = m->nrej.data(); out->status = m->status.data(); out->ids = m->ids.data();
+    out->corners = m->corners.data(); out->rejected = m->rejected.data();
+    out->rvecs = cam ? m->rvecs.data() : nullptr; out->tvecs = cam ? m->tvecs.data() : nullptr;
+    return rc;
 }
 
 extern "C" int b2a_detector_set_streams(b2a_detector *d, int n)

@@ -200,8 +200,7 @@ def bench_c4(args, rank, local_rank, world):
     from aruco_slam_b200 import slam, aruco, formats
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        nccl_init(dist, torch, local_rank)
     frames, enc, truth = synth.c4_stream(rank, n)
     d_frames = torch.from_numpy(frames).cuda()
     h_frames = torch.from_numpy(frames).pin_memory()
@@ -313,6 +312,27 @@ def measured_peak_gbs():
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def nccl_init(dist, torch, local_rank):
+    """NCCL's own lines (the box exports NCCL_DEBUG; the version banner goes to stdout whatever NCCL_DEBUG_FILE says) must not share
+    stdout with the one JSON line: while the communicator comes up, file descriptor 1 points at stderr, so the lines stay visible
+    there at the box's own debug level."""
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        t = torch.zeros(1, device="cuda")
+        dist.all_reduce(t)                                     # the communicator is created lazily: bring it up now
+        parts = [torch.zeros(1, device="cuda") for _ in range(dist.get_world_size())] if dist.get_rank() == 0 else None
+        dist.gather(t, parts, dst=0)                           # and the point-to-point channels the gather uses
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
 
 
 class ClockSampler(threading.Thread):
@@ -477,9 +497,7 @@ def main():
         raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL's own version / debug lines must not share stdout with the JSON line: they go to stderr, at the box's own level
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        nccl_init(dist, torch, local_rank)
 
     frames = synth.render_batch(args.workload, B, base_seed=1000 * rank)          # this rank's shard
     dic = D.getPredefinedDictionary(dict_id)
@@ -539,6 +557,14 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), {k: v / steps for k, v in stage_acc.items()}, launches
 
+    KM = 64                                                    # markers per frame that travel in the gather (C2 frames carry <= 30; more are counted only)
+    stream_rec = None
+    if world > 1:
+        stream_rec = torch.zeros((max(args.steps, args.warmup, 1), B, 1 + KM * (1 + 8 + 6)), dtype=torch.float64).pin_memory()
+        warm = stream_rec[:args.steps].cuda()
+        dist.gather(warm, [torch.empty_like(warm) for _ in range(world)] if rank == 0 else None, dst=0)      # buffers and channels of this message size
+        torch.cuda.synchronize()
+
     def run_stream(frames_desc, steps, warmup):
         """the end-to-end number: b2a_detect_pose_submit / _wait through ONE handle from ONE host thread.  Step k+1 is
         submitted before step k is waited for, so its PCIe copy runs under step k's kernels; every step still copies its
@@ -554,18 +580,48 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(lib_stream)                                  # the stream is idle: this is the start of the region
         got, pending = 0, None
-        for _ in range(steps):
+        rec = stream_rec[:steps] if world > 1 else None
+
+        def take(step, det_c):
+            """read the step's result on the host; with several ranks also file its compact record for the gather"""
+            na = np.ctypeslib.as_array(det_c.n_accepted, (B,))
+            if rec is not None:
+                K_ = det_c.max_markers
+                r = rec[step].numpy()
+                r[:, 0] = na
+                ids = np.ctypeslib.as_array(det_c.ids, (B, K_))[:, :KM]
+                cor = np.ctypeslib.as_array(det_c.corners, (B, K_, 8))[:, :KM]
+                rv = np.ctypeslib.as_array(det_c.rvecs, (B, K_, 3))[:, :KM]
+                tv = np.ctypeslib.as_array(det_c.tvecs, (B, K_, 3))[:, :KM]
+                m = min(KM, K_)
+                r[:, 1:1 + m] = ids
+                r[:, 1 + KM:1 + KM + 8 * m] = cor.reshape(B, -1)
+                r[:, 1 + 9 * KM:1 + 9 * KM + 3 * m] = rv.reshape(B, -1)
+                r[:, 1 + 12 * KM:1 + 12 * KM + 3 * m] = tv.reshape(B, -1)
+            return int(na.sum())
+
+        for k in range(steps):
             t = det.submit_raw(frames_desc, cam)
             if pending is not None:
-                got += int(np.ctypeslib.as_array(det.wait_raw(pending).n_accepted, (B,)).sum())
+                got += take(k - 1, det.wait_raw(pending))
             pending = t
-        got += int(np.ctypeslib.as_array(det.wait_raw(pending).n_accepted, (B,)).sum())
+        got += take(steps - 1, det.wait_raw(pending))
+        gathered = None
+        if world > 1:
+            # only the detections travel: every rank's records to rank 0 (frame order = rank order, SURVEY 8(e)), inside the region
+            dev_rec = rec.cuda(non_blocking=True)
+            parts = [torch.empty_like(dev_rec) for _ in range(world)] if rank == 0 else None
+            dist.gather(dev_rec, parts, dst=0)
+            if rank == 0:
+                gathered = torch.stack(parts).cpu()
         e1.record(lib_stream)                                  # after the last wait returned: everything is complete
         e1.synchronize()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if gathered is not None:
+            got = int(gathered[..., 0].sum().item())            # markers of ALL ranks, counted from the gathered records
         return float(t.item()), got
 
     sampler = ClockSampler(local_rank)
@@ -635,7 +691,8 @@ def main():
                     "how": "b2a_detect_pose_submit / _wait on pinned host frames: one handle, one host thread, step k+1 submitted before step k "
                            "is waited for (its H2D copy overlaps step k's kernels); every step's H2D and D2H are inside the region and every "
                            "step's result is read on the host; CUDA events around the K steps; L2 flushed before the region (each step "
-                           "streams 66 MB of new frames through it)",
+                           "streams 66 MB of new frames through it); with several ranks every rank's detection records are gathered to rank 0 "
+                           "(one NCCL gather of the compact records at the end of the region, inside it)",
                     "markers_read": markers_e2e},
             "e2e_sync": {"value": total_frames / (ms_e2e_sync * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e_sync / args.steps,
                          "how": "one synchronous b2a_detect_pose call per step on pinned host frames (copy, kernels, results; nothing overlaps "

@@ -137,6 +137,18 @@ int b2a_detect_pose(b2a_detector *d, const b2a_frames *frames, const b2a_camera 
 int b2a_detect_pose_submit(b2a_detector *d, const b2a_frames *frames, const b2a_camera *cam, int *ticket);
 int b2a_detect_pose_wait(b2a_detector *d, int ticket, b2a_detections *out);
 
+/* ---- several GPUs of one box from one process (frames are independent: no collective) ----
+ * One detector handle and one host thread per listed device (a device may be listed more than once); a batch of HOST frames is
+ * cut into contiguous blocks, frames [g B / G, (g+1) B / G) go to device g, and the detections are gathered on the host in frame
+ * order into library-owned arrays (valid until the next call).  cfg->max_batch is the largest batch of a CALL; cfg->device is
+ * ignored.  cam = NULL: detect only. */
+typedef struct b2a_multi b2a_multi;
+int  b2a_multi_create(const int *devices, int n_devices, const b2a_detector_config *cfg, const b2a_dictionary *dict,
+                      const b2a_detector_params *params, b2a_multi **out);
+void b2a_multi_destroy(b2a_multi *m);
+int  b2a_multi_num_devices(const b2a_multi *m);
+int  b2a_multi_detect_pose(b2a_multi *m, const b2a_frames *frames, const b2a_camera *cam, b2a_detections *out);
+
 /* estimatePoseSingleMarkers on caller-provided corners (host arrays): corners [n][4][2] f32,
  * rvecs/tvecs [n][3] f64.  (aruco_slam.cpp:314) */
 int b2a_estimate_pose_single_markers(b2a_detector *d, const float *corners, int n, const b2a_camera *cam,

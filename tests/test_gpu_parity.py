@@ -427,3 +427,29 @@ def test_submit_wait_matches_synchronous_calls(aruco, oracle):
     assert np.array_equal(r.ids[0], want[0].ids[0])
     det.detect_pose_batch(batches[0], 0.27, K, Dist)          # and the synchronous call works again
     det.close()
+
+
+def test_multi_device_detector_gathers_in_frame_order(aruco, oracle):
+    """b2a_multi_*: one handle and one host thread per listed device, contiguous blocks, detections gathered on the host in frame
+    order.  On a one-GPU box the two handles share device 0; with more devices visible they spread."""
+    import torch
+    n_dev = torch.cuda.device_count()
+    devices = tuple(range(min(n_dev, 4))) if n_dev >= 2 else (0, 0)
+    B = 7                                               # not a multiple of the device count: ragged blocks
+    frames = synth.render_batch("C2", B, base_seed=300)
+    dic = D.getPredefinedDictionary(D.DICT_6X6_250)
+    K = np.array([[1400.0, 0, 960], [0, 1400.0, 540], [0, 0, 1]])
+    Dist = np.array([0.05, -0.1, 0.001, -0.002, 0.02])
+    md = aruco.MultiDetector(dic, devices=devices, max_shape=frames.shape[1:], max_batch=B)
+    r = md.detect_pose_batch(frames, 0.27, K, Dist)
+    single = _detector(aruco, dic, frames.shape[1:], batch=B)
+    r1 = single.detect_pose_batch(frames, 0.27, K, Dist)
+    for b in range(B):
+        oc, oi, orj = oracle.detect(frames[b], dic)
+        assert np.array_equal(r.ids[b], oi) and np.array_equal(r.corners[b], oc) and np.array_equal(r.rejected[b], orj), b
+        assert np.array_equal(r.rvecs[b], r1.rvecs[b]) and np.array_equal(r.tvecs[b], r1.tvecs[b])
+    r2 = md.detect_pose_batch(frames[:1], 0.27, K, Dist)          # fewer frames than devices: empty blocks
+    assert np.array_equal(r2.ids[0], r.ids[0])
+    r3 = md.detect_pose_batch(frames[2:5])                        # detect only
+    assert r3.rvecs is None and np.array_equal(r3.ids[1], r.ids[3])
+    md.close(); single.close()
