@@ -396,8 +396,9 @@ def _cpu_worker(frame):
     return len(ids)
 
 
-def cpu_reference_fps(frames, dict_id, seconds_target=12.0, max_passes=50, pool=None):
-    """frames/s of the CPU path, frame-parallel over all host cores (the CPU's best case)."""
+def cpu_reference_fps(frames, dict_id, seconds_target=8.0, max_passes=50, pool=None):
+    """frames/s of the CPU path, frame-parallel over all host cores (the CPU's best case), plus the two single-process modes of
+    BASELINE.md section 3 (cv2 with 1 thread, cv2 with all cores as threads) as per-frame median / min."""
     import multiprocessing as mp
     try:
         import cv2  # noqa: F401
@@ -410,11 +411,14 @@ def cpu_reference_fps(frames, dict_id, seconds_target=12.0, max_passes=50, pool=
         pool = mp.get_context("fork").Pool(cores, initializer=_cpu_worker_init, initargs=(use_cv2, dict_id))
     lst = [f for f in frames]
     pool.map(_cpu_worker, lst[:min(len(lst), cores)])            # warm-up
+    per_pass = []
     t0 = time.perf_counter()
     done = 0
     passes = 0
     while passes < max_passes:
+        t1 = time.perf_counter()
         pool.map(_cpu_worker, lst, chunksize=max(1, len(lst) // (cores * 2) or 1))
+        per_pass.append(len(lst) / (time.perf_counter() - t1))
         done += len(lst)
         passes += 1
         if time.perf_counter() - t0 > seconds_target:
@@ -424,7 +428,24 @@ def cpu_reference_fps(frames, dict_id, seconds_target=12.0, max_passes=50, pool=
         pool.close()
     kind = "reference" if use_cv2 else "port"
     what = ("cv2 4.13 ArucoDetector.detectMarkers + per-marker solvePnP(ITERATIVE)" if use_cv2 else "oracle/ C port (detect + pose)")
-    return done / dt, cores, kind, "%s, %d passes over %d frames, %d worker processes x 1 thread" % (what, passes, len(lst), cores)
+    modes = {"process_pool": {"workers": cores, "frames_per_s_mean": done / dt, "frames_per_s_median_pass": statistics.median(per_pass), "frames_per_s_best_pass": max(per_pass),
+                              "passes": passes}}
+    if use_cv2:
+        import cv2
+        for name, nthreads in (("single_process_1_thread", 1), ("single_process_all_threads", cores)):
+            cv2.setNumThreads(nthreads)
+            _cpu_worker_init(True, dict_id)
+            cv2.setNumThreads(nthreads)                        # the worker initialiser pins 1 thread: undo for this mode
+            sample = lst[:min(len(lst), 8)]
+            _cpu_worker(sample[0])
+            ts = []
+            for f in sample:
+                t1 = time.perf_counter()
+                _cpu_worker(f)
+                ts.append(time.perf_counter() - t1)
+            modes[name] = {"threads": nthreads, "ms_per_frame_median": 1e3 * statistics.median(ts), "ms_per_frame_min": 1e3 * min(ts),
+                           "frames_per_s_median": 1.0 / statistics.median(ts), "frames": len(sample)}
+    return done / dt, cores, kind, "%s, %d passes over %d frames, %d worker processes x 1 thread" % (what, passes, len(lst), cores), modes
 
 
 # ----------------------------------------------------------------------------------------------
@@ -475,8 +496,11 @@ def main():
         for _ in range(max(args.warmup, 1)):
             pool.map(_cpu_worker, lst)
         t0 = time.perf_counter()
+        step_s = []
         for _ in range(args.steps):
+            t1 = time.perf_counter()
             pool.map(_cpu_worker, lst)
+            step_s.append(time.perf_counter() - t1)
         dt = time.perf_counter() - t0
         pool.close()
         fps = args.steps * B / dt
@@ -487,6 +511,7 @@ def main():
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
+                          "ms_per_step_median": 1e3 * statistics.median(step_s), "ms_per_step_min": 1e3 * min(step_s), "ms_per_step_max": 1e3 * max(step_s),
                           "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -717,8 +742,8 @@ def main():
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            fps, cores, kind, sample = cpu_reference_fps(frames, dict_id)
-            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
+            fps, cores, kind, sample, modes = cpu_reference_fps(frames, dict_id)
+            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample, "modes": modes}
         print(json.dumps(out))
     det.close()
     if world > 1:
