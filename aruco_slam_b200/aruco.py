@@ -211,6 +211,21 @@ class ArucoDetector:
         _lib.check(_lib.lib().b2a_estimate_pose_single_markers(self._h, c.ctypes.data, n, C.byref(cam), rv.ctypes.data, tv.ctypes.data))
         return rv.reshape(n, 1, 3), tv.reshape(n, 1, 3)
 
+    def drawDetectedMarkers(self, image, corners, ids=None, borderColor=(0, 255, 0)):
+        """cv::aruco::drawDetectedMarkers: draws into `image` ((H,W) or (H,W,3) uint8, contiguous) in place and returns it"""
+        img = np.asarray(image)
+        if img.dtype != np.uint8 or img.ndim not in (2, 3) or (img.ndim == 3 and img.shape[2] != 3) or not img.flags.c_contiguous:
+            raise B2AError(1, "drawDetectedMarkers takes a contiguous 8-bit image with 1 or 3 channels")
+        c = np.ascontiguousarray(np.asarray(corners, np.float32).reshape(-1, 8))
+        n = len(c)
+        ida = None if ids is None else np.ascontiguousarray(np.asarray(ids, np.int32).reshape(-1))
+        if ida is not None and len(ida) != n:
+            raise B2AError(1, "ids and corners differ in length")
+        col = (C.c_uint8 * 3)(*[int(v) for v in borderColor[:3]])
+        _lib.check(_lib.lib().b2a_draw_detected_markers(self._h, img.ctypes.data, img.shape[1], img.shape[0], 1 if img.ndim == 2 else 3, 0,
+                                                        c.ctypes.data, ida.ctypes.data if ida is not None else None, n, col))
+        return img
+
     # ---- stage taps (parity tests) ---------------------------------------------------------------
     @property
     def num_scales(self) -> int:

@@ -6,6 +6,7 @@
 #include "detect_kernels.cuh"
 #include "ekf_kernels.cuh"
 #include "pose_core.h"
+#include "draw_core.h"
 
 #include <algorithm>
 #include <cctype>
@@ -969,6 +970,70 @@ extern "C" int b2a_detect_pose_wait(b2a_detector *d, int ticket, b2a_detections 
     TRY(finish_pipeline(t));
     if (t != d) { d->launches = t->launches; std::memcpy(d->stage_ms, t->stage_ms, sizeof(d->stage_ms)); }
     return fill_out(t, t->pending_batch, t->pending_pose, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// overlay: cv::aruco::drawDetectedMarkers (aruco_slam.cpp:319).  One CTA per image; the markers are drawn one after the other (a later
+// marker's lines may cross an earlier label), inside a marker the four lines are walked by four threads, the corner stamp is a pixel
+// per thread and the label a pixel per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_draw_markers(OverlayImage im, OverlayTables t, const float *__restrict__ corners, const int32_t *__restrict__ ids, const int32_t *__restrict__ n_dev, int n,
+               uchar3 border)
+{
+    if (n_dev) n = *n_dev;
+    const uint8_t bc[3] = {border.x, border.y, border.z};
+    uint8_t text[3], corner[3];
+    overlay_colours(bc, text, corner);
+    for (int i = 0; i < n; ++i) {
+        const float *q = corners + 8 * i;
+        int px[4], py[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { px[j] = overlay_round(q[2 * j]); py[j] = overlay_round(q[2 * j + 1]); }
+        if (threadIdx.x < 4) { const int j = threadIdx.x; overlay_line(im, px[j], py[j], px[(j + 1) & 3], py[(j + 1) & 3], bc); }
+        __syncthreads();
+        if (threadIdx.x < 121) overlay_stamp_pixel(im, t, px[0], py[0], (int)threadIdx.x % 11 - 5, (int)threadIdx.x / 11 - 5, corner);
+        __syncthreads();
+        if (ids) {
+            int ox, oy;
+            overlay_text_origin(q, ox, oy);
+            const int id = ids[i];
+            for (int k = threadIdx.x; k < 16 * 72; k += blockDim.x) {
+                const int tx = k % 72, ty = k / 72 - 13;
+                if (overlay_text_bit(t, id, tx, ty)) overlay_put(im, ox + tx, oy + ty, text);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+extern "C" int b2a_draw_detected_markers(b2a_detector *d, uint8_t *image, int width, int height, int channels, size_t row_stride,
+                                         const float *corners, const int32_t *ids, int n, const uint8_t border_bgr[3])
+{
+    if (!d || !image || (n > 0 && !corners)) return set_err(B2A_ERR_INVALID, "null argument");
+    if (channels != 1 && channels != 3) return set_err(B2A_ERR_INVALID, "channels must be 1 or 3");            // CV_Assert in drawDetectedMarkers
+    if (width <= 0 || height <= 0 || (size_t)width * height > (size_t)d->cfg.max_width * d->cfg.max_height) return set_err(B2A_ERR_INVALID, "image size outside the handle's maximum");
+    if (n < 0 || n > d->max_markers) return set_err(B2A_ERR_INVALID, "more markers than max_markers");
+    if (d->in_flight) return set_err(B2A_ERR_INVALID, "a submitted batch is still in flight on this handle");
+    if (ids) for (int i = 0; i < n; ++i) if (ids[i] < 0 || ids[i] > 9999) return set_err(B2A_ERR_UNSUPPORTED, "marker id outside 0 .. 9999");
+    if (n == 0) return B2A_OK;
+    CU(cudaSetDevice(d->device));
+    static const OverlayTables tables = make_overlay_tables();
+    const size_t rowbytes = (size_t)width * channels, pitch = row_stride ? row_stride : rowbytes;
+    cudaStream_t st = d->stream;
+    // the image visits the frame buffer of the handle; corners / ids use the output arrays of the first frame slot
+    CU(cudaMemcpy2DAsync(d->d_in, rowbytes, image, pitch, rowbytes, height, cudaMemcpyHostToDevice, st));
+    float *dc = d->d_corners2;
+    int32_t *di = (int32_t *)d->d_wM;
+    CU(cudaMemcpyAsync(dc, corners, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    if (ids) CU(cudaMemcpyAsync(di, ids, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    OverlayImage im{d->d_in, width, height, channels, rowbytes};
+    const uint8_t dflt[3] = {0, 255, 0};
+    const uint8_t *b = border_bgr ? border_bgr : dflt;
+    k_draw_markers<<<1, 256, 0, st>>>(im, tables, dc, ids ? di : nullptr, nullptr, n, make_uchar3(b[0], b[1], b[2]));
+    CU(cudaMemcpy2DAsync(image, pitch, d->d_in, rowbytes, rowbytes, height, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return launch_err("k_draw_markers");
 }
 
 // ------------------------------------------------------------------------------------------------

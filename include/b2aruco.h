@@ -137,6 +137,14 @@ int b2a_detect_pose(b2a_detector *d, const b2a_frames *frames, const b2a_camera 
 int b2a_detect_pose_submit(b2a_detector *d, const b2a_frames *frames, const b2a_camera *cam, int *ticket);
 int b2a_detect_pose_wait(b2a_detector *d, int ticket, b2a_detections *out);
 
+/* cv::aruco::drawDetectedMarkers(image, corners, ids, borderColor) (aruco_slam.cpp:319; the image getMarkedImg returns,
+ * aruco_slam.h:152): the overlay is drawn into `image` (host memory, 8-bit, 1 or 3 channels, in place) on the device -- marker
+ * sides, the anti-aliased square on the first corner, the "id=N" label -- pixel for pixel as OpenCV 4.13 draws it when the corners
+ * are integer valued (CORNER_REFINE_NONE) and inside the image.  ids may be NULL (no labels); border_bgr NULL = (0, 255, 0).
+ * n <= max_markers of the handle; ids 0 .. 9999. */
+int b2a_draw_detected_markers(b2a_detector *d, uint8_t *image, int width, int height, int channels, size_t row_stride,
+                              const float *corners, const int32_t *ids, int n, const uint8_t border_bgr[3]);
+
 /* ---- several GPUs of one box from one process (frames are independent: no collective) ----
  * One detector handle and one host thread per listed device (a device may be listed more than once); a batch of HOST frames is
  * cut into contiguous blocks, frames [g B / G, (g+1) B / G) go to device g, and the detections are gathered on the host in frame

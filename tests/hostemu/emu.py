@@ -22,7 +22,7 @@ class EmuParams(C.Structure):
 
 
 def build():
-    srcs = [os.path.join(_HERE, "hostemu.cpp")] + [os.path.join(_CSRC, f) for f in ("core.h", "frame_logic.h", "pose_core.h")]
+    srcs = [os.path.join(_HERE, "hostemu.cpp")] + [os.path.join(_CSRC, f) for f in ("core.h", "frame_logic.h", "pose_core.h", "draw_core.h")] + [os.path.join(_CSRC, "..", "data", "overlay_tables.inc")]
     if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", _SO, srcs[0]])
     return _SO
@@ -131,3 +131,20 @@ def approx(contour, eps):
     lib().emu_approx.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
     m = lib().emu_approx(c.ctypes.data_as(C.c_void_p), len(c), float(eps), out.ctypes.data_as(C.c_void_p))
     return None if m < 0 else out[:m].copy()
+
+
+def draw(image, corners, ids=None, border=(0, 255, 0)):
+    """product drawDetectedMarkers logic (draw_core.h) on a copy of `image` ((H,W) or (H,W,3) uint8)"""
+    img = np.ascontiguousarray(image, np.uint8).copy()
+    H, W = img.shape[:2]
+    ch = 1 if img.ndim == 2 else 3
+    c = np.ascontiguousarray(corners, np.float32).reshape(-1, 8)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    idp = None
+    if ids is not None:
+        ida = np.ascontiguousarray(ids, np.int32).reshape(-1)
+        idp = P(ida)
+    b = np.array(border, np.uint8)
+    lib().emu_draw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib().emu_draw(P(img), W, H, ch, P(c), idp, len(c), P(b))
+    return img

@@ -6,6 +6,7 @@
 #include "../../aruco_slam_b200/csrc/core.h"
 #include "../../aruco_slam_b200/csrc/frame_logic.h"
 #include "../../aruco_slam_b200/csrc/pose_core.h"
+#include "../../aruco_slam_b200/csrc/draw_core.h"
 
 #include <algorithm>
 #include <cmath>
@@ -343,6 +344,14 @@ int emu_observation(const float *corners, int id, const double *rvec, const doub
     obs12[0] = o.x; obs12[1] = o.y; obs12[2] = o.theta;
     for (int i = 0; i < 9; ++i) obs12[3 + i] = o.cov[i];
     return 1;
+}
+
+// drawDetectedMarkers through the product's draw_core.h, one thread
+void emu_draw(uint8_t *img, int W, int H, int channels, const float *corners, const int32_t *ids, int n, const uint8_t *border)
+{
+    static const OverlayTables t = make_overlay_tables();
+    OverlayImage im{img, W, H, channels, (size_t)W * channels};
+    overlay_draw_sequential(im, t, corners, ids, n, border);
 }
 
 }  // extern "C"

@@ -453,3 +453,20 @@ def test_multi_device_detector_gathers_in_frame_order(aruco, oracle):
     r3 = md.detect_pose_batch(frames[2:5])                        # detect only
     assert r3.rvecs is None and np.array_equal(r3.ids[1], r.ids[3])
     md.close(); single.close()
+
+
+@pytest.mark.parametrize("name", golden_names("draw_"))
+def test_draw_detected_markers_vs_cv2(aruco, name):
+    """b2a_draw_detected_markers against cv2.aruco.drawDetectedMarkers overlays, every pixel (with ids, without, custom colour)"""
+    from test_draw import draw_case
+    g = golden(name)
+    img, want = draw_case(g)
+    det = _detector(aruco, D.getPredefinedDictionary(0), img.shape[:2])
+    assert np.array_equal(det.drawDetectedMarkers(img.copy(), g["corners"], g["ids"]), want["ids"])
+    assert np.array_equal(det.drawDetectedMarkers(img.copy(), g["corners"]), want["no_ids"])
+    assert np.array_equal(det.drawDetectedMarkers(img.copy(), g["corners"], g["ids"], tuple(int(v) for v in g["colour"])), want["colour"])
+    # what the reference does per frame: detect, then draw on a copy (aruco_slam.cpp:313-319)
+    c, ids, _ = det.detectMarkers(img) if int(g["ids"].max()) < 50 else (None, None, None)
+    if ids is not None and sorted(ids.ravel().tolist()) == sorted(g["ids"].tolist()):
+        assert np.array_equal(det.drawDetectedMarkers(img.copy(), np.array(c), ids), want["ids"])
+    det.close()
