@@ -211,6 +211,12 @@ class ArucoDetector:
         _lib.check(_lib.lib().b2a_estimate_pose_single_markers(self._h, c.ctypes.data, n, C.byref(cam), rv.ctypes.data, tv.ctypes.data))
         return rv.reshape(n, 1, 3), tv.reshape(n, 1, 3)
 
+    def last_detections(self) -> BatchDetections:
+        """the results of the handle's last completed call again (b2a_detector_last_detections)"""
+        det = _lib.Detections()
+        _lib.check(_lib.lib().b2a_detector_last_detections(self._h, C.byref(det)))
+        return self._collect(det, bool(det.rvecs))
+
     def drawDetectedMarkers(self, image, corners, ids=None, borderColor=(0, 255, 0)):
         """cv::aruco::drawDetectedMarkers: draws into `image` ((H,W) or (H,W,3) uint8, contiguous) in place and returns it"""
         img = np.asarray(image)

@@ -242,6 +242,7 @@ struct b2a_detector {
     float stage_ms[ST_COUNT];
     int launches = 0;
     int timed_mode = 0;
+    int last_call_batch = 0; bool last_call_pose = false;       // what the result arrays hold (b2a_detector_last_detections)
     // asynchronous submit / wait: the handle owns a second, lazily created pipeline context (all buffers and streams); batches
     // alternate between the two, so the H2D copy of one overlaps the kernels of the other
     b2a_detector *twin = nullptr;
@@ -791,6 +792,7 @@ static int enqueue_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_came
     std::memset(d->ev_used, 0, sizeof(d->ev_used));
     d->launches = 0;
     d->timed_mode = mode;
+    d->last_call_batch = mode == 0 ? B : 0; d->last_call_pose = cam != nullptr;
     cudaStream_t s0 = d->stream;
     if (W != d->lastW || H != d->lastH || B > d->lastB) {       // padding words / rows of the masks must be zero
         CU(cudaMemsetAsync(d->d_masks, 0, d->masks_words * sizeof(uint32_t), s0));
@@ -921,6 +923,14 @@ static int fill_out(b2a_detector *d, int B, bool pose, b2a_detections *out)
     out->status = d->h_status;
     for (int b = 0; b < B; ++b) if (d->h_status[b] != 0) return set_err(B2A_ERR_CAPACITY, "an internal list overflowed (see b2a_detections.status)");
     return B2A_OK;
+}
+
+extern "C" int b2a_detector_last_detections(b2a_detector *d, b2a_detections *out)
+{
+    if (!d || !out) return set_err(B2A_ERR_INVALID, "null argument");
+    if (d->in_flight) return set_err(B2A_ERR_INVALID, "a submitted batch is still in flight on this handle");
+    if (d->lastB <= 0 || d->last_call_batch <= 0) return set_err(B2A_ERR_INVALID, "no completed call on this handle yet");
+    return fill_out(d, d->last_call_batch, d->last_call_pose, out);
 }
 
 extern "C" int b2a_detect(b2a_detector *d, const b2a_frames *frames, b2a_detections *out)

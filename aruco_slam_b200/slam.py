@@ -65,6 +65,19 @@ class ArucoSlam:
             raise _lib.B2AError(1, "setCameraParameters first")
         fr, keep = ArucoDetector._frames_host(image)
         _lib.check(_lib.lib().b2a_slam_add_image(self._h, self.detector._h, C.byref(fr), C.byref(self._cam)))
+        self._last_image = keep[0]
+
+    def getMarkedImg(self):
+        """the last frame with cv::aruco::drawDetectedMarkers applied (aruco_slam.cpp:318-319, aruco_slam.h:152); drawn on demand from
+        the detections the last addImage left in the detector's host arrays"""
+        img = getattr(self, "_last_image", None)
+        if img is None:
+            return None
+        try:
+            r = self.detector.last_detections()
+        except _lib.B2AError:
+            return None                                        # addImage before the first encoder message does not look at the frame (:84-85)
+        return self.detector.drawDetectedMarkers(img.copy(), r.corners[0], r.ids[0]) if len(r.ids[0]) else img.copy()
 
     def addImageFrames(self, frames):
         """addImage on a one-frame b2a_frames descriptor (host or device memory, see ArucoDetector.frames_device)"""

@@ -126,6 +126,10 @@ typedef struct {
 /* detectMarkers + estimatePoseSingleMarkers without leaving the device (aruco_slam.cpp:313-314). */
 int b2a_detect_pose(b2a_detector *d, const b2a_frames *frames, const b2a_camera *cam, b2a_detections *out);
 
+/* The result arrays of the handle's last completed b2a_detect / b2a_detect_pose / b2a_slam_add_image call again (still valid: no call
+ * since); used to draw the overlay of the frame addImage just processed (getMarkedImg, aruco_slam.h:152). */
+int b2a_detector_last_detections(b2a_detector *d, b2a_detections *out);
+
 /* The same call split in two, so that one host thread keeps two batches in flight on ONE handle: submit enqueues the H2D
  * copies and every kernel of a batch and returns at once (cam = NULL: detect only); wait blocks until that batch's results
  * are in host memory and fills `out`.  Tickets alternate between two internal pipeline contexts (the second is created on

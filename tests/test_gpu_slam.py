@@ -224,6 +224,10 @@ def test_add_image_vs_reference_run_scene():
         mu, sg, lm = s.get_state()
         assert np.array_equal(lm, g["ids_%d" % f]), f
         assert np.abs(mu - g["mu_%d" % f]).max() < 1e-4 and np.abs(sg - g["sigma_%d" % f]).max() < 1e-4, f
+        if f in (0, 7):                              # getMarkedImg (aruco_slam.h:152): the frame with the detections drawn on it
+            marked = s.getMarkedImg()
+            want = s.detector.drawDetectedMarkers(frames[f].copy(), g["det_corners_%d" % f], g["det_ids_%d" % f])
+            assert np.array_equal(marked, want) and not np.array_equal(marked, frames[f])
     s.close()
 
 
