@@ -13,10 +13,12 @@
  * published algorithm in plain C and are PINNED against
  * outputs of the `cv2 4.13.0` wheel: tests/golden/ (written by
  * tools/make_golden.py) -- every stage (gray, masks, contours, polygons,
- * candidates, ids/corners/rejected, poses).  The EKF part follows the reference
- * file line by line; the reference has no tests or golden vectors for it
- * (SURVEY section 4), so that part is "parity unpinned" beyond self-consistency
- * with an independent NumPy restatement (tests/test_oracle_ekf.py).
+ * candidates, ids/corners/rejected, poses).  The observation / EKF part follows the
+ * reference file line by line and is PINNED against runs of the reference ITSELF:
+ * oracle/_ref is /root/reference/src/aruco_slam.cpp + src/map_loader.cpp compiled
+ * unmodified against stand-in headers (oracle/ref_stubs, oracle/Makefile target
+ * `ref`); tools/make_golden_slam.py drives it with cv2 behind its OpenCV calls and
+ * writes tests/golden/slam_*.npz and map_txt.npz (tests/test_slam_golden.py).
  */
 #ifndef B2A_ORACLE_H
 #define B2A_ORACLE_H

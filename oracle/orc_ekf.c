@@ -1,14 +1,16 @@
 /* orc_ekf.c -- CPU restatement of the reference's EKF: ArucoSlam::addEncoder
  * (src/aruco_slam.cpp:21-74) and the correction / augmentation loop of
  * ArucoSlam::addImage (src/aruco_slam.cpp:88-263), dense row-major doubles in
- * place of Eigen.  TEST INFRASTRUCTURE ONLY (see oracle.h).  The reference has
- * no tests for this part: PARITY UNPINNED except against an independent NumPy
- * restatement (tests/test_oracle_ekf.py).  dt is an argument instead of
+ * place of Eigen.  TEST INFRASTRUCTURE ONLY (see oracle.h).  PINNED against runs
+ * of the reference itself (oracle/_ref = the unmodified aruco_slam.cpp; vectors in
+ * tests/golden/slam_*.npz, tests/test_slam_golden.py: mu, Sigma <= 1e-9 per frame,
+ * landmark order = the reference's priority-queue order).  dt is an argument instead of
  * ros::Time::now() (:26,31-32); the log prints (:79,:89,:96,:161-171,:283-286)
  * are omitted.  Quirks kept: frame-start snapshot `mu`
  * (:88), float sin/cos in augmentation (:210-211), (I-KG)Sigma form (:204),
  * single-wrap normAngle (:412-421), kl used for both wheels in wkh (:62), the
- * "stationary" branch (:193-198) is a no-op on the state.
+ * "stationary" branch (:193-198) skips the update (its mu_.topLeftCorner(3, 0) is a
+ * 3 x 0 block) and leaves that marker's last_observation_ unset.
  */
 #include "oracle.h"
 #include <math.h>
