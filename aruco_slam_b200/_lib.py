@@ -93,7 +93,7 @@ SYMBOLS = [
     "b2a_slam_set_state", "b2a_slam_add_encoder", "b2a_slam_make_observations", "b2a_slam_update", "b2a_slam_add_image", "b2a_slam_synchronize",
     "b2a_quaternion_from_rpy", "b2a_map_parse", "b2a_map_load", "b2a_slam_robot_pose", "b2a_slam_detected_map",
     "b2a_pack_robot_pose", "b2a_pack_map_marker", "b2a_slam_stream",
-    "b2a_multi_create", "b2a_multi_destroy", "b2a_multi_num_devices", "b2a_multi_detect_pose", "b2a_draw_detected_markers", "b2a_detector_last_detections",
+    "b2a_multi_create", "b2a_multi_destroy", "b2a_multi_num_devices", "b2a_multi_detect_pose", "b2a_draw_detected_markers", "b2a_detector_last_detections", "b2a_pack_detections",
 ]
 
 _lib = None
@@ -133,6 +133,7 @@ def lib():
         L.b2a_multi_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2a_multi_destroy.argtypes = [C.c_void_p]
         L.b2a_detector_last_detections.argtypes = [C.c_void_p, C.c_void_p]
+        L.b2a_pack_detections.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.b2a_draw_detected_markers.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.b2a_multi_detect_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2a_slam_stream.argtypes = [C.c_void_p]

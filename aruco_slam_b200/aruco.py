@@ -281,6 +281,33 @@ class ArucoDetector:
         return int(_lib.lib().b2a_detector_stream(self._h) or 0)
 
 
+def pack_detections(det, out: np.ndarray) -> int:
+    """b2a_pack_detections: the compact records of a C result struct into the uint8 array `out`; returns the bytes written"""
+    n = C.c_size_t(0)
+    _lib.check(_lib.lib().b2a_pack_detections(C.byref(det), out.ctypes.data, out.nbytes, C.byref(n)))
+    return int(n.value)
+
+
+def unpack_detections(buf) -> BatchDetections:
+    """the inverse of pack_detections (host side of a gather)"""
+    b = np.frombuffer(memoryview(buf), np.uint8)
+    magic, B, pose, K = np.frombuffer(b[:16].tobytes(), np.int32)
+    if magic != 0x42324144:
+        raise B2AError(1, "not a packed detection record")
+    o = 16
+    out = BatchDetections([], [], [], [] if pose else None, [] if pose else None)
+    for _ in range(B):
+        na, nr = np.frombuffer(b[o:o + 8].tobytes(), np.int32)
+        o += 8
+        out.ids.append(np.frombuffer(b[o:o + 4 * na].tobytes(), np.int32)); o += 4 * na
+        out.corners.append(np.frombuffer(b[o:o + 32 * na].tobytes(), np.float32).reshape(na, 4, 2)); o += 32 * na
+        if pose:
+            out.rvecs.append(np.frombuffer(b[o:o + 24 * na].tobytes(), np.float64).reshape(na, 3)); o += 24 * na
+            out.tvecs.append(np.frombuffer(b[o:o + 24 * na].tobytes(), np.float64).reshape(na, 3)); o += 24 * na
+        out.rejected.append(np.frombuffer(b[o:o + 32 * nr].tobytes(), np.float32).reshape(nr, 4, 2)); o += 32 * nr
+    return out
+
+
 class MultiDetector:
     """Several GPUs of one box from one process: a batch of host frames is cut into contiguous blocks, one per device, each through
     its own handle and host thread (inside the library); the detections come back gathered in frame order.  Frames are independent,

@@ -925,6 +925,34 @@ static int fill_out(b2a_detector *d, int B, bool pose, b2a_detections *out)
     return B2A_OK;
 }
 
+// compact records of a call's detections: what travels when results are gathered from several GPUs / processes
+extern "C" int b2a_pack_detections(const b2a_detections *det, void *out, size_t cap, size_t *n_bytes)
+{
+    if (!det || !n_bytes || (cap > 0 && !out)) return set_err(B2A_ERR_INVALID, "null argument");
+    const int B = det->batch, K = det->max_markers;
+    const bool pose = det->rvecs && det->tvecs;
+    size_t need = 16;
+    for (int b = 0; b < B; ++b) need += 8 + (size_t)det->n_accepted[b] * (4 + 32 + (pose ? 48 : 0)) + (size_t)det->n_rejected[b] * 32;
+    *n_bytes = need;
+    if (need > cap) return set_err(B2A_ERR_CAPACITY, "packed detections do not fit the buffer");
+    uint8_t *p = (uint8_t *)out;
+    const int32_t hdr[4] = {0x42324144 /* "DA2B" */, B, pose ? 1 : 0, K};
+    std::memcpy(p, hdr, 16); p += 16;
+    for (int b = 0; b < B; ++b) {
+        const int na = det->n_accepted[b], nr = det->n_rejected[b];
+        const int32_t cnt[2] = {na, nr};
+        std::memcpy(p, cnt, 8); p += 8;
+        std::memcpy(p, det->ids + (size_t)b * K, (size_t)na * 4); p += (size_t)na * 4;
+        std::memcpy(p, det->corners + (size_t)b * K * 8, (size_t)na * 32); p += (size_t)na * 32;
+        if (pose) {
+            std::memcpy(p, det->rvecs + (size_t)b * K * 3, (size_t)na * 24); p += (size_t)na * 24;
+            std::memcpy(p, det->tvecs + (size_t)b * K * 3, (size_t)na * 24); p += (size_t)na * 24;
+        }
+        std::memcpy(p, det->rejected + (size_t)b * K * 8, (size_t)nr * 32); p += (size_t)nr * 32;
+    }
+    return B2A_OK;
+}
+
 extern "C" int b2a_detector_last_detections(b2a_detector *d, b2a_detections *out)
 {
     if (!d || !out) return set_err(B2A_ERR_INVALID, "null argument");

@@ -582,10 +582,10 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), {k: v / steps for k, v in stage_acc.items()}, launches
 
-    KM = 64                                                    # markers per frame that travel in the gather (C2 frames carry <= 30; more are counted only)
     stream_rec = None
     if world > 1:
-        stream_rec = torch.zeros((max(args.steps, args.warmup, 1), B, 1 + KM * (1 + 8 + 6)), dtype=torch.float64).pin_memory()
+        # one fixed-size slot per step for the compact detection records of the batch (b2a_pack_detections; a C2 batch packs to ~115 KB)
+        stream_rec = torch.zeros((max(args.steps, args.warmup, 1), 16 + B * (8 + 128 * 116)), dtype=torch.uint8).pin_memory()
         warm = stream_rec[:args.steps].cuda()
         dist.gather(warm, [torch.empty_like(warm) for _ in range(world)] if rank == 0 else None, dst=0)      # buffers and channels of this message size
         torch.cuda.synchronize()
@@ -605,24 +605,14 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(lib_stream)                                  # the stream is idle: this is the start of the region
         got, pending = 0, None
-        rec = stream_rec[:steps] if world > 1 else None
+        rec = stream_rec[:steps] if (world > 1 and not os.environ.get("B2A_BENCH_NO_GATHER")) else None      # (the switch is for diagnosis only)
+        rec_np = rec.numpy() if rec is not None else None
 
         def take(step, det_c):
-            """read the step's result on the host; with several ranks also file its compact record for the gather"""
+            """read the step's result on the host; with several ranks also file its compact record (b2a_pack_detections) for the gather"""
             na = np.ctypeslib.as_array(det_c.n_accepted, (B,))
             if rec is not None:
-                K_ = det_c.max_markers
-                r = rec[step].numpy()
-                r[:, 0] = na
-                ids = np.ctypeslib.as_array(det_c.ids, (B, K_))[:, :KM]
-                cor = np.ctypeslib.as_array(det_c.corners, (B, K_, 8))[:, :KM]
-                rv = np.ctypeslib.as_array(det_c.rvecs, (B, K_, 3))[:, :KM]
-                tv = np.ctypeslib.as_array(det_c.tvecs, (B, K_, 3))[:, :KM]
-                m = min(KM, K_)
-                r[:, 1:1 + m] = ids
-                r[:, 1 + KM:1 + KM + 8 * m] = cor.reshape(B, -1)
-                r[:, 1 + 9 * KM:1 + 9 * KM + 3 * m] = rv.reshape(B, -1)
-                r[:, 1 + 12 * KM:1 + 12 * KM + 3 * m] = tv.reshape(B, -1)
+                aruco.pack_detections(det_c, rec_np[step])
             return int(na.sum())
 
         for k in range(steps):
@@ -632,21 +622,21 @@ def main():
             pending = t
         got += take(steps - 1, det.wait_raw(pending))
         gathered = None
-        if world > 1:
+        if rec is not None:
             # only the detections travel: every rank's records to rank 0 (frame order = rank order), inside the region
             dev_rec = rec.cuda(non_blocking=True)
             parts = [torch.empty_like(dev_rec) for _ in range(world)] if rank == 0 else None
             dist.gather(dev_rec, parts, dst=0)
             if rank == 0:
-                gathered = torch.stack(parts).cpu()
+                gathered = torch.stack(parts).cpu().numpy()
         e1.record(lib_stream)                                  # after the last wait returned: everything is complete
         e1.synchronize()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if gathered is not None:
-            got = int(gathered[..., 0].sum().item())            # markers of ALL ranks, counted from the gathered records
+        if gathered is not None:                                # after the region: the markers of ALL ranks, counted from the gathered records
+            got = sum(len(x) for r_ in range(world) for k in range(steps) for x in aruco.unpack_detections(gathered[r_, k]).ids)
         return float(t.item()), got
 
     sampler = ClockSampler(local_rank)

@@ -126,6 +126,12 @@ typedef struct {
 /* detectMarkers + estimatePoseSingleMarkers without leaving the device (aruco_slam.cpp:313-314). */
 int b2a_detect_pose(b2a_detector *d, const b2a_frames *frames, const b2a_camera *cam, b2a_detections *out);
 
+/* Compact records of a call's detections (what travels when several GPUs / processes gather their results on one host):
+ * header {magic, batch, has_pose, max_markers} (4 x i32), then per frame {n_accepted, n_rejected} (2 x i32), ids [na] i32,
+ * corners [na][8] f32, rvecs [na][3] f64 and tvecs [na][3] f64 (if has_pose), rejected [nr][8] f32.  *n_bytes = size written;
+ * B2A_ERR_CAPACITY (with *n_bytes = size needed) when cap is too small. */
+int b2a_pack_detections(const b2a_detections *det, void *out, size_t cap, size_t *n_bytes);
+
 /* The result arrays of the handle's last completed b2a_detect / b2a_detect_pose / b2a_slam_add_image call again (still valid: no call
  * since); used to draw the overlay of the frame addImage just processed (getMarkedImg, aruco_slam.h:152). */
 int b2a_detector_last_detections(b2a_detector *d, b2a_detections *out);

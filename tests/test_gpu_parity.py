@@ -470,3 +470,26 @@ def test_draw_detected_markers_vs_cv2(aruco, name):
     if ids is not None and sorted(ids.ravel().tolist()) == sorted(g["ids"].tolist()):
         assert np.array_equal(det.drawDetectedMarkers(img.copy(), np.array(c), ids), want["ids"])
     det.close()
+
+
+def test_pack_detections_round_trip(aruco):
+    """b2a_pack_detections: the compact record of a call (what a multi-process gather moves) unpacks to the same detections"""
+    frames = synth.render_batch("C2", 3, base_seed=400)
+    dic = D.getPredefinedDictionary(D.DICT_6X6_250)
+    det = _detector(aruco, dic, frames.shape[1:], batch=3)
+    K = np.array([[1400.0, 0, 960], [0, 1400.0, 540], [0, 0, 1]])
+    cam = aruco._camera(K, np.zeros(5), 0.27)
+    fr, keep = det._frames_host(frames)
+    raw = det.detect_raw(fr, cam)
+    want = det._collect(raw, True)
+    buf = np.zeros(1 << 16, np.uint8)
+    n = aruco.pack_detections(raw, buf)
+    got = aruco.unpack_detections(buf[:n])
+    assert 0 < n < 20000
+    for b in range(3):
+        assert np.array_equal(got.ids[b], want.ids[b]) and np.array_equal(got.corners[b], want.corners[b]) and np.array_equal(got.rejected[b], want.rejected[b])
+        assert np.array_equal(got.rvecs[b], want.rvecs[b]) and np.array_equal(got.tvecs[b], want.tvecs[b])
+    from aruco_slam_b200._lib import B2AError
+    with pytest.raises(B2AError):
+        aruco.pack_detections(raw, np.zeros(64, np.uint8))
+    det.close()
