@@ -288,8 +288,8 @@ def pack_detections(det, out: np.ndarray) -> int:
     return int(n.value)
 
 
-def unpack_detections(buf) -> BatchDetections:
-    """the inverse of pack_detections (host side of a gather)"""
+def unpack_detections(buf, with_size: bool = False):
+    """the inverse of pack_detections (host side of a gather); with_size: also the number of bytes the record occupies"""
     b = np.frombuffer(memoryview(buf), np.uint8)
     magic, B, pose, K = np.frombuffer(b[:16].tobytes(), np.int32)
     if magic != 0x42324144:
@@ -305,7 +305,7 @@ def unpack_detections(buf) -> BatchDetections:
             out.rvecs.append(np.frombuffer(b[o:o + 24 * na].tobytes(), np.float64).reshape(na, 3)); o += 24 * na
             out.tvecs.append(np.frombuffer(b[o:o + 24 * na].tobytes(), np.float64).reshape(na, 3)); o += 24 * na
         out.rejected.append(np.frombuffer(b[o:o + 32 * nr].tobytes(), np.float32).reshape(nr, 4, 2)); o += 32 * nr
-    return out
+    return (out, o) if with_size else out
 
 
 class MultiDetector:

@@ -582,11 +582,14 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), {k: v / steps for k, v in stage_acc.items()}, launches
 
-    stream_rec = None
+    stream_rec = gather_host = None
     if world > 1:
-        # one fixed-size slot per step for the compact detection records of the batch (b2a_pack_detections; a C2 batch packs to ~115 KB)
-        stream_rec = torch.zeros((max(args.steps, args.warmup, 1), 16 + B * (8 + 128 * 116)), dtype=torch.uint8).pin_memory()
-        warm = stream_rec[:args.steps].cuda()
+        # the compact detection records of a run's steps, packed back to back (b2a_pack_detections; a C2 batch packs to ~115 KB), and
+        # rank 0's pinned landing area for every rank's records
+        slot = 16 + B * (8 + 64 * 116)
+        stream_rec = torch.zeros(max(args.steps, args.warmup, 1) * slot, dtype=torch.uint8).pin_memory()
+        gather_host = torch.zeros((world, stream_rec.numel()), dtype=torch.uint8).pin_memory() if rank == 0 else None
+        warm = stream_rec.cuda()
         dist.gather(warm, [torch.empty_like(warm) for _ in range(world)] if rank == 0 else None, dst=0)      # buffers and channels of this message size
         torch.cuda.synchronize()
 
@@ -605,14 +608,15 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(lib_stream)                                  # the stream is idle: this is the start of the region
         got, pending = 0, None
-        rec = stream_rec[:steps] if (world > 1 and not os.environ.get("B2A_BENCH_NO_GATHER")) else None      # (the switch is for diagnosis only)
+        rec = stream_rec if (world > 1 and not os.environ.get("B2A_BENCH_NO_GATHER")) else None      # (the switch is for diagnosis only)
         rec_np = rec.numpy() if rec is not None else None
+        rec_off = [0]
 
         def take(step, det_c):
             """read the step's result on the host; with several ranks also file its compact record (b2a_pack_detections) for the gather"""
             na = np.ctypeslib.as_array(det_c.n_accepted, (B,))
             if rec is not None:
-                aruco.pack_detections(det_c, rec_np[step])
+                rec_off.append(rec_off[-1] + aruco.pack_detections(det_c, rec_np[rec_off[-1]:]))
             return int(na.sum())
 
         for k in range(steps):
@@ -623,12 +627,19 @@ def main():
         got += take(steps - 1, det.wait_raw(pending))
         gathered = None
         if rec is not None:
-            # only the detections travel: every rank's records to rank 0 (frame order = rank order), inside the region
-            dev_rec = rec.cuda(non_blocking=True)
+            # only the detections travel: every rank's records to rank 0 (frame order = rank order), inside the region.
+            # Message size = the largest rank's record bytes (one tiny all-reduce), landing in pinned memory on rank 0.
+            used = torch.tensor([rec_off[-1]], dtype=torch.int64, device="cuda")
+            dist.all_reduce(used, op=dist.ReduceOp.MAX)
+            nbytes = (int(used.item()) + 15) & ~15
+            dev_rec = rec[:nbytes].cuda(non_blocking=True)
             parts = [torch.empty_like(dev_rec) for _ in range(world)] if rank == 0 else None
             dist.gather(dev_rec, parts, dst=0)
             if rank == 0:
-                gathered = torch.stack(parts).cpu().numpy()
+                for r_ in range(world):
+                    gather_host[r_, :nbytes].copy_(parts[r_], non_blocking=True)
+                torch.cuda.synchronize()
+                gathered = gather_host.numpy()
         e1.record(lib_stream)                                  # after the last wait returned: everything is complete
         e1.synchronize()
         torch.cuda.synchronize()
@@ -636,7 +647,13 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if gathered is not None:                                # after the region: the markers of ALL ranks, counted from the gathered records
-            got = sum(len(x) for r_ in range(world) for k in range(steps) for x in aruco.unpack_detections(gathered[r_, k]).ids)
+            got = 0
+            for r_ in range(world):
+                o = 0
+                for k in range(steps):
+                    d_, n_ = aruco.unpack_detections(gathered[r_, o:], with_size=True)
+                    got += sum(len(x) for x in d_.ids)
+                    o += n_
         return float(t.item()), got
 
     sampler = ClockSampler(local_rank)
