@@ -17,9 +17,24 @@ _SO = os.path.join(_HERE, "liboracle.so")
 
 
 def build(force: bool = False) -> str:
+    """make liboracle.so when it is missing or older than its sources.  Several processes may call this at once (every rank of a
+    torchrun bench checks its frames): the build runs under a file lock, into a temporary name, and is renamed into place."""
     srcs = [os.path.join(_HERE, f) for f in ("orc_detect.c", "orc_pose.c", "orc_ekf.c", "oracle.h")]
-    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "liboracle.so"])
+
+    def stale():
+        return force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+
+    if stale():
+        import fcntl
+        with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if stale():
+                    tmp = _SO + ".tmp.%d" % os.getpid()
+                    subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "liboracle.so", "OUT=" + tmp])
+                    os.replace(tmp, _SO)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return _SO
 
 
