@@ -314,6 +314,25 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
+def bind_near_gpu(index):
+    """pin this rank's threads (and with them the first-touch placement of its pinned frame buffers) to the CPUs the driver reports as
+    local to its GPU: with several ranks the H2D copies otherwise share one socket's memory and its PCIe root"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1]
+        cpus = [c for c in cpus if c < os.cpu_count()]
+        if cpus and len(cpus) < os.cpu_count():
+            os.sched_setaffinity(0, cpus)
+            return "%d of %d cpus" % (len(cpus), os.cpu_count())
+        return "all cpus local"
+    except Exception as e:                                     # no NVML / no topology information: leave the scheduler alone
+        return "not bound (%s)" % type(e).__name__
+
+
 def nccl_init(dist, torch, local_rank):
     """NCCL's own lines (the box exports NCCL_DEBUG; the version banner goes to stdout whatever NCCL_DEBUG_FILE says) must not share
     stdout with the one JSON line: while the communicator comes up, file descriptor 1 points at stderr, so the lines stay visible
@@ -521,6 +540,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa = bind_near_gpu(local_rank) if world > 1 else "single rank"
     if world > 1:
         nccl_init(dist, torch, local_rank)
 
@@ -743,6 +763,7 @@ def main():
             "stages_ms_per_step_one_stream": {k: round(v, 4) for k, v in stages_1s.items()},
             "stages_ms_per_step": {k: round(v, 4) for k, v in stages.items()},
             "stages_ms_per_step_e2e": {k: round(v, 4) for k, v in stages_e2e.items()},
+            "cpu_binding": numa,
             "parity": parity, "parity_checked": {"frames": n_checked, "mismatching_frames": n_bad, "ranks": world,
                                                   "how": "every frame of every rank vs oracle/ (ids, corners, rejected bit-exact; rvec, tvec 1e-4), all-reduced"},
             "markers_per_step": n_markers_all,
