@@ -731,7 +731,7 @@ def main():
         d2h = int(B * 12 + na.sum() * (4 + 32 + 24 + 24) + nr.sum() * 32)
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_threshold_march"]["dram_bytes_per_launch"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["k_threshold_march"]["dram_bytes_per_launch"]
         except Exception:
             pass
         out = {
@@ -751,13 +751,13 @@ def main():
                                 "between steps), L2 flushed between steps"},
             "e2e_pipelined": e2e_pipelined,
             "gpu_launches": launches,
-            "roofline": {"kernel": "k_threshold_march<1,6,11>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "k_threshold_march<1,6,11>", "bound": "hbm", "limited_by": "instruction issue (24 thread-instructions per pixel at 57 % of the issue slots)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else which,
                          "algorithmic_bytes_per_launch": thr_bytes, "launch_ms": thr_ms,
                          "achieved_packed": achieved_packed, "frac_packed": achieved_packed / peak if peak else None, "packed_bytes_per_launch": thr_bytes_packed,
                          "note": "achieved = SURVEY.md 8(d)'s algorithmic bytes, B*(1+nScales)*P (gray read once, one byte per mask pixel as the reference writes), / launch_ms; "
                                  "the kernel writes the masks bit-packed, so the bytes it actually has to move are B*(P + nScales*P/8) = achieved_packed, and the stage is "
-                                 "bound by instruction issue (~22 instructions per pixel), not by HBM; "
+                                 "bound by instruction issue (24 instructions per pixel), not by HBM; "
                                  "launch_ms = average CUDA-event duration of the one-stream pass; traffic = dram bytes of one ncu --set full capture (profiles/)",
                          "pipeline_frac_7P": (value / world) * 7 * P / (peak * 1e9)},
             "stages_ms_per_step_one_stream": {k: round(v, 4) for k, v in stages_1s.items()},
