@@ -1182,19 +1182,20 @@ extern "C" int b2a_estimate_pose_single_markers(b2a_detector *d, const float *co
     if (!d || !cam || (n > 0 && (!corners || !rvecs || !tvecs))) return set_err(B2A_ERR_INVALID, "null argument");
     if (!(cam->marker_length > 0)) return set_err(B2A_ERR_INVALID, "markerLength <= 0");
     if (n <= 0) return B2A_OK;
+    if (d->in_flight) return set_err(B2A_ERR_INVALID, "a submitted batch is still in flight on this handle");
     CU(cudaSetDevice(d->device));
-    float *dc = nullptr; double *dr = nullptr, *dt = nullptr;
-    CU(cudaMalloc(&dc, (size_t)n * 8 * sizeof(float)));
-    CU(cudaMalloc(&dr, (size_t)n * 3 * sizeof(double)));
-    CU(cudaMalloc(&dt, (size_t)n * 3 * sizeof(double)));
+    // the handle's own output arrays serve as scratch (no allocation per call); more markers than they hold go in chunks
+    const int cap = d->cfg.max_batch * d->max_markers;
     cudaStream_t st = d->stream;
-    cudaMemcpyAsync(dc, corners, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice, st);
-    k_pose<<<(n * 32 + POSE_THREADS - 1) / POSE_THREADS, POSE_THREADS, 0, st>>>(dc, nullptr, 1, n, to_camera(cam), cam->marker_length, dr, dt, nullptr);
-    cudaMemcpyAsync(rvecs, dr, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(tvecs, dt, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
-    cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(dc); cudaFree(dr); cudaFree(dt);
-    if (e != cudaSuccess) return set_err(B2A_ERR_CUDA, cudaGetErrorString(e));
+    for (int o = 0; o < n; o += cap) {
+        const int m = std::min(cap, n - o);
+        CU(cudaMemcpyAsync(d->d_corners2, corners + (size_t)o * 8, (size_t)m * 8 * sizeof(float), cudaMemcpyHostToDevice, st));
+        k_pose<<<(m * 32 + POSE_THREADS - 1) / POSE_THREADS, POSE_THREADS, 0, st>>>(d->d_corners2, nullptr, 1, m, to_camera(cam), cam->marker_length, d->d_rvecs, d->d_tvecs, nullptr);
+        CU(cudaMemcpyAsync(rvecs + (size_t)o * 3, d->d_rvecs, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(tvecs + (size_t)o * 3, d->d_tvecs, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    d->last_call_batch = 0;                                   // the result arrays no longer hold a detect call's poses
     return launch_err("k_pose");
 }
 

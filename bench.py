@@ -218,7 +218,7 @@ def bench_c4(args, rank, local_rank, world):
         det_stream = torch.cuda.ExternalStream(s.detector.stream, device=local_rank)
         ekf_stream = torch.cuda.ExternalStream(s.stream, device=local_rank)
         descs = [aruco.ArucoDetector._frames_host(h_np[f]) if host else (aruco.ArucoDetector.frames_device(d_frames[f].data_ptr(), 1, H, W), None) for f in range(n)]
-        thr, launches, poses = 0.0, 0, []
+        thr, launches, poses, stage_acc = 0.0, 0, [], {}
         for f in range(args.warmup):
             s.addEncoder(*enc[f])
             s.addImageFrames(descs[f][0])
@@ -233,7 +233,9 @@ def bench_c4(args, rank, local_rank, world):
             s.addImageFrames(descs[f][0])
             if host:
                 poses.append(formats.robot_pose(s).position[:2].copy())       # the step's result read on the host (toRosPose), waits for the EKF
-            thr += s.detector.last_stage_times().get("threshold", 0.0)
+            for k_, v_ in s.detector.last_stage_times().items():
+                stage_acc[k_] = stage_acc.get(k_, 0.0) + v_
+            thr = stage_acc.get("threshold", 0.0)
             launches += s.detector.last_launch_count()
         e1.record(ekf_stream)
         e1.synchronize()
@@ -243,13 +245,13 @@ def bench_c4(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         mu, sg, ids = s.get_state()
         s.close()
-        return float(t.item()), mu, sg, ids, thr / args.steps, launches
+        return float(t.item()), mu, sg, ids, thr / args.steps, launches, {k_: round(v_ / args.steps, 4) for k_, v_ in stage_acc.items()}
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, mu, sg, ids, thr_ms, launches = run(False)
-    ms_e2e, mu2, sg2, ids2, _, _ = run(True)
+    ms_dev, mu, sg, ids, thr_ms, launches, stages = run(False)
+    ms_e2e, mu2, sg2, ids2, _, _, _ = run(True)
     clocks = sampler.result() if rank == 0 else None
     # parity: the CPU chain (oracle detector + pose + observations + EKF) over this rank's stream
     from oracle import oracle as O
@@ -279,7 +281,7 @@ def bench_c4(args, rank, local_rank, world):
                           "parallelism": "one stream and one filter per GPU, no collective"},
                "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": P, "d2h_bytes_per_step": 12 * 8 + 12 + 12 * 84,
                        "how": "per step: b2a_slam_add_encoder, b2a_slam_add_image on a pinned host frame (H2D inside), b2a_slam_robot_pose read back (waits for the step's EKF kernels)"},
-               "gpu_launches": launches,
+               "gpu_launches": launches, "stages_ms_per_frame": stages,
                "roofline": {"kernel": "k_threshold_march<1,6,11> (one 1080p frame per launch)", "bound": "hbm", "achieved": 4 * P / (thr_ms * 1e-3) / 1e9 if thr_ms > 0 else 0.0, "peak": peak,
                             "unit": "GB/s", "frac": (4 * P / (thr_ms * 1e-3) / 1e9 / peak) if thr_ms > 0 else None, "traffic": None, "peak_source": which, "algorithmic_bytes_per_launch": 4 * P,
                             "launch_ms": thr_ms, "note": "a single frame per call: the loop is a chain of small launches (latency), not a streaming workload; the figure is the threshold "
