@@ -90,7 +90,7 @@ SYMBOLS = [
     "b2a_estimate_pose_single_markers", "b2a_debug_threshold", "b2a_debug_contours", "b2a_debug_candidates",
     "b2a_detector_num_scales", "b2a_detector_set_streams", "b2a_last_stage_times", "b2a_last_launch_count", "b2a_detector_stream",
     "b2a_default_slam_params", "b2a_slam_create", "b2a_slam_destroy", "b2a_slam_dim", "b2a_slam_get_state",
-    "b2a_slam_set_state", "b2a_slam_add_encoder", "b2a_slam_make_observations", "b2a_slam_update", "b2a_slam_add_image", "b2a_slam_synchronize",
+    "b2a_slam_set_state", "b2a_slam_add_encoder", "b2a_slam_make_observations", "b2a_slam_update", "b2a_slam_add_image", "b2a_slam_add_image_submit", "b2a_slam_add_image_wait", "b2a_slam_synchronize",
     "b2a_quaternion_from_rpy", "b2a_map_parse", "b2a_map_load", "b2a_slam_robot_pose", "b2a_slam_detected_map",
     "b2a_pack_robot_pose", "b2a_pack_map_marker", "b2a_slam_stream",
     "b2a_multi_create", "b2a_multi_destroy", "b2a_multi_num_devices", "b2a_multi_detect_pose", "b2a_draw_detected_markers", "b2a_detector_last_detections", "b2a_pack_detections",
@@ -136,6 +136,8 @@ def lib():
         L.b2a_pack_detections.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.b2a_draw_detected_markers.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.b2a_multi_detect_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2a_slam_add_image_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2a_slam_add_image_wait.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.b2a_slam_stream.argtypes = [C.c_void_p]
         L.b2a_slam_stream.restype = C.c_void_p
         L.b2a_detect_pose_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -976,7 +976,9 @@ extern "C" int b2a_detect_pose(b2a_detector *d, const b2a_frames *frames, const 
     return fill_out(d, frames->batch, true, out);
 }
 
-extern "C" int b2a_detect_pose_submit(b2a_detector *d, const b2a_frames *frames, const b2a_camera *cam, int *ticket)
+// post(context, stream): work appended behind the batch on the context that runs it
+static int submit_impl(b2a_detector *d, const b2a_frames *frames, const b2a_camera *cam, int *ticket,
+                       const std::function<int(b2a_detector *, cudaStream_t)> *post)
 {
     if (!d || !frames || !ticket) return set_err(B2A_ERR_INVALID, "null argument");
     if (cam && !(cam->marker_length > 0)) return set_err(B2A_ERR_INVALID, "markerLength <= 0");
@@ -990,12 +992,19 @@ extern "C" int b2a_detect_pose_submit(b2a_detector *d, const b2a_frames *frames,
     }
     if (t->in_flight) return set_err(B2A_ERR_INVALID, "two batches are already in flight on this handle (b2a_detect_pose_wait first)");
     t->pipelined = true;
-    const int rc_enq = enqueue_pipeline(t, frames, cam, 0, 0, nullptr);
+    std::function<int(cudaStream_t)> bound;
+    if (post) bound = [&](cudaStream_t st) { return (*post)(t, st); };
+    const int rc_enq = enqueue_pipeline(t, frames, cam, 0, 0, nullptr, post ? &bound : nullptr);
     t->pipelined = false;
     TRY(rc_enq);
     t->in_flight = true; t->pending_pose = cam != nullptr; t->pending_batch = frames->batch;
     *ticket = (int)d->next_ticket++;
     return B2A_OK;
+}
+
+extern "C" int b2a_detect_pose_submit(b2a_detector *d, const b2a_frames *frames, const b2a_camera *cam, int *ticket)
+{
+    return submit_impl(d, frames, cam, ticket, nullptr);
 }
 
 extern "C" int b2a_detect_pose_wait(b2a_detector *d, int ticket, b2a_detections *out)
@@ -1289,7 +1298,8 @@ struct b2a_slam {
     // per-frame scratch, allocated once (grown only when a frame brings more markers than ever before)
     int obs_cap = 0;
     float *d_c = nullptr; int32_t *d_i = nullptr; double *d_r = nullptr, *d_t = nullptr;      // detections of the host-array entry point
-    Observation *h_obs = nullptr; int *h_keep = nullptr, *h_n = nullptr;                      // pinned, written by k_observations
+    Observation *h_obs = nullptr; int *h_keep = nullptr, *h_n = nullptr;                      // pinned, written by k_observations; two sets
+                                                                                              // (h_obs + set * obs_cap ...): one per frame in flight
     EkfObs *d_ekf = nullptr, *h_ekf[2] = {nullptr, nullptr}; cudaEvent_t ev_ekf[2] = {nullptr, nullptr}; int ekf_buf = 0;   // corrections of a frame
     std::vector<int32_t> ids;                       // landmark k -> aruco id
     std::unordered_map<int32_t, int> id_index;      // aruco_id_map (aruco_slam.h:164): id -> landmark index, first insertion wins (:256)
@@ -1322,7 +1332,7 @@ static int slam_reserve(b2a_slam *s, int n)
     slam_free_scratch(s);
     const size_t c = (size_t)std::max(256, 2 * n);
     if (cudaMalloc(&s->d_c, c * 32) || cudaMalloc(&s->d_i, c * 4) || cudaMalloc(&s->d_r, c * 24) || cudaMalloc(&s->d_t, c * 24) ||
-        cudaMalloc(&s->d_ekf, c * sizeof(EkfObs)) || cudaMallocHost(&s->h_obs, c * sizeof(Observation)) || cudaMallocHost(&s->h_keep, c * 4) ||
+        cudaMalloc(&s->d_ekf, c * sizeof(EkfObs)) || cudaMallocHost(&s->h_obs, 2 * c * sizeof(Observation)) || cudaMallocHost(&s->h_keep, 2 * c * 4) ||
         cudaMallocHost(&s->h_ekf[0], c * sizeof(EkfObs)) || cudaMallocHost(&s->h_ekf[1], c * sizeof(EkfObs))) {
         slam_free_scratch(s);
         (void)cudaGetLastError();
@@ -1391,7 +1401,7 @@ extern "C" int b2a_slam_create(int device, const b2a_slam_params *p, b2a_slam **
     cudaMemsetAsync(s->d_mu, 0, LD * 8, s->stream);
     cudaMemsetAsync(s->d_sigma, 0, LD * LD * 8, s->stream);
     if (cudaStreamSynchronize(s->stream) != cudaSuccess) return fail("memset");
-    if (cudaMallocHost(&s->h_n, sizeof(int)) || cudaEventCreateWithFlags(&s->ev_ekf[0], cudaEventDisableTiming) ||
+    if (cudaMallocHost(&s->h_n, 2 * sizeof(int)) || cudaEventCreateWithFlags(&s->ev_ekf[0], cudaEventDisableTiming) ||
         cudaEventCreateWithFlags(&s->ev_ekf[1], cudaEventDisableTiming) || slam_reserve(s, 256) != B2A_OK)
         return fail("frame scratch");
     *out = s;
@@ -1593,13 +1603,15 @@ static ObsParams obs_params(const b2a_slam *s, const b2a_camera *cam)
 }
 
 // the observations k_observations left in the pinned arrays, gated ones dropped, detection order (:325-374)
-static int collect_observations(const b2a_slam *s, int n, b2a_observation *out)
+static int collect_observations(const b2a_slam *s, int n, b2a_observation *out, int set = 0)
 {
     int k = 0;
+    const Observation *ho = s->h_obs + (size_t)set * s->obs_cap;
+    const int *hk = s->h_keep + (size_t)set * s->obs_cap;
     for (int i = 0; i < n; ++i) {
-        if (!s->h_keep[i]) continue;
+        if (!hk[i]) continue;
         b2a_observation &o = out[k++];
-        const Observation &h = s->h_obs[i];
+        const Observation &h = ho[i];
         o.aruco_id = h.aruco_id; o.aruco_index = -1; o.x = h.x; o.y = h.y; o.theta = h.theta;
         std::memcpy(o.cov, h.cov, sizeof(o.cov));
     }
@@ -1731,26 +1743,65 @@ extern "C" int b2a_slam_update(b2a_slam *s, const b2a_observation *obs, int n)
     return launch_err("EKF kernels");
 }
 
-extern "C" int b2a_slam_add_image(b2a_slam *s, b2a_detector *d, const b2a_frames *frame, const b2a_camera *cam)
+static int add_image_checks(b2a_slam *s, b2a_detector *d, const b2a_frames *frame, const b2a_camera *cam)
 {
     if (!s || !d || !frame || !cam) return set_err(B2A_ERR_INVALID, "null argument");
     if (frame->batch != 1) return set_err(B2A_ERR_INVALID, "add_image takes one frame");
     if (!(cam->marker_length > 0)) return set_err(B2A_ERR_INVALID, "markerLength <= 0");
     if (s->device != d->device) return set_err(B2A_ERR_INVALID, "detector and filter live on different devices");
+    return B2A_OK;
+}
+
+// k_observations behind the detection of one frame: reads the context's device outputs, leaves the records in pinned set `set`
+static int enqueue_observations(b2a_slam *s, b2a_detector *ctx, const b2a_camera *cam, int set, cudaStream_t st)
+{
+    const float *corners = ctx->prm.cornerRefinementMethod == 1 ? ctx->d_corners2 : ctx->fo0.corners;
+    k_observations<<<(ctx->max_markers + 63) / 64, 64, 0, st>>>(corners, ctx->fo0.ids, ctx->d_rvecs, ctx->d_tvecs, 0, ctx->fo0.n_accepted, ctx->max_markers,
+                                                                to_camera(cam), obs_params(s, cam), s->h_obs + (size_t)set * s->obs_cap,
+                                                                s->h_keep + (size_t)set * s->obs_cap, s->h_n + set);
+    ctx->launches++;
+    return launch_err("k_observations");
+}
+
+extern "C" int b2a_slam_add_image(b2a_slam *s, b2a_detector *d, const b2a_frames *frame, const b2a_camera *cam)
+{
+    TRY(add_image_checks(s, d, frame, cam));
     if (!s->is_init) return B2A_OK;                                    // :84-85 (needs one encoder message first)
     TRY(slam_reserve(s, d->max_markers));
     // detect + pose + observation mapping in one enqueue: k_observations reads the detector's device outputs and leaves
     // the (few) observation records in pinned host memory; the call's one synchronisation covers it
-    const std::function<int(cudaStream_t)> post = [&](cudaStream_t st) -> int {
-        const float *corners = d->prm.cornerRefinementMethod == 1 ? d->d_corners2 : d->fo0.corners;
-        k_observations<<<(d->max_markers + 63) / 64, 64, 0, st>>>(corners, d->fo0.ids, d->d_rvecs, d->d_tvecs, 0, d->fo0.n_accepted, d->max_markers,
-                                                                  to_camera(cam), obs_params(s, cam), s->h_obs, s->h_keep, s->h_n);
-        d->launches++;
-        return launch_err("k_observations");
-    };
+    const std::function<int(cudaStream_t)> post = [&](cudaStream_t st) -> int { return enqueue_observations(s, d, cam, 0, st); };
     TRY(run_pipeline(d, frame, cam, 0, 0, nullptr, &post));
     if (d->h_status[0] != 0) return set_err(B2A_ERR_CAPACITY, "an internal list overflowed (see b2a_detections.status)");
-    std::vector<b2a_observation> obs((size_t)std::max(*s->h_n, 1));
-    const int k = collect_observations(s, *s->h_n, obs.data());
+    std::vector<b2a_observation> obs((size_t)std::max(s->h_n[0], 1));
+    const int k = collect_observations(s, s->h_n[0], obs.data(), 0);
+    return b2a_slam_update(s, obs.data(), k);
+}
+
+// The same split in two: the detection half of frame k + 1 can be enqueued (on the detector's other context) before the filter half of
+// frame k runs, so a camera stream keeps two frames in flight.  State evolution is unchanged as long as the caller keeps the
+// reference's order per frame: add_encoder (prediction) before the frame's wait (correction).
+extern "C" int b2a_slam_add_image_submit(b2a_slam *s, b2a_detector *d, const b2a_frames *frame, const b2a_camera *cam, int *ticket)
+{
+    TRY(add_image_checks(s, d, frame, cam));
+    if (!ticket) return set_err(B2A_ERR_INVALID, "null argument");
+    *ticket = -1;
+    if (!s->is_init) return B2A_OK;                                    // ignored like addImage before the first encoder message (:84-85)
+    TRY(slam_reserve(s, d->max_markers));
+    const int set = (int)(d->next_ticket & 1u);
+    const std::function<int(b2a_detector *, cudaStream_t)> post = [&](b2a_detector *ctx, cudaStream_t st) -> int { return enqueue_observations(s, ctx, cam, set, st); };
+    return submit_impl(d, frame, cam, ticket, &post);
+}
+
+extern "C" int b2a_slam_add_image_wait(b2a_slam *s, b2a_detector *d, int ticket)
+{
+    if (!s || !d) return set_err(B2A_ERR_INVALID, "null argument");
+    if (ticket < 0) return B2A_OK;                                     // the submit was ignored
+    b2a_detections det;
+    const int rc = b2a_detect_pose_wait(d, ticket, &det);
+    if (rc != B2A_OK) return rc;
+    const int set = ticket & 1;
+    std::vector<b2a_observation> obs((size_t)std::max(s->h_n[set], 1));
+    const int k = collect_observations(s, s->h_n[set], obs.data(), set);
     return b2a_slam_update(s, obs.data(), k);
 }

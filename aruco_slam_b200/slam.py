@@ -85,6 +85,18 @@ class ArucoSlam:
             raise _lib.B2AError(1, "setCameraParameters first")
         _lib.check(_lib.lib().b2a_slam_add_image(self._h, self.detector._h, C.byref(frames), C.byref(self._cam)))
 
+    def submitImageFrames(self, frames) -> int:
+        """the detection half of addImage, enqueued (b2a_slam_add_image_submit); returns the ticket for waitImage"""
+        if self._cam is None:
+            raise _lib.B2AError(1, "setCameraParameters first")
+        t = C.c_int(-1)
+        _lib.check(_lib.lib().b2a_slam_add_image_submit(self._h, self.detector._h, C.byref(frames), C.byref(self._cam), C.byref(t)))
+        return t.value
+
+    def waitImage(self, ticket: int):
+        """the filter half of addImage for a submitted frame (b2a_slam_add_image_wait)"""
+        _lib.check(_lib.lib().b2a_slam_add_image_wait(self._h, self.detector._h, int(ticket)))
+
     def make_observations(self, corners, ids, rvecs, tvecs):
         c = np.ascontiguousarray(corners, np.float32).reshape(-1, 8)
         n = len(c)

@@ -240,6 +240,14 @@ void *b2a_slam_stream(const b2a_slam *s);
 /* addImage(img): detect + pose + observations + EKF update for one frame (aruco_slam.cpp:76-263). */
 int  b2a_slam_add_image(b2a_slam *s, b2a_detector *d, const b2a_frames *frame, const b2a_camera *cam);
 
+/* addImage split in two (like b2a_detect_pose_submit / _wait): submit enqueues detection, pose and observation mapping of a frame on
+ * one of the detector's two contexts and returns; wait blocks for that frame and runs the EKF loop on its observations.  Submitting
+ * frame k + 1 before waiting for frame k keeps two frames of a camera stream in flight.  The filter's state evolves exactly as with
+ * b2a_slam_add_image as long as every frame's b2a_slam_add_encoder call(s) come before that frame's wait (prediction before
+ * correction, aruco_slam.cpp:21-74 then :76-263).  *ticket = -1 when the frame is ignored (no encoder message yet, :84-85). */
+int  b2a_slam_add_image_submit(b2a_slam *s, b2a_detector *d, const b2a_frames *frame, const b2a_camera *cam, int *ticket);
+int  b2a_slam_add_image_wait(b2a_slam *s, b2a_detector *d, int ticket);
+
 /* ---- wire / on-disk formats either side of the path (host only, no ROS types) ---- */
 /* One line of the landmark map (reference map/map.txt:1 "id length x y z roll_x pitch_y yaw_z") and, equally, one cube of the
  * reference's MarkerArray messages (visualization_msgs::Marker fields the reference fills, map_loader.cpp:96-117 and
