@@ -219,9 +219,10 @@ def bench_c4(args, rank, local_rank, world):
         ekf_stream = torch.cuda.ExternalStream(s.stream, device=local_rank)
         descs = [aruco.ArucoDetector._frames_host(h_np[f]) if host else (aruco.ArucoDetector.frames_device(d_frames[f].data_ptr(), 1, H, W), None) for f in range(n)]
         thr, launches, poses, stage_acc = 0.0, 0, [], {}
-        for f in range(args.warmup):
+        for f in range(args.warmup):                            # through submit / wait, so that both detector contexts exist before the timed region
+            tk = s.submitImageFrames(descs[f][0])
             s.addEncoder(*enc[f])
-            s.addImageFrames(descs[f][0])
+            s.waitImage(tk)
         s.synchronize()
         if world > 1:
             dist.barrier()
