@@ -86,7 +86,7 @@ class PoseWithCovariance(C.Structure):
 # every symbol include/b2aruco.h declares
 SYMBOLS = [
     "b2a_last_error", "b2a_version", "b2a_default_detector_params", "b2a_get_predefined_dictionary",
-    "b2a_detector_create", "b2a_detector_destroy", "b2a_detect", "b2a_detect_pose", "b2a_detect_pose_submit", "b2a_detect_pose_wait",
+    "b2a_detector_create", "b2a_detector_destroy", "b2a_detect", "b2a_detect_pose", "b2a_detect_pose_submit", "b2a_detect_pose_wait", "b2a_detector_set_inflight",
     "b2a_estimate_pose_single_markers", "b2a_debug_threshold", "b2a_debug_contours", "b2a_debug_candidates",
     "b2a_detector_num_scales", "b2a_detector_set_streams", "b2a_last_stage_times", "b2a_last_launch_count", "b2a_detector_stream",
     "b2a_default_slam_params", "b2a_slam_create", "b2a_slam_destroy", "b2a_slam_dim", "b2a_slam_get_state",
@@ -128,6 +128,7 @@ def lib():
         L.b2a_slam_robot_pose.argtypes = [C.c_void_p, C.c_void_p]
         L.b2a_slam_detected_map.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p]
         L.b2a_detector_set_streams.argtypes = [C.c_void_p, C.c_int]
+        L.b2a_detector_set_inflight.argtypes = [C.c_void_p, C.c_int]
         L.b2a_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2a_detect_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2a_multi_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -273,6 +273,10 @@ class ArucoDetector:
         """number of concurrent sub-batches (CUDA streams) a call is cut into; 1 = serial stages"""
         _lib.check(_lib.lib().b2a_detector_set_streams(self._h, int(n)))
 
+    def set_inflight(self, n: int):
+        """batches that submit / wait keep in flight on this handle (1 .. 4 contexts, default 2)"""
+        _lib.check(_lib.lib().b2a_detector_set_inflight(self._h, int(n)))
+
     def last_launch_count(self) -> int:
         return _lib.lib().b2a_last_launch_count(self._h)
 

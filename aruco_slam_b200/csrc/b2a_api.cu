@@ -245,7 +245,9 @@ struct b2a_detector {
     int last_call_batch = 0; bool last_call_pose = false;       // what the result arrays hold (b2a_detector_last_detections)
     // asynchronous submit / wait: the handle owns a second, lazily created pipeline context (all buffers and streams); batches
     // alternate between the two, so the H2D copy of one overlaps the kernels of the other
-    b2a_detector *twin = nullptr;
+    static constexpr int MAX_CTX = 4;
+    b2a_detector *more[MAX_CTX - 1] = {};         // contexts 1 .. n_ctx - 1 (this object is context 0)
+    int n_ctx = 2;                                // batches in flight that submit / wait alternate over (b2a_detector_set_inflight)
     bool in_flight = false, pending_pose = false, pipelined = false; int pending_batch = 0;
     unsigned next_ticket = 0;
     std::vector<void *> allocs, pinned;
@@ -276,7 +278,7 @@ static int pin_alloc(b2a_detector *d, T **p, size_t count)
 extern "C" void b2a_detector_destroy(b2a_detector *d)
 {
     if (!d) return;
-    if (d->twin) { b2a_detector_destroy(d->twin); d->twin = nullptr; }
+    for (b2a_detector *&m : d->more) if (m) { b2a_detector_destroy(m); m = nullptr; }
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
     for (void *p : d->allocs) cudaFree(p);
@@ -983,14 +985,15 @@ static int submit_impl(b2a_detector *d, const b2a_frames *frames, const b2a_came
     if (!d || !frames || !ticket) return set_err(B2A_ERR_INVALID, "null argument");
     if (cam && !(cam->marker_length > 0)) return set_err(B2A_ERR_INVALID, "markerLength <= 0");
     b2a_detector *t = d;
-    if (d->next_ticket & 1u) {
-        if (!d->twin) {                                        // the second context is created on first use
-            TRY(b2a_detector_create(&d->cfg, &d->dict, &d->prm, &d->twin));
+    const int slot = (int)(d->next_ticket % (unsigned)d->n_ctx);
+    if (slot > 0) {
+        if (!d->more[slot - 1]) {                              // further contexts are created on first use
+            TRY(b2a_detector_create(&d->cfg, &d->dict, &d->prm, &d->more[slot - 1]));
         }
-        t = d->twin;
+        t = d->more[slot - 1];
         t->n_streams = d->n_streams;
     }
-    if (t->in_flight) return set_err(B2A_ERR_INVALID, "two batches are already in flight on this handle (b2a_detect_pose_wait first)");
+    if (t->in_flight) return set_err(B2A_ERR_INVALID, "all contexts of this handle are in flight (b2a_detect_pose_wait first)");
     t->pipelined = true;
     std::function<int(cudaStream_t)> bound;
     if (post) bound = [&](cudaStream_t st) { return (*post)(t, st); };
@@ -1010,8 +1013,9 @@ extern "C" int b2a_detect_pose_submit(b2a_detector *d, const b2a_frames *frames,
 extern "C" int b2a_detect_pose_wait(b2a_detector *d, int ticket, b2a_detections *out)
 {
     if (!d || !out) return set_err(B2A_ERR_INVALID, "null argument");
-    b2a_detector *t = (ticket & 1) ? d->twin : d;
-    if (!t || !t->in_flight || (unsigned)ticket + 2 < d->next_ticket || (unsigned)ticket >= d->next_ticket)
+    const int slot = ticket < 0 ? 0 : ticket % d->n_ctx;
+    b2a_detector *t = slot ? d->more[slot - 1] : d;
+    if (ticket < 0 || !t || !t->in_flight || (unsigned)ticket + (unsigned)d->n_ctx < d->next_ticket || (unsigned)ticket >= d->next_ticket)
         return set_err(B2A_ERR_INVALID, "no batch in flight under this ticket");
     t->in_flight = false;
     TRY(finish_pipeline(t));
@@ -1179,6 +1183,16 @@ extern "C" int b2a_multi_detect_pose(b2a_multi *m, const b2a_frames *f, const b2
     return rc;
 }
 
+extern "C" int b2a_detector_set_inflight(b2a_detector *d, int n)
+{
+    if (!d || n < 1 || n > b2a_detector::MAX_CTX) return set_err(B2A_ERR_INVALID, "in-flight batches must be 1 .. 4");
+    if (d->in_flight) return set_err(B2A_ERR_INVALID, "a submitted batch is still in flight on this handle");
+    for (b2a_detector *m : d->more) if (m && m->in_flight) return set_err(B2A_ERR_INVALID, "a submitted batch is still in flight on this handle");
+    d->n_ctx = n;
+    d->next_ticket = 0;
+    return B2A_OK;
+}
+
 extern "C" int b2a_detector_set_streams(b2a_detector *d, int n)
 {
     if (!d || n < 0) return set_err(B2A_ERR_INVALID, "streams must be >= 0 (0 = automatic)");
@@ -1332,7 +1346,7 @@ static int slam_reserve(b2a_slam *s, int n)
     slam_free_scratch(s);
     const size_t c = (size_t)std::max(256, 2 * n);
     if (cudaMalloc(&s->d_c, c * 32) || cudaMalloc(&s->d_i, c * 4) || cudaMalloc(&s->d_r, c * 24) || cudaMalloc(&s->d_t, c * 24) ||
-        cudaMalloc(&s->d_ekf, c * sizeof(EkfObs)) || cudaMallocHost(&s->h_obs, 2 * c * sizeof(Observation)) || cudaMallocHost(&s->h_keep, 2 * c * 4) ||
+        cudaMalloc(&s->d_ekf, c * sizeof(EkfObs)) || cudaMallocHost(&s->h_obs, b2a_detector::MAX_CTX * c * sizeof(Observation)) || cudaMallocHost(&s->h_keep, b2a_detector::MAX_CTX * c * 4) ||
         cudaMallocHost(&s->h_ekf[0], c * sizeof(EkfObs)) || cudaMallocHost(&s->h_ekf[1], c * sizeof(EkfObs))) {
         slam_free_scratch(s);
         (void)cudaGetLastError();
@@ -1401,7 +1415,7 @@ extern "C" int b2a_slam_create(int device, const b2a_slam_params *p, b2a_slam **
     cudaMemsetAsync(s->d_mu, 0, LD * 8, s->stream);
     cudaMemsetAsync(s->d_sigma, 0, LD * LD * 8, s->stream);
     if (cudaStreamSynchronize(s->stream) != cudaSuccess) return fail("memset");
-    if (cudaMallocHost(&s->h_n, 2 * sizeof(int)) || cudaEventCreateWithFlags(&s->ev_ekf[0], cudaEventDisableTiming) ||
+    if (cudaMallocHost(&s->h_n, b2a_detector::MAX_CTX * sizeof(int)) || cudaEventCreateWithFlags(&s->ev_ekf[0], cudaEventDisableTiming) ||
         cudaEventCreateWithFlags(&s->ev_ekf[1], cudaEventDisableTiming) || slam_reserve(s, 256) != B2A_OK)
         return fail("frame scratch");
     *out = s;
@@ -1788,7 +1802,7 @@ extern "C" int b2a_slam_add_image_submit(b2a_slam *s, b2a_detector *d, const b2a
     *ticket = -1;
     if (!s->is_init) return B2A_OK;                                    // ignored like addImage before the first encoder message (:84-85)
     TRY(slam_reserve(s, d->max_markers));
-    const int set = (int)(d->next_ticket & 1u);
+    const int set = (int)(d->next_ticket % (unsigned)d->n_ctx);
     const std::function<int(b2a_detector *, cudaStream_t)> post = [&](b2a_detector *ctx, cudaStream_t st) -> int { return enqueue_observations(s, ctx, cam, set, st); };
     return submit_impl(d, frame, cam, ticket, &post);
 }
@@ -1800,7 +1814,7 @@ extern "C" int b2a_slam_add_image_wait(b2a_slam *s, b2a_detector *d, int ticket)
     b2a_detections det;
     const int rc = b2a_detect_pose_wait(d, ticket, &det);
     if (rc != B2A_OK) return rc;
-    const int set = ticket & 1;
+    const int set = ticket % d->n_ctx;
     std::vector<b2a_observation> obs((size_t)std::max(s->h_n[set], 1));
     const int k = collect_observations(s, s->h_n[set], obs.data(), set);
     return b2a_slam_update(s, obs.data(), k);

@@ -215,11 +215,17 @@ def bench_c4(args, rank, local_rank, world):
     def run(host):
         """W untimed + K timed steps of the loop on a fresh filter; CUDA events from the idle detector stream to the filter's stream after the last frame"""
         s = new_filter()
+        s.detector.set_inflight(args.inflight)
         det_stream = torch.cuda.ExternalStream(s.detector.stream, device=local_rank)
         ekf_stream = torch.cuda.ExternalStream(s.stream, device=local_rank)
         descs = [aruco.ArucoDetector._frames_host(h_np[f]) if host else (aruco.ArucoDetector.frames_device(d_frames[f].data_ptr(), 1, H, W), None) for f in range(n)]
         thr, launches, poses, stage_acc = 0.0, 0, [], {}
-        for f in range(args.warmup):                            # through submit / wait, so that both detector contexts exist before the timed region
+        # every detector context the loop will use is created (and warmed) by plain detector submits that do not touch the filter
+        tks = [s.detector.submit_raw(descs[0][0], s._cam) for _ in range(args.inflight)]
+        for t_ in tks:
+            s.detector.wait_raw(t_)
+        s.detector.set_inflight(args.inflight)                  # ticket counter back to 0
+        for f in range(args.warmup):
             tk = s.submitImageFrames(descs[f][0])
             s.addEncoder(*enc[f])
             s.waitImage(tk)
@@ -229,14 +235,16 @@ def bench_c4(args, rank, local_rank, world):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(det_stream)
-        # two frames of the stream in flight: frame f + 1's detection is submitted before frame f's filter half runs; per frame the
-        # order of the reference holds (addEncoder = prediction, then the frame's correction)
-        tk = s.submitImageFrames(descs[args.warmup][0])
+        # several frames of the stream in flight: the detection of the next frames is submitted before frame f's filter half runs; per
+        # frame the order of the reference holds (addEncoder = prediction, then the frame's correction)
+        import collections
+        q, nxt = collections.deque(), args.warmup
         for f in range(args.warmup, n):
-            nxt = s.submitImageFrames(descs[f + 1][0]) if f + 1 < n else None
+            while nxt < n and len(q) < args.inflight:
+                q.append(s.submitImageFrames(descs[nxt][0]))
+                nxt += 1
             s.addEncoder(*enc[f])
-            s.waitImage(tk)
-            tk = nxt
+            s.waitImage(q.popleft())
             if host:
                 poses.append(formats.robot_pose(s).position[:2].copy())       # the step's result read on the host (toRosPose), waits for the EKF
             for k_, v_ in s.detector.last_stage_times().items():
@@ -284,10 +292,10 @@ def bench_c4(args, rank, local_rank, world):
                "config": {"workload": "C4: %d camera stream(s) (one per GPU), 1080p, map.txt-style landmark map (%d markers, DICT_ARUCO_ORIGINAL), encoder + frame per step, "
                                       "full EKF SLAM loop (addEncoder + addImage)" % (world, len(synth.c4_map())),
                           "l2": "every step brings a new 2 MB frame; L2 not flushed (a stream's consecutive frames are what a camera delivers)",
-                          "parallelism": "one stream and one filter per GPU, no collective; two frames of the stream in flight (b2a_slam_add_image_submit / _wait)"},
+                          "parallelism": "one stream and one filter per GPU, no collective; %d frames of the stream in flight (b2a_slam_add_image_submit / _wait)" % args.inflight},
                "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": P, "d2h_bytes_per_step": 12 * 8 + 12 + 12 * 84,
                        "how": "per step: b2a_slam_add_image_submit of the NEXT pinned host frame (H2D inside), b2a_slam_add_encoder, b2a_slam_add_image_wait of this frame, "
-                              "b2a_slam_robot_pose read back (waits for the step's EKF kernels); two frames in flight on one detector handle"},
+                              "b2a_slam_robot_pose read back (waits for the step's EKF kernels); %d frames in flight on one detector handle" % args.inflight},
                "gpu_launches": launches, "stages_ms_per_frame": stages,
                "roofline": {"kernel": "k_threshold_march<1,6,11> (one 1080p frame per launch)", "bound": "hbm", "achieved": 4 * P / (thr_ms * 1e-3) / 1e9 if thr_ms > 0 else 0.0, "peak": peak,
                             "unit": "GB/s", "frac": (4 * P / (thr_ms * 1e-3) / 1e9 / peak) if thr_ms > 0 else None, "traffic": None, "peak_source": which, "algorithmic_bytes_per_launch": 4 * P,
@@ -486,6 +494,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=list(WORKLOADS) + ["C4", "C5"])
     ap.add_argument("--ekf-landmarks", type=int, default=500)
     ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
+    ap.add_argument("--inflight", type=int, default=4, help="C4: frames of a stream kept in flight (1 .. 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipelined", action="store_true", help="skip the two-handle / two-thread extra (use under ncu: the profiler serialises the two threads' launches)")
     args = ap.parse_args()

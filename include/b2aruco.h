@@ -141,10 +141,14 @@ int b2a_detector_last_detections(b2a_detector *d, b2a_detections *out);
  * are in host memory and fills `out`.  Tickets alternate between two internal pipeline contexts (the second is created on
  * the first odd ticket), so the PCIe copy of batch k+1 overlaps the kernels of batch k:
  *     submit(k+1) ... wait(k) ... submit(k+2) ... wait(k+1) ...
- * At most two batches in flight; waits in submission order; frames->data must stay valid until the matching wait; the
+ * At most n batches in flight (b2a_detector_set_inflight, default two); waits in submission order; frames->data must stay valid until the matching wait; the
  * arrays `out` points to stay valid until the second submit after it.  The synchronous calls above refuse to run while a
  * batch is in flight on the first context. */
 int b2a_detect_pose_submit(b2a_detector *d, const b2a_frames *frames, const b2a_camera *cam, int *ticket);
+/* how many batches submit / wait keep in flight on this handle: 1 .. 4 contexts, default 2 (more pay off for single frames, whose
+ * kernels leave most of the GPU idle; a 32-frame batch is bound by its PCIe copy with two).  Resets the ticket counter; not while a
+ * batch is in flight. */
+int b2a_detector_set_inflight(b2a_detector *d, int n);
 int b2a_detect_pose_wait(b2a_detector *d, int ticket, b2a_detections *out);
 
 /* cv::aruco::drawDetectedMarkers(image, corners, ids, borderColor) (aruco_slam.cpp:319; the image getMarkedImg returns,

@@ -271,8 +271,10 @@ def test_c5_vs_reference_run(name):
     s.close()
 
 
-def test_add_image_submit_wait_equals_sequential_loop():
-    """b2a_slam_add_image_submit / _wait with two frames in flight: the same filter state, frame by frame, as the sequential addImage loop"""
+@pytest.mark.parametrize("depth", [2, 4])
+def test_add_image_submit_wait_equals_sequential_loop(depth):
+    """b2a_slam_add_image_submit / _wait with 2 / 4 frames in flight: the same filter state, frame by frame, as the sequential addImage loop"""
+    import collections
     from aruco_slam_b200.aruco import ArucoDetector
     g = golden("slam_scene")
     frames = g["frames"]
@@ -280,17 +282,19 @@ def test_add_image_submit_wait_equals_sequential_loop():
     a = _golden_slam(g, image_shape=frames.shape[1:])
     b = _golden_slam(g, image_shape=frames.shape[1:])
     descs = [ArucoDetector._frames_host(frames[f]) for f in range(n)]
+    b.detector.set_inflight(depth)
     assert b.submitImageFrames(descs[0][0]) == -1                  # before the first encoder message the frame is ignored (aruco_slam.cpp:84-85)
     b.waitImage(-1)
     a.addEncoder(0, 0, None); b.addEncoder(0, 0, None)
-    tk = b.submitImageFrames(descs[0][0])
+    q, nxt = collections.deque(), 0
     for f in range(n):
-        nxt = b.submitImageFrames(descs[f + 1][0]) if f + 1 < n else None
+        while nxt < n and len(q) < depth:
+            q.append(b.submitImageFrames(descs[nxt][0]))
+            nxt += 1
         for wl, wr, dt in g["enc_%d" % f]:
             a.addEncoder(wl, wr, dt); b.addEncoder(wl, wr, dt)
         a.addImage(frames[f])
-        b.waitImage(tk)
-        tk = nxt
+        b.waitImage(q.popleft())
         ma, sa, ia = a.get_state()
         mb, sb, ib = b.get_state()
         assert np.array_equal(ia, ib) and np.array_equal(ma, mb) and np.array_equal(sa, sb), f
