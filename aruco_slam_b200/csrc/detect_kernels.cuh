@@ -606,29 +606,34 @@ __device__ __forceinline__ unsigned warp_append(unsigned *counter, int cnt, int 
 // interior of a region are dropped) and queues the others in shared memory; whenever 256 are queued
 // every thread takes one, so the logic always runs on full warps, and the two global list counters see
 // one atomic per 256 words (same-address atomics serialise in L2: one per warp was 60 % of this kernel).
+constexpr int ANCHOR_SCAN_U = 4;      // mask words a thread filters per iteration (independent loads in flight, a quarter of the barriers)
 struct AnchorBlock {
-    unsigned queue[512];
+    unsigned queue[256 + 256 * ANCHOR_SCAN_U];
     int nq;
-    int wsum[2][8];
+    int wsum[2][16];
     unsigned base[2];
 };
 
-// exclusive position of this thread's cnt items in the CTA-wide append to *counter (which = 0 anchors, 1 starts)
-__device__ __forceinline__ unsigned block_append(AnchorBlock &sb, int which, unsigned *counter, int cnt)
+// exclusive positions of this thread's cnt0 anchors and cnt1 start candidates in the CTA-wide appends to the two list counters:
+// one round (two barriers, the two atomics issued together) for both lists
+__device__ __forceinline__ void block_append2(AnchorBlock &sb, unsigned *counter0, unsigned *counter1, int cnt0, int cnt1, unsigned &pos0, unsigned &pos1)
 {
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    int incl = cnt;
+    int incl = cnt0 | (cnt1 << 16);                     // a word holds at most 128 states of either kind: the two scans share the shuffles
 #pragma unroll
     for (int dd = 1; dd < 32; dd <<= 1) { const int o = __shfl_up_sync(0xFFFFFFFFu, incl, dd); if (lane >= dd) incl += o; }
-    if (lane == 31) sb.wsum[which][wp] = incl;
+    if (lane == 31) sb.wsum[0][wp] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 2) {
+        const int sh = 16 * threadIdx.x;
         int tot = 0;
-        for (int w = 0; w < 8; ++w) { const int v = sb.wsum[which][w]; sb.wsum[which][w] = tot; tot += v; }
-        sb.base[which] = tot ? atomicAdd(counter, (unsigned)tot) : 0u;
+        for (int w = 0; w < 8; ++w) { const int v = (sb.wsum[0][w] >> sh) & 0xFFFF; sb.wsum[1][2 * w + threadIdx.x] = tot; tot += v; }
+        sb.base[threadIdx.x] = tot ? atomicAdd(threadIdx.x ? counter1 : counter0, (unsigned)tot) : 0u;
     }
     __syncthreads();
-    return sb.base[which] + (unsigned)sb.wsum[which][wp] + (unsigned)(incl - cnt);
+    const int excl = incl - (cnt0 | (cnt1 << 16));
+    pos0 = sb.base[0] + (unsigned)sb.wsum[1][2 * wp] + (unsigned)(excl & 0xFFFF);
+    pos1 = sb.base[1] + (unsigned)sb.wsum[1][2 * wp + 1] + (unsigned)(excl >> 16);
 }
 
 __device__ __forceinline__ void anchors_of_word(AnchorBlock &sb, const uint32_t *__restrict__ masks, const BorderGraph &bg, int *__restrict__ iso_count,
@@ -651,7 +656,9 @@ __device__ __forceinline__ void anchors_of_word(AnchorBlock &sb, const uint32_t 
     }
     // anchors: pixel by pixel, canonical directions E, N, W, S inside a pixel
     const int cnt = __popc(A[0]) + __popc(A[1]) + __popc(A[2]) + __popc(A[3]);
-    unsigned pos = block_append(sb, 0, bg.n_anchors, cnt);
+    const int ucnt = __popc(U[0]) + __popc(U[1]) + __popc(U[2]) + __popc(U[3]);
+    unsigned pos, upos;
+    block_append2(sb, bg.n_anchors, bg.n_starts, cnt, ucnt, pos, upos);
     if (cnt && pos < bg.cap) bg.amap[((size_t)fs * g.H + y) * g.WW + wx] = pos;
     for (uint32_t px = A[0] | A[1] | A[2] | A[3]; px; px &= px - 1) {
         const int b = __ffs(px) - 1, x = wx * 32 + b;
@@ -669,8 +676,6 @@ __device__ __forceinline__ void anchors_of_word(AnchorBlock &sb, const uint32_t 
         }
     }
     // start candidates
-    const int ucnt = __popc(U[0]) + __popc(U[1]) + __popc(U[2]) + __popc(U[3]);
-    unsigned upos = block_append(sb, 1, bg.n_starts, ucnt);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         for (uint32_t px = U[k]; px; px &= px - 1) {
@@ -691,34 +696,44 @@ k_anchors(const uint32_t *__restrict__ masks, BorderGraph bg, int *__restrict__ 
     if (threadIdx.x == 0) sb.nq = 0;
     __syncthreads();
     // word index = (fs * H + y) * WW + wx; every thread of the CTA runs the same number of iterations
-    for (unsigned i0 = blockIdx.x * blockDim.x; i0 < total; i0 += stride) {
-        const unsigned i = i0 + threadIdx.x;
-        bool keep = false;
-        if (i < total) {
-            const unsigned fs = i / words_per_plane, rem = i - fs * words_per_plane;
-            const unsigned y = rem / (unsigned)g.WW, wx = rem - y * (unsigned)g.WW;
-            const uint32_t *row = masks + (size_t)fs * g.mask_plane + (size_t)(y + 1) * g.PWW + wx + 1;
-            const uint32_t m = __ldg(row);
-            if (m) {
-                // interior of a region: the word, the words above and below are full and so are the six flanking bits
-                const uint32_t u = __ldg(row - g.PWW), d = __ldg(row + g.PWW);
-                keep = (m & u & d) != 0xFFFFFFFFu || !(__ldg(row - 1) >> 31) || !(__ldg(row + 1) & 1u) ||
-                       !(__ldg(row - g.PWW - 1) >> 31) || !(__ldg(row - g.PWW + 1) & 1u) || !(__ldg(row + g.PWW - 1) >> 31) || !(__ldg(row + g.PWW + 1) & 1u);
+    constexpr int U = ANCHOR_SCAN_U;
+    for (unsigned i0 = blockIdx.x * blockDim.x * U; i0 < total; i0 += stride * U) {
+        const uint32_t *row[U];
+        uint32_t m[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const unsigned i = i0 + k * blockDim.x + threadIdx.x;
+            m[k] = 0; row[k] = masks;
+            if (i < total) {
+                const unsigned fs = i / words_per_plane, rem = i - fs * words_per_plane;
+                const unsigned y = rem / (unsigned)g.WW, wx = rem - y * (unsigned)g.WW;
+                row[k] = masks + (size_t)fs * g.mask_plane + (size_t)(y + 1) * g.PWW + wx + 1;
+                m[k] = __ldg(row[k]);
             }
         }
-        const unsigned km = __ballot_sync(0xFFFFFFFFu, keep);
-        int wbase = 0;
-        if (lane == 0 && km) wbase = atomicAdd(&sb.nq, __popc(km));
-        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-        if (keep) sb.queue[wbase + __popc(km & ((1u << lane) - 1u))] = i;          // nq < 256 before: never past 511
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            bool keep = false;
+            if (m[k]) {
+                // interior of a region: the word, the words above and below are full and so are the six flanking bits
+                const uint32_t *r = row[k];
+                const uint32_t u = __ldg(r - g.PWW), d = __ldg(r + g.PWW);
+                keep = (m[k] & u & d) != 0xFFFFFFFFu || !(__ldg(r - 1) >> 31) || !(__ldg(r + 1) & 1u) ||
+                       !(__ldg(r - g.PWW - 1) >> 31) || !(__ldg(r - g.PWW + 1) & 1u) || !(__ldg(r + g.PWW - 1) >> 31) || !(__ldg(r + g.PWW + 1) & 1u);
+            }
+            const unsigned km = __ballot_sync(0xFFFFFFFFu, keep);
+            int wbase = 0;
+            if (lane == 0 && km) wbase = atomicAdd(&sb.nq, __popc(km));
+            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+            if (keep) sb.queue[wbase + __popc(km & ((1u << lane) - 1u))] = i0 + k * blockDim.x + threadIdx.x;   // nq < 256 before the iteration: never past the queue
+        }
         __syncthreads();
-        const int nq = sb.nq;
-        if (nq >= 256) {
+        for (int nq = sb.nq; nq >= 256; nq -= 256) {                              // the same count in every thread
             const unsigned widx = sb.queue[nq - 256 + threadIdx.x];                  // take the last 256: the rest stays in place
-            __syncthreads();
-            if (threadIdx.x == 0) sb.nq = nq - 256;
             anchors_of_word(sb, masks, bg, iso_count, Rm, Rm2, g, widx, true);
         }
+        __syncthreads();
+        if (threadIdx.x == 0) sb.nq &= 255;
         __syncthreads();
     }
     const int nq = sb.nq;
