@@ -228,7 +228,7 @@ struct b2a_detector {
     WalkTables *d_tables = nullptr;
     FrameScratch fs0{};                       // frame-0 pointers
     FrameOutputs fo0{};
-    float *d_corners2 = nullptr;              // subpix output
+    float *d_corners2 = nullptr;              // corners after the optional refinement (subpix / contour lines)
     double *d_rvecs = nullptr, *d_tvecs = nullptr;
     // pinned host mirrors of the outputs
     int32_t *h_nacc = nullptr, *h_nrej = nullptr, *h_ids = nullptr, *h_status = nullptr;
@@ -398,6 +398,8 @@ extern "C" int b2a_detector_create(const b2a_detector_config *cfg, const b2a_dic
     b2a_detector_params prm;
     if (params) prm = *params; else b2a_default_detector_params(&prm);
     if (prm.markerBorderBits < 1) return set_err(B2A_ERR_INVALID, "markerBorderBits < 1");
+    if (prm.cornerRefinementMethod < 0 || prm.cornerRefinementMethod > 3) return set_err(B2A_ERR_INVALID, "cornerRefinementMethod");
+    if (prm.cornerRefinementMethod == 3) return set_err(B2A_ERR_UNSUPPORTED, "CORNER_REFINE_APRILTAG (the AprilTag quad detector is not part of this library)");
     if (prm.adaptiveThreshWinSizeMin < 3 || prm.adaptiveThreshWinSizeMax < prm.adaptiveThreshWinSizeMin || prm.adaptiveThreshWinSizeStep <= 0)
         return set_err(B2A_ERR_INVALID, "adaptiveThreshWinSize*");
     if (dict->markerSize < 1 || dict->markerSize * dict->markerSize > 64 || dict->nBytes != (dict->markerSize * dict->markerSize + 7) / 8)
@@ -739,6 +741,13 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
         sp.maxIter = d->prm.cornerRefinementMaxIterations; sp.relWin = d->prm.relativeCornerRefinmentWinSize; sp.eps = d->prm.cornerRefinementMinAccuracy;
         float *c2 = d->d_corners2 + (size_t)b0 * K * 8;
         k_subpix<<<d->num_sms * 2, 128, 0, st>>>(s.gray, fa.fo0.n_accepted, fa.fo0.corners, c2, nb, sp);
+        d->launches++;
+        corners = c2;
+    } else if (d->prm.cornerRefinementMethod == 2) {
+        float *c2 = d->d_corners2 + (size_t)b0 * K * 8;
+        k_refine_contour<<<(nb * (int)K * 32 + 127) / 128, 128, 0, st>>>(fa.fo0.corners, fa.fo0.n_accepted, c2, d->d_surv_count + fs0, d->d_pts_off + fs0 * g.surv_cap,
+                                                                        d->d_pts + fs0 * (size_t)g.pts_cap, d->d_quad_ok + fs0 * g.surv_cap, d->d_quad_xy + fs0 * g.surv_cap * 8,
+                                                                        d->d_quad_len + fs0 * g.surv_cap, g, nb, d->max_markers);
         d->launches++;
         corners = c2;
     }
@@ -1769,7 +1778,7 @@ static int add_image_checks(b2a_slam *s, b2a_detector *d, const b2a_frames *fram
 // k_observations behind the detection of one frame: reads the context's device outputs, leaves the records in pinned set `set`
 static int enqueue_observations(b2a_slam *s, b2a_detector *ctx, const b2a_camera *cam, int set, cudaStream_t st)
 {
-    const float *corners = ctx->prm.cornerRefinementMethod == 1 ? ctx->d_corners2 : ctx->fo0.corners;
+    const float *corners = ctx->prm.cornerRefinementMethod != 0 ? ctx->d_corners2 : ctx->fo0.corners;
     k_observations<<<(ctx->max_markers + 63) / 64, 64, 0, st>>>(corners, ctx->fo0.ids, ctx->d_rvecs, ctx->d_tvecs, 0, ctx->fo0.n_accepted, ctx->max_markers,
                                                                 to_camera(cam), obs_params(s, cam), s->h_obs + (size_t)set * s->obs_cap,
                                                                 s->h_keep + (size_t)set * s->obs_cap, s->h_n + set);

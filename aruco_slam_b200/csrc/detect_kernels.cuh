@@ -16,11 +16,13 @@
 //   k_identify        A7   per candidate: homography, NN warp, Otsu, bits, dictionary match
 //   k_finalize        A6   per frame: depth-ordered acceptance, output
 //   k_subpix          A8   optional cornerSubPix
+//   k_refine_contour  A8   optional CORNER_REFINE_CONTOUR (refine_core.h)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "core.h"
 #include "frame_logic.h"
+#include "refine_core.h"
 
 namespace b2a {
 
@@ -1607,6 +1609,50 @@ __global__ void k_subpix(const uint8_t *__restrict__ gray, const int32_t *__rest
         if (fabsf(cIx - cTx) > (float)win || fabsf(cIy - cTy) > (float)win) { cIx = cTx; cIy = cTy; }
         pt[0] = cIx; pt[1] = cIy;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A8 (optional): CORNER_REFINE_CONTOUR, one warp per accepted marker (refine_core.h).  The marker's contour is still in the
+// point arrays of the contour stage; the warp finds it by its quad, sums the four sides and lane 0 writes the crossings.
+// ---------------------------------------------------------------------------------------------
+struct RefineLanes {
+    __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+    __device__ __forceinline__ int nlanes() const { return 32; }
+    __device__ __forceinline__ uint32_t ballot(bool p) const { return __ballot_sync(0xFFFFFFFFu, p); }
+    __device__ __forceinline__ int bcast(int v, int l) const { return __shfl_sync(0xFFFFFFFFu, v, l); }
+    __device__ __forceinline__ long long sum(long long v) const
+    {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        return v;
+    }
+    __device__ __forceinline__ int imin(int v) const { return __reduce_min_sync(0xFFFFFFFFu, v); }
+    __device__ __forceinline__ int imax(int v) const { return __reduce_max_sync(0xFFFFFFFFu, v); }
+};
+
+__global__ void __launch_bounds__(128)
+k_refine_contour(const float *__restrict__ corners, const int32_t *__restrict__ n_acc, float *__restrict__ out,
+                 const int *__restrict__ surv_count, const int *__restrict__ pts_off, const uint32_t *__restrict__ pts,
+                 const uint8_t *__restrict__ quad_ok, const int32_t *__restrict__ quad_xy, const int32_t *__restrict__ quad_len,
+                 DetGeom g, int nb, int max_markers)
+{
+    const int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int f = w / max_markers, m = w - f * max_markers;
+    if (f >= nb || m >= n_acc[f]) return;
+    const RefineLanes lg;
+    const float *cin = corners + ((size_t)f * max_markers + m) * 8;
+    float *co = out + ((size_t)f * max_markers + m) * 8;
+    const size_t fs0 = (size_t)f * g.nScales;
+    const int hit = refine_find_border(lg, surv_count + fs0, quad_ok + fs0 * g.surv_cap, quad_xy + fs0 * g.surv_cap * 8, g.nScales, g.surv_cap, cin);
+    float r[8];
+    bool done = false;
+    if (hit >= 0) {
+        const size_t slot = fs0 * g.surv_cap + hit, fs = fs0 + hit / g.surv_cap;
+        const int off = pts_off[slot];
+        if (off >= 0) { refine_marker_lines(lg, pts + fs * (size_t)g.pts_cap + off, quad_len[slot], cin, r); done = true; }
+    }
+    if (lg.lane() == 0)
+        for (int k = 0; k < 8; ++k) co[k] = done ? r[k] : cin[k];
 }
 
 }  // namespace b2a

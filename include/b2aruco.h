@@ -53,7 +53,8 @@ typedef struct {
     double maxErroneousBitsInBorderRate;          /* 0.35 */
     double minOtsuStdDev;                         /* 5.0 */
     double errorCorrectionRate;                   /* 0.6 */
-    int    cornerRefinementMethod;                /* 0 = CORNER_REFINE_NONE, 1 = CORNER_REFINE_SUBPIX */
+    int    cornerRefinementMethod;                /* 0 = CORNER_REFINE_NONE, 1 = CORNER_REFINE_SUBPIX, 2 = CORNER_REFINE_CONTOUR;
+                                                     3 (CORNER_REFINE_APRILTAG) -> B2A_ERR_UNSUPPORTED */
     int    cornerRefinementWinSize;               /* 5 */
     double relativeCornerRefinmentWinSize;        /* 0.3 */
     int    cornerRefinementMaxIterations;         /* 30 */

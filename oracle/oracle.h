@@ -46,7 +46,7 @@ typedef struct {
     double maxErroneousBitsInBorderRate;      /* 0.35 */
     double minOtsuStdDev;                     /* 5.0 */
     double errorCorrectionRate;               /* 0.6 */
-    int    cornerRefinementMethod;            /* 0 none, 1 subpix */
+    int    cornerRefinementMethod;            /* 0 none, 1 subpix, 2 contour */
     int    cornerRefinementWinSize;           /* 5 */
     double relativeCornerRefinmentWinSize;    /* 0.3 */
     int    cornerRefinementMaxIterations;     /* 30 */
@@ -82,6 +82,8 @@ int  orc_identify_one(const uint8_t *gray, int W, int H, const float *corners4,
                       const orc_dict *d, const orc_params *p, int *id, int *rot, uint8_t *bits_out);
 void orc_corner_subpix(const uint8_t *gray, int W, int H, float *corners, int n,
                        int win, int maxIter, double eps);
+/* CORNER_REFINE_CONTOUR of one marker (_refineCandidateLines): contour n x (x, y); corners 4 x (x, y) in / out */
+int  orc_refine_candidate_lines(const int32_t *contour, int n, float *corners);
 
 /* ---- full detector ---- */
 typedef struct {

@@ -203,6 +203,14 @@ def corner_subpix(gray, corners, win, max_iter=30, eps=0.1):
     return c
 
 
+def refine_candidate_lines(contour, corners):
+    """CORNER_REFINE_CONTOUR of one marker: contour (n, 2) int, corners (4, 2) -> refined (4, 2) f32 (None when cv2 would raise)"""
+    ct = np.ascontiguousarray(contour, np.int32).reshape(-1, 2)
+    c = np.array(corners, np.float32).reshape(4, 2).copy()
+    ok = lib().orc_refine_candidate_lines(_p(ct), len(ct), _p(c))
+    return c if ok else None
+
+
 def detect(img, dic, params=None, debug=False):
     """-> (corners (n,4,2) f32, ids (n,) i32, rejected (m,4,2) f32[, debug dict])"""
     img = np.ascontiguousarray(img, np.uint8)

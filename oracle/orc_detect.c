@@ -522,12 +522,108 @@ void orc_corner_subpix(const uint8_t *gray, int W, int H, float *corners, int n,
 /* ------------------------------------------------------------------------- */
 /* full detector                                                             */
 /* ------------------------------------------------------------------------- */
+
+/* ---- CORNER_REFINE_CONTOUR: cv::aruco _refineCandidateLines / _interpolate2Dline / _getCrossPoint (cv2 4.13
+ *      aruco_detector.cpp).  Every side of the marker becomes the least-squares line through the contour points between two
+ *      corners; the corners move to the crossings.  cv2 fits with cv::solve(A, B, DECOMP_NORMAL) on CV_32F matrices: A^T A
+ *      and A^T B are rounded to float (exact sums here: the coordinates are integers), the 2 x 2 system goes through the
+ *      float LU of hal::LU32f, the crossing through Matx22f::solve's closed form -- all restated below in float.  cv2
+ *      itself computes A^T B with its BLAS once a side has 100 points or more, so there its sums carry float rounding
+ *      that depends on the BLAS build: parity with cv2 is exact below 100 points per side and within 0.05 px above
+ *      (tests/golden/contour_refine_*.npz). ---- */
+static int lu2_solve_f32(float A[2][2], float b[2], float x[2])
+{
+    for (int i = 0; i < 2; i++) {
+        int k = i;
+        for (int j = i + 1; j < 2; j++) if (fabsf(A[j][i]) > fabsf(A[k][i])) k = j;
+        if (fabsf(A[k][i]) < FLT_EPSILON * 10) return 0;
+        if (k != i) {
+            for (int c = 0; c < 2; c++) { float t = A[i][c]; A[i][c] = A[k][c]; A[k][c] = t; }
+            float t = b[i]; b[i] = b[k]; b[k] = t;
+        }
+        float d = -1 / A[i][i];
+        for (int j = i + 1; j < 2; j++) {
+            float alpha = A[j][i] * d;
+            for (int c = i + 1; c < 2; c++) A[j][c] += alpha * A[i][c];
+            b[j] += alpha * b[i];
+        }
+    }
+    for (int i = 1; i >= 0; i--) {
+        float s = b[i];
+        for (int c = i + 1; c < 2; c++) s -= A[i][c] * x[c];
+        x[i] = s / A[i][i];
+    }
+    return 1;
+}
+
+typedef struct { double n, sx, sy, sxx, syy, sxy; int minx, maxx, miny, maxy; } side_sums;
+
+static void interpolate_2d_line(const side_sums *g, float line[3])
+{
+    float A[2][2], b[2], x[2] = {0.f, 0.f};
+    if (g->maxx - g->minx > g->maxy - g->miny) {          /* y = a x + b  ->  (a, -1, b) */
+        A[0][0] = (float)g->sxx; A[0][1] = A[1][0] = (float)g->sx; A[1][1] = (float)g->n;
+        b[0] = (float)g->sxy; b[1] = (float)g->sy;
+        if (!lu2_solve_f32(A, b, x)) x[0] = x[1] = 0.f;
+        line[0] = x[0]; line[1] = -1.f; line[2] = x[1];
+    } else {                                              /* x = a y + b  ->  (-1, a, b) */
+        A[0][0] = (float)g->syy; A[0][1] = A[1][0] = (float)g->sy; A[1][1] = (float)g->n;
+        b[0] = (float)g->sxy; b[1] = (float)g->sx;
+        if (!lu2_solve_f32(A, b, x)) x[0] = x[1] = 0.f;
+        line[0] = -1.f; line[1] = x[0]; line[2] = x[1];
+    }
+}
+
+static void cross_point(const float l1[3], const float l2[3], float out[2])
+{
+    float d = l1[0] * l2[1] - l1[1] * l2[0];
+    out[0] = out[1] = 0.f;
+    if (d == 0) return;
+    d = 1 / d;
+    const float b0 = -l1[2], b1 = -l2[2];
+    out[0] = (b0 * l2[1] - b1 * l1[1]) * d;
+    out[1] = (b1 * l1[0] - b0 * l2[0]) * d;
+}
+
+/* corners: 4 x (x, y), each one a point of the contour; returns 0 (corners untouched) when a corner is not on the contour or a
+ * side has fewer than two points (cv2 raises there) */
+int orc_refine_candidate_lines(const int32_t *contour, int n, float *corners)
+{
+    side_sums g[5];
+    int cornerIndex[4] = {-1, -1, -1, -1}, group = 4;
+    memset(g, 0, sizeof(g));
+    for (int k = 0; k < 5; k++) { g[k].minx = g[k].miny = INT32_MAX; g[k].maxx = g[k].maxy = INT32_MIN; }
+    for (int i = 0; i < n; i++) {
+        const int x = contour[2 * i], y = contour[2 * i + 1];
+        for (int j = 0; j < 4; j++) if (corners[2 * j] == (float)x && corners[2 * j + 1] == (float)y) { cornerIndex[j] = i; group = j; }
+        side_sums *s = &g[group];
+        s->n += 1; s->sx += x; s->sy += y; s->sxx += (double)x * x; s->syy += (double)y * y; s->sxy += (double)x * y;
+        if (x < s->minx) s->minx = x; if (x > s->maxx) s->maxx = x; if (y < s->miny) s->miny = y; if (y > s->maxy) s->maxy = y;
+    }
+    for (int j = 0; j < 4; j++) if (cornerIndex[j] == -1) return 0;
+    if (g[4].n > 0) {                                     /* the points before the first corner belong to the last side */
+        side_sums *s = &g[group], *e = &g[4];
+        s->n += e->n; s->sx += e->sx; s->sy += e->sy; s->sxx += e->sxx; s->syy += e->syy; s->sxy += e->sxy;
+        if (e->minx < s->minx) s->minx = e->minx; if (e->maxx > s->maxx) s->maxx = e->maxx;
+        if (e->miny < s->miny) s->miny = e->miny; if (e->maxy > s->maxy) s->maxy = e->maxy;
+    }
+    for (int j = 0; j < 4; j++) if (g[j].n < 2) return 0;
+    int inc = 1;
+    if (cornerIndex[0] > cornerIndex[1] && cornerIndex[3] > cornerIndex[0]) inc = -1;
+    if (cornerIndex[2] > cornerIndex[3] && cornerIndex[1] > cornerIndex[2]) inc = -1;
+    float lines[4][3];
+    for (int j = 0; j < 4; j++) interpolate_2d_line(&g[j], lines[j]);
+    for (int j = 0; j < 4; j++) cross_point(lines[j], lines[inc < 0 ? (j + 1) % 4 : (j + 3) % 4], corners + 2 * j);
+    return 1;
+}
+
 typedef struct {
     float c[8];
     float perimeter;
     int   len;          /* contour length */
     int   parent, depth;
     int   n_close; int *close;   /* indices into the sorted candidate array T */
+    int32_t *contour;            /* the candidate's contour points (x, y), kept only for CORNER_REFINE_CONTOUR */
 } cand_t;
 
 static float perimeter_f(const float *c)
@@ -624,6 +720,10 @@ int orc_detect(const uint8_t *img, int W, int H, int channels, const orc_dict *d
                     memset(c, 0, sizeof(*c));
                     for (int j = 0; j < 8; j++) c->c[j] = (float)ap[j];
                     c->len = n; c->parent = -1; c->depth = 0;
+                    if (p->cornerRefinementMethod == 2) {
+                        c->contour = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)n);
+                        memcpy(c->contour, pts + 2 * (size_t)offs[ci], sizeof(int32_t) * 2 * (size_t)n);
+                    }
                     /* A4: clockwise */
                     double dx1 = c->c[2] - c->c[0], dy1 = c->c[3] - c->c[1];
                     double dx2 = c->c[4] - c->c[0], dy2 = c->c[5] - c->c[1];
@@ -713,7 +813,8 @@ int orc_detect(const uint8_t *img, int W, int H, int channels, const orc_dict *d
     char *valid = (char *)calloc((size_t)(nS ? nS : 1), 1), *was = (char *)calloc((size_t)(nS ? nS : 1), 1);
     int *ids = (int *)malloc(sizeof(int) * (size_t)(nS ? nS : 1)), *rots = (int *)calloc((size_t)(nS ? nS : 1), sizeof(int));
     float *fc = (float *)malloc(sizeof(float) * 8 * (size_t)(nS ? nS : 1));   /* final corners per selected */
-    for (int i = 0; i < nS; i++) { ids[i] = -1; memcpy(fc + 8 * i, T[S[i]].c, sizeof(float) * 8); }
+    int *fcand = (int *)malloc(sizeof(int) * (size_t)(nS ? nS : 1));          /* the candidate (index into T) they come from */
+    for (int i = 0; i < nS; i++) { ids[i] = -1; memcpy(fc + 8 * i, T[S[i]].c, sizeof(float) * 8); fcand[i] = S[i]; }
     int maxDepth = 0;
     for (int i = 0; i < nS; i++) if (T[S[i]].depth > maxDepth) maxDepth = T[S[i]].depth;
     int counter = 0;
@@ -726,7 +827,7 @@ int orc_detect(const uint8_t *img, int W, int H, int channels, const orc_dict *d
                 for (int k = 0; k < T[S[v]].n_close; k++) {
                     const float *cc = T[T[S[v]].close[k]].c;
                     if (orc_identify_one(gray, W, H, cc, d, p, &ids[v], &rots[v], NULL)) {
-                        valid[v] = 1; memcpy(fc + 8 * v, cc, sizeof(float) * 8); break;
+                        valid[v] = 1; memcpy(fc + 8 * v, cc, sizeof(float) * 8); fcand[v] = T[S[v]].close[k]; break;
                     }
                 }
             }
@@ -752,6 +853,8 @@ int orc_detect(const uint8_t *img, int W, int H, int channels, const orc_dict *d
             int r = rots[v];
             /* std::rotate(begin, begin + 4 - rot, end): out[j] = in[(j + 4 - rot) % 4] */
             for (int j = 0; j < 4; j++) { o[2 * j] = fc[8 * v + 2 * ((j + 4 - r) % 4)]; o[2 * j + 1] = fc[8 * v + 2 * ((j + 4 - r) % 4) + 1]; }
+            /* optional refinement with the contour's side lines (after the rotation, as detectMarkers does) */
+            if (p->cornerRefinementMethod == 2) orc_refine_candidate_lines(T[fcand[v]].contour, T[fcand[v]].len, o);
             out->ids[out->n_acc++] = ids[v];
         } else {
             memcpy(out->rejected + 8 * out->n_rej, fc + 8 * v, sizeof(float) * 8);
@@ -770,7 +873,8 @@ int orc_detect(const uint8_t *img, int W, int H, int channels, const orc_dict *d
             orc_corner_subpix(gray, W, H, c, 4, win, p->cornerRefinementMaxIterations, p->cornerRefinementMinAccuracy);
         }
     }
-    for (int i = 0; i < nT; i++) free(T[i].close);
+    for (int i = 0; i < nT; i++) { free(T[i].close); free(T[i].contour); }
+    free(fcand);
     for (int g = 0; g < ng; g++) free(groups[g]);
     free(groups); free(gsz); free(gid); free(sel); free(S); free(valid); free(was); free(ids); free(rots); free(fc);
     free(T); free(gray);

@@ -22,7 +22,7 @@ class EmuParams(C.Structure):
 
 
 def build():
-    srcs = [os.path.join(_HERE, "hostemu.cpp")] + [os.path.join(_CSRC, f) for f in ("core.h", "frame_logic.h", "pose_core.h", "draw_core.h")] + [os.path.join(_CSRC, "..", "data", "overlay_tables.inc")]
+    srcs = [os.path.join(_HERE, "hostemu.cpp")] + [os.path.join(_CSRC, f) for f in ("core.h", "frame_logic.h", "pose_core.h", "draw_core.h", "refine_core.h")] + [os.path.join(_CSRC, "..", "data", "overlay_tables.inc")]
     if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", _SO, srcs[0]])
     return _SO
@@ -148,3 +148,12 @@ def draw(image, corners, ids=None, border=(0, 255, 0)):
     lib().emu_draw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib().emu_draw(P(img), W, H, ch, P(c), idp, len(c), P(b))
     return img
+
+
+def refine_lines(contour, corners):
+    """CORNER_REFINE_CONTOUR of one marker through refine_core.h: (ok, refined (4, 2) f32)"""
+    ct = np.ascontiguousarray(contour, np.int32).reshape(-1, 2)
+    cin = np.ascontiguousarray(corners, np.float32).reshape(8)
+    out = np.zeros(8, np.float32)
+    ok = lib().emu_refine_lines(ct.ctypes.data_as(C.c_void_p), len(ct), cin.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return bool(ok), out.reshape(4, 2)

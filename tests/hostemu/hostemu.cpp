@@ -7,6 +7,7 @@
 #include "../../aruco_slam_b200/csrc/frame_logic.h"
 #include "../../aruco_slam_b200/csrc/pose_core.h"
 #include "../../aruco_slam_b200/csrc/draw_core.h"
+#include "../../aruco_slam_b200/csrc/refine_core.h"
 
 #include <algorithm>
 #include <cmath>
@@ -352,6 +353,23 @@ void emu_draw(uint8_t *img, int W, int H, int channels, const float *corners, co
     static const OverlayTables t = make_overlay_tables();
     OverlayImage im{img, W, H, channels, (size_t)W * channels};
     overlay_draw_sequential(im, t, corners, ids, n, border);
+}
+
+// CORNER_REFINE_CONTOUR of one marker through the product's refine_core.h, one lane.  contour: n x (x, y)
+struct OneRefineLane {
+    int lane() const { return 0; }
+    int nlanes() const { return 1; }
+    uint32_t ballot(bool p) const { return p ? 1u : 0u; }
+    int bcast(int v, int) const { return v; }
+    long long sum(long long v) const { return v; }
+    int imin(int v) const { return v; }
+    int imax(int v) const { return v; }
+};
+int emu_refine_lines(const int32_t *contour, int n, const float *cin, float *cout)
+{
+    std::vector<uint32_t> P((size_t)n);
+    for (int i = 0; i < n; ++i) P[i] = (uint32_t)contour[2 * i] | ((uint32_t)contour[2 * i + 1] << 16);
+    return refine_marker_lines(OneRefineLane{}, P.data(), n, cin, cout) ? 1 : 0;
 }
 
 }  // extern "C"
