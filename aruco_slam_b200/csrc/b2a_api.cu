@@ -380,6 +380,7 @@ static int create_impl(b2a_detector *d)
     CU(cudaFuncSetAttribute(k_threshold_march<1, 6, 11, 24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmCfg<24>::SMEM));
     CU(cudaFuncSetAttribute(k_threshold_march<1, 6, 11, 12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmCfg<12>::SMEM));
     CU(cudaFuncSetAttribute(k_threshold_march<1, 6, 11, 12, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmCfg<12>::SMEM));
+    CU(cudaFuncSetAttribute(k_threshold_march<1, 6, 11, 12, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmCfg<12, true>::SMEM));
     if (const char *e = std::getenv("B2A_TM_VARIANT")) d->tm_variant = std::atoi(e);
     d->thresh_tiles = std::getenv("B2A_THRESH_TILES") != nullptr;          // A/B switch: the tiled kernel (k_threshold3) instead of the marching one
     CU(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (int)sizeof(int32_t) * d->max_cand));
@@ -545,14 +546,22 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     }
     if (s.tl_after_h2d) cudaEventRecord(s.tl_after_h2d, st);
     stage_mark(d, s, ST_GRAY);
-    if (f->channels == 3) {
-        uint8_t *gdst = d->d_gray + (size_t)b0 * d->gray_pitch * H;
-        k_bgr2gray<<<d->num_sms * 4, 256, 0, st>>>(src, src_pitch, src_frame, gdst, d->gray_pitch, d->gray_pitch * H, W, H, nb);
-        d->launches++;
-        s.gray = gdst; s.pitch = d->gray_pitch; s.frame_stride = d->gray_pitch * H;
-    } else { s.gray = src; s.pitch = src_pitch; s.frame_stride = src_frame; }
     s.g = make_geom(d, W, H, nb);
     DetGeom &g = s.g;
+    const bool default_windows = g.nScales == 3 && g.radius[0] == 1 && g.radius[1] == 6 && g.radius[2] == 11 && std::abs(g.Cfloor) <= 2048;
+    // bgr8 frames whose rows are whole words go straight into the marching threshold kernel, which converts on the fly and leaves the
+    // gray plane for the later stages (S0 fused into S1); anything else takes the separate conversion pass
+    static const bool fuse_env = !(std::getenv("B2A_FUSE_BGR") && std::atoi(std::getenv("B2A_FUSE_BGR")) == 0);
+    const bool fuse_bgr = f->channels == 3 && fuse_env && default_windows && !d->thresh_tiles && (W & 3) == 0 && (src_pitch & 3) == 0 && (src_frame & 3) == 0 &&
+                          (((size_t)src) & 3) == 0 && src_pitch < (1ull << 32);
+    if (f->channels == 3) {
+        uint8_t *gdst = d->d_gray + (size_t)b0 * d->gray_pitch * H;
+        if (!fuse_bgr) {
+            k_bgr2gray<<<d->num_sms * 4, 256, 0, st>>>(src, src_pitch, src_frame, gdst, d->gray_pitch, d->gray_pitch * H, W, H, nb);
+            d->launches++;
+        }
+        s.gray = gdst; s.pitch = d->gray_pitch; s.frame_stride = d->gray_pitch * H;
+    } else { s.gray = src; s.pitch = src_pitch; s.frame_stride = src_frame; }
     g.count_all = walk_max_len > 0 ? 1 : 0;          // the contour tap (exact counts, no give-up length) is the only caller that asks
     // this sub-batch's slice of the anchor arrays, and its per-(frame,scale) arrays addressed from frame b0
     const size_t fs0 = (size_t)b0 * g.nScales, FS = (size_t)nb * g.nScales;
@@ -575,9 +584,21 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     uint32_t *masks = d->d_masks + fs0 * g.mask_plane;
     stage_mark(d, s, ST_THRESH);
     {
-        const bool default_windows = g.nScales == 3 && g.radius[0] == 1 && g.radius[1] == 6 && g.radius[2] == 11 && std::abs(g.Cfloor) <= 2048;
         const bool aligned4 = (s.pitch & 3) == 0 && (s.frame_stride & 3) == 0 && (((size_t)s.gray) & 3) == 0 && s.pitch < (1ull << 32);
-        if (default_windows && aligned4 && !d->thresh_tiles) {
+        if (fuse_bgr) {
+            // same work items as below with 12-row chunks (the staged rows are three times as wide) at 4 CTAs per SM
+            const int n_sx = (W + TM_WT - 1) / TM_WT, slots = d->num_sms * 4;
+            int Hs = TM_RC;
+            double best = -1.0;
+            for (int h = TM_RC; h <= TM_MAX_HS; h += TM_RC) {
+                const int n = nb * n_sx * ((H + h - 1) / h);
+                const double score = (double)n / ((double)((n + slots - 1) / slots) * slots) / (1.0 + 0.3 * 22.0 / h);
+                if (score > best * 1.0001) { best = score; Hs = h; }
+            }
+            const int n_sy = (H + Hs - 1) / Hs, n_items = nb * n_sx * n_sy;
+            k_threshold_march<1, 6, 11, 12, 4, true><<<std::min(n_items, slots), TM_THREADS, TmCfg<12, true>::SMEM, st>>>(
+                src, (uint32_t)src_pitch, src_frame, masks, g, Hs, n_sy, n_sx, n_items, const_cast<uint8_t *>(s.gray), (uint32_t)s.pitch, s.frame_stride);
+        } else if (default_windows && aligned4 && !d->thresh_tiles) {
             // marching kernel: work items = (frame, 320-column strip, Hs-row segment); Hs is the tallest segment that still gives every
             // resident CTA slot an item (a segment costs 22 rows of prefix warm-up)
             const int ctas_per_sm = d->tm_variant == 0 ? 3 : d->tm_variant == 1 ? 4 : 5;

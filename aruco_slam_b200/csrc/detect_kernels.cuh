@@ -300,12 +300,15 @@ constexpr int TM_MAX_HS = 216;                        // (Hs + 22) * 255 < 2^16
 // RC = rows per chunk (24 or 12): the three u16 planes of a chunk are what shared memory holds, so 12-row chunks halve the
 // footprint (37 KB instead of 74 KB) and more CTAs share an SM; the H phase then covers a chunk with 12 rows x 10 segments of
 // 32 columns instead of 24 x 5 of 64.  The raw-row ring of the centre pixels holds two chunks.
-template <int RC> struct TmCfg {
+// BGR: the kernel reads bgr8 frames, converts on the fly (S0 of SURVEY 8(a)) and also leaves the gray plane for the later stages;
+// a staged row word is then three words (four pixels x 3 bytes).
+template <int RC, bool BGR = false> struct TmCfg {
     static_assert(RC == 24 || RC == 12, "chunk rows");
+    static constexpr int SW = BGR ? 3 : 1;                // staging words per (row, V thread)
     static constexpr int SEG = 64 * RC / 24;              // output columns of one H-phase thread
     static constexpr int NSEG = TM_WT / SEG;
     static constexpr int GROWS = 2 * RC;
-    static constexpr size_t SMEM = (size_t)3 * RC * TM_VPITCH + (size_t)GROWS * TM_GPITCH + (size_t)RC * TM_VG * 4;
+    static constexpr size_t SMEM = (size_t)3 * RC * TM_VPITCH + (size_t)GROWS * TM_GPITCH + (size_t)RC * TM_VG * 4 * SW;
     static_assert(RC * NSEG <= TM_THREADS, "thread roles");
 };
 constexpr int TM_RC = 24;                             // the chunk height the host sizes work items by (a multiple of both variants)
@@ -368,26 +371,60 @@ __device__ __forceinline__ void tm_cp_async4(uint32_t dst_shared, const void *sr
 __device__ __forceinline__ void tm_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tm_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// four bgr8 pixels (three words) -> four gray bytes, g = (3735 B + 19235 G + 9798 R + 16384) >> 15 (cv2's fixed point, bit-exact):
+// every pixel is two dp2a with doubled weights, so that the result sits in byte 2 of the sum and three byte permutes pack the word
+__device__ __forceinline__ uint32_t tm_dp2a_lo_u(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t tm_dp2a_hi_u(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t tm_bgr_to_gray4(uint32_t w0, uint32_t w1, uint32_t w2)
+{
+    constexpr uint32_t WB = 2 * 3735, WG = 2 * 19235, WR = 2 * 9798, RND = 2 * 16384;
+    // w0 = B0 G0 R0 B1, w1 = G1 R1 B2 G2, w2 = R2 B3 G3 R3 (byte 0 first)
+    const uint32_t s0 = tm_dp2a_hi_u(WR, w0, tm_dp2a_lo_u(WB | (WG << 16), w0, RND));
+    const uint32_t s1 = tm_dp2a_lo_u(WG | (WR << 16), w1, tm_dp2a_hi_u(WB << 16, w0, RND));
+    const uint32_t s2 = tm_dp2a_lo_u(WR, w2, tm_dp2a_hi_u(WB | (WG << 16), w1, RND));
+    const uint32_t s3 = tm_dp2a_hi_u(WG | (WR << 16), w2, tm_dp2a_lo_u(WB << 16, w2, RND));
+    return __byte_perm(__byte_perm(s0, s1, 0x4462), __byte_perm(s2, s3, 0x4462), 0x5410);
+}
+
 // shared-memory views and per-thread constants of one CTA
 struct TmCtx {
     uint8_t *pl0, *pl1, *pl2, *stash, *my_stash, *my_stage;
     uint32_t my_stage_s;
     int tid, wmax;
     bool vthread, stash_ok;
+    uint8_t *gdst;            // BGR only: this thread's word of image row Y0 + 11 in the gray plane (null: column outside the frame)
+    uint32_t gpitch;
 };
 
 // V phase of one chunk: the chunk's RC raw rows (already in the staging words) extend the prefix ring and leave the three
 // plane rows.  PAR = parity of the chunk: the ring position of a 12-row chunk ((first output row) mod 24) and the half of the
 // raw-row ring a chunk writes alternate, and the ring lives in registers, so the two parities are two instantiations.
-template <int R0, int R1, int R2, int RC, int PAR>
+// BGR: grows = how many of the chunk's rows are rows of this work item (their gray words go to the gray plane), m0 = first output row of the chunk
+template <int R0, int R1, int R2, int RC, int PAR, bool BGR>
 __device__ __forceinline__ void tm_v_chunk(const TmCtx &c, uint32_t (&Ce)[TM_RING], uint32_t (&Co)[TM_RING], uint32_t &ce, uint32_t &co,
-                                           uint32_t sel_e, uint32_t sel_o)
+                                           uint32_t sel_e, uint32_t sel_o, int m0, int grows)
 {
-    constexpr int G = TmCfg<RC>::GROWS, OFF = (RC * PAR) % TM_RING;
+    constexpr int G = TmCfg<RC>::GROWS, OFF = (RC * PAR) % TM_RING, SW = TmCfg<RC, BGR>::SW;
     uint32_t w[RC];
     tm_cp_async_wait_all();
 #pragma unroll
-    for (int u = 0; u < RC; ++u) w[u] = *reinterpret_cast<const volatile uint32_t *>(c.my_stage + u * (TM_VG * 4));
+    for (int u = 0; u < RC; ++u) {
+        const volatile uint32_t *sp = reinterpret_cast<const volatile uint32_t *>(c.my_stage + u * (TM_VG * 4 * SW));
+        if (BGR) {
+            w[u] = tm_bgr_to_gray4(sp[0], sp[1], sp[2]);
+            if (c.gdst && u < grows) *reinterpret_cast<uint32_t *>(c.gdst + (size_t)(m0 + u) * c.gpitch) = w[u];
+        } else w[u] = sp[0];
+    }
 #pragma unroll
     for (int u = 0; u < RC; ++u) {
         ce += __byte_perm(w[u], 0, sel_e); co += __byte_perm(w[u], 0, sel_o);
@@ -404,13 +441,15 @@ __device__ __forceinline__ void tm_v_chunk(const TmCtx &c, uint32_t (&Ce)[TM_RIN
 }
 
 // requires pitch, frame_stride and the base pointer to be multiples of 4 (the host checks and falls back to k_threshold3)
-template <int R0, int R1, int R2, int RC, int MINB>
+// BGR: `gray` points at bgr8 frames (pitch, frame_stride in bytes of that layout, W a multiple of 4) and the gray plane is written to gray_out
+template <int R0, int R1, int R2, int RC, int MINB, bool BGR = false>
 __global__ void __launch_bounds__(TM_THREADS, MINB)
 k_threshold_march(const uint8_t *__restrict__ gray, uint32_t pitch, size_t frame_stride, uint32_t *__restrict__ masks, DetGeom g,
-                  int Hs, int n_sy, int n_sx, int n_items)
+                  int Hs, int n_sy, int n_sx, int n_items, uint8_t *__restrict__ gray_out = nullptr, uint32_t gray_pitch = 0, size_t gray_frame = 0)
 {
     static_assert(R0 <= 11 && R1 <= 11 && R2 <= 11 && R0 >= 1 && R1 >= 1 && R2 >= 1, "radii");
-    using Cfg = TmCfg<RC>;
+    using Cfg = TmCfg<RC, BGR>;
+    constexpr int SW = Cfg::SW;
     constexpr int SEG = Cfg::SEG;
     extern __shared__ __align__(16) uint8_t tm_smem[];
     TmCtx c;
@@ -422,8 +461,9 @@ k_threshold_march(const uint8_t *__restrict__ gray, uint32_t pitch, size_t frame
     c.vthread = tid < TM_VG;
     c.stash_ok = tid >= TM_HALO / 4 && tid < TM_VG - TM_HALO / 4;
     c.my_stash = c.stash + 4 * (tid - TM_HALO / 4);
-    c.my_stage = stage + 4 * tid;
+    c.my_stage = stage + 4 * SW * tid;
     c.my_stage_s = (uint32_t)__cvta_generic_to_shared(c.my_stage);
+    c.gpitch = gray_pitch;
     const int rho = tid % RC, sigma = tid / RC;
     const bool hthread = tid < RC * Cfg::NSEG;
     const int bias0 = -(TmWin<R0>::K2 * g.Cfloor - (TmWin<R0>::K2 - 1) / 2);
@@ -450,7 +490,9 @@ k_threshold_march(const uint8_t *__restrict__ gray, uint32_t pitch, size_t frame
             sel_e = (uint32_t)bj[0] | 0x40u | ((uint32_t)bj[2] << 8) | 0x4000u;
             sel_o = (uint32_t)bj[1] | 0x40u | ((uint32_t)bj[3] << 8) | 0x4000u;
         }
-        const uint8_t *colp = gray + (size_t)b * frame_stride + 4 * (size_t)wc;
+        const uint8_t *colp = gray + (size_t)b * frame_stride + 4 * SW * (size_t)wc;
+        // the gray plane gets this item's own rows and columns (the V phase runs 11 rows ahead of the output rows)
+        c.gdst = (BGR && c.stash_ok && wcol <= c.wmax) ? gray_out + (size_t)b * gray_frame + (size_t)(Y0 + 11) * gray_pitch + 4 * (size_t)wcol : nullptr;
 
         // prefix ring: slot (j + 1) % 24 holds the column prefix through raw index j; slot 0 starts as C[-1] = 0
         uint32_t Ce[TM_RING], Co[TM_RING];
@@ -462,12 +504,15 @@ k_threshold_march(const uint8_t *__restrict__ gray, uint32_t pitch, size_t frame
             if (r_first >= 0 && r_first + RC - 1 <= g.H - 1) {                                // no clamping inside the frame
                 const uint8_t *p = colp + (size_t)((uint32_t)r_first * (uint64_t)pitch);
 #pragma unroll
-                for (int u = 0; u < RC; ++u) tm_cp_async4(c.my_stage_s + u * (TM_VG * 4), p + (size_t)((uint32_t)u * (uint64_t)pitch));
+                for (int u = 0; u < RC; ++u)
+#pragma unroll
+                    for (int k = 0; k < SW; ++k) tm_cp_async4(c.my_stage_s + u * (TM_VG * 4 * SW) + 4 * k, p + (size_t)((uint32_t)u * (uint64_t)pitch) + 4 * k);
             } else {
 #pragma unroll
                 for (int u = 0; u < RC; ++u) {
                     const int gy = min(max(r_first + u, 0), g.H - 1);
-                    tm_cp_async4(c.my_stage_s + u * (TM_VG * 4), colp + (size_t)((uint32_t)gy * (uint64_t)pitch));
+#pragma unroll
+                    for (int k = 0; k < SW; ++k) tm_cp_async4(c.my_stage_s + u * (TM_VG * 4 * SW) + 4 * k, colp + (size_t)((uint32_t)gy * (uint64_t)pitch) + 4 * k);
                 }
             }
             tm_cp_async_commit();
@@ -476,10 +521,29 @@ k_threshold_march(const uint8_t *__restrict__ gray, uint32_t pitch, size_t frame
             // chunk 0's rows (raw index 22 .. 22 + RC - 1) start towards shared memory, then the 22 warm-up rows come through registers
             prefetch(ytop + 22);
             uint32_t w[22];
+            if (BGR) {
 #pragma unroll
-            for (int i = 0; i < 22; ++i) {
-                const int gy = min(max(ytop + i, 0), g.H - 1);
-                w[i] = __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)((uint32_t)gy * (uint64_t)pitch)));
+                for (int i0 = 0; i0 < 22; i0 += 11) {                                           // two rounds of 33 loads in flight
+                    uint32_t t[33];
+#pragma unroll
+                    for (int i = 0; i < 11; ++i) {
+                        const int gy = min(max(ytop + i0 + i, 0), g.H - 1);
+                        const uint32_t *q = reinterpret_cast<const uint32_t *>(colp + (size_t)((uint32_t)gy * (uint64_t)pitch));
+                        t[3 * i] = __ldg(q); t[3 * i + 1] = __ldg(q + 1); t[3 * i + 2] = __ldg(q + 2);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 11; ++i) {
+                        w[i0 + i] = tm_bgr_to_gray4(t[3 * i], t[3 * i + 1], t[3 * i + 2]);
+                        // raw index i0 + i is image row Y0 - 11 + i0 + i: rows 11 .. 21 are this item's first output rows
+                        if (c.gdst && i0 + i >= 11 && i0 + i - 11 < rows) *reinterpret_cast<uint32_t *>(c.gdst + (ptrdiff_t)(i0 + i - 22) * (ptrdiff_t)gray_pitch) = w[i0 + i];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 22; ++i) {
+                    const int gy = min(max(ytop + i, 0), g.H - 1);
+                    w[i] = __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)((uint32_t)gy * (uint64_t)pitch)));
+                }
             }
 #pragma unroll
             for (int i = 0; i < 22; ++i) {
@@ -490,8 +554,9 @@ k_threshold_march(const uint8_t *__restrict__ gray, uint32_t pitch, size_t frame
         }
         for (int m0 = 0, par = 0; m0 < rows; m0 += RC, par ^= 1) {
             if (c.vthread) {
-                if (par == 0) tm_v_chunk<R0, R1, R2, RC, 0>(c, Ce, Co, ce, co, sel_e, sel_o);
-                else tm_v_chunk<R0, R1, R2, RC, 1>(c, Ce, Co, ce, co, sel_e, sel_o);
+                // chunk row u is image row Y0 + 11 + m0 + u: the item's own rows end at Y0 + rows - 1
+                if (par == 0) tm_v_chunk<R0, R1, R2, RC, 0, BGR>(c, Ce, Co, ce, co, sel_e, sel_o, m0, rows - 11 - m0);
+                else tm_v_chunk<R0, R1, R2, RC, 1, BGR>(c, Ce, Co, ce, co, sel_e, sel_o, m0, rows - 11 - m0);
                 if (m0 + RC < rows) prefetch(ytop + m0 + RC + 22);                            // the next chunk's rows fly during this chunk's H phase
             }
             __syncthreads();

@@ -226,6 +226,34 @@ def test_threshold_edge_shapes(aruco, oracle):
     det.close()
 
 
+def test_bgr_ingest_fused_into_threshold(aruco, oracle):
+    """bgr8 frames: the marching threshold kernel converts on the fly and writes the gray plane (widths that are multiples of 4);
+    other widths take the separate conversion pass.  Gray plane and masks against the oracle on random colour frames, batches,
+    multi-chunk work items and ragged last strips; detections on a rendered frame equal those of its gray version."""
+    rng = np.random.default_rng(21)
+    dic = D.getPredefinedDictionary(0)
+    for (H, W, B) in ((31, 36, 1), (130, 64, 2), (50, 324, 1), (26, 644, 3), (241, 8, 1), (700, 1000, 2), (95, 257, 1), (64, 130, 2)):
+        img = rng.integers(0, 256, (B, H, W, 3)).astype(np.uint8)
+        img[0, : H // 2] = (img[0, : H // 2] // 64) * 64 + 63            # flat areas too
+        det = _detector(aruco, dic, (H, W), batch=B)
+        gg, masks = det.debug_threshold(img if B > 1 else img[0])
+        for b in range(B):
+            want = oracle.bgr2gray(img[b])
+            assert np.array_equal(gg[b], want), (H, W, b)
+            for si, k in enumerate((3, 13, 23)):
+                assert np.array_equal(masks[b, si], oracle.adaptive_threshold(want, k, 7.0)), (H, W, b, k)
+        det.close()
+    fr = synth.render_config("C2", 5).image
+    bgr = synth.gray_to_bgr(fr, 3)
+    det = _detector(aruco, D.getPredefinedDictionary(10), fr.shape, batch=2)
+    r = det.detect_batch(np.stack([bgr, bgr[:, ::-1].copy()]))
+    oc, oi, orj = oracle.detect(bgr, D.getPredefinedDictionary(10))
+    assert len(oi) >= 25 and np.array_equal(r.ids[0], oi) and np.array_equal(r.corners[0], oc) and np.array_equal(r.rejected[0], orj)
+    oc, oi, orj = oracle.detect(bgr[:, ::-1].copy(), D.getPredefinedDictionary(10))
+    assert np.array_equal(r.ids[1], oi) and np.array_equal(r.corners[1], oc) and np.array_equal(r.rejected[1], orj)
+    det.close()
+
+
 def test_threshold_device_frames_pitches(aruco, oracle):
     """frames already in device memory: an unaligned row pitch takes the tiled kernel, a padded (4-byte aligned) pitch and a
     frame stride take the marching kernel; both must give the oracle's masks and the same detections as host frames"""
