@@ -1,0 +1,108 @@
+"""refineDetectedMarkers (cv::aruco::ArucoDetector::refineDetectedMarkers, part of the detectMarkers surface of reference
+src/aruco_slam.cpp:313): the numpy restatement (oracle/refine_np.py) and the product (b2a_refine_detected_markers)
+against what cv2 4.13 returned on the rendered, damaged GridBoard of tests/golden/refine_board.npz (tools/make_golden_refine.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from aruco_slam_b200 import dictionaries as D
+from oracle import oracle, refine_np
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "refine_board.npz"))
+CASES = [(str(n), tuple(p)) for n, p in zip(G["cases"], G["case_params"])]
+DIC = D.getPredefinedDictionary(int(G["dict_id"]))
+
+
+def same_as_cv2(name, c, i, r, rec):
+    assert np.array_equal(i, G[name + "/ids"])
+    assert np.array_equal(c, G[name + "/corners"])                 # recovered corners are the candidates' own, rotated: exact
+    assert np.array_equal(r, G[name + "/rejected"])
+    assert np.array_equal(rec, G[name + "/recovered"])
+
+
+def test_golden_has_every_kind_of_case():
+    n = [len(G[c + "/recovered"]) for c, _ in CASES]
+    assert 0 in n and 5 in n and 3 in n and 4 in n                # nothing, everything, and two partial recoveries
+
+
+def test_oracle_detect_is_the_starting_point():
+    c, i, r = oracle.detect(G["frame"], DIC)
+    assert np.array_equal(c, G["corners"]) and np.array_equal(i, G["ids"]) and np.array_equal(r, G["rejected"])
+
+
+@pytest.mark.parametrize("name,prm", CASES)
+def test_numpy_restatement_vs_cv2(name, prm):
+    rep, ecr, orders, cam = prm
+    out = refine_np.refine_detected_markers(G["frame"], DIC, G["board_ids"], G["board_obj"], G["corners"], G["ids"], G["rejected"],
+                                            K=G["K"] if cam else None, D=G["D"] if cam else None, min_rep_distance=rep,
+                                            error_correction_rate=ecr, check_all_orders=bool(orders))
+    same_as_cv2(name, *out)
+
+
+def test_numpy_restatement_edge_cases():
+    none = np.zeros((0, 4, 2), np.float32)
+    # nothing detected / nothing rejected: inputs come back untouched
+    c, i, r, rec = refine_np.refine_detected_markers(G["frame"], DIC, G["board_ids"], G["board_obj"], none, np.zeros(0, np.int32), G["rejected"])
+    assert len(i) == 0 and len(rec) == 0 and np.array_equal(r, G["rejected"])
+    c, i, r, rec = refine_np.refine_detected_markers(G["frame"], DIC, G["board_ids"], G["board_obj"], G["corners"], G["ids"], none)
+    assert np.array_equal(i, G["ids"]) and len(rec) == 0
+    # a board that shares no id with the detections: no homography, nothing recovered
+    c, i, r, rec = refine_np.refine_detected_markers(G["frame"], DIC, G["board_ids"] + 100, G["board_obj"], G["corners"], G["ids"], G["rejected"])
+    assert np.array_equal(i, G["ids"]) and len(rec) == 0
+    # homography / pose pieces against closed forms
+    H = np.array([[1.1, 0.02, 5.0], [-0.03, 0.95, -2.0], [1e-4, -2e-4, 1.0]])
+    src = np.random.default_rng(0).uniform(0, 100, (12, 2))
+    assert np.allclose(refine_np.find_homography(src, refine_np.perspective_transform(src, H)), H, atol=1e-9)
+    rv, tv = np.array([0.3, -0.2, 0.1]), np.array([0.05, -0.02, 0.6])
+    obj = np.c_[np.random.default_rng(1).uniform(-0.1, 0.1, (16, 2)), np.zeros(16)]
+    img = refine_np.project_points(obj, rv, tv, G["K"], G["D"])
+    r2, t2 = refine_np.solve_pnp_planar(obj, img, G["K"], G["D"])
+    assert np.allclose(r2, rv, atol=1e-8) and np.allclose(t2, tv, atol=1e-8)
+
+
+# ---- the product through the C ABI ----
+@pytest.fixture(scope="module")
+def aruco():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from aruco_slam_b200 import aruco as A
+    return A
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,prm", CASES)
+def test_gpu_refine_detected_markers_vs_cv2(aruco, name, prm):
+    rep, ecr, orders, cam = prm
+    det = aruco.ArucoDetector(DIC, aruco.DetectorParameters(), max_shape=G["frame"].shape, max_batch=1)
+    c, ids, rej = det.detectMarkers(G["frame"])
+    board = aruco.Board(G["board_obj"], G["board_ids"])
+    out = det.refineDetectedMarkers(G["frame"], board, c, ids, rej, cameraMatrix=G["K"] if cam else None, distCoeffs=G["D"] if cam else None,
+                                    refineParams=aruco.RefineParameters(rep, ecr, bool(orders)))
+    oc, oi, orj, rec = out
+    same_as_cv2(name, np.array(oc, np.float32).reshape(-1, 4, 2), np.asarray(oi, np.int32).ravel(), np.array(orj, np.float32).reshape(-1, 4, 2),
+                np.zeros(0, np.int32) if rec is None else np.asarray(rec, np.int32).ravel())
+    det.close()
+
+
+@pytest.mark.gpu
+def test_gpu_refine_detected_markers_edges(aruco):
+    det = aruco.ArucoDetector(DIC, aruco.DetectorParameters(), max_shape=G["frame"].shape, max_batch=1)
+    c, ids, rej = det.detectMarkers(G["frame"])
+    board = aruco.Board(G["board_obj"], G["board_ids"])
+    # bgr frame, same answer
+    bgr = np.repeat(G["frame"][..., None], 3, axis=2)
+    oc, oi, orj, rec = det.refineDetectedMarkers(bgr, board, c, ids, rej)
+    assert np.array_equal(np.asarray(oi).ravel(), G["h_default/ids"]) and np.array_equal(np.asarray(rec).ravel(), G["h_default/recovered"])
+    # nothing rejected / nothing detected: untouched, recovered None (cv2 returns without writing)
+    oc, oi, orj, rec = det.refineDetectedMarkers(G["frame"], board, c, ids, ())
+    assert rec is None and np.array_equal(np.asarray(oi).ravel(), G["ids"])
+    oc, oi, orj, rec = det.refineDetectedMarkers(G["frame"], board, (), None, rej)
+    assert rec is None and len(orj) == len(rej)
+    # a board in general position is not supported with a camera (cv2 would take its DLT branch)
+    obj = G["board_obj"].copy()
+    obj[::2, :, 2] += 0.05
+    with pytest.raises(Exception):
+        det.refineDetectedMarkers(G["frame"], aruco.Board(obj, G["board_ids"]), c, ids, rej, cameraMatrix=G["K"], distCoeffs=G["D"])
+    det.close()
