@@ -63,6 +63,14 @@ class Camera(C.Structure):
     _fields_ = [("K", C.c_double * 9), ("D", C.c_double * 5), ("nD", C.c_int), ("marker_length", C.c_float)]
 
 
+class Board(C.Structure):
+    _fields_ = [("n_markers", C.c_int), ("ids", C.c_void_p), ("obj_points", C.c_void_p)]
+
+
+class RefineParams(C.Structure):
+    _fields_ = [("minRepDistance", C.c_float), ("errorCorrectionRate", C.c_float), ("checkAllOrders", C.c_int)]
+
+
 class SlamParams(C.Structure):
     _fields_ = [("Q_k", C.c_double), ("R_x", C.c_double), ("R_y", C.c_double), ("R_theta", C.c_double),
                 ("kl", C.c_double), ("kr", C.c_double), ("b", C.c_double), ("r2c_tx", C.c_double), ("r2c_ty", C.c_double),
@@ -94,6 +102,7 @@ SYMBOLS = [
     "b2a_quaternion_from_rpy", "b2a_map_parse", "b2a_map_load", "b2a_slam_robot_pose", "b2a_slam_detected_map",
     "b2a_pack_robot_pose", "b2a_pack_map_marker", "b2a_slam_stream",
     "b2a_multi_create", "b2a_multi_destroy", "b2a_multi_num_devices", "b2a_multi_detect_pose", "b2a_draw_detected_markers", "b2a_detector_last_detections", "b2a_pack_detections",
+    "b2a_default_refine_params", "b2a_refine_detected_markers",
 ]
 
 _lib = None
@@ -144,6 +153,10 @@ def lib():
         L.b2a_detect_pose_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2a_detect_pose_wait.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.b2a_estimate_pose_single_markers.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2a_default_refine_params.argtypes = [C.c_void_p]
+        L.b2a_default_refine_params.restype = None
+        L.b2a_refine_detected_markers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2a_debug_threshold.argtypes = [C.c_void_p] * 4
         L.b2a_debug_contours.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.b2a_debug_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]

@@ -75,6 +75,29 @@ class BatchDetections:
     tvecs: list | None = None
 
 
+class Board:
+    """cv2.aruco.Board: object points (n, 4, 3) of every marker's corners and the markers' ids"""
+
+    def __init__(self, objPoints, ids):
+        self.objPoints = np.ascontiguousarray(np.asarray(objPoints, np.float32).reshape(-1, 4, 3))
+        self.ids = np.ascontiguousarray(np.asarray(ids, np.int32).ravel())
+        if len(self.ids) != len(self.objPoints):
+            raise B2AError(1, "objPoints and ids differ in length")
+
+    def getObjPoints(self):
+        return self.objPoints
+
+    def getIds(self):
+        return self.ids
+
+
+class RefineParameters:
+    """cv2.aruco.RefineParameters"""
+
+    def __init__(self, minRepDistance=10.0, errorCorrectionRate=3.0, checkAllOrders=True):
+        self.minRepDistance, self.errorCorrectionRate, self.checkAllOrders = float(minRepDistance), float(errorCorrectionRate), bool(checkAllOrders)
+
+
 class ArucoDetector:
     """One detector handle (one GPU, one stream).  `max_shape` = (H, W) of the largest frame."""
 
@@ -188,6 +211,33 @@ class ArucoDetector:
     def detect_pose_batch(self, images, marker_length, K, D) -> BatchDetections:
         fr, keep = self._frames_host(images) if not isinstance(images, _lib.Frames) else (images, None)
         return self._collect(self.detect_raw(fr, _camera(K, D, marker_length)), True)
+
+    def refineDetectedMarkers(self, image, board, detectedCorners, detectedIds, rejectedCorners, cameraMatrix=None, distCoeffs=None,
+                              refineParams=None):
+        """cv2.aruco.ArucoDetector.refineDetectedMarkers: -> (corners, ids, rejected, recoveredIdxs) shaped like cv2's
+        (recoveredIdxs None when nothing was recovered, as cv2 leaves its output untouched then)"""
+        fr, keep = self._frames_host(image)
+        c = np.array([np.asarray(q, np.float32).reshape(4, 2) for q in detectedCorners], np.float32).reshape(-1, 4, 2)
+        i = np.zeros(0, np.int32) if detectedIds is None else np.asarray(detectedIds, np.int32).ravel()
+        r = np.array([np.asarray(q, np.float32).reshape(4, 2) for q in rejectedCorners], np.float32).reshape(-1, 4, 2)
+        nd, nr = len(i), len(r)
+        cap = nd + nr + 1
+        cbuf = np.zeros((cap, 4, 2), np.float32); cbuf[:nd] = c
+        ibuf = np.zeros(cap, np.int32); ibuf[:nd] = i
+        rbuf = np.ascontiguousarray(r) if nr else np.zeros((1, 4, 2), np.float32)
+        rec = np.zeros(max(nr, 1), np.int32)
+        n_d, n_r, n_rec = C.c_int(nd), C.c_int(nr), C.c_int(0)
+        cam = _camera(cameraMatrix, distCoeffs if distCoeffs is not None else np.zeros(5), 1.0) if cameraMatrix is not None else None
+        rp = refineParams or RefineParameters()
+        prm = _lib.RefineParams(float(rp.minRepDistance), float(rp.errorCorrectionRate), int(bool(rp.checkAllOrders)))
+        bd = _lib.Board(len(board.ids), board.ids.ctypes.data, board.objPoints.ctypes.data)
+        _lib.check(_lib.lib().b2a_refine_detected_markers(self._h, C.byref(fr), C.byref(bd), cbuf.ctypes.data, ibuf.ctypes.data, C.byref(n_d), cap,
+                                                          rbuf.ctypes.data, C.byref(n_r), C.byref(cam) if cam is not None else None, C.byref(prm),
+                                                          rec.ctypes.data, C.byref(n_rec)))
+        corners = tuple(q.reshape(1, 4, 2).copy() for q in cbuf[:n_d.value])
+        ids = ibuf[:n_d.value].reshape(-1, 1).copy() if n_d.value else None
+        rejected = tuple(q.reshape(1, 4, 2).copy() for q in rbuf[:n_r.value]) if nr else ()
+        return corners, ids, rejected, (rec[:n_rec.value].reshape(-1, 1).copy() if n_rec.value else None)
 
     # ---- cv2-shaped single-image API -----------------------------------------------------------
     def detectMarkers(self, image):

@@ -4,6 +4,7 @@
 // create calls fail.
 #include "../../include/b2aruco.h"
 #include "detect_kernels.cuh"
+#include "board_core.h"
 #include "ekf_kernels.cuh"
 #include "pose_core.h"
 #include "draw_core.h"
@@ -225,6 +226,7 @@ struct b2a_detector {
     uint8_t *d_quad_ok = nullptr; int32_t *d_quad_xy = nullptr, *d_quad_len = nullptr;
     unsigned long long *d_dict = nullptr;
     double *d_wM = nullptr;                   // inverse perspective map of every identification work item
+    unsigned long long *d_idcodes = nullptr;  // refineDetectedMarkers: extracted inner bits of one frame's work items
     WalkTables *d_tables = nullptr;
     FrameScratch fs0{};                       // frame-0 pointers
     FrameOutputs fo0{};
@@ -364,6 +366,7 @@ static int create_impl(b2a_detector *d)
     TRY(dev_alloc(d, &fs.wq, BM * 8)); TRY(dev_alloc(d, &fs.wres, BM)); TRY(dev_alloc(d, &fs.closeStart, BM)); TRY(dev_alloc(d, &fs.closeNum, BM));
     TRY(dev_alloc(d, &fs.counters, (size_t)B * 8));
     TRY(dev_alloc(d, &d->d_wM, BM * 9));
+    TRY(dev_alloc(d, &d->d_idcodes, (size_t)d->max_cand));
     const size_t BK = (size_t)B * d->max_markers;
     FrameOutputs &fo = d->fo0;
     TRY(dev_alloc(d, &fo.n_accepted, B)); TRY(dev_alloc(d, &fo.n_rejected, B)); TRY(dev_alloc(d, &fo.status, B));
@@ -716,7 +719,7 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
     ip.maxBorderErr = (int)(d->dict.markerSize * d->dict.markerSize * d->prm.maxErroneousBitsInBorderRate);
     ip.detectInverted = d->prm.detectInvertedMarker ? 1 : 0;
     ip.minOtsuStdDev = d->prm.minOtsuStdDev; ip.W = g.W; ip.H = g.H; ip.pitch = s.pitch; ip.frame_stride = s.frame_stride; ip.max_cand = d->max_cand;
-    ip.marks = nullptr;
+    ip.marks = nullptr; ip.codes = nullptr;
 #ifdef B2A_DEBUG_TAPS
     static long long *id_marks = nullptr;
     if (std::getenv("B2A_IDENT_MARKS") && s.sb == 0) {
@@ -1227,6 +1230,205 @@ extern "C" int b2a_detector_set_streams(b2a_detector *d, int n)
 {
     if (!d || n < 0) return set_err(B2A_ERR_INVALID, "streams must be >= 0 (0 = automatic)");
     d->n_streams = std::min(n, d->n_sub_max);
+    return B2A_OK;
+}
+
+// ---- refineDetectedMarkers ----------------------------------------------------------------------------------------------
+extern "C" void b2a_default_refine_params(b2a_refine_params *p) { p->minRepDistance = 10.f; p->errorCorrectionRate = 3.f; p->checkAllOrders = 1; }
+
+// the inner bits of every (rejected candidate, corner order) of one frame: the identification kernels run on a work list
+// written by the host into frame slot 0 (the detector's results of its last call are overwritten)
+static int refine_extract_codes(b2a_detector *d, const b2a_frames *f, const float *rejected, int n_rej, std::vector<unsigned long long> &codes)
+{
+    const int W = f->width, H = f->height, nw = 4 * n_rej;
+    if (nw > d->max_cand) return set_err(B2A_ERR_CAPACITY, "4 x rejected candidates exceed max_candidates");
+    cudaStream_t st = d->stream;
+    const size_t in_pitch = f->row_stride ? f->row_stride : (size_t)W * f->channels;
+    const uint8_t *src = f->data;
+    size_t src_pitch = in_pitch;
+    if (!f->on_device) {
+        const size_t rowbytes = (size_t)W * f->channels;
+        CU(cudaMemcpy2DAsync(d->d_in, rowbytes, f->data, in_pitch, rowbytes, H, cudaMemcpyHostToDevice, st));
+        src = d->d_in; src_pitch = rowbytes;
+    }
+    const uint8_t *gray = src;
+    size_t gpitch = src_pitch;
+    if (f->channels == 3) {
+        k_bgr2gray<<<d->num_sms * 4, 256, 0, st>>>(src, src_pitch, src_pitch * H, d->d_gray, d->gray_pitch, d->gray_pitch * H, W, H, 1);
+        gray = d->d_gray; gpitch = d->gray_pitch;
+    }
+    std::vector<float> wq((size_t)nw * 8);
+    for (int j = 0; j < n_rej; ++j)
+        for (int c = 0; c < 4; ++c)
+            for (int k = 0; k < 4; ++k) { wq[((size_t)j * 4 + c) * 8 + 2 * k] = rejected[j * 8 + 2 * ((c + k) & 3)]; wq[((size_t)j * 4 + c) * 8 + 2 * k + 1] = rejected[j * 8 + 2 * ((c + k) & 3) + 1]; }
+    int counters[8] = {0, 0, nw, 0, 0, 0, 0, 0};
+    CU(cudaMemcpyAsync(d->fs0.wq, wq.data(), wq.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d->fs0.counters, counters, sizeof(counters), cudaMemcpyHostToDevice, st));
+    FrameArrays fa;
+    fa.fs0 = d->fs0; fa.fo0 = d->fo0; fa.fo0.status = d->d_status;
+    fa.surv_count = d->d_surv_count; fa.quad_ok = d->d_quad_ok; fa.quad_xy = d->d_quad_xy; fa.quad_len = d->d_quad_len; fa.marks = nullptr;
+    IdentParams ip;
+    ip.markerSize = d->dict.markerSize; ip.borderBits = d->prm.markerBorderBits; ip.cellSize = d->prm.perspectiveRemovePixelPerCell;
+    ip.cellMargin = (int)(d->prm.perspectiveRemoveIgnoredMarginPerCell * ip.cellSize);
+    ip.nMarkers = d->dict.nMarkers; ip.maxCorr = 0; ip.maxBorderErr = -1;            // only the extracted bits are wanted: no dictionary scan
+    ip.detectInverted = 0; ip.minOtsuStdDev = d->prm.minOtsuStdDev; ip.W = W; ip.H = H; ip.pitch = gpitch; ip.frame_stride = gpitch * H; ip.max_cand = d->max_cand;
+    ip.marks = nullptr;
+    unsigned long long *d_codes = d->d_idcodes;
+    ip.codes = d_codes;
+    const int S = (ip.markerSize + 2 * ip.borderBits) * ip.cellSize;
+    k_homography<<<dim3(4, 1), 64, 0, st>>>(fa, d->d_wM, S, d->max_cand);
+    k_identify<<<dim3(48, 1), ID_THREADS, identify_smem_bytes(S), st>>>(gray, d->d_dict, d->d_wM, fa, ip);
+    codes.resize((size_t)nw);
+    CU(cudaMemcpyAsync(codes.data(), d_codes, (size_t)nw * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    d->last_call_batch = 0;
+    return launch_err("refine: bit extraction");
+}
+
+extern "C" int b2a_refine_detected_markers(b2a_detector *d, const b2a_frames *image, const b2a_board *board, float *corners, int32_t *ids, int *n_detected,
+                                           int capacity, float *rejected, int *n_rejected, const b2a_camera *cam, const b2a_refine_params *rp_in,
+                                           int32_t *recovered_idx, int *n_recovered)
+{
+    if (!d || !image || !board || !corners || !ids || !n_detected || !rejected || !n_rejected) return set_err(B2A_ERR_INVALID, "null argument");
+    if (n_recovered) *n_recovered = 0;
+    b2a_refine_params rp;
+    if (rp_in) rp = *rp_in; else b2a_default_refine_params(&rp);
+    if (!(rp.minRepDistance > 0)) return set_err(B2A_ERR_INVALID, "minRepDistance must be positive");            // CV_Assert in refineDetectedMarkers
+    if (board->n_markers <= 0 || !board->ids || !board->obj_points) return set_err(B2A_ERR_INVALID, "empty board");
+    if (image->batch != 1) return set_err(B2A_ERR_INVALID, "refineDetectedMarkers takes one image");
+    TRY(check_frames(d, image));
+    const int nd = *n_detected, nr = *n_rejected, nbm = board->n_markers;
+    if (nd < 0 || nr < 0 || nd > capacity) return set_err(B2A_ERR_INVALID, "bad counts");
+    if (nd == 0 || nr == 0) return B2A_OK;
+    CU(cudaSetDevice(d->device));
+    // ---- where the undetected markers of the board should be (board_core.h) ----
+    std::vector<int> und;                                   // board entries without a detection, board order
+    std::vector<float> und_c;                               // their projected corners, Point2f like cv2's vectors
+    auto detected = [&](int id) { for (int i = 0; i < nd; ++i) if (ids[i] == id) return i; return -1; };
+    if (!cam) {
+        const float z0 = board->obj_points[2];
+        for (int i = 0; i < nbm * 4; ++i) if (board->obj_points[3 * i + 2] != z0) return set_err(B2A_ERR_INVALID, "board points must share one z for the homography form");
+        std::vector<double> src, dst;
+        for (int j = 0; j < nbm; ++j) {
+            const int i = detected(board->ids[j]);
+            if (i < 0) { und.push_back(j); continue; }
+            for (int c = 0; c < 4; ++c) {
+                src.push_back(board->obj_points[(j * 4 + c) * 3]); src.push_back(board->obj_points[(j * 4 + c) * 3 + 1]);
+                dst.push_back(corners[i * 8 + 2 * c]); dst.push_back(corners[i * 8 + 2 * c + 1]);
+            }
+        }
+        if (dst.empty() || und.empty()) return B2A_OK;
+        double Hm[9];
+        if (!homography_ls(src.data(), dst.data(), (int)dst.size() / 2, Hm, 10)) return set_err(B2A_ERR_INVALID, "degenerate homography");
+        for (int j : und)
+            for (int c = 0; c < 4; ++c) {
+                double x, y;
+                homography_apply(Hm, board->obj_points[(j * 4 + c) * 3], board->obj_points[(j * 4 + c) * 3 + 1], x, y);
+                und_c.push_back((float)x); und_c.push_back((float)y);
+            }
+    } else {
+        std::vector<double> obj, img;
+        for (int i = 0; i < nd; ++i) {                      // Board::matchImagePoints: detection order
+            int j = -1;
+            for (int k = 0; k < nbm; ++k) if (board->ids[k] == ids[i]) { j = k; break; }
+            if (j < 0) continue;
+            for (int c = 0; c < 4; ++c) {
+                for (int k = 0; k < 3; ++k) obj.push_back(board->obj_points[(j * 4 + c) * 3 + k]);
+                img.push_back(corners[i * 8 + 2 * c]); img.push_back(corners[i * 8 + 2 * c + 1]);
+            }
+        }
+        if (img.size() / 2 < 4) return B2A_OK;
+        for (int j = 0; j < nbm; ++j) if (detected(board->ids[j]) < 0) und.push_back(j);
+        if (und.empty()) return B2A_OK;
+        double rvec[3], tvec[3], R[9];
+        const Camera c = to_camera(cam);
+        const int rc = board_pose_planar(c, obj.data(), img.data(), (int)img.size() / 2, rvec, tvec);
+        if (rc == 2) return set_err(B2A_ERR_UNSUPPORTED, "board corners are not coplanar (camera form)");
+        if (rc) return set_err(B2A_ERR_INVALID, "degenerate board pose");
+        rodrigues_to_R(rvec, R);
+        for (int j : und)
+            for (int k = 0; k < 4; ++k) {
+                const double X[3] = {board->obj_points[(j * 4 + k) * 3], board->obj_points[(j * 4 + k) * 3 + 1], board->obj_points[(j * 4 + k) * 3 + 2]};
+                double u, v;
+                project_point(c, R, tvec, X, u, v);
+                und_c.push_back((float)u); und_c.push_back((float)v);
+            }
+    }
+    // ---- bits of every candidate in its four corner orders (GPU) ----
+    std::vector<unsigned long long> codes;
+    if (rp.errorCorrectionRate >= 0 || d->prm.cornerRefinementMethod == 1) TRY(refine_extract_codes(d, image, rejected, nr, codes));   // also brings the gray frame to the device
+    const int maxCorr = (int)((double)d->dict.maxCorrectionBits * (double)rp.errorCorrectionRate);
+    auto dict_code = [&](int id) {
+        unsigned long long v = 0;
+        for (int k = 0; k < d->dict.nBytes; ++k) v |= (unsigned long long)d->dict_bytes[((size_t)id * 4) * d->dict.nBytes + k] << (8 * k);
+        return v;
+    };
+    // ---- the greedy loop of refineDetectedMarkers ----
+    std::vector<char> taken((size_t)nr, 0);
+    std::vector<int> rec;
+    int n_out = nd;
+    for (size_t u = 0; u < und.size(); ++u) {
+        const int uid = board->ids[und[u]];
+        const float *uc = und_c.data() + u * 8;
+        int bestj = -1, bestrot = 0;
+        double bestd = (double)rp.minRepDistance * (double)rp.minRepDistance + 1;
+        for (int j = 0; j < nr; ++j) {
+            if (taken[j]) continue;
+            bool valid = false;
+            int rot = 0;
+            double mind = bestd + 1;
+            for (int c = 0; c < 4; ++c) {                    // the last corner order that beats the best so far stays (cv2 keeps overwriting)
+                double cur = 0;
+                for (int k = 0; k < 4; ++k) {
+                    const float dx = uc[2 * k] - rejected[j * 8 + 2 * ((c + k) & 3)], dy = uc[2 * k + 1] - rejected[j * 8 + 2 * ((c + k) & 3) + 1];
+                    const double dd = (double)(dx * dx + dy * dy);
+                    if (dd > cur) cur = dd;
+                }
+                if (cur < bestd) { valid = true; rot = c; mind = cur; }
+                if (!rp.checkAllOrders) break;
+            }
+            if (!valid) continue;
+            int dist = 0;
+            if (rp.errorCorrectionRate >= 0) {
+                if (uid < 0 || uid >= d->dict.nMarkers) return set_err(B2A_ERR_INVALID, "board id outside the dictionary");
+                dist = popc64(codes[(size_t)j * 4 + (rp.checkAllOrders ? rot : 0)] ^ dict_code(uid));
+            }
+            if (rp.errorCorrectionRate < 0 || dist < maxCorr) { bestj = j; bestd = mind; bestrot = rp.checkAllOrders ? rot : 0; }
+        }
+        if (bestj < 0) continue;
+        if (n_out >= capacity) return set_err(B2A_ERR_CAPACITY, "detected markers exceed the caller's capacity");
+        taken[bestj] = 1;
+        for (int k = 0; k < 4; ++k) { corners[n_out * 8 + 2 * k] = rejected[bestj * 8 + 2 * ((bestrot + k) & 3)]; corners[n_out * 8 + 2 * k + 1] = rejected[bestj * 8 + 2 * ((bestrot + k) & 3) + 1]; }
+        ids[n_out++] = uid;
+        rec.push_back(bestj);
+    }
+    if (rec.empty()) return B2A_OK;
+    // recovered corners get the detector's sub-pixel refinement, like accepted ones
+    if (d->prm.cornerRefinementMethod == 1) {
+        const int m = (int)rec.size();
+        cudaStream_t st = d->stream;
+        const int32_t cnt = m;
+        CU(cudaMemcpyAsync(d->fo0.corners, corners + (size_t)nd * 8, (size_t)m * 8 * sizeof(float), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d->fo0.n_accepted, &cnt, sizeof(cnt), cudaMemcpyHostToDevice, st));
+        SubpixParams sp;
+        const bool bgr = image->channels == 3;
+        const size_t gp = bgr ? d->gray_pitch : (image->on_device ? (image->row_stride ? image->row_stride : (size_t)image->width) : (size_t)image->width);
+        sp.W = image->width; sp.H = image->height; sp.pitch = gp; sp.frame_stride = gp * image->height; sp.max_markers = d->max_markers;
+        sp.markerSize = d->dict.markerSize; sp.borderBits = d->prm.markerBorderBits; sp.maxWin = d->prm.cornerRefinementWinSize;
+        sp.maxIter = d->prm.cornerRefinementMaxIterations; sp.relWin = d->prm.relativeCornerRefinmentWinSize; sp.eps = d->prm.cornerRefinementMinAccuracy;
+        const uint8_t *gray = bgr ? d->d_gray : (image->on_device ? image->data : d->d_in);
+        if (m > d->max_markers) return set_err(B2A_ERR_CAPACITY, "recovered markers exceed max_markers");
+        k_subpix<<<d->num_sms * 2, 128, 0, st>>>(gray, d->fo0.n_accepted, d->fo0.corners, d->d_corners2, 1, sp);
+        CU(cudaMemcpyAsync(corners + (size_t)nd * 8, d->d_corners2, (size_t)m * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        TRY(launch_err("refine: k_subpix"));
+    }
+    // rejected list without the recovered candidates, order kept
+    int w = 0;
+    for (int j = 0; j < nr; ++j) if (!taken[j]) { if (w != j) std::memmove(rejected + (size_t)w * 8, rejected + (size_t)j * 8, 8 * sizeof(float)); ++w; }
+    *n_rejected = w; *n_detected = n_out;
+    for (size_t k = 0; k < rec.size(); ++k) if (recovered_idx) recovered_idx[k] = rec[k];
+    if (n_recovered) *n_recovered = (int)rec.size();
     return B2A_OK;
 }
 

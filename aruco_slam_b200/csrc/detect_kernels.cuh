@@ -1400,6 +1400,7 @@ struct IdentParams {
     size_t pitch, frame_stride;
     int max_cand;
     long long *marks;            // debug: clock64 after each phase of work item 0 of frame 0 (null = off)
+    unsigned long long *codes;   // optional [frames][max_cand]: every work item's inner bits as extracted (before the inverted-marker choice)
 };
 
 // A7 step 1: the inverse perspective map of every work item, one thread each (cv2's 8x8 LU lives in
@@ -1566,6 +1567,7 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
         }
         berr = __reduce_add_sync(FULL, berr);
         code = ((unsigned long long)__reduce_or_sync(FULL, (unsigned)(code >> 32)) << 32) | __reduce_or_sync(FULL, (unsigned)code);
+        if (ip.codes && lane == 0) ip.codes[(size_t)f * ip.max_cand + w] = code;
         if (ip.detectInverted) ident_choose_inverted(ip.markerSize, ip.borderBits, berr, code);
         const int ok = berr <= ip.maxBorderErr;
         int best_m = 0x7FFFFFFF;

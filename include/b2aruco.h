@@ -172,6 +172,31 @@ void b2a_multi_destroy(b2a_multi *m);
 int  b2a_multi_num_devices(const b2a_multi *m);
 int  b2a_multi_detect_pose(b2a_multi *m, const b2a_frames *frames, const b2a_camera *cam, b2a_detections *out);
 
+/* ---- cv::aruco::ArucoDetector::refineDetectedMarkers (cv2 4.13; part of the cv::aruco surface of aruco_slam.cpp:313, the reference
+ * itself does not call it).  Rejected candidates that lie where the board says an undetected marker must be are moved to the
+ * detected list.  board: cv::aruco::Board (ids + object points of every marker's four corners); cam null = the global-homography
+ * form (all board points must share one z), else the board pose is fitted through the camera (coplanar boards; a board in
+ * general position -> B2A_ERR_UNSUPPORTED).  corners / ids / rejected are host arrays, edited in place like cv2's
+ * InputOutputArrays: recovered markers are appended in board order with the candidate's corners rotated to the matching order
+ * (and refined when the detector was created with CORNER_REFINE_SUBPIX), the recovered candidates leave `rejected`;
+ * recovered_idx (optional, room for *n_rejected entries) gets their indices in the incoming rejected list.
+ * The bit extraction of the candidates runs on the GPU (the identification kernels); it overwrites the detector's results of its
+ * last detect call.  Errors: B2A_ERR_CAPACITY when 4 * n_rejected exceeds max_candidates or the outputs exceed `capacity`. */
+typedef struct {
+    int n_markers;
+    const int32_t *ids;          /* [n_markers] */
+    const float *obj_points;     /* [n_markers][4][3], Board::getObjPoints order */
+} b2a_board;
+typedef struct {                 /* cv::aruco::RefineParameters */
+    float minRepDistance;        /* 10 */
+    float errorCorrectionRate;   /* 3; negative = no code test */
+    int   checkAllOrders;        /* 1 */
+} b2a_refine_params;
+void b2a_default_refine_params(b2a_refine_params *p);
+int b2a_refine_detected_markers(b2a_detector *d, const b2a_frames *image, const b2a_board *board, float *corners, int32_t *ids,
+                                int *n_detected, int capacity, float *rejected, int *n_rejected, const b2a_camera *cam,
+                                const b2a_refine_params *params, int32_t *recovered_idx, int *n_recovered);
+
 /* estimatePoseSingleMarkers on caller-provided corners (host arrays): corners [n][4][2] f32,
  * rvecs/tvecs [n][3] f64.  (aruco_slam.cpp:314) */
 int b2a_estimate_pose_single_markers(b2a_detector *d, const float *corners, int n, const b2a_camera *cam,

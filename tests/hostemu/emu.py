@@ -22,7 +22,7 @@ class EmuParams(C.Structure):
 
 
 def build():
-    srcs = [os.path.join(_HERE, "hostemu.cpp")] + [os.path.join(_CSRC, f) for f in ("core.h", "frame_logic.h", "pose_core.h", "draw_core.h", "refine_core.h")] + [os.path.join(_CSRC, "..", "data", "overlay_tables.inc")]
+    srcs = [os.path.join(_HERE, "hostemu.cpp")] + [os.path.join(_CSRC, f) for f in ("core.h", "frame_logic.h", "pose_core.h", "draw_core.h", "refine_core.h", "board_core.h")] + [os.path.join(_CSRC, "..", "data", "overlay_tables.inc")]
     if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", _SO, srcs[0]])
     return _SO
@@ -157,3 +157,22 @@ def refine_lines(contour, corners):
     out = np.zeros(8, np.float32)
     ok = lib().emu_refine_lines(ct.ctypes.data_as(C.c_void_p), len(ct), cin.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
     return bool(ok), out.reshape(4, 2)
+
+
+def homography(src, dst, refine_iters=10):
+    s = np.ascontiguousarray(src, np.float64).reshape(-1, 2)
+    d = np.ascontiguousarray(dst, np.float64).reshape(-1, 2)
+    H = np.zeros(9)
+    ok = lib().emu_homography(s.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), len(s), H.ctypes.data_as(C.c_void_p), int(refine_iters))
+    return bool(ok), H.reshape(3, 3)
+
+
+def board_pose(K, D, obj, img):
+    K9 = np.ascontiguousarray(K, np.float64).reshape(9)
+    D5 = np.r_[np.asarray(D, np.float64).ravel(), np.zeros(5)][:5].copy()
+    o = np.ascontiguousarray(obj, np.float64).reshape(-1, 3)
+    i = np.ascontiguousarray(img, np.float64).reshape(-1, 2)
+    r, t = np.zeros(3), np.zeros(3)
+    rc = lib().emu_board_pose(K9.ctypes.data_as(C.c_void_p), D5.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p), i.ctypes.data_as(C.c_void_p), len(o),
+                              r.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p))
+    return rc, r, t

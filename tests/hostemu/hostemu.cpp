@@ -8,6 +8,7 @@
 #include "../../aruco_slam_b200/csrc/pose_core.h"
 #include "../../aruco_slam_b200/csrc/draw_core.h"
 #include "../../aruco_slam_b200/csrc/refine_core.h"
+#include "../../aruco_slam_b200/csrc/board_core.h"
 
 #include <algorithm>
 #include <cmath>
@@ -370,6 +371,14 @@ int emu_refine_lines(const int32_t *contour, int n, const float *cin, float *cou
     std::vector<uint32_t> P((size_t)n);
     for (int i = 0; i < n; ++i) P[i] = (uint32_t)contour[2 * i] | ((uint32_t)contour[2 * i + 1] << 16);
     return refine_marker_lines(OneRefineLane{}, P.data(), n, cin, cout) ? 1 : 0;
+}
+
+// board_core.h: the least-squares homography and the planar board pose
+int emu_homography(const double *src, const double *dst, int n, double *H, int refine_iters) { return homography_ls(src, dst, n, H, refine_iters) ? 1 : 0; }
+int emu_board_pose(const double *K9, const double *D5, const double *obj, const double *img, int n, double *rvec, double *tvec)
+{
+    Camera cam{K9[0], K9[4], K9[2], K9[5], D5[0], D5[1], D5[2], D5[3], D5[4]};
+    return board_pose_planar(cam, obj, img, n, rvec, tvec);
 }
 
 }  // extern "C"

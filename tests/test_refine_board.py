@@ -3,8 +3,12 @@ src/aruco_slam.cpp:313): the numpy restatement (oracle/refine
 against what cv2 4.13 returned on the rendered, damaged GridBoard of tests/golden/refine_board.npz (tools/make_golden_refine.py)."""
 import os
 
+import sys
+
 import numpy as np
 import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
 
 from aruco_slam_b200 import dictionaries as D
 from oracle import oracle, refine_np
@@ -40,6 +44,17 @@ def test_numpy_restatement_vs_cv2(name, prm):
     same_as_cv2(name, *out)
 
 
+def test_numpy_restatement_subpix_vs_cv2():
+    p = oracle.default_params()
+    p.cornerRefinementMethod = 1
+    c, i, r, rec = refine_np.refine_detected_markers(G["frame"], DIC, G["board_ids"], G["board_obj"], G["subpix/in_corners"], G["subpix/in_ids"],
+                                                     G["subpix/in_rejected"], params=p)
+    assert np.array_equal(i, G["subpix/ids"]) and np.array_equal(rec, G["subpix/recovered"]) and np.array_equal(r, G["subpix/rejected"])
+    assert np.abs(c - G["subpix/corners"]).max() < 0.05 and len(rec) == 5
+    n0 = len(G["subpix/in_ids"])
+    assert np.abs(G["subpix/corners"][n0:] - np.rint(G["subpix/corners"][n0:])).max() > 0.05       # the recovered corners did move off the pixel grid
+
+
 def test_numpy_restatement_edge_cases():
     none = np.zeros((0, 4, 2), np.float32)
     # nothing detected / nothing rejected: inputs come back untouched
@@ -59,6 +74,30 @@ def test_numpy_restatement_edge_cases():
     img = refine_np.project_points(obj, rv, tv, G["K"], G["D"])
     r2, t2 = refine_np.solve_pnp_planar(obj, img, G["K"], G["D"])
     assert np.allclose(r2, rv, atol=1e-8) and np.allclose(t2, tv, atol=1e-8)
+
+
+def test_product_board_geometry_vs_restatement():
+    """board_core.h (the product's host-side fits) against the numpy restatement on the golden detections, and against closed forms"""
+    from hostemu import emu
+    ids = [int(i) for i in G["ids"]]
+    bids = [int(i) for i in G["board_ids"]]
+    obj = np.concatenate([G["board_obj"][bids.index(i)] for i in ids]).astype(np.float64)
+    img = G["corners"].reshape(-1, 2).astype(np.float64)
+    ok, H = emu.homography(obj[:, :2], img)
+    assert ok and np.abs(refine_np.perspective_transform(obj[:, :2], H) - refine_np.perspective_transform(obj[:, :2], refine_np.find_homography(obj[:, :2], img))).max() < 1e-6
+    rc, r, t = emu.board_pose(G["K"], G["D"], obj, img)
+    r2, t2 = refine_np.solve_pnp_planar(obj, img, G["K"], G["D"])
+    assert rc == 0
+    assert np.abs(refine_np.project_points(obj, r, t, G["K"], G["D"]) - refine_np.project_points(obj, r2, t2, G["K"], G["D"])).max() < 1e-6
+    # a tilted, offset board plane: exact recovery from exact projections
+    rng = np.random.default_rng(4)
+    R0 = refine_np.rodrigues(np.array([0.4, 0.3, -0.2]))
+    pl = np.c_[rng.uniform(-0.2, 0.2, (20, 2)), np.zeros(20)] @ R0.T + np.array([0.3, -0.1, 0.7])
+    rv, tv = np.array([-0.25, 0.5, 0.15]), np.array([-0.2, 0.1, 1.1])
+    rc, r, t = emu.board_pose(G["K"], G["D"], pl, refine_np.project_points(pl, rv, tv, G["K"], G["D"]))
+    assert rc == 0 and np.allclose(r, rv, atol=1e-7) and np.allclose(t, tv, atol=1e-7)
+    pl[::3, 2] += 0.05
+    assert emu.board_pose(G["K"], G["D"], pl, refine_np.project_points(pl, rv, tv, G["K"], G["D"]))[0] == 2     # not coplanar
 
 
 # ---- the product through the C ABI ----
@@ -83,6 +122,18 @@ def test_gpu_refine_detected_markers_vs_cv2(aruco, name, prm):
     oc, oi, orj, rec = out
     same_as_cv2(name, np.array(oc, np.float32).reshape(-1, 4, 2), np.asarray(oi, np.int32).ravel(), np.array(orj, np.float32).reshape(-1, 4, 2),
                 np.zeros(0, np.int32) if rec is None else np.asarray(rec, np.int32).ravel())
+    det.close()
+
+
+@pytest.mark.gpu
+def test_gpu_refine_detected_markers_subpix(aruco):
+    det = aruco.ArucoDetector(DIC, aruco.DetectorParameters(cornerRefinementMethod=1), max_shape=G["frame"].shape, max_batch=1)
+    c, ids, rej = det.detectMarkers(G["frame"])
+    assert np.array_equal(ids.ravel(), G["subpix/in_ids"]) and np.abs(np.array(c).reshape(-1, 4, 2) - G["subpix/in_corners"]).max() < 0.05
+    oc, oi, orj, rec = det.refineDetectedMarkers(G["frame"], aruco.Board(G["board_obj"], G["board_ids"]), c, ids, rej)
+    assert np.array_equal(oi.ravel(), G["subpix/ids"]) and np.array_equal(rec.ravel(), G["subpix/recovered"])
+    assert np.array_equal(np.array(orj).reshape(-1, 4, 2), G["subpix/rejected"])
+    assert np.abs(np.array(oc).reshape(-1, 4, 2) - G["subpix/corners"]).max() < 0.05
     det.close()
 
 

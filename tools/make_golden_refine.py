@@ -96,6 +96,17 @@ def board_fixture():
         rec = np.zeros(0, np.int32) if out[3] is None else np.asarray(out[3]).ravel().astype(np.int32)
         kw.update({name + "/corners": oc, name + "/ids": oi, name + "/rejected": orj, name + "/recovered": rec})
         print("  %-12s -> detected %d, rejected %d, recovered candidates %s as ids %s" % (name, len(oi), len(orj), rec.tolist(), oi[len(ids):].tolist()))
+    # the same with CORNER_REFINE_SUBPIX in the detector: recovered candidates are refined like accepted ones
+    prm = A.DetectorParameters()
+    prm.cornerRefinementMethod = A.CORNER_REFINE_SUBPIX
+    d3 = A.ArucoDetector(dic, prm, A.RefineParameters())
+    c3, i3, r3 = d3.detectMarkers(damaged)
+    out = d3.refineDetectedMarkers(damaged, board, list(c3), i3.copy(), list(r3))
+    kw.update({"subpix/in_corners": np.array(c3, np.float32).reshape(-1, 4, 2), "subpix/in_ids": i3.ravel().astype(np.int32),
+               "subpix/in_rejected": np.array(r3, np.float32).reshape(-1, 4, 2), "subpix/corners": np.array(out[0], np.float32).reshape(-1, 4, 2),
+               "subpix/ids": np.asarray(out[1]).ravel().astype(np.int32), "subpix/rejected": np.array(out[2], np.float32).reshape(-1, 4, 2),
+               "subpix/recovered": np.asarray(out[3]).ravel().astype(np.int32)})
+    print("  subpix       -> detected %d, recovered %s" % (len(out[1]), np.asarray(out[3]).ravel().tolist()))
     path = os.path.join(OUT, "refine_board.npz")
     np.savez_compressed(path, provenance=np.array(PROV), **kw)
     print("refine_board.npz %.1f KB" % (os.path.getsize(path) / 1024))
