@@ -323,6 +323,10 @@ class ArucoDetector:
         """number of concurrent sub-batches (CUDA streams) a call is cut into; 1 = serial stages"""
         _lib.check(_lib.lib().b2a_detector_set_streams(self._h, int(n)))
 
+    def set_graph(self, on: bool):
+        """CUDA-graph replay of small calls (default on); off = plain launches, e.g. to read per-stage times"""
+        _lib.check(_lib.lib().b2a_detector_set_graph(self._h, int(bool(on))))
+
     def set_inflight(self, n: int):
         """batches that submit / wait keep in flight on this handle (1 .. 4 contexts, default 2)"""
         _lib.check(_lib.lib().b2a_detector_set_inflight(self._h, int(n)))

@@ -251,6 +251,15 @@ struct b2a_detector {
     b2a_detector *more[MAX_CTX - 1] = {};         // contexts 1 .. n_ctx - 1 (this object is context 0)
     int n_ctx = 2;                                // batches in flight that submit / wait alternate over (b2a_detector_set_inflight)
     bool in_flight = false, pending_pose = false, pipelined = false; int pending_batch = 0;
+    // small batches are launch-bound on the host (one 1080p frame: 19 launches, ~100 us of host time): the whole call is captured
+    // once per (shape, camera) into a CUDA graph and replayed; the frames go through d_in so that every node reads fixed addresses
+    struct GraphEntry {
+        int B, W, H, channels, n_streams; bool has_cam, pipelined; b2a_camera cam;
+        cudaGraphExec_t exec; int launches; unsigned long long last_use;
+    };
+    std::vector<GraphEntry> graphs;
+    bool use_graph = true, graph_failed = false, capturing = false;
+    unsigned long long graph_tick = 0;
     unsigned next_ticket = 0;
     std::vector<void *> allocs, pinned;
 };
@@ -288,6 +297,7 @@ extern "C" void b2a_detector_destroy(b2a_detector *d)
     for (int i = 0; i <= ST_COUNT; ++i) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     for (int i = 0; i < b2a_detector::MAX_SUB; ++i) { if (d->streams[i]) cudaStreamDestroy(d->streams[i]); if (d->ev_join[i]) cudaEventDestroy(d->ev_join[i]); }
     if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+    for (auto &g : d->graphs) cudaGraphExecDestroy(g.exec);
     delete d;
 }
 
@@ -818,6 +828,66 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
 // mode: 0 full pipeline, 1 stop after the front end (taps), 2 stop after grouping (candidate tap)
 // post: work the caller appends on the handle's stream after the sub-batches have joined
 // enqueue_pipeline returns as soon as everything is queued; finish_pipeline is the one synchronisation of a call
+constexpr int GRAPH_MAX_BATCH = 4, GRAPH_CACHE = 8;
+static int enqueue_body(b2a_detector *d, const b2a_frames *f, const b2a_camera *cam, int mode, int walk_max_len, std::vector<Sub> *subs_out);
+
+// the call as one graph launch: frames into d_in (plain copies on the handle's stream), then the captured kernels of this
+// (batch, shape, camera); the first call of a kind captures and instantiates.  A capture that fails switches the handle back
+// to plain launches for good.
+static int enqueue_graph(b2a_detector *d, const b2a_frames *f, const b2a_camera *cam)
+{
+    const int B = f->batch, W = f->width, H = f->height;
+    cudaStream_t s0 = d->stream;
+    const size_t rowbytes = (size_t)W * f->channels, dpitch = f->channels == 1 ? ((rowbytes + 3) & ~(size_t)3) : rowbytes;
+    const size_t in_pitch = f->row_stride ? f->row_stride : rowbytes, in_frame = f->frame_stride ? f->frame_stride : in_pitch * H;
+    const cudaMemcpyKind kind = f->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (in_frame == in_pitch * H && in_pitch == rowbytes && dpitch == rowbytes) CU(cudaMemcpyAsync(d->d_in, f->data, rowbytes * H * B, kind, s0));
+    else if (in_frame == in_pitch * H) CU(cudaMemcpy2DAsync(d->d_in, dpitch, f->data, in_pitch, rowbytes, (size_t)H * B, kind, s0));
+    else for (int b = 0; b < B; ++b) CU(cudaMemcpy2DAsync(d->d_in + (size_t)b * dpitch * H, dpitch, f->data + (size_t)b * in_frame, in_pitch, rowbytes, H, kind, s0));
+    b2a_frames fg = *f;
+    fg.data = d->d_in; fg.on_device = 1; fg.row_stride = dpitch; fg.frame_stride = dpitch * H;
+    b2a_camera cz;
+    std::memset(&cz, 0, sizeof(cz));
+    if (cam) { std::memcpy(cz.K, cam->K, sizeof(cz.K)); std::memcpy(cz.D, cam->D, sizeof(cz.D)); cz.nD = cam->nD; cz.marker_length = cam->marker_length; }
+    b2a_detector::GraphEntry *e = nullptr;
+    for (auto &g : d->graphs)
+        if (g.B == B && g.W == W && g.H == H && g.channels == f->channels && g.n_streams == d->n_streams && g.has_cam == (cam != nullptr) &&
+            g.pipelined == d->pipelined && std::memcmp(&g.cam, &cz, sizeof(cz)) == 0) { e = &g; break; }
+    if (!e) {
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal);
+        int rc = B2A_ERR_CUDA;
+        if (ce == cudaSuccess) {
+            d->capturing = true;
+            d->launches = 0;
+            rc = enqueue_body(d, &fg, cam, 0, 0, nullptr);
+            d->capturing = false;
+            ce = cudaStreamEndCapture(s0, &graph);
+        }
+        cudaGraphExec_t exec = nullptr;
+        if (rc == B2A_OK && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != B2A_OK || ce != cudaSuccess || !exec) {
+            cudaGetLastError();
+            d->graph_failed = true;                          // plain launches from now on (the frames are already in d_in)
+            d->launches = 0;
+            return enqueue_body(d, &fg, cam, 0, 0, nullptr);
+        }
+        if ((int)d->graphs.size() >= GRAPH_CACHE) {
+            size_t lru = 0;
+            for (size_t i = 1; i < d->graphs.size(); ++i) if (d->graphs[i].last_use < d->graphs[lru].last_use) lru = i;
+            cudaGraphExecDestroy(d->graphs[lru].exec);
+            d->graphs.erase(d->graphs.begin() + (long)lru);
+        }
+        d->graphs.push_back(b2a_detector::GraphEntry{B, W, H, f->channels, d->n_streams, cam != nullptr, d->pipelined, cz, exec, d->launches, 0});
+        e = &d->graphs.back();
+    }
+    e->last_use = ++d->graph_tick;
+    CU(cudaGraphLaunch(e->exec, s0));
+    d->launches = e->launches;
+    return B2A_OK;
+}
+
 static int enqueue_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_camera *cam, int mode, int walk_max_len, std::vector<Sub> *subs_out,
                             const std::function<int(cudaStream_t)> *post = nullptr)
 {
@@ -833,6 +903,19 @@ static int enqueue_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_came
         CU(cudaMemsetAsync(d->d_masks, 0, d->masks_words * sizeof(uint32_t), s0));
         d->lastW = W; d->lastH = H; d->lastB = std::max(B, d->lastB);
     }
+    static const bool graph_env = !(std::getenv("B2A_GRAPH") && std::atoi(std::getenv("B2A_GRAPH")) == 0);
+    if (graph_env && d->use_graph && !d->graph_failed && mode == 0 && !subs_out && B <= GRAPH_MAX_BATCH && !sync_debug()) {
+        int rc = enqueue_graph(d, f, cam);
+        if (rc != B2A_OK) return rc;
+    } else TRY(enqueue_body(d, f, cam, mode, walk_max_len, subs_out));
+    if (post) TRY((*post)(s0));
+    return B2A_OK;
+}
+
+static int enqueue_body(b2a_detector *d, const b2a_frames *f, const b2a_camera *cam, int mode, int walk_max_len, std::vector<Sub> *subs_out)
+{
+    const int B = f->batch;
+    cudaStream_t s0 = d->stream;
     const size_t FSmax = (size_t)d->cfg.max_batch * d->nScales;
     CU(cudaMemsetAsync(d->d_counters, 0, (d->n_sub_max + 3 * FSmax + d->cfg.max_batch) * sizeof(int), s0));
     CU(cudaMemsetAsync(d->d_counters2, 0, d->n_sub_max * sizeof(unsigned), s0));
@@ -869,7 +952,7 @@ static int enqueue_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_came
     for (int i = 0; i < nsub; ++i) {
         Sub &s = subs[i];
         s.sb = i; s.b0 = bounds[i]; s.nb = bounds[i + 1] - bounds[i];
-        s.st = d->streams[i]; s.timed = (i == 0);
+        s.st = d->streams[i]; s.timed = (i == 0) && !d->capturing;       // stage events cannot be read back from a replayed graph
     }
     CU(cudaEventRecord(d->ev_fork, s0));
     for (int i = 1; i < nsub; ++i) CU(cudaStreamWaitEvent(subs[i].st, d->ev_fork, 0));
@@ -893,7 +976,6 @@ static int enqueue_pipeline(b2a_detector *d, const b2a_frames *f, const b2a_came
 #endif
     }
     for (int i = 1; i < nsub; ++i) { CU(cudaEventRecord(d->ev_join[i], subs[i].st)); CU(cudaStreamWaitEvent(s0, d->ev_join[i], 0)); }
-    if (post) TRY((*post)(s0));
 #ifdef B2A_DEBUG_TAPS
     if (timeline && mode == 0) {
         cudaStreamSynchronize(s0);
@@ -1024,7 +1106,7 @@ static int submit_impl(b2a_detector *d, const b2a_frames *frames, const b2a_came
             TRY(b2a_detector_create(&d->cfg, &d->dict, &d->prm, &d->more[slot - 1]));
         }
         t = d->more[slot - 1];
-        t->n_streams = d->n_streams;
+        t->n_streams = d->n_streams; t->use_graph = d->use_graph;
     }
     if (t->in_flight) return set_err(B2A_ERR_INVALID, "all contexts of this handle are in flight (b2a_detect_pose_wait first)");
     t->pipelined = true;
@@ -1035,6 +1117,13 @@ static int submit_impl(b2a_detector *d, const b2a_frames *frames, const b2a_came
     TRY(rc_enq);
     t->in_flight = true; t->pending_pose = cam != nullptr; t->pending_batch = frames->batch;
     *ticket = (int)d->next_ticket++;
+    return B2A_OK;
+}
+
+extern "C" int b2a_detector_set_graph(b2a_detector *d, int on)
+{
+    if (!d) return set_err(B2A_ERR_INVALID, "null argument");
+    d->use_graph = on != 0;
     return B2A_OK;
 }
 

@@ -212,9 +212,10 @@ def bench_c4(args, rank, local_rank, world):
         s.addEncoder(0, 0, None)
         return s
 
-    def run(host):
+    def run(host, graph=True):
         """W untimed + K timed steps of the loop on a fresh filter; CUDA events from the idle detector stream to the filter's stream after the last frame"""
         s = new_filter()
+        s.detector.set_graph(graph)
         s.detector.set_inflight(args.inflight)
         det_stream = torch.cuda.ExternalStream(s.detector.stream, device=local_rank)
         ekf_stream = torch.cuda.ExternalStream(s.stream, device=local_rank)
@@ -264,9 +265,10 @@ def bench_c4(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, mu, sg, ids, thr_ms, launches, stages = run(False)
+    ms_dev, mu, sg, ids, _, launches, _ = run(False)
     ms_e2e, mu2, sg2, ids2, _, _, _ = run(True)
     clocks = sampler.result() if rank == 0 else None
+    _, _, _, _, thr_ms, _, stages = run(False, graph=False)       # per-stage times need plain launches (a replayed CUDA graph has no stage events)
     # parity: the CPU chain (oracle detector + pose + observations + EKF) over this rank's stream
     from oracle import oracle as O
     dic = D.getPredefinedDictionary(synth.C4_DICT)
@@ -291,6 +293,7 @@ def bench_c4(args, rank, local_rank, world):
                "data": "synthetic",
                "config": {"workload": "C4: %d camera stream(s) (one per GPU), 1080p, map.txt-style landmark map (%d markers, DICT_ARUCO_ORIGINAL), encoder + frame per step, "
                                       "full EKF SLAM loop (addEncoder + addImage)" % (world, len(synth.c4_map())),
+                          "launches": "the detector's kernels of a frame are one CUDA graph launch (captured on the first frame of the shape); stages_ms_per_frame from a separate pass with plain launches",
                           "l2": "every step brings a new 2 MB frame; L2 not flushed (a stream's consecutive frames are what a camera delivers)",
                           "parallelism": "one stream and one filter per GPU, no collective; %d frames of the stream in flight (b2a_slam_add_image_submit / _wait)" % args.inflight},
                "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": P, "d2h_bytes_per_step": 12 * 8 + 12 + 12 * 84,
@@ -705,8 +708,13 @@ def main():
     # on the launching stream (L2 flushed before every step like the main runs)
     n_streams = int(os.environ.get("B2A_STREAMS", "0"))          # 0 = the library's own choice (2 sub-batches for resident frames, 4 for host frames)
     det.set_streams(1)
+    det.set_graph(False)                                          # a replayed CUDA graph (calls of up to 4 frames) has no per-stage events
     _, stages_1s, _ = run(fr_dev, max(3, min(args.steps, 10)), 1)
     det.set_streams(n_streams)
+    if B <= 4:                                                    # the timed runs above replayed graphs: per-stage times from plain launches
+        _, stages, _ = run(fr_dev, max(3, min(args.steps, 10)), 1)
+        _, stages_e2e, _ = run(fr_host, max(3, min(args.steps, 10)), 1)
+    det.set_graph(True)
     na = np.ctypeslib.as_array(det.detect_raw(fr_dev, cam).n_accepted, (B,)).copy()
     nr = np.ctypeslib.as_array(det.detect_raw(fr_dev, cam).n_rejected, (B,)).copy()
 

@@ -150,6 +150,10 @@ int b2a_detect_pose_submit(b2a_detector *d, const b2a_frames *frames, const b2a_
  * kernels leave most of the GPU idle; a 32-frame batch is bound by its PCIe copy with two).  Resets the ticket counter; not while a
  * batch is in flight. */
 int b2a_detector_set_inflight(b2a_detector *d, int n);
+/* Calls on up to 4 frames are launch-bound on the host, so by default their kernels are captured once per (batch, shape, camera)
+ * into a CUDA graph and replayed (the frames are first copied into the handle's own buffer so that every node reads fixed
+ * addresses); b2a_last_stage_times reports zeros for such calls.  on = 0 goes back to plain launches. */
+int  b2a_detector_set_graph(b2a_detector *d, int on);
 int b2a_detect_pose_wait(b2a_detector *d, int ticket, b2a_detections *out);
 
 /* cv::aruco::drawDetectedMarkers(image, corners, ids, borderColor) (aruco_slam.cpp:319; the image getMarkedImg returns,
