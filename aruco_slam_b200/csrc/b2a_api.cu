@@ -247,7 +247,7 @@ struct b2a_detector {
     int last_call_batch = 0; bool last_call_pose = false;       // what the result arrays hold (b2a_detector_last_detections)
     // asynchronous submit / wait: the handle owns a second, lazily created pipeline context (all buffers and streams); batches
     // alternate between the two, so the H2D copy of one overlaps the kernels of the other
-    static constexpr int MAX_CTX = 4;
+    static constexpr int MAX_CTX = 8;
     b2a_detector *more[MAX_CTX - 1] = {};         // contexts 1 .. n_ctx - 1 (this object is context 0)
     int n_ctx = 2;                                // batches in flight that submit / wait alternate over (b2a_detector_set_inflight)
     bool in_flight = false, pending_pose = false, pipelined = false; int pending_batch = 0;
@@ -1307,7 +1307,7 @@ extern "C" int b2a_multi_detect_pose(b2a_multi *m, const b2a_frames *f, const b2
 
 extern "C" int b2a_detector_set_inflight(b2a_detector *d, int n)
 {
-    if (!d || n < 1 || n > b2a_detector::MAX_CTX) return set_err(B2A_ERR_INVALID, "in-flight batches must be 1 .. 4");
+    if (!d || n < 1 || n > b2a_detector::MAX_CTX) return set_err(B2A_ERR_INVALID, "in-flight batches must be 1 .. 8");
     if (d->in_flight) return set_err(B2A_ERR_INVALID, "a submitted batch is still in flight on this handle");
     for (b2a_detector *m : d->more) if (m && m->in_flight) return set_err(B2A_ERR_INVALID, "a submitted batch is still in flight on this handle");
     d->n_ctx = n;
@@ -1636,6 +1636,11 @@ struct b2a_slam {
     Observation *h_obs = nullptr; int *h_keep = nullptr, *h_n = nullptr;                      // pinned, written by k_observations; two sets
                                                                                               // (h_obs + set * obs_cap ...): one per frame in flight
     EkfObs *d_ekf = nullptr, *h_ekf[2] = {nullptr, nullptr}; cudaEvent_t ev_ekf[2] = {nullptr, nullptr}; int ekf_buf = 0;   // corrections of a frame
+    // a frame whose landmarks are all known is one copy + four kernels of fixed shape per (N, corrections, staging buffer): replayed as a CUDA graph
+    struct EkfGraph { int N, nb, buf; cudaGraphExec_t exec; unsigned long long last_use; };
+    std::vector<EkfGraph> ekf_graphs;
+    unsigned long long ekf_graph_tick = 0;
+    bool ekf_graph_ok = true;
     std::vector<int32_t> ids;                       // landmark k -> aruco id
     std::unordered_map<int32_t, int> id_index;      // aruco_id_map (aruco_slam.h:164): id -> landmark index, first insertion wins (:256)
     std::vector<int32_t> last_ids; std::vector<double> last_obs;   // last_observed_marker_ (NaN = unset)
@@ -1653,6 +1658,8 @@ extern "C" void b2a_default_slam_params(b2a_slam_params *p)
 
 static void slam_free_scratch(b2a_slam *s)
 {
+    for (auto &g : s->ekf_graphs) cudaGraphExecDestroy(g.exec);        // their nodes hold the addresses freed below
+    s->ekf_graphs.clear();
     cudaFree(s->d_c); cudaFree(s->d_i); cudaFree(s->d_r); cudaFree(s->d_t); cudaFree(s->d_ekf);
     cudaFreeHost(s->h_obs); cudaFreeHost(s->h_keep); cudaFreeHost(s->h_ekf[0]); cudaFreeHost(s->h_ekf[1]);
     s->d_c = nullptr; s->d_i = nullptr; s->d_r = s->d_t = nullptr; s->d_ekf = nullptr; s->h_obs = nullptr; s->h_keep = nullptr; s->h_ekf[0] = s->h_ekf[1] = nullptr;
@@ -2012,19 +2019,54 @@ extern "C" int b2a_slam_update(b2a_slam *s, const b2a_observation *obs, int n)
         const int N = s->N;
         if (s->panel) {
             // one rank-3M update per (at most 32) corrections: Sigma is read and written once
-            CU(cudaMemcpyAsync(s->d_ekf + batch0, stage + batch0, (size_t)nb * sizeof(EkfObs), cudaMemcpyHostToDevice, st));
-            for (int o0 = 0; o0 < nb; o0 += EP_MAX_OBS) {
-                EkfPanel p;
-                p.obs = s->d_ekf + batch0 + o0; p.M = std::min(EP_MAX_OBS, nb - o0);
-                p.ze = s->d_pze; p.U0 = s->d_pU0; p.Kall = s->d_pK; p.V0 = s->d_pV0; p.Vall = s->d_pV; p.fac = s->d_pfac; p.facT = s->d_pfacT;
-                const int tiles = (N + EG_T - 1) / EG_T, kdim = (3 * p.M + 3) & ~3;
-                const int gx = std::max((N + 127) / 128, (EP_K * EP_K + 127) / 128);          // the y == M slice also clears the padding of the 96 x 96 matrix
-                k_ekf_panel_gather<<<dim3(gx, p.M + 1), 128, 0, st>>>(s->d_sigma, s->d_mus, N, s->LD, p);
-                k_ekf_panel_factor<<<1, EP_MAX_OBS * EP_MAX_OBS, 0, st>>>(p);
-                const int rc = (N + EP_SW * EP_SV - 1) / (EP_SW * EP_SV);
-                k_ekf_panel_solve<<<2 * rc, 32 * EP_SW, EP_SSMEM, st>>>(s->d_mu, N, s->LD, p, rc);
-                k_ekf_panel_gemm<<<dim3(tiles, tiles), 512, EG_SMEM, st>>>(s->d_sigma, N, s->LD, p, kdim);
+            auto issue = [&]() -> int {
+                CU(cudaMemcpyAsync(s->d_ekf + batch0, stage + batch0, (size_t)nb * sizeof(EkfObs), cudaMemcpyHostToDevice, st));
+                for (int o0 = 0; o0 < nb; o0 += EP_MAX_OBS) {
+                    EkfPanel p;
+                    p.obs = s->d_ekf + batch0 + o0; p.M = std::min(EP_MAX_OBS, nb - o0);
+                    p.ze = s->d_pze; p.U0 = s->d_pU0; p.Kall = s->d_pK; p.V0 = s->d_pV0; p.Vall = s->d_pV; p.fac = s->d_pfac; p.facT = s->d_pfacT;
+                    const int tiles = (N + EG_T - 1) / EG_T, kdim = (3 * p.M + 3) & ~3;
+                    const int gx = std::max((N + 127) / 128, (EP_K * EP_K + 127) / 128);          // the y == M slice also clears the padding of the 96 x 96 matrix
+                    k_ekf_panel_gather<<<dim3(gx, p.M + 1), 128, 0, st>>>(s->d_sigma, s->d_mus, N, s->LD, p);
+                    k_ekf_panel_factor<<<1, EP_MAX_OBS * EP_MAX_OBS, 0, st>>>(p);
+                    const int rc = (N + EP_SW * EP_SV - 1) / (EP_SW * EP_SV);
+                    k_ekf_panel_solve<<<2 * rc, 32 * EP_SW, EP_SSMEM, st>>>(s->d_mu, N, s->LD, p, rc);
+                    k_ekf_panel_gemm<<<dim3(tiles, tiles), 512, EG_SMEM, st>>>(s->d_sigma, N, s->LD, p, kdim);
+                }
+                return B2A_OK;
+            };
+            // a frame whose landmarks are all known has one such flush of fixed shape per (N, corrections, staging buffer): captured once, replayed
+            static const bool graph_env = !(std::getenv("B2A_GRAPH") && std::atoi(std::getenv("B2A_GRAPH")) == 0);
+            bool done = false;
+            if (graph_env && s->ekf_graph_ok && batch0 == 0 && nb <= EP_MAX_OBS) {
+                b2a_slam::EkfGraph *ge = nullptr;
+                for (auto &g : s->ekf_graphs) if (g.N == N && g.nb == nb && g.buf == buf) { ge = &g; break; }
+                if (!ge) {
+                    cudaGraph_t graph = nullptr;
+                    cudaGraphExec_t exec = nullptr;
+                    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+                    if (ce == cudaSuccess) {
+                        const int rc = issue();
+                        ce = cudaStreamEndCapture(st, &graph);
+                        if (rc != B2A_OK && ce == cudaSuccess) ce = cudaErrorUnknown;
+                    }
+                    if (ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&exec, graph, 0);
+                    if (graph) cudaGraphDestroy(graph);
+                    if (ce != cudaSuccess || !exec) { (void)cudaGetLastError(); s->ekf_graph_ok = false; }      // plain launches from now on
+                    else {
+                        if (s->ekf_graphs.size() >= 48) {
+                            size_t lru = 0;
+                            for (size_t i = 1; i < s->ekf_graphs.size(); ++i) if (s->ekf_graphs[i].last_use < s->ekf_graphs[lru].last_use) lru = i;
+                            cudaGraphExecDestroy(s->ekf_graphs[lru].exec);
+                            s->ekf_graphs.erase(s->ekf_graphs.begin() + (long)lru);
+                        }
+                        s->ekf_graphs.push_back(b2a_slam::EkfGraph{N, nb, buf, exec, 0});
+                        ge = &s->ekf_graphs.back();
+                    }
+                }
+                if (ge) { ge->last_use = ++s->ekf_graph_tick; CU(cudaGraphLaunch(ge->exec, st)); done = true; }
             }
+            if (!done) TRY(issue());
         } else if (s->coop_grid > 0 && (N + s->coop_grid - 1) / s->coop_grid <= 64) {
             CU(cudaMemcpyAsync(s->d_ekf + batch0, stage + batch0, (size_t)nb * sizeof(EkfObs), cudaMemcpyHostToDevice, st));
             int LD = s->LD, n_obs = nb, N_ = N;

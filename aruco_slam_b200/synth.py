@@ -380,11 +380,21 @@ def c4_stream(stream: int, n_frames: int, dt: float = 0.1):
     cmap = c4_map()
     pose = np.array([2.45 + 0.12 * (stream % 4), -0.9 + 0.2 * (stream // 4) + rng.uniform(-0.1, 0.1), rng.uniform(-0.25, 0.1)])
     frames, enc, truth = [], [], []
+    fwd = []
     for f in range(n_frames):
         turn = -1.0 if (f // 6) % 2 == 0 else 0.6
         wl, wr = 2.0 + 0.5 * turn + rng.uniform(-0.2, 0.2), 2.0 - 0.5 * turn + rng.uniform(-0.2, 0.2)
         if f % 9 == 4:
             wl = wr = 0.0                                   # standing still: the reference's stationary gate
+        # a long stream drives 24 frames forward, then the same wheel speeds backwards in reverse order, and so on: the robot stays
+        # in front of the same part of the map (about nine markers in view) however long the stream is
+        if f % 48 < 24:
+            if f < 24:
+                fwd.append((wl, wr))
+            else:
+                wl, wr = fwd[f % 48]
+        else:
+            wl, wr = (-v for v in fwd[47 - f % 48])
         pose = drive(pose, wl, wr, dt)
         poses = scene_poses(cmap, pose, C4_R2C, C4_K, C4_D, 1920, 1080)
         fr = render_scene(1920, 1080, C4_DICT, C4_K, C4_D, C4_MARKER_LENGTH, poses, seed=1000 * stream + f, noise_sigma=1.0, blur_sigma=0.8)

@@ -146,7 +146,7 @@ int b2a_detector_last_detections(b2a_detector *d, b2a_detections *out);
  * arrays `out` points to stay valid until the second submit after it.  The synchronous calls above refuse to run while a
  * batch is in flight on the first context. */
 int b2a_detect_pose_submit(b2a_detector *d, const b2a_frames *frames, const b2a_camera *cam, int *ticket);
-/* how many batches submit / wait keep in flight on this handle: 1 .. 4 contexts, default 2 (more pay off for single frames, whose
+/* how many batches submit / wait keep in flight on this handle: 1 .. 8 contexts, default 2 (more pay off for single frames, whose
  * kernels leave most of the GPU idle; a 32-frame batch is bound by its PCIe copy with two).  Resets the ticket counter; not while a
  * batch is in flight. */
 int b2a_detector_set_inflight(b2a_detector *d, int n);

@@ -254,6 +254,32 @@ def test_bgr_ingest_fused_into_threshold(aruco, oracle):
     det.close()
 
 
+def test_graph_replay_equals_plain_launches(aruco, oracle):
+    """calls of up to 4 frames replay a CUDA graph captured per (batch, shape, camera): different frames, batch sizes, shapes and
+    cameras through one handle give what plain launches give (and the oracle), and per-stage times exist only for plain launches"""
+    dic = D.getPredefinedDictionary(0)
+    frs = [synth.render_config("C1", s).image for s in range(10, 16)]
+    K1 = np.array([[600.0, 0, 320], [0, 600.0, 240], [0, 0, 1]])
+    K2 = np.array([[450.0, 0, 300], [0, 470.0, 250], [0, 0, 1]])
+    det = _detector(aruco, dic, frs[0].shape, batch=4)
+    plain = _detector(aruco, dic, frs[0].shape, batch=4)
+    plain.set_graph(False)
+    seq = [(frs[0], K1), (frs[1], K1), (np.stack(frs[2:5]), K1), (frs[5], K2), (frs[0][:400, :600].copy(), K2), (frs[1], K1), (np.stack(frs[1:5]), K2),
+           (synth.gray_to_bgr(frs[2], 1), K1), (frs[3], K1)]
+    for img, K in seq:
+        a = det.detect_pose_batch(img, 0.05, K, np.array([0.05, -0.02, 0.001, 0.0, 0.0]))
+        b = plain.detect_pose_batch(img, 0.05, K, np.array([0.05, -0.02, 0.001, 0.0, 0.0]))
+        for f in range(len(a.ids)):
+            assert np.array_equal(a.ids[f], b.ids[f]) and np.array_equal(a.corners[f], b.corners[f]) and np.array_equal(a.rejected[f], b.rejected[f])
+            assert np.array_equal(a.rvecs[f], b.rvecs[f]) and np.array_equal(a.tvecs[f], b.tvecs[f])
+        one = img if img.ndim == 2 or img.shape[-1] == 3 and img.ndim == 3 else img[0]
+        oc, oi, _ = oracle.detect(one, dic)
+        assert np.array_equal(a.ids[0], oi) and np.array_equal(a.corners[0], oc)
+    assert det.last_launch_count() == plain.last_launch_count() > 10
+    assert sum(det.last_stage_times().values()) == 0 and sum(plain.last_stage_times().values()) > 0
+    det.close(); plain.close()
+
+
 def test_threshold_device_frames_pitches(aruco, oracle):
     """frames already in device memory: an unaligned row pitch takes the tiled kernel, a padded (4-byte aligned) pitch and a
     frame stride take the marching kernel; both must give the oracle's masks and the same detections as host frames"""

@@ -271,9 +271,9 @@ def test_c5_vs_reference_run(name):
     s.close()
 
 
-@pytest.mark.parametrize("depth", [2, 4])
+@pytest.mark.parametrize("depth", [2, 4, 8])
 def test_add_image_submit_wait_equals_sequential_loop(depth):
-    """b2a_slam_add_image_submit / _wait with 2 / 4 frames in flight: the same filter state, frame by frame, as the sequential addImage loop"""
+    """b2a_slam_add_image_submit / _wait with 2 / 4 / 8 frames in flight: the same filter state, frame by frame, as the sequential addImage loop"""
     import collections
     from aruco_slam_b200.aruco import ArucoDetector
     g = golden("slam_scene")
