@@ -7,7 +7,7 @@ O=gpurun_out
 mkdir -p $O
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 600 $RUN --master-port 29521 bench.py --gpus $N --steps 20 --warmup 3 > $O/${TAG}_c2_n$N.json 2> $O/${TAG}_c2_n$N.err
-timeout 600 $RUN --master-port 29522 bench.py --gpus $N --workload C4 --steps 20 --warmup 3 > $O/${TAG}_c4_n$N.json 2> $O/${TAG}_c4_n$N.err
+timeout 600 $RUN --master-port 29522 bench.py --gpus $N --workload C4 > $O/${TAG}_c4_n$N.json 2> $O/${TAG}_c4_n$N.err
 timeout 600 $RUN --master-port 29523 bench.py --gpus $N --impl reference --steps 3 --warmup 1 > $O/${TAG}_c2_ref_n$N.json 2> $O/${TAG}_c2_ref_n$N.err
 for f in c2_n$N c4_n$N c2_ref_n$N; do
 python - <<PY
