@@ -102,7 +102,7 @@ SYMBOLS = [
     "b2a_quaternion_from_rpy", "b2a_map_parse", "b2a_map_load", "b2a_slam_robot_pose", "b2a_slam_detected_map",
     "b2a_pack_robot_pose", "b2a_pack_map_marker", "b2a_slam_stream",
     "b2a_multi_create", "b2a_multi_destroy", "b2a_multi_num_devices", "b2a_multi_detect_pose", "b2a_draw_detected_markers", "b2a_detector_last_detections", "b2a_pack_detections",
-    "b2a_default_refine_params", "b2a_refine_detected_markers", "b2a_detector_set_graph",
+    "b2a_default_refine_params", "b2a_refine_detected_markers", "b2a_detector_set_graph", "b2a_slam_robot_pose_submit", "b2a_slam_robot_pose_wait",
 ]
 
 _lib = None

@@ -1637,6 +1637,10 @@ struct b2a_slam {
                                                                                               // (h_obs + set * obs_cap ...): one per frame in flight
     EkfObs *d_ekf = nullptr, *h_ekf[2] = {nullptr, nullptr}; cudaEvent_t ev_ekf[2] = {nullptr, nullptr}; int ekf_buf = 0;   // corrections of a frame
     // a frame whose landmarks are all known is one copy + four kernels of fixed shape per (N, corrections, staging buffer): replayed as a CUDA graph
+    static constexpr int POSE_SLOTS = 8;
+    double *h_pose = nullptr;                        // pinned [POSE_SLOTS][12]: mu[0..2], Sigma[0..2][0..2] of b2a_slam_robot_pose_submit
+    cudaEvent_t ev_pose[POSE_SLOTS] = {};
+    bool pose_pending[POSE_SLOTS] = {};
     struct EkfGraph { int N, nb, buf; cudaGraphExec_t exec; unsigned long long last_use; };
     std::vector<EkfGraph> ekf_graphs;
     unsigned long long ekf_graph_tick = 0;
@@ -1692,6 +1696,8 @@ extern "C" void b2a_slam_destroy(b2a_slam *s)
     slam_free_scratch(s);
     cudaFreeHost(s->h_n);
     for (cudaEvent_t e : s->ev_ekf) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : s->ev_pose) if (e) cudaEventDestroy(e);
+    cudaFreeHost(s->h_pose);
     cudaFree(s->d_sigma2);
     cudaFree(s->d_pze); cudaFree(s->d_pU0); cudaFree(s->d_pK); cudaFree(s->d_pV0); cudaFree(s->d_pV); cudaFree(s->d_pfac); cudaFree(s->d_pfacT);
     cudaFree(s->d_mu); cudaFree(s->d_mus); cudaFree(s->d_sigma); cudaFree(s->d_K); cudaFree(s->d_GS); cudaFree(s->d_scratch);
@@ -1880,6 +1886,35 @@ extern "C" int b2a_slam_robot_pose(b2a_slam *s, b2a_pose_with_covariance *out)
     CU(cudaMemcpy(mu, s->d_mu, sizeof(mu), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy2D(S, 3 * 8, s->d_sigma, (size_t)s->LD * 8, 3 * 8, 3, cudaMemcpyDeviceToHost));
     b2a_pack_robot_pose(mu, S, out);
+    return B2A_OK;
+}
+
+// the same record without stalling the host thread: _submit enqueues the 96-byte read-back behind everything the filter has
+// been given so far, _wait blocks only until that copy has landed
+extern "C" int b2a_slam_robot_pose_submit(b2a_slam *s, int slot)
+{
+    if (!s || slot < 0 || slot >= b2a_slam::POSE_SLOTS) return set_err(B2A_ERR_INVALID, "pose slot outside 0 .. 7");
+    CU(cudaSetDevice(s->device));
+    if (!s->h_pose) {
+        CU(cudaMallocHost(&s->h_pose, b2a_slam::POSE_SLOTS * 12 * sizeof(double)));
+        for (auto &e : s->ev_pose) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    double *h = s->h_pose + 12 * slot;
+    CU(cudaMemcpyAsync(h, s->d_mu, 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpy2DAsync(h + 3, 3 * 8, s->d_sigma, (size_t)s->LD * 8, 3 * 8, 3, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaEventRecord(s->ev_pose[slot], s->stream));
+    s->pose_pending[slot] = true;
+    return B2A_OK;
+}
+
+extern "C" int b2a_slam_robot_pose_wait(b2a_slam *s, int slot, b2a_pose_with_covariance *out)
+{
+    if (!s || !out || slot < 0 || slot >= b2a_slam::POSE_SLOTS) return set_err(B2A_ERR_INVALID, "bad argument");
+    if (!s->pose_pending[slot]) return set_err(B2A_ERR_INVALID, "no pose read-back submitted in this slot");
+    CU(cudaSetDevice(s->device));
+    CU(cudaEventSynchronize(s->ev_pose[slot]));
+    s->pose_pending[slot] = false;
+    b2a_pack_robot_pose(s->h_pose + 12 * slot, s->h_pose + 12 * slot + 3, out);
     return B2A_OK;
 }
 

@@ -67,6 +67,19 @@ def robot_pose(slam) -> PoseWithCovariance:
     return PoseWithCovariance(np.array(out.position[:]), np.array(out.orientation[:]), np.array(out.covariance[:]).reshape(6, 6))
 
 
+def robot_pose_submit(slam, slot: int = 0):
+    """enqueue the read-back of the pose record as of now into pinned slot 0 .. 7 (b2a_slam_robot_pose_submit)"""
+    _lib.lib().b2a_slam_robot_pose_submit.argtypes = [C.c_void_p, C.c_int]
+    _lib.check(_lib.lib().b2a_slam_robot_pose_submit(slam._h, int(slot)))
+
+
+def robot_pose_wait(slam, slot: int = 0) -> PoseWithCovariance:
+    out = _lib.PoseWithCovariance()
+    _lib.lib().b2a_slam_robot_pose_wait.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    _lib.check(_lib.lib().b2a_slam_robot_pose_wait(slam._h, int(slot), C.byref(out)))
+    return PoseWithCovariance(np.array(out.position[:]), np.array(out.orientation[:]), np.array(out.covariance[:]).reshape(6, 6))
+
+
 def detected_map(slam, marker_length: float = None):
     n_lm = (slam.dim - 3) // 3
     arr = (_lib.MapMarker * max(1, n_lm))()

@@ -309,6 +309,11 @@ typedef struct {
     double covariance[36];
 } b2a_pose_with_covariance;
 int  b2a_slam_robot_pose(b2a_slam *s, b2a_pose_with_covariance *out);
+/* The same record read back without stalling the host thread (a camera loop with several frames in flight): _submit enqueues the
+ * 96-byte copy into pinned slot `slot` (0 .. 7) behind everything the filter has been given so far, _wait blocks only until that
+ * copy has landed and packs the record. */
+int  b2a_slam_robot_pose_submit(b2a_slam *s, int slot);
+int  b2a_slam_robot_pose_wait(b2a_slam *s, int slot, b2a_pose_with_covariance *out);
 /* the packing step alone, on host values: mu[0:3] and Sigma[0:3,0:3] row-major (no device access) */
 void b2a_pack_robot_pose(const double mu3[3], const double sigma33[9], b2a_pose_with_covariance *out);
 /* detected_map_ of addImage (aruco_slam.cpp:266-281): one cube per landmark i: id = i (the landmark index, not the aruco id),

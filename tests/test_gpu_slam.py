@@ -300,3 +300,26 @@ def test_add_image_submit_wait_equals_sequential_loop(depth):
         assert np.array_equal(ia, ib) and np.array_equal(ma, mb) and np.array_equal(sa, sb), f
         assert np.array_equal(ia, g["ids_%d" % f])
     a.close(); b.close()
+
+
+def test_robot_pose_submit_wait_equals_synchronous_read():
+    """b2a_slam_robot_pose_submit / _wait: the record enqueued behind a frame's filter work equals the synchronous read at that point"""
+    from aruco_slam_b200 import formats
+    g = golden("slam_scene")
+    frames = g["frames"]
+    s = _golden_slam(g, image_shape=frames.shape[1:])
+    s.addEncoder(0, 0, None)
+    want = []
+    for f in range(6):
+        for wl, wr, dt in g["enc_%d" % f]:
+            s.addEncoder(wl, wr, dt)
+        s.addImage(frames[f])
+        formats.robot_pose_submit(s, f % 8)
+        want.append(formats.robot_pose(s))
+    for f in range(6):
+        got = formats.robot_pose_wait(s, f % 8)
+        assert np.array_equal(got.position, want[f].position) and np.array_equal(got.orientation, want[f].orientation)
+        assert np.array_equal(got.covariance, want[f].covariance)
+    with pytest.raises(Exception):
+        formats.robot_pose_wait(s, 7)                                   # nothing submitted in that slot
+    s.close()
