@@ -52,6 +52,9 @@ typedef struct {
     int    cornerRefinementMaxIterations;     /* 30 */
     double cornerRefinementMinAccuracy;       /* 0.1 */
     int    detectInvertedMarker;              /* 0 */
+    int    useAruco3Detection;                /* 0 */
+    int    minSideLengthCanonicalImg;         /* 32 */
+    float  minMarkerLengthRatioOriginalImg;   /* 0 */
 } orc_params;
 
 typedef struct {
@@ -60,6 +63,9 @@ typedef struct {
 } orc_dict;
 
 void orc_default_params(orc_params *p);
+/* cv::pyrDown and cv::resize(INTER_LINEAR) on 8-bit gray images (orc_pyramid.c): the two image operations of ArUco3 */
+void orc_pyr_down(const uint8_t *src, int W, int H, uint8_t *dst);                       /* dst is ((W + 1) / 2) x ((H + 1) / 2) */
+void orc_resize_linear(const uint8_t *src, int W, int H, uint8_t *dst, int dW, int dH);
 
 /* ---- stage functions (each pinned separately against cv2) ---- */
 void orc_bgr2gray(const uint8_t *bgr, int W, int H, uint8_t *gray);

@@ -19,7 +19,7 @@ _SO = os.path.join(_HERE, "liboracle.so")
 def build(force: bool = False) -> str:
     """make liboracle.so when it is missing or older than its sources.  Several processes may call this at once (every rank of a
     torchrun bench checks its frames): the build runs under a file lock, into a temporary name, and is renamed into place."""
-    srcs = [os.path.join(_HERE, f) for f in ("orc_detect.c", "orc_pose.c", "orc_ekf.c", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("orc_detect.c", "orc_pyramid.c", "orc_pose.c", "orc_ekf.c", "oracle.h")]
 
     def stale():
         return force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
@@ -52,6 +52,7 @@ class Params(C.Structure):
         ("cornerRefinementWinSize", C.c_int), ("relativeCornerRefinmentWinSize", C.c_double),
         ("cornerRefinementMaxIterations", C.c_int), ("cornerRefinementMinAccuracy", C.c_double),
         ("detectInvertedMarker", C.c_int),
+        ("useAruco3Detection", C.c_int), ("minSideLengthCanonicalImg", C.c_int), ("minMarkerLengthRatioOriginalImg", C.c_float),
     ]
 
 
@@ -117,6 +118,22 @@ def bgr2gray(bgr):
     H, W, _ = bgr.shape
     out = np.empty((H, W), np.uint8)
     lib().orc_bgr2gray(_p(bgr), W, H, _p(out))
+    return out
+
+
+def pyr_down(gray):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    H, W = gray.shape
+    out = np.zeros(((H + 1) // 2, (W + 1) // 2), np.uint8)
+    lib().orc_pyr_down(_p(gray), W, H, _p(out))
+    return out
+
+
+def resize_linear(gray, dW, dH):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    H, W = gray.shape
+    out = np.zeros((dH, dW), np.uint8)
+    lib().orc_resize_linear(_p(gray), W, H, _p(out), int(dW), int(dH))
     return out
 
 

@@ -37,6 +37,9 @@ void orc_default_params(orc_params *p)
     p->cornerRefinementMaxIterations = 30;
     p->cornerRefinementMinAccuracy = 0.1;
     p->detectInvertedMarker = 0;
+    p->useAruco3Detection = 0;
+    p->minSideLengthCanonicalImg = 32;
+    p->minMarkerLengthRatioOriginalImg = 0.f;
 }
 
 /* A1: cvtColor(BGR2GRAY) 8-bit: 15-bit fixed point, SURVEY App. A1 / probe P3 */
@@ -679,6 +682,28 @@ static void stable_sort_desc(cand_t *a, int n)
 
 static int cmp_int(const void *a, const void *b) { return *(const int *)a - *(const int *)b; }
 
+/* _findOptPyrImageForCanonicalImg: the level whose scaled contour length exceeds min_perimeter by the least (level 0 when none does) */
+static int find_opt_pyr_level(const int *pyrW, int nLevels, int scaled_width, int cur_perimeter, int min_perimeter)
+{
+    int opt = 0;
+    float dist = FLT_MAX;
+    for (int i = 0; i < nLevels; i++) {
+        const float scale = (float)pyrW[i] / (float)scaled_width;
+        const float perimeter_scaled = (float)cur_perimeter * scale;
+        const float new_dist = perimeter_scaled - (float)min_perimeter;
+        if (new_dist < dist && new_dist > 0.f) { dist = new_dist; opt = i; }
+    }
+    return opt;
+}
+
+/* _identifyOneCandidate with its `scale` argument: the corners are scaled (in float) to the image they are read in */
+static int identify_scaled(const uint8_t *im, int W, int H, const float *c, float scale, const orc_dict *d, const orc_params *p, int *id, int *rot)
+{
+    float sc[8];
+    for (int j = 0; j < 8; j++) sc[j] = c[j] * scale;
+    return orc_identify_one(im, W, H, sc, d, p, id, rot, NULL);
+}
+
 int orc_detect(const uint8_t *img, int W, int H, int channels, const orc_dict *d, const orc_params *p, orc_detections *out)
 {
     memset(out, 0, sizeof(*out));
@@ -686,12 +711,44 @@ int orc_detect(const uint8_t *img, int W, int H, int channels, const orc_dict *d
     uint8_t *gray = (uint8_t *)malloc(P);
     if (channels == 3) orc_bgr2gray(img, W, H, gray); else memcpy(gray, img, P);
 
+    /* ArUco3 (useAruco3Detection): the image pyramid of the full-size gray image, and the smaller "segmentation image" the
+     * candidates are searched in.  Off: one level, factor 1 (detectMarkers zeroes the two ArUco3 parameters itself). */
+    const int a3 = p->useAruco3Detection != 0;
+    const int minSide = a3 ? p->minSideLengthCanonicalImg : 0;
+    const int refineMethod = a3 ? 1 : p->cornerRefinementMethod;      /* "always turn on corner refinement in case of Aruco3, due to upsampling" */
+    float fxfy = 1.f;
+    int numLevels = 0, closestIdx = 0;
+    if (a3) {
+        fxfy = (float)minSide / ((float)minSide + (float)(W > H ? W : H) * p->minMarkerLengthRatioOriginalImg);
+        const float img_area = (float)(H * W), min_area_marker = (float)(minSide * minSide);
+        numLevels = (int)(log2f(img_area / min_area_marker) / 2.f);
+        const float scale_img_area = img_area * fxfy * fxfy;
+        closestIdx = (int)lrintf(log2f(img_area / scale_img_area) / 2.f);
+    }
+    uint8_t *pyr[32]; int pyrW[32], pyrH[32];
+    pyr[0] = gray; pyrW[0] = W; pyrH[0] = H;
+    if (numLevels > 31) numLevels = 31;
+    if (numLevels < 0) numLevels = 0;
+    for (int l = 1; l <= numLevels; l++) {
+        pyrW[l] = (pyrW[l - 1] + 1) / 2; pyrH[l] = (pyrH[l - 1] + 1) / 2;
+        pyr[l] = (uint8_t *)malloc((size_t)pyrW[l] * pyrH[l]);
+        orc_pyr_down(pyr[l - 1], pyrW[l - 1], pyrH[l - 1], pyr[l]);
+    }
+    const int W0 = W;
+    if (fxfy != 1.f) {
+        const int sW = (int)lrintf(fxfy * (float)W), sH = (int)lrintf(fxfy * (float)H);
+        uint8_t *seg = (uint8_t *)malloc((size_t)sW * sH);
+        orc_resize_linear(gray, W, H, seg, sW, sH);
+        gray = seg; W = sW; H = sH; P = (size_t)W * H;
+    }
+
     int nScales = (p->adaptiveThreshWinSizeMax - p->adaptiveThreshWinSizeMin) / p->adaptiveThreshWinSizeStep + 1;
     out->n_scales = nScales;
     out->n_contours = (int32_t *)calloc((size_t)nScales, sizeof(int32_t));
     int maxWH = W > H ? W : H;
     unsigned minPerim = (unsigned)(p->minMarkerPerimeterRate * maxWH);
     unsigned maxPerim = (unsigned)(p->maxMarkerPerimeterRate * maxWH);
+    if (minSide) minPerim = 4u * (unsigned)minSide;          /* _findMarkerContours: "for aruco3 we want to filter contours with min size" */
 
     cand_t *T = NULL; int nT = 0, capT = 0;
     uint8_t *mask = (uint8_t *)malloc(P);
@@ -720,7 +777,7 @@ int orc_detect(const uint8_t *img, int W, int H, int channels, const orc_dict *d
                     memset(c, 0, sizeof(*c));
                     for (int j = 0; j < 8; j++) c->c[j] = (float)ap[j];
                     c->len = n; c->parent = -1; c->depth = 0;
-                    if (p->cornerRefinementMethod == 2) {
+                    if (refineMethod == 2) {
                         c->contour = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)n);
                         memcpy(c->contour, pts + 2 * (size_t)offs[ci], sizeof(int32_t) * 2 * (size_t)n);
                     }
@@ -822,11 +879,18 @@ int orc_detect(const uint8_t *img, int W, int H, int channels, const orc_dict *d
         for (int v = 0; v < nS; v++) {
             if (T[S[v]].depth != depth) continue;
             was[v] = 1;
-            valid[v] = (char)orc_identify_one(gray, W, H, T[S[v]].c, d, p, &ids[v], &rots[v], NULL);
+            /* ArUco3, "equation (4)": the candidate is read in the pyramid level where its contour is closest to (and longer
+             * than) the canonical perimeter; the close candidates of its group are read in the same level */
+            const uint8_t *im = gray; int iW = W, iH = H; float scale = 1.f;
+            if (a3) {
+                int lvl = find_opt_pyr_level(pyrW, numLevels + 1, W, T[S[v]].len, 4 * minSide);
+                im = pyr[lvl]; iW = pyrW[lvl]; iH = pyrH[lvl]; scale = (float)iW / (float)W;
+            }
+            valid[v] = (char)identify_scaled(im, iW, iH, T[S[v]].c, scale, d, p, &ids[v], &rots[v]);
             if (!valid[v]) {
                 for (int k = 0; k < T[S[v]].n_close; k++) {
                     const float *cc = T[T[S[v]].close[k]].c;
-                    if (orc_identify_one(gray, W, H, cc, d, p, &ids[v], &rots[v], NULL)) {
+                    if (identify_scaled(im, iW, iH, cc, scale, d, p, &ids[v], &rots[v])) {
                         valid[v] = 1; memcpy(fc + 8 * v, cc, sizeof(float) * 8); fcand[v] = T[S[v]].close[k]; break;
                     }
                 }
@@ -854,15 +918,29 @@ int orc_detect(const uint8_t *img, int W, int H, int channels, const orc_dict *d
             /* std::rotate(begin, begin + 4 - rot, end): out[j] = in[(j + 4 - rot) % 4] */
             for (int j = 0; j < 4; j++) { o[2 * j] = fc[8 * v + 2 * ((j + 4 - r) % 4)]; o[2 * j + 1] = fc[8 * v + 2 * ((j + 4 - r) % 4) + 1]; }
             /* optional refinement with the contour's side lines (after the rotation, as detectMarkers does) */
-            if (p->cornerRefinementMethod == 2) orc_refine_candidate_lines(T[fcand[v]].contour, T[fcand[v]].len, o);
+            if (refineMethod == 2) orc_refine_candidate_lines(T[fcand[v]].contour, T[fcand[v]].len, o);
             out->ids[out->n_acc++] = ids[v];
         } else {
             memcpy(out->rejected + 8 * out->n_rej, fc + 8 * v, sizeof(float) * 8);
             out->n_rej++;
         }
     }
+    /* ArUco3 forces CORNER_REFINE_SUBPIX and refines up the pyramid (findCornerInPyrImage): corners to the level closest to the
+     * segmentation image, then level by level x 2 with a 3-pixel (5 above 1080 px) window down to the full-size image */
+    if (a3) {
+        const float scale_init = (float)pyrW[closestIdx <= numLevels ? closestIdx : numLevels] / (float)W;
+        for (int i = 0; i < out->n_acc; i++) {
+            float *c = out->corners + 8 * i;
+            if (scale_init != 1.f) for (int j = 0; j < 8; j++) c[j] *= scale_init;
+            for (int idx = closestIdx - 1; idx >= 0; --idx) {
+                for (int j = 0; j < 8; j++) c[j] *= 2.f;
+                const int mx = pyrW[idx] > pyrH[idx] ? pyrW[idx] : pyrH[idx];
+                orc_corner_subpix(pyr[idx], pyrW[idx], pyrH[idx], c, 4, mx > 1080 ? 5 : 3, p->cornerRefinementMaxIterations, p->cornerRefinementMinAccuracy);
+            }
+        }
+    }
     /* A8: optional sub-pixel refinement of accepted markers */
-    if (p->cornerRefinementMethod == 1) {
+    if (!a3 && refineMethod == 1) {
         for (int i = 0; i < out->n_acc; i++) {
             float *c = out->corners + 8 * i;
             float per = perimeter_f(c);
@@ -877,7 +955,10 @@ int orc_detect(const uint8_t *img, int W, int H, int channels, const orc_dict *d
     free(fcand);
     for (int g = 0; g < ng; g++) free(groups[g]);
     free(groups); free(gsz); free(gid); free(sel); free(S); free(valid); free(was); free(ids); free(rots); free(fc);
-    free(T); free(gray);
+    free(T);
+    if (gray != pyr[0]) free((void *)gray);
+    for (int l = 0; l <= numLevels; l++) free(pyr[l]);
+    (void)W0;
     return out->n_acc;
 }
 

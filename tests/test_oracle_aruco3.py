@@ -1,0 +1,52 @@
+"""Pin the oracle's ArUco3 path (useAruco3Detection: image pyramid, reduced segmentation image, identification in the pyramid level
+that suits each candidate, corner refinement up the pyramid) to what cv2 4.13.0 returns: tests/golden/aruco3.npz, written by
+tools/make_golden_aruco3.py.  No GPU, no cv2."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from aruco_slam_b200 import dictionaries as D
+
+A3 = golden("aruco3")
+SUBPIX_TOL = 0.05        # accepted corners go through cornerSubPix (float32 accumulations): same tolerance as the SUBPIX tests
+
+
+def a3_params(oracle, g, fixture, case):
+    i = list(A3["cases"]).index(case)
+    extra = {"r015_inv": {"detectInvertedMarker": 1}, "r020_contour": {"cornerRefinementMethod": 2}}.get(case, {})
+    return oracle.default_params(useAruco3Detection=1, minSideLengthCanonicalImg=int(A3["sides"][i]),
+                                 minMarkerLengthRatioOriginalImg=float(A3["%s/%s/ratio" % (fixture, case)]), **extra)
+
+
+def test_pyr_down_equals_cv2(oracle):
+    for i in range(int(A3["n_pyr"])):
+        assert np.array_equal(oracle.pyr_down(A3["pyr/%d/src" % i]), A3["pyr/%d/dst" % i]), i
+
+
+def test_resize_linear_equals_cv2(oracle):
+    for i in range(int(A3["n_resize"])):
+        dst = A3["resize/%d/dst" % i]
+        assert np.array_equal(oracle.resize_linear(A3["resize/%d/src" % i], dst.shape[1], dst.shape[0]), dst), i
+
+
+@pytest.mark.parametrize("fixture", [str(f) for f in A3["fixtures"]])
+def test_detect_aruco3(oracle, fixture):
+    g = golden(fixture)
+    dic = D.getPredefinedDictionary(int(g["dict_id"]))
+    n_markers = 0
+    for case in [str(c) for c in A3["cases"]]:
+        key = "%s/%s" % (fixture, case)
+        c, ids, rej = oracle.detect(g["frame"], dic, a3_params(oracle, g, fixture, case))
+        assert np.array_equal(ids, A3[key + "/ids"]), key
+        assert np.array_equal(rej, A3[key + "/rejected"]), key              # segmentation-image coordinates, bit exact
+        if len(ids):
+            assert np.abs(c - A3[key + "/corners"]).max() <= SUBPIX_TOL, key
+        n_markers += len(ids)
+    assert n_markers > 0 or fixture == "detect_blank"
+
+
+def test_aruco3_off_leaves_the_two_parameters_without_effect(oracle):
+    g = golden("detect_vga_4x4_s2")
+    dic = D.getPredefinedDictionary(int(g["dict_id"]))
+    c, ids, rej = oracle.detect(g["frame"], dic, oracle.default_params(minSideLengthCanonicalImg=64, minMarkerLengthRatioOriginalImg=0.05))
+    assert np.array_equal(ids, g["ids"]) and np.array_equal(c, g["corners"]) and np.array_equal(rej, g["rejected"])
