@@ -34,6 +34,7 @@ class DetectorParams(C.Structure):
         ("cornerRefinementWinSize", C.c_int), ("relativeCornerRefinmentWinSize", C.c_double),
         ("cornerRefinementMaxIterations", C.c_int), ("cornerRefinementMinAccuracy", C.c_double),
         ("detectInvertedMarker", C.c_int),
+        ("useAruco3Detection", C.c_int), ("minSideLengthCanonicalImg", C.c_int), ("minMarkerLengthRatioOriginalImg", C.c_float),
     ]
 
 

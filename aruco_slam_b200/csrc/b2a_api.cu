@@ -49,6 +49,7 @@ extern "C" void b2a_default_detector_params(b2a_detector_params *p)
     p->maxErroneousBitsInBorderRate = 0.35; p->minOtsuStdDev = 5.0; p->errorCorrectionRate = 0.6;
     p->cornerRefinementMethod = 0; p->cornerRefinementWinSize = 5; p->relativeCornerRefinmentWinSize = 0.3;
     p->cornerRefinementMaxIterations = 30; p->cornerRefinementMinAccuracy = 0.1; p->detectInvertedMarker = 0;
+    p->useAruco3Detection = 0; p->minSideLengthCanonicalImg = 32; p->minMarkerLengthRatioOriginalImg = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -213,6 +214,7 @@ struct b2a_detector {
     size_t gray_pitch = 0;
     // device memory
     uint8_t *d_in = nullptr, *d_gray = nullptr;
+    uint8_t *d_pyr = nullptr, *d_segimg = nullptr;   // ArUco3: pyramid levels 1.. of every frame ([level][frame] planes) and the segmentation images
     uint32_t *d_masks = nullptr; size_t masks_words = 0;
     // border graph (core.h): anchors of all (frame,scale) masks of a sub-batch share one slice of these arrays
     uint2 *d_ast = nullptr; Seg *d_seg = nullptr, *d_sseg = nullptr; uint32_t *d_minoff = nullptr, *d_ssoff = nullptr; int2 *d_emit = nullptr; uint32_t *d_amap = nullptr;
@@ -322,6 +324,15 @@ static int create_impl(b2a_detector *d)
     d->gray_pitch = ((size_t)W + 15) & ~(size_t)15;
     TRY(dev_alloc(d, &d->d_in, (size_t)B * std::max(P * 3, (((size_t)W + 3) & ~(size_t)3) * H)));
     TRY(dev_alloc(d, &d->d_gray, (size_t)B * d->gray_pitch * H));
+    if (p.useAruco3Detection) {
+        Aruco3Plan plan;
+        if (!aruco3_plan(W, H, p.minSideLengthCanonicalImg, p.minMarkerLengthRatioOriginalImg, plan))
+            return set_err(B2A_ERR_UNSUPPORTED, "ArUco3: the image pyramid of the largest frame needs more than 12 levels, or the segmentation image is smaller than its last level");
+        size_t per_frame = 0;
+        for (int l = 1; l <= plan.numLevels; ++l) per_frame += (((size_t)plan.W[l] + 15) & ~(size_t)15) * plan.H[l];
+        TRY(dev_alloc(d, &d->d_pyr, (size_t)B * per_frame));
+        TRY(dev_alloc(d, &d->d_segimg, (size_t)B * d->gray_pitch * H));
+    }
     const int WW = (W + 31) / 32, PWW = WW + 2;
     d->masks_words = (size_t)B * nS * PWW * (H + 2);
     TRY(dev_alloc(d, &d->d_masks, d->masks_words));
@@ -375,6 +386,7 @@ static int create_impl(b2a_detector *d)
     TRY(dev_alloc(d, &fs.closeM, BM * 2 * ((MC + 31) / 32)));       // M and its transpose
     TRY(dev_alloc(d, &fs.wq, BM * 8)); TRY(dev_alloc(d, &fs.wres, BM)); TRY(dev_alloc(d, &fs.closeStart, BM)); TRY(dev_alloc(d, &fs.closeNum, BM));
     TRY(dev_alloc(d, &fs.counters, (size_t)B * 8));
+    if (p.useAruco3Detection) { TRY(dev_alloc(d, &fs.tlen, BM)); TRY(dev_alloc(d, &fs.wlen, BM)); }
     TRY(dev_alloc(d, &d->d_wM, BM * 9));
     TRY(dev_alloc(d, &d->d_idcodes, (size_t)d->max_cand));
     const size_t BK = (size_t)B * d->max_markers;
@@ -388,7 +400,8 @@ static int create_impl(b2a_detector *d)
     TRY(pin_alloc(d, &d->h_rvecs, BK * 3)); TRY(pin_alloc(d, &d->h_tvecs, BK * 3));
     CU(cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(k_group_a, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (d->max_cand + 1) * (int)sizeof(uint32_t)));
-    CU(cudaFuncSetAttribute(k_identify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)identify_smem_bytes(ID_MAX_S)));
+    CU(cudaFuncSetAttribute(k_identify<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)identify_smem_bytes(ID_MAX_S)));
+    CU(cudaFuncSetAttribute(k_identify<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)identify_smem_bytes(ID_MAX_S)));
     CU(cudaFuncSetAttribute(k_threshold3<1, 6, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3_SMEM));
     CU(cudaFuncSetAttribute(k_threshold_march<1, 6, 11, 24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmCfg<24>::SMEM));
     CU(cudaFuncSetAttribute(k_threshold_march<1, 6, 11, 12, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmCfg<12>::SMEM));
@@ -414,6 +427,10 @@ extern "C" int b2a_detector_create(const b2a_detector_config *cfg, const b2a_dic
     if (prm.markerBorderBits < 1) return set_err(B2A_ERR_INVALID, "markerBorderBits < 1");
     if (prm.cornerRefinementMethod < 0 || prm.cornerRefinementMethod > 3) return set_err(B2A_ERR_INVALID, "cornerRefinementMethod");
     if (prm.cornerRefinementMethod == 3) return set_err(B2A_ERR_UNSUPPORTED, "CORNER_REFINE_APRILTAG (the AprilTag quad detector is not part of this library)");
+    if (prm.useAruco3Detection) {
+        if (prm.minSideLengthCanonicalImg < 1 || !(prm.minMarkerLengthRatioOriginalImg >= 0.f)) return set_err(B2A_ERR_INVALID, "ArUco3 needs minSideLengthCanonicalImg >= 1 and minMarkerLengthRatioOriginalImg >= 0");
+        prm.cornerRefinementMethod = 1;        // "always turn on corner refinement in case of Aruco3, due to upsampling" (detectMarkers)
+    }
     if (prm.adaptiveThreshWinSizeMin < 3 || prm.adaptiveThreshWinSizeMax < prm.adaptiveThreshWinSizeMin || prm.adaptiveThreshWinSizeStep <= 0)
         return set_err(B2A_ERR_INVALID, "adaptiveThreshWinSize*");
     if (dict->markerSize < 1 || dict->markerSize * dict->markerSize > 64 || dict->nBytes != (dict->markerSize * dict->markerSize + 7) / 8)
@@ -470,7 +487,9 @@ struct Sub {
     bool timed;              // stage events are recorded for sub-batch 0 only
     cudaEvent_t tl_after_h2d = nullptr;   // debug timeline
     DetGeom g;               // geometry with B = nb
-    const uint8_t *gray; size_t pitch, frame_stride;      // gray frames of this sub-batch
+    const uint8_t *gray; size_t pitch, frame_stride;      // gray frames of this sub-batch (ArUco3: the segmentation images)
+    PyrLevels pyr;           // ArUco3: the pyramid of the full-size gray frames (n = 0: off)
+    int closestIdx = 0;      // ArUco3: the pyramid level closest to the segmentation image
 };
 
 static int check_frames(b2a_detector *d, const b2a_frames *f)
@@ -535,13 +554,16 @@ static FrameScratch offset_scratch(const FrameScratch &b, size_t f, size_t mc)
     s.closeM += o * 2 * ((mc + 31) / 32);
     s.wq += o * 8; s.wres += o; s.closeStart += o; s.closeNum += o;
     s.counters += f * 8;
+    if (s.tlen) { s.tlen += o; s.wlen += o; }
     return s;
 }
 
 // ingest + A1 + A2 + A3 for one sub-batch: everything up to the quads of every (frame, scale)
 static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_len /* 0 = maxPerimeter */)
 {
-    const int W = f->width, H = f->height, nb = s.nb, b0 = s.b0;
+    int W = f->width, H = f->height;
+    const int nb = s.nb, b0 = s.b0;
+    const bool a3 = d->prm.useAruco3Detection != 0;
     const size_t in_pitch = f->row_stride ? f->row_stride : (size_t)W * f->channels;
     const size_t in_frame = f->frame_stride ? f->frame_stride : in_pitch * H;
     cudaStream_t st = s.st;
@@ -566,7 +588,7 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
     // gray plane for the later stages (S0 fused into S1); anything else takes the separate conversion pass
     static const bool fuse_env = !(std::getenv("B2A_FUSE_BGR") && std::atoi(std::getenv("B2A_FUSE_BGR")) == 0);
     const bool fuse_bgr = f->channels == 3 && fuse_env && default_windows && !d->thresh_tiles && (W & 3) == 0 && (src_pitch & 3) == 0 && (src_frame & 3) == 0 &&
-                          (((size_t)src) & 3) == 0 && src_pitch < (1ull << 32);
+                          (((size_t)src) & 3) == 0 && src_pitch < (1ull << 32) && !a3;     // ArUco3 needs the gray plane before the threshold
     if (f->channels == 3) {
         uint8_t *gdst = d->d_gray + (size_t)b0 * d->gray_pitch * H;
         if (!fuse_bgr) {
@@ -575,6 +597,41 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
         }
         s.gray = gdst; s.pitch = d->gray_pitch; s.frame_stride = d->gray_pitch * H;
     } else { s.gray = src; s.pitch = src_pitch; s.frame_stride = src_frame; }
+    s.pyr.n = 0;
+    if (a3) {
+        // the pyramid of the full-size gray frames (levels 1.. live in d_pyr as [level][frame] planes) and, when the factor is
+        // not 1, the reduced segmentation image that every later stage of the front end works on
+        Aruco3Plan plan;
+        if (!aruco3_plan(W, H, d->prm.minSideLengthCanonicalImg, d->prm.minMarkerLengthRatioOriginalImg, plan))
+            return set_err(B2A_ERR_INVALID, "ArUco3: for this frame size the segmentation image is smaller than the last pyramid level (cv2 reads past its pyramid there)");
+        PyrLevels &pl = s.pyr;
+        pl.n = plan.numLevels + 1; pl.segW = plan.segW; pl.minPerimeter = 4 * d->prm.minSideLengthCanonicalImg;
+        pl.W[0] = W; pl.H[0] = H; pl.base[0] = s.gray; pl.pitch[0] = s.pitch; pl.frame_stride[0] = s.frame_stride;
+        s.closestIdx = plan.closestIdx;
+        size_t off = 0;
+        for (int l = 1; l <= plan.numLevels; ++l) {
+            const size_t lp = ((size_t)plan.W[l] + 15) & ~(size_t)15, lf = lp * plan.H[l];
+            uint8_t *dst = d->d_pyr + off + (size_t)b0 * lf;
+            pl.W[l] = plan.W[l]; pl.H[l] = plan.H[l]; pl.base[l] = dst; pl.pitch[l] = lp; pl.frame_stride[l] = lf;
+            const long long px = (long long)nb * plan.W[l] * plan.H[l];
+            k_pyr_down<<<(unsigned)std::min<long long>((px + 255) / 256, (long long)d->num_sms * 8), 256, 0, st>>>(pl.base[l - 1], pl.W[l - 1], pl.H[l - 1], pl.pitch[l - 1], pl.frame_stride[l - 1],
+                                                                                                               dst, lp, lf, nb);
+            d->launches++;
+            off += (size_t)d->cfg.max_batch * lf;
+        }
+        if (plan.fxfy != 1.f) {
+            const size_t sp = ((size_t)plan.segW + 15) & ~(size_t)15, sf = sp * plan.segH;
+            uint8_t *seg = d->d_segimg + (size_t)b0 * sf;
+            const long long px = (long long)nb * plan.segW * plan.segH;
+            k_resize_linear<<<(unsigned)std::min<long long>((px + 255) / 256, (long long)d->num_sms * 8), 256, 0, st>>>(s.gray, W, H, s.pitch, s.frame_stride, seg, plan.segW, plan.segH, sp, sf, nb);
+            d->launches++;
+            s.gray = seg; s.pitch = sp; s.frame_stride = sf;
+            W = plan.segW; H = plan.segH;
+        }
+        s.g = make_geom(d, W, H, nb);
+        g.minPerim = pl.minPerimeter;          // _findMarkerContours: "for aruco3 we want to filter contours with min size"
+        DBG_SYNC(st);
+    }
     g.count_all = walk_max_len > 0 ? 1 : 0;          // the contour tap (exact counts, no give-up length) is the only caller that asks
     // this sub-batch's slice of the anchor arrays, and its per-(frame,scale) arrays addressed from frame b0
     const size_t fs0 = (size_t)b0 * g.nScales, FS = (size_t)nb * g.nScales;
@@ -730,6 +787,7 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
     ip.detectInverted = d->prm.detectInvertedMarker ? 1 : 0;
     ip.minOtsuStdDev = d->prm.minOtsuStdDev; ip.W = g.W; ip.H = g.H; ip.pitch = s.pitch; ip.frame_stride = s.frame_stride; ip.max_cand = d->max_cand;
     ip.marks = nullptr; ip.codes = nullptr;
+    ip.pyr = s.pyr;
 #ifdef B2A_DEBUG_TAPS
     static long long *id_marks = nullptr;
     if (std::getenv("B2A_IDENT_MARKS") && s.sb == 0) {
@@ -740,10 +798,11 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
     }
 #endif
     double *wM = d->d_wM + (size_t)b0 * d->max_cand * 9;
-    k_homography<<<dim3(4, nb), 64, 0, st>>>(fa, wM, (ip.markerSize + 2 * ip.borderBits) * ip.cellSize, d->max_cand);
+    k_homography<<<dim3(4, nb), 64, 0, st>>>(fa, wM, (ip.markerSize + 2 * ip.borderBits) * ip.cellSize, d->max_cand, s.pyr);
     d->launches++;
     static const int id_blocks = std::getenv("B2A_ID_BLOCKS") ? std::max(1, std::atoi(std::getenv("B2A_ID_BLOCKS"))) : 48;   // x 4 warps = work items of a frame in flight (a frame has ~124 of them; with 128 warps the frames that have more made a second round: 0.118 -> 0.102 ms)
-    k_identify<<<dim3(id_blocks, nb), ID_THREADS, identify_smem_bytes((ip.markerSize + 2 * ip.borderBits) * ip.cellSize), st>>>(s.gray, d->d_dict, wM, fa, ip);
+    if (s.pyr.n > 0) k_identify<true><<<dim3(id_blocks, nb), ID_THREADS, identify_smem_bytes((ip.markerSize + 2 * ip.borderBits) * ip.cellSize), st>>>(s.gray, d->d_dict, wM, fa, ip);
+    else k_identify<false><<<dim3(id_blocks, nb), ID_THREADS, identify_smem_bytes((ip.markerSize + 2 * ip.borderBits) * ip.cellSize), st>>>(s.gray, d->d_dict, wM, fa, ip);
     d->launches++;
 #ifdef B2A_DEBUG_TAPS
     if (ip.marks) {
@@ -768,11 +827,37 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
     k_finalize<<<nb, 128, 8 * sizeof(int32_t) * d->max_cand, st>>>(fa, fp);
     d->launches++;
     float *corners = fa.fo0.corners;
-    if (d->prm.cornerRefinementMethod == 1) {
+    if (s.pyr.n > 0) {
+        // ArUco3, findCornerInPyrImage: the accepted corners go to the pyramid level closest to the segmentation image and are then
+        // doubled and refined level by level down to the full-size frame; with closestIdx = 0 they are only scaled
+        const PyrLevels &pl = s.pyr;
+        SubpixParams sp;
+        sp.max_markers = d->max_markers; sp.markerSize = d->dict.markerSize; sp.borderBits = d->prm.markerBorderBits; sp.maxWin = d->prm.cornerRefinementWinSize;
+        sp.maxIter = d->prm.cornerRefinementMaxIterations; sp.relWin = d->prm.relativeCornerRefinmentWinSize; sp.eps = d->prm.cornerRefinementMinAccuracy;
+        float *c2 = d->d_corners2 + (size_t)b0 * K * 8;
+        const float scale_init = (float)pl.W[s.closestIdx] / (float)pl.segW;
+        if (s.closestIdx == 0) {
+            sp.W = pl.W[0]; sp.H = pl.H[0]; sp.pitch = pl.pitch[0]; sp.frame_stride = pl.frame_stride[0];
+            sp.fixedWin = 3; sp.refine = 0; sp.mul0 = scale_init; sp.mul1 = 1.f;
+            k_subpix<<<d->num_sms * 2, 128, 0, st>>>(pl.base[0], fa.fo0.n_accepted, fa.fo0.corners, c2, nb, sp);
+            d->launches++;
+        } else {
+            for (int idx = s.closestIdx - 1; idx >= 0; --idx) {
+                const bool first = idx == s.closestIdx - 1;
+                sp.W = pl.W[idx]; sp.H = pl.H[idx]; sp.pitch = pl.pitch[idx]; sp.frame_stride = pl.frame_stride[idx];
+                sp.fixedWin = std::max(pl.W[idx], pl.H[idx]) > 1080 ? 5 : 3; sp.refine = 1;
+                sp.mul0 = first ? scale_init : 2.f; sp.mul1 = first ? 2.f : 1.f;
+                k_subpix<<<d->num_sms * 2, 128, 0, st>>>(pl.base[idx], fa.fo0.n_accepted, first ? fa.fo0.corners : c2, c2, nb, sp);
+                d->launches++;
+            }
+        }
+        corners = c2;
+    } else if (d->prm.cornerRefinementMethod == 1) {
         SubpixParams sp;
         sp.W = g.W; sp.H = g.H; sp.pitch = s.pitch; sp.frame_stride = s.frame_stride; sp.max_markers = d->max_markers;
         sp.markerSize = d->dict.markerSize; sp.borderBits = d->prm.markerBorderBits; sp.maxWin = d->prm.cornerRefinementWinSize;
         sp.maxIter = d->prm.cornerRefinementMaxIterations; sp.relWin = d->prm.relativeCornerRefinmentWinSize; sp.eps = d->prm.cornerRefinementMinAccuracy;
+        sp.fixedWin = 0; sp.refine = 1; sp.mul0 = 1.f; sp.mul1 = 1.f;
         float *c2 = d->d_corners2 + (size_t)b0 * K * 8;
         k_subpix<<<d->num_sms * 2, 128, 0, st>>>(s.gray, fa.fo0.n_accepted, fa.fo0.corners, c2, nb, sp);
         d->launches++;
@@ -1362,11 +1447,12 @@ static int refine_extract_codes(b2a_detector *d, const b2a_frames *f, const floa
     ip.nMarkers = d->dict.nMarkers; ip.maxCorr = 0; ip.maxBorderErr = -1;            // only the extracted bits are wanted: no dictionary scan
     ip.detectInverted = 0; ip.minOtsuStdDev = d->prm.minOtsuStdDev; ip.W = W; ip.H = H; ip.pitch = gpitch; ip.frame_stride = gpitch * H; ip.max_cand = d->max_cand;
     ip.marks = nullptr;
+    ip.pyr.n = 0;
     unsigned long long *d_codes = d->d_idcodes;
     ip.codes = d_codes;
     const int S = (ip.markerSize + 2 * ip.borderBits) * ip.cellSize;
-    k_homography<<<dim3(4, 1), 64, 0, st>>>(fa, d->d_wM, S, d->max_cand);
-    k_identify<<<dim3(48, 1), ID_THREADS, identify_smem_bytes(S), st>>>(gray, d->d_dict, d->d_wM, fa, ip);
+    k_homography<<<dim3(4, 1), 64, 0, st>>>(fa, d->d_wM, S, d->max_cand, ip.pyr);
+    k_identify<false><<<dim3(48, 1), ID_THREADS, identify_smem_bytes(S), st>>>(gray, d->d_dict, d->d_wM, fa, ip);
     codes.resize((size_t)nw);
     CU(cudaMemcpyAsync(codes.data(), d_codes, (size_t)nw * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -1385,6 +1471,7 @@ extern "C" int b2a_refine_detected_markers(b2a_detector *d, const b2a_frames *im
     if (!(rp.minRepDistance > 0)) return set_err(B2A_ERR_INVALID, "minRepDistance must be positive");            // CV_Assert in refineDetectedMarkers
     if (board->n_markers <= 0 || !board->ids || !board->obj_points) return set_err(B2A_ERR_INVALID, "empty board");
     if (image->batch != 1) return set_err(B2A_ERR_INVALID, "refineDetectedMarkers takes one image");
+    if (d->prm.useAruco3Detection) return set_err(B2A_ERR_UNSUPPORTED, "refineDetectedMarkers on an ArUco3 detector (its rejected candidates are in the coordinates of the reduced image)");
     TRY(check_frames(d, image));
     const int nd = *n_detected, nr = *n_rejected, nbm = board->n_markers;
     if (nd < 0 || nr < 0 || nd > capacity) return set_err(B2A_ERR_INVALID, "bad counts");
@@ -1505,6 +1592,7 @@ extern "C" int b2a_refine_detected_markers(b2a_detector *d, const b2a_frames *im
         sp.W = image->width; sp.H = image->height; sp.pitch = gp; sp.frame_stride = gp * image->height; sp.max_markers = d->max_markers;
         sp.markerSize = d->dict.markerSize; sp.borderBits = d->prm.markerBorderBits; sp.maxWin = d->prm.cornerRefinementWinSize;
         sp.maxIter = d->prm.cornerRefinementMaxIterations; sp.relWin = d->prm.relativeCornerRefinmentWinSize; sp.eps = d->prm.cornerRefinementMinAccuracy;
+        sp.fixedWin = 0; sp.refine = 1; sp.mul0 = 1.f; sp.mul1 = 1.f;
         const uint8_t *gray = bgr ? d->d_gray : (image->on_device ? image->data : d->d_in);
         if (m > d->max_markers) return set_err(B2A_ERR_CAPACITY, "recovered markers exceed max_markers");
         k_subpix<<<d->num_sms * 2, 128, 0, st>>>(gray, d->fo0.n_accepted, d->fo0.corners, d->d_corners2, 1, sp);

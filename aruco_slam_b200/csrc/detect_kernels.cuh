@@ -23,6 +23,7 @@
 #include "core.h"
 #include "frame_logic.h"
 #include "refine_core.h"
+#include "pyr_core.h"
 
 namespace b2a {
 
@@ -1304,6 +1305,7 @@ __device__ __forceinline__ FrameScratch frame_scratch(const FrameScratch &b, int
     s.closeM += o * 2 * (size_t)((mc + 31) / 32);
     s.wq += o * 8; s.wres += o; s.closeStart += o; s.closeNum += o;
     s.counters += (size_t)f * 8;
+    if (s.tlen) { s.tlen += o; s.wlen += o; }
     return s;
 }
 
@@ -1401,18 +1403,26 @@ struct IdentParams {
     int max_cand;
     long long *marks;            // debug: clock64 after each phase of work item 0 of frame 0 (null = off)
     unsigned long long *codes;   // optional [frames][max_cand]: every work item's inner bits as extracted (before the inverted-marker choice)
+    PyrLevels pyr;               // ArUco3: the image pyramid a work item picks its level from (n = 0: off)
 };
 
 // A7 step 1: the inverse perspective map of every work item, one thread each (cv2's 8x8 LU lives in
 // ~150 registers; keeping it out of k_identify lets that kernel run many more warps per SM)
 __global__ void __launch_bounds__(64)
-k_homography(FrameArrays fa, double *__restrict__ wM, int S, int max_cand)
+k_homography(FrameArrays fa, double *__restrict__ wM, int S, int max_cand, PyrLevels pyr)
 {
     const int f = blockIdx.y;
     const int nw = fa.fs0.counters[(size_t)f * 8 + FC_NWORK];
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += gridDim.x * blockDim.x) {
         double M[9];
-        perspective_inverse(fa.fs0.wq + ((size_t)f * max_cand + w) * 8, S, M);
+        const float *q = fa.fs0.wq + ((size_t)f * max_cand + w) * 8;
+        float sq[8];
+        if (pyr.n > 0) {                 // ArUco3: the quad in the coordinates of the pyramid level it is read in
+            const int lvl = pyr_opt_level(pyr.W, pyr.n, pyr.segW, fa.fs0.wlen[(size_t)f * max_cand + w], pyr.minPerimeter);
+            pyr_scale_quad(q, f_div((float)pyr.W[lvl], (float)pyr.segW), sq);
+            q = sq;
+        }
+        perspective_inverse(q, S, M);
 #pragma unroll
         for (int i = 0; i < 9; ++i) wM[((size_t)f * max_cand + w) * 9 + i] = M[i];
     }
@@ -1426,6 +1436,8 @@ inline size_t identify_smem_bytes(int S) { return (size_t)ID_WARPS * (3 * 256 * 
 // A7 step 2.  One WARP per work item: the sequential pieces (the Otsu recurrence, the border
 // check) run on lane 0 while the other warps of the SM work on other candidates; sampling, the
 // between-class variances, the cell votes and the dictionary scan are spread over the 32 lanes.
+// PYR (ArUco3): every work item reads the pyramid level its contour length picks (pyr_opt_level) instead of `gray`
+template <bool PYR>
 __global__ void __launch_bounds__(ID_THREADS, 7)
 k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restrict__ dict, const double *__restrict__ wM, FrameArrays fa, IdentParams ip)
 {
@@ -1445,10 +1457,17 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
     const int S = nb * ip.cellSize;
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const uint8_t *img = gray + (size_t)f * ip.frame_stride;
+    int iW = ip.W, iH = ip.H;
+    size_t ipitch = ip.pitch;
     const unsigned FULL = 0xFFFFFFFFu;
     for (int w = blockIdx.x * ID_WARPS + wp; w < nw; w += gridDim.x * ID_WARPS) {
         for (int i = lane; i < 256; i += 32) histw[i] = 0;
         __syncwarp();
+        if (PYR) {
+            const int lvl = pyr_opt_level(ip.pyr.W, ip.pyr.n, ip.pyr.segW, fa.fs0.wlen[(size_t)f * ip.max_cand + w], ip.pyr.minPerimeter);
+            img = ip.pyr.base[lvl] + (size_t)f * ip.pyr.frame_stride[lvl];
+            iW = ip.pyr.W[lvl]; iH = ip.pyr.H[lvl]; ipitch = ip.pyr.pitch[lvl];
+        }
         double M[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) M[i] = __ldg(wM + ((size_t)f * ip.max_cand + w) * 9 + i);
@@ -1469,7 +1488,7 @@ k_identify(const uint8_t *__restrict__ gray, const unsigned long long *__restric
             for (int k = 0; k < 4; ++k) {
                 pp[k] = base + k * 32 + lane;
                 const int y = pp[k] / S, x = pp[k] - y * S;
-                off[k] = pp[k] < S * S ? warp_source(ip.W, ip.H, ip.pitch, M, x, y) : -1;
+                off[k] = pp[k] < S * S ? warp_source(iW, iH, ipitch, M, x, y) : -1;
             }
             unsigned v[4];
 #pragma unroll
@@ -1607,6 +1626,11 @@ struct SubpixParams {
     int W, H; size_t pitch, frame_stride;
     int max_markers, markerSize, borderBits, maxWin, maxIter;
     double relWin, eps;
+    // ArUco3's refinement up the pyramid (findCornerInPyrImage): the corner is first multiplied by mul0, then by mul1 (two float
+    // products, as cv2 scales to the closest level and then doubles per level), the window is fixedWin (0 = the relative rule of
+    // CORNER_REFINE_SUBPIX) and refine = 0 only scales.  With fixedWin a thread touches its own corner only: in place is fine.
+    int fixedWin, refine;
+    float mul0, mul1;
 };
 
 __device__ __forceinline__ float subpix_sample(const uint8_t *img, int W, int H, size_t pitch, int ipx, int ipy, float a11, float a12, float a21, float a22, int x, int y)
@@ -1625,15 +1649,19 @@ __global__ void k_subpix(const uint8_t *__restrict__ gray, const int32_t *__rest
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const int f = t / (sp.max_markers * 4), r = t - f * sp.max_markers * 4, mk = r >> 2;
         if (mk >= n_acc[f]) continue;
-        const float *c = corners + ((size_t)f * sp.max_markers + mk) * 8;
-        const float per = quad_perimeter(c);
-        const int nm = sp.markerSize + 2 * sp.borderBits;
-        int win = (int)lroundf((float)sp.relWin * f_div(per, 4.f * (float)nm));
-        win = win < 1 ? 1 : (win > sp.maxWin ? sp.maxWin : win);
+        int win = sp.fixedWin;
+        if (win == 0) {
+            const float *c = corners + ((size_t)f * sp.max_markers + mk) * 8;
+            const float per = quad_perimeter(c);
+            const int nm = sp.markerSize + 2 * sp.borderBits;
+            win = (int)lroundf((float)sp.relWin * f_div(per, 4.f * (float)nm));
+            win = win < 1 ? 1 : (win > sp.maxWin ? sp.maxWin : win);
+        }
         const uint8_t *img = gray + (size_t)f * sp.frame_stride;
         const float *pin = corners + ((size_t)f * sp.max_markers + mk) * 8 + (r & 3) * 2;
         float *pt = corners_out + ((size_t)f * sp.max_markers + mk) * 8 + (r & 3) * 2;
-        const float cTx = pin[0], cTy = pin[1];
+        const float cTx = f_mul(f_mul(pin[0], sp.mul0), sp.mul1), cTy = f_mul(f_mul(pin[1], sp.mul0), sp.mul1);
+        if (!sp.refine) { pt[0] = cTx; pt[1] = cTy; continue; }
         float cIx = cTx, cIy = cTy;
         const int ww = 2 * win + 1;
         const double eps2 = sp.eps * sp.eps;
@@ -1720,6 +1748,35 @@ k_refine_contour(const float *__restrict__ corners, const int32_t *__restrict__ 
     }
     if (lg.lane() == 0)
         for (int k = 0; k < 8; ++k) co[k] = done ? r[k] : cin[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// ArUco3 (useAruco3Detection): the image pyramid (cv::buildPyramid = repeated cv::pyrDown) and the reduced segmentation image
+// (cv::resize, INTER_LINEAR) of every frame of a sub-batch; one thread per destination pixel (pyr_core.h)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pyr_down(const uint8_t *__restrict__ src, int W, int H, size_t spitch, size_t sframe, uint8_t *__restrict__ dst, size_t dpitch, size_t dframe, int nb)
+{
+    const int dW = (W + 1) / 2, dH = (H + 1) / 2;
+    const long long total = (long long)nb * dW * dH;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(t % dW);
+        const long long r = t / dW;
+        const int y = (int)(r % dH), b = (int)(r / dH);
+        dst[(size_t)b * dframe + (size_t)y * dpitch + x] = pyr_down_pixel(src + (size_t)b * sframe, W, H, spitch, x, y);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_resize_linear(const uint8_t *__restrict__ src, int W, int H, size_t spitch, size_t sframe, uint8_t *__restrict__ dst, int dW, int dH, size_t dpitch, size_t dframe, int nb)
+{
+    const long long total = (long long)nb * dW * dH;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(t % dW);
+        const long long r = t / dW;
+        const int y = (int)(r % dH), b = (int)(r / dH);
+        dst[(size_t)b * dframe + (size_t)y * dpitch + x] = resize_pixel(src + (size_t)b * sframe, W, H, spitch, dW, dH, x, y);
+    }
 }
 
 }  // namespace b2a

@@ -57,6 +57,10 @@ struct FrameScratch {
     int32_t *closeStart;// [max_cand]  selected -> first work item of its close list
     int32_t *closeNum;  // [max_cand]
     int32_t *counters;  // [8]: 0 n_cand, 1 n_sel, 2 n_work, 3 status
+    // ArUco3 (null when the mode is off): contour lengths in T order, and per work item the contour length of the selected
+    // candidate whose list it belongs to (a group's close candidates are read in their representative's pyramid level)
+    int32_t *tlen;      // [max_cand]
+    int32_t *wlen;      // [max_cand]
 };
 
 enum { FC_NCAND = 0, FC_NSEL = 1, FC_NWORK = 2, FC_STATUS = 3 };
@@ -132,6 +136,7 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
     for (int i = tid; i < n; i += nt) {
         const int r = fs.members[i];
         for (int k = 0; k < 8; ++k) fs.tq[(size_t)r * 8 + k] = fs.cq[(size_t)i * 8 + k];
+        if (fs.tlen) fs.tlen[r] = fs.clen[i];
     }
     ctx.sync();
     for (int i = tid; i < n; i += nt) {
@@ -320,10 +325,12 @@ B2A_HD void frame_group(Ctx &ctx, const FrameParams &fp, const ScaleQuads &sq, c
     const int nw = fs.counters[FC_NWORK];
     for (int v = tid; v < nS; v += nt) {
         for (int k = 0; k < 8; ++k) fs.wq[(size_t)v * 8 + k] = tq[(size_t)S[v] * 8 + k];
+        if (fs.wlen) fs.wlen[v] = fs.tlen[S[v]];
         const int g = selGroup[v];
         for (int c = 0; c < closeNum[v]; ++c) {
             const int id = fs.closeIdx[fs.gstart[g] + c];
             for (int k = 0; k < 8; ++k) fs.wq[(size_t)(closeStart[v] + c) * 8 + k] = tq[(size_t)id * 8 + k];
+            if (fs.wlen) fs.wlen[closeStart[v] + c] = fs.tlen[S[v]];
         }
     }
     for (int w = tid; w < nw; w += nt) fs.wres[w] = 0;

@@ -60,6 +60,15 @@ typedef struct {
     int    cornerRefinementMaxIterations;         /* 30 */
     double cornerRefinementMinAccuracy;           /* 0.1 */
     int    detectInvertedMarker;                  /* 0 */
+    /* ArUco3 ("Speeded up detection of squared fiducial markers", the mode cv2 enables with useAruco3Detection): candidates are
+     * searched in a reduced copy of the frame (factor minSide / (minSide + max(W, H) * ratio), cv::resize INTER_LINEAR), every
+     * candidate is identified in the level of the frame's image pyramid (cv::buildPyramid) where its contour is just longer than
+     * 4 * minSide, and the accepted corners are refined level by level up to the full-size frame (cornerSubPix, window 3, or 5
+     * above 1080 px); cornerRefinementMethod is then CORNER_REFINE_SUBPIX whatever was asked, and -- as in cv2 4.13 -- the
+     * REJECTED quads stay in the coordinates of the reduced image.  Needs minSideLengthCanonicalImg >= 1 and a ratio >= 0. */
+    int    useAruco3Detection;                    /* 0 */
+    int    minSideLengthCanonicalImg;             /* 32 */
+    float  minMarkerLengthRatioOriginalImg;       /* 0 */
 } b2a_detector_params;
 
 void b2a_default_detector_params(b2a_detector_params *p);

@@ -103,7 +103,8 @@ inline bool same_params(const b2a_detector_params &a, const b2a_detector_params 
            a.errorCorrectionRate == b.errorCorrectionRate && a.cornerRefinementMethod == b.cornerRefinementMethod &&
            a.cornerRefinementWinSize == b.cornerRefinementWinSize && a.relativeCornerRefinmentWinSize == b.relativeCornerRefinmentWinSize &&
            a.cornerRefinementMaxIterations == b.cornerRefinementMaxIterations && a.cornerRefinementMinAccuracy == b.cornerRefinementMinAccuracy &&
-           a.detectInvertedMarker == b.detectInvertedMarker;
+           a.detectInvertedMarker == b.detectInvertedMarker && a.useAruco3Detection == b.useAruco3Detection &&
+           a.minSideLengthCanonicalImg == b.minSideLengthCanonicalImg && a.minMarkerLengthRatioOriginalImg == b.minMarkerLengthRatioOriginalImg;
 }
 inline b2a_detector *handle_for(const Dictionary &dict, const DetectorParameters &prm, int cols, int rows)
 {

@@ -22,7 +22,7 @@ class EmuParams(C.Structure):
 
 
 def build():
-    srcs = [os.path.join(_HERE, "hostemu.cpp")] + [os.path.join(_CSRC, f) for f in ("core.h", "frame_logic.h", "pose_core.h", "draw_core.h", "refine_core.h", "board_core.h")] + [os.path.join(_CSRC, "..", "data", "overlay_tables.inc")]
+    srcs = [os.path.join(_HERE, "hostemu.cpp")] + [os.path.join(_CSRC, f) for f in ("core.h", "frame_logic.h", "pose_core.h", "draw_core.h", "refine_core.h", "board_core.h", "pyr_core.h")] + [os.path.join(_CSRC, "..", "data", "overlay_tables.inc")]
     if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", _SO, srcs[0]])
     return _SO
@@ -93,6 +93,41 @@ def detect(gray, dic, masks=None, dbg_scale=-1, anchor_R=32, detect_inverted=Fal
         out["kept_len"] = ln
         out["kept_pts"] = dpts[:int(ln.sum())].copy()
     return out
+
+
+def pyr_down(gray):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    H, W = gray.shape
+    out = np.zeros(((H + 1) // 2, (W + 1) // 2), np.uint8)
+    lib().emu_pyr_down(gray.ctypes.data_as(C.c_void_p), W, H, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def resize_linear(gray, dW, dH):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    H, W = gray.shape
+    out = np.zeros((dH, dW), np.uint8)
+    lib().emu_resize_linear(gray.ctypes.data_as(C.c_void_p), W, H, out.ctypes.data_as(C.c_void_p), int(dW), int(dH))
+    return out
+
+
+def detect_aruco3(gray, dic, min_side=32, ratio=0.0, detect_inverted=False):
+    """ArUco3 through the product's headers: ids / rejected as the device returns them, accepted corners before the refinement
+    chain (segmentation-image coordinates), plan = (segW, segH, numLevels, closestIdx); None when the plan is refused"""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    H, W = gray.shape
+    p = params_for(dic, detect_inverted=detect_inverted)
+    d = pack_dict(dic)
+    n_acc, n_rej = C.c_int(), C.c_int()
+    corners = np.zeros((p.max_markers, 4, 2), np.float32)
+    ids = np.zeros(p.max_markers, np.int32)
+    rej = np.zeros((p.max_markers, 4, 2), np.float32)
+    plan = np.zeros(4, np.int32)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    st = lib().emu_detect_aruco3(P(gray), W, H, P(d), C.byref(p), int(min_side), C.c_float(ratio), C.byref(n_acc), C.byref(n_rej), P(corners), P(ids), P(rej), P(plan))
+    if st < 0:
+        return None
+    return dict(status=st, corners=corners[:n_acc.value].copy(), ids=ids[:n_acc.value].copy(), rejected=rej[:n_rej.value].copy(), plan=tuple(int(v) for v in plan))
 
 
 def pose(corners, K, D, L):

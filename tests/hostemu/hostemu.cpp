@@ -9,6 +9,7 @@
 #include "../../aruco_slam_b200/csrc/draw_core.h"
 #include "../../aruco_slam_b200/csrc/refine_core.h"
 #include "../../aruco_slam_b200/csrc/board_core.h"
+#include "../../aruco_slam_b200/csrc/pyr_core.h"
 
 #include <algorithm>
 #include <cmath>
@@ -74,20 +75,19 @@ static void emu_threshold(const uint8_t *g, int W, int H, int r, int C, uint32_t
         }
 }
 
-extern "C" {
-
 // masks_in: optional [nScales][H][W] u8 masks to use instead of thresholding (0 = compute)
 // outputs: n_acc/n_rej, corners[max_markers*8], ids, rejected; debug: n_contours[nScales] (incl. one-point borders),
 // n_cand, cand[max_cand*8]; kept contour lengths / points of scale dbg_scale
-int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const unsigned long long *dict, const EmuParams *ep,
+// pyr (ArUco3): gray is the segmentation image, candidates are identified in the pyramid level pyr_opt_level picks
+static int emu_detect_impl(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const unsigned long long *dict, const EmuParams *ep,
                int *n_acc, int *n_rej, float *corners, int32_t *ids, float *rejected,
                int *n_contours, int *n_cand, float *cand,
-               int dbg_scale, int *dbg_nkept, int *dbg_len, int dbg_cap, int16_t *dbg_pts, int dbg_pts_cap, int anchor_R)
+               int dbg_scale, int *dbg_nkept, int *dbg_len, int dbg_cap, int16_t *dbg_pts, int dbg_pts_cap, int anchor_R, const PyrLevels *pyr)
 {
     const int nS = ep->nScales, WW = (W + 31) / 32, PWW = WW + 2, KS = W + 1;
     const size_t plane_words = (size_t)PWW * (H + 2);
     const int maxWH = std::max(W, H);
-    const int minPerim = (int)(unsigned)(ep->minPerimRate * maxWH), maxPerim = (int)(unsigned)(ep->maxPerimRate * maxWH);
+    const int minPerim = pyr ? pyr->minPerimeter : (int)(unsigned)(ep->minPerimRate * maxWH), maxPerim = (int)(unsigned)(ep->maxPerimRate * maxWH);
     std::vector<uint32_t> masks(plane_words * nS, 0);
     for (int s = 0; s < nS; ++s) {
         uint32_t *pl = masks.data() + plane_words * s;
@@ -261,11 +261,11 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
     const int MC = ep->max_cand;
     std::vector<float> cq((size_t)MC * 8), tq((size_t)MC * 8), tper(MC), cent((size_t)MC * 3), wq((size_t)MC * 8);
     std::vector<int32_t> clen(MC), gid(MC), sel(MC), gstart(MC + 1), gfill(MC), members(MC), closeIdx(MC), closeCnt(MC), S(MC), parent(MC), depth(MC),
-        selGroup(MC), wres(MC), closeStart(MC), closeNum(MC), counters(8, 0);
+        selGroup(MC), wres(MC), closeStart(MC), closeNum(MC), counters(8, 0), tlen(MC), wlen(MC);
     std::vector<uint32_t> closeM((size_t)MC * 2 * ((MC + 31) / 32));
     FrameScratch fs{cq.data(), clen.data(), tq.data(), tper.data(), cent.data(), gid.data(), sel.data(), gstart.data(), gfill.data(), members.data(),
                     closeIdx.data(), closeCnt.data(), S.data(), parent.data(), depth.data(), selGroup.data(), closeM.data(),
-                    wq.data(), wres.data(), closeStart.data(), closeNum.data(), counters.data()};
+                    wq.data(), wres.data(), closeStart.data(), closeNum.data(), counters.data(), pyr ? tlen.data() : nullptr, pyr ? wlen.data() : nullptr};
     FrameParams fp;
     fp.W = W; fp.H = H; fp.nScales = nS; fp.surv_cap = surv_cap; fp.max_cand = MC; fp.max_markers = ep->max_markers;
     fp.markerSize = ep->markerSize; fp.borderBits = ep->borderBits; fp.minDistanceToBorder = ep->minDistanceToBorder;
@@ -280,13 +280,22 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
     const int nb = ep->markerSize + 2 * ep->borderBits, Sz = nb * ep->cellSize, m0 = ep->cellSize / 2;
     for (int w = 0; w < counters[FC_NWORK]; ++w) {
         double M[9];
-        perspective_inverse(wq.data() + (size_t)w * 8, Sz, M);
+        const float *q = wq.data() + (size_t)w * 8;
+        float sq8[8];
+        const uint8_t *im = gray; int iW = W, iH = H; size_t ipitch = (size_t)W;
+        if (pyr) {               // k_homography / k_identify<true>
+            const int lvl = pyr_opt_level(pyr->W, pyr->n, pyr->segW, wlen[w], pyr->minPerimeter);
+            pyr_scale_quad(q, f_div((float)pyr->W[lvl], (float)pyr->segW), sq8);
+            q = sq8;
+            im = pyr->base[lvl]; iW = pyr->W[lvl]; iH = pyr->H[lvl]; ipitch = pyr->pitch[lvl];
+        }
+        perspective_inverse(q, Sz, M);
         std::vector<uint8_t> patch((size_t)Sz * Sz);
         int hist[256] = {0};
         long long sum = 0, sqs = 0;
         for (int p = 0; p < Sz * Sz; ++p) {
             const int y = p / Sz, x = p - y * Sz;
-            const unsigned v = warp_sample(gray, W, H, (size_t)W, M, x, y);
+            const unsigned v = warp_sample(im, iW, iH, ipitch, M, x, y);
             patch[p] = (uint8_t)v; hist[v]++;
             if (x >= m0 && x < Sz - m0 && y >= m0 && y < Sz - m0) { sum += v; sqs += v * v; }
         }
@@ -307,6 +316,56 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
     FrameOutputs fo{n_acc, n_rej, corners, ids, rejected, &st};
     frame_finalize(ctx, fp, fs, fo);
     return st;
+}
+
+extern "C" {
+
+int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const unsigned long long *dict, const EmuParams *ep,
+               int *n_acc, int *n_rej, float *corners, int32_t *ids, float *rejected,
+               int *n_contours, int *n_cand, float *cand,
+               int dbg_scale, int *dbg_nkept, int *dbg_len, int dbg_cap, int16_t *dbg_pts, int dbg_pts_cap, int anchor_R)
+{
+    return emu_detect_impl(gray, W, H, masks_in, dict, ep, n_acc, n_rej, corners, ids, rejected, n_contours, n_cand, cand, dbg_scale, dbg_nkept, dbg_len, dbg_cap,
+                           dbg_pts, dbg_pts_cap, anchor_R, nullptr);
+}
+
+// ArUco3 (pyr_core.h): one pyrDown / one resize, a pixel at a time as the kernels compute them
+void emu_pyr_down(const uint8_t *src, int W, int H, uint8_t *dst)
+{
+    const int dW = (W + 1) / 2, dH = (H + 1) / 2;
+    for (int y = 0; y < dH; ++y) for (int x = 0; x < dW; ++x) dst[(size_t)y * dW + x] = pyr_down_pixel(src, W, H, (size_t)W, x, y);
+}
+void emu_resize_linear(const uint8_t *src, int W, int H, uint8_t *dst, int dW, int dH)
+{
+    for (int y = 0; y < dH; ++y) for (int x = 0; x < dW; ++x) dst[(size_t)y * dW + x] = resize_pixel(src, W, H, (size_t)W, dW, dH, x, y);
+}
+
+// the ArUco3 front half of a call as run_front / run_back arrange it: plan, pyramid, segmentation image, detection in it with the
+// identification in the pyramid; the accepted corners come back UNREFINED in segmentation-image coordinates (the refinement chain
+// is k_subpix, device only) together with the plan (seg size, closest level, level-0-to-seg scale) for the caller
+int emu_detect_aruco3(const uint8_t *gray, int W, int H, const unsigned long long *dict, const EmuParams *ep, int minSide, float ratio,
+                      int *n_acc, int *n_rej, float *corners, int32_t *ids, float *rejected, int *plan_out /* segW, segH, numLevels, closestIdx */)
+{
+    Aruco3Plan plan;
+    if (!aruco3_plan(W, H, minSide, ratio, plan)) return -1;
+    std::vector<std::vector<uint8_t>> lv((size_t)plan.numLevels + 1);
+    PyrLevels pl;
+    pl.n = plan.numLevels + 1; pl.segW = plan.segW; pl.minPerimeter = 4 * minSide;
+    pl.W[0] = W; pl.H[0] = H; pl.base[0] = gray; pl.pitch[0] = (size_t)W; pl.frame_stride[0] = 0;
+    for (int l = 1; l <= plan.numLevels; ++l) {
+        lv[l].resize((size_t)plan.W[l] * plan.H[l]);
+        emu_pyr_down(pl.base[l - 1], pl.W[l - 1], pl.H[l - 1], lv[l].data());
+        pl.W[l] = plan.W[l]; pl.H[l] = plan.H[l]; pl.base[l] = lv[l].data(); pl.pitch[l] = (size_t)plan.W[l]; pl.frame_stride[l] = 0;
+    }
+    std::vector<uint8_t> seg;
+    const uint8_t *sg = gray;
+    if (plan.fxfy != 1.f) { seg.resize((size_t)plan.segW * plan.segH); emu_resize_linear(gray, W, H, seg.data(), plan.segW, plan.segH); sg = seg.data(); }
+    plan_out[0] = plan.segW; plan_out[1] = plan.segH; plan_out[2] = plan.numLevels; plan_out[3] = plan.closestIdx;
+    std::vector<int> ncont(ep->nScales);
+    std::vector<float> cand((size_t)ep->max_cand * 8);
+    int n_cand = 0, nk = 0;
+    return emu_detect_impl(sg, plan.segW, plan.segH, nullptr, dict, ep, n_acc, n_rej, corners, ids, rejected, ncont.data(), &n_cand, cand.data(), -1, &nk, nullptr, 0,
+                           nullptr, 0, 32, &pl);
 }
 
 // approxPolyDP(closed) of the product (one lane) on an integer contour; returns the vertex count (-1: gave up, > 8 vertices)

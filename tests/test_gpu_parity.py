@@ -547,3 +547,78 @@ def test_pack_detections_round_trip(aruco):
     with pytest.raises(B2AError):
         aruco.pack_detections(raw, np.zeros(64, np.uint8))
     det.close()
+
+
+# ---- ArUco3 (useAruco3Detection) ------------------------------------------------------------------------------------------
+_A3 = golden("aruco3")
+_A3_EXTRA = {"r015_inv": {"detectInvertedMarker": 1}, "r020_contour": {"cornerRefinementMethod": 2}}
+
+
+@pytest.mark.parametrize("fixture", [str(f) for f in _A3["fixtures"]])
+def test_aruco3_vs_golden(aruco, fixture):
+    """useAruco3Detection on the GPU path against cv2 4.13 (tests/golden/aruco3.npz): ids and the rejected quads (which cv2 leaves in
+    the coordinates of the reduced image) bit exact and in order, accepted corners (refined up the pyramid) <= 0.05 px"""
+    g = golden(fixture)
+    gray = g["frame"]
+    dic = D.getPredefinedDictionary(int(g["dict_id"]))
+    for ci, case in enumerate([str(c) for c in _A3["cases"]]):
+        key = "%s/%s" % (fixture, case)
+        det = _detector(aruco, dic, gray.shape, useAruco3Detection=1, minSideLengthCanonicalImg=int(_A3["sides"][ci]),
+                        minMarkerLengthRatioOriginalImg=float(_A3[key + "/ratio"]), **_A3_EXTRA.get(case, {}))
+        r = det.detect_batch(gray)
+        assert np.array_equal(r.ids[0], _A3[key + "/ids"]), key
+        assert np.array_equal(r.rejected[0], _A3[key + "/rejected"]), key
+        if len(r.ids[0]):
+            assert np.abs(r.corners[0] - _A3[key + "/corners"]).max() < 0.05, key
+        det.close()
+
+
+def test_aruco3_batch_colour_pose_vs_oracle(aruco, oracle):
+    """a batch of colour 1080p frames through the sub-batch streams and, one frame at a time, through the graph replay: every frame
+    equal to the oracle's ArUco3 path; the poses follow from the refined corners"""
+    B = 6
+    gray = synth.render_batch("C2", B, base_seed=300)
+    bgr = np.stack([synth.gray_to_bgr(f, 3 + i) for i, f in enumerate(gray)])
+    dic = D.getPredefinedDictionary(D.DICT_6X6_250)
+    K = np.array([[1400.0, 0, 960], [0, 1400.0, 540], [0, 0, 1]])
+    Dist = np.array([0.05, -0.1, 0.001, -0.002, 0.02])
+    for ratio, side in ((0.02, 32), (0.0, 32), (32 / 1920, 32)):
+        prm = dict(useAruco3Detection=1, minSideLengthCanonicalImg=side, minMarkerLengthRatioOriginalImg=ratio)
+        det = _detector(aruco, dic, gray.shape[1:], batch=B, **prm)
+        r = det.detect_pose_batch(bgr, 0.27, K, Dist)
+        n = 0
+        for b in range(B):
+            oc, oi, orj = oracle.detect(bgr[b], dic, oracle.default_params(**prm))
+            assert np.array_equal(r.ids[b], oi) and np.array_equal(r.rejected[b], orj), (ratio, b)
+            if len(oi):
+                assert np.abs(r.corners[b] - oc).max() < 0.05, (ratio, b)
+                orv, otv = oracle.estimate_pose_single_markers(r.corners[b], 0.27, K, Dist)
+                assert np.abs(r.tvecs[b] - otv).max() < 1e-4
+                assert max(synth.rvec_distance(a, c) for a, c in zip(r.rvecs[b], orv)) < 1e-4
+            n += len(oi)
+        assert n > 3 * B
+        # single frames (graph replay, gray input) give the same as the batch
+        for b in (0, B - 1):
+            r1 = det.detect_batch(gray[b])
+            oc, oi, orj = oracle.detect(gray[b], dic, oracle.default_params(**prm))
+            assert np.array_equal(r1.ids[0], oi) and np.array_equal(r1.rejected[0], orj)
+            if len(oi):
+                assert np.abs(r1.corners[0] - oc).max() < 0.05
+            r2 = det.detect_batch(gray[b])
+            assert np.array_equal(r1.corners[0], r2.corners[0]) and np.array_equal(r1.ids[0], r2.ids[0])
+        det.close()
+
+
+def test_aruco3_parameter_checks(aruco):
+    from aruco_slam_b200._lib import B2AError
+    dic = D.getPredefinedDictionary(0)
+    with pytest.raises(B2AError):
+        _detector(aruco, dic, (480, 640), useAruco3Detection=1, minSideLengthCanonicalImg=0)
+    with pytest.raises(B2AError):
+        _detector(aruco, dic, (480, 640), useAruco3Detection=1, minMarkerLengthRatioOriginalImg=-0.1)
+    # the two parameters do nothing while the mode is off
+    g = golden("detect_vga_4x4_s2")
+    det = _detector(aruco, dic, g["frame"].shape, minSideLengthCanonicalImg=64, minMarkerLengthRatioOriginalImg=0.05)
+    r = det.detect_batch(g["frame"])
+    assert np.array_equal(r.ids[0], g["ids"]) and np.array_equal(r.corners[0], g["corners"]) and np.array_equal(r.rejected[0], g["rejected"])
+    det.close()

@@ -50,3 +50,47 @@ def test_aruco3_off_leaves_the_two_parameters_without_effect(oracle):
     dic = D.getPredefinedDictionary(int(g["dict_id"]))
     c, ids, rej = oracle.detect(g["frame"], dic, oracle.default_params(minSideLengthCanonicalImg=64, minMarkerLengthRatioOriginalImg=0.05))
     assert np.array_equal(ids, g["ids"]) and np.array_equal(c, g["corners"]) and np.array_equal(rej, g["rejected"])
+
+
+# ---- the product's ArUco3 logic (pyr_core.h, frame_logic.h) compiled for the host: tests/hostemu ----
+@pytest.fixture(scope="module")
+def emu():
+    from hostemu import emu as E
+    E.lib()
+    return E
+
+
+def test_product_pyr_down_and_resize_equal_cv2(emu):
+    for i in range(int(A3["n_pyr"])):
+        assert np.array_equal(emu.pyr_down(A3["pyr/%d/src" % i]), A3["pyr/%d/dst" % i]), i
+    for i in range(int(A3["n_resize"])):
+        dst = A3["resize/%d/dst" % i]
+        assert np.array_equal(emu.resize_linear(A3["resize/%d/src" % i], dst.shape[1], dst.shape[0]), dst), i
+
+
+def test_product_pyramid_equals_oracle_on_frames(emu, oracle):
+    g = golden("detect_vga_4x4_s2")["frame"]
+    cur_e = cur_o = g
+    for _ in range(4):
+        cur_e, cur_o = emu.pyr_down(cur_e), oracle.pyr_down(cur_o)
+        assert np.array_equal(cur_e, cur_o)
+    for dw, dh in ((457, 343), (320, 240), (213, 160), (639, 479)):
+        assert np.array_equal(emu.resize_linear(g, dw, dh), oracle.resize_linear(g, dw, dh))
+
+
+@pytest.mark.parametrize("fixture", [str(f) for f in A3["fixtures"] if "1080p" not in str(f) and "720p" not in str(f)])
+def test_product_logic_aruco3_vs_cv2(emu, fixture):
+    """level choice, scaled identification, perimeter gate of the product headers: ids and rejected equal cv2's; the accepted
+    corners before the refinement chain are the refined ones to within the refinement's reach"""
+    g = golden(fixture)
+    dic = D.getPredefinedDictionary(int(g["dict_id"]))
+    H, W = g["frame"].shape
+    for ci, case in enumerate([str(c) for c in A3["cases"]]):
+        key = "%s/%s" % (fixture, case)
+        out = emu.detect_aruco3(g["frame"], dic, int(A3["sides"][ci]), float(A3[key + "/ratio"]), detect_inverted=(case == "r015_inv"))
+        assert out is not None and out["status"] == 0, key
+        assert np.array_equal(out["ids"], A3[key + "/ids"]), key
+        assert np.array_equal(out["rejected"], A3[key + "/rejected"]), key
+        if len(out["ids"]):
+            up = out["corners"] * (W / out["plan"][0])
+            assert np.abs(up - A3[key + "/corners"]).max() <= 2.0 * (W / out["plan"][0]) + 3.0, key
