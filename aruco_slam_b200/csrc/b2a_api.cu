@@ -214,6 +214,7 @@ struct b2a_detector {
     size_t gray_pitch = 0;
     // device memory
     uint8_t *d_in = nullptr, *d_gray = nullptr;
+    int2 *d_rtab = nullptr;                       // ArUco3: the resize tables of each sub-batch ([MAX_SUB][max_width + max_height])
     uint8_t *d_pyr = nullptr, *d_segimg = nullptr;   // ArUco3: pyramid levels 1.. of every frame ([level][frame] planes) and the segmentation images
     uint32_t *d_masks = nullptr; size_t masks_words = 0;
     // border graph (core.h): anchors of all (frame,scale) masks of a sub-batch share one slice of these arrays
@@ -332,6 +333,7 @@ static int create_impl(b2a_detector *d)
         for (int l = 1; l <= plan.numLevels; ++l) per_frame += (((size_t)plan.W[l] + 15) & ~(size_t)15) * plan.H[l];
         TRY(dev_alloc(d, &d->d_pyr, (size_t)B * per_frame));
         TRY(dev_alloc(d, &d->d_segimg, (size_t)B * d->gray_pitch * H));
+        TRY(dev_alloc(d, &d->d_rtab, (size_t)b2a_detector::MAX_SUB * ((size_t)W + H)));
     }
     const int WW = (W + 31) / 32, PWW = WW + 2;
     d->masks_words = (size_t)B * nS * PWW * (H + 2);
@@ -611,20 +613,25 @@ static int run_front(b2a_detector *d, const b2a_frames *f, Sub &s, int walk_max_
         size_t off = 0;
         for (int l = 1; l <= plan.numLevels; ++l) {
             const size_t lp = ((size_t)plan.W[l] + 15) & ~(size_t)15, lf = lp * plan.H[l];
-            uint8_t *dst = d->d_pyr + off + (size_t)b0 * lf;
-            pl.W[l] = plan.W[l]; pl.H[l] = plan.H[l]; pl.base[l] = dst; pl.pitch[l] = lp; pl.frame_stride[l] = lf;
-            const long long px = (long long)nb * plan.W[l] * plan.H[l];
-            k_pyr_down<<<(unsigned)std::min<long long>((px + 255) / 256, (long long)d->num_sms * 8), 256, 0, st>>>(pl.base[l - 1], pl.W[l - 1], pl.H[l - 1], pl.pitch[l - 1], pl.frame_stride[l - 1],
-                                                                                                               dst, lp, lf, nb);
-            d->launches++;
+            pl.W[l] = plan.W[l]; pl.H[l] = plan.H[l]; pl.base[l] = d->d_pyr + off + (size_t)b0 * lf; pl.pitch[l] = lp; pl.frame_stride[l] = lf;
             off += (size_t)d->cfg.max_batch * lf;
         }
+        // the large levels by the whole grid, one launch each; once a frame's level is a few thousand 4-pixel groups, the rest of the
+        // pyramid by one CTA per frame in one launch (measured: a CTA per frame from level 2 on cost 0.13 ms more per 32 frames)
+        int l = 1;
+        for (; l <= plan.numLevels && ((plan.W[l] + 3) / 4) * plan.H[l] > 4096; ++l) {
+            k_pyr_down<<<(unsigned)std::min<long long>(((long long)nb * plan.H[l] + 3) / 4, (long long)d->num_sms * 8), dim3(64, 4), 0, st>>>(pl.base[l - 1], pl.W[l - 1], pl.H[l - 1], pl.pitch[l - 1], pl.frame_stride[l - 1],
+                                                                                                                   const_cast<uint8_t *>(pl.base[l]), pl.pitch[l], pl.frame_stride[l], nb);
+            d->launches++;
+        }
+        if (l <= plan.numLevels) { k_pyr_chain<<<nb, 1024, 0, st>>>(pl, l); d->launches++; }
         if (plan.fxfy != 1.f) {
             const size_t sp = ((size_t)plan.segW + 15) & ~(size_t)15, sf = sp * plan.segH;
             uint8_t *seg = d->d_segimg + (size_t)b0 * sf;
-            const long long px = (long long)nb * plan.segW * plan.segH;
-            k_resize_linear<<<(unsigned)std::min<long long>((px + 255) / 256, (long long)d->num_sms * 8), 256, 0, st>>>(s.gray, W, H, s.pitch, s.frame_stride, seg, plan.segW, plan.segH, sp, sf, nb);
-            d->launches++;
+            int2 *tab = d->d_rtab + (size_t)s.sb * ((size_t)d->cfg.max_width + d->cfg.max_height);
+            k_resize_tabs<<<(plan.segW + plan.segH + 255) / 256, 256, 0, st>>>(W, H, plan.segW, plan.segH, tab);
+            k_resize_linear<<<(unsigned)std::min<long long>(((long long)nb * plan.segH + 3) / 4, (long long)d->num_sms * 8), dim3(64, 4), 0, st>>>(s.gray, W, H, s.pitch, s.frame_stride, seg, plan.segW, plan.segH, sp, sf, nb, tab);
+            d->launches += 2;
             s.gray = seg; s.pitch = sp; s.frame_stride = sf;
             W = plan.segW; H = plan.segH;
         }
@@ -738,6 +745,18 @@ static FrameParams frame_params(const b2a_detector *d, const DetGeom &g)
     return fp;
 }
 
+// cornerSubPix of the accepted corners: a warp per corner while the largest window's patch fits the default shared memory
+// (windows up to 25), else a thread per corner
+static void launch_subpix(b2a_detector *d, cudaStream_t st, const uint8_t *gray, const int32_t *n_acc, const float *cin, float *cout, int nb, const SubpixParams &sp)
+{
+    const int wmax = sp.fixedWin > 0 ? sp.fixedWin : std::max(1, sp.maxWin);
+    const size_t smem = subpix_warp_smem_bytes(wmax);
+    static const bool thread_form = std::getenv("B2A_SUBPIX_THREAD") != nullptr;          // A/B switch
+    if (smem <= 48 * 1024 && !thread_form) k_subpix_warp<<<d->num_sms * 8, 128, smem, st>>>(gray, n_acc, cin, cout, nb, sp, wmax);
+    else k_subpix<<<d->num_sms * 2, 128, 0, st>>>(gray, n_acc, cin, cout, nb, sp);
+    d->launches++;
+}
+
 static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_after_group)
 {
     const DetGeom &g = s.g;
@@ -839,16 +858,14 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
         if (s.closestIdx == 0) {
             sp.W = pl.W[0]; sp.H = pl.H[0]; sp.pitch = pl.pitch[0]; sp.frame_stride = pl.frame_stride[0];
             sp.fixedWin = 3; sp.refine = 0; sp.mul0 = scale_init; sp.mul1 = 1.f;
-            k_subpix<<<d->num_sms * 2, 128, 0, st>>>(pl.base[0], fa.fo0.n_accepted, fa.fo0.corners, c2, nb, sp);
-            d->launches++;
+            launch_subpix(d, st, pl.base[0], fa.fo0.n_accepted, fa.fo0.corners, c2, nb, sp);
         } else {
             for (int idx = s.closestIdx - 1; idx >= 0; --idx) {
                 const bool first = idx == s.closestIdx - 1;
                 sp.W = pl.W[idx]; sp.H = pl.H[idx]; sp.pitch = pl.pitch[idx]; sp.frame_stride = pl.frame_stride[idx];
                 sp.fixedWin = std::max(pl.W[idx], pl.H[idx]) > 1080 ? 5 : 3; sp.refine = 1;
                 sp.mul0 = first ? scale_init : 2.f; sp.mul1 = first ? 2.f : 1.f;
-                k_subpix<<<d->num_sms * 2, 128, 0, st>>>(pl.base[idx], fa.fo0.n_accepted, first ? fa.fo0.corners : c2, c2, nb, sp);
-                d->launches++;
+                launch_subpix(d, st, pl.base[idx], fa.fo0.n_accepted, first ? fa.fo0.corners : c2, c2, nb, sp);
             }
         }
         corners = c2;
@@ -859,8 +876,7 @@ static int run_back(b2a_detector *d, Sub &s, const b2a_camera *cam, bool stop_af
         sp.maxIter = d->prm.cornerRefinementMaxIterations; sp.relWin = d->prm.relativeCornerRefinmentWinSize; sp.eps = d->prm.cornerRefinementMinAccuracy;
         sp.fixedWin = 0; sp.refine = 1; sp.mul0 = 1.f; sp.mul1 = 1.f;
         float *c2 = d->d_corners2 + (size_t)b0 * K * 8;
-        k_subpix<<<d->num_sms * 2, 128, 0, st>>>(s.gray, fa.fo0.n_accepted, fa.fo0.corners, c2, nb, sp);
-        d->launches++;
+        launch_subpix(d, st, s.gray, fa.fo0.n_accepted, fa.fo0.corners, c2, nb, sp);
         corners = c2;
     } else if (d->prm.cornerRefinementMethod == 2) {
         float *c2 = d->d_corners2 + (size_t)b0 * K * 8;
@@ -1595,7 +1611,7 @@ extern "C" int b2a_refine_detected_markers(b2a_detector *d, const b2a_frames *im
         sp.fixedWin = 0; sp.refine = 1; sp.mul0 = 1.f; sp.mul1 = 1.f;
         const uint8_t *gray = bgr ? d->d_gray : (image->on_device ? image->data : d->d_in);
         if (m > d->max_markers) return set_err(B2A_ERR_CAPACITY, "recovered markers exceed max_markers");
-        k_subpix<<<d->num_sms * 2, 128, 0, st>>>(gray, d->fo0.n_accepted, d->fo0.corners, d->d_corners2, 1, sp);
+        launch_subpix(d, st, gray, d->fo0.n_accepted, d->fo0.corners, d->d_corners2, 1, sp);
         CU(cudaMemcpyAsync(corners + (size_t)nd * 8, d->d_corners2, (size_t)m * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         TRY(launch_err("refine: k_subpix"));

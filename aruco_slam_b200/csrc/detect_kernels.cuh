@@ -1706,6 +1706,94 @@ __global__ void k_subpix(const uint8_t *__restrict__ gray, const int32_t *__rest
     }
 }
 
+// The same refinement with one WARP per corner (the form the pipeline launches; k_subpix stays for windows too large for shared
+// memory): the lanes build the bilinearly interpolated (ww + 2)^2 patch around the corner once per iteration in shared memory
+// (cv2's getRectSubPix; the thread form recomputes every patch value up to four times), split the ww^2 gradient terms -- each term
+// computed exactly as above -- and add their partial sums with a butterfly, so every lane holds the same normal equations and takes
+// the same step; the Gaussian window weights are computed once per corner.  Only the ORDER of the double-precision sums differs
+// from the sequential loop (results agree to the last bits of the float corner).
+__device__ __forceinline__ double warp_sum_f64(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+inline size_t subpix_warp_smem_bytes(int wmax) { return (size_t)4 * ((size_t)(2 * wmax + 3) * (2 * wmax + 3) + 2 * wmax + 1) * sizeof(float); }
+
+__global__ void __launch_bounds__(128)
+k_subpix_warp(const uint8_t *__restrict__ gray, const int32_t *__restrict__ n_acc, const float *__restrict__ corners,
+              float *__restrict__ corners_out, int B, SubpixParams sp, int wmax)
+{
+    extern __shared__ float spw_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int pw_max = 2 * wmax + 3;
+    float *patch = spw_smem + (size_t)wib * (pw_max * pw_max + 2 * wmax + 1);
+    float *mask = patch + pw_max * pw_max;
+    const int total = B * sp.max_markers * 4;
+    for (int t = blockIdx.x * 4 + wib; t < total; t += gridDim.x * 4) {
+        const int f = t / (sp.max_markers * 4), r = t - f * sp.max_markers * 4, mk = r >> 2;
+        if (mk >= n_acc[f]) continue;
+        int win = sp.fixedWin;
+        if (win == 0) {
+            const float *c = corners + ((size_t)f * sp.max_markers + mk) * 8;
+            const float per = quad_perimeter(c);
+            const int nm = sp.markerSize + 2 * sp.borderBits;
+            win = (int)lroundf((float)sp.relWin * f_div(per, 4.f * (float)nm));
+            win = win < 1 ? 1 : (win > sp.maxWin ? sp.maxWin : win);
+        }
+        if (win > wmax) win = wmax;                                       // cannot happen: wmax is the largest window of the launch
+        const uint8_t *img = gray + (size_t)f * sp.frame_stride;
+        const float *pin = corners + ((size_t)f * sp.max_markers + mk) * 8 + (r & 3) * 2;
+        float *pt = corners_out + ((size_t)f * sp.max_markers + mk) * 8 + (r & 3) * 2;
+        const float cTx = f_mul(f_mul(pin[0], sp.mul0), sp.mul1), cTy = f_mul(f_mul(pin[1], sp.mul0), sp.mul1);
+        if (!sp.refine) { if (lane == 0) { pt[0] = cTx; pt[1] = cTy; } continue; }
+        float cIx = cTx, cIy = cTy;
+        const int ww = 2 * win + 1, pw = ww + 2;
+        __syncwarp();
+        for (int i = lane; i < ww; i += 32) {
+            const float yy = (float)(i - win) / (float)win;
+            mask[i] = (float)exp(-(double)(yy * yy));
+        }
+        const double eps2 = sp.eps * sp.eps;
+        int iter = 0; double err = 0;
+        do {
+            const float fx = cIx - (float)(ww + 1) * 0.5f, fy = cIy - (float)(ww + 1) * 0.5f;
+            const int ipx = (int)floorf(fx), ipy = (int)floorf(fy);
+            const float a = fx - (float)ipx, b = fy - (float)ipy;
+            const float a11 = f_mul(1.f - a, 1.f - b), a12 = f_mul(a, 1.f - b), a21 = f_mul(1.f - a, b), a22 = f_mul(a, b);
+            __syncwarp();
+            for (int p = lane; p < pw * pw; p += 32) {
+                const int y = p / pw, x = p - y * pw;
+                patch[p] = subpix_sample(img, sp.W, sp.H, sp.pitch, ipx, ipy, a11, a12, a21, a22, x, y);
+            }
+            __syncwarp();
+            double A = 0, Bm = 0, C = 0, bb1 = 0, bb2 = 0;
+            for (int p = lane; p < ww * ww; p += 32) {
+                const int i = p / ww, j = p - i * ww;
+                const double m = (double)f_mul(mask[i], mask[j]);
+                const double tgx = (double)patch[(i + 1) * pw + j + 2] - (double)patch[(i + 1) * pw + j];
+                const double tgy = (double)patch[(i + 2) * pw + j + 1] - (double)patch[i * pw + j + 1];
+                const double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
+                const double px = j - win, py = i - win;
+                A += gxx; Bm += gxy; C += gyy;
+                bb1 += gxx * px + gxy * py;
+                bb2 += gxy * px + gyy * py;
+            }
+            A = warp_sum_f64(A); Bm = warp_sum_f64(Bm); C = warp_sum_f64(C); bb1 = warp_sum_f64(bb1); bb2 = warp_sum_f64(bb2);
+            const double det = A * C - Bm * Bm;
+            if (fabs(det) <= DBL_EPSILON * DBL_EPSILON) break;
+            const double scale = 1.0 / det;
+            const float nx = (float)((double)cIx + (C * scale * bb1 - Bm * scale * bb2));
+            const float ny = (float)((double)cIy + (-Bm * scale * bb1 + A * scale * bb2));
+            err = (double)((nx - cIx) * (nx - cIx) + (ny - cIy) * (ny - cIy));
+            cIx = nx; cIy = ny;
+            if (cIx < 0 || cIx >= (float)sp.W || cIy < 0 || cIy >= (float)sp.H) break;
+        } while (++iter < sp.maxIter && err > eps2);
+        if (fabsf(cIx - cTx) > (float)win || fabsf(cIy - cTy) > (float)win) { cIx = cTx; cIy = cTy; }
+        if (lane == 0) { pt[0] = cIx; pt[1] = cIy; }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // A8 (optional): CORNER_REFINE_CONTOUR, one warp per accepted marker (refine_core.h).  The marker's contour is still in the
 // point arrays of the contour stage; the warp finds it by its quad, sums the four sides and lane 0 writes the crossings.
@@ -1754,28 +1842,97 @@ k_refine_contour(const float *__restrict__ corners, const int32_t *__restrict__ 
 // ArUco3 (useAruco3Detection): the image pyramid (cv::buildPyramid = repeated cv::pyrDown) and the reduced segmentation image
 // (cv::resize, INTER_LINEAR) of every frame of a sub-batch; one thread per destination pixel (pyr_core.h)
 // ---------------------------------------------------------------------------------------------
+// a thread makes four neighbouring destination pixels (one word store when all four exist).  Source window inside the image: word
+// loads + dp4a when the rows are word aligned, byte loads otherwise; window across the border: reflected indices (images of at
+// least 3 x 3 pixels), pixel by pixel below that
+__device__ __forceinline__ void pyr_down_group(const uint8_t *sb, int W, int H, size_t spitch, bool aligned, uint8_t *drow, int dW, int x0, int y)
+{
+    uint32_t word;
+    if (pyr_down_is_interior4(W, H, dW, x0, y)) {
+        const bool words = aligned && 2 * x0 - 4 >= 0 && 2 * x0 + 11 < W;
+        word = words ? pyr_down_interior4<true>(sb, spitch, x0, y) : pyr_down_interior4<false>(sb, spitch, x0, y);
+    } else if (W >= 3 && H >= 3) word = pyr_down_border4(sb, W, H, spitch, dW, x0, y);
+    else {
+        word = 0;
+        for (int q = 0; q < 4 && x0 + q < dW; ++q) word |= (uint32_t)pyr_down_pixel(sb, W, H, spitch, x0 + q, y) << (8 * q);
+    }
+    if (x0 + 3 < dW) *reinterpret_cast<uint32_t *>(drow + x0) = word;
+    else for (int q = 0; x0 + q < dW; ++q) drow[x0 + q] = (uint8_t)(word >> (8 * q));
+}
+
+// one level of every frame: block = 64 groups x 4 rows, blockIdx.x walks the rows of all frames (row index = frame * dH + y)
 __global__ void __launch_bounds__(256)
 k_pyr_down(const uint8_t *__restrict__ src, int W, int H, size_t spitch, size_t sframe, uint8_t *__restrict__ dst, size_t dpitch, size_t dframe, int nb)
 {
-    const int dW = (W + 1) / 2, dH = (H + 1) / 2;
-    const long long total = (long long)nb * dW * dH;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(t % dW);
-        const long long r = t / dW;
-        const int y = (int)(r % dH), b = (int)(r / dH);
-        dst[(size_t)b * dframe + (size_t)y * dpitch + x] = pyr_down_pixel(src + (size_t)b * sframe, W, H, spitch, x, y);
+    const int dW = (W + 1) / 2, dH = (H + 1) / 2, gW = (dW + 3) / 4;
+    const bool aligned = ((spitch | sframe | (size_t)src) & 3) == 0;
+    const unsigned rows = (unsigned)nb * (unsigned)dH;
+    for (unsigned R = blockIdx.x * 4u + threadIdx.y; R < rows; R += gridDim.x * 4u) {
+        const unsigned b = R / (unsigned)dH;
+        const int y = (int)(R - b * (unsigned)dH);
+        const uint8_t *sb = src + (size_t)b * sframe;
+        uint8_t *drow = dst + (size_t)b * dframe + (size_t)y * dpitch;
+        for (int gx = threadIdx.x; gx < gW; gx += 64) pyr_down_group(sb, W, H, spitch, aligned, drow, dW, 4 * gx, y);
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_resize_linear(const uint8_t *__restrict__ src, int W, int H, size_t spitch, size_t sframe, uint8_t *__restrict__ dst, int dW, int dH, size_t dpitch, size_t dframe, int nb)
+// levels first .. n - 1 of one frame per CTA, one after the other (a level depends on the whole level before it, and the last
+// levels of a frame are a few thousand pixels: launches and their gaps would cost more than the work)
+__global__ void __launch_bounds__(1024)
+k_pyr_chain(PyrLevels pl, int first)
 {
-    const long long total = (long long)nb * dW * dH;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(t % dW);
-        const long long r = t / dW;
-        const int y = (int)(r % dH), b = (int)(r / dH);
-        dst[(size_t)b * dframe + (size_t)y * dpitch + x] = resize_pixel(src + (size_t)b * sframe, W, H, spitch, dW, dH, x, y);
+    const int b = blockIdx.x;
+    for (int l = first; l < pl.n; ++l) {
+        const uint8_t *sb = pl.base[l - 1] + (size_t)b * pl.frame_stride[l - 1];
+        uint8_t *db = const_cast<uint8_t *>(pl.base[l]) + (size_t)b * pl.frame_stride[l];
+        const int W = pl.W[l - 1], H = pl.H[l - 1], dW = pl.W[l], dH = pl.H[l], gW = (dW + 3) / 4;
+        const size_t spitch = pl.pitch[l - 1], dpitch = pl.pitch[l];
+        const bool aligned = ((spitch | (size_t)sb) & 3) == 0;
+        for (int t = threadIdx.x; t < gW * dH; t += blockDim.x) {
+            const int y = t / gW, gx = t - y * gW;
+            pyr_down_group(sb, W, H, spitch, aligned, db + (size_t)y * dpitch, dW, 4 * gx, y);
+        }
+        __syncthreads();                 // the level is complete (and visible to this CTA) before the next one reads it
+    }
+}
+
+// the two tables of one resize (source index; 11-bit weights c0 | c1 << 16 per destination column / row): dW + dH entries per call
+__global__ void k_resize_tabs(int W, int H, int dW, int dH, int2 *__restrict__ tab)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dW + dH; i += gridDim.x * blockDim.x) {
+        int s, c0, c1;
+        if (i < dW) resize_tab(i, dW, W, s, c0, c1); else resize_tab(i - dW, dH, H, s, c0, c1);
+        tab[i] = make_int2(s, c0 | (c1 << 16));
+    }
+}
+
+// a thread makes four neighbouring destination pixels of a row (one word store; dpitch is a multiple of 4); block = 64 groups x 4
+// rows, blockIdx.x walks the rows of all frames
+__global__ void __launch_bounds__(256)
+k_resize_linear(const uint8_t *__restrict__ src, int W, int H, size_t spitch, size_t sframe, uint8_t *__restrict__ dst, int dW, int dH, size_t dpitch, size_t dframe, int nb,
+                const int2 *__restrict__ tab)
+{
+    const int gW = (dW + 3) / 4;
+    const bool area = (W == 2 * dW && H == 2 * dH);
+    const unsigned rows = (unsigned)nb * (unsigned)dH;
+    for (unsigned R = blockIdx.x * 4u + threadIdx.y; R < rows; R += gridDim.x * 4u) {
+        const unsigned b = R / (unsigned)dH;
+        const int y = (int)(R - b * (unsigned)dH);
+        const uint8_t *sb = src + (size_t)b * sframe;
+        uint8_t *drow = dst + (size_t)b * dframe + (size_t)y * dpitch;
+        const int2 ty = area ? make_int2(0, 0) : __ldg(tab + dW + y);
+        for (int gx = threadIdx.x; gx < gW; gx += 64) {
+            const int x0 = 4 * gx;
+            uint32_t word = 0;
+            for (int q = 0; q < 4 && x0 + q < dW; ++q) {
+                uint32_t v;
+                if (area) v = resize_pixel(sb, W, H, spitch, dW, dH, x0 + q, y);
+                else { const int2 tx = __ldg(tab + x0 + q); v = resize_pixel_tab(sb, W, H, spitch, tx.x, tx.y & 0xFFFF, tx.y >> 16, ty.x, ty.y & 0xFFFF, ty.y >> 16); }
+                word |= v << (8 * q);
+            }
+            if (x0 + 3 < dW) *reinterpret_cast<uint32_t *>(drow + x0) = word;
+            else for (int q = 0; x0 + q < dW; ++q) drow[x0 + q] = (uint8_t)(word >> (8 * q));
+        }
     }
 }
 

@@ -20,6 +20,12 @@ B2A_HD int pyr_reflect101(int p, int len)
     while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
     return p;
 }
+// the same for -2 <= p <= len + 1 and len >= 3 (every index pyrDown forms on an image of at least 3 pixels): one reflection, no loop
+B2A_HD int pyr_reflect101_near(int p, int len)
+{
+    p = p < 0 ? -p : p;
+    return p >= len ? 2 * (len - 1) - p : p;
+}
 
 // destination pixel (dx, dy) of pyrDown of a W x H image
 B2A_HD uint8_t pyr_down_pixel(const uint8_t *src, int W, int H, size_t pitch, int dx, int dy)
@@ -60,6 +66,16 @@ B2A_HD void resize_tab(int d, int dlen, int slen, int &s, int &c0, int &c1)
     c1 = pyr_round_half_even(f_mul(f, 2048.f));
 }
 
+// one destination pixel from its two table entries (source column sx with weights a0, a1; source row sy with b0, b1)
+B2A_HD uint8_t resize_pixel_tab(const uint8_t *src, int W, int H, size_t pitch, int sx, int a0, int a1, int sy, int b0, int b1)
+{
+    const int sx1 = sx + 1 < W ? sx + 1 : W - 1, sy1 = sy + 1 < H ? sy + 1 : H - 1;
+    const uint8_t *s0 = src + (size_t)sy * pitch, *s1 = src + (size_t)sy1 * pitch;
+    const int r0 = (int)s0[sx] * a0 + (int)s0[sx1] * a1, r1 = (int)s1[sx] * a0 + (int)s1[sx1] * a1;
+    const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+    return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+}
+
 // destination pixel (dx, dy) of cv::resize(src W x H -> dW x dH, INTER_LINEAR)
 B2A_HD uint8_t resize_pixel(const uint8_t *src, int W, int H, size_t pitch, int dW, int dH, int dx, int dy)
 {
@@ -70,11 +86,78 @@ B2A_HD uint8_t resize_pixel(const uint8_t *src, int W, int H, size_t pitch, int 
     int sx, a0, a1, sy, b0, b1;
     resize_tab(dx, dW, W, sx, a0, a1);
     resize_tab(dy, dH, H, sy, b0, b1);
-    const int sx1 = sx + 1 < W ? sx + 1 : W - 1, sy1 = sy + 1 < H ? sy + 1 : H - 1;
-    const uint8_t *s0 = src + (size_t)sy * pitch, *s1 = src + (size_t)sy1 * pitch;
-    const int r0 = (int)s0[sx] * a0 + (int)s0[sx1] * a1, r1 = (int)s1[sx] * a0 + (int)s1[sx1] * a1;
-    const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-    return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+    return resize_pixel_tab(src, W, H, pitch, sx, a0, a1, sy, b0, b1);
+}
+
+// sum of the four bytes of a weighted by the four bytes of b (dp4a.u32.u32)
+B2A_HD uint32_t pyr_dp4a(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    return __dp4a(a, b, c);
+#else
+    for (int k = 0; k < 4; ++k) c += ((a >> (8 * k)) & 255u) * ((b >> (8 * k)) & 255u);
+    return c;
+#endif
+}
+
+// four neighbouring destination pixels (dx0 .. dx0 + 3, dy; dx0 a multiple of 4) of pyrDown whose 5 x 11 source window lies inside
+// the image: the same sums as pyr_down_pixel without the border reflection, packed into one word (byte 0 = dx0).
+// ALIGNED (rows of src start on word boundaries): a row's 11 bytes come as four words starting at column 2 dx0 - 4 and every
+// horizontal [1 4 6 4 1] is two dp4a; otherwise byte loads.
+template <bool ALIGNED>
+B2A_HD uint32_t pyr_down_interior4(const uint8_t *src, size_t pitch, int dx0, int dy)
+{
+    uint32_t v[4] = {0, 0, 0, 0};
+    B2A_UNROLL
+    for (int k = 0; k < 5; ++k) {
+        const uint32_t wk = (k == 0 || k == 4) ? 1u : (k == 2 ? 6u : 4u);
+        const uint8_t *row = src + (size_t)(2 * dy + k - 2) * pitch;
+        if (ALIGNED) {
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(row + (2 * dx0 - 4));
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+            // window byte n = source column 2 dx0 - 4 + n; pixel q needs bytes 2 q + 2 .. 2 q + 6 with weights 1 4 6 4 1
+            const uint32_t h0 = pyr_dp4a(w0, 0x04010000u, pyr_dp4a(w1, 0x00010406u, 0u));
+            const uint32_t h1 = pyr_dp4a(w1, 0x04060401u, pyr_dp4a(w2, 0x00000001u, 0u));
+            const uint32_t h2 = pyr_dp4a(w1, 0x04010000u, pyr_dp4a(w2, 0x00010406u, 0u));
+            const uint32_t h3 = pyr_dp4a(w2, 0x04060401u, pyr_dp4a(w3, 0x00000001u, 0u));
+            v[0] += wk * h0; v[1] += wk * h1; v[2] += wk * h2; v[3] += wk * h3;
+        } else {
+            const uint8_t *s = row + (2 * dx0 - 2);
+            uint32_t t[11];
+            B2A_UNROLL
+            for (int i = 0; i < 11; ++i) t[i] = s[i];
+            B2A_UNROLL
+            for (int q = 0; q < 4; ++q) v[q] += wk * (t[2 * q] + t[2 * q + 4] + 4 * (t[2 * q + 1] + t[2 * q + 3]) + 6 * t[2 * q + 2]);
+        }
+    }
+    return ((v[0] + 128) >> 8) | (((v[1] + 128) >> 8) << 8) | (((v[2] + 128) >> 8) << 16) | (((v[3] + 128) >> 8) << 24);
+}
+// up to four neighbouring destination pixels (dx0 .. min(dx0 + 3, dW - 1), dy) anywhere in an image of at least 3 x 3 pixels: the
+// 11 source columns and 5 source rows are reflected once each, then the sums of pyr_down_pixel; bytes of missing pixels are 0
+B2A_HD uint32_t pyr_down_border4(const uint8_t *src, int W, int H, size_t pitch, int dW, int dx0, int dy)
+{
+    int xs[11];
+    B2A_UNROLL
+    for (int i = 0; i < 11; ++i) { const int p = 2 * dx0 - 2 + i; xs[i] = pyr_reflect101_near(p > W + 1 ? W + 1 : p, W); }     // columns past W + 1 belong to pixels >= dW
+    uint32_t v[4] = {0, 0, 0, 0};
+    B2A_UNROLL
+    for (int k = 0; k < 5; ++k) {
+        const uint32_t wk = (k == 0 || k == 4) ? 1u : (k == 2 ? 6u : 4u);
+        const uint8_t *s = src + (size_t)pyr_reflect101_near(2 * dy + k - 2, H) * pitch;
+        uint32_t t[11];
+        B2A_UNROLL
+        for (int i = 0; i < 11; ++i) t[i] = s[xs[i]];
+        B2A_UNROLL
+        for (int q = 0; q < 4; ++q) v[q] += wk * (t[2 * q] + t[2 * q + 4] + 4 * (t[2 * q + 1] + t[2 * q + 3]) + 6 * t[2 * q + 2]);
+    }
+    uint32_t word = 0;
+    B2A_UNROLL
+    for (int q = 0; q < 4; ++q) if (dx0 + q < dW) word |= ((v[q] + 128) >> 8) << (8 * q);
+    return word;
+}
+B2A_HD bool pyr_down_is_interior4(int W, int H, int dW, int dx0, int dy)
+{
+    return dx0 + 3 < dW && 2 * dx0 - 2 >= 0 && 2 * (dx0 + 3) + 2 < W && 2 * dy - 2 >= 0 && 2 * dy + 2 < H;
 }
 
 // what detectMarkers derives from the image size and the two ArUco3 parameters before it looks at a pixel

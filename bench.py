@@ -412,13 +412,24 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------
 # CPU reference arm
 # ----------------------------------------------------------------------------------------------
+A3_RATIO = None          # --aruco3 RATIO: useAruco3Detection with minMarkerLengthRatioOriginalImg = RATIO (minSideLengthCanonicalImg 32)
+
+
+def a3_params():
+    return {} if A3_RATIO is None else {"useAruco3Detection": 1, "minMarkerLengthRatioOriginalImg": A3_RATIO}
+
+
 def _cpu_worker_init(use_cv2, dict_id):
     global _W
     _W = {}
     if use_cv2:
         import cv2
         cv2.setNumThreads(1)
-        _W["det"] = cv2.aruco.ArucoDetector(cv2.aruco.getPredefinedDictionary(dict_id), cv2.aruco.DetectorParameters())
+        prm = cv2.aruco.DetectorParameters()
+        if A3_RATIO is not None:                # --aruco3: both arms run OpenCV's ArUco3 mode with the same ratio
+            prm.useAruco3Detection = True
+            prm.minMarkerLengthRatioOriginalImg = A3_RATIO
+        _W["det"] = cv2.aruco.ArucoDetector(cv2.aruco.getPredefinedDictionary(dict_id), prm)
         h = np.float32(MARKER_LENGTH) / np.float32(2)
         _W["obj"] = np.array([[-h, h, 0], [h, h, 0], [h, -h, 0], [-h, -h, 0]], np.float32)
         _W["cv2"] = cv2
@@ -438,7 +449,7 @@ def _cpu_worker(frame):
             n += 1
         return n
     O = _W["O"]
-    c, ids, _ = O.detect(frame, _W["dic"])
+    c, ids, _ = O.detect(frame, _W["dic"], O.default_params(**a3_params()))
     O.estimate_pose_single_markers(c, MARKER_LENGTH, K_CAM, D_CAM)
     return len(ids)
 
@@ -506,6 +517,8 @@ def main():
     ap.add_argument("--ekf-landmarks", type=int, default=500)
     ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
     ap.add_argument("--inflight", type=int, default=8, help="C4: frames of a stream kept in flight (1 .. 8)")
+    ap.add_argument("--aruco3", type=float, default=None, metavar="RATIO",
+                    help="C1-C3: run the detector's ArUco3 mode (useAruco3Detection, minMarkerLengthRatioOriginalImg = RATIO) in both arms")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipelined", action="store_true", help="skip the two-handle / two-thread extra (use under ncu: the profiler serialises the two threads' launches)")
     args = ap.parse_args()
@@ -530,6 +543,10 @@ def main():
     W, H, B = cfg["W"], cfg["H"], args.batch
     global K_CAM
     K_CAM = camera_matrix(W, H)
+    global A3_RATIO
+    A3_RATIO = args.aruco3
+    if A3_RATIO is not None:
+        desc += ", ArUco3 mode (minMarkerLengthRatioOriginalImg %g)" % A3_RATIO
     config = {"workload": "%s: %s, batch %d per GPU, detect+pose" % (args.workload, desc, B), "batch_per_gpu": B,
               "l2": "L2 flushed (256 MiB write) between timed steps", "parallelism": "frame shards, %d GPU(s), no collective" % world}
 
@@ -580,7 +597,7 @@ def main():
 
     frames = synth.render_batch(args.workload, B, base_seed=1000 * rank)          # this rank's shard
     dic = D.getPredefinedDictionary(dict_id)
-    det = aruco.ArucoDetector(dic, max_shape=(H, W), max_batch=B, device=local_rank)
+    det = aruco.ArucoDetector(dic, aruco.DetectorParameters(**a3_params()), max_shape=(H, W), max_batch=B, device=local_rank)
     cam = aruco._camera(K_CAM, D_CAM, MARKER_LENGTH)
     d_frames = torch.from_numpy(frames).cuda()
     h_frames = torch.from_numpy(frames).pin_memory()
@@ -595,9 +612,13 @@ def main():
     r = det._collect(det.detect_raw(fr_dev, cam), True)
     bad = []
     for b in range(B):
-        oc, oi, orj = O.detect(frames[b], dic)
+        oc, oi, orj = O.detect(frames[b], dic, O.default_params(**a3_params()))
+        if A3_RATIO is None:
+            ok = np.array_equal(r.ids[b], oi) and np.array_equal(r.corners[b], oc) and np.array_equal(r.rejected[b], orj)
+        else:                                   # ArUco3 refines the corners (cornerSubPix up the pyramid): 0.05 px; poses from the device's corners
+            ok = np.array_equal(r.ids[b], oi) and np.array_equal(r.rejected[b], orj) and bool(len(oi) == 0 or np.abs(r.corners[b] - oc).max() < 0.05)
+            oc = r.corners[b] if ok else oc
         orv, otv = O.estimate_pose_single_markers(oc, MARKER_LENGTH, K_CAM, D_CAM)
-        ok = np.array_equal(r.ids[b], oi) and np.array_equal(r.corners[b], oc) and np.array_equal(r.rejected[b], orj)
         ok = ok and bool(len(oi) == 0 or (np.abs(r.tvecs[b] - otv).max() < 1e-4 and max(synth.rvec_distance(x, y) for x, y in zip(r.rvecs[b], orv)) < 1e-4))
         if not ok:
             bad.append(b)
@@ -737,7 +758,7 @@ def main():
     e2e_pipelined = None
     if rank == 0 and world == 1 and not args.no_pipelined:
         from concurrent.futures import ThreadPoolExecutor
-        det2 = aruco.ArucoDetector(dic, max_shape=(H, W), max_batch=B, device=local_rank)
+        det2 = aruco.ArucoDetector(dic, aruco.DetectorParameters(**a3_params()), max_shape=(H, W), max_batch=B, device=local_rank)
         dets = (det, det2)
         for dd in dets:
             dd.detect_raw(fr_host, cam)
@@ -759,6 +780,10 @@ def main():
         value = total_frames / (ms_dev * 1e-3)
         e2e = total_frames / (ms_e2e * 1e-3)
         P = W * H
+        e2e_bytes = B * P                                       # what crosses PCIe per step: the full-size frames
+        if A3_RATIO is not None:                                # ArUco3: the threshold kernel runs on the reduced segmentation image
+            fxfy = np.float32(32) / (np.float32(32) + np.float32(max(W, H)) * np.float32(A3_RATIO))
+            P = int(np.rint(fxfy * np.float32(W))) * int(np.rint(fxfy * np.float32(H)))
         nS = det.num_scales
         peak, which = measured_peak_gbs()
         thr_bytes = B * (1 + nS) * P                           # read P + write nS*P (the reference's byte masks) = 4P per frame
@@ -778,7 +803,7 @@ def main():
             "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 (detect) / f64 (pose)", "data": "synthetic", "config": config,
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * P, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                     "how": "b2a_detect_pose_submit / _wait on pinned host frames: one handle, one host thread, step k+1 submitted before step k "
                            "is waited for (its H2D copy overlaps step k's kernels); every step's H2D and D2H are inside the region and every "
                            "step's result is read on the host; CUDA events around the K steps; L2 flushed before the region (each step "

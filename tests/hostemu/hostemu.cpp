@@ -333,11 +333,29 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
 void emu_pyr_down(const uint8_t *src, int W, int H, uint8_t *dst)
 {
     const int dW = (W + 1) / 2, dH = (H + 1) / 2;
-    for (int y = 0; y < dH; ++y) for (int x = 0; x < dW; ++x) dst[(size_t)y * dW + x] = pyr_down_pixel(src, W, H, (size_t)W, x, y);
+    for (int y = 0; y < dH; ++y)
+        for (int x0 = 0; x0 < dW; x0 += 4) {                     // k_pyr_down: four pixels at a time away from the border
+            if (pyr_down_is_interior4(W, H, dW, x0, y)) {
+                // the word form needs word-aligned rows: the emulation takes it when the image width allows, as the kernel does for its pitched levels
+                const bool words = (W & 3) == 0 && (((size_t)src) & 3) == 0 && 2 * x0 - 4 >= 0 && 2 * x0 + 11 < W;
+                const uint32_t w = words ? pyr_down_interior4<true>(src, (size_t)W, x0, y) : pyr_down_interior4<false>(src, (size_t)W, x0, y);
+                for (int q = 0; q < 4; ++q) dst[(size_t)y * dW + x0 + q] = (uint8_t)(w >> (8 * q));
+            } else if (W >= 3 && H >= 3) {
+                const uint32_t w = pyr_down_border4(src, W, H, (size_t)W, dW, x0, y);
+                for (int q = 0; q < 4 && x0 + q < dW; ++q) dst[(size_t)y * dW + x0 + q] = (uint8_t)(w >> (8 * q));
+            } else for (int x = x0; x < x0 + 4 && x < dW; ++x) dst[(size_t)y * dW + x] = pyr_down_pixel(src, W, H, (size_t)W, x, y);
+        }
 }
 void emu_resize_linear(const uint8_t *src, int W, int H, uint8_t *dst, int dW, int dH)
 {
-    for (int y = 0; y < dH; ++y) for (int x = 0; x < dW; ++x) dst[(size_t)y * dW + x] = resize_pixel(src, W, H, (size_t)W, dW, dH, x, y);
+    const bool area = (W == 2 * dW && H == 2 * dH);
+    std::vector<int> tab((size_t)3 * (dW + dH));                // k_resize_tabs, then k_resize_linear
+    for (int i = 0; i < dW + dH; ++i) { if (i < dW) resize_tab(i, dW, W, tab[3 * i], tab[3 * i + 1], tab[3 * i + 2]); else resize_tab(i - dW, dH, H, tab[3 * i], tab[3 * i + 1], tab[3 * i + 2]); }
+    for (int y = 0; y < dH; ++y)
+        for (int x = 0; x < dW; ++x) {
+            const int *tx = &tab[3 * x], *ty = &tab[3 * (dW + y)];
+            dst[(size_t)y * dW + x] = area ? resize_pixel(src, W, H, (size_t)W, dW, dH, x, y) : resize_pixel_tab(src, W, H, (size_t)W, tx[0], tx[1], tx[2], ty[0], ty[1], ty[2]);
+        }
 }
 
 // the ArUco3 front half of a call as run_front / run_back arrange it: plan, pyramid, segmentation image, detection in it with the
