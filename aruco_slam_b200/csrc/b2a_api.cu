@@ -1534,8 +1534,8 @@ extern "C" int b2a_refine_detected_markers(b2a_detector *d, const b2a_frames *im
         if (und.empty()) return B2A_OK;
         double rvec[3], tvec[3], R[9];
         const Camera c = to_camera(cam);
-        const int rc = board_pose_planar(c, obj.data(), img.data(), (int)img.size() / 2, rvec, tvec);
-        if (rc == 2) return set_err(B2A_ERR_UNSUPPORTED, "board corners are not coplanar (camera form)");
+        const int rc = board_pose(c, obj.data(), img.data(), (int)img.size() / 2, rvec, tvec);
+        if (rc == 2) return set_err(B2A_ERR_INVALID, "board corners in general position need at least 6 matched points (cv2: DLT algorithm needs at least 6 points)");
         if (rc) return set_err(B2A_ERR_INVALID, "degenerate board pose");
         rodrigues_to_R(rvec, R);
         for (int j : und)

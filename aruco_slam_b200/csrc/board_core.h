@@ -2,7 +2,9 @@
 // markers should appear in the image.  Replaces the two _projectUndetectedMarkers of cv2 4.13's aruco_detector.cpp (part of the
 // cv::aruco surface of reference src/aruco_slam.cpp:313):
 //   no camera   findHomography(board xy -> detected corners, method 0) + perspectiveTransform
-//   camera      solvePnP(matched board corners, detected corners, ITERATIVE) + projectPoints, for boards whose corners are coplanar
+//   camera      solvePnP(matched board corners, detected corners, ITERATIVE) + projectPoints: start from the plane homography when
+//               the corners are (nearly) coplanar -- cv2's test, W[2] / W[1] < 1e-3 on the scatter's singular values -- else from
+//               the DLT over at least 6 points
 // A few dozen points per call: plain double-precision host code (the per-candidate bit extraction is the GPU part).
 // Both fits are least-squares problems; cv2 reaches their minima with its normalised DLT + LM and its LM on (rvec, tvec), this
 // file with the same DLT and Gauss-Newton, so the projections agree to ~1e-3 px.
@@ -102,8 +104,9 @@ inline void homography_apply(const double *H, double X, double Y, double &x, dou
     x = (H[0] * X + H[1] * Y + H[2]) / w; y = (H[3] * X + H[4] * Y + H[5]) / w;
 }
 
-// solvePnP(ITERATIVE) for coplanar object points obj (n x 3) seen at img (n x 2).  Returns 0 ok, 1 degenerate, 2 not coplanar
-inline int board_pose_planar(const Camera &cam, const double *obj, const double *img, int n, double *rvec, double *tvec)
+// solvePnP(ITERATIVE) for object points obj (n x 3) seen at img (n x 2).  Returns 0 ok, 1 degenerate, 2 points in general position
+// but fewer than 6 of them (cv2 throws: "DLT algorithm needs at least 6 points")
+inline int board_pose(const Camera &cam, const double *obj, const double *img, int n, double *rvec, double *tvec)
 {
     if (n < 4) return 1;
     double mean[3] = {0, 0, 0};
@@ -114,7 +117,33 @@ inline int board_pose_planar(const Camera &cam, const double *obj, const double 
     double V[9], w[3];
     sym_eig_jacobi(3, C, V, w);
     if (w[2] <= 0) return 1;
-    if (w[0] > 1e-9 * w[2]) return 2;
+    const bool planar = w[0] / w[1] < 1e-3;
+    if (!planar && n < 6) return 2;
+    double p[6];
+    if (!planar) {
+        // DLT: the 3 x 4 projection is the eigenvector of L^T L with the smallest eigenvalue (normalised image points), its left
+        // block becomes a rotation (SVD), the translation is scaled alike
+        double LtL[144] = {0};
+        for (int i = 0; i < n; ++i) {
+            double x, y;
+            undistort_point(cam, img[2 * i], img[2 * i + 1], x, y);
+            const double X = obj[3 * i], Y = obj[3 * i + 1], Z = obj[3 * i + 2];
+            const double Lx[12] = {X, Y, Z, 1, 0, 0, 0, 0, -x * X, -x * Y, -x * Z, -x}, Ly[12] = {0, 0, 0, 0, X, Y, Z, 1, -y * X, -y * Y, -y * Z, -y};
+            for (int a = 0; a < 12; ++a) for (int b = 0; b < 12; ++b) LtL[a * 12 + b] += Lx[a] * Lx[b] + Ly[a] * Ly[b];
+        }
+        double V12[144], w12[12], RR[12];
+        sym_eig_jacobi(12, LtL, V12, w12);
+        for (int k = 0; k < 12; ++k) RR[k] = V12[k * 12 + 0];
+        const double dRR = RR[0] * (RR[5] * RR[10] - RR[6] * RR[9]) - RR[1] * (RR[4] * RR[10] - RR[6] * RR[8]) + RR[2] * (RR[4] * RR[9] - RR[5] * RR[8]);
+        if (dRR < 0) for (int k = 0; k < 12; ++k) RR[k] = -RR[k];
+        double R[9], nrm = 0;
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { R[r * 3 + c] = RR[r * 4 + c]; nrm += RR[r * 4 + c] * RR[r * 4 + c]; }
+        if (nrm <= 0) return 1;
+        nearest_rotation(R);
+        R_to_rodrigues(R, p);
+        const double sc = std::sqrt(3.0) / std::sqrt(nrm);                    // |R|_F / |RR[:, :3]|_F
+        for (int k = 0; k < 3; ++k) p[3 + k] = RR[k * 4 + 3] * sc;
+    } else {
     // plane frame: e1, e2 = the two in-plane axes (largest eigenvalues), e3 = normal, right-handed
     double E[9];
     for (int k = 0; k < 3; ++k) { E[k * 3 + 0] = V[k * 3 + 2]; E[k * 3 + 1] = V[k * 3 + 1]; E[k * 3 + 2] = V[k * 3 + 0]; }
@@ -135,10 +164,11 @@ inline int board_pose_planar(const Camera &cam, const double *obj, const double 
     const double r3[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
     for (int k = 0; k < 3; ++k) { Rh[k * 3 + 0] = r1[k]; Rh[k * 3 + 1] = r2[k]; Rh[k * 3 + 2] = r3[k]; }
     nearest_rotation(Rh);
-    double R[9], p[6];
+    double R[9];
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { R[r * 3 + c] = 0; for (int k = 0; k < 3; ++k) R[r * 3 + c] += Rh[r * 3 + k] * E[c * 3 + k]; }   // Rh * E^T
     R_to_rodrigues(R, p);
     for (int k = 0; k < 3; ++k) p[3 + k] = H[2 + 3 * k] * lam - (R[k * 3] * mean[0] + R[k * 3 + 1] * mean[1] + R[k * 3 + 2] * mean[2]);
+    }
     // Gauss-Newton on the reprojection error, numeric Jacobian
     auto residuals = [&](const double *q, double *r) {
         double Rq[9];

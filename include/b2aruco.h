@@ -188,8 +188,9 @@ int  b2a_multi_detect_pose(b2a_multi *m, const b2a_frames *frames, const b2a_cam
 /* ---- cv::aruco::ArucoDetector::refineDetectedMarkers (cv2 4.13; part of the cv::aruco surface of aruco_slam.cpp:313, the reference
  * itself does not call it).  Rejected candidates that lie where the board says an undetected marker must be are moved to the
  * detected list.  board: cv::aruco::Board (ids + object points of every marker's four corners); cam null = the global-homography
- * form (all board points must share one z), else the board pose is fitted through the camera (coplanar boards; a board in
- * general position -> B2A_ERR_UNSUPPORTED).  corners / ids / rejected are host arrays, edited in place like cv2's
+ * form (all board points must share one z), else the board pose is fitted through the camera as cv::solvePnP(ITERATIVE) fits it
+ * (start from the plane homography for coplanar boards, from the DLT for boards in general position, which need >= 6 matched
+ * corners; then least squares on the reprojection error).  corners / ids / rejected are host arrays, edited in place like cv2's
  * InputOutputArrays: recovered markers are appended in board order with the candidate's corners rotated to the matching order
  * (and refined when the detector was created with CORNER_REFINE_SUBPIX), the recovered candidates leave `rejected`;
  * recovered_idx (optional, room for *n_rejected entries) gets their indices in the incoming rejected list.

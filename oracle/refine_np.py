@@ -111,14 +111,65 @@ def undistort_points(img, K, D, iters=20):
     return np.c_[x, y]
 
 
+def _least_squares_pose(p, obj, img, K, D, iters=30):
+    """Gauss-Newton on the reprojection error over (rvec, tvec), numeric Jacobian (cv2 runs its LM to the same minimum)"""
+    f = lambda q: (project_points(obj, q[:3], q[3:], K, D) - img).ravel()
+    for _ in range(iters):
+        r = f(p)
+        J = np.empty((len(r), 6))
+        for k in range(6):
+            d = np.zeros(6)
+            d[k] = 1e-7
+            J[:, k] = (f(p + d) - f(p - d)) / 2e-7
+        step = np.linalg.solve(J.T @ J, J.T @ r)
+        p = p - step
+        if np.linalg.norm(step) < 1e-12:
+            break
+    return p[:3], p[3:]
+
+
+def is_planar(obj):
+    """the test of cv::solvePnP(ITERATIVE)'s start: singular values W of the scatter of the object points, W[2] / W[1] < 1e-3"""
+    obj = np.asarray(obj, np.float64)
+    w = np.linalg.eigvalsh((obj - obj.mean(0)).T @ (obj - obj.mean(0)))
+    return w[0] / w[1] < 1e-3
+
+
+def solve_pnp_dlt(obj, img, K, D, iters=30):
+    """cv::solvePnP(ITERATIVE) for object points in general position (>= 6): the DLT start -- the 3 x 4 projection from the smallest
+    eigenvector of L^T L over normalised image points, its left block made a rotation by SVD, the translation scaled alike --
+    then least squares on the reprojection error"""
+    obj = np.asarray(obj, np.float64)
+    img = np.asarray(img, np.float64)
+    if len(obj) < 6:
+        raise ValueError("DLT algorithm needs at least 6 points")
+    mn = undistort_points(img, K, D)
+    L = np.zeros((2 * len(obj), 12))
+    for i, (M, m) in enumerate(zip(obj, mn)):
+        L[2 * i, 0:3] = M; L[2 * i, 3] = 1; L[2 * i, 8:11] = -m[0] * M; L[2 * i, 11] = -m[0]
+        L[2 * i + 1, 4:7] = M; L[2 * i + 1, 7] = 1; L[2 * i + 1, 8:11] = -m[1] * M; L[2 * i + 1, 11] = -m[1]
+    w, V = np.linalg.eigh(L.T @ L)
+    RR = V[:, 0].reshape(3, 4)
+    if np.linalg.det(RR[:, :3]) < 0:
+        RR = -RR
+    u, _, vt = np.linalg.svd(RR[:, :3])
+    R = u @ vt
+    t = RR[:, 3] * (np.linalg.norm(R) / np.linalg.norm(RR[:, :3]))
+    return _least_squares_pose(np.r_[rvec_of(R), t], obj, img, K, D, iters)
+
+
+def solve_pnp(obj, img, K, D):
+    return solve_pnp_planar(obj, img, K, D) if is_planar(obj) else solve_pnp_dlt(obj, img, K, D)
+
+
 def solve_pnp_planar(obj, img, K, D, iters=30):
-    """cv::solvePnP(ITERATIVE) for coplanar object points: pose from the plane homography, then least squares on the
+    """cv::solvePnP(ITERATIVE) for (nearly) coplanar object points: pose from the plane homography, then least squares on the
     reprojection error (Gauss-Newton with a numeric Jacobian; cv2 runs its LM to the same minimum)"""
     obj = np.asarray(obj, np.float64)
     img = np.asarray(img, np.float64)
     mean = obj.mean(0)
     w, E = np.linalg.eigh(np.cov((obj - mean).T))
-    if w[0] > 1e-9 * max(w[2], 1e-30):
+    if not is_planar(obj):
         raise ValueError("board is not planar")
     E = E[:, ::-1]                                        # columns: two in-plane axes, then the normal
     if np.linalg.det(E) < 0:
@@ -135,20 +186,7 @@ def solve_pnp_planar(obj, img, K, D, iters=30):
     Rh = u @ vt
     R = Rh @ E.T
     t = h3 * lam - R @ mean
-    p = np.r_[rvec_of(R), t]
-    f = lambda q: (project_points(obj, q[:3], q[3:], K, D) - img).ravel()
-    for _ in range(iters):
-        r = f(p)
-        J = np.empty((len(r), 6))
-        for k in range(6):
-            d = np.zeros(6)
-            d[k] = 1e-7
-            J[:, k] = (f(p + d) - f(p - d)) / 2e-7
-        step = np.linalg.solve(J.T @ J, J.T @ r)
-        p = p - step
-        if np.linalg.norm(step) < 1e-12:
-            break
-    return p[:3], p[3:]
+    return _least_squares_pose(np.r_[rvec_of(R), t], obj, img, K, D, iters)
 
 
 def project_undetected(board_ids, board_obj, corners, ids, K=None, D=None):
@@ -173,7 +211,7 @@ def project_undetected(board_ids, board_obj, corners, ids, K=None, D=None):
             obj_pts += list(board_obj[board_ids.index(did)]); img_pts += list(corners[i])
     if len(obj_pts) < 4:
         return [], np.zeros((0, 4, 2))
-    rvec, tvec = solve_pnp_planar(np.array(obj_pts), np.array(img_pts), K, D)
+    rvec, tvec = solve_pnp(np.array(obj_pts), np.array(img_pts), K, D)
     und = [j for j, bid in enumerate(board_ids) if bid not in ids]
     return [board_ids[j] for j in und], np.array([project_points(board_obj[j], rvec, tvec, K, D) for j in und]).reshape(-1, 4, 2)
 

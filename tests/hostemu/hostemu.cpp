@@ -455,7 +455,7 @@ int emu_homography(const double *src, const double *dst, int n, double *H, int r
 int emu_board_pose(const double *K9, const double *D5, const double *obj, const double *img, int n, double *rvec, double *tvec)
 {
     Camera cam{K9[0], K9[4], K9[2], K9[5], D5[0], D5[1], D5[2], D5[3], D5[4]};
-    return board_pose_planar(cam, obj, img, n, rvec, tvec);
+    return board_pose(cam, obj, img, n, rvec, tvec);
 }
 
 }  // extern "C"

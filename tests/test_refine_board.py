@@ -96,8 +96,45 @@ def test_product_board_geometry_vs_restatement():
     rv, tv = np.array([-0.25, 0.5, 0.15]), np.array([-0.2, 0.1, 1.1])
     rc, r, t = emu.board_pose(G["K"], G["D"], pl, refine_np.project_points(pl, rv, tv, G["K"], G["D"]))
     assert rc == 0 and np.allclose(r, rv, atol=1e-7) and np.allclose(t, tv, atol=1e-7)
+    # in general position: the DLT start, exact recovery as well; fewer than 6 such points are refused (cv2 throws)
     pl[::3, 2] += 0.05
-    assert emu.board_pose(G["K"], G["D"], pl, refine_np.project_points(pl, rv, tv, G["K"], G["D"]))[0] == 2     # not coplanar
+    rc, r, t = emu.board_pose(G["K"], G["D"], pl, refine_np.project_points(pl, rv, tv, G["K"], G["D"]))
+    assert rc == 0 and np.allclose(r, rv, atol=1e-7) and np.allclose(t, tv, atol=1e-7)
+    assert emu.board_pose(G["K"], G["D"], pl[:5], refine_np.project_points(pl[:5], rv, tv, G["K"], G["D"]))[0] == 2
+
+
+NP = np.load(os.path.join(os.path.dirname(__file__), "golden", "refine_nonplanar.npz"))
+NP_CASES = [(str(n), tuple(p)) for n, p in zip(NP["cases"], NP["case_params"])]
+
+
+def test_pose_start_planar_or_dlt_vs_cv2_solvepnp():
+    """cv2.solvePnP(ITERATIVE) on points in general position and on nearly planar ones (tests/golden/refine_nonplanar.npz): the numpy
+    restatement and the product's board_core.h reach the same reprojection as cv2"""
+    from hostemu import emu
+    kinds = set()
+    for i in range(int(NP["n_pnp"])):
+        obj, img = NP["pnp/%d/obj" % i], NP["pnp/%d/img" % i]
+        want = refine_np.project_points(obj, NP["pnp/%d/rvec" % i], NP["pnp/%d/tvec" % i], G["K"], G["D"])
+        kinds.add(bool(refine_np.is_planar(obj)))
+        r, t = refine_np.solve_pnp(obj, img, G["K"], G["D"])
+        assert np.abs(refine_np.project_points(obj, r, t, G["K"], G["D"]) - want).max() < 1e-4, i
+        rc, r, t = emu.board_pose(G["K"], G["D"], obj, img)
+        assert rc == 0 and np.abs(refine_np.project_points(obj, r, t, G["K"], G["D"]) - want).max() < 1e-4, i
+    assert kinds == {True, False}
+
+
+def same_as_cv2_nonplanar(name, c, i, r, rec):
+    assert np.array_equal(i, NP[name + "/ids"]) and np.array_equal(c, NP[name + "/corners"])
+    assert np.array_equal(r, NP[name + "/rejected"]) and np.array_equal(rec, NP[name + "/recovered"])
+
+
+@pytest.mark.parametrize("name,prm", NP_CASES)
+def test_numpy_restatement_nonplanar_board_vs_cv2(name, prm):
+    rep, ecr, orders = prm
+    assert not refine_np.is_planar(NP["board_obj"].reshape(-1, 3))
+    out = refine_np.refine_detected_markers(G["frame"], DIC, G["board_ids"], NP["board_obj"], G["corners"], G["ids"], G["rejected"], K=G["K"], D=G["D"],
+                                            min_rep_distance=rep, error_correction_rate=ecr, check_all_orders=bool(orders))
+    same_as_cv2_nonplanar(name, *out)
 
 
 # ---- the product through the C ABI ----
@@ -151,9 +188,18 @@ def test_gpu_refine_detected_markers_edges(aruco):
     assert rec is None and np.array_equal(np.asarray(oi).ravel(), G["ids"])
     oc, oi, orj, rec = det.refineDetectedMarkers(G["frame"], board, (), None, rej)
     assert rec is None and len(orj) == len(rej)
-    # a board in general position is not supported with a camera (cv2 would take its DLT branch)
-    obj = G["board_obj"].copy()
-    obj[::2, :, 2] += 0.05
-    with pytest.raises(Exception):
-        det.refineDetectedMarkers(G["frame"], aruco.Board(obj, G["board_ids"]), c, ids, rej, cameraMatrix=G["K"], distCoeffs=G["D"])
+    det.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,prm", NP_CASES)
+def test_gpu_refine_detected_markers_nonplanar_board_vs_cv2(aruco, name, prm):
+    """a board in general position seen through a camera: the pose starts from the DLT, as cv2's does"""
+    rep, ecr, orders = prm
+    det = aruco.ArucoDetector(DIC, aruco.DetectorParameters(), max_shape=G["frame"].shape, max_batch=1)
+    c, ids, rej = det.detectMarkers(G["frame"])
+    oc, oi, orj, rec = det.refineDetectedMarkers(G["frame"], aruco.Board(NP["board_obj"], G["board_ids"]), c, ids, rej, cameraMatrix=G["K"], distCoeffs=G["D"],
+                                                 refineParams=aruco.RefineParameters(rep, ecr, bool(orders)))
+    same_as_cv2_nonplanar(name, np.array(oc, np.float32).reshape(-1, 4, 2), np.asarray(oi, np.int32).ravel(), np.array(orj, np.float32).reshape(-1, 4, 2),
+                          np.zeros(0, np.int32) if rec is None else np.asarray(rec, np.int32).ravel())
     det.close()

@@ -112,8 +112,53 @@ def board_fixture():
     print("refine_board.npz %.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def nonplanar_fixture():
+    """tests/golden/refine_nonplanar.npz: cv2.solvePnP (ITERATIVE) on object points in general position (its DLT start) and on nearly
+    planar ones (its homography start), and refineDetectedMarkers with a camera on a board whose markers sit 2.5 mm above / below
+    the sheet in turn (general position by cv2's test, W[2] / W[1] >= 1e-3), on the frame and detections of refine_board.npz"""
+    G = np.load(os.path.join(OUT, "refine_board.npz"))
+    K, D = G["K"], G["D"]
+    rng = np.random.default_rng(11)
+    kw = {}
+    n_pnp = 0
+    for n, zscale in ((6, 1.0), (7, 0.3), (12, 1.0), (20, 0.1), (24, 0.04), (24, 0.02), (40, 0.5), (16, 0.0), (9, 0.005)):
+        obj = rng.uniform(-0.2, 0.2, (n, 3))
+        obj[:, 2] *= zscale
+        obj = obj.astype(np.float32).astype(np.float64)
+        rv = rng.uniform(-0.6, 0.6, 3)
+        tv = np.array([rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2), rng.uniform(0.6, 1.5)])
+        img = (cv2.projectPoints(obj, rv, tv, K, D)[0].reshape(-1, 2) + rng.normal(0, 0.3, (n, 2))).astype(np.float32).astype(np.float64)
+        ok, r, t = cv2.solvePnP(obj, img, K, D)
+        assert ok
+        kw.update({"pnp/%d/obj" % n_pnp: obj, "pnp/%d/img" % n_pnp: img, "pnp/%d/rvec" % n_pnp: r.ravel(), "pnp/%d/tvec" % n_pnp: t.ravel()})
+        n_pnp += 1
+    dic = A.getPredefinedDictionary(int(G["dict_id"]))
+    obj = G["board_obj"].copy()
+    obj[::2, :, 2] += 0.0025
+    obj[1::2, :, 2] -= 0.0025
+    board = A.Board(obj, dic, G["board_ids"].reshape(-1, 1))
+    c = [q.reshape(1, 4, 2) for q in G["corners"]]
+    rej = [q.reshape(1, 4, 2) for q in G["rejected"]]
+    cases = [("cam_default", 10.0, 3.0, True), ("cam_near", 3.0, 3.0, True), ("cam_nocode", 10.0, -1.0, False)]
+    for name, rep, ecr, orders in cases:
+        d2 = A.ArucoDetector(dic, A.DetectorParameters(), A.RefineParameters(rep, ecr, orders))
+        out = d2.refineDetectedMarkers(G["frame"], board, list(c), G["ids"].reshape(-1, 1).copy(), list(rej), cameraMatrix=K, distCoeffs=D)
+        rec = np.zeros(0, np.int32) if out[3] is None else np.asarray(out[3]).ravel().astype(np.int32)
+        kw.update({name + "/corners": np.array(out[0], np.float32).reshape(-1, 4, 2), name + "/ids": np.asarray(out[1]).ravel().astype(np.int32),
+                   name + "/rejected": np.array(out[2], np.float32).reshape(-1, 4, 2), name + "/recovered": rec})
+        print("  nonplanar %-12s -> detected %d, recovered %s" % (name, len(kw[name + "/ids"]), rec.tolist()))
+    path = os.path.join(OUT, "refine_nonplanar.npz")
+    np.savez_compressed(path, provenance=np.array(PROV), board_obj=obj.astype(np.float32), n_pnp=np.int32(n_pnp), cases=np.array([c_[0] for c_ in cases]),
+                        case_params=np.array([[c_[1], c_[2], float(c_[3])] for c_ in cases]), **kw)
+    print("refine_nonplanar.npz %.1f KB" % (os.path.getsize(path) / 1024))
+
+
 def main():
+    if "--nonplanar-only" in sys.argv:
+        nonplanar_fixture()
+        return
     board_fixture()
+    nonplanar_fixture()
     kw = {}
     names = []
     for path in sorted(glob.glob(os.path.join(OUT, "detect_*.npz"))):
