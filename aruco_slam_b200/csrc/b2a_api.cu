@@ -1652,6 +1652,7 @@ extern "C" int b2a_estimate_pose_single_markers(b2a_detector *d, const float *co
 // ------------------------------------------------------------------------------------------------
 extern "C" int b2a_debug_threshold(b2a_detector *d, const b2a_frames *f, uint8_t *gray, uint8_t *masks)
 {
+    if (d && d->prm.useAruco3Detection) return set_err(B2A_ERR_UNSUPPORTED, "stage taps of an ArUco3 detector (its front end runs on the reduced image)");
     std::vector<Sub> subs;
     TRY(run_pipeline(d, f, nullptr, 1, 0, &subs));
     const DetGeom g = make_geom(d, f->width, f->height, f->batch);
@@ -1677,6 +1678,7 @@ extern "C" int b2a_debug_threshold(b2a_detector *d, const b2a_frames *f, uint8_t
 extern "C" int b2a_debug_contours(b2a_detector *d, const b2a_frames *f, int32_t *counts, int32_t *n_kept, int32_t *kept_len, int cap, int16_t *pts, int pts_cap)
 {
     if (!f) return set_err(B2A_ERR_INVALID, "null argument");
+    if (d && d->prm.useAruco3Detection) return set_err(B2A_ERR_UNSUPPORTED, "stage taps of an ArUco3 detector (its front end runs on the reduced image)");
     TRY(run_pipeline(d, f, nullptr, 1, 2 * f->width * f->height + 16, nullptr));     // exact total count: never give up on long borders
     const DetGeom g = make_geom(d, f->width, f->height, f->batch);
     const size_t FS = (size_t)g.B * g.nScales;
@@ -1709,6 +1711,7 @@ extern "C" int b2a_debug_contours(b2a_detector *d, const b2a_frames *f, int32_t 
 
 extern "C" int b2a_debug_candidates(b2a_detector *d, const b2a_frames *f, int32_t *n_cand, float *quads, int cap)
 {
+    if (d && d->prm.useAruco3Detection) return set_err(B2A_ERR_UNSUPPORTED, "stage taps of an ArUco3 detector (its front end runs on the reduced image)");
     TRY(run_pipeline(d, f, nullptr, 2, 0, nullptr));
     const int B = f->batch;
     std::vector<int> cnt((size_t)B * 8);

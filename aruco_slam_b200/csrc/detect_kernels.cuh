@@ -1860,19 +1860,43 @@ __device__ __forceinline__ void pyr_down_group(const uint8_t *sb, int W, int H, 
     else for (int q = 0; x0 + q < dW; ++q) drow[x0 + q] = (uint8_t)(word >> (8 * q));
 }
 
-// one level of every frame: block = 64 groups x 4 rows, blockIdx.x walks the rows of all frames (row index = frame * dH + y)
+// one level of every frame: block = 64 groups x 4 rows, blockIdx.x walks the rows of all frames (row index = frame * dH + y).
+// Rows whose 5 source rows lie inside the image: the interior groups by all threads (no divergence: every lane takes the same
+// path), then the few border groups of the block's four rows together on the lanes of one warp -- with the border groups inside
+// the row loop a quarter of all warps ran both paths (profiles/r2_aruco3_ncu.md).  Top and bottom rows: the general path.
 __global__ void __launch_bounds__(256)
 k_pyr_down(const uint8_t *__restrict__ src, int W, int H, size_t spitch, size_t sframe, uint8_t *__restrict__ dst, size_t dpitch, size_t dframe, int nb)
 {
     const int dW = (W + 1) / 2, dH = (H + 1) / 2, gW = (dW + 3) / 4;
     const bool aligned = ((spitch | sframe | (size_t)src) & 3) == 0;
+    const int gR = pyr_interior_gx_end(W, dW), yB = pyr_interior_y_end(H), nbm = 1 + (gW - gR);
     const unsigned rows = (unsigned)nb * (unsigned)dH;
-    for (unsigned R = blockIdx.x * 4u + threadIdx.y; R < rows; R += gridDim.x * 4u) {
-        const unsigned b = R / (unsigned)dH;
-        const int y = (int)(R - b * (unsigned)dH);
-        const uint8_t *sb = src + (size_t)b * sframe;
-        uint8_t *drow = dst + (size_t)b * dframe + (size_t)y * dpitch;
-        for (int gx = threadIdx.x; gx < gW; gx += 64) pyr_down_group(sb, W, H, spitch, aligned, drow, dW, 4 * gx, y);
+    for (unsigned R0 = blockIdx.x * 4u; R0 < rows; R0 += gridDim.x * 4u) {
+        const unsigned R = R0 + threadIdx.y;
+        if (R < rows) {
+            const unsigned b = R / (unsigned)dH;
+            const int y = (int)(R - b * (unsigned)dH);
+            const uint8_t *sb = src + (size_t)b * sframe;
+            uint8_t *drow = dst + (size_t)b * dframe + (size_t)y * dpitch;
+            if (y >= 1 && y < yB) {
+                for (int gx = 1 + threadIdx.x; gx < gR; gx += 64) {
+                    const int x0 = 4 * gx;
+                    const bool words = aligned && 2 * x0 + 11 < W;
+                    *reinterpret_cast<uint32_t *>(drow + x0) = words ? pyr_down_interior4<true>(sb, spitch, x0, y) : pyr_down_interior4<false>(sb, spitch, x0, y);
+                }
+            } else for (int gx = threadIdx.x; gx < gW; gx += 64) pyr_down_group(sb, W, H, spitch, aligned, drow, dW, 4 * gx, y);
+        }
+        if (threadIdx.y == 0 && threadIdx.x < 32)
+            for (int i = threadIdx.x; i < 4 * nbm; i += 32) {
+                const int q = i / nbm, j = i - q * nbm;
+                const unsigned Rq = R0 + (unsigned)q;
+                if (Rq >= rows) continue;
+                const unsigned b = Rq / (unsigned)dH;
+                const int y = (int)(Rq - b * (unsigned)dH);
+                if (!(y >= 1 && y < yB)) continue;                       // that row went through the general path above
+                const int gx = j == 0 ? 0 : gR + j - 1;
+                pyr_down_group(src + (size_t)b * sframe, W, H, spitch, aligned, dst + (size_t)b * dframe + (size_t)y * dpitch, dW, 4 * gx, y);
+            }
     }
 }
 
@@ -1907,7 +1931,7 @@ __global__ void k_resize_tabs(int W, int H, int dW, int dH, int2 *__restrict__ t
 }
 
 // a thread makes four neighbouring destination pixels of a row (one word store; dpitch is a multiple of 4); block = 64 groups x 4
-// rows, blockIdx.x walks the rows of all frames
+// rows, blockIdx.x walks the rows of all frames; the row's two source rows and weights are set up once per thread and row
 __global__ void __launch_bounds__(256)
 k_resize_linear(const uint8_t *__restrict__ src, int W, int H, size_t spitch, size_t sframe, uint8_t *__restrict__ dst, int dW, int dH, size_t dpitch, size_t dframe, int nb,
                 const int2 *__restrict__ tab)
@@ -1921,13 +1945,15 @@ k_resize_linear(const uint8_t *__restrict__ src, int W, int H, size_t spitch, si
         const uint8_t *sb = src + (size_t)b * sframe;
         uint8_t *drow = dst + (size_t)b * dframe + (size_t)y * dpitch;
         const int2 ty = area ? make_int2(0, 0) : __ldg(tab + dW + y);
+        const int sy1 = ty.x + 1 < H ? ty.x + 1 : H - 1, b0 = ty.y & 0xFFFF, b1 = ty.y >> 16;
+        const uint8_t *s0 = sb + (size_t)ty.x * spitch, *s1 = sb + (size_t)sy1 * spitch;
         for (int gx = threadIdx.x; gx < gW; gx += 64) {
             const int x0 = 4 * gx;
             uint32_t word = 0;
             for (int q = 0; q < 4 && x0 + q < dW; ++q) {
                 uint32_t v;
                 if (area) v = resize_pixel(sb, W, H, spitch, dW, dH, x0 + q, y);
-                else { const int2 tx = __ldg(tab + x0 + q); v = resize_pixel_tab(sb, W, H, spitch, tx.x, tx.y & 0xFFFF, tx.y >> 16, ty.x, ty.y & 0xFFFF, ty.y >> 16); }
+                else { const int2 tx = __ldg(tab + x0 + q); v = resize_pixel_rows(s0, s1, W, tx.x, tx.y & 0xFFFF, tx.y >> 16, b0, b1); }
                 word |= v << (8 * q);
             }
             if (x0 + 3 < dW) *reinterpret_cast<uint32_t *>(drow + x0) = word;

@@ -66,14 +66,19 @@ B2A_HD void resize_tab(int d, int dlen, int slen, int &s, int &c0, int &c1)
     c1 = pyr_round_half_even(f_mul(f, 2048.f));
 }
 
-// one destination pixel from its two table entries (source column sx with weights a0, a1; source row sy with b0, b1)
-B2A_HD uint8_t resize_pixel_tab(const uint8_t *src, int W, int H, size_t pitch, int sx, int a0, int a1, int sy, int b0, int b1)
+// one destination pixel from its two source rows s0, s1 (weights b0, b1) and its source column sx (weights a0, a1)
+B2A_HD uint8_t resize_pixel_rows(const uint8_t *s0, const uint8_t *s1, int W, int sx, int a0, int a1, int b0, int b1)
 {
-    const int sx1 = sx + 1 < W ? sx + 1 : W - 1, sy1 = sy + 1 < H ? sy + 1 : H - 1;
-    const uint8_t *s0 = src + (size_t)sy * pitch, *s1 = src + (size_t)sy1 * pitch;
+    const int sx1 = sx + 1 < W ? sx + 1 : W - 1;
     const int r0 = (int)s0[sx] * a0 + (int)s0[sx1] * a1, r1 = (int)s1[sx] * a0 + (int)s1[sx1] * a1;
     const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
     return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+}
+// the same from the two table entries (source column sx with weights a0, a1; source row sy with b0, b1)
+B2A_HD uint8_t resize_pixel_tab(const uint8_t *src, int W, int H, size_t pitch, int sx, int a0, int a1, int sy, int b0, int b1)
+{
+    const int sy1 = sy + 1 < H ? sy + 1 : H - 1;
+    return resize_pixel_rows(src + (size_t)sy * pitch, src + (size_t)sy1 * pitch, W, sx, a0, a1, b0, b1);
 }
 
 // destination pixel (dx, dy) of cv::resize(src W x H -> dW x dH, INTER_LINEAR)
@@ -158,6 +163,18 @@ B2A_HD uint32_t pyr_down_border4(const uint8_t *src, int W, int H, size_t pitch,
 B2A_HD bool pyr_down_is_interior4(int W, int H, int dW, int dx0, int dy)
 {
     return dx0 + 3 < dW && 2 * dx0 - 2 >= 0 && 2 * (dx0 + 3) + 2 < W && 2 * dy - 2 >= 0 && 2 * dy + 2 < H;
+}
+// the same test as ranges: groups gx (dx0 = 4 gx) with 1 <= gx < pyr_interior_gx_end and rows 1 <= dy < pyr_interior_y_end are interior
+B2A_HD int pyr_interior_gx_end(int W, int dW)
+{
+    const int a = dW >= 4 ? (dW - 4) / 4 : -1, b = W >= 9 ? (W - 9) / 8 : -1;
+    const int m = a < b ? a : b;
+    return m + 1 > 1 ? m + 1 : 1;
+}
+B2A_HD int pyr_interior_y_end(int H)
+{
+    const int m = H >= 3 ? (H - 3) / 2 : -1;
+    return m + 1 > 1 ? m + 1 : 1;
 }
 
 // what detectMarkers derives from the image size and the two ArUco3 parameters before it looks at a pixel

@@ -329,6 +329,20 @@ int emu_detect(const uint8_t *gray, int W, int H, const uint8_t *masks_in, const
                            dbg_pts, dbg_pts_cap, anchor_R, nullptr);
 }
 
+// the interior ranges k_pyr_down iterates over against the per-group test
+int emu_pyr_ranges_ok(int W, int H)
+{
+    const int dW = (W + 1) / 2, dH = (H + 1) / 2, gW = (dW + 3) / 4, gR = pyr_interior_gx_end(W, dW), yB = pyr_interior_y_end(H);
+    if (gR < 1 || gR > gW || yB < 1) return 0;
+    for (int y = 0; y < dH; ++y)
+        for (int gx = 0; gx < gW; ++gx) {
+            const bool by_range = gx >= 1 && gx < gR && y >= 1 && y < yB;
+            if (by_range != pyr_down_is_interior4(W, H, dW, 4 * gx, y)) return 0;
+            if (by_range && !(2 * (4 * gx) - 4 >= 0)) return 0;          // the word path's left bound holds for every interior group
+        }
+    return 1;
+}
+
 // ArUco3 (pyr_core.h): one pyrDown / one resize, a pixel at a time as the kernels compute them
 void emu_pyr_down(const uint8_t *src, int W, int H, uint8_t *dst)
 {

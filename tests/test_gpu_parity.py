@@ -622,3 +622,24 @@ def test_aruco3_parameter_checks(aruco):
     r = det.detect_batch(g["frame"])
     assert np.array_equal(r.ids[0], g["ids"]) and np.array_equal(r.corners[0], g["corners"]) and np.array_equal(r.rejected[0], g["rejected"])
     det.close()
+
+
+def test_aruco3_odd_sizes_and_two_level_chain(aruco, oracle):
+    """frame sizes that are not multiples of 4 (byte path of the pyramid's first level, ragged last groups of every level), tiny frames
+    (a pyramid of one image) and parameters whose refinement climbs two levels: equal to the oracle's ArUco3 path"""
+    fr = synth.render_config("C1", 5).image
+    dic = D.getPredefinedDictionary(0)
+    found = 0
+    for W, H in ((639, 479), (637, 475), (333, 250), (64, 48)):
+        crop = np.ascontiguousarray(fr[:H, :W])
+        for ratio, side in ((0.0, 32), (0.05, 16), (0.01, 8)):
+            prm = dict(useAruco3Detection=1, minSideLengthCanonicalImg=side, minMarkerLengthRatioOriginalImg=ratio)
+            det = _detector(aruco, dic, crop.shape, **prm)
+            r = det.detect_batch(crop)
+            oc, oi, orj = oracle.detect(crop, dic, oracle.default_params(**prm))
+            assert np.array_equal(r.ids[0], oi) and np.array_equal(r.rejected[0], orj), (W, H, ratio, side)
+            if len(oi):
+                assert np.abs(r.corners[0] - oc).max() < 0.05, (W, H, ratio, side)
+            found += len(oi)
+            det.close()
+    assert found >= 10

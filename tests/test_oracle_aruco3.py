@@ -94,3 +94,27 @@ def test_product_logic_aruco3_vs_cv2(emu, fixture):
         if len(out["ids"]):
             up = out["corners"] * (W / out["plan"][0])
             assert np.abs(up - A3[key + "/corners"]).max() <= 2.0 * (W / out["plan"][0]) + 3.0, key
+
+
+def test_product_logic_aruco3_odd_sizes_vs_oracle(emu, oracle):
+    from aruco_slam_b200 import synth
+    fr = synth.render_config("C1", 5).image
+    dic = D.getPredefinedDictionary(0)
+    plans = set()
+    for W, H in ((639, 479), (637, 475), (333, 250), (201, 199), (64, 48), (40, 30)):
+        crop = np.ascontiguousarray(fr[:H, :W])
+        for ratio, side in ((0.0, 32), (0.02, 32), (0.05, 16), (0.01, 8)):
+            oc, oi, orj = oracle.detect(crop, dic, oracle.default_params(useAruco3Detection=1, minSideLengthCanonicalImg=side, minMarkerLengthRatioOriginalImg=ratio))
+            out = emu.detect_aruco3(crop, dic, side, ratio)
+            assert out is not None and np.array_equal(out["ids"], oi) and np.array_equal(out["rejected"], orj), (W, H, ratio, side)
+            plans.add(out["plan"][2:])
+    assert (5, 2) in plans and (0, 0) in plans          # a refinement chain over two levels, and a pyramid of one image
+
+
+def test_interior_ranges_equal_the_per_group_test(emu):
+    """k_pyr_down walks the interior groups by ranges (pyr_interior_gx_end / pyr_interior_y_end): the same set as pyr_down_is_interior4"""
+    import ctypes as C
+    f = emu.lib().emu_pyr_ranges_ok
+    for W in list(range(1, 70)) + [639, 640, 641, 1919, 1920]:
+        for H in (1, 2, 3, 4, 5, 9, 34, 479):
+            assert f(W, H) == 1, (W, H)
