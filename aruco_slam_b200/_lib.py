@@ -9,6 +9,8 @@ import ctypes as C
 import os
 import subprocess
 
+import numpy as np
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("B2A_LIB", os.path.join(_HERE, "csrc", "libb2aruco.so"))        # B2A_LIB: an instrumented build (profiling only)
 
@@ -104,6 +106,7 @@ SYMBOLS = [
     "b2a_pack_robot_pose", "b2a_pack_map_marker", "b2a_slam_stream",
     "b2a_multi_create", "b2a_multi_destroy", "b2a_multi_num_devices", "b2a_multi_detect_pose", "b2a_draw_detected_markers", "b2a_detector_last_detections", "b2a_pack_detections",
     "b2a_default_refine_params", "b2a_refine_detected_markers", "b2a_detector_set_graph", "b2a_slam_robot_pose_submit", "b2a_slam_robot_pose_wait",
+    "b2a_host_alloc", "b2a_host_free",
 ]
 
 _lib = None
@@ -170,6 +173,9 @@ def lib():
                                                  C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2a_slam_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.b2a_slam_add_image.argtypes = [C.c_void_p] * 4
+        L.b2a_host_alloc.argtypes = [C.c_size_t, C.c_int, C.c_void_p]
+        L.b2a_host_free.argtypes = [C.c_void_p]
+        L.b2a_host_free.restype = None
         _lib = L
     return _lib
 
@@ -177,3 +183,26 @@ def lib():
 def check(rc: int):
     if rc != 0:
         raise B2AError(rc, lib().b2a_last_error().decode())
+
+
+class HostBuffer:
+    """b2a_host_alloc'd pinned staging memory as a numpy array (`.array`); freed with the object."""
+
+    def __init__(self, shape, dtype=np.uint8, write_combined=False):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        check(lib().b2a_host_alloc(n, 1 if write_combined else 0, C.byref(p)))
+        self._p = p
+        self.array = np.ctypeslib.as_array((C.c_uint8 * n).from_address(p.value)).view(dtype).reshape(shape)
+
+    def close(self):
+        if self._p is not None and self._p.value:
+            self.array = None
+            lib().b2a_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

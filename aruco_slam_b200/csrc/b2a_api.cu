@@ -38,6 +38,16 @@ static int set_err(int code, const std::string &msg) { g_err = msg; return code;
 extern "C" const char *b2a_last_error(void) { return g_err.c_str(); }
 extern "C" const char *b2a_version(void) { return "b2aruco 0.1 (sm_100a)"; }
 
+extern "C" int b2a_host_alloc(size_t bytes, int write_combined, void **out)
+{
+    if (!out || bytes == 0) return set_err(B2A_ERR_INVALID, "null argument");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0));
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(B2A_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
+    return B2A_OK;
+}
+extern "C" void b2a_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 extern "C" void b2a_default_detector_params(b2a_detector_params *p)
 {
     p->adaptiveThreshWinSizeMin = 3; p->adaptiveThreshWinSizeMax = 23; p->adaptiveThreshWinSizeStep = 10;

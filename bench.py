@@ -203,8 +203,7 @@ def bench_c4(args, rank, local_rank, world):
         nccl_init(dist, torch, local_rank)
     frames, enc, truth = synth.c4_stream(rank, n)
     d_frames = torch.from_numpy(frames).cuda()
-    h_frames = torch.from_numpy(frames).pin_memory()
-    h_np = h_frames.numpy()
+    h_np, _h_keep = host_frames(frames, args.host_mem)
 
     def new_filter():
         s = slam.ArucoSlam(synth.C4_DICT, synth.C4_MARKER_LENGTH, image_shape=(H, W), device=local_rank, r2c_tx=synth.C4_R2C[0], r2c_ty=synth.C4_R2C[1], max_landmarks=96)
@@ -412,6 +411,21 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------
 # CPU reference arm
 # ----------------------------------------------------------------------------------------------
+HOST_MEM_DEFAULT = "pinned"
+
+
+def host_frames(frames, kind):
+    """the frames in pinned host memory -> (numpy view, keep-alive)"""
+    if kind == "wc":
+        from aruco_slam_b200 import _lib
+        hb = _lib.HostBuffer(frames.shape, frames.dtype, write_combined=True)
+        hb.array[...] = frames
+        return hb.array, hb
+    import torch
+    t = torch.from_numpy(frames).pin_memory()
+    return t.numpy(), t
+
+
 A3_RATIO = None          # --aruco3 RATIO: useAruco3Detection with minMarkerLengthRatioOriginalImg = RATIO (minSideLengthCanonicalImg 32)
 
 
@@ -519,6 +533,8 @@ def main():
     ap.add_argument("--inflight", type=int, default=8, help="C4: frames of a stream kept in flight (1 .. 8)")
     ap.add_argument("--aruco3", type=float, default=None, metavar="RATIO",
                     help="C1-C3: run the detector's ArUco3 mode (useAruco3Detection, minMarkerLengthRatioOriginalImg = RATIO) in both arms")
+    ap.add_argument("--host-mem", default=HOST_MEM_DEFAULT, choices=["pinned", "wc"],
+                    help="host frames of the end-to-end legs: torch pinned memory, or write-combined pinned memory from b2a_host_alloc")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipelined", action="store_true", help="skip the two-handle / two-thread extra (use under ncu: the profiler serialises the two threads' launches)")
     args = ap.parse_args()
@@ -600,9 +616,9 @@ def main():
     det = aruco.ArucoDetector(dic, aruco.DetectorParameters(**a3_params()), max_shape=(H, W), max_batch=B, device=local_rank)
     cam = aruco._camera(K_CAM, D_CAM, MARKER_LENGTH)
     d_frames = torch.from_numpy(frames).cuda()
-    h_frames = torch.from_numpy(frames).pin_memory()
+    h_np, _h_keep = host_frames(frames, args.host_mem)
     fr_dev = aruco.ArucoDetector.frames_device(d_frames.data_ptr(), B, H, W)
-    fr_host, _keep = aruco.ArucoDetector._frames_host(h_frames.numpy())
+    fr_host, _keep = aruco.ArucoDetector._frames_host(h_np)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     lib_stream = torch.cuda.ExternalStream(det.stream, device=local_rank)
 

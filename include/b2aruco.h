@@ -73,6 +73,13 @@ typedef struct {
 
 void b2a_default_detector_params(b2a_detector_params *p);
 
+/* ---- pinned host staging memory for the frames handed to the detect calls (what the reference's node gets from cv_bridge,
+ * aruco_slam_node.cpp:93, once a caller owns the buffer).  cudaHostAlloc'd, usable from every device.  write_combined != 0 asks
+ * for write-combined pages: the GPU reads them over PCIe without snooping the CPU caches, which some hosts turn into a faster
+ * (and, with several GPUs, less contended) host-to-device copy; the CPU should only WRITE such memory, front to back. ---- */
+int  b2a_host_alloc(size_t bytes, int write_combined, void **out);
+void b2a_host_free(void *p);
+
 /* ---- dictionaries: cv::aruco::getPredefinedDictionary (aruco_slam.cpp:11-12) ---- */
 typedef struct {
     int markerSize, maxCorrectionBits, nMarkers, nBytes;
