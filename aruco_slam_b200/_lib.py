@@ -106,7 +106,7 @@ SYMBOLS = [
     "b2a_pack_robot_pose", "b2a_pack_map_marker", "b2a_slam_stream",
     "b2a_multi_create", "b2a_multi_destroy", "b2a_multi_num_devices", "b2a_multi_detect_pose", "b2a_draw_detected_markers", "b2a_detector_last_detections", "b2a_pack_detections",
     "b2a_default_refine_params", "b2a_refine_detected_markers", "b2a_detector_set_graph", "b2a_slam_robot_pose_submit", "b2a_slam_robot_pose_wait",
-    "b2a_host_alloc", "b2a_host_free",
+    "b2a_host_alloc", "b2a_host_free", "b2a_pack_detected_markers",
 ]
 
 _lib = None
@@ -173,6 +173,7 @@ def lib():
                                                  C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2a_slam_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.b2a_slam_add_image.argtypes = [C.c_void_p] * 4
+        L.b2a_pack_detected_markers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.b2a_host_alloc.argtypes = [C.c_size_t, C.c_int, C.c_void_p]
         L.b2a_host_free.argtypes = [C.c_void_p]
         L.b2a_host_free.restype = None

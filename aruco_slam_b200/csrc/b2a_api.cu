@@ -1994,6 +1994,71 @@ extern "C" void b2a_pack_map_marker(int index, double marker_length, const doubl
     *out = m;
 }
 
+namespace {
+// tf2::Matrix3x3::getRotation (Shepperd's method as tf2 writes it): row-major R -> (x, y, z, w)
+void tf2_get_rotation(const double *m, double *q)
+{
+    const double trace = m[0] + m[4] + m[8];
+    if (trace > 0.0) {
+        double s = std::sqrt(trace + 1.0);
+        q[3] = s * 0.5;
+        s = 0.5 / s;
+        q[0] = (m[7] - m[5]) * s; q[1] = (m[2] - m[6]) * s; q[2] = (m[3] - m[1]) * s;
+    } else {
+        const int i = m[0] < m[4] ? (m[4] < m[8] ? 2 : 1) : (m[0] < m[8] ? 2 : 0);
+        const int j = (i + 1) % 3, k = (i + 2) % 3;
+        double s = std::sqrt(m[i * 3 + i] - m[j * 3 + j] - m[k * 3 + k] + 1.0);
+        q[i] = s * 0.5;
+        s = 0.5 / s;
+        q[3] = (m[k * 3 + j] - m[j * 3 + k]) * s;
+        q[j] = (m[j * 3 + i] + m[i * 3 + j]) * s;
+        q[k] = (m[k * 3 + i] + m[i * 3 + k]) * s;
+    }
+}
+// tf2::Quaternion product a * b, (x, y, z, w)
+void quat_mul(const double *a, const double *b, double *o)
+{
+    o[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    o[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+    o[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+    o[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+}
+}  // namespace
+
+extern "C" int b2a_pack_detected_markers(const int32_t *ids, const double *rvecs, const double *tvecs, int n, double marker_length,
+                                         float useful_distance_threshold, const double r2c_q[4], const double r2c_t[3],
+                                         b2a_map_marker *out, int cap, int *n_out)
+{   // aruco_slam.cpp:324-347
+    if (n < 0 || !n_out || (n > 0 && (!ids || !rvecs || !tvecs)) || (cap > 0 && !out)) return set_err(B2A_ERR_INVALID, "null argument");
+    const double qi[4] = {0, 0, 0, 1}, t0[3] = {0, 0, 0};
+    const double *qt = r2c_q ? r2c_q : qi, *tt = r2c_t ? r2c_t : t0;
+    int cnt = 0;
+    for (int i = 0; i < n; ++i) {
+        const double *rv = rvecs + 3 * i, *tv = tvecs + 3 * i;
+        const float dist = (float)std::sqrt(tv[0] * tv[0] + tv[1] * tv[1] + tv[2] * tv[2]);
+        if (dist > useful_distance_threshold) continue;
+        if (cnt < cap) {
+            b2a_map_marker m;
+            std::memset(&m, 0, sizeof(m));
+            m.id = ids[i]; m.length = marker_length;
+            double R[9], q[4];
+            rodrigues_to_R(rv, R);
+            tf2_get_rotation(R, q);
+            // tf2::doTransform(pose, pose, r2c): position qt * (p, 0) * qt^-1 + t, orientation qt * q
+            const double p[4] = {tv[0], tv[1], tv[2], 0.0}, qc[4] = {-qt[0], -qt[1], -qt[2], qt[3]};
+            double a[4], r[4];
+            quat_mul(qt, p, a); quat_mul(a, qc, r);
+            m.x = r[0] + tt[0]; m.y = r[1] + tt[1]; m.z = r[2] + tt[2];
+            quat_mul(qt, q, m.q);
+            out[cnt] = m;
+        }
+        ++cnt;
+    }
+    *n_out = cnt;
+    if (cnt > cap) return set_err(B2A_ERR_CAPACITY, "more detected markers than the output array");
+    return B2A_OK;
+}
+
 extern "C" int b2a_slam_robot_pose(b2a_slam *s, b2a_pose_with_covariance *out)
 {
     if (!s || !out) return set_err(B2A_ERR_INVALID, "null argument");

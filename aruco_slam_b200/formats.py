@@ -4,6 +4,7 @@
   quaternion_from_rpy      <-> tf2::Quaternion::setRPY         (map_loader.cpp:90, aruco_slam.cpp:273,387)
   robot_pose(slam)         <-> ArucoSlam::toRosPose            (aruco_slam.cpp:376-407)
   detected_map(slam)       <-> detected_map_ of addImage       (aruco_slam.cpp:266-281)
+  detected_markers(...)    <-> detected_markers_ of getObservations / toRosDetectedMarkers (aruco_slam.cpp:324-347)
 
 Thin ctypes wrappers over the host-side entry points of libb2aruco.so (include/b2aruco.h)."""
 import ctypes as C
@@ -107,3 +108,19 @@ def detected_map_records(mu, marker_length: float):
         _lib.lib().b2a_pack_map_marker.argtypes = [C.c_int, C.c_double, C.c_void_p, C.c_void_p]
         _lib.lib().b2a_pack_map_marker(i, float(marker_length), lm, C.byref(arr[i]))
     return _markers(arr, n)
+
+
+def detected_markers(ids, rvecs, tvecs, marker_length: float, useful_distance_threshold: float = 3.0, r2c_q=None, r2c_t=None):
+    """toRosDetectedMarkers: the cubes of the current frame's markers inside the useful range, in detection order, in the robot
+    frame (b2a_pack_detected_markers); r2c_q = (x, y, z, w) rotation and r2c_t = translation of transformStamped_r2c"""
+    ids = np.ascontiguousarray(np.asarray(ids).ravel(), np.int32)
+    rv = np.ascontiguousarray(np.asarray(rvecs, np.float64).reshape(-1, 3))
+    tv = np.ascontiguousarray(np.asarray(tvecs, np.float64).reshape(-1, 3))
+    n = len(ids)
+    arr = (_lib.MapMarker * max(1, n))()
+    cnt = C.c_int(0)
+    q = None if r2c_q is None else (C.c_double * 4)(*[float(v) for v in r2c_q])
+    t = None if r2c_t is None else (C.c_double * 3)(*[float(v) for v in r2c_t])
+    _lib.check(_lib.lib().b2a_pack_detected_markers(ids.ctypes.data, rv.ctypes.data, tv.ctypes.data, n, float(marker_length), float(useful_distance_threshold),
+                                                    q, t, arr, max(1, n), C.byref(cnt)))
+    return _markers(arr, cnt.value)

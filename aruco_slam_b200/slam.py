@@ -79,6 +79,19 @@ class ArucoSlam:
             return None                                        # addImage before the first encoder message does not look at the frame (:84-85)
         return self.detector.drawDetectedMarkers(img.copy(), r.corners[0], r.ids[0]) if len(r.ids[0]) else img.copy()
 
+    def toRosDetectedMarkers(self, r2c_q=None, r2c_t=None):
+        """the cubes of the last frame's markers inside the useful range, in the robot frame (detected_markers_, aruco_slam.cpp:324-347);
+        r2c_q / r2c_t = rotation (x, y, z, w) and translation of transformStamped_r2c (default: identity, (r2c_tx, r2c_ty, 0))"""
+        from . import formats
+        try:
+            r = self.detector.last_detections()
+        except _lib.B2AError:
+            return []
+        if r.rvecs is None or not len(r.ids[0]):
+            return []
+        t = (self.params.r2c_tx, self.params.r2c_ty, 0.0) if r2c_t is None else r2c_t
+        return formats.detected_markers(r.ids[0], r.rvecs[0], r.tvecs[0], self.marker_length, self.params.useful_distance_threshold, r2c_q, t)
+
     def addImageFrames(self, frames):
         """addImage on a one-frame b2a_frames descriptor (host or device memory, see ArucoDetector.frames_device)"""
         if self._cam is None:

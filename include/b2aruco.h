@@ -318,6 +318,15 @@ void b2a_quaternion_from_rpy(double roll, double pitch, double yaw, double q[4])
 int  b2a_map_parse(const char *text, size_t len, b2a_map_marker *out, int cap, int *n_out);
 /* the same from a file; B2A_ERR_INVALID when the file cannot be opened (the reference logs and leaves the map empty, :13-17) */
 int  b2a_map_load(const char *path, b2a_map_marker *out, int cap, int *n_out);
+/* ArucoSlam::toRosDetectedMarkers (the cubes getObservations builds for the markers of the CURRENT frame, aruco_slam.cpp:324-347):
+ * one record per detection whose distance passes the range gate (float norm(tvec) <= useful_distance_threshold, :327-333), in
+ * detection order; id = the marker's ArUco id, length = marker_length, orientation = r2c rotation * getRotation(Rodrigues(rvec))
+ * (tf2::Matrix3x3::getRotation, fillTransform :473-489), position = r2c * tvec (tf2::doTransform with transformStamped_r2c_, frame
+ * "base_link", lifetime 0.1 s); roll / pitch / yaw are left 0.  r2c_q = (x, y, z, w) (NULL = identity), r2c_t = translation
+ * (NULL = 0).  Host only.  B2A_ERR_CAPACITY (with *n_out = the count) when cap is too small. */
+int  b2a_pack_detected_markers(const int32_t *ids, const double *rvecs, const double *tvecs, int n, double marker_length,
+                               float useful_distance_threshold, const double r2c_q[4], const double r2c_t[3],
+                               b2a_map_marker *out, int cap, int *n_out);
 /* ArucoSlam::toRosPose (aruco_slam.cpp:376-407): position (mu0, mu1, 0.1), orientation setRPY(0, 0, mu2), and the 6x6 row-major
  * covariance with Sigma[0:3,0:3] scattered to entries 0,1,5 / 6,7,11 / 30,31,35 (all others 0). */
 typedef struct {

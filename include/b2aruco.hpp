@@ -12,13 +12,17 @@
 // cv::Point2f / cv::Vec3d are replaced by the POD stand-ins below; with OpenCV present the
 // adaptor is `Image{mat.data, mat.cols, mat.rows, mat.channels(), mat.step}` and a
 // reinterpret_cast of the Point2f / Vec3d vectors (identical layouts).  INTEGRATION.md shows
-// the three-line patch of aruco_slam.cpp.
+// the three-line patch of aruco_slam.cpp.  b2a::ArucoSlam (end of this file) is the reference's ArucoSlam class itself over the C
+// ABI: ArucoSlam(init data), addEncoder, addImage, setCameraParameters, toRosMappedMarkers, toRosDetectedMarkers, toRosPose,
+// getMarkedImg (include/aruco_slam/aruco_slam.h:101-152) with plain records where the reference returns ROS messages.
 //
 // The detector handle (device memory, streams) is cached per (device, dictionary, frame size):
 // the reference calls detectMarkers once per camera frame from a single thread
 // (aruco_slam_node.cpp:79,96), so the first call creates the handle and later calls reuse it.
 #pragma once
+#include <chrono>
 #include <cstdint>
+#include <cstring>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -206,4 +210,133 @@ inline b2a_pose_with_covariance robotPose(b2a_slam *slam)
     check(b2a_slam_robot_pose(slam, &p));
     return p;
 }
+// ---- the reference's ArucoSlam class (include/aruco_slam/aruco_slam.h:101-193) over the C ABI: same public methods, no ROS types ----
+// ArucoSlamIniteData (aruco_slam.h:40-60) without the frame / topic / file names the node consumes itself; the robot-to-camera
+// transform is a plain (rotation quaternion x y z w, translation) pair; image_width / image_height / max_landmarks size the buffers.
+struct ArucoSlamIniteData {
+    double Q_k = 0.01, R_x = 100.0, R_y = 100.0, R_theta = 10.0;      // parameters.yaml:5-8
+    double kl = 0.05, kr = 0.05, b = 0.09;                            // parameters.yaml:11-13
+    int markers_dictionary = aruco::DICT_ARUCO_ORIGINAL;
+    double marker_length = 0.27;
+    double r2c_rotation[4] = {0, 0, 0, 1};
+    double r2c_translation[3] = {0, 0, 0};
+    float USEFUL_DISTANCE_THRESHOLD = 3;
+    int image_width = 640, image_height = 480;
+    int max_landmarks = 0;              // 0 = 512
+    int device = 0;
+};
+// an owned 8-bit image (what getMarkedImg returns: cv::Mat markered_img_, aruco_slam.h:152)
+struct OwnedImage {
+    std::vector<uint8_t> data;
+    int cols = 0, rows = 0, channels = 1;
+    bool empty() const { return data.empty(); }
+};
+
+class ArucoSlam {
+public:
+    explicit ArucoSlam(const ArucoSlamIniteData &d) : init_(d)
+    {
+        b2a_slam_params p;
+        b2a_default_slam_params(&p);
+        p.Q_k = d.Q_k; p.R_x = d.R_x; p.R_y = d.R_y; p.R_theta = d.R_theta; p.kl = d.kl; p.kr = d.kr; p.b = d.b;
+        p.r2c_tx = d.r2c_translation[0]; p.r2c_ty = d.r2c_translation[1];
+        p.useful_distance_threshold = d.USEFUL_DISTANCE_THRESHOLD; p.max_landmarks = d.max_landmarks;
+        check(b2a_slam_create(d.device, &p, &slam_));
+        dictionary_ = aruco::getPredefinedDictionary(d.markers_dictionary);                 // aruco_slam.cpp:11-12
+        b2a_detector_config cfg{d.device, d.image_width, d.image_height, 1, 0, 0};
+        const int rc = b2a_detector_create(&cfg, &dictionary_->c, nullptr, &det_);
+        if (rc != B2A_OK) { const std::string m = b2a_last_error(); b2a_slam_destroy(slam_); slam_ = nullptr; throw Exception(rc, m); }
+    }
+    ~ArucoSlam() { if (det_) b2a_detector_destroy(det_); if (slam_) b2a_slam_destroy(slam_); }
+    ArucoSlam(const ArucoSlam &) = delete;
+    ArucoSlam &operator=(const ArucoSlam &) = delete;
+
+    // addEncoder(wl, wr) (aruco_slam.cpp:21-74): the time step is what a steady clock measured since the previous call, as the
+    // reference takes it from ros::Time::now() (:26-32); the first call only starts the clock (:24-29).  The three-argument
+    // form takes dt from the caller (replayed logs, tests).
+    void addEncoder(const double &wl, const double &wr)
+    {
+        const auto now = std::chrono::steady_clock::now();
+        const double dt = started_ ? std::chrono::duration<double>(now - last_time_).count() : 0.0;
+        last_time_ = now; started_ = true;
+        check(b2a_slam_add_encoder(slam_, wl, wr, dt));
+    }
+    void addEncoder(const double &wl, const double &wr, double dt) { started_ = true; last_time_ = std::chrono::steady_clock::now(); check(b2a_slam_add_encoder(slam_, wl, wr, dt)); }
+
+    // addImage(img) (aruco_slam.cpp:76-263): detection, poses, observations and the EKF loop of one frame; the frame is kept for getMarkedImg
+    void addImage(const Image &img)
+    {
+        if (img.empty()) throw Exception(B2A_ERR_INVALID, "addImage: empty image");
+        if (!have_cam_) throw Exception(B2A_ERR_INVALID, "addImage: setCameraParameters first");
+        b2a_frames fr{img.data, 0, 1, img.cols, img.rows, img.channels, img.step, 0};
+        check(b2a_slam_add_image(slam_, det_, &fr, &cam_));
+        const size_t row = (size_t)img.cols * img.channels, step = img.step ? img.step : row;
+        last_.cols = img.cols; last_.rows = img.rows; last_.channels = img.channels;
+        last_.data.resize(row * img.rows);
+        for (int y = 0; y < img.rows; ++y) std::memcpy(last_.data.data() + y * row, img.data + y * step, row);
+    }
+    // setCameraParameters (aruco_slam.h:129-133): K 9 doubles row-major, dist 0, 4 or 5 doubles
+    void setCameraParameters(const double *cameraMatrix, const std::vector<double> &distCoeffs)
+    {
+        if (distCoeffs.size() != 0 && distCoeffs.size() != 4 && distCoeffs.size() != 5) throw Exception(B2A_ERR_UNSUPPORTED, "setCameraParameters: distCoeffs must hold 0, 4 or 5 values");
+        cam_ = b2a_camera{};
+        for (int i = 0; i < 9; ++i) cam_.K[i] = cameraMatrix[i];
+        cam_.nD = (int)distCoeffs.size();
+        for (int i = 0; i < cam_.nD; ++i) cam_.D[i] = distCoeffs[i];
+        cam_.marker_length = (float)init_.marker_length;
+        have_cam_ = true;
+    }
+    // toRosMappedMarkers (detected_map_, :265-281): one cube per landmark of the map
+    std::vector<b2a_map_marker> toRosMappedMarkers()
+    {
+        const int n = (b2a_slam_dim(slam_) - 3) / 3;
+        std::vector<b2a_map_marker> out((size_t)(n > 0 ? n : 1));
+        int cnt = 0;
+        check(b2a_slam_detected_map(slam_, init_.marker_length, out.data(), (int)out.size(), &cnt));
+        out.resize((size_t)cnt);
+        return out;
+    }
+    // toRosDetectedMarkers (detected_markers_, :324-347): the cubes of the last frame's markers inside the useful range, robot frame
+    std::vector<b2a_map_marker> toRosDetectedMarkers()
+    {
+        b2a_detections det{};
+        if (b2a_detector_last_detections(det_, &det) != B2A_OK || !det.rvecs) return {};
+        const int n = det.n_accepted[0];
+        std::vector<b2a_map_marker> out((size_t)(n > 0 ? n : 1));
+        int cnt = 0;
+        check(b2a_pack_detected_markers(det.ids, det.rvecs, det.tvecs, n, init_.marker_length, init_.USEFUL_DISTANCE_THRESHOLD, init_.r2c_rotation,
+                                        init_.r2c_translation, out.data(), (int)out.size(), &cnt));
+        out.resize((size_t)cnt);
+        return out;
+    }
+    // toRosPose (:376-407)
+    b2a_pose_with_covariance toRosPose() { return robotPose(slam_); }
+    // getMarkedImg (aruco_slam.h:152): the last frame with drawDetectedMarkers applied (:318-319)
+    OwnedImage getMarkedImg()
+    {
+        OwnedImage out = last_;
+        if (out.empty()) return out;
+        b2a_detections det{};
+        if (b2a_detector_last_detections(det_, &det) != B2A_OK) return out;     // addImage before the first encoder message does not look at the frame (:84-85)
+        const int n = det.n_accepted[0];
+        if (n > 0) check(b2a_draw_detected_markers(det_, out.data.data(), out.cols, out.rows, out.channels, 0, det.corners, det.ids, n, nullptr));
+        return out;
+    }
+    // mu_ and sigma_ (aruco_slam.h:182-183), row-major
+    std::vector<double> mu() { std::vector<double> m((size_t)b2a_slam_dim(slam_)); check(b2a_slam_get_state(slam_, m.data(), nullptr, nullptr)); return m; }
+    std::vector<double> sigma() { const size_t n = (size_t)b2a_slam_dim(slam_); std::vector<double> s(n * n); check(b2a_slam_get_state(slam_, nullptr, s.data(), nullptr)); return s; }
+    b2a_slam *handle() { return slam_; }
+    b2a_detector *detector() { return det_; }
+
+private:
+    ArucoSlamIniteData init_;
+    b2a_slam *slam_ = nullptr;
+    b2a_detector *det_ = nullptr;
+    aruco::DictionaryPtr dictionary_;
+    b2a_camera cam_{};
+    bool have_cam_ = false, started_ = false;
+    std::chrono::steady_clock::time_point last_time_{};
+    OwnedImage last_;
+};
+
 }  // namespace b2a

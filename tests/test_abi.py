@@ -101,3 +101,60 @@ def test_cpp_shim_matches_python_surface(so_path, tmp_path):
         assert np.allclose(nums[:8], c.reshape(-1), atol=0.051)
         assert np.allclose(nums[8:11], rv.reshape(-1), atol=2e-5) and np.allclose(nums[11:14], tv.reshape(-1), atol=2e-5)
     det.close()
+
+
+def test_cpp_arucoslam_class_compiles_and_fails_loudly_without_gpu(so_path, tmp_path):
+    """b2a::ArucoSlam (the reference's class interface over the C ABI, include/b2aruco.hpp) builds with plain g++; without a GPU its
+    constructor throws the library's error"""
+    import subprocess
+    import torch
+    exe = _build_demo(so_path, tmp_path)
+    pgm = tmp_path / "f.pgm"
+    with open(pgm, "wb") as f:
+        f.write(b"P5\n64 48\n255\n" + bytes(64 * 48))
+    r = subprocess.run([exe, str(pgm), "0", "0.27", "slam"], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "pose " in r.stdout and "marked 64 x 48 x 1" in r.stdout
+    else:
+        assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_arucoslam_matches_python_mirror(so_path, tmp_path):
+    """the same three addEncoder / addImage steps through b2a::ArucoSlam (C++) and through aruco_slam_b200.slam.ArucoSlam: pose record,
+    mapped markers, detected-marker cubes and the marked image agree"""
+    import subprocess
+    import numpy as np
+    from aruco_slam_b200 import slam, synth, formats
+    exe = _build_demo(so_path, tmp_path)
+    fr = synth.render_config("C1", 1).image
+    H, W = fr.shape
+    pgm = tmp_path / "c1.pgm"
+    with open(pgm, "wb") as f:
+        f.write(b"P5\n%d %d\n255\n" % (W, H) + fr.tobytes())
+    out = subprocess.run([exe, str(pgm), "0", "0.27", "slam"], capture_output=True, text=True, check=True).stdout.splitlines()
+    s = slam.ArucoSlam(0, 0.27, image_shape=fr.shape, r2c_tx=0.12, r2c_ty=0.0)
+    K = np.array([[1400.0, 0, W / 2.0], [0, 1400.0, H / 2.0], [0, 0, 1]])
+    s.setCameraParameters(K, np.zeros(0))
+    s.addEncoder(0.0, 0.0, 0.0)
+    for _ in range(3):
+        s.addEncoder(2.0, 2.5, 0.05)
+        s.addImage(fr)
+    nums = lambda line: [float(x) for x in re.findall(r"-?\d+\.\d+(?:e[-+]\d+)?", line)]
+    pose = formats.robot_pose(s)
+    got = nums(out[0])
+    assert out[0].startswith("pose ") and np.allclose(got[:3], pose.position, atol=1e-8) and np.allclose(got[3:7], pose.orientation, atol=1e-8)
+    assert np.allclose(got[7:10], [pose.covariance[0, 0], pose.covariance[1, 1], pose.covariance[5, 5]], rtol=1e-6, atol=1e-12)
+    mapped = [l for l in out if l.startswith("mapped ")]
+    want = formats.detected_map(s)
+    assert len(mapped) == len(want) > 0
+    for line, m in zip(mapped, want):
+        assert int(line.split()[1]) == m.id and np.allclose(nums(line)[-3:], [m.x, m.y, m.yaw], atol=1e-8)
+    det = [l for l in out if l.startswith("detected ")]
+    wd = s.toRosDetectedMarkers(r2c_t=(0.12, 0.0, 0.25))
+    assert len(det) == len(wd) > 0
+    for line, m in zip(det, wd):
+        assert int(line.split()[1]) == m.id and np.allclose(nums(line)[-7:], [m.x, m.y, m.z, *m.q], atol=1e-8)
+    marked = s.getMarkedImg()
+    assert out[-1].startswith("marked %d x %d x 1 sum %d dim %d" % (W, H, int(marked.astype(np.int64).sum()), s.dim))
+    s.close()

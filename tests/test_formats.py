@@ -64,3 +64,33 @@ def test_parse_map_short_and_malformed_lines():
     assert [m.id for m in formats.parse_map("5 0.27 1 2")] == [5]                      # no trailing newline
     with pytest.raises(B2AError):
         formats.parse_map("1 1 1 1\n2 1 1 1\n", cap=1)
+
+
+def test_detected_marker_cubes_vs_reference_run():
+    """ArucoSlam::toRosDetectedMarkers (aruco_slam.cpp:324-347) through b2a_pack_detected_markers against the cubes the reference
+    itself produced (tests/golden/slam_scene.npz, slam_synth.npz: detm_*): same markers pass the range gate, same order,
+    positions and orientations to rounding"""
+    import os
+    for name in ("slam_scene", "slam_synth"):
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+        f = total = dropped = 0
+        while "det_ids_%d" % f in g.files:
+            ms = formats.detected_markers(g["det_ids_%d" % f], g["det_rvecs_%d" % f], g["det_tvecs_%d" % f], float(g["marker_length"]),
+                                          float(g["useful_distance_threshold"]), None, g["r2c_t"])
+            assert np.array_equal([m.id for m in ms], g["detm_id_%d" % f]), (name, f)
+            if ms:
+                assert np.abs(np.array([[m.x, m.y, m.z] for m in ms]) - g["detm_pos_%d" % f]).max() < 1e-12
+                assert np.abs(np.array([m.q for m in ms]) - g["detm_q_%d" % f]).max() < 1e-12
+                assert all(m.length == float(g["marker_length"]) for m in ms)
+            total += len(ms); dropped += len(g["det_ids_%d" % f]) - len(ms); f += 1
+        assert total > 50 and dropped > 0
+
+
+def test_detected_marker_cubes_rotated_mount():
+    """a camera mounted a quarter turn about z: positions and orientations follow tf2::doTransform (out = T * in)"""
+    s = np.sqrt(0.5)
+    ms = formats.detected_markers([7], [[0.0, 0.0, 0.0]], [[1.0, 2.0, 0.5]], 0.27, 3.0, (0, 0, s, s), (0.1, 0.0, 0.3))
+    assert len(ms) == 1 and ms[0].id == 7
+    assert np.allclose([ms[0].x, ms[0].y, ms[0].z], [-2.0 + 0.1, 1.0, 0.8], atol=1e-12)
+    assert np.allclose(ms[0].q, (0, 0, s, s), atol=1e-12)
+    assert formats.detected_markers([7], [[0.0, 0.0, 0.0]], [[0.0, 0.0, 3.5]], 0.27, 3.0) == []          # beyond the useful range

@@ -1,7 +1,9 @@
 // b2a_demo.cpp -- the reference's two calls (src/aruco_slam.cpp:313-314) through the C++ shim, no ROS:
-//   ./b2a_demo frame.pgm [dict_id=10] [marker_length=0.27]
+//   ./b2a_demo frame.pgm [dict_id=10] [marker_length=0.27] [slam]
 // reads a binary PGM (P5, 8 bit), runs detectMarkers + estimatePoseSingleMarkers on GPU 0 and prints
-// ids, corners and poses.  Build:  g++ -std=c++17 -Iinclude tools/b2a_demo.cpp -Laruco_slam_b200/csrc -lb2aruco -o b2a_demo
+// ids, corners and poses.  With a fourth argument "slam" the frame goes three times through b2a::ArucoSlam
+// (the reference's class interface: addEncoder / addImage / toRosPose / toRosMappedMarkers / toRosDetectedMarkers /
+// getMarkedImg) with fixed encoder readings and time steps, and the records are printed.  Build:  g++ -std=c++17 -Iinclude tools/b2a_demo.cpp -Laruco_slam_b200/csrc -lb2aruco -o b2a_demo
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -34,6 +36,34 @@ int main(int argc, char **argv)
     if (!read_pgm(argv[1], px, w, h)) { std::fprintf(stderr, "cannot read %s as 8-bit P5\n", argv[1]); return 2; }
     const int dict_id = argc > 2 ? std::atoi(argv[2]) : b2a::aruco::DICT_6X6_250;
     const float len = argc > 3 ? (float)std::atof(argv[3]) : 0.27f;
+    if (argc > 4 && std::string(argv[4]) == "slam") {
+        try {
+            b2a::ArucoSlamIniteData init;
+            init.markers_dictionary = dict_id; init.marker_length = len; init.image_width = w; init.image_height = h;
+            init.r2c_translation[0] = 0.12; init.r2c_translation[2] = 0.25;
+            b2a::ArucoSlam slam(init);
+            const double K[9] = {1400.0, 0, w / 2.0, 0, 1400.0, h / 2.0, 0, 0, 1};
+            slam.setCameraParameters(K, {});
+            slam.addEncoder(0.0, 0.0, 0.0);                              // the first message only starts the clock
+            for (int k = 0; k < 3; ++k) {
+                slam.addEncoder(2.0, 2.5, 0.05);
+                slam.addImage(b2a::Image{px.data(), w, h, 1, 0});
+            }
+            const auto pose = slam.toRosPose();
+            std::printf("pose %.9f %.9f %.9f q %.9f %.9f %.9f %.9f cov %.9e %.9e %.9e\n", pose.position[0], pose.position[1], pose.position[2], pose.orientation[0],
+                        pose.orientation[1], pose.orientation[2], pose.orientation[3], pose.covariance[0], pose.covariance[7], pose.covariance[35]);
+            for (const auto &m : slam.toRosMappedMarkers()) std::printf("mapped %d %.9f %.9f %.9f\n", m.id, m.x, m.y, m.yaw);
+            for (const auto &m : slam.toRosDetectedMarkers()) std::printf("detected %d %.9f %.9f %.9f q %.9f %.9f %.9f %.9f\n", m.id, m.x, m.y, m.z, m.q[0], m.q[1], m.q[2], m.q[3]);
+            const auto img = slam.getMarkedImg();
+            unsigned long long sum = 0;
+            for (uint8_t v : img.data) sum += v;
+            std::printf("marked %d x %d x %d sum %llu dim %zu\n", img.cols, img.rows, img.channels, sum, slam.mu().size());
+        } catch (const b2a::Exception &e) {
+            std::fprintf(stderr, "b2aruco error %d: %s\n", e.code, e.what());
+            return 1;
+        }
+        return 0;
+    }
     try {
         auto dict = b2a::aruco::getPredefinedDictionary(dict_id);
         std::vector<std::vector<b2a::Point2f>> corners, rejected;
