@@ -132,8 +132,9 @@ def test_cpp_arucoslam_matches_python_mirror(so_path, tmp_path):
     pgm = tmp_path / "c1.pgm"
     with open(pgm, "wb") as f:
         f.write(b"P5\n%d %d\n255\n" % (W, H) + fr.tobytes())
-    out = subprocess.run([exe, str(pgm), "0", "0.27", "slam"], capture_output=True, text=True, check=True).stdout.splitlines()
-    s = slam.ArucoSlam(0, 0.27, image_shape=fr.shape, r2c_tx=0.12, r2c_ty=0.0)
+    # markers of 50-90 px seen with f = 1400 px: a 0.1 m marker is 1.6-2.8 m away, inside the 3 m useful range
+    out = subprocess.run([exe, str(pgm), "0", "0.1", "slam"], capture_output=True, text=True, check=True).stdout.splitlines()
+    s = slam.ArucoSlam(0, 0.1, image_shape=fr.shape, r2c_tx=0.12, r2c_ty=0.0, R_x=0.1, R_y=0.1, R_theta=0.01)      # the demo's values
     K = np.array([[1400.0, 0, W / 2.0], [0, 1400.0, H / 2.0], [0, 0, 1]])
     s.setCameraParameters(K, np.zeros(0))
     s.addEncoder(0.0, 0.0, 0.0)
@@ -147,7 +148,7 @@ def test_cpp_arucoslam_matches_python_mirror(so_path, tmp_path):
     assert np.allclose(got[7:10], [pose.covariance[0, 0], pose.covariance[1, 1], pose.covariance[5, 5]], rtol=1e-6, atol=1e-12)
     mapped = [l for l in out if l.startswith("mapped ")]
     want = formats.detected_map(s)
-    assert len(mapped) == len(want) > 0
+    assert len(mapped) == len(want) == 4
     for line, m in zip(mapped, want):
         assert int(line.split()[1]) == m.id and np.allclose(nums(line)[-3:], [m.x, m.y, m.yaw], atol=1e-8)
     det = [l for l in out if l.startswith("detected ")]

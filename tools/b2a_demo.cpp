@@ -41,6 +41,7 @@ int main(int argc, char **argv)
             b2a::ArucoSlamIniteData init;
             init.markers_dictionary = dict_id; init.marker_length = len; init.image_width = w; init.image_height = h;
             init.r2c_translation[0] = 0.12; init.r2c_translation[2] = 0.25;
+            init.R_x = 0.1; init.R_y = 0.1; init.R_theta = 0.01;          // observation noise small enough for integer-pixel corners to pass the covariance gate (:367-368)
             b2a::ArucoSlam slam(init);
             const double K[9] = {1400.0, 0, w / 2.0, 0, 1400.0, h / 2.0, 0, 0, 1};
             slam.setCameraParameters(K, {});
