@@ -159,3 +159,17 @@ def test_cpp_arucoslam_matches_python_mirror(so_path, tmp_path):
     marked = s.getMarkedImg()
     assert out[-1].startswith("marked %d x %d x 1 sum %d dim %d" % (W, H, int(marked.astype(np.int64).sum()), s.dim))
     s.close()
+
+
+def test_host_staging_memory_needs_a_device(so_path):
+    """b2a_host_alloc is cudaHostAlloc: without a CUDA device it reports the error instead of handing out pageable memory"""
+    import torch
+    from aruco_slam_b200 import _lib
+    if torch.cuda.is_available():
+        hb = _lib.HostBuffer((3, 5), write_combined=True)
+        hb.array[...] = 7
+        assert hb.array.shape == (3, 5) and int(hb.array.sum()) == 105
+        hb.close()
+    else:
+        with pytest.raises(_lib.B2AError):
+            _lib.HostBuffer((3, 5))
