@@ -4,6 +4,7 @@
 //     cv::aruco::getPredefinedDictionary(int)                                   -> b2a::aruco::getPredefinedDictionary
 //     cv::aruco::detectMarkers(img, dictionary, corners, ids[, params, rejected]) -> b2a::aruco::detectMarkers
 //     cv::aruco::estimatePoseSingleMarkers(corners, len, K, D, rvecs, tvecs)     -> b2a::aruco::estimatePoseSingleMarkers
+//     cv::aruco::drawDetectedMarkers(image, corners, ids)            (:318-319)  -> b2a::aruco::drawDetectedMarkers
 //
 // Same argument order and meaning, same output container shapes
 // (std::vector<std::vector<Point2f>>, std::vector<int>, std::vector<Vec3d>, aruco_slam.cpp:309-311),
@@ -186,6 +187,31 @@ inline void estimatePoseSingleMarkers(const std::vector<std::vector<Point2f>> &c
         h = tmp->h;
     }
     check(b2a_estimate_pose_single_markers(h, flat.data(), n, &cam, &rvecs[0].v[0], &tvecs[0].v[0]));
+}
+
+// cv::aruco::drawDetectedMarkers(image, corners, ids, borderColor) (aruco_slam.cpp:318-319): the overlay is drawn into `image` in
+// place.  `image` is a writable 8-bit image (1 or 3 channels) no larger than the frame of the last detectMarkers call on this
+// thread, whose handle does the drawing; ids may be empty (no labels); borderColor = (b, g, r), default green.
+struct MutableImage {
+    uint8_t *data = nullptr;
+    int cols = 0, rows = 0, channels = 1;
+    size_t step = 0;
+    bool empty() const { return !data || cols <= 0 || rows <= 0; }
+};
+inline void drawDetectedMarkers(const MutableImage &image, const std::vector<std::vector<Point2f>> &corners, const std::vector<int> &ids = {},
+                                const uint8_t *borderColor = nullptr)
+{
+    if (image.empty()) throw Exception(B2A_ERR_INVALID, "drawDetectedMarkers: empty image");
+    if (!ids.empty() && ids.size() != corners.size()) throw Exception(B2A_ERR_INVALID, "drawDetectedMarkers: ids and corners differ in length");   // CV_Assert
+    b2a_detector *h = detail::last_handle();
+    if (!h) throw Exception(B2A_ERR_INVALID, "drawDetectedMarkers: no detectMarkers call on this thread yet");
+    const int n = (int)corners.size();
+    std::vector<float> flat((size_t)n * 8);
+    for (int i = 0; i < n; ++i) {
+        if (corners[i].size() != 4) throw Exception(B2A_ERR_INVALID, "drawDetectedMarkers: a marker needs 4 corners");
+        for (int j = 0; j < 4; ++j) { flat[(i * 4 + j) * 2] = corners[i][j].x; flat[(i * 4 + j) * 2 + 1] = corners[i][j].y; }
+    }
+    check(b2a_draw_detected_markers(h, image.data, image.cols, image.rows, image.channels, image.step, flat.data(), ids.empty() ? nullptr : ids.data(), n, borderColor));
 }
 
 }  // namespace aruco

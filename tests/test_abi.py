@@ -173,3 +173,33 @@ def test_host_staging_memory_needs_a_device(so_path):
     else:
         with pytest.raises(_lib.B2AError):
             _lib.HostBuffer((3, 5))
+
+
+def test_cpp_shim_draw_wrapper_compiles(so_path, tmp_path):
+    """b2a::aruco::drawDetectedMarkers (aruco_slam.cpp:318-319 through the shim) builds with plain g++ -Wall -Wextra; without a GPU the
+    program stops at the detect call with the library's error"""
+    import subprocess
+    import torch
+    src = tmp_path / "draw.cpp"
+    src.write_text('''#include "b2aruco.hpp"
+#include <cstdio>
+int main() {
+    try {
+        std::vector<uint8_t> px(64 * 48, 120);
+        auto dict = b2a::aruco::getPredefinedDictionary(0);
+        std::vector<std::vector<b2a::Point2f>> corners; std::vector<int> ids;
+        b2a::aruco::detectMarkers(b2a::Image{px.data(), 64, 48, 1, 0}, dict, corners, ids);
+        b2a::aruco::drawDetectedMarkers(b2a::aruco::MutableImage{px.data(), 64, 48, 1, 0}, corners, ids);
+        std::printf("%zu markers drawn\\n", ids.size());
+    } catch (const b2a::Exception &e) { std::fprintf(stderr, "b2aruco error %d: %s\\n", e.code, e.what()); return 1; }
+    return 0;
+}
+''')
+    exe = str(tmp_path / "draw")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src), "-L" + os.path.dirname(so_path), "-lb2aruco",
+                           "-Wl,-rpath," + os.path.dirname(so_path), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "0 markers drawn" in r.stdout
+    else:
+        assert r.returncode == 1 and "no CUDA device" in r.stderr
