@@ -5,6 +5,8 @@
   robot_pose(slam)         <-> ArucoSlam::toRosPose            (aruco_slam.cpp:376-407)
   detected_map(slam)       <-> detected_map_ of addImage       (aruco_slam.cpp:266-281)
   detected_markers(...)    <-> detected_markers_ of getObservations / toRosDetectedMarkers (aruco_slam.cpp:324-347)
+  load_parameters(path)    <-> ArucoSlamRosNode::parseArucoSlamIniteData (aruco_slam_node.cpp:146-164) on parameters.yaml
+  load_camera(path)        <-> the camera block of default.yaml (:10-20): K and (k1, k2, p1, p2, k3)
 
 Thin ctypes wrappers over the host-side entry points of libb2aruco.so (include/b2aruco.h)."""
 import ctypes as C
@@ -124,3 +126,35 @@ def detected_markers(ids, rvecs, tvecs, marker_length: float, useful_distance_th
     _lib.check(_lib.lib().b2a_pack_detected_markers(ids.ctypes.data, rv.ctypes.data, tv.ctypes.data, n, float(marker_length), float(useful_distance_threshold),
                                                     q, t, arr, max(1, n), C.byref(cnt)))
     return _markers(arr, cnt.value)
+
+
+def load_parameters(path_or_text) -> dict:
+    """The rosparam tree of the reference's parameters.yaml as parseArucoSlamIniteData reads it (aruco_slam_node.cpp:146-164): keyword
+    arguments for slam.ArucoSlam (`slam`: Q_k, R_x, R_y, R_theta, kl, kr, b, useful_distance_threshold), `markers_dictionary`,
+    `marker_length`, and the frame / topic names.  A key the file lacks keeps ArucoSlamIniteData's default, as nh.getParam leaves it.
+    The node asks for const/USEFUL_DISTANCE_THRESHOLD_ (with the trailing underscore, :160) while the shipped file spells the key
+    without it, so the threshold stays at its default 3 (aruco_slam.h:58) -- reproduced here."""
+    import os
+    import yaml
+    text = open(path_or_text).read() if os.path.exists(str(path_or_text)) else str(path_or_text)
+    tree = yaml.safe_load(text) or {}
+    d = _lib.SlamParams()
+    _lib.lib().b2a_default_slam_params(C.byref(d))
+    get = lambda sec, key, dflt: (tree.get(sec) or {}).get(key, dflt)
+    slam = dict(Q_k=float(get("covariance", "Q_k", d.Q_k)), R_x=float(get("covariance", "R_x", d.R_x)), R_y=float(get("covariance", "R_y", d.R_y)),
+                R_theta=float(get("covariance", "R_theta", d.R_theta)), kl=float(get("odom", "kl", d.kl)), kr=float(get("odom", "kr", d.kr)),
+                b=float(get("odom", "b", d.b)), useful_distance_threshold=float(get("const", "USEFUL_DISTANCE_THRESHOLD_", 3.0)))
+    return dict(slam=slam, markers_dictionary=int(get("aruco", "markers_dictionary", 16)), marker_length=float(get("aruco", "marker_length", 0.27)),
+                frames=dict(tree.get("frame") or {}), topics=dict(tree.get("topic") or {}))
+
+
+def load_camera(path_or_text):
+    """camera: {fx, fy, cx, cy, k1, k2, p1, p2, k3} (the reference's default.yaml:10-20) -> (K 3x3, D (k1, k2, p1, p2, k3)), the shapes
+    setCameraParameters takes (aruco_slam_node.cpp:121-130)"""
+    import os
+    import yaml
+    text = open(path_or_text).read() if os.path.exists(str(path_or_text)) else str(path_or_text)
+    cam = (yaml.safe_load(text) or {}).get("camera") or {}
+    K = np.array([[float(cam["fx"]), 0.0, float(cam["cx"])], [0.0, float(cam["fy"]), float(cam["cy"])], [0.0, 0.0, 1.0]])
+    D = np.array([float(cam.get(k, 0.0)) for k in ("k1", "k2", "p1", "p2", "k3")])
+    return K, D

@@ -94,3 +94,50 @@ def test_detected_marker_cubes_rotated_mount():
     assert np.allclose([ms[0].x, ms[0].y, ms[0].z], [-2.0 + 0.1, 1.0, 0.8], atol=1e-12)
     assert np.allclose(ms[0].q, (0, 0, s, s), atol=1e-12)
     assert formats.detected_markers([7], [[0.0, 0.0, 0.0]], [[0.0, 0.0, 3.5]], 0.27, 3.0) == []          # beyond the useful range
+
+
+PARAMETERS_YAML = """
+covariance:
+    Q_k: 0.01           ## Error coefficient of encoder
+    R_x: 100
+    R_y: 100
+    R_theta: 10
+odom:
+    kl: 0.05
+    kr: 0.05
+    b: 0.09
+aruco:
+    markers_dictionary: 16 ## cv::aruco::PREDEFINED_DICTIONARY_NAME
+    marker_length: 0.27
+frame:
+    world_frame: "world"
+    robot_frame_base: "base_link"
+const:
+    USEFUL_DISTANCE_THRESHOLD: 4
+"""
+
+
+def test_parameters_yaml_as_the_node_reads_it():
+    """parseArucoSlamIniteData (aruco_slam_node.cpp:146-164): the values of the shipped parameters.yaml, and the threshold key the
+    node misspells (so the file's 4 is never read and the default 3 stays)"""
+    import os
+    p = formats.load_parameters(PARAMETERS_YAML)
+    assert p["slam"] == dict(Q_k=0.01, R_x=100.0, R_y=100.0, R_theta=10.0, kl=0.05, kr=0.05, b=0.09, useful_distance_threshold=3.0)
+    assert p["markers_dictionary"] == 16 and p["marker_length"] == 0.27 and p["frames"]["robot_frame_base"] == "base_link"
+    assert formats.load_parameters("const:\n    USEFUL_DISTANCE_THRESHOLD_: 2.5\n")["slam"]["useful_distance_threshold"] == 2.5
+    assert formats.load_parameters("")["slam"]["R_x"] == 100.0 and formats.load_parameters("")["marker_length"] == 0.27      # defaults survive missing keys
+    ref = "/root/reference/parameters.yaml"
+    if os.path.exists(ref):                                    # authoring container only: the shipped file itself
+        q = formats.load_parameters(ref)
+        assert q["slam"] == p["slam"] and q["markers_dictionary"] == 16 and q["marker_length"] == 0.27
+        assert q["topics"] == {"image": "/camera/image_raw", "encoder": "/encoder"}
+
+
+def test_camera_yaml():
+    import os
+    K, D = formats.load_camera("camera:\n    fx: 525.5\n    fy: 524.5\n    cx: 472.0\n    cy: 264.0\n    k1: 0.04\n    k2: -0.05\n    p1: -0.003\n    p2: -0.004\n    k3: 0.01\n")
+    assert np.array_equal(K, [[525.5, 0, 472.0], [0, 524.5, 264.0], [0, 0, 1]]) and np.array_equal(D, [0.04, -0.05, -0.003, -0.004, 0.01])
+    ref = "/root/reference/default.yaml"
+    if os.path.exists(ref):
+        K, D = formats.load_camera(ref)
+        assert abs(K[0, 0] - 525.2866213437447) < 1e-12 and abs(K[1, 2] - 264.77181506420266) < 1e-12 and abs(D[4] - 0.01110263483766991) < 1e-15
