@@ -118,3 +118,14 @@ def test_interior_ranges_equal_the_per_group_test(emu):
     for W in list(range(1, 70)) + [639, 640, 641, 1919, 1920]:
         for H in (1, 2, 3, 4, 5, 9, 34, 479):
             assert f(W, H) == 1, (W, H)
+
+
+def test_plans_the_product_refuses(emu):
+    """aruco3_plan says no where cv2 would index past its pyramid (the level closest to the segmentation image does not exist) or
+    where the pyramid needs more than 12 images; the create / detect calls turn that into B2A_ERR_INVALID / B2A_ERR_UNSUPPORTED"""
+    dic = D.getPredefinedDictionary(0)
+    small = np.full((48, 64), 120, np.uint8)
+    assert emu.detect_aruco3(small, dic, 8, 2.0) is None               # segmentation image 4 x 3: its level 4 lies past a pyramid of 3 images
+    assert emu.detect_aruco3(small, dic, 8, 0.05) is not None
+    wide = np.full((4, 20000), 120, np.uint8)
+    assert emu.detect_aruco3(wide, dic, 1, 0.0) is not None            # log2(80000) / 2 = 8 levels: fine
