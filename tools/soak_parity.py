@@ -9,8 +9,12 @@
 
   product pose vs cv2       pose_core.h on the host (one lane) against cv2.solvePnP(ITERATIVE) on random marker poses seen by the C2 camera
                            and by the reference's default.yaml camera, integer corners as the detector delivers them: 1e-4 rad / 1e-4 m
+  oracle EKF vs the reference  oracle/_ref (the reference's own aruco_slam.cpp, compiled unmodified) against orc_ekf.c / orc_pose.c on random
+                           sequences: random noise parameters and robot-to-camera offsets, 1-3 encoder messages per frame, 0-8
+                           detections per frame with duplicate ids, out-of-range and noisy markers: state dimension, mapped ids,
+                           mu and Sigma to 1e-9 after every frame
 
-Usage: python tools/soak_parity.py [n_cv2=300] [n_emu=160]       (last run: 300 + 160 + 345 cases, 0 mismatches, worst refined corner 6e-5 px, worst pose 8e-9 rad / 9e-9 m)
+Usage: python tools/soak_parity.py [n_cv2=300] [n_emu=160]       (last run: 300 + 160 + 345 cases and 120 sequences, 0 mismatches, worst refined corner 6e-5 px, worst pose 8e-9 rad / 9e-9 m)
 """
 import os
 import sys
@@ -132,11 +136,74 @@ def soak_pose(n):
     return bad
 
 
+def soak_ekf(n_seq):
+    from oracle import ref
+    if not ref.available():
+        print("oracle/_ref not built: EKF leg skipped")
+        return 0
+    ref.use_orc_hooks()
+    K = np.array([[900.0, 0, 480], [0, 900.0, 270], [0, 0, 1]])
+    D = np.array([-0.05, 0.02, 0.001, -0.001, 0.0])
+    L = 0.2
+    h = L / 2
+    obj = np.array([[-h, h, 0], [h, h, 0], [h, -h, 0], [-h, -h, 0]])
+    img = np.zeros((8, 8), np.uint8)
+    bad = 0
+    worst = 0.0
+    for seed in range(n_seq):
+        rng = np.random.default_rng(seed)
+        Rx, Ry, Rt = [float(v) for v in rng.choice([0.05, 0.2, 1.0], 3)]
+        r2c = (float(rng.uniform(-0.2, 0.2)), float(rng.uniform(-0.1, 0.1)), 0.3)
+        r = ref.RefSlam(R_x=Rx, R_y=Ry, R_theta=Rt, marker_length=L, r2c_t=r2c)
+        r.set_camera(K, D)
+        sp = oracle.slam_params(r2c_tx=r2c[0], r2c_ty=r2c[1], marker_length=L, R_x=Rx, R_y=Ry, R_theta=Rt, useful_distance_threshold=3.0)
+        e = oracle.Ekf(sp)
+        t = 0.0
+        r.add_encoder(1.0, 1.0, t)
+        verdict = None
+        for f in range(25):
+            for _ in range(int(rng.integers(1, 4))):
+                wl, wr, dt = float(rng.uniform(-3, 3)), float(rng.uniform(-3, 3)), float(rng.uniform(0.01, 0.1))
+                t += dt
+                r.add_encoder(wl, wr, t)
+                e.predict(wl, wr, dt)
+            m = int(rng.integers(0, 9))
+            ids = rng.choice(14, m, replace=bool(rng.random() < 0.2)).astype(np.int32) if m else np.zeros(0, np.int32)
+            rv = rng.normal(0, 0.4, (m, 3))
+            rv[:, 0] += np.pi
+            tv = np.c_[rng.uniform(-1.5, 1.5, m), rng.uniform(-0.5, 0.5, m), rng.uniform(0.6, 5.0, m)]
+            corners = np.zeros((m, 4, 2), np.float32)
+            for i in range(m):
+                corners[i] = np.rint(oracle.project_points(obj, rv[i], tv[i], K, D) + rng.normal(0, float(rng.choice([0.1, 0.5, 2.0])), (4, 2)))
+            ref.set_replay(corners, ids, rv, tv)
+            r.add_image(img)
+            e.update(oracle.make_observations(corners, ids, rv, tv, K, D, sp))
+            mu, sg, lid = r.get_state()
+            mu2, sg2, lid2 = e.get_state()
+            # the reference's id list comes from its id -> index map: a slot a duplicate new id left unmapped reads -1 (or is cut off at the end)
+            if len(mu) != len(mu2) or not all(a == b or a == -1 for a, b in zip(lid, lid2)):
+                verdict = ("layout differs", f)
+                break
+            d = max(float(np.abs(mu - mu2).max()), float(np.abs(sg - sg2).max()))
+            worst = max(worst, d)
+            if not np.isfinite(d) or d > 1e-9 * max(1.0, float(np.abs(sg).max())):
+                verdict = ("state differs", f, d)
+                break
+        ref.set_replay()
+        r.close()
+        if verdict:
+            bad += 1
+            print("MISMATCH oracle EKF vs reference: sequence", seed, verdict)
+    print("oracle EKF vs the reference build: %d sequences of 25 frames, %d mismatches, worst |d mu|, |d Sigma| %.1e" % (n_seq, bad, worst))
+    return bad
+
+
 if __name__ == "__main__":
     t0 = time.time()
     n_cv2 = int(sys.argv[1]) if len(sys.argv) > 1 else 300
     n_emu = int(sys.argv[2]) if len(sys.argv) > 2 else 160
     bad = soak_emu(n_emu)
+    bad += soak_ekf(120)
     try:
         import cv2  # noqa: F401
         bad += soak_cv2(n_cv2)
