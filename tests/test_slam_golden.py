@@ -235,3 +235,18 @@ def test_ref_build_reproduces_goldens(oracle):
         assert np.abs(mu - g["mu_%d" % f]).max() < 1e-9 and np.abs(sg - g["sigma_%d" % f]).max() < 1e-9
     ref.set_replay()
     r.close()
+
+
+def test_oracle_ekf_equals_reference_build_on_random_sequences():
+    """beyond the fixed fixtures: random noise parameters, offsets, encoder messages and detections (duplicate ids in a frame,
+    out-of-range and noisy markers) through oracle/_ref (the reference compiled unmodified) and through orc_pose.c / orc_ekf.c --
+    the leg of tools/soak_parity.py, 12 sequences of 25 frames here"""
+    import importlib.util
+    import os
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref is not built and /root/reference is absent")
+    spec = importlib.util.spec_from_file_location("soak_parity", os.path.join(os.path.dirname(__file__), "..", "tools", "soak_parity.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.soak_ekf(12) == 0
